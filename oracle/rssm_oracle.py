@@ -1,0 +1,356 @@
+"""CPU oracle for the RSSM hot path (TEST INFRASTRUCTURE — never the product path).
+
+This file restates, in plain functional torch-on-CPU code with *explicit* noise
+arguments, the algorithm of the reference's RSSM recurrence and the reductions
+hanging off it.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+`cpu_baseline` / `--impl reference` legs may import it.  `repo_b200/` must not.
+
+Parity status: PINNED against the live reference.  The reference ships no tests
+or golden vectors for this path, so `oracle/make_golden.py`
+imports the unmodified reference modules from /root/reference in the build
+container, injects fixed noise (patching `torch.randn_like` and
+`torch.distributions.normal._standard_normal`), and commits the input seeds +
+outputs under `tests/golden/`.  `tests/test_oracle_golden.py` checks every
+function here against those fixtures (bit-exact or <=1e-6 in fp32).
+
+The arithmetic itself lives in a third-party dependency of the reference:
+torch==1.12.1 (requirements.txt:18; installed here: torch 2.11).  Formulas
+restated from its published semantics: `nn.Linear` (y = x W^T + b),
+`nn.GRUCell` (gate order r,z,n; n = tanh(W_in x + b_in + r*(W_hn h + b_hn));
+h' = (1-z)*n + z*h), `F.elu`, `F.softplus` (threshold 20),
+`kl_divergence(Normal, Normal)`, `Normal.log_prob`.
+
+Reference citations (relative to /root/reference):
+  compute_belief            algorithms/repo/models/rssm.py:34-40
+  compute_prior_state       algorithms/repo/models/rssm.py:42-50
+  compute_posterior_state   algorithms/repo/models/rssm.py:52-64
+  observe                   algorithms/repo/models/rssm.py:76-146
+  imagine                   algorithms/repo/models/rssm.py:148-184
+  ActorModel                algorithms/repo/models/actor_critic.py:50-102
+  ValueModel / RewardModel  actor_critic.py:9-26 / decoder.py:178-195
+  TanhBijector / SampleDist algorithms/repo/models/utils.py:112-163
+  lambda_return             common/utils.py:61-71
+  KL terms                  algorithms/repo/repo.py:63-83, dreamer.py:278-282
+  replay index math         common/buffers.py:156-166
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+
+# ----------------------------------------------------------------------------
+# deterministic, portable parameter / input generation (numpy RandomState so the
+# same bytes are produced in the build container and on the GPU box)
+# ----------------------------------------------------------------------------
+
+DEFAULT_DIMS = dict(belief=200, state=30, action=6, hidden=200, embed=1024)
+
+
+def _uniform(rs: np.random.RandomState, shape, bound) -> torch.Tensor:
+    return torch.from_numpy(rs.uniform(-bound, bound, size=shape).astype(np.float32))
+
+
+def make_transition_params(seed: int, dims=DEFAULT_DIMS, scale: float = 1.0) -> Params:
+    """Same key names/shapes as TransitionModel.state_dict() (rssm.py:9-32).
+
+    Values follow torch's default init *distribution* (U(+-1/sqrt(fan_in))) but are
+    drawn from numpy so fixtures are reproducible anywhere. `scale` > 1 makes the
+    recurrence livelier (stresses numerics more than a fresh init does)."""
+    rs = np.random.RandomState(seed)
+    D, S, A, H, E = dims["belief"], dims["state"], dims["action"], dims["hidden"], dims["embed"]
+    p: Params = {}
+
+    def lin(name, out_f, in_f):
+        b = scale / math.sqrt(in_f)
+        p[name + ".weight"] = _uniform(rs, (out_f, in_f), b)
+        p[name + ".bias"] = _uniform(rs, (out_f,), b)
+
+    lin("fc_embed_state_action", D, S + A)
+    b = scale / math.sqrt(D)
+    p["rnn.weight_ih"] = _uniform(rs, (3 * D, D), b)
+    p["rnn.weight_hh"] = _uniform(rs, (3 * D, D), b)
+    p["rnn.bias_ih"] = _uniform(rs, (3 * D,), b)
+    p["rnn.bias_hh"] = _uniform(rs, (3 * D,), b)
+    lin("fc_embed_belief_prior", H, D)
+    lin("fc_state_prior", 2 * S, H)
+    lin("fc_embed_belief_posterior", H, D + E)
+    lin("fc_state_posterior", 2 * S, H)
+    return p
+
+
+def make_mlp_params(seed: int, in_f: int, hidden: int, out_f: int, n_hidden: int, scale: float = 1.0) -> Params:
+    """fc1..fc{n_hidden+1}: in_f -> hidden x n_hidden -> out_f  (ActorModel n_hidden=4,
+    out=2A; RewardModel/ValueModel n_hidden=3, out=1)."""
+    rs = np.random.RandomState(seed)
+    p: Params = {}
+    sizes = [in_f] + [hidden] * n_hidden + [out_f]
+    for i in range(len(sizes) - 1):
+        b = scale / math.sqrt(sizes[i])
+        p[f"fc{i + 1}.weight"] = _uniform(rs, (sizes[i + 1], sizes[i]), b)
+        p[f"fc{i + 1}.bias"] = _uniform(rs, (sizes[i + 1],), b)
+    return p
+
+
+def cast_params(p: Params, dtype) -> Params:
+    return {k: v.to(dtype) for k, v in p.items()}
+
+
+# ----------------------------------------------------------------------------
+# optional emulation of the device arithmetic (fp16 hi/lo split, 3 products, fp32
+# accumulate) — used by tests to predict how far the CUDA path may sit from fp32
+# ----------------------------------------------------------------------------
+
+class Precision:
+    """`exact`: plain matmul in the tensor dtype.  `f16x3`: each operand is split
+    x = hi + lo (both fp16, lo subnormal-safe); the product keeps hi*hi + lo*hi +
+    hi*lo, accumulated in fp32 — what the tcgen05 kernels do."""
+
+    def __init__(self, mode: str = "exact"):
+        assert mode in ("exact", "f16x3", "bf16x3", "f16", "bf16")
+        self.mode = mode
+
+    def _split(self, x, dt):
+        hi = x.to(dt).to(torch.float32)
+        lo = (x - hi).to(dt).to(torch.float32)
+        return hi, lo
+
+    def linear(self, x, w, b):
+        if self.mode == "exact":
+            return F.linear(x, w, b)
+        dt = torch.float16 if self.mode.startswith("f16") else torch.bfloat16
+        x32, w32 = x.float(), w.float()
+        xh, xl = self._split(x32, dt)
+        wh, wl = self._split(w32, dt)
+        if self.mode in ("f16", "bf16"):
+            y = xh.double() @ wh.double().t()
+        else:
+            y = xh.double() @ wh.double().t() + xl.double() @ wh.double().t() + xh.double() @ wl.double().t()
+        y = y.float()
+        return (y + b.float()).to(x.dtype) if b is not None else y.to(x.dtype)
+
+
+EXACT = Precision("exact")
+
+# ----------------------------------------------------------------------------
+# cell-level functions
+# ----------------------------------------------------------------------------
+
+def _act(name: str):
+    return getattr(F, name)
+
+
+def compute_belief(p: Params, prev_belief, state, action, act="elu", prec: Precision = EXACT):
+    """rssm.py:34-40 — h = act(W_sa [s|a] + b); belief' = GRUCell(h, belief)."""
+    x = torch.cat([state, action], dim=1)
+    hid = _act(act)(prec.linear(x, p["fc_embed_state_action.weight"], p["fc_embed_state_action.bias"]))
+    gi = prec.linear(hid, p["rnn.weight_ih"], p["rnn.bias_ih"])
+    gh = prec.linear(prev_belief, p["rnn.weight_hh"], p["rnn.bias_hh"])
+    i_r, i_z, i_n = gi.chunk(3, dim=1)
+    h_r, h_z, h_n = gh.chunk(3, dim=1)
+    r = torch.sigmoid(i_r + h_r)
+    z = torch.sigmoid(i_z + h_z)
+    n = torch.tanh(i_n + r * h_n)
+    return (1.0 - z) * n + z * prev_belief
+
+
+def _gaussian_head(p: Params, pre: str, out: str, x, eps, act, min_std, prec):
+    hid = _act(act)(prec.linear(x, p[pre + ".weight"], p[pre + ".bias"]))
+    o = prec.linear(hid, p[out + ".weight"], p[out + ".bias"])
+    mean, raw = o.chunk(2, dim=1)  # mean first, raw std second (rssm.py:45-47)
+    std = F.softplus(raw) + min_std
+    return mean + std * eps, mean, std
+
+
+def compute_prior_state(p: Params, belief, eps, act="elu", min_std=0.1, prec: Precision = EXACT):
+    """rssm.py:42-50."""
+    return _gaussian_head(p, "fc_embed_belief_prior", "fc_state_prior", belief, eps, act, min_std, prec)
+
+
+def compute_posterior_state(p: Params, belief, embed, eps, act="elu", min_std=0.1, prec: Precision = EXACT):
+    """rssm.py:52-64."""
+    x = torch.cat([belief, embed], dim=1)
+    return _gaussian_head(p, "fc_embed_belief_posterior", "fc_state_posterior", x, eps, act, min_std, prec)
+
+
+# ----------------------------------------------------------------------------
+# observe / imagine
+# ----------------------------------------------------------------------------
+
+def observe(p: Params, prev_belief, prev_state, actions, embeds: Optional[torch.Tensor],
+            nonterms: Optional[torch.Tensor], eps_prior, eps_post: Optional[torch.Tensor],
+            act="elu", min_std=0.1, prec: Precision = EXACT):
+    """rssm.py:76-146.  actions (T1,B,A); embeds (T1,B,E) already shifted by the caller;
+    nonterms (T1,B,1); eps_* (T1,B,S) in the reference's RNG draw order (prior first,
+    posterior second, every step).  Returns the reference's list of 7 (or 4) tensors."""
+    T1 = actions.shape[0]
+    belief, state = prev_belief, prev_state
+    outs = [[] for _ in range(7)]
+    for t in range(T1):
+        s_in = state if nonterms is None else state * nonterms[t]  # only the state is masked (rssm.py:118-119)
+        belief = compute_belief(p, belief, s_in, actions[t], act, prec)
+        ps, pm, pd = compute_prior_state(p, belief, eps_prior[t], act, min_std, prec)
+        outs[0].append(belief); outs[1].append(ps); outs[2].append(pm); outs[3].append(pd)
+        if embeds is not None:
+            qs, qm, qd = compute_posterior_state(p, belief, embeds[t], eps_post[t], act, min_std, prec)
+            outs[4].append(qs); outs[5].append(qm); outs[6].append(qd)
+            state = qs
+        else:
+            state = ps
+    n = 7 if embeds is not None else 4
+    return [torch.stack(o, 0) for o in outs[:n]]
+
+
+def mlp(p: Params, x, n_layers: int, act="elu", prec: Precision = EXACT):
+    for i in range(1, n_layers):
+        x = _act(act)(prec.linear(x, p[f"fc{i}.weight"], p[f"fc{i}.bias"]))
+    return prec.linear(x, p[f"fc{n_layers}.weight"], p[f"fc{n_layers}.bias"])
+
+
+def actor_forward(ap: Params, belief, state, mean_scale=5.0, init_std=0.0, min_std=0.1, prec: Precision = EXACT):
+    """actor_critic.py:76-87 — hidden activation is always ELU."""
+    o = mlp(ap, torch.cat([belief, state], 1), 5, "elu", prec)
+    m, s = o.chunk(2, dim=1)
+    mean = mean_scale * torch.tanh(m / mean_scale)
+    std = F.softplus(s + init_std) + min_std
+    return mean, std
+
+
+def head_forward(hp: Params, belief, state, act="elu", prec: Precision = EXACT):
+    """RewardModel/ValueModel forward (decoder.py:189-195, actor_critic.py:20-26)."""
+    return mlp(hp, torch.cat([belief, state], 1), 4, act, prec).squeeze(1)
+
+
+def imagine(p: Params, ap: Params, prev_belief, prev_state, eps_action, eps_prior, horizon: int,
+            act="elu", min_std=0.1, prec: Precision = EXACT):
+    """rssm.py:148-184 with ActorModel.get_action = tanh(mean + std*eps) (actor_critic.py:97-102).
+    eps_action (H-1,N,A), eps_prior (H-1,N,S).  Returns [beliefs, prior_states, prior_means,
+    prior_std_devs] each with H-1 leading entries (start row excluded) plus the actions taken."""
+    belief, state = prev_belief, prev_state
+    outs = [[] for _ in range(5)]
+    for t in range(horizon - 1):
+        mean, std = actor_forward(ap, belief, state, prec=prec)
+        action = torch.tanh(mean + std * eps_action[t])
+        belief = compute_belief(p, belief, state, action, act, prec)
+        state, pm, pd = compute_prior_state(p, belief, eps_prior[t], act, min_std, prec)
+        for o, v in zip(outs, (belief, state, pm, pd, action)):
+            o.append(v)
+    return [torch.stack(o, 0) for o in outs]
+
+
+# ----------------------------------------------------------------------------
+# reductions hanging off the recurrence
+# ----------------------------------------------------------------------------
+
+def lambda_return(rewards, values, discounts, bootstrap, lambda_=0.95):
+    """common/utils.py:61-71."""
+    next_values = torch.cat([values[1:], bootstrap[None]], 0)
+    inputs = rewards + discounts * next_values * (1 - lambda_)
+    last = bootstrap
+    out = [None] * inputs.shape[0]
+    for t in range(inputs.shape[0] - 1, -1, -1):
+        last = inputs[t] + discounts[t] * lambda_ * last
+        out[t] = last
+    return torch.stack(out, 0)
+
+
+def imagine_returns(reward_preds, value_preds, gamma=0.99, lambda_=0.95):
+    """dreamer.py:341-349 — H-2 rows, bootstrap = value_preds[-1]."""
+    disc = gamma * torch.ones_like(reward_preds)
+    return lambda_return(reward_preds[:-1], value_preds[:-1], disc[:-1], value_preds[-1], lambda_)
+
+
+def kl_normal(mp, sp, mq, sq):
+    """KL(N(mp,sp) || N(mq,sq)) elementwise (torch/distributions/kl.py _kl_normal_normal)."""
+    var_ratio = (sp / sq) ** 2
+    t1 = ((mp - mq) / sq) ** 2
+    return 0.5 * (var_ratio + t1 - 1 - var_ratio.log())
+
+
+def kl_sum(post_mean, post_std, prior_mean, prior_std):
+    """KL(post||prior).sum over the state dim -> (T1,B)."""
+    return kl_normal(post_mean, post_std, prior_mean, prior_std).sum(2)
+
+
+def dreamer_kl_loss(kl_tb, free_nats=3.0):
+    """dreamer.py:278-282 — max(kl, free_nats) per (t,b), then mean."""
+    return torch.clamp(kl_tb, min=free_nats).mean()
+
+
+def repo_kl_terms(kl_tb, log_beta, prior_train_steps=5, target_kl=3.0):
+    """repo.py:63-96 forward values: kl_div, kl_viol, kl_loss, beta_loss."""
+    kl_mean = kl_tb.mean()
+    alpha = prior_train_steps / (1 + prior_train_steps)
+    kl_div = alpha * kl_mean + (1 - alpha) * kl_mean
+    kl_viol = kl_div - target_kl
+    kl_loss = math.exp(log_beta) * kl_viol
+    beta_loss = -log_beta * kl_viol
+    return kl_div, kl_viol, kl_loss, beta_loss
+
+
+def tanh_normal_entropy(mean, std, eps):
+    """SampleDist.entropy over Independent(Transformed(Normal, TanhBijector),1)
+    (models/utils.py:112-163). eps (K,M,A) standard-normal draws. Returns (M,)."""
+    x = mean[None] + std[None] * eps
+    y = torch.tanh(x)
+    yc = torch.where(y.abs() <= 1.0, torch.clamp(y, -0.99999997, 0.99999997), y)
+    xi = torch.atanh(yc)
+    var = std[None] ** 2
+    base_lp = -((xi - mean[None]) ** 2) / (2 * var) - std[None].log() - math.log(math.sqrt(2 * math.pi))
+    ladj = 2.0 * (math.log(2.0) - xi - F.softplus(-2.0 * xi))
+    lp = (base_lp - ladj).sum(-1)
+    return -lp.mean(0)
+
+
+# ----------------------------------------------------------------------------
+# sequence bookkeeping (bit-exact integer work)
+# ----------------------------------------------------------------------------
+
+def replay_indices(start_inds: np.ndarray, seq_len: int, pos: int, full: bool, length: int) -> np.ndarray:
+    """common/buffers.py:156-166 after `np.random.choice` — time-major flat indices."""
+    inds = np.stack([np.arange(s, s + seq_len) for s in start_inds], 0)
+    inds = inds.transpose().reshape(-1)
+    if full:
+        inds = (inds + pos) % length
+    return inds
+
+
+def shift_for_observe(actions, embeds, nonterms):
+    """dreamer.py:253-258 — the caller-side time shift paired with observe()."""
+    return actions[:-1], embeds[1:], nonterms[:-1]
+
+
+# ----------------------------------------------------------------------------
+# synthetic inputs of the DMC shape
+# ----------------------------------------------------------------------------
+
+def make_observe_inputs(seed: int, T: int, B: int, dims=DEFAULT_DIMS, p_done=1 / 500.0, embed_scale=1.0):
+    rs = np.random.RandomState(seed)
+    D, S, A, E = dims["belief"], dims["state"], dims["action"], dims["embed"]
+    T1 = T - 1
+    f = lambda a: torch.from_numpy(a.astype(np.float32))
+    return dict(
+        prev_belief=torch.zeros(B, D), prev_state=torch.zeros(B, S),
+        actions=f(rs.uniform(-1, 1, (T1, B, A))),
+        embeds=f(rs.standard_normal((T1, B, E)) * embed_scale),
+        nonterms=f((rs.uniform(0, 1, (T1, B, 1)) >= p_done)),
+        eps_prior=f(rs.standard_normal((T1, B, S))),
+        eps_post=f(rs.standard_normal((T1, B, S))),
+    )
+
+
+def make_imagine_inputs(seed: int, N: int, horizon: int, dims=DEFAULT_DIMS):
+    rs = np.random.RandomState(seed)
+    D, S, A = dims["belief"], dims["state"], dims["action"]
+    f = lambda a: torch.from_numpy(a.astype(np.float32))
+    return dict(
+        belief=f(np.clip(rs.standard_normal((N, D)) * 0.3, -1, 1)),
+        state=f(rs.standard_normal((N, S))),
+        eps_action=f(rs.standard_normal((horizon - 1, N, A))),
+        eps_prior=f(rs.standard_normal((horizon - 1, N, S))),
+    )

@@ -1,0 +1,106 @@
+"""CPU: the oracle (oracle/rssm_oracle.py) against fixtures produced by the live reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rssm_oracle as O
+from tests import _cases as C
+
+torch.set_num_threads(1)
+
+
+@pytest.mark.parametrize("name", C.OBSERVE_CASES)
+def test_observe_matches_reference(name):
+    params, x, gold, meta = C.observe_case(name)
+    outs = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"],
+                     x["eps_prior"], x["eps_post"])
+    assert len(outs) == (7 if meta["use_obs"] else 4)
+    keep = int(meta["keep"])
+    for nm, o in zip(C.OBS_NAMES, outs):
+        assert o.shape[0] == meta["T"] - 1  # T-1 steps, init sliced off (rssm.py:135)
+        got = o if keep == 0 else o[-keep:]
+        np.testing.assert_allclose(got.numpy(), gold[nm], rtol=2e-5, atol=2e-6, err_msg=nm)
+    if meta["use_obs"]:
+        kl = O.kl_sum(outs[5], outs[6], outs[2], outs[3])
+        np.testing.assert_allclose(kl.numpy(), gold["kl_tb"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(O.dreamer_kl_loss(kl).item(), gold["kl_dreamer"], rtol=1e-5)
+        kl_div, kl_viol, kl_loss, beta_loss = O.repo_kl_terms(kl, np.log(1e-5))
+        np.testing.assert_allclose(kl_div.item(), gold["kl_mean"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", C.IMAGINE_CASES)
+def test_imagine_matches_reference(name):
+    params, actor, reward, value, x, gold, meta = C.imagine_case(name)
+    H = int(meta["H"])
+    outs = O.imagine(params, actor, x["belief"], x["state"], x["eps_action"], x["eps_prior"], H)
+    for nm, o in zip(C.IMG_NAMES, outs):
+        assert o.shape[0] == H - 1  # start row excluded (rssm.py:178-183)
+        np.testing.assert_allclose(o.numpy(), gold[nm], rtol=2e-5, atol=2e-6, err_msg=nm)
+    T1, N = outs[0].shape[:2]
+    rew = O.head_forward(reward, outs[0].flatten(0, 1), outs[1].flatten(0, 1)).reshape(T1, N)
+    val = O.head_forward(value, outs[0].flatten(0, 1), outs[1].flatten(0, 1)).reshape(T1, N)
+    np.testing.assert_allclose(rew.numpy(), gold["rewards"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(val.numpy(), gold["values"], rtol=2e-5, atol=2e-6)
+    ret = O.imagine_returns(rew, val, 0.99, 0.95)
+    assert ret.shape[0] == H - 2  # dreamer.py:343-349
+    np.testing.assert_allclose(ret.numpy(), gold["returns"], rtol=2e-5, atol=2e-6)
+
+
+def test_lambda_return_known_answer():
+    g, _ = C.load("lambda_return")
+    # hand computation of the 3-step toy: gamma=0.9, lambda=0.8, bootstrap 4
+    r, v, boot = [1.0, 2.0, 3.0], [0.5, 0.25, 0.125], 4.0
+    nxt = v[1:] + [boot]
+    inp = [r[i] + 0.9 * nxt[i] * (1 - 0.8) for i in range(3)]
+    last, hand = boot, [0.0] * 3
+    for i in (2, 1, 0):
+        last = inp[i] + 0.9 * 0.8 * last
+        hand[i] = last
+    np.testing.assert_allclose(g["toy_out"].ravel(), hand, rtol=1e-6)
+    out = O.lambda_return(C.t(g["toy_r"]), C.t(g["toy_v"]), 0.9 * torch.ones(3, 1), C.t(g["toy_boot"]), 0.8)
+    np.testing.assert_array_equal(out.numpy(), g["toy_out"])
+    out2 = O.lambda_return(C.t(g["r"]), C.t(g["v"]), 0.99 * torch.ones(13, 37), C.t(g["boot"]), 0.95)
+    np.testing.assert_array_equal(out2.numpy(), g["out"])
+
+
+def test_kl_closed_form():
+    mp, sp, mq, sq = torch.tensor(0.3), torch.tensor(0.7), torch.tensor(-0.2), torch.tensor(1.3)
+    want = np.log(1.3 / 0.7) + (0.7 ** 2 + 0.5 ** 2) / (2 * 1.3 ** 2) - 0.5
+    np.testing.assert_allclose(O.kl_normal(mp, sp, mq, sq).item(), want, rtol=1e-6)
+    ref = torch.distributions.kl_divergence(torch.distributions.Normal(mp, sp), torch.distributions.Normal(mq, sq))
+    np.testing.assert_allclose(O.kl_normal(mp, sp, mq, sq).item(), ref.item(), rtol=1e-6)
+
+
+def test_tanh_normal_entropy_matches_reference():
+    g, _ = C.load("entropy_M50_A6_K100")
+    ent = O.tanh_normal_entropy(C.t(g["mean"]), C.t(g["std"]), C.t(g["eps"]))
+    np.testing.assert_allclose(ent.numpy(), g["entropy"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("tag", ["partial", "full", "fullwrap"])
+def test_replay_indices_bit_exact(tag):
+    g, _ = C.load("replay_indices")
+    cap, n_push, B, L, pos, full, length = [int(v) for v in g[f"{tag}_meta"]]
+    inds = O.replay_indices(g[f"{tag}_starts"], L, pos, bool(full), length)
+    assert inds.shape == (L * B,)
+    # rebuild the ring buffer contents the generator pushed: slot i%cap holds push index i
+    owner = np.full(cap, -1, dtype=np.int64)
+    for i in range(n_push):
+        owner[i % cap] = i
+    src = owner[inds].reshape(L, B)
+    np.testing.assert_array_equal(g[f"{tag}_obs"][..., 0], src.astype(np.float32))
+    np.testing.assert_array_equal(g[f"{tag}_rew"][..., 0], src.astype(np.float32))
+    np.testing.assert_array_equal(g[f"{tag}_done"][..., 0], (src % 11 == 0).astype(np.float32))
+    # sequences are contiguous in push order (never straddle the write head)
+    assert (np.diff(src, axis=0) == 1).all()
+
+
+def test_f16x3_emulation_is_within_tolerance():
+    """The split-fp16 arithmetic the tcgen05 kernels use must sit well inside rtol 1e-3."""
+    params, x, gold, meta = C.observe_case("observe_T8_B10_hot")
+    exact = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"],
+                      x["eps_prior"], x["eps_post"])
+    emu = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"],
+                    x["eps_prior"], x["eps_post"], prec=O.Precision("f16x3"))
+    for a, b in zip(exact, emu):
+        np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=1e-4, atol=1e-5)
