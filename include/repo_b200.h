@@ -1,0 +1,104 @@
+/* repo_b200 — C-ABI of the B200-native RSSM hot path (librepo_b200.so).
+ *
+ * The reference (zchuning/repo) has no FFI for this path: the boundary it exposes is the Python
+ * class algorithms/repo/models/rssm.py::TransitionModel (rssm.py:8-184) plus the helpers it
+ * calls (ActorModel actor_critic.py:50-102, RewardModel decoder.py:178-195, ValueModel
+ * actor_critic.py:9-26, lambda_return common/utils.py:61-71, the KL of repo.py:63-83).  Each
+ * entry point below names the reference symbol whose arithmetic it replaces.  The Python side
+ * (repo_b200/rssm.py) binds these with ctypes and keeps the reference's module interface.
+ *
+ * Conventions: every pointer is a DEVICE pointer to contiguous fp32, row-major, time-major
+ * (T, rows, feature) memory owned by the caller; `stream` is a cudaStream_t; no call
+ * synchronises or allocates; the caller provides the workspace (size from *_workspace_bytes).
+ * Return 0 on success, negative on error; repo_b200_last_error() gives the message
+ * (thread-local).  There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef REPO_B200_H
+#define REPO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REPO_B200_ACT_RELU 0
+#define REPO_B200_ACT_ELU 1
+
+/* flags */
+#define REPO_B200_WEIGHTS_PACKED 1 /* workspace already holds the packed weights of these exact tensors */
+
+typedef struct repo_b200_dims {
+  int belief, state, action, hidden, embed; /* TransitionModel ctor sizes, rssm.py:9-18 */
+} repo_b200_dims;
+
+/* TransitionModel.state_dict() (rssm.py:21-32): nn.Linear weights are [out, in]; nn.GRUCell gate
+ * order r,z,n. */
+typedef struct repo_b200_rssm_weights {
+  const float *fc_embed_state_action_w, *fc_embed_state_action_b;         /* (D, S+A), (D)   */
+  const float *rnn_w_ih, *rnn_w_hh, *rnn_b_ih, *rnn_b_hh;                 /* (3D, D) x2, (3D) x2 */
+  const float *fc_embed_belief_prior_w, *fc_embed_belief_prior_b;         /* (H, D), (H)     */
+  const float *fc_state_prior_w, *fc_state_prior_b;                       /* (2S, H), (2S)   */
+  const float *fc_embed_belief_posterior_w, *fc_embed_belief_posterior_b; /* (H, D+E), (H)   */
+  const float *fc_state_posterior_w, *fc_state_posterior_b;               /* (2S, H), (2S)   */
+} repo_b200_rssm_weights;
+
+/* fc1..fcN of ActorModel (N=5, out 2A), RewardModel / ValueModel (N=4, out 1); input = [belief|state]. */
+typedef struct repo_b200_mlp_weights {
+  const float* w[5];
+  const float* b[5];
+  int n_layers;
+} repo_b200_mlp_weights;
+
+int repo_b200_version(void);
+const char* repo_b200_last_error(void);
+/* number of SMs / compute capability of the current device; <0 if no device */
+int repo_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* bring-up only: bit0 swaps LBO/SBO in the tcgen05 shared-memory descriptors */
+void repo_b200_debug_flags(int flags);
+
+/* ---- imagine: TransitionModel.imagine (rssm.py:148-184) with policy = ActorModel.get_action
+ * (actor_critic.py:97-102), fused with RewardModel / ValueModel on every imagined state
+ * (dreamer.py:315-317) and lambda_return (common/utils.py:61-71 as called at dreamer.py:342-349).
+ *   start_belief (N,D), start_state (N,S); eps_action (H-1,N,A), eps_prior (H-1,N,S) standard normal;
+ *   outputs beliefs (H-1,N,D), prior_* (H-1,N,S), actions (H-1,N,A, nullable), rewards/values (H-1,N),
+ *   returns (H-2,N).  reward/value may be NULL (then rewards/values/returns are not written).
+ *   row_tile: 0 = auto, else 16/32/64 rows per CTA. */
+size_t repo_b200_imagine_workspace_bytes(const repo_b200_dims* dims);
+int repo_b200_imagine_fwd(const repo_b200_dims* dims, const repo_b200_rssm_weights* rssm,
+                          const repo_b200_mlp_weights* actor, const repo_b200_mlp_weights* reward,
+                          const repo_b200_mlp_weights* value, const float* start_belief, const float* start_state,
+                          const float* eps_action, const float* eps_prior, float* beliefs, float* prior_states,
+                          float* prior_means, float* prior_std_devs, float* actions, float* rewards, float* values,
+                          float* returns, int horizon, int n_rows, int act_kind, float min_std_dev,
+                          float actor_mean_scale, float actor_init_std, float actor_min_std, float gamma,
+                          float lambda_, void* workspace, size_t workspace_bytes, int flags, int row_tile,
+                          void* stream);
+
+/* ---- observe: TransitionModel.observe (rssm.py:76-146) fused with the per-(t,b) Gaussian KL
+ * KL(posterior || prior).sum(state) used by dreamer.py:278-282 / repo.py:63-83.
+ *   prev_belief (B,D), prev_state (B,S), actions (T1,B,A), embeds (T1,B,E) or NULL (prior-only
+ *   rollout), nonterminals (T1,B) or NULL, eps_prior/eps_post (T1,B,S).
+ *   outputs: beliefs (T1,B,D), prior_states/means/std_devs, posterior_states/means/std_devs
+ *   (T1,B,S) (posterior_* ignored when embeds == NULL), kl (T1,B) nullable. */
+size_t repo_b200_observe_workspace_bytes(const repo_b200_dims* dims, int t1, int batch);
+int repo_b200_observe_fwd(const repo_b200_dims* dims, const repo_b200_rssm_weights* rssm, const float* prev_belief,
+                          const float* prev_state, const float* actions, const float* embeds,
+                          const float* nonterminals, const float* eps_prior, const float* eps_post, float* beliefs,
+                          float* prior_states, float* prior_means, float* prior_std_devs, float* posterior_states,
+                          float* posterior_means, float* posterior_std_devs, float* kl, int t1, int batch,
+                          int act_kind, float min_std_dev, void* workspace, size_t workspace_bytes, int flags,
+                          int row_tile, void* stream);
+
+/* ---- linear: y = x W^T + b on the same machine (nn.Linear as used by rssm.py:23-32); building block
+ * and bring-up test.  x (rows, in_f) ld = x_ld; w (out_f, in_f); b (out_f) nullable; y ld = y_ld. */
+size_t repo_b200_linear_workspace_bytes(int in_features, int out_features);
+int repo_b200_linear_fwd(const float* x, int x_ld, int rows, int in_features, const float* w, const float* b,
+                         int out_features, float* y, int y_ld, void* workspace, size_t workspace_bytes,
+                         int row_tile, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REPO_B200_H */

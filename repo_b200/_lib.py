@@ -1,0 +1,84 @@
+"""ctypes binding of librepo_b200.so (C-ABI in include/repo_b200.h).
+
+There is no fallback: if the library is missing or a call fails, this raises."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "librepo_b200.so")
+
+ACT_KINDS = {"relu": 0, "elu": 1}
+WEIGHTS_PACKED = 1
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("belief", "state", "action", "hidden", "embed")]
+
+
+_RSSM_FIELDS = [
+    "fc_embed_state_action_w", "fc_embed_state_action_b",
+    "rnn_w_ih", "rnn_w_hh", "rnn_b_ih", "rnn_b_hh",
+    "fc_embed_belief_prior_w", "fc_embed_belief_prior_b",
+    "fc_state_prior_w", "fc_state_prior_b",
+    "fc_embed_belief_posterior_w", "fc_embed_belief_posterior_b",
+    "fc_state_posterior_w", "fc_state_posterior_b",
+]
+
+
+class RssmWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _RSSM_FIELDS]
+
+
+class MlpWeights(C.Structure):
+    _fields_ = [("w", C.c_void_p * 5), ("b", C.c_void_p * 5), ("n_layers", C.c_int)]
+
+
+EXPORTS = [
+    "repo_b200_version", "repo_b200_last_error", "repo_b200_device_info", "repo_b200_debug_flags",
+    "repo_b200_imagine_workspace_bytes", "repo_b200_imagine_fwd",
+    "repo_b200_observe_workspace_bytes", "repo_b200_observe_fwd",
+    "repo_b200_linear_workspace_bytes", "repo_b200_linear_fwd",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA library first (python -m repo_b200.build). "
+            "repo_b200 has no CPU or PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, ci, cf, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    L.repo_b200_version.restype = ci
+    L.repo_b200_last_error.restype = C.c_char_p
+    L.repo_b200_device_info.argtypes = [C.POINTER(ci)] * 3
+    L.repo_b200_device_info.restype = ci
+    L.repo_b200_debug_flags.argtypes = [ci]
+    L.repo_b200_debug_flags.restype = None
+    L.repo_b200_imagine_workspace_bytes.argtypes = [C.POINTER(Dims)]
+    L.repo_b200_imagine_workspace_bytes.restype = sz
+    L.repo_b200_imagine_fwd.argtypes = (
+        [C.POINTER(Dims), C.POINTER(RssmWeights), C.POINTER(MlpWeights), C.POINTER(MlpWeights), C.POINTER(MlpWeights)]
+        + [vp] * 12 + [ci, ci, ci] + [cf] * 6 + [vp, sz, ci, ci, vp])
+    L.repo_b200_imagine_fwd.restype = ci
+    L.repo_b200_observe_workspace_bytes.argtypes = [C.POINTER(Dims), ci, ci]
+    L.repo_b200_observe_workspace_bytes.restype = sz
+    L.repo_b200_observe_fwd.argtypes = (
+        [C.POINTER(Dims), C.POINTER(RssmWeights)] + [vp] * 15 + [ci, ci, ci, cf, vp, sz, ci, ci, vp])
+    L.repo_b200_observe_fwd.restype = ci
+    L.repo_b200_linear_workspace_bytes.argtypes = [ci, ci]
+    L.repo_b200_linear_workspace_bytes.restype = sz
+    L.repo_b200_linear_fwd.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp, ci, vp, sz, ci, vp]
+    L.repo_b200_linear_fwd.restype = ci
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().repo_b200_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

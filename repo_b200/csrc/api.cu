@@ -1,0 +1,450 @@
+// Host side of librepo_b200.so: builds the stage table ("program") for observe / imagine /
+// linear from the model sizes, packs the caller's fp32 weights into the workspace, and launches
+// the layer machine (vm.cuh).  C-ABI declared in include/repo_b200.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/repo_b200.h"
+#include "pack.cuh"
+#include "vm.cuh"
+
+using namespace rb;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_OK(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess) return fail(-2, "%s failed: %s", #expr, cudaGetErrorString(e_));  \
+  } while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Builds the stage/gemm tables and the matching pack jobs in lock-step.
+struct Builder {
+  VmParams P;
+  PackArgs pack;
+  BiasArgs bias;
+  int n_gemms = 0, n_stages = 0, n_bias_tiles = 0;
+  uint32_t n_slabs = 0;
+  int blk = 0;
+  int max_acc_tiles = 0;
+  bool overflow = false;
+
+  Builder() {
+    std::memset(&P, 0, sizeof(P));
+    std::memset(&pack, 0, sizeof(pack));
+    std::memset(&bias, 0, sizeof(bias));
+  }
+
+  // one 128-row tile of a weight matrix -> one gemm + one pack job
+  void gemm_tile(const float* w, int ld, int row0, int nrows, int col0, int ncols, int kofs, int ksl, int src,
+                 int src_k16, int acc_tile, int accumulate) {
+    if (n_gemms >= kMaxGemms || pack.n_jobs >= kMaxPackJobs) { overflow = true; return; }
+    VmGemm& g = P.gemms[n_gemms++];
+    g.w_slab = n_slabs;
+    g.ksl = (uint8_t)ksl;
+    g.src = (uint8_t)src;
+    g.src_k16 = (uint8_t)src_k16;
+    g.acc_tile = (uint8_t)acc_tile;
+    g.accumulate = (uint8_t)accumulate;
+    PackJob& j = pack.jobs[pack.n_jobs++];
+    j.w = w; j.ld = ld; j.row0 = row0; j.nrows = nrows; j.col0 = col0; j.ncols = ncols;
+    j.kofs = kofs; j.ksl = ksl; j.w_slab = n_slabs; j.blk0 = blk;
+    n_slabs += ksl;
+    blk += ksl;
+    max_acc_tiles = std::max(max_acc_tiles, acc_tile + 1);
+  }
+  // all tiles of rows [row0, row0+nrows) of a matrix; accumulator tiles acc0, acc0+1, ...
+  void gemm_rows(const float* w, int ld, int row0, int nrows, int col0, int ncols, int kofs, int ksl, int src,
+                 int src_k16, int acc0, int accumulate) {
+    for (int t = 0; t * 128 < nrows; ++t)
+      gemm_tile(w, ld, row0 + t * 128, std::min(128, nrows - t * 128), col0, ncols, kofs, ksl, src, src_k16,
+                acc0 + t, accumulate);
+  }
+  void bias_tile(const float* a, int a_off, const float* b, int b_off, int n) {
+    if (bias.n_jobs >= kMaxPackJobs) { overflow = true; return; }
+    BiasJob& j = bias.jobs[bias.n_jobs++];
+    j.a = a; j.a_off = a_off; j.b = b; j.b_off = b_off; j.n = std::max(0, std::min(128, n));
+    j.dst_tile = n_bias_tiles++;
+  }
+  void bias_rows(const float* a, int a_off, const float* b, int b_off, int n) {
+    for (int t = 0; t * 128 < n; ++t) bias_tile(a, a_off + t * 128, b, b ? b_off + t * 128 : 0, n - t * 128);
+  }
+  VmStage& begin_stage() {
+    VmStage& s = P.stages[std::min(n_stages, kMaxStages - 1)];
+    if (n_stages >= kMaxStages) overflow = true;
+    s.gemm_begin = (uint8_t)n_gemms;
+    s.bias_tile = (uint16_t)n_bias_tiles;
+    return s;
+  }
+  void end_stage(VmStage& s, int epi, int flags, int ntiles, int acc_tile0, int nfeat, int act) {
+    s.gemm_end = (uint8_t)n_gemms;
+    s.epi = (uint8_t)epi;
+    s.flags = (uint8_t)flags;
+    s.ntiles = (uint8_t)ntiles;
+    s.acc_tile0 = (uint8_t)acc_tile0;
+    s.nfeat = (uint16_t)nfeat;
+    s.act = (uint8_t)act;
+    ++n_stages;
+  }
+
+  // dense layer with activation: H = act(W src + b)
+  void dense_to_h(const float* w, const float* b, int ld, int out_f, int col0, int ncols, int kofs, int ksl, int src,
+                  int src_k16, int act, int flags = 0) {
+    VmStage& s = begin_stage();
+    gemm_rows(w, ld, 0, out_f, col0, ncols, kofs, ksl, src, src_k16, 0, 0);
+    bias_rows(b, 0, nullptr, 0, out_f);
+    end_stage(s, EPI_ACT_H, flags, cdiv(out_f, 128), 0, out_f, act);
+  }
+  // Gaussian head: rows [0,n) = mean -> tile 0, rows [n,2n) = raw std -> tile 1
+  void gaussian_head(const float* w, const float* b, int ld, int n, int ksl, int epi, int flags) {
+    VmStage& s = begin_stage();
+    gemm_tile(w, ld, 0, n, 0, ld, 0, ksl, 1, 0, 0, 0);
+    gemm_tile(w, ld, n, n, 0, ld, 0, ksl, 1, 0, 1, 0);
+    bias_tile(b, 0, nullptr, 0, n);
+    bias_tile(b, n, nullptr, 0, n);
+    end_stage(s, epi, flags, 1, 0, n, 0);
+  }
+  // fc_embed_state_action + GRUCell  (rssm.py:34-40)
+  void belief_update(const repo_b200_rssm_weights* W, int D, int S, int A, int act) {
+    const int kD16 = cdiv(D, 16), kx16 = cdiv(D + S + A, 16), kSA0 = D / 16, mtD = cdiv(D, 128);
+    dense_to_h(W->fc_embed_state_action_w, W->fc_embed_state_action_b, S + A, D, 0, S + A, D - 16 * kSA0,
+               kx16 - kSA0, 0, kSA0, act);
+    VmStage& s = begin_stage();
+    for (int g = 0; g < 3; ++g)  // W_ih * hidden: r, z, i_n
+      gemm_rows(W->rnn_w_ih, D, g * D, D, 0, D, 0, kD16, 1, 0, g * mtD, 0);
+    for (int g = 0; g < 3; ++g)  // W_hh * belief: r, z accumulate; h_n separate
+      gemm_rows(W->rnn_w_hh, D, g * D, D, 0, D, 0, kD16, 0, 0, (g < 2 ? g : 3) * mtD, g < 2 ? 1 : 0);
+    bias_rows(W->rnn_b_ih, 0, W->rnn_b_hh, 0, D);
+    bias_rows(W->rnn_b_ih, D, W->rnn_b_hh, D, D);
+    bias_rows(W->rnn_b_ih, 2 * D, nullptr, 0, D);
+    bias_rows(W->rnn_b_hh, 2 * D, nullptr, 0, D);
+    end_stage(s, EPI_GRU, 0, mtD, 0, D, 0);
+  }
+  // 4-layer scalar head on [belief|state]  (decoder.py:189-195 / actor_critic.py:20-26)
+  void scalar_head(const repo_b200_mlp_weights* M, int D, int S, int Hd, int act, int flags) {
+    const int kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);
+    dense_to_h(M->w[0], M->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, act);
+    dense_to_h(M->w[1], M->b[1], Hd, Hd, 0, Hd, 0, kH16, 1, 0, act);
+    dense_to_h(M->w[2], M->b[2], Hd, Hd, 0, Hd, 0, kH16, 1, 0, act);
+    VmStage& s = begin_stage();
+    gemm_tile(M->w[3], Hd, 0, 1, 0, Hd, 0, kH16, 1, 0, 0, 0);
+    bias_tile(M->b[3], 0, nullptr, 0, 1);
+    end_stage(s, EPI_SCALAR, flags, 1, 0, 1, 0);
+  }
+
+  size_t wblob_bytes() const { return (size_t)n_slabs * kSlabBytes; }
+  size_t bias_bytes() const { return (size_t)n_bias_tiles * 128 * sizeof(float); }
+  size_t packed_bytes() const { return wblob_bytes() + bias_bytes(); }
+
+  // point the program at a workspace and (optionally) enqueue the packing kernels
+  int bind_and_pack(void* ws, size_t ws_bytes, bool do_pack, cudaStream_t st) {
+    if (overflow) return fail(-3, "program too large (stages %d gemms %d)", n_stages, n_gemms);
+    if (ws_bytes < packed_bytes()) return fail(-4, "workspace too small: need %zu bytes, got %zu", packed_bytes(), ws_bytes);
+    if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return fail(-4, "workspace must be 16-byte aligned");
+    uint8_t* wb = static_cast<uint8_t*>(ws);
+    float* bb = reinterpret_cast<float*>(wb + wblob_bytes());
+    P.wblob = wb;
+    P.bias = bb;
+    P.n_stages = n_stages;
+    if (do_pack) {
+      pack.wblob = wb;
+      bias.bias = bb;
+      pack_weights_kernel<<<blk, 128, 0, st>>>(pack);
+      pack_bias_kernel<<<bias.n_jobs, 128, 0, st>>>(bias);
+      CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+  }
+};
+
+int g_dbg_flags = 0;
+int g_sm_count = 0;
+int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_sm_count;
+}
+
+template <int NT>
+int launch_nt(const VmParams& P, cudaStream_t st) {
+  const size_t smem = vm_smem_bytes(NT, P.kx16, P.kh16);
+  if (smem > 227 * 1024) return fail(-5, "shared memory budget exceeded: %zu bytes at row tile %d", smem, NT);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CUDA_OK(cudaFuncSetAttribute(rssm_vm_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int grid = cdiv(P.N, NT);
+  VmParams Q = P;
+  Q.dbg_flags = g_dbg_flags;
+  rssm_vm_kernel<NT><<<grid, kThreads, smem, st>>>(Q);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// rows per CTA: the largest tile that still gives every SM a CTA (weights are re-streamed per
+// CTA, so bigger tiles amortise them; smaller tiles spread a small batch over the chip)
+int pick_row_tile(int rows, int max_acc_tiles, int kx16, int kh16, int requested) {
+  int nt = 64;
+  if (requested == 16 || requested == 32 || requested == 64) nt = requested;
+  else {
+    const int sms = std::max(1, sm_count());
+    while (nt > 16 && cdiv(rows, nt) < sms) nt >>= 1;
+  }
+  while (nt > 16 && (max_acc_tiles * nt > (int)kTmemCols || vm_smem_bytes(nt, kx16, kh16) > 227 * 1024)) nt >>= 1;
+  return nt;
+}
+
+int launch(const VmParams& P, int max_acc_tiles, int requested, cudaStream_t st) {
+  if (P.N <= 0 || P.n_steps <= 0) return 0;
+  const int nt = pick_row_tile(P.N, max_acc_tiles, P.kx16, P.kh16, requested);
+  if (max_acc_tiles * nt > (int)kTmemCols) return fail(-5, "TMEM budget exceeded (%d accumulator tiles x %d rows)", max_acc_tiles, nt);
+  switch (nt) {
+    case 16: return launch_nt<16>(P, st);
+    case 32: return launch_nt<32>(P, st);
+    default: return launch_nt<64>(P, st);
+  }
+}
+
+int check_dims(const repo_b200_dims* d) {
+  if (!d) return fail(-1, "dims is NULL");
+  if (d->belief < 1 || d->belief > 256) return fail(-1, "belief_size %d unsupported (1..256)", d->belief);
+  if (d->hidden < 1 || d->hidden > 256) return fail(-1, "hidden_size %d unsupported (1..256)", d->hidden);
+  if (d->state < 1 || d->state > 128) return fail(-1, "state_size %d unsupported (1..128)", d->state);
+  if (d->action < 1 || d->action > 128) return fail(-1, "action_size %d unsupported (1..128)", d->action);
+  if (d->belief + d->state + d->action > 255 * 16) return fail(-1, "input width too large");
+  return 0;
+}
+int check_act(int act) {
+  if (act != REPO_B200_ACT_RELU && act != REPO_B200_ACT_ELU)
+    return fail(-1, "activation kind %d unsupported (relu=0, elu=1)", act);
+  return 0;
+}
+
+void set_dims(VmParams& P, const repo_b200_dims* d) {
+  P.D = d->belief; P.S = d->state; P.A = d->action; P.Hd = d->hidden;
+  P.kx16 = cdiv(d->belief + d->state + d->action, 16);
+  P.kh16 = cdiv(std::max(d->belief, d->hidden), 16);
+}
+
+void build_imagine(Builder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W,
+                   const repo_b200_mlp_weights* actor, const repo_b200_mlp_weights* reward,
+                   const repo_b200_mlp_weights* value, int act) {
+  const int D = d->belief, S = d->state, A = d->action, Hd = d->hidden;
+  const int kD16 = cdiv(D, 16), kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);
+  set_dims(b.P, d);
+  // actor (always ELU: actor_critic.py:58 + the positional-arg quirk at dreamer.py:99-105)
+  b.dense_to_h(actor->w[0], actor->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, ACT_ELU);
+  for (int i = 1; i < 4; ++i) b.dense_to_h(actor->w[i], actor->b[i], Hd, Hd, 0, Hd, 0, kH16, 1, 0, ACT_ELU);
+  b.gaussian_head(actor->w[4], actor->b[4], Hd, A, kH16, EPI_ACTION, 0);
+  b.belief_update(W, D, S, A, act);
+  b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act);
+  b.gaussian_head(W->fc_state_prior_w, W->fc_state_prior_b, Hd, S, kH16, EPI_PRIOR, SF_WRITES_STATE);
+  if (reward) b.scalar_head(reward, D, S, Hd, act, 0);
+  if (value) b.scalar_head(value, D, S, Hd, act, SF_SCALAR_VALUE);
+}
+
+void build_observe(Builder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W, bool with_obs, int act) {
+  const int D = d->belief, S = d->state, A = d->action, Hd = d->hidden, E = d->embed;
+  const int kD16 = cdiv(D, 16), kH16 = cdiv(Hd, 16);
+  set_dims(b.P, d);
+  b.belief_update(W, D, S, A, act);
+  b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act);
+  b.gaussian_head(W->fc_state_prior_w, W->fc_state_prior_b, Hd, S, kH16, EPI_PRIOR,
+                  with_obs ? 0 : (SF_WRITES_STATE | SF_LOADS_ACTION));
+  if (with_obs) {
+    // belief half of fc_embed_belief_posterior; the embedding half was hoisted into `addend`
+    b.dense_to_h(W->fc_embed_belief_posterior_w, W->fc_embed_belief_posterior_b, D + E, Hd, 0, D, 0, kD16, 0, 0, act,
+                 SF_ADDEND);
+    b.gaussian_head(W->fc_state_posterior_w, W->fc_state_posterior_b, Hd, S, kH16, EPI_POST,
+                    SF_WRITES_STATE | SF_LOADS_ACTION);
+  }
+}
+
+void build_linear(Builder& b, const float* w, const float* bias, int ld, int col0, int in_f, int out_f) {
+  b.P.kx16 = cdiv(in_f, 16);
+  b.P.kh16 = 0;
+  VmStage& s = b.begin_stage();
+  b.gemm_rows(w, ld, 0, out_f, col0, in_f, 0, cdiv(in_f, 16), 0, 0, 0, 0);
+  b.bias_rows(bias, 0, nullptr, 0, out_f);
+  b.end_stage(s, EPI_STORE, 0, cdiv(out_f, 128), 0, out_f, 0);
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int run_linear(const float* x, int x_ld, int rows, int in_f, const float* w, int w_ld, int w_col0, const float* b,
+               int out_f, float* y, int y_ld, void* ws, size_t ws_bytes, int row_tile, cudaStream_t st) {
+  if (in_f < 1 || in_f > 1900) return fail(-1, "linear: in_features %d unsupported (1..1900)", in_f);
+  if (out_f < 1 || out_f > 128 * 8) return fail(-1, "linear: out_features %d unsupported (1..1024)", out_f);
+  Builder bl;
+  build_linear(bl, w, b, w_ld, w_col0, in_f, out_f);
+  int rc = bl.bind_and_pack(ws, ws_bytes, true, st);
+  if (rc) return rc;
+  VmParams& P = bl.P;
+  P.n_steps = 1;
+  P.N = rows;
+  P.init_x = x; P.init_x_cols = in_f; P.init_x_ld = x_ld;
+  P.out = y; P.out_ld = y_ld;
+  // big K: small row tiles keep X inside shared memory
+  int nt = row_tile;
+  if (nt == 0) nt = pick_row_tile(rows, bl.max_acc_tiles, P.kx16, 0, 0);
+  return launch(P, bl.max_acc_tiles, nt, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int repo_b200_version(void) { return 1; }
+void repo_b200_debug_flags(int flags) { g_dbg_flags = flags; }
+const char* repo_b200_last_error(void) { return g_err; }
+
+int repo_b200_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(-2, "no CUDA device");
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return fail(-2, "cudaGetDeviceProperties failed");
+  if (sms) *sms = p.multiProcessorCount;
+  if (major) *major = p.major;
+  if (minor) *minor = p.minor;
+  return 0;
+}
+
+size_t repo_b200_linear_workspace_bytes(int in_f, int out_f) {
+  return (size_t)cdiv(out_f, 128) * cdiv(in_f, 16) * kSlabBytes + (size_t)cdiv(out_f, 128) * 512 + 64;
+}
+
+int repo_b200_linear_fwd(const float* x, int x_ld, int rows, int in_f, const float* w, const float* b, int out_f,
+                         float* y, int y_ld, void* ws, size_t ws_bytes, int row_tile, void* stream) {
+  if (!x || !w || !y || !ws) return fail(-1, "linear: NULL pointer");
+  return run_linear(x, x_ld, rows, in_f, w, in_f, 0, b, out_f, y, y_ld, ws, ws_bytes, row_tile,
+                    static_cast<cudaStream_t>(stream));
+}
+
+size_t repo_b200_imagine_workspace_bytes(const repo_b200_dims* d) {
+  if (check_dims(d)) return 0;
+  // size the program with dummy (null) weights: the layout depends on the sizes only
+  repo_b200_rssm_weights W{};
+  repo_b200_mlp_weights m{};
+  Builder b;
+  build_imagine(b, d, &W, &m, &m, &m, ACT_ELU);
+  return align_up(b.packed_bytes(), 256);
+}
+
+int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const repo_b200_mlp_weights* actor,
+                          const repo_b200_mlp_weights* reward, const repo_b200_mlp_weights* value,
+                          const float* start_belief, const float* start_state, const float* eps_action,
+                          const float* eps_prior, float* beliefs, float* prior_states, float* prior_means,
+                          float* prior_std_devs, float* actions, float* rewards, float* values, float* returns,
+                          int horizon, int n_rows, int act_kind, float min_std, float a_mean_scale, float a_init_std,
+                          float a_min_std, float gamma, float lambda_, void* ws, size_t ws_bytes, int flags,
+                          int row_tile, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_act(act_kind))) return rc;
+  if (!W || !actor) return fail(-1, "imagine: rssm / actor weights are required");
+  if (actor->n_layers != 5) return fail(-1, "imagine: policy must be an ActorModel with fc1..fc5 (got %d layers)", actor->n_layers);
+  if ((reward && reward->n_layers != 4) || (value && value->n_layers != 4)) return fail(-1, "imagine: reward/value heads must have fc1..fc4");
+  if (!start_belief || !start_state || !eps_action || !eps_prior || !beliefs || !prior_states || !prior_means || !prior_std_devs)
+    return fail(-1, "imagine: NULL input/output pointer");
+  if ((reward && !rewards) || (value && !values)) return fail(-1, "imagine: rewards/values output missing");
+  if (horizon < 1 || n_rows < 0) return fail(-1, "imagine: bad horizon %d / rows %d", horizon, n_rows);
+  if (horizon == 1 || n_rows == 0) return 0;  // reference returns empty stacks' worth of work
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Builder b;
+  build_imagine(b, d, W, actor, reward, value, act_kind);
+  if ((rc = b.bind_and_pack(ws, ws_bytes, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
+  VmParams& P = b.P;
+  P.n_steps = horizon - 1;
+  P.N = n_rows;
+  P.min_std = min_std;
+  P.a_mean_scale = a_mean_scale; P.a_init_std = a_init_std; P.a_min_std = a_min_std;
+  P.gamma = gamma; P.lambda = lambda_;
+  P.one_minus_lambda = (float)(1.0 - (double)lambda_);
+  P.init_belief = start_belief; P.init_state = start_state;
+  P.eps_action = eps_action; P.eps_prior = eps_prior;
+  P.beliefs = beliefs; P.prior_s = prior_states; P.prior_m = prior_means; P.prior_sd = prior_std_devs;
+  P.actions_out = actions;
+  P.rewards = reward ? rewards : nullptr;
+  P.values = value ? values : nullptr;
+  P.returns = (reward && value) ? returns : nullptr;
+  return launch(P, b.max_acc_tiles, row_tile, st);
+}
+
+size_t repo_b200_observe_workspace_bytes(const repo_b200_dims* d, int t1, int batch) {
+  if (check_dims(d)) return 0;
+  repo_b200_rssm_weights W{};
+  Builder b;
+  build_observe(b, d, &W, true, ACT_ELU);
+  const size_t main = align_up(b.packed_bytes(), 256);
+  const size_t lin = align_up(repo_b200_linear_workspace_bytes(d->embed, d->hidden), 256);
+  const size_t addend = align_up((size_t)std::max(t1, 0) * std::max(batch, 0) * d->hidden * sizeof(float), 256);
+  return main + lin + addend;
+}
+
+int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const float* prev_belief,
+                          const float* prev_state, const float* actions, const float* embeds, const float* nonterm,
+                          const float* eps_prior, const float* eps_post, float* beliefs, float* prior_states,
+                          float* prior_means, float* prior_std_devs, float* post_states, float* post_means,
+                          float* post_std_devs, float* kl, int t1, int batch, int act_kind, float min_std, void* ws,
+                          size_t ws_bytes, int flags, int row_tile, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_act(act_kind))) return rc;
+  if (!W || !prev_belief || !prev_state || !actions || !eps_prior || !beliefs || !prior_states || !prior_means || !prior_std_devs)
+    return fail(-1, "observe: NULL input/output pointer");
+  const bool with_obs = embeds != nullptr;
+  if (with_obs && (!eps_post || !post_states || !post_means || !post_std_devs)) return fail(-1, "observe: posterior buffers missing");
+  if (t1 < 0 || batch < 0) return fail(-1, "observe: bad sizes");
+  if (t1 == 0 || batch == 0) return 0;
+  if (ws_bytes < repo_b200_observe_workspace_bytes(d, t1, batch)) return fail(-4, "observe: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Builder b;
+  build_observe(b, d, W, with_obs, act_kind);
+  const size_t main = align_up(b.packed_bytes(), 256);
+  const size_t lin = align_up(repo_b200_linear_workspace_bytes(d->embed, d->hidden), 256);
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  if ((rc = b.bind_and_pack(base, main, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
+  float* addend = reinterpret_cast<float*>(base + main + lin);
+  if (with_obs) {
+    // hoisted, non-recurrent half of the posterior layer: all (t, b) rows in one pass
+    rc = run_linear(embeds, d->embed, t1 * batch, d->embed, W->fc_embed_belief_posterior_w, d->belief + d->embed,
+                    d->belief, nullptr, d->hidden, addend, d->hidden, base + main, lin, 0, st);
+    if (rc) return rc;
+  }
+  VmParams& P = b.P;
+  P.n_steps = t1;
+  P.N = batch;
+  P.min_std = min_std;
+  P.init_belief = prev_belief; P.init_state = prev_state;
+  P.actions_in = actions; P.nonterm = nonterm;
+  P.addend = with_obs ? addend : nullptr;
+  P.eps_prior = eps_prior; P.eps_post = eps_post;
+  P.beliefs = beliefs; P.prior_s = prior_states; P.prior_m = prior_means; P.prior_sd = prior_std_devs;
+  P.post_s = post_states; P.post_m = post_means; P.post_sd = post_std_devs;
+  P.kl = with_obs ? kl : nullptr;
+  if (P.kl && d->state > 32) CUDA_OK(cudaMemsetAsync(kl, 0, (size_t)t1 * batch * sizeof(float), st));
+  return launch(P, b.max_acc_tiles, row_tile, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,530 @@
+// The persistent "layer machine" behind observe / imagine / linear.
+//
+// One CTA owns NT rows (batch rows = independent RSSM sequences) for the whole time loop.
+// Activations stay on-chip: X = [belief | state | action] and H = hidden, both kept as fp16
+// hi/lo pairs in shared memory in the tcgen05 K-major core-matrix layout, so they are the
+// B operand (N = NT rows) of every MMA.  Weights are the A operand (M = 128 output features
+// per tile); they are pre-packed (pack.cuh) into 8 KB k16-slabs [hi 4 KB | lo 4 KB] already in
+// the smem image, and streamed L2 -> smem by the TMA engine (1-D bulk copies) through a ring.
+// Accumulators live in TMEM: tile j at columns [j*NT, (j+1)*NT), lane = output feature.
+//
+// Every x*W is three tcgen05.mma (hi*hi + lo*hi + hi*lo, fp32 accumulate) — fp32-grade
+// accuracy on the fp16 tensor pipe (see DESIGN.md "Arithmetic").
+//
+// Warp roles: warp 0 = weight loader (one thread), warp 1 = MMA issuer (one thread) + TMEM
+// owner, warps 2..5 = epilogue (thread <-> TMEM lane <-> output feature).  The three roles walk
+// the same stage table (VmParams, passed by value), so they cannot disagree about the order.
+#pragma once
+#include "ptx.cuh"
+
+namespace rb {
+
+constexpr int kSlabBytes = 8192;  // one k16 slab of a 128-feature tile: hi 4096 B then lo 4096 B
+constexpr int kSlotSlabs = 4;     // slabs per ring slot
+constexpr int kSlots = 3;
+constexpr int kSlotBytes = kSlotSlabs * kSlabBytes;
+constexpr int kRingBytes = kSlots * kSlotBytes;
+constexpr int kMaxStages = 20;
+constexpr int kMaxGemms = 48;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr uint32_t kTmemCols = 512;
+
+enum EpiKind : uint8_t {
+  EPI_ACT_H = 0,   // H[:, f] = act(acc + bias (+ addend[t]))
+  EPI_ACTION = 1,  // a = tanh(ms*tanh(m/ms) + (softplus(s+init)+min)*eps) -> X action slot
+  EPI_GRU = 2,     // GRU gates -> belief' -> beliefs[t], X belief slot
+  EPI_PRIOR = 3,   // prior mean/std/sample -> outputs (+ X state slot when it feeds the recurrence)
+  EPI_POST = 4,    // posterior mean/std/sample + KL -> outputs, X state slot
+  EPI_SCALAR = 5,  // lane 0: scalar head output (reward / value)
+  EPI_STORE = 6,   // out[row, f] = acc + bias   (plain linear layer)
+};
+enum StageFlags : uint8_t {
+  SF_WRITES_STATE = 1,  // epilogue writes the sampled state into X (masked by nonterm[t+1])
+  SF_LOADS_ACTION = 2,  // epilogue stages actions_in[t+1] into X
+  SF_ADDEND = 4,        // EPI_ACT_H adds addend[t, row, f]
+  SF_SCALAR_VALUE = 8,  // EPI_SCALAR writes `values` instead of `rewards`
+};
+enum ActKind : int { ACT_RELU = 0, ACT_ELU = 1 };
+
+struct VmGemm {        // acc[acc_tile] (+)= Wtile(128 x 16*ksl) * Src[:, 16*src_k16 ...)^T
+  uint32_t w_slab;     // first slab of this tile in the packed weight blob
+  uint8_t ksl;         // k16 slabs
+  uint8_t src;         // 0 = X, 1 = H
+  uint8_t src_k16;     // first k16 slab inside the source buffer
+  uint8_t acc_tile;    // accumulator tile
+  uint8_t accumulate;  // keep what the tile already holds
+  uint8_t pad[3];
+};
+struct VmStage {
+  uint8_t gemm_begin, gemm_end;
+  uint8_t epi, flags;
+  uint8_t ntiles;     // feature tiles the epilogue walks (per gate for GRU)
+  uint8_t acc_tile0;  // first accumulator tile
+  uint16_t nfeat;     // valid output features
+  uint16_t bias_tile; // first 128-float bias tile
+  uint8_t act;        // ActKind of EPI_ACT_H (the actor is always ELU, actor_critic.py:58)
+  uint8_t pad;
+};
+
+struct VmParams {
+  int n_steps, n_stages;
+  int N;                 // rows
+  int D, S, A, Hd;       // belief, state, action, hidden sizes
+  int kx16, kh16;        // k16 slabs held by X / H
+  float min_std;         // RSSM min std
+  float a_mean_scale, a_init_std, a_min_std;
+  float gamma, lambda, one_minus_lambda;  // (1 - lambda) rounded from double like the reference's Python scalar
+  const uint8_t* wblob;
+  const float* bias;
+  // initial contents of X
+  const float* init_belief;  // (N, D) or null (zeros)
+  const float* init_state;   // (N, S) or null
+  const float* init_x;       // linear mode: (N, init_x_cols) row-major, ld = init_x_ld
+  int init_x_cols, init_x_ld;
+  // per-step inputs, time-major
+  const float* actions_in;   // (T, N, A) or null
+  const float* nonterm;      // (T, N) or null
+  const float* addend;       // (T, N, Hd) or null
+  const float* eps_action;   // (T, N, A)
+  const float* eps_prior;    // (T, N, S)
+  const float* eps_post;     // (T, N, S)
+  // outputs, time-major
+  float* beliefs;            // (T, N, D)
+  float* prior_s; float* prior_m; float* prior_sd;  // (T, N, S)
+  float* post_s; float* post_m; float* post_sd;     // (T, N, S)
+  float* kl;                 // (T, N) or null
+  float* actions_out;        // (T, N, A) or null
+  float* rewards; float* values;  // (T, N) or null
+  float* returns;            // (T-1, N) or null
+  float* out; int out_ld;    // EPI_STORE
+  int dbg_flags;             // bring-up only: bit0 swaps LBO/SBO in the smem descriptors
+  VmStage stages[kMaxStages];
+  VmGemm gemms[kMaxGemms];
+};
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_fn(float x, int kind) {
+  if (kind == ACT_ELU) return x > 0.f ? x : expm1f(x);
+  return fmaxf(x, 0.f);
+}
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int NT>
+struct Tile {
+  static constexpr uint32_t LBO = NT * 16 + 16;  // bytes between k-groups (8 columns); +16 spreads banks
+  static constexpr uint32_t SBO = 128;           // bytes between 8-row groups
+  // byte offset of element (row n, column k) inside an activation buffer
+  __device__ static __forceinline__ uint32_t off(int n, int k) {
+    return (uint32_t)(k >> 3) * LBO + (uint32_t)(n >> 3) * SBO + (uint32_t)(n & 7) * 16 + (uint32_t)(k & 7) * 2;
+  }
+  __device__ static __forceinline__ void put(uint8_t* hi, uint8_t* lo, int n, int k, float v) {
+    __half h, l;
+    split_f16(v, h, l);
+    const uint32_t o = off(n, k);
+    *reinterpret_cast<__half*>(hi + o) = h;
+    *reinterpret_cast<__half*>(lo + o) = l;
+  }
+  __host__ __device__ static constexpr uint32_t buf_bytes(int k16) { return (uint32_t)k16 * 2u * LBO; }
+};
+
+__host__ __device__ inline size_t vm_smem_bytes(int NT, int kx16, int kh16) {
+  const size_t lbo = (size_t)NT * 16 + 16;
+  return (size_t)kRingBytes + 2 * (size_t)kx16 * 2 * lbo + 2 * (size_t)kh16 * 2 * lbo + 256;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_constant__ VmParams P) {
+  using TL = Tile<NT>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;
+  uint8_t* x_hi = ring + kRingBytes;
+  uint8_t* x_lo = x_hi + TL::buf_bytes(P.kx16);
+  uint8_t* h_hi = x_lo + TL::buf_bytes(P.kx16);
+  uint8_t* h_lo = h_hi + TL::buf_bytes(P.kh16);
+  uint8_t* tail = h_lo + TL::buf_bytes(P.kh16);
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tail) + 15) & ~uintptr_t(15));
+  // bars[0..kSlots) full, [kSlots..2kSlots) empty, [2kSlots] acc_full, [2kSlots+1] act_ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * NT;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kSlots);
+  const uint32_t bar_acc = smem_u32(bars + 2 * kSlots), bar_act = smem_u32(bars + 2 * kSlots + 1);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_act, kEpiThreads);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ weight loader ================================
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      for (int t = 0; t < P.n_steps; ++t) {
+        for (int s = 0; s < P.n_stages; ++s) {
+          const VmStage& st = P.stages[s];
+          for (int g = st.gemm_begin; g < st.gemm_end; ++g) {
+            const VmGemm& gm = P.gemms[g];
+            for (int c0 = 0; c0 < gm.ksl; c0 += kSlotSlabs) {
+              const int nsl = min(kSlotSlabs, (int)gm.ksl - c0);
+              mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+              const uint32_t bytes = (uint32_t)nsl * kSlabBytes;
+              mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+              bulk_g2s(smem_u32(ring + slot * kSlotBytes), P.wblob + (size_t)(gm.w_slab + c0) * kSlabBytes, bytes,
+                       bar_full + 8 * slot);
+              if (++slot == kSlots) { slot = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, NT);
+      uint32_t slot = 0, phase = 0, act_phase = 0;
+      const uint32_t ring_a = smem_u32(ring);
+      const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo), hh = smem_u32(h_hi), hl = smem_u32(h_lo);
+      for (int t = 0; t < P.n_steps; ++t) {
+        for (int s = 0; s < P.n_stages; ++s) {
+          const VmStage& st = P.stages[s];
+          mbar_wait(bar_act, act_phase);  // previous epilogue: activations written, TMEM drained
+          act_phase ^= 1;
+          tc_fence_after();
+          for (int g = st.gemm_begin; g < st.gemm_end; ++g) {
+            const VmGemm& gm = P.gemms[g];
+            const uint32_t b_hi = gm.src ? hh : xh, b_lo = gm.src ? hl : xl;
+            const uint32_t d = tmem_base + (uint32_t)gm.acc_tile * NT;
+            for (int c0 = 0; c0 < gm.ksl; c0 += kSlotSlabs) {
+              const int nsl = min(kSlotSlabs, (int)gm.ksl - c0);
+              mbar_wait(bar_full + 8 * slot, phase);
+              tc_fence_after();
+              for (int j = 0; j < nsl; ++j) {
+                const uint32_t a_addr = ring_a + slot * kSlotBytes + j * kSlabBytes;
+                const uint32_t koff = (uint32_t)(gm.src_k16 + c0 + j) * 2u * TL::LBO;
+                uint64_t a_hi, a_lo, bd_hi, bd_lo;
+                if (P.dbg_flags & 1) {
+                  a_hi = make_smem_desc(a_addr, 128, 2048);
+                  a_lo = make_smem_desc(a_addr + 4096, 128, 2048);
+                  bd_hi = make_smem_desc(b_hi + koff, TL::SBO, TL::LBO);
+                  bd_lo = make_smem_desc(b_lo + koff, TL::SBO, TL::LBO);
+                } else {
+                  a_hi = make_smem_desc(a_addr, 2048, 128);
+                  a_lo = make_smem_desc(a_addr + 4096, 2048, 128);
+                  bd_hi = make_smem_desc(b_hi + koff, TL::LBO, TL::SBO);
+                  bd_lo = make_smem_desc(b_lo + koff, TL::LBO, TL::SBO);
+                }
+                const uint32_t acc = (gm.accumulate || (c0 + j) > 0) ? 1u : 0u;
+                umma_f16(d, a_hi, bd_hi, idesc, acc);
+                umma_f16(d, a_hi, bd_lo, idesc, 1u);
+                umma_f16(d, a_lo, bd_hi, idesc, 1u);
+              }
+              umma_commit(bar_empty + 8 * slot);  // slot reusable once these MMAs retire
+              if (++slot == kSlots) { slot = 0; phase ^= 1; }
+            }
+          }
+          umma_commit(bar_acc);  // accumulators of this stage complete
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue warps ================================
+    const int et = threadIdx.x - 64;                 // 0..127
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+    const int lf = q * 32 + lane;                    // lane / feature-within-tile
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int N = P.N, D = P.D, S = P.S, A = P.A;
+    auto epi_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+
+    // ---- init: zero both buffers (pad columns must stay finite), then stage X ----
+    {
+      const uint32_t words = (2 * TL::buf_bytes(P.kx16) + 2 * TL::buf_bytes(P.kh16)) / 16;
+      uint4* z = reinterpret_cast<uint4*>(x_hi);
+      for (uint32_t i = et; i < words; i += kEpiThreads) z[i] = make_uint4(0, 0, 0, 0);
+      epi_sync();
+      if (P.init_x) {
+        for (int idx = et; idx < NT * P.init_x_cols; idx += kEpiThreads) {
+          const int n = idx / P.init_x_cols, k = idx - n * P.init_x_cols, row = row0 + n;
+          if (row < N) TL::put(x_hi, x_lo, n, k, P.init_x[(size_t)row * P.init_x_ld + k]);
+        }
+      } else {
+        if (P.init_belief)
+          for (int idx = et; idx < NT * D; idx += kEpiThreads) {
+            const int n = idx / D, k = idx - n * D, row = row0 + n;
+            if (row < N) TL::put(x_hi, x_lo, n, k, P.init_belief[(size_t)row * D + k]);
+          }
+        if (P.init_state)
+          for (int idx = et; idx < NT * S; idx += kEpiThreads) {
+            const int n = idx / S, k = idx - n * S, row = row0 + n;
+            if (row < N) {
+              float v = P.init_state[(size_t)row * S + k];
+              if (P.nonterm) v *= P.nonterm[row];
+              TL::put(x_hi, x_lo, n, D + k, v);
+            }
+          }
+        if (P.actions_in)
+          for (int idx = et; idx < NT * A; idx += kEpiThreads) {
+            const int n = idx / A, k = idx - n * A, row = row0 + n;
+            if (row < N) TL::put(x_hi, x_lo, n, D + S + k, P.actions_in[(size_t)row * A + k]);
+          }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_act);
+    }
+
+    uint32_t acc_phase = 0;
+    for (int t = 0; t < P.n_steps; ++t) {
+      const size_t trow = (size_t)t * N;  // row offset of time step t in time-major tensors
+      const bool has_next = (t + 1) < P.n_steps;
+      for (int s = 0; s < P.n_stages; ++s) {
+        const VmStage& st = P.stages[s];
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        const uint32_t tacc = tlane + (uint32_t)st.acc_tile0 * NT;
+
+        switch (st.epi) {
+          case EPI_ACT_H: {
+            for (int tile = 0; tile < st.ntiles; ++tile) {
+              const int f = tile * 128 + lf;
+              const bool vf = f < st.nfeat;
+              const float bias = P.bias[(st.bias_tile + tile) * 128 + lf];
+#pragma unroll 1
+              for (int c = 0; c < NT / 16; ++c) {
+                float v[16];
+                tmem_ld16(tacc + tile * NT + c * 16, v);
+                tmem_ld_wait();
+                if (vf) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int n = c * 16 + i, row = row0 + n;
+                    float x = v[i] + bias;
+                    if ((st.flags & SF_ADDEND) && row < N) x += P.addend[(trow + row) * P.Hd + f];
+                    TL::put(h_hi, h_lo, n, f, act_fn(x, st.act));
+                  }
+                }
+              }
+            }
+          } break;
+
+          case EPI_STORE: {
+            for (int tile = 0; tile < st.ntiles; ++tile) {
+              const int f = tile * 128 + lf;
+              const bool vf = f < st.nfeat;
+              const float bias = P.bias[(st.bias_tile + tile) * 128 + lf];
+#pragma unroll 1
+              for (int c = 0; c < NT / 16; ++c) {
+                float v[16];
+                tmem_ld16(tacc + tile * NT + c * 16, v);
+                tmem_ld_wait();
+                if (vf) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int row = row0 + c * 16 + i;
+                    if (row < N) P.out[(size_t)row * P.out_ld + f] = v[i] + bias;
+                  }
+                }
+              }
+            }
+          } break;
+
+          case EPI_GRU: {
+            const int mt = st.ntiles;
+            for (int tile = 0; tile < mt; ++tile) {
+              const int u = tile * 128 + lf;
+              const bool vu = u < D;
+              const float br = P.bias[(st.bias_tile + tile) * 128 + lf];
+              const float bz = P.bias[(st.bias_tile + mt + tile) * 128 + lf];
+              const float bin = P.bias[(st.bias_tile + 2 * mt + tile) * 128 + lf];
+              const float bhn = P.bias[(st.bias_tile + 3 * mt + tile) * 128 + lf];
+              const float* bprev = (t == 0) ? P.init_belief : (P.beliefs + (trow - N) * D);
+#pragma unroll 1
+              for (int c = 0; c < NT / 16; ++c) {
+                float vr[16], vz[16], vi[16], vh[16];
+                tmem_ld16(tacc + (tile)*NT + c * 16, vr);
+                tmem_ld16(tacc + (mt + tile) * NT + c * 16, vz);
+                tmem_ld16(tacc + (2 * mt + tile) * NT + c * 16, vi);
+                tmem_ld16(tacc + (3 * mt + tile) * NT + c * 16, vh);
+                tmem_ld_wait();
+                if (vu) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int n = c * 16 + i, row = row0 + n;
+                    const bool vr_ = row < N;
+                    const float r = sigmoid_f(vr[i] + br);
+                    const float z = sigmoid_f(vz[i] + bz);
+                    const float nn = tanhf(vi[i] + bin + r * (vh[i] + bhn));
+                    const float bo = (vr_ && bprev) ? bprev[(size_t)row * D + u] : 0.f;
+                    const float bn = (1.f - z) * nn + z * bo;
+                    if (vr_) P.beliefs[(trow + row) * D + u] = bn;
+                    TL::put(x_hi, x_lo, n, u, bn);
+                  }
+                }
+              }
+            }
+          } break;
+
+          case EPI_PRIOR:
+          case EPI_POST: {
+            const bool post = st.epi == EPI_POST;
+            const int j = lf;
+            const bool vj = j < S;
+            const float bm = P.bias[(st.bias_tile) * 128 + lf];
+            const float bs = P.bias[(st.bias_tile + 1) * 128 + lf];
+            const float* eps = post ? P.eps_post : P.eps_prior;
+            float* o_s = post ? P.post_s : P.prior_s;
+            float* o_m = post ? P.post_m : P.prior_m;
+            float* o_sd = post ? P.post_sd : P.prior_sd;
+            const bool any_valid_in_warp = (q * 32) < S;
+#pragma unroll 1
+            for (int c = 0; c < NT / 16; ++c) {
+              float vm[16], vs[16];
+              tmem_ld16(tacc + c * 16, vm);
+              tmem_ld16(tacc + NT + c * 16, vs);
+              tmem_ld_wait();
+              if (any_valid_in_warp) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int n = c * 16 + i, row = row0 + n;
+                  const bool ok = vj && row < N;
+                  const size_t o = (trow + row) * S + j;
+                  const float m = vm[i] + bm;
+                  const float sd = softplus_f(vs[i] + bs) + P.min_std;
+                  const float e = ok ? eps[o] : 0.f;
+                  const float smp = m + sd * e;
+                  if (ok) {
+                    o_s[o] = smp;
+                    o_m[o] = m;
+                    o_sd[o] = sd;
+                  }
+                  if (post && P.kl) {
+                    float klj = 0.f;
+                    if (ok) {
+                      const float pm = P.prior_m[o], psd = P.prior_sd[o];
+                      const float ratio = sd / psd, vr = ratio * ratio;
+                      const float dm = (m - pm) / psd;
+                      klj = 0.5f * (vr + dm * dm - 1.f - logf(vr));
+                    }
+#pragma unroll
+                    for (int sh = 16; sh > 0; sh >>= 1) klj += __shfl_xor_sync(0xffffffffu, klj, sh);
+                    if (lane == 0 && row < N) {
+                      if (S <= 32) P.kl[trow + row] = klj;
+                      else atomicAdd(&P.kl[trow + row], klj);
+                    }
+                  }
+                  if ((st.flags & SF_WRITES_STATE) && vj) {
+                    float sx = smp;
+                    if (P.nonterm && has_next && row < N) sx *= P.nonterm[trow + N + row];
+                    TL::put(x_hi, x_lo, n, D + j, sx);
+                  }
+                }
+              }
+            }
+            if ((st.flags & SF_LOADS_ACTION) && has_next) {
+              for (int idx = et; idx < NT * A; idx += kEpiThreads) {
+                const int n = idx / A, k = idx - n * A, row = row0 + n;
+                if (row < N) TL::put(x_hi, x_lo, n, D + S + k, P.actions_in[(trow + N + row) * A + k]);
+              }
+            }
+          } break;
+
+          case EPI_ACTION: {
+            const int j = lf;
+            const bool vj = j < A;
+            const float bm = P.bias[(st.bias_tile) * 128 + lf];
+            const float bs = P.bias[(st.bias_tile + 1) * 128 + lf];
+            const bool any_valid_in_warp = (q * 32) < A;
+#pragma unroll 1
+            for (int c = 0; c < NT / 16; ++c) {
+              float vm[16], vs[16];
+              tmem_ld16(tacc + c * 16, vm);
+              tmem_ld16(tacc + NT + c * 16, vs);
+              tmem_ld_wait();
+              if (any_valid_in_warp && vj) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int n = c * 16 + i, row = row0 + n;
+                  const bool ok = row < N;
+                  const size_t o = (trow + row) * A + j;
+                  const float mean = P.a_mean_scale * tanhf((vm[i] + bm) / P.a_mean_scale);
+                  const float sd = softplus_f(vs[i] + bs + P.a_init_std) + P.a_min_std;
+                  const float e = ok ? P.eps_action[o] : 0.f;
+                  const float a = tanhf(mean + sd * e);
+                  if (ok && P.actions_out) P.actions_out[o] = a;
+                  TL::put(x_hi, x_lo, n, D + S + j, a);
+                }
+              }
+            }
+          } break;
+
+          case EPI_SCALAR: {
+            const float b0 = P.bias[(st.bias_tile) * 128 + lf];
+            float* dst = (st.flags & SF_SCALAR_VALUE) ? P.values : P.rewards;
+#pragma unroll 1
+            for (int c = 0; c < NT / 16; ++c) {
+              float v[16];
+              tmem_ld16(tacc + c * 16, v);
+              tmem_ld_wait();
+              if (lf == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int row = row0 + c * 16 + i;
+                  if (row < N) dst[trow + row] = v[i] + b0;
+                }
+              }
+            }
+          } break;
+          default: break;
+        }
+
+        // hand the buffers / TMEM back to the MMA issuer
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_act);
+      }
+    }
+
+    // ---- lambda-return: reverse scan over the horizon, one thread per row ----
+    if (P.returns && P.rewards && P.values && P.n_steps >= 2) {
+      __threadfence_block();
+      epi_sync();
+      const int row = row0 + et;
+      if (et < NT && row < N) {
+        const int T = P.n_steps;
+        const float g = P.gamma, lam = P.lambda;
+        float last = P.values[(size_t)(T - 1) * N + row];  // bootstrap = values[-1]
+        float next_v = last;
+        for (int t = T - 2; t >= 0; --t) {
+          const float r = P.rewards[(size_t)t * N + row];
+          const float inp = r + g * next_v * P.one_minus_lambda;
+          last = inp + g * lam * last;
+          P.returns[(size_t)t * N + row] = last;
+          next_v = P.values[(size_t)t * N + row];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace rb
