@@ -104,12 +104,34 @@ struct VmParams {
 };
 
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float act_fn(float x, int kind) {
-  if (kind == ACT_ELU) return x > 0.f ? x : expm1f(x);
+// Epilogue math: MUFU-based (ex2/lg2/rcp) forms with ~1e-7 absolute error — two orders of
+// magnitude inside the 1e-3 parity budget — instead of the multi-instruction libm slow paths.
+__device__ __forceinline__ float ex2_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_f(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float exp_f(float x) { return ex2_f(x * 1.4426950408889634f); }
+template <int ACT>
+__device__ __forceinline__ float act_t(float x) {
+  if (ACT == ACT_ELU) return x > 0.f ? x : exp_f(x) - 1.f;
   return fmaxf(x, 0.f);
 }
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : __logf(1.f + exp_f(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return rcp_f(1.f + exp_f(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 1.f - 2.f * rcp_f(1.f + exp_f(2.f * x)); }
+// 16 strided read-only loads issued back to back (one memory round trip, not sixteen)
+__device__ __forceinline__ void ldg16(float* dst, const float* __restrict__ base, size_t stride, int row_first,
+                                      int n_rows, bool lane_ok) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    dst[i] = (lane_ok && (row_first + i) < n_rows) ? __ldg(base + (size_t)i * stride) : 0.f;
+}
 
 template <int NT>
 struct Tile {
@@ -132,6 +154,43 @@ struct Tile {
 __host__ __device__ inline size_t vm_smem_bytes(int NT, int kx16, int kh16) {
   const size_t lbo = (size_t)NT * 16 + 16;
   return (size_t)kRingBytes + 2 * (size_t)kx16 * 2 * lbo + 2 * (size_t)kh16 * 2 * lbo + 256;
+}
+
+
+// H[:, f] = act(acc + bias (+ addend)) for every feature tile of the stage; thread <-> feature.
+template <int NT, int ACT>
+__device__ __forceinline__ void epi_act_h(const VmParams& P, const VmStage& st, uint8_t* h_hi, uint8_t* h_lo,
+                                          uint32_t tacc, int lf, int row0, size_t trow) {
+  using TL = Tile<NT>;
+  const bool addend = (st.flags & SF_ADDEND) != 0;
+  const int ntiles = st.ntiles, nfeat = st.nfeat, N = P.N;
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int f = tile * 128 + lf;
+    const bool vf = f < nfeat;
+    const float bias = P.bias[(st.bias_tile + tile) * 128 + lf];
+    uint8_t* bh = h_hi + TL::off(0, f);
+    uint8_t* bl = h_lo + TL::off(0, f);
+#pragma unroll 1
+    for (int c = 0; c < NT / 16; ++c) {
+      float v[16], ad[16];
+      const int r0 = row0 + c * 16;
+      if (addend) ldg16(ad, P.addend + (trow + r0) * P.Hd + f, P.Hd, r0, N, vf);
+      tmem_ld16(tacc + tile * NT + c * 16, v);
+      tmem_ld_wait();
+      if (vf) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = v[i] + bias;
+          if (addend) x += ad[i];
+          __half h, l;
+          split_f16(act_t<ACT>(x), h, l);
+          const uint32_t o = (uint32_t)c * 256u + (uint32_t)(i >> 3) * 128u + (uint32_t)(i & 7) * 16u;
+          *reinterpret_cast<__half*>(bh + o) = h;
+          *reinterpret_cast<__half*>(bl + o) = l;
+        }
+      }
+    }
+  }
 }
 
 template <int NT>
@@ -173,77 +232,84 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
 
   if (warp == 0) {
     // ================================ weight loader ================================
-    if (lane == 0) {
-      uint32_t slot = 0, phase = 0;
-      for (int t = 0; t < P.n_steps; ++t) {
-        for (int s = 0; s < P.n_stages; ++s) {
-          const VmStage& st = P.stages[s];
-          for (int g = st.gemm_begin; g < st.gemm_end; ++g) {
-            const VmGemm& gm = P.gemms[g];
-            for (int c0 = 0; c0 < gm.ksl; c0 += kSlotSlabs) {
-              const int nsl = min(kSlotSlabs, (int)gm.ksl - c0);
-              mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+    // The whole warp walks the table (warp-uniform control flow); one elected lane issues.
+    uint32_t slot = 0, phase = 0;
+    for (int t = 0; t < P.n_steps; ++t) {
+      for (int s = 0; s < P.n_stages; ++s) {
+        const int g0 = P.stages[s].gemm_begin, g1 = P.stages[s].gemm_end;
+        for (int g = g0; g < g1; ++g) {
+          const uint32_t w_slab = P.gemms[g].w_slab;
+          const int ksl = P.gemms[g].ksl;
+          for (int c0 = 0; c0 < ksl; c0 += kSlotSlabs) {
+            const int nsl = min(kSlotSlabs, ksl - c0);
+            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+            if (elect_one()) {
               const uint32_t bytes = (uint32_t)nsl * kSlabBytes;
               mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
-              bulk_g2s(smem_u32(ring + slot * kSlotBytes), P.wblob + (size_t)(gm.w_slab + c0) * kSlabBytes, bytes,
+              bulk_g2s(smem_u32(ring + slot * kSlotBytes), P.wblob + (size_t)(w_slab + c0) * kSlabBytes, bytes,
                        bar_full + 8 * slot);
-              if (++slot == kSlots) { slot = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++slot == kSlots) { slot = 0; phase ^= 1; }
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, NT);
-      uint32_t slot = 0, phase = 0, act_phase = 0;
-      const uint32_t ring_a = smem_u32(ring);
-      const uint32_t xh = smem_u32(x_hi), xl = smem_u32(x_lo), hh = smem_u32(h_hi), hl = smem_u32(h_lo);
-      for (int t = 0; t < P.n_steps; ++t) {
-        for (int s = 0; s < P.n_stages; ++s) {
-          const VmStage& st = P.stages[s];
-          mbar_wait(bar_act, act_phase);  // previous epilogue: activations written, TMEM drained
-          act_phase ^= 1;
-          tc_fence_after();
-          for (int g = st.gemm_begin; g < st.gemm_end; ++g) {
-            const VmGemm& gm = P.gemms[g];
-            const uint32_t b_hi = gm.src ? hh : xh, b_lo = gm.src ? hl : xl;
-            const uint32_t d = tmem_base + (uint32_t)gm.acc_tile * NT;
-            for (int c0 = 0; c0 < gm.ksl; c0 += kSlotSlabs) {
-              const int nsl = min(kSlotSlabs, (int)gm.ksl - c0);
-              mbar_wait(bar_full + 8 * slot, phase);
-              tc_fence_after();
-              for (int j = 0; j < nsl; ++j) {
-                const uint32_t a_addr = ring_a + slot * kSlotBytes + j * kSlabBytes;
-                const uint32_t koff = (uint32_t)(gm.src_k16 + c0 + j) * 2u * TL::LBO;
-                uint64_t a_hi, a_lo, bd_hi, bd_lo;
-                if (P.dbg_flags & 1) {
-                  a_hi = make_smem_desc(a_addr, 128, 2048);
-                  a_lo = make_smem_desc(a_addr + 4096, 128, 2048);
-                  bd_hi = make_smem_desc(b_hi + koff, TL::SBO, TL::LBO);
-                  bd_lo = make_smem_desc(b_lo + koff, TL::SBO, TL::LBO);
-                } else {
-                  a_hi = make_smem_desc(a_addr, 2048, 128);
-                  a_lo = make_smem_desc(a_addr + 4096, 2048, 128);
-                  bd_hi = make_smem_desc(b_hi + koff, TL::LBO, TL::SBO);
-                  bd_lo = make_smem_desc(b_lo + koff, TL::LBO, TL::SBO);
+    // Warp-uniform loops; `elect.sync` picks the single issuing lane so the descriptors stay in
+    // uniform registers (no per-instruction convergence loops around UTCHMMA).
+    constexpr uint32_t idesc = make_idesc_f16(128, NT);
+    uint32_t slot = 0, phase = 0, act_phase = 0;
+    const bool swap = (P.dbg_flags & 1) != 0;
+    // descriptors are built once; the loops below only add to their (14-bit, >>4) address field
+    const uint64_t a_ring = swap ? make_smem_desc(smem_u32(ring), 128, 2048) : make_smem_desc(smem_u32(ring), 2048, 128);
+    const uint64_t b_x = swap ? make_smem_desc(smem_u32(x_hi), TL::SBO, TL::LBO) : make_smem_desc(smem_u32(x_hi), TL::LBO, TL::SBO);
+    const uint64_t b_h = swap ? make_smem_desc(smem_u32(h_hi), TL::SBO, TL::LBO) : make_smem_desc(smem_u32(h_hi), TL::LBO, TL::SBO);
+    const uint64_t x_lo_delta = TL::buf_bytes(P.kx16) >> 4, h_lo_delta = TL::buf_bytes(P.kh16) >> 4;
+    constexpr uint64_t kA_lo = 4096 >> 4, kA_slab = kSlabBytes >> 4, kA_slot = kSlotBytes >> 4;
+    constexpr uint64_t kB_slab = (2u * TL::LBO) >> 4;
+    for (int t = 0; t < P.n_steps; ++t) {
+      for (int s = 0; s < P.n_stages; ++s) {
+        const int g0 = P.stages[s].gemm_begin, g1 = P.stages[s].gemm_end;
+        mbar_wait(bar_act, act_phase);  // previous epilogue: activations written, TMEM drained
+        act_phase ^= 1;
+        tc_fence_after();
+        for (int g = g0; g < g1; ++g) {
+          const VmGemm gm = P.gemms[g];
+          const uint64_t lo_delta = gm.src ? h_lo_delta : x_lo_delta;
+          uint64_t bd = (gm.src ? b_h : b_x) + (uint64_t)gm.src_k16 * kB_slab;
+          const uint32_t d = tmem_base + (uint32_t)gm.acc_tile * NT;
+          uint32_t acc = gm.accumulate;
+          for (int c0 = 0; c0 < gm.ksl; c0 += kSlotSlabs) {
+            const int nsl = min(kSlotSlabs, (int)gm.ksl - c0);
+            mbar_wait(bar_full + 8 * slot, phase);
+            tc_fence_after();
+            if (elect_one()) {
+              uint64_t ad = a_ring + (uint64_t)slot * kA_slot;
+              uint64_t bj = bd;
+#pragma unroll
+              for (int j = 0; j < kSlotSlabs; ++j) {
+                if (j < nsl) {
+                  umma_f16(d, ad, bj, idesc, (j == 0) ? acc : 1u);
+                  umma_f16(d, ad, bj + lo_delta, idesc, 1u);
+                  umma_f16(d, ad + kA_lo, bj, idesc, 1u);
+                  ad += kA_slab;
+                  bj += kB_slab;
                 }
-                const uint32_t acc = (gm.accumulate || (c0 + j) > 0) ? 1u : 0u;
-                umma_f16(d, a_hi, bd_hi, idesc, acc);
-                umma_f16(d, a_hi, bd_lo, idesc, 1u);
-                umma_f16(d, a_lo, bd_hi, idesc, 1u);
               }
               umma_commit(bar_empty + 8 * slot);  // slot reusable once these MMAs retire
-              if (++slot == kSlots) { slot = 0; phase ^= 1; }
             }
+            __syncwarp();
+            acc = 1u;
+            bd += (uint64_t)nsl * kB_slab;
+            if (++slot == kSlots) { slot = 0; phase ^= 1; }
           }
-          umma_commit(bar_acc);  // accumulators of this stage complete
         }
+        if (elect_one()) umma_commit(bar_acc);  // accumulators of this stage complete
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ================================ epilogue warps ================================
     const int et = threadIdx.x - 64;                 // 0..127
@@ -302,26 +368,8 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
 
         switch (st.epi) {
           case EPI_ACT_H: {
-            for (int tile = 0; tile < st.ntiles; ++tile) {
-              const int f = tile * 128 + lf;
-              const bool vf = f < st.nfeat;
-              const float bias = P.bias[(st.bias_tile + tile) * 128 + lf];
-#pragma unroll 1
-              for (int c = 0; c < NT / 16; ++c) {
-                float v[16];
-                tmem_ld16(tacc + tile * NT + c * 16, v);
-                tmem_ld_wait();
-                if (vf) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    const int n = c * 16 + i, row = row0 + n;
-                    float x = v[i] + bias;
-                    if ((st.flags & SF_ADDEND) && row < N) x += P.addend[(trow + row) * P.Hd + f];
-                    TL::put(h_hi, h_lo, n, f, act_fn(x, st.act));
-                  }
-                }
-              }
-            }
+            if (st.act == ACT_ELU) epi_act_h<NT, ACT_ELU>(P, st, h_hi, h_lo, tacc, lf, row0, trow);
+            else epi_act_h<NT, ACT_RELU>(P, st, h_hi, h_lo, tacc, lf, row0, trow);
           } break;
 
           case EPI_STORE: {
@@ -354,28 +402,37 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
               const float bz = P.bias[(st.bias_tile + mt + tile) * 128 + lf];
               const float bin = P.bias[(st.bias_tile + 2 * mt + tile) * 128 + lf];
               const float bhn = P.bias[(st.bias_tile + 3 * mt + tile) * 128 + lf];
+              // previous belief in fp32: the start belief at t=0, else what this very thread stored at t-1
               const float* bprev = (t == 0) ? P.init_belief : (P.beliefs + (trow - N) * D);
 #pragma unroll 1
               for (int c = 0; c < NT / 16; ++c) {
-                float vr[16], vz[16], vi[16], vh[16];
+                float vr[16], vz[16], vi[16], vh[16], bo[16];
+                const int r0 = row0 + c * 16;
+                if (bprev) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) bo[i] = (vu && r0 + i < N) ? bprev[(size_t)(r0 + i) * D + u] : 0.f;
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) bo[i] = 0.f;
+                }
                 tmem_ld16(tacc + (tile)*NT + c * 16, vr);
                 tmem_ld16(tacc + (mt + tile) * NT + c * 16, vz);
                 tmem_ld16(tacc + (2 * mt + tile) * NT + c * 16, vi);
                 tmem_ld16(tacc + (3 * mt + tile) * NT + c * 16, vh);
                 tmem_ld_wait();
                 if (vu) {
+                  float bn[16];
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
-                    const int n = c * 16 + i, row = row0 + n;
-                    const bool vr_ = row < N;
                     const float r = sigmoid_f(vr[i] + br);
                     const float z = sigmoid_f(vz[i] + bz);
-                    const float nn = tanhf(vi[i] + bin + r * (vh[i] + bhn));
-                    const float bo = (vr_ && bprev) ? bprev[(size_t)row * D + u] : 0.f;
-                    const float bn = (1.f - z) * nn + z * bo;
-                    if (vr_) P.beliefs[(trow + row) * D + u] = bn;
-                    TL::put(x_hi, x_lo, n, u, bn);
+                    const float nn = tanh_f(vi[i] + bin + r * (vh[i] + bhn));
+                    bn[i] = (1.f - z) * nn + z * bo[i];
+                    TL::put(x_hi, x_lo, c * 16 + i, u, bn[i]);
                   }
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (r0 + i < N) P.beliefs[(trow + r0 + i) * D + u] = bn[i];
                 }
               }
             }
@@ -393,46 +450,67 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
             float* o_m = post ? P.post_m : P.prior_m;
             float* o_sd = post ? P.post_sd : P.prior_sd;
             const bool any_valid_in_warp = (q * 32) < S;
+            const bool want_kl = post && P.kl != nullptr;
+            const bool mask_next = (st.flags & SF_WRITES_STATE) && P.nonterm && has_next;
 #pragma unroll 1
             for (int c = 0; c < NT / 16; ++c) {
-              float vm[16], vs[16];
+              float vm[16], vs[16], e[16], pm[16], psd[16], nt[16];
+              const int r0 = row0 + c * 16;
+              const size_t o0 = (trow + r0) * S + j;
+              if (any_valid_in_warp) {
+                ldg16(e, eps + o0, S, r0, N, vj);
+                if (want_kl) {  // written by this same thread in EPI_PRIOR of this step
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const bool ok = vj && r0 + i < N;
+                    pm[i] = ok ? P.prior_m[o0 + (size_t)i * S] : 0.f;
+                    psd[i] = ok ? P.prior_sd[o0 + (size_t)i * S] : 1.f;
+                  }
+                }
+                if (mask_next) ldg16(nt, P.nonterm + trow + N + r0, 1, r0, N, true);
+              }
               tmem_ld16(tacc + c * 16, vm);
               tmem_ld16(tacc + NT + c * 16, vs);
               tmem_ld_wait();
               if (any_valid_in_warp) {
+                float smp[16], m[16], sd[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  const int n = c * 16 + i, row = row0 + n;
-                  const bool ok = vj && row < N;
-                  const size_t o = (trow + row) * S + j;
-                  const float m = vm[i] + bm;
-                  const float sd = softplus_f(vs[i] + bs) + P.min_std;
-                  const float e = ok ? eps[o] : 0.f;
-                  const float smp = m + sd * e;
-                  if (ok) {
-                    o_s[o] = smp;
-                    o_m[o] = m;
-                    o_sd[o] = sd;
-                  }
-                  if (post && P.kl) {
+                  m[i] = vm[i] + bm;
+                  sd[i] = softplus_f(vs[i] + bs) + P.min_std;
+                  smp[i] = m[i] + sd[i] * e[i];
+                }
+                if (want_kl) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
                     float klj = 0.f;
-                    if (ok) {
-                      const float pm = P.prior_m[o], psd = P.prior_sd[o];
-                      const float ratio = sd / psd, vr = ratio * ratio;
-                      const float dm = (m - pm) / psd;
+                    if (vj && r0 + i < N) {
+                      const float ratio = sd[i] / psd[i], vr = ratio * ratio;
+                      const float dm = (m[i] - pm[i]) / psd[i];
                       klj = 0.5f * (vr + dm * dm - 1.f - logf(vr));
                     }
 #pragma unroll
                     for (int sh = 16; sh > 0; sh >>= 1) klj += __shfl_xor_sync(0xffffffffu, klj, sh);
-                    if (lane == 0 && row < N) {
-                      if (S <= 32) P.kl[trow + row] = klj;
-                      else atomicAdd(&P.kl[trow + row], klj);
+                    if (lane == 0 && r0 + i < N) {
+                      if (S <= 32) P.kl[trow + r0 + i] = klj;
+                      else atomicAdd(&P.kl[trow + r0 + i], klj);
                     }
                   }
-                  if ((st.flags & SF_WRITES_STATE) && vj) {
-                    float sx = smp;
-                    if (P.nonterm && has_next && row < N) sx *= P.nonterm[trow + N + row];
-                    TL::put(x_hi, x_lo, n, D + j, sx);
+                }
+                if (vj) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    if (r0 + i < N) {
+                      const size_t o = o0 + (size_t)i * S;
+                      o_s[o] = smp[i];
+                      o_m[o] = m[i];
+                      o_sd[o] = sd[i];
+                    }
+                  }
+                  if (st.flags & SF_WRITES_STATE) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                      TL::put(x_hi, x_lo, c * 16 + i, D + j, mask_next ? smp[i] * nt[i] : smp[i]);
                   }
                 }
               }
@@ -440,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
             if ((st.flags & SF_LOADS_ACTION) && has_next) {
               for (int idx = et; idx < NT * A; idx += kEpiThreads) {
                 const int n = idx / A, k = idx - n * A, row = row0 + n;
-                if (row < N) TL::put(x_hi, x_lo, n, D + S + k, P.actions_in[(trow + N + row) * A + k]);
+                if (row < N) TL::put(x_hi, x_lo, n, D + S + k, __ldg(P.actions_in + (trow + N + row) * A + k));
               }
             }
           } break;
@@ -451,24 +529,24 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
             const float bm = P.bias[(st.bias_tile) * 128 + lf];
             const float bs = P.bias[(st.bias_tile + 1) * 128 + lf];
             const bool any_valid_in_warp = (q * 32) < A;
+            const float inv_ms = 1.f / P.a_mean_scale;
 #pragma unroll 1
             for (int c = 0; c < NT / 16; ++c) {
-              float vm[16], vs[16];
+              float vm[16], vs[16], e[16];
+              const int r0 = row0 + c * 16;
+              const size_t o0 = (trow + r0) * A + j;
+              if (any_valid_in_warp) ldg16(e, P.eps_action + o0, A, r0, N, vj);
               tmem_ld16(tacc + c * 16, vm);
               tmem_ld16(tacc + NT + c * 16, vs);
               tmem_ld_wait();
               if (any_valid_in_warp && vj) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  const int n = c * 16 + i, row = row0 + n;
-                  const bool ok = row < N;
-                  const size_t o = (trow + row) * A + j;
-                  const float mean = P.a_mean_scale * tanhf((vm[i] + bm) / P.a_mean_scale);
+                  const float mean = P.a_mean_scale * tanh_f((vm[i] + bm) * inv_ms);
                   const float sd = softplus_f(vs[i] + bs + P.a_init_std) + P.a_min_std;
-                  const float e = ok ? P.eps_action[o] : 0.f;
-                  const float a = tanhf(mean + sd * e);
-                  if (ok && P.actions_out) P.actions_out[o] = a;
-                  TL::put(x_hi, x_lo, n, D + S + j, a);
+                  const float a = tanh_f(mean + sd * e[i]);
+                  if (r0 + i < N && P.actions_out) P.actions_out[o0 + (size_t)i * A] = a;
+                  TL::put(x_hi, x_lo, c * 16 + i, D + S + j, a);
                 }
               }
             }

@@ -1,0 +1,168 @@
+"""Drop-in `TransitionModel` (reference: algorithms/repo/models/rssm.py:8-184).
+
+Same constructor, same submodule / parameter names (so `state_dict()` round-trips with the
+reference's checkpoints, dreamer.py:501-547) and the same methods; the time loops run inside one
+persistent sm_100a kernel launch (repo_b200/csrc/vm.cuh) instead of ~50 Python iterations of
+~45 ATen dispatches.  `obs_step` / `img_step` are the north_star's names for the cell methods.
+
+Noise: the reference draws `torch.randn_like` inline (rssm.py:49,62) and `Normal.rsample` inside
+the policy (actor_critic.py:97-102).  Here the same standard-normal tensors are drawn up front with
+`torch.randn` on the device (optionally in the reference's exact per-step order, `rng_compat`),
+or injected by the caller (`eps_*=` keyword arguments) — that is how parity tests feed identical
+noise to the reference, the oracle and this module.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _named(module: nn.Module) -> Dict[str, torch.Tensor]:
+    return {k: v for k, v in module.named_parameters()}
+
+
+class TransitionModel(nn.Module):
+    def __init__(self, belief_size, state_size, action_size, hidden_size, embedding_size,
+                 activation_function="relu", min_std_dev=0.1):
+        super().__init__()
+        ops.act_kind(activation_function)  # raise early on unsupported activations
+        self.activation_function = activation_function
+        self.min_std_dev = min_std_dev
+        self.belief_size, self.state_size, self.action_size = belief_size, state_size, action_size
+        self.hidden_size, self.embedding_size = hidden_size, embedding_size
+        # parameter holders: identical names, shapes, init order and init distribution as rssm.py:21-32
+        self.fc_embed_state_action = nn.Linear(state_size + action_size, belief_size)
+        self.rnn = nn.GRUCell(belief_size, belief_size)
+        self.fc_embed_belief_prior = nn.Linear(belief_size, hidden_size)
+        self.fc_state_prior = nn.Linear(hidden_size, 2 * state_size)
+        self.fc_embed_belief_posterior = nn.Linear(belief_size + embedding_size, hidden_size)
+        self.fc_state_posterior = nn.Linear(hidden_size, 2 * state_size)
+        # draw noise step by step in the reference's order (bit-identical RNG consumption on the
+        # same device/seed) instead of one batched draw per call
+        self.rng_compat = False
+        self._ws: Dict[str, torch.Tensor] = {}
+        self.last_kl: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ noise
+    def _randn(self, T: int, B: int, F: int, like: torch.Tensor) -> torch.Tensor:
+        return torch.randn(T, B, F, device=like.device, dtype=torch.float32)
+
+    def _observe_noise(self, T1, B, like, with_obs):
+        S = self.state_size
+        if not self.rng_compat:
+            return self._randn(T1, B, S, like), (self._randn(T1, B, S, like) if with_obs else None)
+        pri, post = [], []
+        for _ in range(T1):  # rssm.py:121-132: prior draw then posterior draw, every step
+            pri.append(torch.randn(B, S, device=like.device))
+            if with_obs:
+                post.append(torch.randn(B, S, device=like.device))
+        return torch.stack(pri), (torch.stack(post) if with_obs else None)
+
+    def _imagine_noise(self, T, N, like):
+        S, A = self.state_size, self.action_size
+        if not self.rng_compat:
+            return self._randn(T, N, A, like), self._randn(T, N, S, like)
+        ea, ep = [], []
+        for _ in range(T):  # rssm.py:170-176: action rsample then prior randn_like
+            ea.append(torch.randn(N, A, device=like.device))
+            ep.append(torch.randn(N, S, device=like.device))
+        return torch.stack(ea), torch.stack(ep)
+
+    # ------------------------------------------------------------------ reference API
+    def observe(self, prev_belief: torch.Tensor, prev_state: torch.Tensor, actions: torch.Tensor,
+                observations: Optional[torch.Tensor] = None, nonterminals: Optional[torch.Tensor] = None,
+                *, eps_prior: Optional[torch.Tensor] = None, eps_post: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        """rssm.py:76-146.  Returns [beliefs, prior_states, prior_means, prior_std_devs,
+        posterior_states, posterior_means, posterior_std_devs] (first four when observations is None),
+        each with T-1 leading entries.  The per-(t,b) KL(posterior||prior) computed in the same launch is
+        left in `self.last_kl` (T-1, B)."""
+        T1, B = actions.shape[0], actions.shape[1]
+        with_obs = observations is not None
+        if eps_prior is None:
+            eps_prior, eps_post_d = self._observe_noise(T1, B, actions, with_obs)
+            if eps_post is None:
+                eps_post = eps_post_d
+        elif with_obs and eps_post is None:
+            raise ValueError("eps_post must be given together with eps_prior when observations are passed")
+        self._require_no_grad("observe", [prev_belief, prev_state, actions, observations])
+        outs, kl, ws = ops.observe_fwd(_named(self), prev_belief, prev_state, actions, observations, nonterminals,
+                                       eps_prior, eps_post, act=self.activation_function, min_std=self.min_std_dev,
+                                       workspace=self._ws.get("observe"))
+        self._ws["observe"] = ws
+        self.last_kl = kl
+        return outs
+
+    def imagine(self, prev_belief, prev_state, policy, horizon, *, eps_action=None, eps_prior=None,
+                reward_model=None, value_model=None, gamma=0.99, lambda_=0.95, return_extras=False):
+        """rssm.py:148-184.  `policy` must be an ActorModel-like module (fc1..fc5, `_mean_scale`, `_init_std`,
+        `_min_std`: actor_critic.py:50-74); anything else raises (no fallback).  With `reward_model` /
+        `value_model` (fc1..fc4) the same launch also produces rewards, values and lambda-returns
+        (`return_extras=True` returns them as a dict after the reference's 4-list)."""
+        for need in ("fc1", "fc2", "fc3", "fc4", "fc5", "_mean_scale", "_init_std", "_min_std"):
+            if not hasattr(policy, need):
+                raise TypeError(f"imagine: policy {type(policy).__name__} lacks {need!r}; only ActorModel-style "
+                                "tanh-Normal policies are supported by the fused kernel")
+        if getattr(policy, "_dist", "tanh_normal") not in ("tanh_normal", "elu", "relu"):
+            # the trainers pass the activation name in the `dist` slot (dreamer.py:99-105); any value ends
+            # up as a tanh-Normal policy in the reference, so only reject things we cannot interpret
+            raise TypeError(f"imagine: unsupported policy dist {policy._dist!r}")
+        N, T = prev_belief.shape[0], horizon - 1
+        if eps_action is None or eps_prior is None:
+            ea, ep = self._imagine_noise(T, N, prev_belief)
+            eps_action = ea if eps_action is None else eps_action
+            eps_prior = ep if eps_prior is None else eps_prior
+        self._require_no_grad("imagine", [prev_belief, prev_state], extra=[policy, reward_model, value_model])
+        out = ops.imagine_fwd(_named(self), _named(policy),
+                              _named(reward_model) if reward_model is not None else None,
+                              _named(value_model) if value_model is not None else None,
+                              prev_belief, prev_state, eps_action, eps_prior, horizon,
+                              act=self.activation_function, min_std=self.min_std_dev,
+                              mean_scale=float(policy._mean_scale), init_std=float(policy._init_std),
+                              actor_min_std=float(policy._min_std), gamma=gamma, lambda_=lambda_,
+                              workspace=self._ws.get("imagine"))
+        self._ws["imagine"] = out.pop("workspace")
+        traj = [out["beliefs"], out["prior_states"], out["prior_means"], out["prior_std_devs"]]
+        if return_extras:
+            return traj, out
+        return traj
+
+    # north_star vocabulary
+    def img_step(self, prev_belief, state, action, *, eps=None):
+        belief = self.compute_belief(prev_belief, state, action)
+        return (belief,) + tuple(self.compute_prior_state(belief, eps=eps))
+
+    def obs_step(self, prev_belief, state, action, observation, *, eps_prior=None, eps_post=None):
+        belief = self.compute_belief(prev_belief, state, action)
+        prior = self.compute_prior_state(belief, eps=eps_prior)
+        post = self.compute_posterior_state(belief, observation, eps=eps_post)
+        return (belief,) + tuple(prior) + tuple(post)
+
+    # cell-level methods (rssm.py:34-64) run as one-step programs of the same machine
+    def compute_belief(self, prev_belief, state, action):
+        outs = self.observe(prev_belief, state, action.unsqueeze(0),
+                            eps_prior=torch.zeros(1, state.shape[0], self.state_size, device=state.device))
+        return outs[0][0]
+
+    def compute_prior_state(self, belief, *, eps=None):
+        raise NotImplementedError("compute_prior_state as a standalone call is not wired yet; use observe/imagine")
+
+    def compute_posterior_state(self, belief, observation, *, eps=None):
+        raise NotImplementedError("compute_posterior_state as a standalone call is not wired yet; use observe/imagine")
+
+    # ------------------------------------------------------------------ helpers
+    def _require_no_grad(self, what, tensors, extra=()):
+        if not torch.is_grad_enabled():
+            return
+        needs = any(p.requires_grad for p in self.parameters())
+        needs = needs or any(t is not None and t.requires_grad for t in tensors)
+        for m in extra:
+            if m is not None:
+                needs = needs or any(p.requires_grad for p in m.parameters())
+        if needs:
+            raise NotImplementedError(
+                f"TransitionModel.{what}: the backward kernels are not built yet — call under torch.no_grad() "
+                "(refusing to return silently non-differentiable outputs)")
