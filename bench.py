@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — imagined latent steps/s of the RSSM hot path (BASELINE.json metric) on N GPUs.
+
+A "step" = one pass of the hot path over one batch of synthetic input: `TransitionModel.imagine`
+(actor -> GRU belief -> prior head, reward + value heads on every imagined state, lambda-return) over
+ROWS start states per GPU for horizon 15, RePo default sizes (belief 200, state 30, hidden 200,
+action 6).  Workload = BASELINE configs[4] (large-batch imagination sweep) at a fixed per-GPU row
+count (weak scaling: rows are independent, no data-path collective); the RePo default-shape numbers
+(configs[1]: 2450 rows x 14 steps imagine, 49 x 50 observe) ride along under "default_shape".
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun launches N ranks for N > 1)
+  python bench.py --impl reference ...                     (CPU arm: the oracle port of the reference)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_STEP = 1_440_000      # algorithmic forward FLOPs per imagined latent step
+BYTES_PER_STEP = 1_312         # algorithmic HBM bytes per imagined latent step
+HORIZON = 15
+DIMS = dict(belief=200, state=30, action=6, hidden=200, embed=1024)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="repo_b200", choices=["repo_b200", "reference"])
+    ap.add_argument("--rows-per-gpu", type=int, default=65536)
+    ap.add_argument("--cpu-rows", type=int, default=4096, help="rows per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1384.0), d.get("hbm_gbs", 6553.0), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_imagine_step(O, params, actor, reward, value, x):
+    outs = O.imagine(params, actor, x["belief"], x["state"], x["eps_action"], x["eps_prior"], HORIZON)
+    T, N = outs[0].shape[:2]
+    rew = O.head_forward(reward, outs[0].flatten(0, 1), outs[1].flatten(0, 1)).reshape(T, N)
+    val = O.head_forward(value, outs[0].flatten(0, 1), outs[1].flatten(0, 1)).reshape(T, N)
+    return O.imagine_returns(rew, val, 0.99, 0.95)
+
+
+def cpu_baseline(rows, steps, warmup):
+    """The oracle (a torch-CPU restatement of the reference: nn.Linear/GRUCell arithmetic via ATen/MKL on
+    all host threads) timed on a bounded sample of the same workload."""
+    from oracle import rssm_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = O.make_transition_params(0)
+    actor = O.make_mlp_params(1, 230, 200, 12, 4)
+    reward = O.make_mlp_params(2, 230, 200, 1, 3)
+    value = O.make_mlp_params(3, 230, 200, 1, 3)
+    x = O.make_imagine_inputs(4, rows, HORIZON)
+    with torch.no_grad():
+        for _ in range(warmup):
+            cpu_imagine_step(O, params, actor, reward, value, x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_imagine_step(O, params, actor, reward, value, x)
+        dt = time.perf_counter() - t0
+    return rows * (HORIZON - 1) * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(a.steps, 10))
+    v, sec, cores = cpu_baseline(a.cpu_rows, steps, max(1, min(a.warmup, 2)))
+    sample = f"{a.cpu_rows} start rows x {HORIZON - 1} steps per step (bounded sample of the {a.rows_per_gpu}-row/GPU workload)"
+    line = {
+        "impl": "reference", "metric": "imagined latent steps/sec", "value": v, "unit": "steps/s", "n_gpus": a.gpus,
+        "steps": steps, "warmup": max(1, min(a.warmup, 2)), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a),
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a):
+    return {"workload": f"imagine sweep (BASELINE configs[4]): {a.rows_per_gpu} start states per GPU x horizon {HORIZON}, "
+                        "RePo RSSM default sizes (belief 200, state 30, hidden 200, action 6), actor + reward + value heads + lambda-return",
+            "rows_per_gpu": a.rows_per_gpu, "horizon": HORIZON, "parallelism": f"rows sharded x{a.gpus}, no data-path collective",
+            "l2": "per-step inputs+outputs (1.2 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(a):
+    import torch.distributed as dist
+    from oracle import rssm_oracle as O      # seeded synthetic weights/inputs only (numpy RandomState)
+    from repo_b200 import ops, _lib
+    from repo_b200.models import ActorModel, RewardModel, ValueModel
+    from repo_b200.rssm import TransitionModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, T = a.rows_per_gpu, HORIZON - 1
+    D, S, A, Hd = DIMS["belief"], DIMS["state"], DIMS["action"], DIMS["hidden"]
+    # random-init weights of the reference architecture (seeded numpy; every rank holds a replica)
+    model = TransitionModel(D, S, A, Hd, DIMS["embed"], "elu").to(dev)
+    model.load_state_dict(O.make_transition_params(0))
+    actor = ActorModel(D, S, Hd, A, "elu").to(dev)
+    actor.load_state_dict(O.make_mlp_params(1, D + S, Hd, 2 * A, 4))
+    reward = RewardModel(D, S, Hd, "elu").to(dev)
+    reward.load_state_dict(O.make_mlp_params(2, D + S, Hd, 1, 3))
+    value = ValueModel(D, S, Hd, "elu").to(dev)
+    value.load_state_dict(O.make_mlp_params(3, D + S, Hd, 1, 3))
+    named = lambda m: {k: v.detach() for k, v in m.named_parameters()}
+    P, PA, PR, PV = named(model), named(actor), named(reward), named(value)
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    belief = (torch.randn(N, D, device=dev, generator=g) * 0.3).clamp_(-1, 1)
+    state = torch.randn(N, S, device=dev, generator=g)
+    eps_a = torch.randn(T, N, A, device=dev, generator=g)
+    eps_p = torch.randn(T, N, S, device=dev, generator=g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ws = None
+
+    def step():
+        nonlocal ws
+        out = ops.imagine_fwd(P, PA, PR, PV, belief, state, eps_a, eps_p, HORIZON, workspace=ws)  # packs weights every step
+        ws = out["workspace"]
+        return out
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # kernel-only duration of the layer machine (roofline numerator): events around each launch
+    kms = []
+    for _ in range(5):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        ops.imagine_fwd(P, PA, PR, PV, belief, state, eps_a, eps_p, HORIZON, workspace=ws, packed=True)
+        k1.record()
+        torch.cuda.synchronize()
+        kms.append(k0.elapsed_time(k1))
+    kernel_ms = statistics.median(kms)
+
+    # ---- end to end through the module API with HOST start states ----
+    hb = belief.cpu().pin_memory()
+    hs = state.cpu().pin_memory()
+    hret = torch.empty(T - 1, N, dtype=torch.float32).pin_memory()
+    db, ds = torch.empty_like(belief), torch.empty_like(state)
+
+    def e2e_step():
+        db.copy_(hb, non_blocking=True)
+        ds.copy_(hs, non_blocking=True)
+        with torch.no_grad():   # the public call: noise is drawn on the device inside imagine()
+            traj, extra = model.imagine(db, ds, actor, HORIZON, reward_model=reward, value_model=value, return_extras=True)
+        hret.copy_(extra["returns"], non_blocking=True)
+        return traj
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(a.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, e2e_ms, kernel_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms = [float(v) for v in t.tolist()]
+
+    # ---- RePo default shapes (configs[1]) : forward latency of the two kernels ----
+    default_shape = None
+    if rank == 0:
+        x = O.make_imagine_inputs(5, 2450, HORIZON)
+        xa = [x["belief"].to(dev), x["state"].to(dev), x["eps_action"].to(dev), x["eps_prior"].to(dev)]
+        xo = O.make_observe_inputs(6, 50, 50)
+        go = lambda k: xo[k].to(dev)
+        oa = [go("prev_belief"), go("prev_state"), go("actions"), go("embeds"), go("nonterms"), go("eps_prior"), go("eps_post")]
+
+        def timeit(fn, n=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(n):
+                fn()
+            s1.record()
+            torch.cuda.synchronize()
+            return s0.elapsed_time(s1) / n
+
+        img_ms = timeit(lambda: ops.imagine_fwd(P, PA, PR, PV, *xa, HORIZON))
+        obs_ms = timeit(lambda: ops.observe_fwd(P, *oa))
+        default_shape = {"imagine_2450x14_ms": img_ms, "imagine_steps_per_s": 2450 * 14 / img_ms * 1e3,
+                         "observe_49x50_ms": obs_ms, "observe_row_steps_per_s": 2450 / obs_ms * 1e3}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_steps = N * T * world
+    value_sps = total_steps * a.steps / (ms / 1e3)
+    e2e_sps = total_steps * a.steps / (e2e_ms / 1e3)
+    peak_tf, peak_gbs, peak_src = peaks()
+    achieved_tf = N * T * FLOP_PER_STEP / (kernel_ms / 1e3) / 1e12
+    line = {
+        "metric": "imagined latent steps/sec", "value": value_sps, "unit": "steps/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16x3 split (fp32-grade products, fp32 accumulate) on tcgen05",
+        "data": "synthetic", "config": workload_config(a),
+        "clocks": clocks,
+        "e2e": {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": N * (D + S) * 4, "d2h_bytes_per_step": (T - 1) * N * 4,
+                "ms_per_step": e2e_ms / a.steps,
+                "what": "TransitionModel.imagine(host start states -> pinned H2D, device noise draw, fused kernel) + D2H of lambda-returns"},
+        "gpu_launches": 3 * a.steps,  # per rank per timed loop: pack_weights + pack_bias + rssm_vm_kernel
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "traffic": 1_251_737_000 if N == 65536 else None, "kernel": "rssm_vm_kernel<64>", "kernel_ms": kernel_ms,
+                     "algorithmic_flop_per_step": FLOP_PER_STEP, "algorithmic_bytes_per_step": BYTES_PER_STEP,
+                     "hbm_gbs_achieved": N * T * BYTES_PER_STEP / (kernel_ms / 1e3) / 1e9, "hbm_peak_gbs": peak_gbs,
+                     "peak_source": peak_src,
+                     "note": "algorithmic fp32 FLOPs; the kernel issues 3 fp16 MMAs per product (hi*hi+lo*hi+hi*lo) on 128-feature tiles"},
+        "default_shape": default_shape,
+    }
+    if not a.no_cpu_baseline and world == 1:
+        v, sec, cores = cpu_baseline(2450, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                                "sample": "RePo default shape: 2450 start rows x 14 steps, 3 timed passes of the oracle (torch CPU fp32)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_gpu(a)
+
+
+if __name__ == "__main__":
+    main()

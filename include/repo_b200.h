@@ -91,6 +91,13 @@ int repo_b200_observe_fwd(const repo_b200_dims* dims, const repo_b200_rssm_weigh
                           int act_kind, float min_std_dev, void* workspace, size_t workspace_bytes, int flags,
                           int row_tile, void* stream);
 
+/* ---- head: RewardModel.forward (decoder.py:189-195) / ValueModel.forward (actor_critic.py:20-26):
+ * [belief|state] -> 3 x (Linear + act) -> Linear(1), squeezed.  belief (N,D), state (N,S), out (N). */
+size_t repo_b200_head_workspace_bytes(const repo_b200_dims* dims);
+int repo_b200_head_fwd(const repo_b200_dims* dims, const repo_b200_mlp_weights* head, const float* belief,
+                       const float* state, float* out, int n_rows, int act_kind, void* workspace,
+                       size_t workspace_bytes, int flags, int row_tile, void* stream);
+
 /* ---- linear: y = x W^T + b on the same machine (nn.Linear as used by rssm.py:23-32); building block
  * and bring-up test.  x (rows, in_f) ld = x_ld; w (out_f, in_f); b (out_f) nullable; y ld = y_ld. */
 size_t repo_b200_linear_workspace_bytes(int in_features, int out_features);

@@ -38,6 +38,7 @@ EXPORTS = [
     "repo_b200_imagine_workspace_bytes", "repo_b200_imagine_fwd",
     "repo_b200_observe_workspace_bytes", "repo_b200_observe_fwd",
     "repo_b200_linear_workspace_bytes", "repo_b200_linear_fwd",
+    "repo_b200_head_workspace_bytes", "repo_b200_head_fwd",
 ]
 
 _lib = None
@@ -70,6 +71,10 @@ def lib():
     L.repo_b200_observe_fwd.argtypes = (
         [C.POINTER(Dims), C.POINTER(RssmWeights)] + [vp] * 15 + [ci, ci, ci, cf, vp, sz, ci, ci, vp])
     L.repo_b200_observe_fwd.restype = ci
+    L.repo_b200_head_workspace_bytes.argtypes = [C.POINTER(Dims)]
+    L.repo_b200_head_workspace_bytes.restype = sz
+    L.repo_b200_head_fwd.argtypes = [C.POINTER(Dims), C.POINTER(MlpWeights), vp, vp, vp, ci, ci, vp, sz, ci, ci, vp]
+    L.repo_b200_head_fwd.restype = ci
     L.repo_b200_linear_workspace_bytes.argtypes = [ci, ci]
     L.repo_b200_linear_workspace_bytes.restype = sz
     L.repo_b200_linear_fwd.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp, ci, vp, sz, ci, vp]

@@ -365,11 +365,11 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   if (!W || !actor) return fail(-1, "imagine: rssm / actor weights are required");
   if (actor->n_layers != 5) return fail(-1, "imagine: policy must be an ActorModel with fc1..fc5 (got %d layers)", actor->n_layers);
   if ((reward && reward->n_layers != 4) || (value && value->n_layers != 4)) return fail(-1, "imagine: reward/value heads must have fc1..fc4");
+  if (horizon < 1 || n_rows < 0) return fail(-1, "imagine: bad horizon %d / rows %d", horizon, n_rows);
+  if (horizon == 1 || n_rows == 0) return 0;  // nothing to roll out (the reference returns empty stacks)
   if (!start_belief || !start_state || !eps_action || !eps_prior || !beliefs || !prior_states || !prior_means || !prior_std_devs)
     return fail(-1, "imagine: NULL input/output pointer");
   if ((reward && !rewards) || (value && !values)) return fail(-1, "imagine: rewards/values output missing");
-  if (horizon < 1 || n_rows < 0) return fail(-1, "imagine: bad horizon %d / rows %d", horizon, n_rows);
-  if (horizon == 1 || n_rows == 0) return 0;  // reference returns empty stacks' worth of work
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Builder b;
   build_imagine(b, d, W, actor, reward, value, act_kind);
@@ -388,6 +388,38 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   P.rewards = reward ? rewards : nullptr;
   P.values = value ? values : nullptr;
   P.returns = (reward && value) ? returns : nullptr;
+  return launch(P, b.max_acc_tiles, row_tile, st);
+}
+
+size_t repo_b200_head_workspace_bytes(const repo_b200_dims* d) {
+  if (check_dims(d)) return 0;
+  repo_b200_mlp_weights m{};
+  Builder b;
+  set_dims(b.P, d);
+  b.scalar_head(&m, d->belief, d->state, d->hidden, ACT_ELU, 0);
+  return align_up(b.packed_bytes(), 256);
+}
+
+int repo_b200_head_fwd(const repo_b200_dims* d, const repo_b200_mlp_weights* head, const float* belief,
+                       const float* state, float* out, int n_rows, int act_kind, void* ws, size_t ws_bytes,
+                       int flags, int row_tile, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_act(act_kind))) return rc;
+  if (n_rows < 0) return fail(-1, "head: bad row count %d", n_rows);
+  if (n_rows == 0) return 0;
+  if (!head || head->n_layers != 4) return fail(-1, "head: expected fc1..fc4");
+  if (!belief || !state || !out) return fail(-1, "head: NULL input/output pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Builder b;
+  set_dims(b.P, d);
+  b.scalar_head(head, d->belief, d->state, d->hidden, act_kind, 0);
+  if ((rc = b.bind_and_pack(ws, ws_bytes, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
+  VmParams& P = b.P;
+  P.n_steps = 1;
+  P.N = n_rows;
+  P.init_belief = belief; P.init_state = state;
+  P.rewards = out;
   return launch(P, b.max_acc_tiles, row_tile, st);
 }
 
@@ -411,12 +443,12 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   int rc = check_dims(d);
   if (rc) return rc;
   if ((rc = check_act(act_kind))) return rc;
+  if (t1 < 0 || batch < 0) return fail(-1, "observe: bad sizes");
+  if (t1 == 0 || batch == 0) return 0;
   if (!W || !prev_belief || !prev_state || !actions || !eps_prior || !beliefs || !prior_states || !prior_means || !prior_std_devs)
     return fail(-1, "observe: NULL input/output pointer");
   const bool with_obs = embeds != nullptr;
   if (with_obs && (!eps_post || !post_states || !post_means || !post_std_devs)) return fail(-1, "observe: posterior buffers missing");
-  if (t1 < 0 || batch < 0) return fail(-1, "observe: bad sizes");
-  if (t1 == 0 || batch == 0) return 0;
   if (ws_bytes < repo_b200_observe_workspace_bytes(d, t1, batch)) return fail(-4, "observe: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Builder b;

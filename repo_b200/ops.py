@@ -138,6 +138,8 @@ def observe_fwd(params: Dict[str, torch.Tensor], prev_belief, prev_state, action
     mk = lambda f: torch.empty(T1, B, f, device=dev, dtype=torch.float32)
     outs = [mk(d.belief)] + [mk(d.state) for _ in range(6 if with_obs else 3)]
     kl = torch.empty(T1, B, device=dev, dtype=torch.float32) if (with_obs and want_kl) else None
+    if T1 == 0 or B == 0:
+        return outs, kl, workspace
     need = L.repo_b200_observe_workspace_bytes(C.byref(d), T1, B)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -180,6 +182,9 @@ def imagine_fwd(params: Dict[str, torch.Tensor], actor: Dict[str, torch.Tensor],
     out["rewards"] = mk(T, N) if Rm is not None else None
     out["values"] = mk(T, N) if Vm is not None else None
     out["returns"] = mk(max(T - 1, 0), N) if (Rm is not None and Vm is not None) else None
+    if N == 0 or T == 0:
+        out["workspace"] = workspace
+        return out
     need = L.repo_b200_imagine_workspace_bytes(C.byref(d))
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -194,4 +199,27 @@ def imagine_fwd(params: Dict[str, torch.Tensor], actor: Dict[str, torch.Tensor],
         row_tile, _stream())
     _lib.check(rc, "repo_b200_imagine_fwd")
     out["workspace"] = workspace
+    return out
+
+
+def head_fwd(head: Dict[str, torch.Tensor], belief: torch.Tensor, state: torch.Tensor, act: str = "elu",
+             row_tile: int = 0) -> torch.Tensor:
+    """RewardModel / ValueModel forward on (N, D), (N, S) -> (N,)  (decoder.py:189-195, actor_critic.py:20-26)."""
+    L = _lib.lib()
+    keep = _Keep()
+    N = belief.shape[0]
+    D, S, Hd = belief.shape[1], state.shape[1], head["fc1.weight"].shape[0]
+    if head["fc1.weight"].shape[1] != D + S:
+        raise RuntimeError(f"head: fc1 expects {head['fc1.weight'].shape[1]} inputs, got belief {D} + state {S}")
+    d = Dims(D, S, 1, Hd, 1)
+    M = mlp_struct(head, 4, keep, "head")
+    belief = _chk(belief, "belief", (N, D))
+    state = _chk(state, "state", (N, S))
+    out = torch.empty(N, device=belief.device, dtype=torch.float32)
+    if N == 0:
+        return out
+    ws = torch.empty(L.repo_b200_head_workspace_bytes(C.byref(d)), dtype=torch.uint8, device=belief.device)
+    rc = L.repo_b200_head_fwd(C.byref(d), C.byref(M), _ptr(belief), _ptr(state), _ptr(out), N, act_kind(act),
+                              _ptr(ws), ws.numel(), 0, row_tile, _stream())
+    _lib.check(rc, "repo_b200_head_fwd")
     return out
