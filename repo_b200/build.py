@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "api.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("api.cu", "vm.cuh", "pack.cuh", "ptx.cuh")] + [
+DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))) + [
     os.path.join(os.path.dirname(HERE), "include", "repo_b200.h")]
 OUT = os.path.join(HERE, "librepo_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

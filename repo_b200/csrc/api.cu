@@ -12,6 +12,7 @@
 #include "../../include/repo_b200.h"
 #include "pack.cuh"
 #include "vm.cuh"
+#include "rows.cuh"
 
 using namespace rb;
 
@@ -292,6 +293,192 @@ void build_linear(Builder& b, const float* w, const float* bias, int ld, int col
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// ============================================================================================
+// "rows on M" machine (rows.cuh): program builder
+// ============================================================================================
+inline int r16(int v) { return (v + 15) / 16 * 16; }
+
+struct RBuilder {
+  RowsParams P;
+  PackRowsArgs pack;
+  BiasRowsArgs bias;
+  int n_gemms = 0, n_stages = 0, n_bias = 0, blk = 0;
+  size_t w_bytes = 0;
+  bool overflow = false;
+
+  RBuilder() {
+    std::memset(&P, 0, sizeof(P));
+    std::memset(&pack, 0, sizeof(pack));
+    std::memset(&bias, 0, sizeof(bias));
+  }
+  struct Seg { int src, n, dst; };
+
+  void gemm(const float* w, int ld, std::initializer_list<Seg> segs, int n_pad, int col0, int ncols, int kofs, int ksl,
+            int a_src, int a_k16, int acc_col, int accumulate) {
+    if (n_gemms >= kRMaxGemms || pack.n_jobs >= kMaxRowsJobs || n_pad > 256 || n_pad * 64 > kRSlotBytes) { overflow = true; return; }
+    RGemm& g = P.gemms[n_gemms++];
+    g.w_off16 = (uint32_t)(w_bytes / 16);
+    g.slab_bytes16 = (uint16_t)(n_pad * 4);
+    g.n = (uint16_t)n_pad;
+    g.ksl = (uint8_t)ksl;
+    g.a_src = (uint8_t)a_src;
+    g.a_k16 = (uint8_t)a_k16;
+    g.accumulate = (uint8_t)accumulate;
+    g.acc_col = (uint16_t)acc_col;
+    PackRowsJob& j = pack.jobs[pack.n_jobs++];
+    j.w = w; j.ld = ld; j.col0 = col0; j.ncols = ncols; j.kofs = kofs; j.ksl = ksl; j.n_pad = n_pad;
+    j.nseg = 0;
+    for (const Seg& s : segs) { j.seg_src[j.nseg] = s.src; j.seg_n[j.nseg] = s.n; j.seg_dst[j.nseg] = s.dst; ++j.nseg; }
+    j.dst_off16 = g.w_off16;
+    j.blk0 = blk;
+    blk += ksl;
+    w_bytes += (size_t)ksl * n_pad * 64;
+  }
+  void bias_job(const float* a, int a_off, const float* b, int b_off, int n, int n_pad) {
+    if (bias.n_jobs >= 64) { overflow = true; return; }
+    BiasRowsJob& j = bias.jobs[bias.n_jobs++];
+    j.a = a; j.b = b; j.a_off = a_off; j.b_off = b_off; j.n = n; j.n_pad = n_pad; j.dst_off = n_bias;
+    n_bias += n_pad;
+  }
+  RStage& begin_stage() {
+    RStage& s = P.stages[std::min(n_stages, kRMaxStages - 1)];
+    if (n_stages >= kRMaxStages) overflow = true;
+    s.gemm_begin = (uint8_t)n_gemms;
+    s.bias_off = (uint16_t)n_bias;
+    return s;
+  }
+  void end_stage(RStage& s, int epi, int flags, int nfeat, int act, int unit0 = 0, int width = 0) {
+    s.gemm_end = (uint8_t)n_gemms;
+    s.epi = (uint8_t)epi; s.flags = (uint8_t)flags; s.act = (uint8_t)act;
+    s.nfeat = (uint16_t)nfeat; s.unit0 = (uint16_t)unit0; s.width = (uint16_t)width;
+    ++n_stages;
+  }
+  void dense_to_h(const float* w, const float* b, int ld, int out_f, int col0, int ncols, int kofs, int ksl, int a_src,
+                  int a_k16, int act, int flags = 0) {
+    RStage& s = begin_stage();
+    gemm(w, ld, {{0, out_f, 0}}, r16(out_f), col0, ncols, kofs, ksl, a_src, a_k16, 0, 0);
+    bias_job(b, 0, nullptr, 0, out_f, r16(out_f));
+    end_stage(s, R_ACT_H, flags, out_f, act);
+  }
+  void gaussian_head(const float* w, const float* b, int ld, int n, int ksl, int epi, int flags) {
+    const int np = r16(n);
+    RStage& s = begin_stage();
+    gemm(w, ld, {{0, n, 0}, {n, n, np}}, 2 * np, 0, ld, 0, ksl, 1, 0, 0, 0);
+    bias_job(b, 0, nullptr, 0, n, np);
+    bias_job(b, n, nullptr, 0, n, np);
+    end_stage(s, epi, flags, n, 0, 0, np);
+  }
+  void belief_update(const repo_b200_rssm_weights* W, int D, int S, int A, int act) {
+    const int kD16 = cdiv(D, 16), kx16 = cdiv(D + S + A, 16), kSA0 = D / 16;
+    dense_to_h(W->fc_embed_state_action_w, W->fc_embed_state_action_b, S + A, D, 0, S + A, D - 16 * kSA0, kx16 - kSA0,
+               0, kSA0, act);
+    const int Wd = std::min(64, r16(D));
+    for (int u0 = 0; u0 < D; u0 += Wd) {
+      const int nu = std::min(Wd, D - u0);
+      RStage& s = begin_stage();
+      gemm(W->rnn_w_ih, D, {{u0, nu, 0}, {D + u0, nu, Wd}, {2 * D + u0, nu, 2 * Wd}}, 3 * Wd, 0, D, 0, kD16, 1, 0, 0, 0);
+      gemm(W->rnn_w_hh, D, {{u0, nu, 0}, {D + u0, nu, Wd}}, 2 * Wd, 0, D, 0, kD16, 0, 0, 0, 1);
+      gemm(W->rnn_w_hh, D, {{2 * D + u0, nu, 0}}, Wd, 0, D, 0, kD16, 0, 0, 3 * Wd, 0);
+      bias_job(W->rnn_b_ih, u0, W->rnn_b_hh, u0, nu, Wd);
+      bias_job(W->rnn_b_ih, D + u0, W->rnn_b_hh, D + u0, nu, Wd);
+      bias_job(W->rnn_b_ih, 2 * D + u0, nullptr, 0, nu, Wd);
+      bias_job(W->rnn_b_hh, 2 * D + u0, nullptr, 0, nu, Wd);
+      end_stage(s, R_GRU, (u0 + Wd >= D) ? RF_LAST_CHUNK : 0, nu, 0, u0, Wd);
+    }
+  }
+  void scalar_head(const repo_b200_mlp_weights* M, int D, int S, int Hd, int act, int flags) {
+    const int kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);
+    dense_to_h(M->w[0], M->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, act);
+    dense_to_h(M->w[1], M->b[1], Hd, Hd, 0, Hd, 0, kH16, 1, 0, act);
+    dense_to_h(M->w[2], M->b[2], Hd, Hd, 0, Hd, 0, kH16, 1, 0, act);
+    RStage& s = begin_stage();
+    gemm(M->w[3], Hd, {{0, 1, 0}}, 16, 0, Hd, 0, kH16, 1, 0, 0, 0);
+    bias_job(M->b[3], 0, nullptr, 0, 1, 16);
+    end_stage(s, R_SCALAR, flags, 1, 0);
+  }
+  size_t packed_bytes() const { return align_up_(w_bytes, 256) + (size_t)n_bias * sizeof(float); }
+  static size_t align_up_(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+  int bind_and_pack(void* ws, size_t ws_bytes, bool do_pack, cudaStream_t st) {
+    if (overflow) return fail(-3, "rows program too large (stages %d gemms %d)", n_stages, n_gemms);
+    if (ws_bytes < packed_bytes()) return fail(-4, "workspace too small: need %zu bytes, got %zu", packed_bytes(), ws_bytes);
+    uint8_t* wb = static_cast<uint8_t*>(ws);
+    float* bb = reinterpret_cast<float*>(wb + align_up_(w_bytes, 256));
+    P.v.wblob = wb;
+    P.v.bias = bb;
+    P.n_rstages = n_stages;
+    if (do_pack) {
+      pack.wblob = wb;
+      bias.bias = bb;
+      pack_rows_weights_kernel<<<blk, 256, 0, st>>>(pack);
+      pack_rows_bias_kernel<<<bias.n_jobs, 256, 0, st>>>(bias);
+      CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+  }
+};
+
+void rows_set_dims(RowsParams& P, const repo_b200_dims* d) {
+  set_dims(P.v, d);
+  P.kh_cols = 8 * P.v.kh16;
+}
+
+void build_imagine_rows(RBuilder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W,
+                        const repo_b200_mlp_weights* actor, const repo_b200_mlp_weights* reward,
+                        const repo_b200_mlp_weights* value, int act) {
+  const int D = d->belief, S = d->state, A = d->action, Hd = d->hidden;
+  const int kD16 = cdiv(D, 16), kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);
+  rows_set_dims(b.P, d);
+  b.dense_to_h(actor->w[0], actor->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, ACT_ELU);
+  for (int i = 1; i < 4; ++i) b.dense_to_h(actor->w[i], actor->b[i], Hd, Hd, 0, Hd, 0, kH16, 1, 0, ACT_ELU);
+  b.gaussian_head(actor->w[4], actor->b[4], Hd, A, kH16, R_ACTION, 0);
+  b.belief_update(W, D, S, A, act);
+  b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act);
+  b.gaussian_head(W->fc_state_prior_w, W->fc_state_prior_b, Hd, S, kH16, R_PRIOR, SF_WRITES_STATE);
+  if (reward) b.scalar_head(reward, D, S, Hd, act, 0);
+  if (value) b.scalar_head(value, D, S, Hd, act, SF_SCALAR_VALUE);
+}
+
+void build_observe_rows(RBuilder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W, bool with_obs, int act) {
+  const int D = d->belief, S = d->state, A = d->action, Hd = d->hidden, E = d->embed;
+  const int kD16 = cdiv(D, 16), kH16 = cdiv(Hd, 16);
+  rows_set_dims(b.P, d);
+  b.belief_update(W, D, S, A, act);
+  b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act);
+  b.gaussian_head(W->fc_state_prior_w, W->fc_state_prior_b, Hd, S, kH16, R_PRIOR,
+                  with_obs ? 0 : (SF_WRITES_STATE | SF_LOADS_ACTION));
+  if (with_obs) {
+    b.dense_to_h(W->fc_embed_belief_posterior_w, W->fc_embed_belief_posterior_b, D + E, Hd, 0, D, 0, kD16, 0, 0, act,
+                 SF_ADDEND);
+    b.gaussian_head(W->fc_state_posterior_w, W->fc_state_posterior_b, Hd, S, kH16, R_POST,
+                    SF_WRITES_STATE | SF_LOADS_ACTION);
+  }
+}
+
+int launch_rows(const RowsParams& P, cudaStream_t st) {
+  if (P.v.N <= 0 || P.v.n_steps <= 0) return 0;
+  const size_t smem = rows_smem_bytes(P.v.kx16);
+  if (smem > 227 * 1024) return fail(-5, "rows kernel: shared memory budget exceeded (%zu bytes)", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CUDA_OK(cudaFuncSetAttribute(rssm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  rssm_rows_kernel<<<cdiv(P.v.N, kRowsM), kRowsThreads, smem, st>>>(P);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// 128-row tiles pay off once they fill the machine; below that the flexible row tiles of vm.cuh win
+bool use_rows_kernel(int n_rows, int row_tile) {
+  if (row_tile == 128) return true;
+  if (row_tile == 16 || row_tile == 32 || row_tile == 64) return false;
+  if (g_dbg_flags & 2) return false;
+  if (g_dbg_flags & 4) return true;
+  return n_rows >= 128 * std::max(1, sm_count()) / 2;
+}
+
+
 int run_linear(const float* x, int x_ld, int rows, int in_f, const float* w, int w_ld, int w_col0, const float* b,
                int out_f, float* y, int y_ld, void* ws, size_t ws_bytes, int row_tile, cudaStream_t st) {
   if (in_f < 1 || in_f > 1900) return fail(-1, "linear: in_features %d unsupported (1..1900)", in_f);
@@ -348,7 +535,9 @@ size_t repo_b200_imagine_workspace_bytes(const repo_b200_dims* d) {
   repo_b200_mlp_weights m{};
   Builder b;
   build_imagine(b, d, &W, &m, &m, &m, ACT_ELU);
-  return align_up(b.packed_bytes(), 256);
+  RBuilder rb_;
+  build_imagine_rows(rb_, d, &W, &m, &m, &m, ACT_ELU);
+  return align_up(std::max(b.packed_bytes(), rb_.packed_bytes()), 256);
 }
 
 int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const repo_b200_mlp_weights* actor,
@@ -371,10 +560,17 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
     return fail(-1, "imagine: NULL input/output pointer");
   if ((reward && !rewards) || (value && !values)) return fail(-1, "imagine: rewards/values output missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool rows = use_rows_kernel(n_rows, row_tile);
   Builder b;
-  build_imagine(b, d, W, actor, reward, value, act_kind);
-  if ((rc = b.bind_and_pack(ws, ws_bytes, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
-  VmParams& P = b.P;
+  RBuilder rbld;
+  if (rows) {
+    build_imagine_rows(rbld, d, W, actor, reward, value, act_kind);
+    if ((rc = rbld.bind_and_pack(ws, ws_bytes, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
+  } else {
+    build_imagine(b, d, W, actor, reward, value, act_kind);
+    if ((rc = b.bind_and_pack(ws, ws_bytes, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
+  }
+  VmParams& P = rows ? rbld.P.v : b.P;
   P.n_steps = horizon - 1;
   P.N = n_rows;
   P.min_std = min_std;
@@ -388,6 +584,7 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   P.rewards = reward ? rewards : nullptr;
   P.values = value ? values : nullptr;
   P.returns = (reward && value) ? returns : nullptr;
+  if (rows) return launch_rows(rbld.P, st);
   return launch(P, b.max_acc_tiles, row_tile, st);
 }
 
@@ -423,12 +620,18 @@ int repo_b200_head_fwd(const repo_b200_dims* d, const repo_b200_mlp_weights* hea
   return launch(P, b.max_acc_tiles, row_tile, st);
 }
 
-size_t repo_b200_observe_workspace_bytes(const repo_b200_dims* d, int t1, int batch) {
-  if (check_dims(d)) return 0;
+static size_t observe_main_bytes(const repo_b200_dims* d) {
   repo_b200_rssm_weights W{};
   Builder b;
   build_observe(b, d, &W, true, ACT_ELU);
-  const size_t main = align_up(b.packed_bytes(), 256);
+  RBuilder rb_;
+  build_observe_rows(rb_, d, &W, true, ACT_ELU);
+  return align_up(std::max(b.packed_bytes(), rb_.packed_bytes()), 256);
+}
+
+size_t repo_b200_observe_workspace_bytes(const repo_b200_dims* d, int t1, int batch) {
+  if (check_dims(d)) return 0;
+  const size_t main = observe_main_bytes(d);
   const size_t lin = align_up(repo_b200_linear_workspace_bytes(d->embed, d->hidden), 256);
   const size_t addend = align_up((size_t)std::max(t1, 0) * std::max(batch, 0) * d->hidden * sizeof(float), 256);
   return main + lin + addend;
@@ -451,12 +654,19 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   if (with_obs && (!eps_post || !post_states || !post_means || !post_std_devs)) return fail(-1, "observe: posterior buffers missing");
   if (ws_bytes < repo_b200_observe_workspace_bytes(d, t1, batch)) return fail(-4, "observe: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool rows = use_rows_kernel(batch, row_tile);
   Builder b;
-  build_observe(b, d, W, with_obs, act_kind);
-  const size_t main = align_up(b.packed_bytes(), 256);
+  RBuilder rbld;
+  const size_t main = observe_main_bytes(d);
   const size_t lin = align_up(repo_b200_linear_workspace_bytes(d->embed, d->hidden), 256);
   uint8_t* base = static_cast<uint8_t*>(ws);
-  if ((rc = b.bind_and_pack(base, main, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
+  if (rows) {
+    build_observe_rows(rbld, d, W, with_obs, act_kind);
+    if ((rc = rbld.bind_and_pack(base, main, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
+  } else {
+    build_observe(b, d, W, with_obs, act_kind);
+    if ((rc = b.bind_and_pack(base, main, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
+  }
   float* addend = reinterpret_cast<float*>(base + main + lin);
   if (with_obs) {
     // hoisted, non-recurrent half of the posterior layer: all (t, b) rows in one pass
@@ -464,7 +674,7 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
                     d->belief, nullptr, d->hidden, addend, d->hidden, base + main, lin, 0, st);
     if (rc) return rc;
   }
-  VmParams& P = b.P;
+  VmParams& P = rows ? rbld.P.v : b.P;
   P.n_steps = t1;
   P.N = batch;
   P.min_std = min_std;
@@ -475,6 +685,7 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   P.beliefs = beliefs; P.prior_s = prior_states; P.prior_m = prior_means; P.prior_sd = prior_std_devs;
   P.post_s = post_states; P.post_m = post_means; P.post_sd = post_std_devs;
   P.kl = with_obs ? kl : nullptr;
+  if (rows) return launch_rows(rbld.P, st);
   if (P.kl && d->state > 32) CUDA_OK(cudaMemsetAsync(kl, 0, (size_t)t1 * batch * sizeof(float), st));
   return launch(P, b.max_acc_tiles, row_tile, st);
 }

@@ -70,4 +70,72 @@ __global__ void __launch_bounds__(128) pack_bias_kernel(const __grid_constant__ 
   a.bias[j.dst_tile * 128 + i] = v;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// "rows on M" machine (rows.cuh): weights are the B operand.  One job = one GEMM's weight matrix
+// W'(n_pad x 16*ksl), assembled from up to three row segments of the source (e.g. the r/z/n
+// gate rows of one GRU unit chunk).  Slab = [hi: 2 k-groups x n_pad rows x 16 B][lo: same].
+struct PackRowsJob {
+  const float* w;
+  int ld, col0, ncols, kofs, ksl, n_pad, nseg;
+  int seg_src[3], seg_n[3], seg_dst[3];
+  uint32_t dst_off16;  // destination offset / 16
+  int blk0;
+};
+struct BiasRowsJob {   // dst[dst_off + i] = (i < n) ? a[a_off+i] (+ b[b_off+i]) : 0   for i < n_pad
+  const float* a;
+  const float* b;
+  int a_off, b_off, n, n_pad, dst_off;
+};
+constexpr int kMaxRowsJobs = 40;
+struct PackRowsArgs {
+  PackRowsJob jobs[kMaxRowsJobs];
+  int n_jobs;
+  uint8_t* wblob;
+};
+struct BiasRowsArgs {
+  BiasRowsJob jobs[64];
+  int n_jobs;
+  float* bias;
+};
+
+__global__ void __launch_bounds__(256) pack_rows_weights_kernel(const __grid_constant__ PackRowsArgs a) {
+  int ji = 0;
+  while (ji + 1 < a.n_jobs && (int)blockIdx.x >= a.jobs[ji + 1].blk0) ++ji;
+  const PackRowsJob& j = a.jobs[ji];
+  const int slab = blockIdx.x - j.blk0;
+  const int m = threadIdx.x;
+  if (m >= j.n_pad) return;
+  int src_row = -1;
+  for (int s = 0; s < j.nseg; ++s)
+    if (m >= j.seg_dst[s] && m < j.seg_dst[s] + j.seg_n[s]) src_row = j.seg_src[s] + (m - j.seg_dst[s]);
+  uint8_t* dst = a.wblob + (size_t)j.dst_off16 * 16 + (size_t)slab * j.n_pad * 64;
+  const float* src = j.w + (size_t)(src_row < 0 ? 0 : src_row) * j.ld + j.col0;
+#pragma unroll
+  for (int kg = 0; kg < 2; ++kg) {
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const int kc = slab * 16 + kg * 8 + kk - j.kofs;
+      const float v = (src_row >= 0 && kc >= 0 && kc < j.ncols) ? src[kc] : 0.f;
+      split_f16(v, hi[kk], lo[kk]);
+    }
+    *reinterpret_cast<uint4*>(dst + kg * j.n_pad * 16 + m * 16) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + j.n_pad * 32 + kg * j.n_pad * 16 + m * 16) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_rows_bias_kernel(const __grid_constant__ BiasRowsArgs a) {
+  const BiasRowsJob& j = a.jobs[blockIdx.x];
+  for (int i = threadIdx.x; i < j.n_pad; i += blockDim.x) {
+    float v = 0.f;
+    if (i < j.n) {
+      if (j.a) v = j.a[j.a_off + i];
+      if (j.b) v += j.b[j.b_off + i];
+    }
+    a.bias[j.dst_off + i] = v;
+  }
+}
+
 }  // namespace rb

@@ -53,7 +53,7 @@ def test_observe():
         want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"],
                          x["eps_prior"], x["eps_post"])
         g = lambda k: None if x[k] is None else x[k].to(dev)
-        for rt in (0, 64):
+        for rt in (64, 128):
             outs, kl, _ = ops.observe_fwd(cu(params), g("prev_belief"), g("prev_state"), g("actions"), g("embeds"),
                                           g("nonterms"), g("eps_prior"), g("eps_post"), row_tile=rt)
             torch.cuda.synchronize()
@@ -68,7 +68,7 @@ def test_imagine():
         params, actor, reward, value, x, gold, meta = C.imagine_case(name)
         H = int(meta["H"])
         want = O.imagine(params, actor, x["belief"], x["state"], x["eps_action"], x["eps_prior"], H)
-        for rt in (0, 64):
+        for rt in (64, 128):
             out = ops.imagine_fwd(cu(params), cu(actor), cu(reward), cu(value), x["belief"].to(dev), x["state"].to(dev),
                                   x["eps_action"].to(dev), x["eps_prior"].to(dev), H, row_tile=rt)
             torch.cuda.synchronize()
@@ -80,11 +80,11 @@ def test_imagine():
 
 def quick_timing():
     params, actor, reward, value, x, gold, meta = C.imagine_case("imagine_N8_H15")
-    for N in (2450, 16384, 65536):
+    for N in (2450, 16384, 75776):
         xi = O.make_imagine_inputs(1, N, 15)
         a = [cu(params), cu(actor), cu(reward), cu(value), xi["belief"].to(dev), xi["state"].to(dev),
              xi["eps_action"].to(dev), xi["eps_prior"].to(dev), 15]
-        for rt in (16, 32, 64):
+        for rt in (32, 64, 128):
             out = ops.imagine_fwd(*a, row_tile=rt)
             ws = out["workspace"]
             torch.cuda.synchronize()
@@ -99,7 +99,7 @@ def quick_timing():
     p2, x2, _, _ = C.observe_case("observe_default_tail")
     g = lambda k: x2[k].to(dev)
     a = [cu(p2), g("prev_belief"), g("prev_state"), g("actions"), g("embeds"), g("nonterms"), g("eps_prior"), g("eps_post")]
-    for rt in (16, 32, 64):
+    for rt in (16, 64, 128):
         ops.observe_fwd(*a, row_tile=rt)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -49,7 +49,7 @@ def run_imagine(ops, dev, params, actor, reward, value, x, H, row_tile=0):
                            x["eps_action"].to(dev), x["eps_prior"].to(dev), H, row_tile=row_tile)
 
 
-@pytest.mark.parametrize("row_tile", [0, 16, 32, 64])
+@pytest.mark.parametrize("row_tile", [0, 16, 32, 64, 128])
 @pytest.mark.parametrize("name", C.OBSERVE_CASES)
 def test_observe_vs_golden_and_oracle(ops, dev, name, row_tile):
     params, x, gold, meta = C.observe_case(name)
@@ -70,7 +70,7 @@ def test_observe_vs_golden_and_oracle(ops, dev, name, row_tile):
         assert kl is None
 
 
-@pytest.mark.parametrize("row_tile", [0, 16, 32, 64])
+@pytest.mark.parametrize("row_tile", [0, 16, 32, 64, 128])
 @pytest.mark.parametrize("name", C.IMAGINE_CASES)
 def test_imagine_vs_golden_and_oracle(ops, dev, name, row_tile):
     params, actor, reward, value, x, gold, meta = C.imagine_case(name)
@@ -141,6 +141,12 @@ def test_rows_are_independent_and_tile_invariant(ops, dev):
         other = _big_imagine(ops, dev, N, row_tile=rt)
         for nm in C.IMG_NAMES + ["rewards", "values", "returns"]:
             assert torch.equal(base[nm], other[nm]), (nm, rt)
+    # the 128-row "rows on M" kernel is a different MMA shape: same math, not bit-identical
+    rows = _big_imagine(ops, dev, N, row_tile=128)
+    rows_shuf = _big_imagine(ops, dev, N, row_tile=128, perm=perm)
+    for nm in C.IMG_NAMES + ["rewards", "values", "returns", "actions"]:
+        close(rows[nm], base[nm].cpu(), f"rows-kernel {nm}", rtol=1e-4, atol=2e-5)
+        assert torch.equal(rows[nm][:, perm.to(dev)], rows_shuf[nm]), nm
 
 
 def test_lambda_return_consistent_with_own_heads(ops, dev):
