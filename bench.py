@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 FLOP_PER_STEP = 1_440_000      # algorithmic forward FLOPs per imagined latent step
 BYTES_PER_STEP = 1_312         # algorithmic HBM bytes per imagined latent step
 HORIZON = 15
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture (profiles/), by rows
+TRAFFIC_BYTES = {}
 DIMS = dict(belief=200, state=30, action=6, hidden=200, embed=1024)
 
 
@@ -37,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="repo_b200", choices=["repo_b200", "reference"])
-    ap.add_argument("--rows-per-gpu", type=int, default=65536)
+    ap.add_argument("--rows-per-gpu", type=int, default=75776, help="start states per GPU; default = 4 waves of 148 SMs x 128-row tiles")
     ap.add_argument("--cpu-rows", type=int, default=4096, help="rows per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -147,7 +149,7 @@ def workload_config(a):
     return {"workload": f"imagine sweep (BASELINE configs[4]): {a.rows_per_gpu} start states per GPU x horizon {HORIZON}, "
                         "RePo RSSM default sizes (belief 200, state 30, hidden 200, action 6), actor + reward + value heads + lambda-return",
             "rows_per_gpu": a.rows_per_gpu, "horizon": HORIZON, "parallelism": f"rows sharded x{a.gpus}, no data-path collective",
-            "l2": "per-step inputs+outputs (1.2 GB) exceed the 126 MB L2; no explicit flush"}
+            "l2": "per-step inputs+outputs (~1.4 GB) exceed the 126 MB L2; no explicit flush"}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -308,11 +310,11 @@ def run_gpu(a):
                 "what": "TransitionModel.imagine(host start states -> pinned H2D, device noise draw, fused kernel) + D2H of lambda-returns"},
         "gpu_launches": 3 * a.steps,  # per rank per timed loop: pack_weights + pack_bias + rssm_vm_kernel
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": 1_251_737_000 if N == 65536 else None, "kernel": "rssm_vm_kernel<64>", "kernel_ms": kernel_ms,
+                     "traffic": TRAFFIC_BYTES.get(N), "kernel": "rssm_rows_kernel", "kernel_ms": kernel_ms,
                      "algorithmic_flop_per_step": FLOP_PER_STEP, "algorithmic_bytes_per_step": BYTES_PER_STEP,
                      "hbm_gbs_achieved": N * T * BYTES_PER_STEP / (kernel_ms / 1e3) / 1e9, "hbm_peak_gbs": peak_gbs,
                      "peak_source": peak_src,
-                     "note": "algorithmic fp32 FLOPs; the kernel issues 3 fp16 MMAs per product (hi*hi+lo*hi+hi*lo) on 128-feature tiles"},
+                     "note": "algorithmic fp32 FLOPs; the kernel issues 3 fp16 MMAs per product (hi*hi+lo*hi+hi*lo), so tensor-pipe work is ~3.3x the algorithmic count"},
         "default_shape": default_shape,
     }
     if not a.no_cpu_baseline and world == 1:

@@ -57,6 +57,8 @@ const char* repo_b200_last_error(void);
 int repo_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* bring-up only: bit0 swaps LBO/SBO in the tcgen05 shared-memory descriptors */
 void repo_b200_debug_flags(int flags);
+/* profiling only: CTA 0 of the rows kernel writes [step][stage][2] clock64 stamps into this device buffer (NULL = off) */
+void repo_b200_debug_clock(void* device_buffer);
 
 /* ---- imagine: TransitionModel.imagine (rssm.py:148-184) with policy = ActorModel.get_action
  * (actor_critic.py:97-102), fused with RewardModel / ValueModel on every imagined state

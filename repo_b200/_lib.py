@@ -34,7 +34,7 @@ class MlpWeights(C.Structure):
 
 
 EXPORTS = [
-    "repo_b200_version", "repo_b200_last_error", "repo_b200_device_info", "repo_b200_debug_flags",
+    "repo_b200_version", "repo_b200_last_error", "repo_b200_device_info", "repo_b200_debug_flags", "repo_b200_debug_clock",
     "repo_b200_imagine_workspace_bytes", "repo_b200_imagine_fwd",
     "repo_b200_observe_workspace_bytes", "repo_b200_observe_fwd",
     "repo_b200_linear_workspace_bytes", "repo_b200_linear_fwd",
@@ -60,6 +60,8 @@ def lib():
     L.repo_b200_device_info.restype = ci
     L.repo_b200_debug_flags.argtypes = [ci]
     L.repo_b200_debug_flags.restype = None
+    L.repo_b200_debug_clock.argtypes = [vp]
+    L.repo_b200_debug_clock.restype = None
     L.repo_b200_imagine_workspace_bytes.argtypes = [C.POINTER(Dims)]
     L.repo_b200_imagine_workspace_bytes.restype = sz
     L.repo_b200_imagine_fwd.argtypes = (

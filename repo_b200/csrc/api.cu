@@ -176,6 +176,7 @@ struct Builder {
 };
 
 int g_dbg_flags = 0;
+long long* g_dbg_clock = nullptr;
 int g_sm_count = 0;
 int sm_count() {
   if (g_sm_count == 0) {
@@ -218,6 +219,7 @@ int pick_row_tile(int rows, int max_acc_tiles, int kx16, int kh16, int requested
 
 int launch(const VmParams& P, int max_acc_tiles, int requested, cudaStream_t st) {
   if (P.N <= 0 || P.n_steps <= 0) return 0;
+  if (requested == 128) requested = 64;  // shapes the 128-row kernel does not take
   const int nt = pick_row_tile(P.N, max_acc_tiles, P.kx16, P.kh16, requested);
   if (max_acc_tiles * nt > (int)kTmemCols) return fail(-5, "TMEM budget exceeded (%d accumulator tiles x %d rows)", max_acc_tiles, nt);
   switch (nt) {
@@ -349,6 +351,8 @@ struct RBuilder {
   }
   void end_stage(RStage& s, int epi, int flags, int nfeat, int act, int unit0 = 0, int width = 0) {
     s.gemm_end = (uint8_t)n_gemms;
+    s.bias_n = (uint16_t)(n_bias - s.bias_off);
+    if (s.bias_n > kBiasStage) overflow = true;
     s.epi = (uint8_t)epi; s.flags = (uint8_t)flags; s.act = (uint8_t)act;
     s.nfeat = (uint16_t)nfeat; s.unit0 = (uint16_t)unit0; s.width = (uint16_t)width;
     ++n_stages;
@@ -390,11 +394,13 @@ struct RBuilder {
     const int kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);
     dense_to_h(M->w[0], M->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, act);
     dense_to_h(M->w[1], M->b[1], Hd, Hd, 0, Hd, 0, kH16, 1, 0, act);
-    dense_to_h(M->w[2], M->b[2], Hd, Hd, 0, Hd, 0, kH16, 1, 0, act);
+    // fc3 + fc4 in one stage: the epilogue reduces act(fc3) against fc4's single weight row in fp32
     RStage& s = begin_stage();
-    gemm(M->w[3], Hd, {{0, 1, 0}}, 16, 0, Hd, 0, kH16, 1, 0, 0, 0);
+    gemm(M->w[2], Hd, {{0, Hd, 0}}, r16(Hd), 0, Hd, 0, kH16, 1, 0, 0, 0);
+    bias_job(M->b[2], 0, nullptr, 0, Hd, r16(Hd));
+    bias_job(M->w[3], 0, nullptr, 0, Hd, r16(Hd));
     bias_job(M->b[3], 0, nullptr, 0, 1, 16);
-    end_stage(s, R_SCALAR, flags, 1, 0);
+    end_stage(s, R_ACT_DOT, flags, Hd, act);
   }
   size_t packed_bytes() const { return align_up_(w_bytes, 256) + (size_t)n_bias * sizeof(float); }
   static size_t align_up_(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -464,13 +470,17 @@ int launch_rows(const RowsParams& P, cudaStream_t st) {
     CUDA_OK(cudaFuncSetAttribute(rssm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  rssm_rows_kernel<<<cdiv(P.v.N, kRowsM), kRowsThreads, smem, st>>>(P);
+  RowsParams Q = P;
+  Q.v.dbg_flags = g_dbg_flags;
+  Q.v.dbg_clock = g_dbg_clock;
+  rssm_rows_kernel<<<cdiv(P.v.N, kRowsM), kRowsThreads, smem, st>>>(Q);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 // 128-row tiles pay off once they fill the machine; below that the flexible row tiles of vm.cuh win
-bool use_rows_kernel(int n_rows, int row_tile) {
+bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
+  if (d->state > 32 || d->action > 16) return false;  // the 128-row kernel keeps one row's Gaussian heads in registers
   if (row_tile == 128) return true;
   if (row_tile == 16 || row_tile == 32 || row_tile == 64) return false;
   if (g_dbg_flags & 2) return false;
@@ -504,6 +514,7 @@ extern "C" {
 
 int repo_b200_version(void) { return 1; }
 void repo_b200_debug_flags(int flags) { g_dbg_flags = flags; }
+void repo_b200_debug_clock(void* device_buffer) { g_dbg_clock = static_cast<long long*>(device_buffer); }
 const char* repo_b200_last_error(void) { return g_err; }
 
 int repo_b200_device_info(int* sms, int* major, int* minor) {
@@ -560,7 +571,7 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
     return fail(-1, "imagine: NULL input/output pointer");
   if ((reward && !rewards) || (value && !values)) return fail(-1, "imagine: rewards/values output missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool rows = use_rows_kernel(n_rows, row_tile);
+  const bool rows = use_rows_kernel(d, n_rows, row_tile);
   Builder b;
   RBuilder rbld;
   if (rows) {
@@ -654,7 +665,7 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   if (with_obs && (!eps_post || !post_states || !post_means || !post_std_devs)) return fail(-1, "observe: posterior buffers missing");
   if (ws_bytes < repo_b200_observe_workspace_bytes(d, t1, batch)) return fail(-4, "observe: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool rows = use_rows_kernel(batch, row_tile);
+  const bool rows = use_rows_kernel(d, batch, row_tile);
   Builder b;
   RBuilder rbld;
   const size_t main = observe_main_bytes(d);

@@ -16,20 +16,22 @@
 //   accumulators                    TMEM columns [256,512).
 // x*W = hi*hi + lo*hi + hi*lo (three MMAs, fp32 accumulate) as in vm.cuh.
 //
-// Warps: 0 = weight loader, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (two warps per TMEM lane
-// quadrant; they split the columns of wide layers).
+// Warps: 0 = weight loader, 1 = MMA issuer + TMEM owner (warpgroup 0 gives its registers away with
+// setmaxnreg), 4..11 = epilogue (two warps per TMEM lane quadrant; they split the columns of wide
+// layers) running with 208 registers (128*80 + 256*208 <= the 168*384 registers the CTA was launched with).
 #pragma once
 #include "vm.cuh"
 
 namespace rb {
 
 constexpr int kRowsM = 128;
-constexpr int kRowsThreads = 320;
+constexpr int kRowsThreads = 384;   // warpgroup 0: loader, MMA issuer, 2 spare; warpgroups 1-2: epilogue
 constexpr int kRowsEpiThreads = 256;
 constexpr int kRSlotBytes = 32768;
 constexpr int kRSlots = 3;
 constexpr int kRMaxStages = 32;
 constexpr int kRMaxGemms = 56;
+constexpr int kBiasStage = 512;        // floats per smem bias staging buffer (double-buffered)
 constexpr uint32_t kAccCol = 256;     // accumulators live at TMEM columns [256, 512)
 constexpr uint32_t kXLBO = kRowsM * 16;  // bytes between k-groups of X (128 rows x 16 B)
 
@@ -40,6 +42,7 @@ enum RowsEpi : uint8_t {
   R_PRIOR = 3,
   R_POST = 4,
   R_SCALAR = 5,
+  R_ACT_DOT = 6,  // last hidden layer of a scalar head fused with its 1-output layer: out = w . act(acc + b) + b0
 };
 enum RowsFlags : uint8_t { RF_LAST_CHUNK = 16 };  // plus SF_* from vm.cuh
 
@@ -62,7 +65,7 @@ struct RStage {
   uint16_t bias_off;   // float offset into the bias blob
   uint16_t unit0;      // R_GRU: first unit of the chunk
   uint16_t width;      // R_GRU: padded units per chunk (gate stride in the accumulator); heads: padded half width
-  uint16_t pad1;
+  uint16_t bias_n;     // floats this stage reads from the bias blob (staged in smem by the epilogue warps)
 };
 
 struct RowsParams {
@@ -122,7 +125,7 @@ __device__ __forceinline__ void x_put8(uint8_t* hi, uint8_t* lo, int row, int kg
 }
 
 __host__ __device__ inline size_t rows_smem_bytes(int kx16) {
-  return (size_t)kRSlots * kRSlotBytes + 2 * (size_t)kx16 * 2 * kXLBO + 256;
+  return (size_t)kRSlots * kRSlotBytes + 2 * (size_t)kx16 * 2 * kXLBO + 1024 + 2 * kBiasStage * sizeof(float);
 }
 
 // 16 contiguous floats of one row (guarded tail / alignment handled outside the fast path)
@@ -139,14 +142,22 @@ __device__ __forceinline__ void ld_row16(float* dst, const float* base, int n_va
     for (int i = 0; i < 16; ++i) dst[i] = (row_ok && i < n_valid) ? base[i] : 0.f;
   }
 }
-// 16 floats every lane reads alike (bias blob; offsets are multiples of 16 floats -> 64-byte aligned)
+// 16 floats every lane reads alike, from the smem bias staging buffer (broadcast LDS.128)
 __device__ __forceinline__ void ld_uni16(float* dst, const float* base) {
   const float4* p = reinterpret_cast<const float4*>(base);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 v = __ldg(p + i);
+    const float4 v = p[i];
     dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
   }
+}
+// state pair (k even) of one row: one 4-byte store per half
+__device__ __forceinline__ void x_put2(uint8_t* hi, uint8_t* lo, int row, int k, float v0, float v1) {
+  uint32_t h, l;
+  split2_f16(v0, v1, h, l);
+  const uint32_t o = x_off(row, k);
+  *reinterpret_cast<uint32_t*>(hi + o) = h;
+  *reinterpret_cast<uint32_t*>(lo + o) = l;
 }
 __device__ __forceinline__ void st_row16(float* dst, const float* v, int n_valid) {
   if (n_valid >= 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
@@ -168,32 +179,46 @@ __device__ __forceinline__ float act_bf(float x) {
 
 // H = act(acc + bias (+ addend)): this warp handles 16-column chunks ch = half, half+2, ...
 // Pad columns need no guard: their weight rows and bias are zero, so they come out as act(0) = 0.
-template <int ACT>
-__device__ __forceinline__ void rows_act_h(const RowsParams& P, const RStage& st, uint32_t tacc, uint32_t th_hi,
-                                           uint32_t th_lo, int half, int row, bool row_ok, size_t trow) {
+// The TMEM load of the next chunk is issued before the current one is processed (latency hidden).
+// DOT: instead of storing H, reduce it against a weight vector (the scalar head's last layer).
+template <int ACT, bool DOT>
+__device__ __forceinline__ float rows_act_h(const RowsParams& P, const RStage& st, const float* bias, uint32_t tacc,
+                                            uint32_t th_hi, uint32_t th_lo, int half, int row, bool row_ok,
+                                            size_t trow) {
   const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
   const bool addend = (st.flags & SF_ADDEND) != 0;
-  const float* bias = P.v.bias + st.bias_off;
+  const float* wdot = bias + nch * 16;  // DOT: the 1-output layer's weight row follows the bias
+  const float* adrow = addend ? P.v.addend + (trow + row) * P.v.Hd : nullptr;
+  float dot = 0.f;
+  float ad[16];
+  if (addend && half < nch) ld_row16(ad, adrow + half * 16, nfeat - half * 16, row_ok);
   for (int ch = half; ch < nch; ch += 2) {
     float v[16], bz[16];
     const int f0 = ch * 16;
     tmem_ld16(tacc + f0, v);
     ld_uni16(bz, bias + f0);
     if (addend) {
-      float ad[16];
-      ld_row16(ad, P.v.addend + (trow + row) * P.v.Hd + f0, nfeat - f0, row_ok);
 #pragma unroll
       for (int i = 0; i < 16; ++i) bz[i] += ad[i];
+      if (ch + 2 < nch) ld_row16(ad, adrow + f0 + 32, nfeat - f0 - 32, row_ok);  // next chunk's rows: in flight
     }
     tmem_ld_wait();
-    uint32_t hi[8], lo[8];
+    if (DOT) {
+      float w[16];
+      ld_uni16(w, wdot + f0);
 #pragma unroll
-    for (int i = 0; i < 16; i += 2)
-      split2_f16(act_bf<ACT>(v[i] + bz[i]), act_bf<ACT>(v[i + 1] + bz[i + 1]), hi[i >> 1], lo[i >> 1]);
-    tmem_st8(th_hi + ch * 8, hi);
-    tmem_st8(th_lo + ch * 8, lo);
+      for (int i = 0; i < 16; ++i) dot = fmaf(w[i], act_bf<ACT>(v[i] + bz[i]), dot);
+    } else {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 16; i += 2)
+        split2_f16(act_bf<ACT>(v[i] + bz[i]), act_bf<ACT>(v[i + 1] + bz[i + 1]), hi[i >> 1], lo[i >> 1]);
+      tmem_st8(th_hi + ch * 8, hi);
+      tmem_st8(th_lo + ch * 8, lo);
+    }
   }
-  tmem_st_wait();
+  if (!DOT) tmem_st_wait();
+  return dot;
 }
 
 __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid_constant__ RowsParams P) {
@@ -205,6 +230,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
   uint8_t* x_lo = x_hi + x_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(x_lo + x_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRSlots + 2);
+  float* scratch = reinterpret_cast<float*>(bars + 2 * kRSlots + 4);  // 128 floats: cross-warp partial sums
+  float* bias_s = scratch + 128 + 4;                                  // 2 x kBiasStage floats, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * kRowsM;
@@ -229,7 +256,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Each role changes its register budget INSIDE its own branch (ptxas sizes a region by the
+  // setmaxnreg that dominates it; a shared if/else before the role split would cap everything at 80).
   if (warp == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     // ================================ weight loader ================================
     uint32_t slot = 0, phase = 0;
     for (int t = 0; t < V.n_steps; ++t) {
@@ -255,6 +285,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       }
     }
   } else if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     // ================================ MMA issuer ================================
     uint32_t slot = 0, phase = 0, act_phase = 0;
     const uint64_t x_desc = make_smem_desc(smem_u32(x_hi), kXLBO, 128);
@@ -313,11 +344,14 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         __syncwarp();
       }
     }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");  // spare warps of warpgroup 0: the dec is warpgroup-wide
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ================================ epilogue warps ================================
-    const int et = threadIdx.x - 64;       // 0..255
+    const int et = threadIdx.x - 128;      // 0..255
     const int q = warp & 3;                // TMEM lane quadrant
-    const int half = (warp - 2) >> 2;      // which of the two warps of this quadrant
+    const int half = (warp - 4) >> 2;      // which of the two warps of this quadrant
     const int r = q * 32 + lane;           // row within the tile = TMEM lane
     const int row = row0 + r;
     const int N = V.N, D = V.D, S = V.S, A = V.A;
@@ -355,73 +389,149 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       mbar_arrive(bar_act);
     }
 
+    // With ~220 KB of shared memory in use there is next to no L1: every global load is an L2
+    // round trip.  So while the MMAs of a stage run, the epilogue warps already fetch what that
+    // stage's epilogue will need: its biases into a smem staging buffer, its per-row inputs
+    // (noise, previous belief) into registers.
+    float pre[32];  // per-row inputs of the upcoming stage
+    float pre_nt = 1.f;
+    auto prefetch = [&](int t, int s, int buf) {
+      const RStage& st = P.stages[s];
+      const size_t trow = (size_t)t * N;
+      float* dstb = bias_s + buf * kBiasStage;
+      for (int i = et; i < st.bias_n; i += kRowsEpiThreads) dstb[i] = __ldg(V.bias + st.bias_off + i);
+      switch (st.epi) {
+        case R_GRU: {
+          const float* bprev = (t == 0) ? V.init_belief : (V.beliefs + (trow - N) * D);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int c = (half + 2 * k) * 16;
+            if (bprev && c < st.nfeat) ld_row16(pre + 16 * k, bprev + (size_t)row * D + st.unit0 + c, st.nfeat - c, row_ok);
+            else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) pre[16 * k + i] = 0.f;
+            }
+          }
+        } break;
+        case R_PRIOR:
+        case R_POST: {
+          if (half == 0) {
+            const float* eps = (st.epi == R_POST ? V.eps_post : V.eps_prior) + (trow + row) * S;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pre[i] = (row_ok && i < S) ? __ldg(eps + i) : 0.f;
+            pre_nt = 1.f;
+            if ((st.flags & SF_WRITES_STATE) && V.nonterm && (t + 1) < V.n_steps && row_ok) pre_nt = __ldg(V.nonterm + trow + N + row);
+          }
+        } break;
+        case R_ACTION: {
+          if (half == 0) {
+            const float* eps = V.eps_action + (trow + row) * A;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pre[i] = (row_ok && i < A) ? __ldg(eps + i) : 0.f;
+          }
+        } break;
+        default: break;
+      }
+    };
+
     uint32_t acc_phase = 0;
+    int buf = 0;
+    {  // stage 0 of step 0 never needs per-row inputs ahead of time in either program; stage its biases
+      const RStage& st0 = P.stages[0];
+      for (int i = et; i < st0.bias_n; i += kRowsEpiThreads) bias_s[i] = __ldg(V.bias + st0.bias_off + i);
+      if (st0.epi == R_GRU || st0.epi == R_PRIOR || st0.epi == R_POST || st0.epi == R_ACTION) __trap();
+    }
     for (int t = 0; t < V.n_steps; ++t) {
       const size_t trow = (size_t)t * N;
       const bool has_next = (t + 1) < V.n_steps;
       for (int s = 0; s < P.n_rstages; ++s) {
         const RStage& st = P.stages[s];
+        const float* bias = bias_s + buf * kBiasStage;
         mbar_wait(bar_acc, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        epi_sync();  // staged biases visible to every epilogue warp
+        if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2] = clock64();
 
         switch (st.epi) {
           case R_ACT_H: {
-            if (st.act == ACT_ELU) rows_act_h<ACT_ELU>(P, st, tacc, th_hi, th_lo, half, row, row_ok, trow);
-            else rows_act_h<ACT_RELU>(P, st, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            if (st.act == ACT_ELU) rows_act_h<ACT_ELU, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            else rows_act_h<ACT_RELU, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+          } break;
+
+          case R_ACT_DOT: {
+            float dot;
+            if (st.act == ACT_ELU) dot = rows_act_h<ACT_ELU, true>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            else dot = rows_act_h<ACT_RELU, true>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            if (half == 1) scratch[r] = dot;
+            epi_sync();
+            if (half == 0 && row_ok) {
+              const int nch = (st.nfeat + 15) >> 4;
+              float* dst = (st.flags & SF_SCALAR_VALUE) ? V.values : V.rewards;
+              dst[trow + row] = dot + scratch[r] + bias[2 * nch * 16];
+            }
           } break;
 
           case R_GRU: {
             // accumulator: r at [0,W), z at [W,2W), i_n at [2W,3W), h_n at [3W,4W), W = st.width
             const int W = st.width, u0 = st.unit0, nu = st.nfeat;  // nu valid units in this chunk
-            const float* bias = V.bias + st.bias_off;              // [r | z | in | hn] each W floats
-            const float* bprev = (t == 0) ? V.init_belief : (V.beliefs + (trow - N) * D);
-            for (int sub = half; sub * 16 < nu; sub += 2) {
-              const int c = sub * 16, nv = min(16, nu - c);
-              float vr[16], vz[16], vi[16], vh[16], bo[16], bb[16];
-              tmem_ld16(tacc + c, vr);
-              tmem_ld16(tacc + W + c, vz);
-              tmem_ld16(tacc + 2 * W + c, vi);
-              tmem_ld16(tacc + 3 * W + c, vh);
-              if (bprev) ld_row16(bo, bprev + (size_t)row * D + u0 + c, nv, row_ok);
-              else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) bo[i] = 0.f;
+            for (int k = 0; k < 2; ++k) {
+              const int c = (half + 2 * k) * 16;
+              if (c < nu) {
+                const int nv = min(16, nu - c);
+                float vr[16], vz[16], vi[16], vh[16], bb[16];
+                tmem_ld16(tacc + c, vr);
+                tmem_ld16(tacc + W + c, vz);
+                tmem_ld16(tacc + 2 * W + c, vi);
+                tmem_ld16(tacc + 3 * W + c, vh);
+                tmem_ld_wait();
+                ld_uni16(bb, bias + c);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) vr[i] = sigmoid_f(vr[i] + bb[i]);
+                ld_uni16(bb, bias + W + c);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) vz[i] = sigmoid_f(vz[i] + bb[i]);
+                ld_uni16(bb, bias + 3 * W + c);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) vh[i] = vr[i] * (vh[i] + bb[i]);
+                ld_uni16(bb, bias + 2 * W + c);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float nn = tanh_f(vi[i] + bb[i] + vh[i]);
+                  vi[i] = nn + vz[i] * (pre[16 * k + i] - nn);   // (1-z)*n + z*b_prev
+                }
+                if (row_ok) st_row16(V.beliefs + (trow + row) * D + u0 + c, vi, nv);
               }
-              tmem_ld_wait();
-              ld_uni16(bb, bias + c);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) vr[i] = sigmoid_f(vr[i] + bb[i]);
-              ld_uni16(bb, bias + W + c);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) vz[i] = sigmoid_f(vz[i] + bb[i]);
-              ld_uni16(bb, bias + 3 * W + c);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) vh[i] = vr[i] * (vh[i] + bb[i]);
-              ld_uni16(bb, bias + 2 * W + c);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float nn = tanh_f(vi[i] + bb[i] + vh[i]);
-                bo[i] = nn + vz[i] * (bo[i] - nn);   // (1-z)*n + z*b
-              }
-              if (row_ok) st_row16(V.beliefs + (trow + row) * D + u0 + c, bo, nv);
             }
             if (st.flags & RF_LAST_CHUNK) {
               // every chunk's MMAs are done: now the belief slot of X may be overwritten.  Rows were
-              // written by both warps of the quadrant, so sync the epilogue warps first.
+              // written by both warps of the quadrant, so sync the epilogue warps first; the loads
+              // are issued in batches so the L2 latency is paid once per batch, not once per k-group.
               __threadfence_block();
               epi_sync();
-              if (row_ok) {
-                const float* b = V.beliefs + (trow + row) * D;
-                for (int kg = half; kg * 8 < D; kg += 2) {
-                  float v[8];
+              const float* b = V.beliefs + (trow + row) * D;
+              const int nkg = D >> 3;  // full k-groups
+              for (int kg0 = half; kg0 < nkg; kg0 += 8) {
+                float v[4][8];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = (kg * 8 + i < D) ? b[kg * 8 + i] : 0.f;
-                  if (kg * 8 + 8 <= D) x_put8(x_hi, x_lo, r, kg, v);
-                  else
-                    for (int i = 0; kg * 8 + i < D; ++i) x_put(x_hi, x_lo, r, kg * 8 + i, v[i]);
+                for (int j = 0; j < 4; ++j) {
+                  const int kg = kg0 + 2 * j;
+                  if (kg < nkg && row_ok) {
+                    const float4 lo4 = *reinterpret_cast<const float4*>(b + kg * 8);
+                    const float4 hi4 = *reinterpret_cast<const float4*>(b + kg * 8 + 4);
+                    v[j][0] = lo4.x; v[j][1] = lo4.y; v[j][2] = lo4.z; v[j][3] = lo4.w;
+                    v[j][4] = hi4.x; v[j][5] = hi4.y; v[j][6] = hi4.z; v[j][7] = hi4.w;
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int kg = kg0 + 2 * j;
+                  if (kg < nkg && row_ok) x_put8(x_hi, x_lo, r, kg, v[j]);
                 }
               }
+              if (half == 0 && row_ok)
+                for (int k = nkg * 8; k < D; ++k) x_put(x_hi, x_lo, r, k, b[k]);
             }
           } break;
 
@@ -430,20 +540,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             if (half == 0) {
               const bool post = st.epi == R_POST;
               const int W = st.width;  // mean at [0,W), raw std at [W,2W)
-              const float* bias = V.bias + st.bias_off;
-              const float* eps = post ? V.eps_post : V.eps_prior;
               float* o_s = post ? V.post_s : V.prior_s;
               float* o_m = post ? V.post_m : V.prior_m;
               float* o_sd = post ? V.post_sd : V.prior_sd;
               const bool want_kl = post && V.kl != nullptr;
-              float nt = 1.f;
-              if ((st.flags & SF_WRITES_STATE) && V.nonterm && has_next && row_ok) nt = V.nonterm[trow + N + row];
               float kl = 0.f;
-              for (int c = 0; c < S; c += 16) {
+              auto chunk = [&](const int c, const float* e) {
                 const int nv = min(16, S - c);
-                float vm[16], vs[16], e[16], pm[16], psd[16];
+                float vm[16], vs[16], pm[16], psd[16];
                 const size_t o = (trow + row) * S + c;
-                ld_row16(e, eps + o, nv, row_ok);
                 if (want_kl) {
                   ld_row16(pm, V.prior_m + o, nv, row_ok);
                   ld_row16(psd, V.prior_sd + o, nv, row_ok);
@@ -451,26 +556,44 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
                 tmem_ld16(tacc + c, vm);
                 tmem_ld16(tacc + W + c, vs);
                 tmem_ld_wait();
+                float smp[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  if (i < nv) {
-                    const float m = vm[i] + __ldg(bias + c + i);
-                    const float sd = softplus_f(vs[i] + __ldg(bias + W + c + i)) + V.min_std;
-                    const float smp = m + sd * e[i];
-                    if (row_ok) {
-                      o_s[o + i] = smp;
-                      o_m[o + i] = m;
-                      o_sd[o + i] = sd;
-                      if (want_kl) {
-                        const float ratio = sd / psd[i], vr = ratio * ratio;
-                        const float dm = (m - pm[i]) / psd[i];
-                        kl += 0.5f * (vr + dm * dm - 1.f - logf(vr));
-                      }
+                  vm[i] += bias[c + i];
+                  vs[i] = softplus_f(vs[i] + bias[W + c + i]) + V.min_std;
+                  smp[i] = vm[i] + vs[i] * e[i];
+                }
+                if (want_kl) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    if (i < nv && row_ok) {
+                      const float ratio = vs[i] / psd[i], vr = ratio * ratio;
+                      const float dm = (vm[i] - pm[i]) / psd[i];
+                      kl += 0.5f * (vr + dm * dm - 1.f - logf(vr));
                     }
-                    if (st.flags & SF_WRITES_STATE) x_put(x_hi, x_lo, r, D + c + i, smp * nt);
                   }
                 }
-              }
+                if (row_ok) {
+                  st_row16(o_s + o, smp, nv);
+                  st_row16(o_m + o, vm, nv);
+                  st_row16(o_sd + o, vs, nv);
+                }
+                if (st.flags & SF_WRITES_STATE) {
+                  if (((D + c) & 1) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                      if (i + 1 < nv) x_put2(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt, smp[i + 1] * pre_nt);
+                      else if (i < nv) x_put(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt);
+                    }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                      if (i < nv) x_put(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt);
+                  }
+                }
+              };
+              chunk(0, pre);                      // S <= 32 here (wider states run on the vm.cuh kernel)
+              if (S > 16) chunk(16, pre + 16);
               if (want_kl && row_ok) V.kl[trow + row] = kl;
             } else if ((st.flags & SF_LOADS_ACTION) && has_next && row_ok) {
               for (int j = 0; j < A; ++j) x_put(x_hi, x_lo, r, D + S + j, __ldg(V.actions_in + (trow + N + row) * A + j));
@@ -478,29 +601,24 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
           } break;
 
           case R_ACTION: {
-            if (half == 0) {
+            if (half == 0) {   // A <= 16 here
               const int W = st.width;
-              const float* bias = V.bias + st.bias_off;
               const float inv_ms = 1.f / V.a_mean_scale;
-              for (int c = 0; c < A; c += 16) {
-                const int nv = min(16, A - c);
-                float vm[16], vs[16], e[16];
-                const size_t o = (trow + row) * A + c;
-                ld_row16(e, V.eps_action + o, nv, row_ok);
-                tmem_ld16(tacc + c, vm);
-                tmem_ld16(tacc + W + c, vs);
-                tmem_ld_wait();
+              float vm[16], vs[16];
+              const size_t o = (trow + row) * A;
+              tmem_ld16(tacc, vm);
+              tmem_ld16(tacc + W, vs);
+              tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  if (i < nv) {
-                    const float mean = V.a_mean_scale * tanh_f((vm[i] + __ldg(bias + c + i)) * inv_ms);
-                    const float sd = softplus_f(vs[i] + __ldg(bias + W + c + i) + V.a_init_std) + V.a_min_std;
-                    const float a = tanh_f(mean + sd * e[i]);
-                    if (row_ok && V.actions_out) V.actions_out[o + i] = a;
-                    x_put(x_hi, x_lo, r, D + S + c + i, a);
-                  }
-                }
+              for (int i = 0; i < 16; ++i) {
+                const float mean = V.a_mean_scale * tanh_f((vm[i] + bias[i]) * inv_ms);
+                const float sd = softplus_f(vs[i] + bias[W + i] + V.a_init_std) + V.a_min_std;
+                vm[i] = tanh_f(mean + sd * pre[i]);
               }
+              if (row_ok && V.actions_out) st_row16(V.actions_out + o, vm, A);
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < A) x_put(x_hi, x_lo, r, D + S + i, vm[i]);
             }
           } break;
 
@@ -510,7 +628,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               tmem_ld16(tacc, v);
               tmem_ld_wait();
               float* dst = (st.flags & SF_SCALAR_VALUE) ? V.values : V.rewards;
-              if (row_ok) dst[trow + row] = v[0] + __ldg(V.bias + st.bias_off);
+              if (row_ok) dst[trow + row] = v[0] + bias[0];
             }
           } break;
           default: break;
@@ -518,7 +636,14 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
 
         fence_proxy_async_smem();
         tc_fence_before();
+        if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2 + 1] = clock64();
         mbar_arrive(bar_act);
+        // fetch for the next stage while its MMAs run
+        buf ^= 1;
+        {
+          const bool wrap = (s + 1 == P.n_rstages);
+          if (!wrap || has_next) prefetch(wrap ? t + 1 : t, wrap ? 0 : s + 1, buf);
+        }
       }
     }
 

@@ -99,6 +99,7 @@ struct VmParams {
   float* returns;            // (T-1, N) or null
   float* out; int out_ld;    // EPI_STORE
   int dbg_flags;             // bring-up only: bit0 swaps LBO/SBO in the smem descriptors
+  long long* dbg_clock;      // profiling only: CTA 0 writes [step][stage][2] clock64 stamps (epilogue begin/end)
   VmStage stages[kMaxStages];
   VmGemm gemms[kMaxGemms];
 };

@@ -1,0 +1,44 @@
+"""Per-stage timing of the rows kernel from in-kernel clock64 stamps (CTA 0)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import rssm_oracle as O  # noqa: E402
+from repo_b200 import ops, _lib  # noqa: E402
+
+dev = torch.device("cuda:0")
+cu = lambda p: {k: v.to(dev) for k, v in p.items()}
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 18944
+params = cu(O.make_transition_params(0))
+actor = cu(O.make_mlp_params(1, 230, 200, 12, 4))
+reward = cu(O.make_mlp_params(2, 230, 200, 1, 3))
+value = cu(O.make_mlp_params(3, 230, 200, 1, 3))
+x = O.make_imagine_inputs(1, N, 15)
+a = [params, actor, reward, value, x["belief"].to(dev), x["state"].to(dev), x["eps_action"].to(dev), x["eps_prior"].to(dev), 15]
+ops.imagine_fwd(*a, row_tile=128)
+torch.cuda.synchronize()
+NS = 32
+buf = torch.zeros(14 * NS * 2, dtype=torch.int64, device=dev)
+_lib.lib().repo_b200_debug_clock(C.c_void_p(buf.data_ptr()))
+ops.imagine_fwd(*a, row_tile=128)
+torch.cuda.synchronize()
+_lib.lib().repo_b200_debug_clock(None)
+b = buf.cpu().numpy()
+nz = (b != 0).sum() // (14 * 2)
+b = b[: 14 * nz * 2].reshape(14, nz, 2)
+print("stages per step:", nz)
+names = ["A1", "A2", "A3", "A4", "ACT", "E", "G0", "G1", "G2", "G3", "P1", "P2", "R1", "R2", "R3", "V1", "V2", "V3"]
+t = 5
+tot_epi = tot_mma = 0
+for s in range(nz):
+    epi = b[t, s, 1] - b[t, s, 0]
+    prev_end = b[t, s - 1, 1] if s > 0 else b[t - 1, nz - 1, 1]
+    mma = b[t, s, 0] - prev_end
+    tot_epi += epi
+    tot_mma += mma
+    print(f"{names[s] if s < len(names) else s:>4}: mma_phase {mma:6d} cyc   epilogue {epi:6d} cyc")
+print("step total:", b[t + 1, 0, 0] - b[t, 0, 0], "cycles; mma", tot_mma, "epi", tot_epi)
