@@ -155,7 +155,7 @@ def workload_config(a):
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_gpu(a):
     import torch.distributed as dist
-    from oracle import rssm_oracle as O      # seeded synthetic weights/inputs only (numpy RandomState)
+    from repo_b200 import synth as O         # seeded synthetic weights/inputs (numpy RandomState); no oracle on this arm
     from repo_b200 import ops, _lib
     from repo_b200.models import ActorModel, RewardModel, ValueModel
     from repo_b200.rssm import TransitionModel

@@ -1,0 +1,87 @@
+"""Seeded synthetic weights and inputs of the DMC shape: numpy RandomState, so the
+same bytes come out in the build container and on the GPU box.  Used by bench.py, smoke(), the tests
+and (re-exported) the oracle; contains no model arithmetic."""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import numpy as np
+import torch
+
+Params = Dict[str, torch.Tensor]
+
+DEFAULT_DIMS = dict(belief=200, state=30, action=6, hidden=200, embed=1024)
+
+
+def _uniform(rs: np.random.RandomState, shape, bound) -> torch.Tensor:
+    return torch.from_numpy(rs.uniform(-bound, bound, size=shape).astype(np.float32))
+
+
+def make_transition_params(seed: int, dims=DEFAULT_DIMS, scale: float = 1.0) -> Params:
+    """Same key names/shapes as TransitionModel.state_dict() (rssm.py:9-32).
+
+    Values follow torch's default init *distribution* (U(+-1/sqrt(fan_in))) but are
+    drawn from numpy so fixtures are reproducible anywhere. `scale` > 1 makes the
+    recurrence livelier (stresses numerics more than a fresh init does)."""
+    rs = np.random.RandomState(seed)
+    D, S, A, H, E = dims["belief"], dims["state"], dims["action"], dims["hidden"], dims["embed"]
+    p: Params = {}
+
+    def lin(name, out_f, in_f):
+        b = scale / math.sqrt(in_f)
+        p[name + ".weight"] = _uniform(rs, (out_f, in_f), b)
+        p[name + ".bias"] = _uniform(rs, (out_f,), b)
+
+    lin("fc_embed_state_action", D, S + A)
+    b = scale / math.sqrt(D)
+    p["rnn.weight_ih"] = _uniform(rs, (3 * D, D), b)
+    p["rnn.weight_hh"] = _uniform(rs, (3 * D, D), b)
+    p["rnn.bias_ih"] = _uniform(rs, (3 * D,), b)
+    p["rnn.bias_hh"] = _uniform(rs, (3 * D,), b)
+    lin("fc_embed_belief_prior", H, D)
+    lin("fc_state_prior", 2 * S, H)
+    lin("fc_embed_belief_posterior", H, D + E)
+    lin("fc_state_posterior", 2 * S, H)
+    return p
+
+
+def make_mlp_params(seed: int, in_f: int, hidden: int, out_f: int, n_hidden: int, scale: float = 1.0) -> Params:
+    """fc1..fc{n_hidden+1}: in_f -> hidden x n_hidden -> out_f  (ActorModel n_hidden=4,
+    out=2A; RewardModel/ValueModel n_hidden=3, out=1)."""
+    rs = np.random.RandomState(seed)
+    p: Params = {}
+    sizes = [in_f] + [hidden] * n_hidden + [out_f]
+    for i in range(len(sizes) - 1):
+        b = scale / math.sqrt(sizes[i])
+        p[f"fc{i + 1}.weight"] = _uniform(rs, (sizes[i + 1], sizes[i]), b)
+        p[f"fc{i + 1}.bias"] = _uniform(rs, (sizes[i + 1],), b)
+    return p
+
+
+
+def make_observe_inputs(seed: int, T: int, B: int, dims=DEFAULT_DIMS, p_done=1 / 500.0, embed_scale=1.0):
+    rs = np.random.RandomState(seed)
+    D, S, A, E = dims["belief"], dims["state"], dims["action"], dims["embed"]
+    T1 = T - 1
+    f = lambda a: torch.from_numpy(a.astype(np.float32))
+    return dict(
+        prev_belief=torch.zeros(B, D), prev_state=torch.zeros(B, S),
+        actions=f(rs.uniform(-1, 1, (T1, B, A))),
+        embeds=f(rs.standard_normal((T1, B, E)) * embed_scale),
+        nonterms=f((rs.uniform(0, 1, (T1, B, 1)) >= p_done)),
+        eps_prior=f(rs.standard_normal((T1, B, S))),
+        eps_post=f(rs.standard_normal((T1, B, S))),
+    )
+
+
+def make_imagine_inputs(seed: int, N: int, horizon: int, dims=DEFAULT_DIMS):
+    rs = np.random.RandomState(seed)
+    D, S, A = dims["belief"], dims["state"], dims["action"]
+    f = lambda a: torch.from_numpy(a.astype(np.float32))
+    return dict(
+        belief=f(np.clip(rs.standard_normal((N, D)) * 0.3, -1, 1)),
+        state=f(rs.standard_normal((N, S))),
+        eps_action=f(rs.standard_normal((horizon - 1, N, A))),
+        eps_prior=f(rs.standard_normal((horizon - 1, N, S))),
+    )
