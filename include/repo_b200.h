@@ -93,12 +93,36 @@ int repo_b200_observe_fwd(const repo_b200_dims* dims, const repo_b200_rssm_weigh
                           int act_kind, float min_std_dev, void* workspace, size_t workspace_bytes, int flags,
                           int row_tile, void* stream);
 
+/* ---- cell: TransitionModel.compute_prior_state (rssm.py:42-50; embed == NULL) or
+ * compute_posterior_state (rssm.py:52-64; embed (N,E)).  belief (N,D), eps (N,S) -> state, mean, std_dev (N,S). */
+size_t repo_b200_cell_workspace_bytes(const repo_b200_dims* dims, int n_rows);
+int repo_b200_cell_fwd(const repo_b200_dims* dims, const repo_b200_rssm_weights* rssm, const float* belief,
+                       const float* embed, const float* eps, float* state, float* mean, float* std_dev, int n_rows,
+                       int act_kind, float min_std_dev, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- head: RewardModel.forward (decoder.py:189-195) / ValueModel.forward (actor_critic.py:20-26):
  * [belief|state] -> 3 x (Linear + act) -> Linear(1), squeezed.  belief (N,D), state (N,S), out (N). */
 size_t repo_b200_head_workspace_bytes(const repo_b200_dims* dims);
 int repo_b200_head_fwd(const repo_b200_dims* dims, const repo_b200_mlp_weights* head, const float* belief,
                        const float* state, float* out, int n_rows, int act_kind, void* workspace,
                        size_t workspace_bytes, int flags, int row_tile, void* stream);
+
+/* ---- MC entropy of the tanh-Normal policy: SampleDist.entropy (models/utils.py:160-163) over
+ * Independent(TransformedDistribution(Normal(mean,std), TanhBijector), 1) (actor_critic.py:89-95;
+ * TanhBijector models/utils.py:112-134), called at dreamer.py:320-324.
+ *   mean, std_dev (M,A); eps (K,M,A) standard normal draws; entropy (M). */
+int repo_b200_tanh_normal_entropy_fwd(const float* mean, const float* std_dev, const float* eps, float* entropy, int m,
+                                      int action, int samples, void* stream);
+
+/* ---- replay gather: the index bookkeeping of SequenceReplayBuffer.sample (common/buffers.py:156-166) after
+ * `np.random.choice` (start_inds, drawn on the host so the RNG stream is the reference's), fused with
+ * preprocess (common/utils.py:74-80: x/255*2-1 in numpy's operation order) and nonterms = 1 - dones
+ * (dreamer.py:391).  Ring arrays on the device: obs (cap, frame_bytes) uint8, actions (cap, action_dim),
+ * rewards (cap), dones (cap); outputs time-major (L, B, ...); index_out (L*B) nullable. */
+int repo_b200_replay_gather(const uint8_t* obs, const float* actions, const float* rewards, const float* dones,
+                            const long long* start_inds, int batch, int seq_len, long long pos, int full,
+                            long long length, int frame_bytes, int action_dim, float* obs_out, float* actions_out,
+                            float* rewards_out, float* nonterminals_out, long long* index_out, void* stream);
 
 /* ---- linear: y = x W^T + b on the same machine (nn.Linear as used by rssm.py:23-32); building block
  * and bring-up test.  x (rows, in_f) ld = x_ld; w (out_f, in_f); b (out_f) nullable; y ld = y_ld. */

@@ -39,6 +39,8 @@ EXPORTS = [
     "repo_b200_observe_workspace_bytes", "repo_b200_observe_fwd",
     "repo_b200_linear_workspace_bytes", "repo_b200_linear_fwd",
     "repo_b200_head_workspace_bytes", "repo_b200_head_fwd",
+    "repo_b200_tanh_normal_entropy_fwd", "repo_b200_replay_gather",
+    "repo_b200_cell_workspace_bytes", "repo_b200_cell_fwd",
 ]
 
 _lib = None
@@ -77,6 +79,15 @@ def lib():
     L.repo_b200_head_workspace_bytes.restype = sz
     L.repo_b200_head_fwd.argtypes = [C.POINTER(Dims), C.POINTER(MlpWeights), vp, vp, vp, ci, ci, vp, sz, ci, ci, vp]
     L.repo_b200_head_fwd.restype = ci
+    L.repo_b200_tanh_normal_entropy_fwd.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
+    L.repo_b200_tanh_normal_entropy_fwd.restype = ci
+    ll = C.c_longlong
+    L.repo_b200_replay_gather.argtypes = [vp, vp, vp, vp, vp, ci, ci, ll, ci, ll, ci, ci, vp, vp, vp, vp, vp, vp]
+    L.repo_b200_replay_gather.restype = ci
+    L.repo_b200_cell_workspace_bytes.argtypes = [C.POINTER(Dims), ci]
+    L.repo_b200_cell_workspace_bytes.restype = sz
+    L.repo_b200_cell_fwd.argtypes = [C.POINTER(Dims), C.POINTER(RssmWeights)] + [vp] * 6 + [ci, ci, cf, vp, sz, vp]
+    L.repo_b200_cell_fwd.restype = ci
     L.repo_b200_linear_workspace_bytes.argtypes = [ci, ci]
     L.repo_b200_linear_workspace_bytes.restype = sz
     L.repo_b200_linear_fwd.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp, ci, vp, sz, ci, vp]

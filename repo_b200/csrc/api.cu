@@ -13,6 +13,7 @@
 #include "pack.cuh"
 #include "vm.cuh"
 #include "rows.cuh"
+#include "elementwise.cuh"
 
 using namespace rb;
 
@@ -597,6 +598,92 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   P.returns = (reward && value) ? returns : nullptr;
   if (rows) return launch_rows(rbld.P, st);
   return launch(P, b.max_acc_tiles, row_tile, st);
+}
+
+int repo_b200_tanh_normal_entropy_fwd(const float* mean, const float* std_dev, const float* eps, float* entropy, int m,
+                                      int action, int samples, void* stream) {
+  if (m < 0 || action < 1 || samples < 1) return fail(-1, "entropy: bad sizes m=%d action=%d samples=%d", m, action, samples);
+  if (m == 0) return 0;
+  if (!mean || !std_dev || !eps || !entropy) return fail(-1, "entropy: NULL pointer");
+  const long long threads = (long long)m * kEntSlices;
+  tanh_normal_entropy_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mean, std_dev, eps, entropy, m, action, samples);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int repo_b200_replay_gather(const uint8_t* obs, const float* actions, const float* rewards, const float* dones,
+                            const long long* start_inds, int batch, int seq_len, long long pos, int full,
+                            long long length, int frame_bytes, int action_dim, float* obs_out, float* actions_out,
+                            float* rewards_out, float* nonterminals_out, long long* index_out, void* stream) {
+  if (batch < 0 || seq_len < 0 || frame_bytes < 1 || action_dim < 1 || length < 1) return fail(-1, "replay_gather: bad sizes");
+  if (batch == 0 || seq_len == 0) return 0;
+  if (!obs || !actions || !rewards || !dones || !start_inds || !obs_out || !actions_out || !rewards_out || !nonterminals_out)
+    return fail(-1, "replay_gather: NULL pointer");
+  replay_gather_kernel<<<batch * seq_len, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      obs, actions, rewards, dones, start_inds, batch, seq_len, pos, full, length, frame_bytes, action_dim, obs_out,
+      actions_out, rewards_out, nonterminals_out, index_out);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- standalone Gaussian cells: compute_prior_state (rssm.py:42-50) / compute_posterior_state (rssm.py:52-64)
+static void build_cell(Builder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W, bool posterior, int act) {
+  const int D = d->belief, S = d->state, Hd = d->hidden, E = d->embed;
+  const int kD16 = cdiv(D, 16), kH16 = cdiv(Hd, 16);
+  set_dims(b.P, d);
+  if (!posterior) {
+    b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act);
+    b.gaussian_head(W->fc_state_prior_w, W->fc_state_prior_b, Hd, S, kH16, EPI_PRIOR, 0);
+  } else {
+    b.dense_to_h(W->fc_embed_belief_posterior_w, W->fc_embed_belief_posterior_b, D + E, Hd, 0, D, 0, kD16, 0, 0, act, SF_ADDEND);
+    b.gaussian_head(W->fc_state_posterior_w, W->fc_state_posterior_b, Hd, S, kH16, EPI_POST, 0);
+  }
+}
+
+size_t repo_b200_cell_workspace_bytes(const repo_b200_dims* d, int n_rows) {
+  if (check_dims(d)) return 0;
+  repo_b200_rssm_weights W{};
+  Builder b;
+  build_cell(b, d, &W, true, ACT_ELU);
+  return align_up(b.packed_bytes(), 256) + align_up(repo_b200_linear_workspace_bytes(d->embed, d->hidden), 256) +
+         align_up((size_t)std::max(n_rows, 0) * d->hidden * sizeof(float), 256);
+}
+
+int repo_b200_cell_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const float* belief, const float* embed,
+                       const float* eps, float* state, float* mean, float* std_dev, int n_rows, int act_kind,
+                       float min_std, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_act(act_kind))) return rc;
+  if (n_rows < 0) return fail(-1, "cell: bad row count");
+  if (n_rows == 0) return 0;
+  if (!W || !belief || !eps || !state || !mean || !std_dev) return fail(-1, "cell: NULL pointer");
+  if (ws_bytes < repo_b200_cell_workspace_bytes(d, n_rows)) return fail(-4, "cell: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool posterior = embed != nullptr;
+  Builder b;
+  build_cell(b, d, W, posterior, act_kind);
+  const size_t main = align_up(b.packed_bytes(), 256);
+  const size_t lin = align_up(repo_b200_linear_workspace_bytes(d->embed, d->hidden), 256);
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  if ((rc = b.bind_and_pack(base, main, true, st))) return rc;
+  float* addend = reinterpret_cast<float*>(base + main + lin);
+  VmParams& P = b.P;
+  if (posterior) {
+    rc = run_linear(embed, d->embed, n_rows, d->embed, W->fc_embed_belief_posterior_w, d->belief + d->embed, d->belief,
+                    nullptr, d->hidden, addend, d->hidden, base + main, lin, 0, st);
+    if (rc) return rc;
+    P.addend = addend;
+    P.eps_post = eps; P.post_s = state; P.post_m = mean; P.post_sd = std_dev;
+  } else {
+    P.eps_prior = eps; P.prior_s = state; P.prior_m = mean; P.prior_sd = std_dev;
+  }
+  P.n_steps = 1;
+  P.N = n_rows;
+  P.min_std = min_std;
+  P.init_belief = belief;
+  return launch(P, b.max_acc_tiles, 0, st);
 }
 
 size_t repo_b200_head_workspace_bytes(const repo_b200_dims* d) {

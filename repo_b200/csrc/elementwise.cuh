@@ -1,0 +1,87 @@
+// HBM-bound helpers around the recurrence: the Monte-Carlo tanh-Normal entropy (SampleDist.entropy,
+// models/utils.py:160-163 over TanhBijector :112-134) and the replay gather + preprocess
+// (SequenceReplayBuffer.sample common/buffers.py:156-166 + preprocess common/utils.py:74-80).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rb {
+
+// entropy[m] = -(1/K) sum_k sum_a log p(tanh(mean + std*eps[k,m,a]))
+//   log p(y) = Normal(mean,std).log_prob(atanh(clamp(y))) - 2(log2 - x - softplus(-2x)),  x = atanh(clamp(y))
+// One thread per (m, sample-slice); eps is read once, coalesced along m*A+a (HBM-bound: K*M*A*4 bytes).
+constexpr int kEntSlices = 4;  // threads cooperating on one row (split over k), reduced with shuffles
+__global__ void __launch_bounds__(256) tanh_normal_entropy_kernel(const float* __restrict__ mean,
+                                                                  const float* __restrict__ std_,
+                                                                  const float* __restrict__ eps, float* __restrict__ out,
+                                                                  int M, int A, int K) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = gid / kEntSlices, sl = gid % kEntSlices;
+  float acc = 0.f;
+  if (m < M) {
+    for (int a = 0; a < A; ++a) {
+      const float mu = mean[(size_t)m * A + a], sd = std_[(size_t)m * A + a];
+      const float inv2var = 1.f / (2.f * sd * sd);
+      const float c0 = logf(sd) + 0.9189385332046727f;  // log(std) + log(sqrt(2*pi))
+      for (int k = sl; k < K; k += kEntSlices) {
+        const float e = __ldg(eps + ((size_t)k * M + m) * A + a);
+        const float y = tanhf(mu + sd * e);
+        const float yc = fabsf(y) <= 1.f ? fminf(fmaxf(y, -0.99999997f), 0.99999997f) : y;
+        const float x = atanhf(yc);
+        const float d = x - mu;
+        const float t = -2.f * x;
+        const float sp = t > 20.f ? t : log1pf(expf(t));  // F.softplus(-2x)
+        const float ladj = 2.f * (0.6931471805599453f - x - sp);
+        acc += (-(d * d) * inv2var - c0) - ladj;
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 1; s < kEntSlices; s <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (m < M && sl == 0) out[m] = -acc / (float)K;
+}
+
+// Replay gather: time-major flat index i = l*B + b -> ring slot (start[b] + l (+ pos) mod length); one block
+// per (l,b) copies the frame, applying x/255*2-1 in numpy's exact operation order (no FMA contraction).
+__global__ void __launch_bounds__(128) replay_gather_kernel(const uint8_t* __restrict__ obs, const float* __restrict__ act,
+                                                            const float* __restrict__ rew, const float* __restrict__ done,
+                                                            const long long* __restrict__ starts, int B, int L, long long pos,
+                                                            int full, long long length, int frame_bytes, int act_dim,
+                                                            float* __restrict__ obs_out, float* __restrict__ act_out,
+                                                            float* __restrict__ rew_out, float* __restrict__ nonterm_out,
+                                                            long long* __restrict__ index_out) {
+  const int i = blockIdx.x;  // l*B + b
+  const int l = i / B, b = i - l * B;
+  long long idx = starts[b] + l;
+  if (full) idx = (idx + pos) % length;
+  const uint8_t* src = obs + (size_t)idx * frame_bytes;
+  float* dst = obs_out + (size_t)i * frame_bytes;
+  if ((frame_bytes & 15) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    for (int v = threadIdx.x; v < frame_bytes / 16; v += blockDim.x) {
+      const uint4 q = __ldg(s4 + v);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      float4* d4 = reinterpret_cast<float4*>(dst + (size_t)v * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 o;
+        o.x = __fsub_rn(__fmul_rn(__fdiv_rn((float)(w[j] & 0xff), 255.f), 2.f), 1.f);
+        o.y = __fsub_rn(__fmul_rn(__fdiv_rn((float)((w[j] >> 8) & 0xff), 255.f), 2.f), 1.f);
+        o.z = __fsub_rn(__fmul_rn(__fdiv_rn((float)((w[j] >> 16) & 0xff), 255.f), 2.f), 1.f);
+        o.w = __fsub_rn(__fmul_rn(__fdiv_rn((float)(w[j] >> 24), 255.f), 2.f), 1.f);
+        d4[j] = o;
+      }
+    }
+  } else {
+    for (int v = threadIdx.x; v < frame_bytes; v += blockDim.x)
+      dst[v] = __fsub_rn(__fmul_rn(__fdiv_rn((float)src[v], 255.f), 2.f), 1.f);
+  }
+  for (int v = threadIdx.x; v < act_dim; v += blockDim.x) act_out[(size_t)i * act_dim + v] = act[(size_t)idx * act_dim + v];
+  if (threadIdx.x == 0) {
+    rew_out[i] = rew[idx];
+    nonterm_out[i] = 1.f - done[idx];
+    if (index_out) index_out[i] = idx;
+  }
+}
+
+}  // namespace rb

@@ -223,3 +223,41 @@ def head_fwd(head: Dict[str, torch.Tensor], belief: torch.Tensor, state: torch.T
                               _ptr(ws), ws.numel(), 0, row_tile, _stream())
     _lib.check(rc, "repo_b200_head_fwd")
     return out
+
+
+def tanh_normal_entropy(mean: torch.Tensor, std: torch.Tensor, eps: torch.Tensor) -> torch.Tensor:
+    """SampleDist.entropy of the tanh-Normal policy (models/utils.py:137-163): mean, std (M,A), eps (K,M,A) -> (M,)."""
+    L = _lib.lib()
+    M, A = mean.shape
+    K = eps.shape[0]
+    mean, std = _chk(mean, "mean", (M, A)), _chk(std, "std", (M, A))
+    eps = _chk(eps, "eps", (K, M, A))
+    out = torch.empty(M, device=mean.device, dtype=torch.float32)
+    if M == 0:
+        return out
+    rc = L.repo_b200_tanh_normal_entropy_fwd(_ptr(mean), _ptr(std), _ptr(eps), _ptr(out), M, A, K, _stream())
+    _lib.check(rc, "repo_b200_tanh_normal_entropy_fwd")
+    return out
+
+
+def cell_fwd(params: Dict[str, torch.Tensor], belief: torch.Tensor, embed: Optional[torch.Tensor], eps: torch.Tensor,
+             act: str = "elu", min_std: float = 0.1):
+    """compute_prior_state (embed None, rssm.py:42-50) or compute_posterior_state (rssm.py:52-64):
+    returns (state, mean, std_dev), each (N, S)."""
+    L = _lib.lib()
+    keep = _Keep()
+    d = dims_of(params)
+    W = rssm_struct(params, keep)
+    N = belief.shape[0]
+    belief = _chk(belief, "belief", (N, d.belief))
+    eps = _chk(eps, "eps", (N, d.state))
+    if embed is not None:
+        embed = _chk(embed, "observation", (N, d.embed))
+    outs = [torch.empty(N, d.state, device=belief.device, dtype=torch.float32) for _ in range(3)]
+    if N == 0:
+        return tuple(outs)
+    ws = torch.empty(L.repo_b200_cell_workspace_bytes(C.byref(d), N), dtype=torch.uint8, device=belief.device)
+    rc = L.repo_b200_cell_fwd(C.byref(d), C.byref(W), _ptr(belief), _ptr(embed), _ptr(eps), *[_ptr(o) for o in outs], N,
+                              act_kind(act), float(min_std), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "repo_b200_cell_fwd")
+    return tuple(outs)

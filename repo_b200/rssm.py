@@ -148,10 +148,18 @@ class TransitionModel(nn.Module):
         return outs[0][0]
 
     def compute_prior_state(self, belief, *, eps=None):
-        raise NotImplementedError("compute_prior_state as a standalone call is not wired yet; use observe/imagine")
+        """rssm.py:42-50 -> (prior_state, prior_mean, prior_std_dev)."""
+        self._require_no_grad("compute_prior_state", [belief])
+        if eps is None:
+            eps = torch.randn(belief.shape[0], self.state_size, device=belief.device)
+        return ops.cell_fwd(_named(self), belief, None, eps, act=self.activation_function, min_std=self.min_std_dev)
 
     def compute_posterior_state(self, belief, observation, *, eps=None):
-        raise NotImplementedError("compute_posterior_state as a standalone call is not wired yet; use observe/imagine")
+        """rssm.py:52-64 -> (posterior_state, posterior_mean, posterior_std_dev)."""
+        self._require_no_grad("compute_posterior_state", [belief, observation])
+        if eps is None:
+            eps = torch.randn(belief.shape[0], self.state_size, device=belief.device)
+        return ops.cell_fwd(_named(self), belief, observation, eps, act=self.activation_function, min_std=self.min_std_dev)
 
     # ------------------------------------------------------------------ helpers
     def _require_no_grad(self, what, tensors, extra=()):

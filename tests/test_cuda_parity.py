@@ -208,3 +208,78 @@ def test_cpu_tensors_are_rejected(ops, dev):
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.observe_fwd(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"],
                         x["eps_prior"], x["eps_post"])
+
+
+def test_tanh_normal_entropy(ops, dev):
+    g, _ = C.load("entropy_M50_A6_K100")
+    ent = ops.tanh_normal_entropy(C.t(g["mean"]).to(dev), C.t(g["std"]).to(dev), C.t(g["eps"]).to(dev))
+    close(ent, g["entropy"], "entropy vs reference fixture", rtol=1e-3, atol=1e-3)
+    want = O.tanh_normal_entropy(C.t(g["mean"]), C.t(g["std"]), C.t(g["eps"]))
+    close(ent, want, "entropy vs oracle", rtol=1e-3, atol=1e-3)
+    # full size of the default config: M = 14*2450 rows, 100 samples (82 MB of noise)
+    rs = np.random.RandomState(5)
+    M = 34300
+    mean = torch.from_numpy((rs.standard_normal((M, 6)) * 1.5).astype(np.float32))
+    std = torch.from_numpy(rs.uniform(0.1, 1.2, (M, 6)).astype(np.float32))
+    eps = torch.from_numpy(rs.standard_normal((100, M, 6)).astype(np.float32))
+    ent = ops.tanh_normal_entropy(mean.to(dev), std.to(dev), eps.to(dev))
+    sub = slice(0, 2000)
+    close(ent[sub], O.tanh_normal_entropy(mean[sub], std[sub], eps[:, sub]), "entropy full size (subset checked)", rtol=1e-3, atol=2e-3)
+    assert torch.isfinite(ent).all()
+
+
+@pytest.mark.parametrize("n_push", [90, 64 + 23, 64 * 3 + 63])
+def test_replay_device_gather_is_bit_exact(dev, n_push):
+    """sample_device == sample + preprocess + (1 - dones) of the reference (common/buffers.py:156-166,
+    common/utils.py:74-80, dreamer.py:385-391), bit for bit, including the wrapped ring."""
+    from repo_b200.replay import SequenceReplayBuffer
+    cap, B, L = 64 if n_push != 90 else 128, 7, 9
+    rs = np.random.RandomState(n_push)
+    buf = SequenceReplayBuffer(cap, (3, 64, 64), (6,), obs_type=np.uint8)
+    for i in range(n_push):
+        buf.push(rs.randint(0, 256, (3, 64, 64)).astype(np.uint8), rs.uniform(-1, 1, 6).astype(np.float32),
+                 float(rs.uniform(0, 2)), float(rs.uniform() < 0.1))
+    np.random.seed(11)
+    obs, act, rew, done = buf.sample(B, L)
+    want_obs = ((obs.astype(np.float32) / 255) * 2) - 1.0
+    np.random.seed(11)
+    d_obs, d_act, d_rew, d_nt, inds = buf.sample_device(B, L, dev, return_indices=True)
+    np.testing.assert_array_equal(d_obs.cpu().numpy(), want_obs)
+    np.testing.assert_array_equal(d_act.cpu().numpy(), act)
+    np.testing.assert_array_equal(d_rew.cpu().numpy(), rew)
+    np.testing.assert_array_equal(d_nt.cpu().numpy(), 1 - done)
+    np.random.seed(11)
+    starts = np.random.choice(len(buf) - L, size=B)
+    np.testing.assert_array_equal(inds.cpu().numpy(), O.replay_indices(starts, L, buf.pos, buf.full, len(buf)))
+    # pushes after the first sync reach the device mirror
+    buf.push(np.full((3, 64, 64), 255, np.uint8), np.zeros(6, np.float32), 1.0, 0.0)
+    np.random.seed(12)
+    obs2 = buf.sample(B, L)[0]
+    np.random.seed(12)
+    np.testing.assert_array_equal(buf.sample_device(B, L, dev)[0].cpu().numpy(), ((obs2.astype(np.float32) / 255) * 2) - 1.0)
+
+
+def test_cell_methods_match_oracle(dev):
+    """compute_belief / compute_prior_state / compute_posterior_state / obs_step as standalone calls."""
+    from repo_b200.rssm import TransitionModel
+    params, x, gold, meta = C.observe_case("observe_T8_B10")
+    m = TransitionModel(200, 30, 6, 200, 1024, "elu").to(dev)
+    m.load_state_dict(params)
+    B = 10
+    rs = np.random.RandomState(1)
+    belief = torch.from_numpy(np.clip(rs.standard_normal((B, 200)) * 0.3, -1, 1).astype(np.float32))
+    state = torch.from_numpy(rs.standard_normal((B, 30)).astype(np.float32))
+    action, embed = x["actions"][0], x["embeds"][0]
+    e1, e2 = x["eps_prior"][0], x["eps_post"][0]
+    with torch.no_grad():
+        b1 = m.compute_belief(belief.to(dev), state.to(dev), action.to(dev))
+        ps = m.compute_prior_state(b1, eps=e1.to(dev))
+        qs = m.compute_posterior_state(b1, embed.to(dev), eps=e2.to(dev))
+        step = m.obs_step(belief.to(dev), state.to(dev), action.to(dev), embed.to(dev), eps_prior=e1.to(dev), eps_post=e2.to(dev))
+    wb = O.compute_belief(params, belief, state, action)
+    close(b1, wb, "compute_belief")
+    for got, want, nm in zip(ps, O.compute_prior_state(params, wb, e1), ("prior_state", "prior_mean", "prior_std")):
+        close(got, want, nm)
+    for got, want, nm in zip(qs, O.compute_posterior_state(params, wb, embed, e2), ("post_state", "post_mean", "post_std")):
+        close(got, want, nm)
+    assert len(step) == 7 and torch.equal(step[0], b1) and torch.equal(step[4], qs[0])
