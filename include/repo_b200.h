@@ -89,9 +89,28 @@ int repo_b200_observe_fwd(const repo_b200_dims* dims, const repo_b200_rssm_weigh
                           const float* prev_state, const float* actions, const float* embeds,
                           const float* nonterminals, const float* eps_prior, const float* eps_post, float* beliefs,
                           float* prior_states, float* prior_means, float* prior_std_devs, float* posterior_states,
-                          float* posterior_means, float* posterior_std_devs, float* kl, int t1, int batch,
-                          int act_kind, float min_std_dev, void* workspace, size_t workspace_bytes, int flags,
-                          int row_tile, void* stream);
+                          float* posterior_means, float* posterior_std_devs, float* kl, float* stash, int t1,
+                          int batch, int act_kind, float min_std_dev, void* workspace, size_t workspace_bytes,
+                          int flags, int row_tile, void* stream);
+
+/* ---- observe backward (BPTT): what autograd derives from rssm.py:116-133 in the reference.
+ * `stash` (T1,B,repo_b200_observe_stash_floats) is written by repo_b200_observe_fwd when non-NULL:
+ * per (t,b) [embed hidden D][r D][z D][n D][W_hn h + b_hn D][prior hidden H][posterior hidden H].
+ * Inputs: the forward tensors and the incoming gradients g_* of the seven outputs (each nullable).
+ * Outputs: the gradient of every pre-activation per (t,b) — d_q/d_p (T1,B,2S) for the posterior/prior
+ * [mean | raw std], d_hq/d_hp (T1,B,H), d_gi/d_gh (T1,B,3D) for the GRU's W_ih x + b_ih / W_hh h + b_hh,
+ * d_e (T1,B,D) — plus d_prev_belief (B,D) / d_prev_state (B,S) (nullable).  Weight gradients are plain
+ * GEMMs of these against the stashed layer inputs (repo_b200/autograd.py). */
+int repo_b200_observe_stash_floats(const repo_b200_dims* dims);
+int repo_b200_observe_bwd(const repo_b200_dims* dims, const repo_b200_rssm_weights* rssm, const float* prev_belief,
+                          const float* beliefs, const float* prior_std_devs, const float* posterior_std_devs,
+                          const float* eps_prior, const float* eps_post, const float* nonterminals, const float* stash,
+                          const float* g_beliefs, const float* g_prior_states, const float* g_prior_means,
+                          const float* g_prior_std_devs, const float* g_posterior_states,
+                          const float* g_posterior_means, const float* g_posterior_std_devs, float* d_q, float* d_hq,
+                          float* d_p, float* d_hp, float* d_gi, float* d_gh, float* d_e, float* d_prev_belief,
+                          float* d_prev_state, int t1, int batch, int with_obs, int act_kind, float min_std_dev,
+                          void* stream);
 
 /* ---- cell: TransitionModel.compute_prior_state (rssm.py:42-50; embed == NULL) or
  * compute_posterior_state (rssm.py:52-64; embed (N,E)).  belief (N,D), eps (N,S) -> state, mean, std_dev (N,S). */

@@ -36,7 +36,7 @@ class MlpWeights(C.Structure):
 EXPORTS = [
     "repo_b200_version", "repo_b200_last_error", "repo_b200_device_info", "repo_b200_debug_flags", "repo_b200_debug_clock",
     "repo_b200_imagine_workspace_bytes", "repo_b200_imagine_fwd",
-    "repo_b200_observe_workspace_bytes", "repo_b200_observe_fwd",
+    "repo_b200_observe_workspace_bytes", "repo_b200_observe_fwd", "repo_b200_observe_stash_floats", "repo_b200_observe_bwd",
     "repo_b200_linear_workspace_bytes", "repo_b200_linear_fwd",
     "repo_b200_head_workspace_bytes", "repo_b200_head_fwd",
     "repo_b200_tanh_normal_entropy_fwd", "repo_b200_replay_gather",
@@ -73,8 +73,12 @@ def lib():
     L.repo_b200_observe_workspace_bytes.argtypes = [C.POINTER(Dims), ci, ci]
     L.repo_b200_observe_workspace_bytes.restype = sz
     L.repo_b200_observe_fwd.argtypes = (
-        [C.POINTER(Dims), C.POINTER(RssmWeights)] + [vp] * 15 + [ci, ci, ci, cf, vp, sz, ci, ci, vp])
+        [C.POINTER(Dims), C.POINTER(RssmWeights)] + [vp] * 16 + [ci, ci, ci, cf, vp, sz, ci, ci, vp])
     L.repo_b200_observe_fwd.restype = ci
+    L.repo_b200_observe_stash_floats.argtypes = [C.POINTER(Dims)]
+    L.repo_b200_observe_stash_floats.restype = ci
+    L.repo_b200_observe_bwd.argtypes = [C.POINTER(Dims), C.POINTER(RssmWeights)] + [vp] * 24 + [ci, ci, ci, ci, cf, vp]
+    L.repo_b200_observe_bwd.restype = ci
     L.repo_b200_head_workspace_bytes.argtypes = [C.POINTER(Dims)]
     L.repo_b200_head_workspace_bytes.restype = sz
     L.repo_b200_head_fwd.argtypes = [C.POINTER(Dims), C.POINTER(MlpWeights), vp, vp, vp, ci, ci, vp, sz, ci, ci, vp]

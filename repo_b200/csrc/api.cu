@@ -14,6 +14,7 @@
 #include "vm.cuh"
 #include "rows.cuh"
 #include "elementwise.cuh"
+#include "bwd.cuh"
 
 using namespace rb;
 
@@ -93,6 +94,7 @@ struct Builder {
     if (n_stages >= kMaxStages) overflow = true;
     s.gemm_begin = (uint8_t)n_gemms;
     s.bias_tile = (uint16_t)n_bias_tiles;
+    s.stash_off = 0xFFFF;
     return s;
   }
   void end_stage(VmStage& s, int epi, int flags, int ntiles, int acc_tile0, int nfeat, int act) {
@@ -108,10 +110,11 @@ struct Builder {
 
   // dense layer with activation: H = act(W src + b)
   void dense_to_h(const float* w, const float* b, int ld, int out_f, int col0, int ncols, int kofs, int ksl, int src,
-                  int src_k16, int act, int flags = 0) {
+                  int src_k16, int act, int flags = 0, int stash_off = 0xFFFF) {
     VmStage& s = begin_stage();
     gemm_rows(w, ld, 0, out_f, col0, ncols, kofs, ksl, src, src_k16, 0, 0);
     bias_rows(b, 0, nullptr, 0, out_f);
+    s.stash_off = (uint16_t)stash_off;
     end_stage(s, EPI_ACT_H, flags, cdiv(out_f, 128), 0, out_f, act);
   }
   // Gaussian head: rows [0,n) = mean -> tile 0, rows [n,2n) = raw std -> tile 1
@@ -124,11 +127,13 @@ struct Builder {
     end_stage(s, epi, flags, 1, 0, n, 0);
   }
   // fc_embed_state_action + GRUCell  (rssm.py:34-40)
-  void belief_update(const repo_b200_rssm_weights* W, int D, int S, int A, int act) {
+  // stash record per (t,row): [e D][r D][z D][n D][h_n D][prior hidden Hd][posterior hidden Hd]
+  void belief_update(const repo_b200_rssm_weights* W, int D, int S, int A, int act, bool stash = false) {
     const int kD16 = cdiv(D, 16), kx16 = cdiv(D + S + A, 16), kSA0 = D / 16, mtD = cdiv(D, 128);
     dense_to_h(W->fc_embed_state_action_w, W->fc_embed_state_action_b, S + A, D, 0, S + A, D - 16 * kSA0,
-               kx16 - kSA0, 0, kSA0, act);
+               kx16 - kSA0, 0, kSA0, act, 0, stash ? 0 : 0xFFFF);
     VmStage& s = begin_stage();
+    if (stash) s.stash_off = (uint16_t)D;
     for (int g = 0; g < 3; ++g)  // W_ih * hidden: r, z, i_n
       gemm_rows(W->rnn_w_ih, D, g * D, D, 0, D, 0, kD16, 1, 0, g * mtD, 0);
     for (int g = 0; g < 3; ++g)  // W_hh * belief: r, z accumulate; h_n separate
@@ -268,18 +273,20 @@ void build_imagine(Builder& b, const repo_b200_dims* d, const repo_b200_rssm_wei
   if (value) b.scalar_head(value, D, S, Hd, act, SF_SCALAR_VALUE);
 }
 
-void build_observe(Builder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W, bool with_obs, int act) {
+void build_observe(Builder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W, bool with_obs, int act,
+                   bool stash = false) {
   const int D = d->belief, S = d->state, A = d->action, Hd = d->hidden, E = d->embed;
   const int kD16 = cdiv(D, 16), kH16 = cdiv(Hd, 16);
   set_dims(b.P, d);
-  b.belief_update(W, D, S, A, act);
-  b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act);
+  b.belief_update(W, D, S, A, act, stash);
+  b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act, 0,
+               stash ? 5 * D : 0xFFFF);
   b.gaussian_head(W->fc_state_prior_w, W->fc_state_prior_b, Hd, S, kH16, EPI_PRIOR,
                   with_obs ? 0 : (SF_WRITES_STATE | SF_LOADS_ACTION));
   if (with_obs) {
     // belief half of fc_embed_belief_posterior; the embedding half was hoisted into `addend`
     b.dense_to_h(W->fc_embed_belief_posterior_w, W->fc_embed_belief_posterior_b, D + E, Hd, 0, D, 0, kD16, 0, 0, act,
-                 SF_ADDEND);
+                 SF_ADDEND, stash ? 5 * D + Hd : 0xFFFF);
     b.gaussian_head(W->fc_state_posterior_w, W->fc_state_posterior_b, Hd, S, kH16, EPI_POST,
                     SF_WRITES_STATE | SF_LOADS_ACTION);
   }
@@ -627,6 +634,43 @@ int repo_b200_replay_gather(const uint8_t* obs, const float* actions, const floa
   return 0;
 }
 
+int repo_b200_observe_stash_floats(const repo_b200_dims* d) { return d ? 5 * d->belief + 2 * d->hidden : 0; }
+
+int repo_b200_observe_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const float* prev_belief,
+                          const float* beliefs, const float* prior_std_devs, const float* post_std_devs,
+                          const float* eps_prior, const float* eps_post, const float* nonterminals, const float* stash,
+                          const float* g_beliefs, const float* g_prior_states, const float* g_prior_means,
+                          const float* g_prior_std_devs, const float* g_post_states, const float* g_post_means,
+                          const float* g_post_std_devs, float* d_q, float* d_hq, float* d_p, float* d_hp, float* d_gi,
+                          float* d_gh, float* d_e, float* d_prev_belief, float* d_prev_state, int t1, int batch,
+                          int with_obs, int act_kind, float min_std, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_act(act_kind))) return rc;
+  if (t1 < 0 || batch < 0) return fail(-1, "observe_bwd: bad sizes");
+  if (t1 == 0 || batch == 0) return 0;
+  if (!W || !beliefs || !prior_std_devs || !eps_prior || !stash || !d_p || !d_hp || !d_gi || !d_gh || !d_e)
+    return fail(-1, "observe_bwd: NULL pointer");
+  if (with_obs && (!post_std_devs || !eps_post || !d_q || !d_hq)) return fail(-1, "observe_bwd: posterior buffers missing");
+  ObsBwdParams P{};
+  P.T = t1; P.B = batch; P.D = d->belief; P.S = d->state; P.A = d->action; P.Hd = d->hidden; P.E = d->embed;
+  P.act = act_kind; P.with_obs = with_obs; P.min_std = min_std;
+  P.w_e = W->fc_embed_state_action_w; P.w_ih = W->rnn_w_ih; P.w_hh = W->rnn_w_hh;
+  P.w_p1 = W->fc_embed_belief_prior_w; P.w_p2 = W->fc_state_prior_w;
+  P.w_q1 = W->fc_embed_belief_posterior_w; P.w_q2 = W->fc_state_posterior_w;
+  P.init_belief = prev_belief; P.beliefs = beliefs; P.prior_sd = prior_std_devs; P.post_sd = post_std_devs;
+  P.eps_prior = eps_prior; P.eps_post = eps_post; P.nonterm = nonterminals;
+  P.stash = stash; P.stash_ld = 5 * d->belief + 2 * d->hidden;
+  P.g_beliefs = g_beliefs; P.g_prior_s = g_prior_states; P.g_prior_m = g_prior_means; P.g_prior_sd = g_prior_std_devs;
+  P.g_post_s = g_post_states; P.g_post_m = g_post_means; P.g_post_sd = g_post_std_devs;
+  P.d_q = d_q; P.d_hq = d_hq; P.d_p = d_p; P.d_hp = d_hp; P.d_gi = d_gi; P.d_gh = d_gh; P.d_e = d_e;
+  P.d_init_belief = d_prev_belief; P.d_init_state = d_prev_state;
+  const size_t smem = (size_t)(10 * P.D + 5 * P.S + P.Hd) * sizeof(float);
+  observe_bwd_kernel<<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ---- standalone Gaussian cells: compute_prior_state (rssm.py:42-50) / compute_posterior_state (rssm.py:52-64)
 static void build_cell(Builder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W, bool posterior, int act) {
   const int D = d->belief, S = d->state, Hd = d->hidden, E = d->embed;
@@ -739,8 +783,8 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
                           const float* prev_state, const float* actions, const float* embeds, const float* nonterm,
                           const float* eps_prior, const float* eps_post, float* beliefs, float* prior_states,
                           float* prior_means, float* prior_std_devs, float* post_states, float* post_means,
-                          float* post_std_devs, float* kl, int t1, int batch, int act_kind, float min_std, void* ws,
-                          size_t ws_bytes, int flags, int row_tile, void* stream) {
+                          float* post_std_devs, float* kl, float* stash, int t1, int batch, int act_kind, float min_std,
+                          void* ws, size_t ws_bytes, int flags, int row_tile, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
   if ((rc = check_act(act_kind))) return rc;
@@ -752,7 +796,7 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   if (with_obs && (!eps_post || !post_states || !post_means || !post_std_devs)) return fail(-1, "observe: posterior buffers missing");
   if (ws_bytes < repo_b200_observe_workspace_bytes(d, t1, batch)) return fail(-4, "observe: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool rows = use_rows_kernel(d, batch, row_tile);
+  const bool rows = !stash && use_rows_kernel(d, batch, row_tile);  // the activation stash is written by the vm kernel
   Builder b;
   RBuilder rbld;
   const size_t main = observe_main_bytes(d);
@@ -762,8 +806,10 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
     build_observe_rows(rbld, d, W, with_obs, act_kind);
     if ((rc = rbld.bind_and_pack(base, main, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
   } else {
-    build_observe(b, d, W, with_obs, act_kind);
+    build_observe(b, d, W, with_obs, act_kind, stash != nullptr);
     if ((rc = b.bind_and_pack(base, main, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
+    b.P.stash = stash;
+    b.P.stash_ld = 5 * d->belief + 2 * d->hidden;
   }
   float* addend = reinterpret_cast<float*>(base + main + lin);
   if (with_obs) {

@@ -1,0 +1,156 @@
+// Reverse-time pass of TransitionModel.observe (BPTT; the reference gets it from autograd over
+// rssm.py:116-133).  Small-batch design: one CTA per sequence (batch column), the whole time loop
+// on-chip, fp32.  Every product here is dx = W^T dy, i.e. thread k walks column k of the caller's
+// row-major W — consecutive threads read consecutive addresses, so the weights (L2-resident, 2.2 MB)
+// need no transposed copy.  The kernel emits the gradient of every pre-activation per (t,b); the
+// weight gradients are then plain batched GEMMs over those tensors (host side, repo_b200/autograd.py).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rb {
+
+struct ObsBwdParams {
+  int T, B, D, S, A, Hd, E;
+  int act, with_obs;
+  float min_std;
+  // weights: caller's fp32 tensors, row-major [out, in]
+  const float *w_e, *w_ih, *w_hh, *w_p1, *w_p2, *w_q1, *w_q2;
+  // forward tensors
+  const float *init_belief;          // (B, D) or null (zeros)
+  const float *beliefs;              // (T, B, D)
+  const float *prior_sd, *post_sd;   // (T, B, S)
+  const float *eps_prior, *eps_post; // (T, B, S)
+  const float *nonterm;              // (T, B) or null
+  const float *stash; int stash_ld;  // (T, B, ld): [e D][r D][z D][n D][h_n D][hp Hd][hq Hd]
+  // incoming gradients, each (T, B, feature) or null
+  const float *g_beliefs, *g_prior_s, *g_prior_m, *g_prior_sd, *g_post_s, *g_post_m, *g_post_sd;
+  // outputs: gradients of the pre-activations, time-major
+  float *d_q;   // (T, B, 2S)  posterior [mean | raw std]
+  float *d_hq;  // (T, B, Hd)  posterior hidden pre-activation
+  float *d_p;   // (T, B, 2S)
+  float *d_hp;  // (T, B, Hd)
+  float *d_gi;  // (T, B, 3D)  W_ih x + b_ih
+  float *d_gh;  // (T, B, 3D)  W_hh h + b_hh
+  float *d_e;   // (T, B, D)   fc_embed_state_action pre-activation
+  float *d_init_belief, *d_init_state;  // (B, D), (B, S) or null
+};
+
+__device__ __forceinline__ float act_grad_from_output(float y, int act) {
+  // derivative of the activation expressed through its OUTPUT: relu' = [y > 0]; elu' = y > 0 ? 1 : y + 1
+  if (act == 1) return y > 0.f ? 1.f : y + 1.f;
+  return y > 0.f ? 1.f : 0.f;
+}
+
+// out[k] = sum_j W[j*ld + k] * dy[j], j < n  (dy in shared memory, W column walk is coalesced over k)
+__device__ __forceinline__ float col_dot(const float* __restrict__ W, int ld, int k, const float* dy, int n) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int j = 0;
+  for (; j + 4 <= n; j += 4) {
+    a0 = fmaf(__ldg(W + (size_t)j * ld + k), dy[j], a0);
+    a1 = fmaf(__ldg(W + (size_t)(j + 1) * ld + k), dy[j + 1], a1);
+    a2 = fmaf(__ldg(W + (size_t)(j + 2) * ld + k), dy[j + 2], a2);
+    a3 = fmaf(__ldg(W + (size_t)(j + 3) * ld + k), dy[j + 3], a3);
+  }
+  for (; j < n; ++j) a0 = fmaf(__ldg(W + (size_t)j * ld + k), dy[j], a0);
+  return (a0 + a1) + (a2 + a3);
+}
+
+__global__ void __launch_bounds__(256) observe_bwd_kernel(const __grid_constant__ ObsBwdParams P) {
+  extern __shared__ float sm[];
+  const int D = P.D, S = P.S, A = P.A, Hd = P.Hd, T = P.T, B = P.B;
+  float* db = sm;            // D   recurrent dL/d belief_{t}
+  float* ds = db + D;        // S   recurrent dL/d state_{t} (the state fed into step t+1)
+  float* dq = ds + S;        // 2S
+  float* dp = dq + 2 * S;    // 2S
+  float* dh = dp + 2 * S;    // Hd  hidden pre-activation gradient (posterior, then prior)
+  float* dba = dh + Hd;      // D   accumulated dL/d belief_t
+  float* dgi = dba + D;      // 3D
+  float* dgh = dgi + 3 * D;  // 3D
+  float* de = dgh + 3 * D;   // D
+  const int b = blockIdx.x, k = threadIdx.x;
+  const int nth = blockDim.x;
+  for (int i = k; i < D; i += nth) db[i] = 0.f;
+  for (int i = k; i < S; i += nth) ds[i] = 0.f;
+  __syncthreads();
+
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t tb = (size_t)t * B + b;
+    const float* st = P.stash + tb * P.stash_ld;
+    // ---- Gaussian heads: gradient of [mean | raw std] ----
+    for (int j = k; j < S; j += nth) {
+      const size_t o = tb * S + j;
+      if (P.with_obs) {
+        const float gs = (P.g_post_s ? P.g_post_s[o] : 0.f) + ds[j];  // the posterior sample feeds step t+1
+        const float dmu = (P.g_post_m ? P.g_post_m[o] : 0.f) + gs;
+        const float dsd = (P.g_post_sd ? P.g_post_sd[o] : 0.f) + gs * P.eps_post[o];
+        dq[j] = dmu;
+        dq[S + j] = dsd * (1.f - __expf(-(P.post_sd[o] - P.min_std)));  // softplus' = 1 - exp(-softplus)
+      }
+      const float gsp = (P.g_prior_s ? P.g_prior_s[o] : 0.f) + (P.with_obs ? 0.f : ds[j]);
+      const float dmup = (P.g_prior_m ? P.g_prior_m[o] : 0.f) + gsp;
+      const float dsdp = (P.g_prior_sd ? P.g_prior_sd[o] : 0.f) + gsp * P.eps_prior[o];
+      dp[j] = dmup;
+      dp[S + j] = dsdp * (1.f - __expf(-(P.prior_sd[o] - P.min_std)));
+    }
+    __syncthreads();
+    if (P.with_obs)
+      for (int j = k; j < 2 * S; j += nth) P.d_q[tb * 2 * S + j] = dq[j];
+    for (int j = k; j < 2 * S; j += nth) P.d_p[tb * 2 * S + j] = dp[j];
+    // ---- posterior hidden layer ----
+    for (int i = k; i < D; i += nth) dba[i] = (P.g_beliefs ? P.g_beliefs[tb * D + i] : 0.f) + db[i];
+    if (P.with_obs) {
+      for (int i = k; i < Hd; i += nth) {
+        const float g = col_dot(P.w_q2, Hd, i, dq, 2 * S) * act_grad_from_output(st[5 * D + Hd + i], P.act);
+        dh[i] = g;
+        P.d_hq[tb * Hd + i] = g;
+      }
+      __syncthreads();
+      for (int i = k; i < D; i += nth) dba[i] += col_dot(P.w_q1, D + P.E, i, dh, Hd);
+      __syncthreads();
+    }
+    // ---- prior hidden layer ----
+    for (int i = k; i < Hd; i += nth) {
+      const float g = col_dot(P.w_p2, Hd, i, dp, 2 * S) * act_grad_from_output(st[5 * D + i], P.act);
+      dh[i] = g;
+      P.d_hp[tb * Hd + i] = g;
+    }
+    __syncthreads();
+    for (int i = k; i < D; i += nth) dba[i] += col_dot(P.w_p1, D, i, dh, Hd);
+    __syncthreads();
+    // ---- GRU cell ----
+    for (int i = k; i < D; i += nth) {
+      const float r = st[D + i], z = st[2 * D + i], n = st[3 * D + i], hn = st[4 * D + i];
+      const float bprev = t > 0 ? P.beliefs[(tb - B) * D + i] : (P.init_belief ? P.init_belief[(size_t)b * D + i] : 0.f);
+      const float g = dba[i];
+      const float dnp = g * (1.f - z) * (1.f - n * n);
+      const float dzp = g * (bprev - n) * z * (1.f - z);
+      const float drp = dnp * hn * r * (1.f - r);
+      dgi[i] = drp; dgi[D + i] = dzp; dgi[2 * D + i] = dnp;
+      dgh[i] = drp; dgh[D + i] = dzp; dgh[2 * D + i] = dnp * r;
+      db[i] = g * z;  // direct path to belief_{t-1}; W_hh^T dgh is added below
+      float* o_gi = P.d_gi + tb * 3 * D;
+      float* o_gh = P.d_gh + tb * 3 * D;
+      o_gi[i] = drp; o_gi[D + i] = dzp; o_gi[2 * D + i] = dnp;
+      o_gh[i] = drp; o_gh[D + i] = dzp; o_gh[2 * D + i] = dnp * r;
+    }
+    __syncthreads();
+    for (int i = k; i < D; i += nth) {
+      const float g = col_dot(P.w_ih, D, i, dgi, 3 * D) * act_grad_from_output(st[i], P.act);
+      de[i] = g;
+      P.d_e[tb * D + i] = g;
+      db[i] += col_dot(P.w_hh, D, i, dgh, 3 * D);
+    }
+    __syncthreads();
+    // ---- state that entered this step: s_{t-1} * nonterm[t] ----
+    const float nt = P.nonterm ? P.nonterm[tb] : 1.f;
+    for (int j = k; j < S; j += nth) ds[j] = col_dot(P.w_e, S + A, j, de, D) * nt;
+    __syncthreads();
+  }
+  if (P.d_init_belief)
+    for (int i = k; i < D; i += nth) P.d_init_belief[(size_t)b * D + i] = db[i];
+  if (P.d_init_state)
+    for (int j = k; j < S; j += nth) P.d_init_state[(size_t)b * S + j] = ds[j];
+}
+
+}  // namespace rb

@@ -65,6 +65,8 @@ struct VmStage {
   uint16_t bias_tile; // first 128-float bias tile
   uint8_t act;        // ActKind of EPI_ACT_H (the actor is always ELU, actor_critic.py:58)
   uint8_t pad;
+  uint16_t stash_off; // EPI_ACT_H / EPI_GRU: float offset inside a (t,row) stash record, 0xFFFF = not stashed
+  uint16_t pad2;
 };
 
 struct VmParams {
@@ -99,6 +101,7 @@ struct VmParams {
   float* returns;            // (T-1, N) or null
   float* out; int out_ld;    // EPI_STORE
   int dbg_flags;             // bring-up only: bit0 swaps LBO/SBO in the smem descriptors
+  float* stash; int stash_ld; // backward stash: (T, N, stash_ld) activations the reverse pass needs, or null
   long long* dbg_clock;      // profiling only: CTA 0 writes [step][stage][2] clock64 stamps (epilogue begin/end)
   VmStage stages[kMaxStages];
   VmGemm gemms[kMaxGemms];
@@ -169,6 +172,7 @@ __device__ __forceinline__ void epi_act_h(const VmParams& P, const VmStage& st, 
     const int f = tile * 128 + lf;
     const bool vf = f < nfeat;
     const float bias = P.bias[(st.bias_tile + tile) * 128 + lf];
+    float* stash = (P.stash && st.stash_off != 0xFFFF) ? P.stash + trow * P.stash_ld + st.stash_off : nullptr;
     uint8_t* bh = h_hi + TL::off(0, f);
     uint8_t* bl = h_lo + TL::off(0, f);
 #pragma unroll 1
@@ -184,10 +188,12 @@ __device__ __forceinline__ void epi_act_h(const VmParams& P, const VmStage& st, 
           float x = v[i] + bias;
           if (addend) x += ad[i];
           __half h, l;
-          split_f16(act_t<ACT>(x), h, l);
+          const float y = act_t<ACT>(x);
+          split_f16(y, h, l);
           const uint32_t o = (uint32_t)c * 256u + (uint32_t)(i >> 3) * 128u + (uint32_t)(i & 7) * 16u;
           *reinterpret_cast<__half*>(bh + o) = h;
           *reinterpret_cast<__half*>(bl + o) = l;
+          if (stash && r0 + i < N) stash[(size_t)(r0 + i) * P.stash_ld + f] = y;
         }
       }
     }
@@ -427,9 +433,14 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
                   for (int i = 0; i < 16; ++i) {
                     const float r = sigmoid_f(vr[i] + br);
                     const float z = sigmoid_f(vz[i] + bz);
-                    const float nn = tanh_f(vi[i] + bin + r * (vh[i] + bhn));
+                    const float hn = vh[i] + bhn;
+                    const float nn = tanh_f(vi[i] + bin + r * hn);
                     bn[i] = (1.f - z) * nn + z * bo[i];
                     TL::put(x_hi, x_lo, c * 16 + i, u, bn[i]);
+                    if (P.stash && st.stash_off != 0xFFFF && r0 + i < N) {
+                      float* sp = P.stash + (trow + r0 + i) * P.stash_ld + st.stash_off + u;
+                      sp[0] = r; sp[D] = z; sp[2 * D] = nn; sp[3 * D] = hn;
+                    }
                   }
 #pragma unroll
                   for (int i = 0; i < 16; ++i)

@@ -117,8 +117,10 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], row_tile
 
 def observe_fwd(params: Dict[str, torch.Tensor], prev_belief, prev_state, actions, embeds, nonterms,
                 eps_prior, eps_post, act: str = "elu", min_std: float = 0.1, want_kl: bool = True,
-                row_tile: int = 0, workspace: Optional[torch.Tensor] = None, packed: bool = False):
-    """TransitionModel.observe forward (rssm.py:76-146). Returns (list of 7 or 4 tensors, kl (T1,B) or None)."""
+                row_tile: int = 0, workspace: Optional[torch.Tensor] = None, packed: bool = False,
+                stash: Optional[torch.Tensor] = None):
+    """TransitionModel.observe forward (rssm.py:76-146). Returns (list of 7 or 4 tensors, kl (T1,B) or None,
+    workspace).  `stash` (T1,B,5D+2H), when given, receives the activations the backward pass needs."""
     L = _lib.lib()
     keep = _Keep()
     d = dims_of(params)
@@ -147,7 +149,7 @@ def observe_fwd(params: Dict[str, torch.Tensor], prev_belief, prev_state, action
     o = outs + [None] * (7 - len(outs))
     rc = L.repo_b200_observe_fwd(
         C.byref(d), C.byref(W), _ptr(prev_belief), _ptr(prev_state), _ptr(actions), _ptr(embeds), _ptr(nonterms),
-        _ptr(eps_prior), _ptr(eps_post), *[_ptr(t) for t in o], _ptr(kl), T1, B, act_kind(act), float(min_std),
+        _ptr(eps_prior), _ptr(eps_post), *[_ptr(t) for t in o], _ptr(kl), _ptr(stash), T1, B, act_kind(act), float(min_std),
         _ptr(workspace), workspace.numel(), _lib.WEIGHTS_PACKED if packed else 0, row_tile, _stream())
     _lib.check(rc, "repo_b200_observe_fwd")
     return outs, kl, workspace

@@ -88,7 +88,9 @@ class TransitionModel(nn.Module):
                 eps_post = eps_post_d
         elif with_obs and eps_post is None:
             raise ValueError("eps_post must be given together with eps_prior when observations are passed")
-        self._require_no_grad("observe", [prev_belief, prev_state, actions, observations])
+        if self._wants_grad([prev_belief, prev_state, observations]):
+            from . import autograd as _ag  # forward kernel + stash, hand-written BPTT kernel in backward
+            return _ag.observe(self, prev_belief, prev_state, actions, observations, nonterminals, eps_prior, eps_post)
         outs, kl, ws = ops.observe_fwd(_named(self), prev_belief, prev_state, actions, observations, nonterminals,
                                        eps_prior, eps_post, act=self.activation_function, min_std=self.min_std_dev,
                                        workspace=self._ws.get("observe"))
@@ -143,8 +145,10 @@ class TransitionModel(nn.Module):
 
     # cell-level methods (rssm.py:34-64) run as one-step programs of the same machine
     def compute_belief(self, prev_belief, state, action):
-        outs = self.observe(prev_belief, state, action.unsqueeze(0),
-                            eps_prior=torch.zeros(1, state.shape[0], self.state_size, device=state.device))
+        self._require_no_grad("compute_belief", [prev_belief, state, action])
+        with torch.no_grad():
+            outs = self.observe(prev_belief, state, action.unsqueeze(0),
+                                eps_prior=torch.zeros(1, state.shape[0], self.state_size, device=state.device))
         return outs[0][0]
 
     def compute_prior_state(self, belief, *, eps=None):
@@ -162,6 +166,11 @@ class TransitionModel(nn.Module):
         return ops.cell_fwd(_named(self), belief, observation, eps, act=self.activation_function, min_std=self.min_std_dev)
 
     # ------------------------------------------------------------------ helpers
+    def _wants_grad(self, tensors) -> bool:
+        if not torch.is_grad_enabled():
+            return False
+        return any(p.requires_grad for p in self.parameters()) or any(t is not None and t.requires_grad for t in tensors)
+
     def _require_no_grad(self, what, tensors, extra=()):
         if not torch.is_grad_enabled():
             return

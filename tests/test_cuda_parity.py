@@ -283,3 +283,76 @@ def test_cell_methods_match_oracle(dev):
     for got, want, nm in zip(qs, O.compute_posterior_state(params, wb, embed, e2), ("post_state", "post_mean", "post_std")):
         close(got, want, nm)
     assert len(step) == 7 and torch.equal(step[0], b1) and torch.equal(step[4], qs[0])
+
+
+def _autograd_reference(params, x, R, with_obs, use_nt):
+    """fp64 torch autograd through the oracle: loss = sum_i <R_i, out_i> (+ KL terms via the same outputs)."""
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    f = lambda k: None if x[k] is None else x[k].double()
+    emb = f("embeds")
+    if emb is not None:
+        emb.requires_grad_(True)
+    outs = O.observe(p64, f("prev_belief"), f("prev_state"), f("actions"), emb, f("nonterms") if use_nt else None,
+                     f("eps_prior"), f("eps_post"))
+    loss = sum((r.double() * o).sum() for r, o in zip(R, outs))
+    if with_obs:
+        loss = loss + O.kl_sum(outs[5], outs[6], outs[2], outs[3]).mean()
+    loss.backward()
+    return {k: v.grad for k, v in p64.items()}, (emb.grad if emb is not None else None)
+
+
+@pytest.mark.parametrize("name", ["observe_T8_B10", "observe_T8_B10_hot", "observe_prior_only", "observe_no_nonterm", "observe_tiny_dims"])
+def test_observe_backward_matches_autograd_of_the_oracle(dev, name):
+    """BPTT through the hand-written reverse-time kernel vs fp64 autograd of the oracle (the reference
+    obtains these gradients from autograd over rssm.py:116-133)."""
+    from repo_b200.rssm import TransitionModel
+    params, x, gold, meta = C.observe_case(name)
+    dims = C.dims_of(meta)
+    with_obs, use_nt = bool(meta["use_obs"]), bool(meta["use_nt"])
+    n_out = 7 if with_obs else 4
+    T1, B = x["actions"].shape[:2]
+    rs = np.random.RandomState(3)
+    feat = [dims["belief"]] + [dims["state"]] * 6
+    R = [torch.from_numpy(rs.standard_normal((T1, B, f)).astype(np.float32)) for f in feat[:n_out]]
+    want, want_emb = _autograd_reference(params, x, R, with_obs, use_nt)
+
+    m = TransitionModel(dims["belief"], dims["state"], dims["action"], dims["hidden"], dims["embed"], "elu").to(dev)
+    m.load_state_dict(params)
+    g = lambda k: None if x[k] is None else x[k].to(dev)
+    emb = g("embeds")
+    if emb is not None:
+        emb.requires_grad_(True)
+    outs = m.observe(g("prev_belief"), g("prev_state"), g("actions"), emb, g("nonterms") if use_nt else None,
+                     eps_prior=g("eps_prior"), eps_post=g("eps_post"))
+    loss = sum((r.to(dev) * o).sum() for r, o in zip(R, outs))
+    if with_obs:
+        post_m, post_sd, pri_m, pri_sd = outs[5], outs[6], outs[2], outs[3]
+        vr = (post_sd / pri_sd) ** 2
+        loss = loss + (0.5 * (vr + ((post_m - pri_m) / pri_sd) ** 2 - 1 - vr.log())).sum(2).mean()
+    loss.backward()
+    got = {k: v.grad for k, v in m.named_parameters()}
+    for k, w in want.items():
+        if not with_obs and "posterior" in k:
+            assert got[k] is None or float(got[k].abs().max()) == 0.0
+            continue
+        scale = float(w.abs().max()) + 1e-12
+        np.testing.assert_allclose(got[k].cpu().double().numpy() / scale, w.numpy() / scale, rtol=1e-3, atol=2e-4, err_msg=k)
+    if with_obs:
+        scale = float(want_emb.abs().max())
+        np.testing.assert_allclose(emb.grad.cpu().double().numpy() / scale, want_emb.numpy() / scale, rtol=1e-3, atol=2e-4)
+
+
+def test_frozen_parameters_get_no_gradient(dev):
+    """FreezeParameters (common/utils.py:47-58) sets requires_grad=False at call time."""
+    from repo_b200.rssm import TransitionModel
+    params, x, gold, meta = C.observe_case("observe_T2_B1")
+    m = TransitionModel(200, 30, 6, 200, 1024, "elu").to(dev)
+    m.load_state_dict(params)
+    for n, p in m.named_parameters():
+        p.requires_grad = n.startswith("rnn")
+    g = lambda k: x[k].to(dev)
+    outs = m.observe(g("prev_belief"), g("prev_state"), g("actions"), g("embeds"), g("nonterms"),
+                     eps_prior=g("eps_prior"), eps_post=g("eps_post"))
+    outs[0].sum().backward()
+    for n, p in m.named_parameters():
+        assert (p.grad is not None) == n.startswith("rnn"), n
