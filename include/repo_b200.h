@@ -75,8 +75,25 @@ int repo_b200_imagine_fwd(const repo_b200_dims* dims, const repo_b200_rssm_weigh
                           float* prior_means, float* prior_std_devs, float* actions, float* rewards, float* values,
                           float* returns, int horizon, int n_rows, int act_kind, float min_std_dev,
                           float actor_mean_scale, float actor_init_std, float actor_min_std, float gamma,
-                          float lambda_, void* workspace, size_t workspace_bytes, int flags, int row_tile,
-                          void* stream);
+                          float lambda_, float* stash, void* workspace, size_t workspace_bytes, int flags,
+                          int row_tile, void* stream);
+
+/* ---- imagine backward: what autograd derives from rssm.py:167-176 + actor_critic.py:76-102 in the reference,
+ * with the actor's inputs detached (rssm.py:170).  `stash` (H-1,N,repo_b200_imagine_stash_floats) is written by
+ * repo_b200_imagine_fwd when non-NULL: per (t,row) [embed hidden D][r D][z D][n D][h_n D][prior hidden H]
+ * [actor h1..h4 4H][action mean A][action std A].  g_*: incoming gradients of the four outputs (nullable).
+ * Outputs: pre-activation gradients of the transition layers (d_p (.,2S), d_hp (.,H), d_gi/d_gh (.,3D), d_e (.,D))
+ * and of the actor's fc5..fc1 (d_a5 (.,2A), d_a4..d_a1 (.,H)), plus gradients of the start rows (nullable). */
+int repo_b200_imagine_stash_floats(const repo_b200_dims* dims);
+int repo_b200_imagine_bwd(const repo_b200_dims* dims, const repo_b200_rssm_weights* rssm,
+                          const repo_b200_mlp_weights* actor, const float* start_belief, const float* beliefs,
+                          const float* actions, const float* prior_std_devs, const float* eps_prior,
+                          const float* eps_action, const float* stash, const float* g_beliefs,
+                          const float* g_prior_states, const float* g_prior_means, const float* g_prior_std_devs,
+                          float* d_p, float* d_hp, float* d_gi, float* d_gh, float* d_e, float* d_a5, float* d_a4,
+                          float* d_a3, float* d_a2, float* d_a1, float* d_start_belief, float* d_start_state,
+                          int horizon, int n_rows, int act_kind, float min_std_dev, float actor_mean_scale,
+                          float actor_min_std, void* stream);
 
 /* ---- observe: TransitionModel.observe (rssm.py:76-146) fused with the per-(t,b) Gaussian KL
  * KL(posterior || prior).sum(state) used by dreamer.py:278-282 / repo.py:63-83.

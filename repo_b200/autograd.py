@@ -119,3 +119,97 @@ def observe(model, prev_belief, prev_state, actions, observations, nonterminals,
         return list(outs)
     model.last_kl = None
     return list(res)
+
+
+ACTOR_KEYS = [f"fc{i}.{w}" for i in range(1, 6) for w in ("weight", "bias")]
+
+
+class ImagineFn(torch.autograd.Function):
+    """TransitionModel.imagine under autograd (rssm.py:148-184).  Gradients reach the actor's parameters
+    (outputs -> frozen-or-not dynamics -> action sample -> actor) and the start rows; the actor's inputs
+    are detached exactly like `policy.get_action(belief.detach(), state.detach())` (rssm.py:170)."""
+
+    @staticmethod
+    def forward(ctx, act, min_std, horizon, a_scalars, prev_belief, prev_state, eps_action, eps_prior, *params):
+        tp, ap = params[:len(PARAM_KEYS)], params[len(PARAM_KEYS):]
+        named, anamed = dict(zip(PARAM_KEYS, tp)), dict(zip(ACTOR_KEYS, ap))
+        d = ops.dims_of(named)
+        N, T = prev_belief.shape[0], horizon - 1
+        L = _lib.lib()
+        stash = torch.empty(T, N, L.repo_b200_imagine_stash_floats(C.byref(d)), device=prev_belief.device, dtype=torch.float32)
+        mean_scale, init_std, a_min_std = a_scalars
+        out = ops.imagine_fwd({k: v.detach() for k, v in named.items()}, {k: v.detach() for k, v in anamed.items()}, None, None,
+                              prev_belief.detach(), prev_state.detach(), eps_action, eps_prior, horizon, act=act,
+                              min_std=min_std, mean_scale=mean_scale, init_std=init_std, actor_min_std=a_min_std, stash=stash)
+        ctx.meta = (act, min_std, horizon, a_scalars, d)
+        outs = (out["beliefs"], out["prior_states"], out["prior_means"], out["prior_std_devs"])
+        ctx.save_for_backward(prev_belief, prev_state, eps_action, eps_prior, stash, out["actions"], *outs, *params)
+        ctx.mark_non_differentiable(out["actions"])
+        return (*outs, out["actions"])
+
+    @staticmethod
+    def backward(ctx, g_b, g_s, g_m, g_sd, _g_actions):
+        act, min_std, horizon, (mean_scale, init_std, a_min_std), d = ctx.meta
+        sv = ctx.saved_tensors
+        prev_belief, prev_state, eps_action, eps_prior, stash, actions = sv[:6]
+        beliefs, prior_s, prior_m, prior_sd = sv[6:10]
+        params = sv[10:]
+        tp, ap = params[:len(PARAM_KEYS)], params[len(PARAM_KEYS):]
+        named, anamed = dict(zip(PARAM_KEYS, tp)), dict(zip(ACTOR_KEYS, ap))
+        D, S, A, Hd = d.belief, d.state, d.action, d.hidden
+        N, T = prev_belief.shape[0], horizon - 1
+        dev = prev_belief.device
+        c = lambda g: None if g is None else g.contiguous().float()
+        mk = lambda f: torch.empty(T, N, f, device=dev, dtype=torch.float32)
+        d_p, d_hp, d_gi, d_gh, d_e = mk(2 * S), mk(Hd), mk(3 * D), mk(3 * D), mk(D)
+        d_a5, d_a4, d_a3, d_a2, d_a1 = mk(2 * A), mk(Hd), mk(Hd), mk(Hd), mk(Hd)
+        need_b0, need_s0 = ctx.needs_input_grad[4], ctx.needs_input_grad[5]
+        d_b0 = torch.empty(N, D, device=dev) if (need_b0 or need_s0) else None
+        d_s0 = torch.empty(N, S, device=dev) if (need_b0 or need_s0) else None
+        keep = ops._Keep()
+        W = ops.rssm_struct(named, keep)
+        Am = ops.mlp_struct(anamed, 5, keep, "actor")
+        p = ops._ptr
+        rc = _lib.lib().repo_b200_imagine_bwd(
+            C.byref(d), C.byref(W), C.byref(Am), p(prev_belief.contiguous()), p(beliefs), p(actions), p(prior_sd), p(eps_prior),
+            p(eps_action), p(stash), p(c(g_b)), p(c(g_s)), p(c(g_m)), p(c(g_sd)), p(d_p), p(d_hp), p(d_gi), p(d_gh), p(d_e),
+            p(d_a5), p(d_a4), p(d_a3), p(d_a2), p(d_a1), p(d_b0), p(d_s0), horizon, N, ops.act_kind(act), float(min_std),
+            float(mean_scale), float(a_min_std), ops._stream())
+        _lib.check(rc, "repo_b200_imagine_bwd")
+
+        flat = lambda x: x.reshape(T * N, -1)
+        need = dict(zip(PARAM_KEYS + ["actor." + k for k in ACTOR_KEYS], ctx.needs_input_grad[8:]))
+        gp = {k: None for k in need}
+
+        def lin(wkey, bkey, dpre, inp):
+            if need[wkey]:
+                gp[wkey] = flat(dpre).t() @ flat(inp)
+            if need[bkey]:
+                gp[bkey] = flat(dpre).sum(0)
+
+        b_in = torch.cat([prev_belief.unsqueeze(0), beliefs[:-1]], 0)
+        s_in = torch.cat([prev_state.unsqueeze(0), prior_s[:-1]], 0)
+        off = 5 * D + Hd
+        e, hp = stash[..., :D], stash[..., 5 * D:5 * D + Hd]
+        h = [stash[..., off + i * Hd: off + (i + 1) * Hd] for i in range(4)]
+        lin("fc_embed_state_action.weight", "fc_embed_state_action.bias", d_e, torch.cat([s_in, actions], -1))
+        lin("rnn.weight_ih", "rnn.bias_ih", d_gi, e)
+        lin("rnn.weight_hh", "rnn.bias_hh", d_gh, b_in)
+        lin("fc_embed_belief_prior.weight", "fc_embed_belief_prior.bias", d_hp, beliefs)
+        lin("fc_state_prior.weight", "fc_state_prior.bias", d_p, hp)
+        lin("actor.fc1.weight", "actor.fc1.bias", d_a1, torch.cat([b_in, s_in], -1))
+        lin("actor.fc2.weight", "actor.fc2.bias", d_a2, h[0])
+        lin("actor.fc3.weight", "actor.fc3.bias", d_a3, h[1])
+        lin("actor.fc4.weight", "actor.fc4.bias", d_a4, h[2])
+        lin("actor.fc5.weight", "actor.fc5.bias", d_a5, h[3])
+        return (None, None, None, None, d_b0 if need_b0 else None, d_s0 if need_s0 else None, None, None,
+                *[gp[k] for k in PARAM_KEYS], *[gp["actor." + k] for k in ACTOR_KEYS])
+
+
+def imagine(model, prev_belief, prev_state, policy, horizon, eps_action, eps_prior):
+    tparams = [dict(model.named_parameters())[k] for k in PARAM_KEYS]
+    aparams = [dict(policy.named_parameters())[k] for k in ACTOR_KEYS]
+    scal = (float(policy._mean_scale), float(policy._init_std), float(policy._min_std))
+    *outs, actions = ImagineFn.apply(model.activation_function, model.min_std_dev, horizon, scal, prev_belief, prev_state,
+                                     eps_action, eps_prior, *tparams, *aparams)
+    return list(outs), actions

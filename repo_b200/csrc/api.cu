@@ -118,8 +118,9 @@ struct Builder {
     end_stage(s, EPI_ACT_H, flags, cdiv(out_f, 128), 0, out_f, act);
   }
   // Gaussian head: rows [0,n) = mean -> tile 0, rows [n,2n) = raw std -> tile 1
-  void gaussian_head(const float* w, const float* b, int ld, int n, int ksl, int epi, int flags) {
+  void gaussian_head(const float* w, const float* b, int ld, int n, int ksl, int epi, int flags, int stash_off = 0xFFFF) {
     VmStage& s = begin_stage();
+    s.stash_off = (uint16_t)stash_off;
     gemm_tile(w, ld, 0, n, 0, ld, 0, ksl, 1, 0, 0, 0);
     gemm_tile(w, ld, n, n, 0, ld, 0, ksl, 1, 0, 1, 0);
     bias_tile(b, 0, nullptr, 0, n);
@@ -256,18 +257,22 @@ void set_dims(VmParams& P, const repo_b200_dims* d) {
   P.kh16 = cdiv(std::max(d->belief, d->hidden), 16);
 }
 
+// imagine stash record per (t,row): [e D][r D][z D][n D][h_n D][prior hidden H][actor h1..h4 4H][action mean A][action std A]
 void build_imagine(Builder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W,
                    const repo_b200_mlp_weights* actor, const repo_b200_mlp_weights* reward,
-                   const repo_b200_mlp_weights* value, int act) {
+                   const repo_b200_mlp_weights* value, int act, bool stash = false) {
   const int D = d->belief, S = d->state, A = d->action, Hd = d->hidden;
   const int kD16 = cdiv(D, 16), kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);
+  const int so = 5 * D + Hd;  // actor block of the stash
   set_dims(b.P, d);
   // actor (always ELU: actor_critic.py:58 + the positional-arg quirk at dreamer.py:99-105)
-  b.dense_to_h(actor->w[0], actor->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, ACT_ELU);
-  for (int i = 1; i < 4; ++i) b.dense_to_h(actor->w[i], actor->b[i], Hd, Hd, 0, Hd, 0, kH16, 1, 0, ACT_ELU);
-  b.gaussian_head(actor->w[4], actor->b[4], Hd, A, kH16, EPI_ACTION, 0);
-  b.belief_update(W, D, S, A, act);
-  b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act);
+  b.dense_to_h(actor->w[0], actor->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, ACT_ELU, 0, stash ? so : 0xFFFF);
+  for (int i = 1; i < 4; ++i)
+    b.dense_to_h(actor->w[i], actor->b[i], Hd, Hd, 0, Hd, 0, kH16, 1, 0, ACT_ELU, 0, stash ? so + i * Hd : 0xFFFF);
+  b.gaussian_head(actor->w[4], actor->b[4], Hd, A, kH16, EPI_ACTION, 0, stash ? so + 4 * Hd : 0xFFFF);
+  b.belief_update(W, D, S, A, act, stash);
+  b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act, 0,
+               stash ? 5 * D : 0xFFFF);
   b.gaussian_head(W->fc_state_prior_w, W->fc_state_prior_b, Hd, S, kH16, EPI_PRIOR, SF_WRITES_STATE);
   if (reward) b.scalar_head(reward, D, S, Hd, act, 0);
   if (value) b.scalar_head(value, D, S, Hd, act, SF_SCALAR_VALUE);
@@ -565,8 +570,8 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
                           const float* eps_prior, float* beliefs, float* prior_states, float* prior_means,
                           float* prior_std_devs, float* actions, float* rewards, float* values, float* returns,
                           int horizon, int n_rows, int act_kind, float min_std, float a_mean_scale, float a_init_std,
-                          float a_min_std, float gamma, float lambda_, void* ws, size_t ws_bytes, int flags,
-                          int row_tile, void* stream) {
+                          float a_min_std, float gamma, float lambda_, float* stash, void* ws, size_t ws_bytes,
+                          int flags, int row_tile, void* stream) {
   int rc = check_dims(d);
   if (rc) return rc;
   if ((rc = check_act(act_kind))) return rc;
@@ -579,15 +584,17 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
     return fail(-1, "imagine: NULL input/output pointer");
   if ((reward && !rewards) || (value && !values)) return fail(-1, "imagine: rewards/values output missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool rows = use_rows_kernel(d, n_rows, row_tile);
+  const bool rows = !stash && use_rows_kernel(d, n_rows, row_tile);  // the activation stash is written by the vm kernel
   Builder b;
   RBuilder rbld;
   if (rows) {
     build_imagine_rows(rbld, d, W, actor, reward, value, act_kind);
     if ((rc = rbld.bind_and_pack(ws, ws_bytes, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
   } else {
-    build_imagine(b, d, W, actor, reward, value, act_kind);
+    build_imagine(b, d, W, actor, reward, value, act_kind, stash != nullptr);
     if ((rc = b.bind_and_pack(ws, ws_bytes, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
+    b.P.stash = stash;
+    b.P.stash_ld = 5 * d->belief + 5 * d->hidden + 2 * d->action;
   }
   VmParams& P = rows ? rbld.P.v : b.P;
   P.n_steps = horizon - 1;
@@ -667,6 +674,50 @@ int repo_b200_observe_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   P.d_init_belief = d_prev_belief; P.d_init_state = d_prev_state;
   const size_t smem = (size_t)(10 * P.D + 5 * P.S + P.Hd) * sizeof(float);
   observe_bwd_kernel<<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int repo_b200_imagine_stash_floats(const repo_b200_dims* d) { return d ? 5 * d->belief + 5 * d->hidden + 2 * d->action : 0; }
+
+int repo_b200_imagine_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const repo_b200_mlp_weights* actor,
+                          const float* start_belief, const float* beliefs, const float* actions,
+                          const float* prior_std_devs, const float* eps_prior, const float* eps_action, const float* stash,
+                          const float* g_beliefs, const float* g_prior_states, const float* g_prior_means,
+                          const float* g_prior_std_devs, float* d_p, float* d_hp, float* d_gi, float* d_gh, float* d_e,
+                          float* d_a5, float* d_a4, float* d_a3, float* d_a2, float* d_a1, float* d_start_belief,
+                          float* d_start_state, int horizon, int n_rows, int act_kind, float min_std,
+                          float a_mean_scale, float a_min_std, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_act(act_kind))) return rc;
+  if (horizon < 1 || n_rows < 0) return fail(-1, "imagine_bwd: bad sizes");
+  if (horizon == 1 || n_rows == 0) return 0;
+  if (!W || !actor || actor->n_layers != 5) return fail(-1, "imagine_bwd: weights missing");
+  if (!start_belief || !beliefs || !actions || !prior_std_devs || !eps_prior || !eps_action || !stash || !d_p || !d_hp ||
+      !d_gi || !d_gh || !d_e || !d_a5 || !d_a4 || !d_a3 || !d_a2 || !d_a1)
+    return fail(-1, "imagine_bwd: NULL pointer");
+  ImgBwdParams P{};
+  P.T = horizon - 1; P.N = n_rows; P.D = d->belief; P.S = d->state; P.A = d->action; P.Hd = d->hidden;
+  P.act = act_kind; P.min_std = min_std; P.a_mean_scale = a_mean_scale; P.a_min_std = a_min_std;
+  P.w_e = W->fc_embed_state_action_w; P.w_ih = W->rnn_w_ih; P.w_hh = W->rnn_w_hh;
+  P.w_p1 = W->fc_embed_belief_prior_w; P.w_p2 = W->fc_state_prior_w;
+  P.w_a2 = actor->w[1]; P.w_a3 = actor->w[2]; P.w_a4 = actor->w[3]; P.w_a5 = actor->w[4];
+  P.start_belief = start_belief; P.beliefs = beliefs; P.actions = actions; P.prior_sd = prior_std_devs;
+  P.eps_prior = eps_prior; P.eps_action = eps_action;
+  P.stash = stash; P.stash_ld = repo_b200_imagine_stash_floats(d);
+  P.g_beliefs = g_beliefs; P.g_prior_s = g_prior_states; P.g_prior_m = g_prior_means; P.g_prior_sd = g_prior_std_devs;
+  P.d_p = d_p; P.d_hp = d_hp; P.d_gi = d_gi; P.d_gh = d_gh; P.d_e = d_e;
+  P.d_a5 = d_a5; P.d_a4 = d_a4; P.d_a3 = d_a3; P.d_a2 = d_a2; P.d_a1 = d_a1;
+  P.d_start_belief = d_start_belief; P.d_start_state = d_start_state;
+  constexpr int RB = 8;
+  const size_t smem = (size_t)(9 * P.D + 3 * P.S + 2 * P.Hd + 2 * P.A) * RB * sizeof(float);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CUDA_OK(cudaFuncSetAttribute(imagine_bwd_kernel<RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  imagine_bwd_kernel<RB><<<cdiv(n_rows, RB), 256, smem, static_cast<cudaStream_t>(stream)>>>(P);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -154,3 +154,218 @@ __global__ void __launch_bounds__(256) observe_bwd_kernel(const __grid_constant_
 }
 
 }  // namespace rb
+
+namespace rb {
+
+// =====================================================================================================
+// Reverse-time pass of TransitionModel.imagine (rssm.py:167-176) incl. the tanh-Normal actor
+// (actor_critic.py:76-102).  RB rows per CTA share every weight read (the rollout has thousands of
+// rows, so L2 traffic — not latency — is what matters here).  The actor's INPUTS are detached in the
+// reference (rssm.py:170): gradients flow  outputs -> dynamics -> action -> actor parameters  and
+// outputs -> dynamics -> earlier (belief, state), never through the actor's inputs.
+// =====================================================================================================
+struct ImgBwdParams {
+  int T, N, D, S, A, Hd;
+  int act;
+  float min_std, a_mean_scale, a_min_std;
+  const float *w_e, *w_ih, *w_hh, *w_p1, *w_p2;   // transition weights
+  const float *w_a2, *w_a3, *w_a4, *w_a5;         // actor fc2..fc5 (fc1 only receives d1 as a weight gradient)
+  const float *start_belief;                      // (N, D)
+  const float *beliefs, *actions;                 // (T, N, D), (T, N, A)
+  const float *prior_sd, *eps_prior, *eps_action; // (T, N, S), (T, N, S), (T, N, A)
+  const float *stash; int stash_ld;               // [e D][r D][z D][n D][h_n D][hp H][h1..h4 4H][mean A][std A]
+  const float *g_beliefs, *g_prior_s, *g_prior_m, *g_prior_sd;  // incoming gradients (nullable)
+  float *d_p, *d_hp, *d_gi, *d_gh, *d_e;          // transition pre-activation gradients
+  float *d_a5, *d_a4, *d_a3, *d_a2, *d_a1;        // actor pre-activation gradients: (T,N,2A), 4 x (T,N,H)
+  float *d_start_belief, *d_start_state;          // (N, D), (N, S) or null
+};
+
+template <int RB>
+__device__ __forceinline__ void col_dot_rows(const float* __restrict__ W, int ld, int k, const float* dy, int n,
+                                             float (&acc)[RB]) {
+#pragma unroll
+  for (int r = 0; r < RB; ++r) acc[r] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) {
+    const float w = __ldg(W + (size_t)j * ld + k);
+#pragma unroll
+    for (int r = 0; r < RB; ++r) acc[r] = fmaf(w, dy[j * RB + r], acc[r]);
+  }
+}
+
+template <int RB>
+__global__ void __launch_bounds__(256) imagine_bwd_kernel(const __grid_constant__ ImgBwdParams P) {
+  extern __shared__ float sm[];
+  const int D = P.D, S = P.S, A = P.A, Hd = P.Hd, T = P.T, N = P.N;
+  // all vectors are [feature][RB] so one weight element meets RB rows with a vector LDS
+  float* db = sm;                  // D
+  float* ds = db + D * RB;         // S
+  float* dp = ds + S * RB;         // 2S
+  float* dh = dp + 2 * S * RB;     // Hd (prior hidden, then actor hidden ping)
+  float* dh2 = dh + Hd * RB;       // Hd (actor hidden pong)
+  float* dba = dh2 + Hd * RB;      // D
+  float* dgi = dba + D * RB;       // 3D
+  float* dgh = dgi + 3 * D * RB;   // 3D
+  float* de = dgh + 3 * D * RB;    // D
+  float* d5 = de + D * RB;         // 2A
+  const int k = threadIdx.x, nth = blockDim.x;
+  const int row0 = blockIdx.x * RB;
+  for (int i = k; i < D * RB; i += nth) db[i] = 0.f;
+  for (int i = k; i < S * RB; i += nth) ds[i] = 0.f;
+  __syncthreads();
+
+  for (int t = T - 1; t >= 0; --t) {
+    // ---- prior head ----
+    for (int idx = k; idx < S * RB; idx += nth) {
+      const int j = idx / RB, r = idx - j * RB, row = row0 + r;
+      float dmu = 0.f, draw = 0.f;
+      if (row < N) {
+        const size_t o = ((size_t)t * N + row) * S + j;
+        const float gs = (P.g_prior_s ? P.g_prior_s[o] : 0.f) + ds[idx];
+        dmu = (P.g_prior_m ? P.g_prior_m[o] : 0.f) + gs;
+        const float dsd = (P.g_prior_sd ? P.g_prior_sd[o] : 0.f) + gs * P.eps_prior[o];
+        draw = dsd * (1.f - __expf(-(P.prior_sd[o] - P.min_std)));
+        P.d_p[((size_t)t * N + row) * 2 * S + j] = dmu;
+        P.d_p[((size_t)t * N + row) * 2 * S + S + j] = draw;
+      }
+      dp[j * RB + r] = dmu;
+      dp[(S + j) * RB + r] = draw;
+    }
+    for (int idx = k; idx < D * RB; idx += nth) {
+      const int i = idx / RB, r = idx - i * RB, row = row0 + r;
+      dba[idx] = db[idx] + ((row < N && P.g_beliefs) ? P.g_beliefs[((size_t)t * N + row) * D + i] : 0.f);
+    }
+    __syncthreads();
+    for (int i = k; i < Hd; i += nth) {
+      float acc[RB];
+      col_dot_rows<RB>(P.w_p2, Hd, i, dp, 2 * S, acc);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int row = row0 + r;
+        float g = 0.f;
+        if (row < N) {
+          const size_t tr = (size_t)t * N + row;
+          g = acc[r] * act_grad_from_output(P.stash[tr * P.stash_ld + 5 * D + i], P.act);
+          P.d_hp[tr * Hd + i] = g;
+        }
+        dh[i * RB + r] = g;
+      }
+    }
+    __syncthreads();
+    for (int i = k; i < D; i += nth) {
+      float acc[RB];
+      col_dot_rows<RB>(P.w_p1, D, i, dh, Hd, acc);
+      // ---- GRU cell (same thread owns unit i of every row) ----
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int row = row0 + r;
+        float drp = 0.f, dzp = 0.f, dnp = 0.f, dnr = 0.f, dbz = 0.f;
+        if (row < N) {
+          const size_t tr = (size_t)t * N + row;
+          const float* st = P.stash + tr * P.stash_ld;
+          const float rr = st[D + i], z = st[2 * D + i], n = st[3 * D + i], hn = st[4 * D + i];
+          const float bprev = t > 0 ? P.beliefs[(tr - N) * D + i] : P.start_belief[(size_t)row * D + i];
+          const float g = dba[i * RB + r] + acc[r];
+          dnp = g * (1.f - z) * (1.f - n * n);
+          dzp = g * (bprev - n) * z * (1.f - z);
+          drp = dnp * hn * rr * (1.f - rr);
+          dnr = dnp * rr;
+          dbz = g * z;
+          float* o_gi = P.d_gi + tr * 3 * D;
+          float* o_gh = P.d_gh + tr * 3 * D;
+          o_gi[i] = drp; o_gi[D + i] = dzp; o_gi[2 * D + i] = dnp;
+          o_gh[i] = drp; o_gh[D + i] = dzp; o_gh[2 * D + i] = dnr;
+        }
+        dgi[i * RB + r] = drp; dgi[(D + i) * RB + r] = dzp; dgi[(2 * D + i) * RB + r] = dnp;
+        dgh[i * RB + r] = drp; dgh[(D + i) * RB + r] = dzp; dgh[(2 * D + i) * RB + r] = dnr;
+        db[i * RB + r] = dbz;
+      }
+    }
+    __syncthreads();
+    for (int i = k; i < D; i += nth) {
+      float acc[RB], acc2[RB];
+      col_dot_rows<RB>(P.w_ih, D, i, dgi, 3 * D, acc);
+      col_dot_rows<RB>(P.w_hh, D, i, dgh, 3 * D, acc2);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int row = row0 + r;
+        float g = 0.f;
+        if (row < N) {
+          const size_t tr = (size_t)t * N + row;
+          g = acc[r] * act_grad_from_output(P.stash[tr * P.stash_ld + i], P.act);
+          P.d_e[tr * D + i] = g;
+        }
+        de[i * RB + r] = g;
+        db[i * RB + r] += acc2[r];
+      }
+    }
+    __syncthreads();
+    // ---- [state | action] that entered this step ----
+    for (int j = k; j < S + A; j += nth) {
+      float acc[RB];
+      col_dot_rows<RB>(P.w_e, S + A, j, de, D, acc);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int row = row0 + r;
+        if (j < S) ds[j * RB + r] = acc[r];
+        else {
+          const int a = j - S;
+          float dm = 0.f, dsr = 0.f;
+          if (row < N) {
+            const size_t tr = (size_t)t * N + row;
+            const float av = P.actions[tr * A + a];
+            const float du = acc[r] * (1.f - av * av);           // a = tanh(u)
+            const float* st = P.stash + tr * P.stash_ld + 5 * D + 5 * Hd;
+            const float mean = st[a], sd = st[A + a];
+            const float mm = mean / P.a_mean_scale;
+            dm = du * (1.f - mm * mm);                            // mean = ms * tanh(m / ms)
+            dsr = du * P.eps_action[tr * A + a] * (1.f - __expf(-(sd - P.a_min_std)));
+            P.d_a5[tr * 2 * A + a] = dm;
+            P.d_a5[tr * 2 * A + A + a] = dsr;
+          }
+          d5[a * RB + r] = dm;
+          d5[(A + a) * RB + r] = dsr;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- actor chain fc5 -> fc2 (ELU everywhere); its inputs are detached, so it stops at d1 ----
+    const float* Wk[4] = {P.w_a5, P.w_a4, P.w_a3, P.w_a2};
+    float* outk[4] = {P.d_a4, P.d_a3, P.d_a2, P.d_a1};
+    const float* src = d5;
+    int nsrc = 2 * A;
+    float* dst = dh;
+    for (int l = 0; l < 4; ++l) {
+      const int hoff = 5 * D + Hd + (3 - l) * Hd;  // h4, h3, h2, h1
+      for (int i = k; i < Hd; i += nth) {
+        float acc[RB];
+        col_dot_rows<RB>(Wk[l], Hd, i, src, nsrc, acc);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+          const int row = row0 + r;
+          float g = 0.f;
+          if (row < N) {
+            const size_t tr = (size_t)t * N + row;
+            g = acc[r] * act_grad_from_output(P.stash[tr * P.stash_ld + hoff + i], 1);
+            outk[l][tr * Hd + i] = g;
+          }
+          dst[i * RB + r] = g;
+        }
+      }
+      __syncthreads();
+      src = dst;
+      nsrc = Hd;
+      dst = (dst == dh) ? dh2 : dh;
+    }
+  }
+  for (int idx = k; idx < D * RB; idx += nth) {
+    const int i = idx / RB, r = idx - i * RB, row = row0 + r;
+    if (P.d_start_belief && row < N) P.d_start_belief[(size_t)row * D + i] = db[idx];
+  }
+  for (int idx = k; idx < S * RB; idx += nth) {
+    const int j = idx / RB, r = idx - j * RB, row = row0 + r;
+    if (P.d_start_state && row < N) P.d_start_state[(size_t)row * S + j] = ds[idx];
+  }
+}
+
+}  // namespace rb

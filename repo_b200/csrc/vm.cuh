@@ -558,6 +558,10 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
                   const float sd = softplus_f(vs[i] + bs + P.a_init_std) + P.a_min_std;
                   const float a = tanh_f(mean + sd * e[i]);
                   if (r0 + i < N && P.actions_out) P.actions_out[o0 + (size_t)i * A] = a;
+                  if (P.stash && st.stash_off != 0xFFFF && r0 + i < N) {
+                    float* sp = P.stash + (trow + r0 + i) * P.stash_ld + st.stash_off + j;
+                    sp[0] = mean; sp[A] = sd;
+                  }
                   TL::put(x_hi, x_lo, c * 16 + i, D + S + j, a);
                 }
               }

@@ -160,7 +160,8 @@ def imagine_fwd(params: Dict[str, torch.Tensor], actor: Dict[str, torch.Tensor],
                 belief, state, eps_action, eps_prior, horizon: int, act: str = "elu", min_std: float = 0.1,
                 mean_scale: float = 5.0, init_std: float = 0.0, actor_min_std: float = 0.1,
                 gamma: float = 0.99, lambda_: float = 0.95, row_tile: int = 0,
-                workspace: Optional[torch.Tensor] = None, packed: bool = False, want_actions: bool = True):
+                workspace: Optional[torch.Tensor] = None, packed: bool = False, want_actions: bool = True,
+                stash: Optional[torch.Tensor] = None):
     """TransitionModel.imagine (rssm.py:148-184) + reward/value heads + lambda-return in one launch.
     Returns dict(beliefs, prior_states, prior_means, prior_std_devs, actions, rewards, values, returns)."""
     L = _lib.lib()
@@ -197,7 +198,7 @@ def imagine_fwd(params: Dict[str, torch.Tensor], actor: Dict[str, torch.Tensor],
         _ptr(out["beliefs"]), _ptr(out["prior_states"]), _ptr(out["prior_means"]), _ptr(out["prior_std_devs"]),
         _ptr(out["actions"]), _ptr(out["rewards"]), _ptr(out["values"]), _ptr(out["returns"]),
         horizon, N, act_kind(act), float(min_std), float(mean_scale), float(init_std), float(actor_min_std),
-        float(gamma), float(lambda_), _ptr(workspace), workspace.numel(), _lib.WEIGHTS_PACKED if packed else 0,
+        float(gamma), float(lambda_), _ptr(stash), _ptr(workspace), workspace.numel(), _lib.WEIGHTS_PACKED if packed else 0,
         row_tile, _stream())
     _lib.check(rc, "repo_b200_imagine_fwd")
     out["workspace"] = workspace

@@ -117,7 +117,12 @@ class TransitionModel(nn.Module):
             ea, ep = self._imagine_noise(T, N, prev_belief)
             eps_action = ea if eps_action is None else eps_action
             eps_prior = ep if eps_prior is None else eps_prior
-        self._require_no_grad("imagine", [prev_belief, prev_state], extra=[policy, reward_model, value_model])
+        if self._wants_grad([prev_belief, prev_state]) or (torch.is_grad_enabled() and any(p.requires_grad for p in policy.parameters())):
+            if reward_model is not None or value_model is not None:
+                raise NotImplementedError("imagine under autograd returns the reference's four lists; evaluate the heads on them")
+            from . import autograd as _ag
+            traj, actions = _ag.imagine(self, prev_belief, prev_state, policy, horizon, eps_action, eps_prior)
+            return (traj, {"actions": actions}) if return_extras else traj
         out = ops.imagine_fwd(_named(self), _named(policy),
                               _named(reward_model) if reward_model is not None else None,
                               _named(value_model) if value_model is not None else None,

@@ -356,3 +356,56 @@ def test_frozen_parameters_get_no_gradient(dev):
     outs[0].sum().backward()
     for n, p in m.named_parameters():
         assert (p.grad is not None) == n.startswith("rnn"), n
+
+
+@pytest.mark.parametrize("name", ["imagine_N24_H6", "imagine_N16_H15_hot", "imagine_tiny_dims"])
+def test_imagine_backward_matches_autograd_of_the_oracle(dev, name):
+    """Gradients w.r.t. actor AND transition parameters and the start rows, vs fp64 autograd through the
+    oracle's imagine with the actor inputs detached (rssm.py:170)."""
+    from repo_b200.models import ActorModel
+    from repo_b200.rssm import TransitionModel
+    params, actor, reward, value, x, gold, meta = C.imagine_case(name)
+    dims = C.dims_of(meta)
+    H = int(meta["H"])
+    D, S, A, Hd = dims["belief"], dims["state"], dims["action"], dims["hidden"]
+    N = x["belief"].shape[0]
+    rs = np.random.RandomState(9)
+    R = [torch.from_numpy(rs.standard_normal((H - 1, N, f)).astype(np.float32)) for f in (D, S, S, S)]
+
+    # fp64 reference with the detach structure of the reference
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    a64 = {k: v.double().requires_grad_(True) for k, v in actor.items()}
+    b0, s0 = x["belief"].double().requires_grad_(True), x["state"].double().requires_grad_(True)
+    belief, state, outs = b0, s0, [[], [], [], []]
+    for t in range(H - 1):
+        mean, std = O.actor_forward(a64, belief.detach(), state.detach())
+        action = torch.tanh(mean + std * x["eps_action"][t].double())
+        belief = O.compute_belief(p64, belief, state, action)
+        state, pm, pd = O.compute_prior_state(p64, belief, x["eps_prior"][t].double())
+        for o, v in zip(outs, (belief, state, pm, pd)):
+            o.append(v)
+    outs = [torch.stack(o) for o in outs]
+    sum((r.double() * o).sum() for r, o in zip(R, outs)).backward()
+
+    m = TransitionModel(D, S, A, Hd, dims["embed"], "elu").to(dev)
+    m.load_state_dict(params)
+    pol = ActorModel(D, S, Hd, A, "elu").to(dev)
+    pol.load_state_dict(actor)
+    gb0, gs0 = x["belief"].to(dev).requires_grad_(True), x["state"].to(dev).requires_grad_(True)
+    got_outs = m.imagine(gb0, gs0, pol, H, eps_action=x["eps_action"].to(dev), eps_prior=x["eps_prior"].to(dev))
+    for o, w in zip(got_outs, outs):
+        close(o, w.detach().float(), "imagine forward under autograd")
+    sum((r.to(dev) * o).sum() for r, o in zip(R, got_outs)).backward()
+
+    def cmp(got, want, nm):
+        scale = float(want.abs().max()) + 1e-12
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=1e-3, atol=3e-4, err_msg=nm)
+
+    for k, w in a64.items():
+        cmp(dict(pol.named_parameters())[k].grad, w.grad, "actor." + k)
+    for k, w in p64.items():
+        if "posterior" in k:
+            continue
+        cmp(dict(m.named_parameters())[k].grad, w.grad, k)
+    cmp(gb0.grad, b0.grad, "start belief")
+    cmp(gs0.grad, s0.grad, "start state")
