@@ -143,12 +143,29 @@ int repo_b200_head_fwd(const repo_b200_dims* dims, const repo_b200_mlp_weights* 
                        const float* state, float* out, int n_rows, int act_kind, void* workspace,
                        size_t workspace_bytes, int flags, int row_tile, void* stream);
 
+/* ---- mlp: fc1..fcL on [belief|state] with L in 2..5 — RewardModel / ValueModel (decoder.py:178-195,
+ * actor_critic.py:9-26; L=4, out 1) and ActorModel.forward's trunk (actor_critic.py:76-82; L=5, out 2A).
+ * fwd: out (N,out_features); stash (N,(L-1)*H) nullable receives the hidden activations.
+ * bwd: g_out (N,out_features) -> pre-activation gradients d_h1..d_h{L-1} (N,H) and d_x (N,D+S, nullable);
+ * weight gradients are GEMMs of those against the stashed inputs (repo_b200/autograd.py). */
+size_t repo_b200_mlp_workspace_bytes(const repo_b200_dims* dims, int n_layers, int out_features);
+int repo_b200_mlp_fwd(const repo_b200_dims* dims, const repo_b200_mlp_weights* mlp, const float* belief,
+                      const float* state, float* out, int out_features, float* stash, int n_rows, int act_kind,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int repo_b200_mlp_bwd(const repo_b200_dims* dims, const repo_b200_mlp_weights* mlp, const float* stash,
+                      const float* g_out, int out_features, float* d_h1, float* d_h2, float* d_h3, float* d_h4,
+                      float* d_x, int n_rows, int act_kind, void* stream);
+
 /* ---- MC entropy of the tanh-Normal policy: SampleDist.entropy (models/utils.py:160-163) over
  * Independent(TransformedDistribution(Normal(mean,std), TanhBijector), 1) (actor_critic.py:89-95;
  * TanhBijector models/utils.py:112-134), called at dreamer.py:320-324.
  *   mean, std_dev (M,A); eps (K,M,A) standard normal draws; entropy (M). */
 int repo_b200_tanh_normal_entropy_fwd(const float* mean, const float* std_dev, const float* eps, float* entropy, int m,
                                       int action, int samples, void* stream);
+
+int repo_b200_tanh_normal_entropy_bwd(const float* mean, const float* std_dev, const float* eps,
+                                      const float* g_entropy, float* d_mean, float* d_std, int m, int action,
+                                      int samples, void* stream);
 
 /* ---- replay gather: the index bookkeeping of SequenceReplayBuffer.sample (common/buffers.py:156-166) after
  * `np.random.choice` (start_inds, drawn on the host so the RNG stream is the reference's), fused with

@@ -41,6 +41,7 @@ EXPORTS = [
     "repo_b200_head_workspace_bytes", "repo_b200_head_fwd",
     "repo_b200_tanh_normal_entropy_fwd", "repo_b200_replay_gather",
     "repo_b200_cell_workspace_bytes", "repo_b200_cell_fwd",
+    "repo_b200_mlp_workspace_bytes", "repo_b200_mlp_fwd", "repo_b200_mlp_bwd", "repo_b200_tanh_normal_entropy_bwd",
 ]
 
 _lib = None
@@ -97,6 +98,14 @@ def lib():
     L.repo_b200_cell_workspace_bytes.restype = sz
     L.repo_b200_cell_fwd.argtypes = [C.POINTER(Dims), C.POINTER(RssmWeights)] + [vp] * 6 + [ci, ci, cf, vp, sz, vp]
     L.repo_b200_cell_fwd.restype = ci
+    L.repo_b200_mlp_workspace_bytes.argtypes = [C.POINTER(Dims), ci, ci]
+    L.repo_b200_mlp_workspace_bytes.restype = sz
+    L.repo_b200_mlp_fwd.argtypes = [C.POINTER(Dims), C.POINTER(MlpWeights), vp, vp, vp, ci, vp, ci, ci, vp, sz, vp]
+    L.repo_b200_mlp_fwd.restype = ci
+    L.repo_b200_mlp_bwd.argtypes = [C.POINTER(Dims), C.POINTER(MlpWeights), vp, vp, ci, vp, vp, vp, vp, vp, ci, ci, vp]
+    L.repo_b200_mlp_bwd.restype = ci
+    L.repo_b200_tanh_normal_entropy_bwd.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, vp]
+    L.repo_b200_tanh_normal_entropy_bwd.restype = ci
     L.repo_b200_linear_workspace_bytes.argtypes = [ci, ci]
     L.repo_b200_linear_workspace_bytes.restype = sz
     L.repo_b200_linear_fwd.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp, ci, vp, sz, ci, vp]

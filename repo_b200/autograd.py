@@ -213,3 +213,86 @@ def imagine(model, prev_belief, prev_state, policy, horizon, eps_action, eps_pri
     *outs, actions = ImagineFn.apply(model.activation_function, model.min_std_dev, horizon, scal, prev_belief, prev_state,
                                      eps_action, eps_prior, *tparams, *aparams)
     return list(outs), actions
+
+
+class MlpFn(torch.autograd.Function):
+    """fc1..fcL on [belief|state] (RewardModel / ValueModel / ActorModel trunk): forward on the layer machine
+    with the hidden activations stashed, backward on the SIMT chain kernel + weight-gradient GEMMs."""
+
+    @staticmethod
+    def forward(ctx, act, out_f, belief, state, *params):
+        L_layers = len(params) // 2
+        named = {f"fc{i + 1}.{w}": params[2 * i + j] for i in range(L_layers) for j, w in enumerate(("weight", "bias"))}
+        N, D, S, Hd = belief.shape[0], belief.shape[1], state.shape[1], params[0].shape[0]
+        d = _lib.Dims(D, S, 1, Hd, 1)
+        lib = _lib.lib()
+        keep = ops._Keep()
+        M = ops.mlp_struct({k: v.detach() for k, v in named.items()}, L_layers, keep, "mlp")
+        b, s = ops._chk(belief.detach(), "belief", (N, D)), ops._chk(state.detach(), "state", (N, S))
+        out = torch.empty(N, out_f, device=b.device, dtype=torch.float32)
+        stash = torch.empty(N, (L_layers - 1) * Hd, device=b.device, dtype=torch.float32)
+        if N:
+            ws = torch.empty(lib.repo_b200_mlp_workspace_bytes(C.byref(d), L_layers, out_f), dtype=torch.uint8, device=b.device)
+            rc = lib.repo_b200_mlp_fwd(C.byref(d), C.byref(M), ops._ptr(b), ops._ptr(s), ops._ptr(out), out_f, ops._ptr(stash), N,
+                                       ops.act_kind(act), ops._ptr(ws), ws.numel(), ops._stream())
+            _lib.check(rc, "repo_b200_mlp_fwd")
+        ctx.meta = (act, out_f, L_layers, d)
+        ctx.save_for_backward(b, s, stash, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        act, out_f, L_layers, d = ctx.meta
+        b, s, stash, *params = ctx.saved_tensors
+        N, Hd = b.shape[0], d.hidden
+        named = {f"fc{i + 1}.{w}": params[2 * i + j] for i in range(L_layers) for j, w in enumerate(("weight", "bias"))}
+        keep = ops._Keep()
+        M = ops.mlp_struct(named, L_layers, keep, "mlp")
+        g_out = g_out.contiguous().float()
+        dh = [torch.empty(N, Hd, device=b.device) for _ in range(L_layers - 1)] + [None] * (5 - L_layers)
+        need_x = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        dx = torch.empty(N, d.belief + d.state, device=b.device) if need_x else None
+        if N:
+            rc = _lib.lib().repo_b200_mlp_bwd(C.byref(d), C.byref(M), ops._ptr(stash), ops._ptr(g_out), out_f, ops._ptr(dh[0]),
+                                              ops._ptr(dh[1]), ops._ptr(dh[2]), ops._ptr(dh[3]), ops._ptr(dx), N,
+                                              ops.act_kind(act), ops._stream())
+            _lib.check(rc, "repo_b200_mlp_bwd")
+        grads = []
+        inputs = [torch.cat([b, s], 1)] + [stash[:, i * Hd:(i + 1) * Hd] for i in range(L_layers - 1)]
+        dpre = dh[:L_layers - 1] + [g_out]
+        for i in range(L_layers):
+            need_w, need_b = ctx.needs_input_grad[4 + 2 * i], ctx.needs_input_grad[5 + 2 * i]
+            grads.append(dpre[i].t() @ inputs[i] if need_w else None)
+            grads.append(dpre[i].sum(0) if need_b else None)
+        gb = dx[:, :d.belief] if (need_x and ctx.needs_input_grad[2]) else None
+        gs = dx[:, d.belief:] if (need_x and ctx.needs_input_grad[3]) else None
+        return (None, None, gb, gs, *grads)
+
+
+def mlp(module, n_layers, out_f, belief, state, act):
+    params = []
+    for i in range(1, n_layers + 1):
+        fc = getattr(module, f"fc{i}")
+        params += [fc.weight, fc.bias]
+    return MlpFn.apply(act, out_f, belief, state, *params)
+
+
+class EntropyFn(torch.autograd.Function):
+    """SampleDist.entropy (models/utils.py:160-163) of the tanh-Normal policy with explicit noise."""
+
+    @staticmethod
+    def forward(ctx, mean, std, eps):
+        ctx.save_for_backward(mean, std, eps)
+        return ops.tanh_normal_entropy(mean.detach(), std.detach(), eps)
+
+    @staticmethod
+    def backward(ctx, g):
+        mean, std, eps = ctx.saved_tensors
+        M, A = mean.shape
+        dm, dsd = torch.empty_like(mean), torch.empty_like(std)
+        if M:
+            rc = _lib.lib().repo_b200_tanh_normal_entropy_bwd(ops._ptr(mean.contiguous()), ops._ptr(std.contiguous()), ops._ptr(eps),
+                                                              ops._ptr(g.contiguous().float()), ops._ptr(dm), ops._ptr(dsd), M, A,
+                                                              eps.shape[0], ops._stream())
+            _lib.check(rc, "repo_b200_tanh_normal_entropy_bwd")
+        return dm, dsd, None

@@ -722,6 +722,91 @@ int repo_b200_imagine_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   return 0;
 }
 
+// ---- generic MLP on [belief | state]: forward through the layer machine, backward on the SIMT kernel
+static void build_mlp(Builder& b, const repo_b200_dims* d, const repo_b200_mlp_weights* M, int out_f, int act, bool stash) {
+  const int D = d->belief, S = d->state, Hd = d->hidden;
+  const int kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);
+  const int L = M->n_layers;
+  set_dims(b.P, d);
+  b.dense_to_h(M->w[0], M->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, act, 0, stash ? 0 : 0xFFFF);
+  for (int i = 1; i < L - 1; ++i) b.dense_to_h(M->w[i], M->b[i], Hd, Hd, 0, Hd, 0, kH16, 1, 0, act, 0, stash ? i * Hd : 0xFFFF);
+  VmStage& s = b.begin_stage();
+  b.gemm_rows(M->w[L - 1], Hd, 0, out_f, 0, Hd, 0, kH16, 1, 0, 0, 0);
+  b.bias_rows(M->b[L - 1], 0, nullptr, 0, out_f);
+  b.end_stage(s, EPI_STORE, 0, cdiv(out_f, 128), 0, out_f, 0);
+}
+
+size_t repo_b200_mlp_workspace_bytes(const repo_b200_dims* d, int n_layers, int out_features) {
+  if (check_dims(d) || n_layers < 2 || n_layers > 5) return 0;
+  repo_b200_mlp_weights m{};
+  m.n_layers = n_layers;
+  Builder b;
+  build_mlp(b, d, &m, out_features, ACT_ELU, false);
+  return align_up(b.packed_bytes(), 256);
+}
+
+int repo_b200_mlp_fwd(const repo_b200_dims* d, const repo_b200_mlp_weights* mlp, const float* belief, const float* state,
+                      float* out, int out_features, float* stash, int n_rows, int act_kind, void* ws, size_t ws_bytes,
+                      void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_act(act_kind))) return rc;
+  if (n_rows < 0 || out_features < 1 || out_features > 256) return fail(-1, "mlp: bad sizes");
+  if (n_rows == 0) return 0;
+  if (!mlp || mlp->n_layers < 2 || mlp->n_layers > 5) return fail(-1, "mlp: expected 2..5 layers");
+  if (!belief || !state || !out) return fail(-1, "mlp: NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Builder b;
+  build_mlp(b, d, mlp, out_features, act_kind, stash != nullptr);
+  if ((rc = b.bind_and_pack(ws, ws_bytes, true, st))) return rc;
+  VmParams& P = b.P;
+  P.n_steps = 1;
+  P.N = n_rows;
+  P.init_belief = belief; P.init_state = state;
+  P.out = out; P.out_ld = out_features;
+  P.stash = stash; P.stash_ld = (mlp->n_layers - 1) * d->hidden;
+  return launch(P, b.max_acc_tiles, 0, st);
+}
+
+int repo_b200_mlp_bwd(const repo_b200_dims* d, const repo_b200_mlp_weights* mlp, const float* stash, const float* g_out,
+                      int out_features, float* d_h1, float* d_h2, float* d_h3, float* d_h4, float* d_x, int n_rows,
+                      int act_kind, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if ((rc = check_act(act_kind))) return rc;
+  if (n_rows < 0) return fail(-1, "mlp_bwd: bad sizes");
+  if (n_rows == 0) return 0;
+  if (!mlp || mlp->n_layers < 2 || mlp->n_layers > 5 || !stash || !g_out) return fail(-1, "mlp_bwd: bad arguments");
+  MlpBwdParams P{};
+  P.N = n_rows; P.in_f = d->belief + d->state; P.Hd = d->hidden; P.out_f = out_features; P.L = mlp->n_layers; P.act = act_kind;
+  for (int i = 0; i < P.L; ++i) P.w[i] = mlp->w[i];
+  P.stash = stash; P.stash_ld = (P.L - 1) * d->hidden;
+  P.g_out = g_out;
+  float* dh[4] = {d_h1, d_h2, d_h3, d_h4};
+  for (int i = 0; i < P.L - 1; ++i) {
+    if (!dh[i]) return fail(-1, "mlp_bwd: d_h%d missing", i + 1);
+    P.d_h[i] = dh[i];
+  }
+  P.d_x = d_x;
+  constexpr int RB = 8;
+  const size_t smem = (size_t)2 * std::max(out_features, d->hidden) * RB * sizeof(float);
+  mlp_bwd_kernel<RB><<<cdiv(n_rows, RB), 256, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int repo_b200_tanh_normal_entropy_bwd(const float* mean, const float* std_dev, const float* eps, const float* g_entropy,
+                                      float* d_mean, float* d_std, int m, int action, int samples, void* stream) {
+  if (m < 0 || action < 1 || samples < 1) return fail(-1, "entropy_bwd: bad sizes");
+  if (m == 0) return 0;
+  if (!mean || !std_dev || !eps || !g_entropy || !d_mean || !d_std) return fail(-1, "entropy_bwd: NULL pointer");
+  const long long n = (long long)m * action;
+  tanh_normal_entropy_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mean, std_dev, eps, g_entropy, d_mean, d_std, m, action, samples);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ---- standalone Gaussian cells: compute_prior_state (rssm.py:42-50) / compute_posterior_state (rssm.py:52-64)
 static void build_cell(Builder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W, bool posterior, int act) {
   const int D = d->belief, S = d->state, Hd = d->hidden, E = d->embed;

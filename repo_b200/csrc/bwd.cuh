@@ -369,3 +369,104 @@ __global__ void __launch_bounds__(256) imagine_bwd_kernel(const __grid_constant_
 }
 
 }  // namespace rb
+
+namespace rb {
+
+// =====================================================================================================
+// Backward of an L-layer MLP on [belief | state] (RewardModel / ValueModel: L=4, out 1; ActorModel.forward:
+// L=5, out 2A).  RB rows per CTA.  Emits the pre-activation gradient of every layer (for the weight-gradient
+// GEMMs) and, if wanted, the gradient of the input rows.
+// =====================================================================================================
+struct MlpBwdParams {
+  int N, in_f, Hd, out_f, L;          // L layers: in_f -> Hd x (L-1) -> out_f
+  int act;
+  const float* w[5];                  // fc1..fcL, row-major [out, in]
+  const float* stash; int stash_ld;   // (N, (L-1)*Hd): post-activation h1..h_{L-1}
+  const float* g_out;                 // (N, out_f)
+  float* d_h[4];                      // pre-activation gradients of fc1..fc_{L-1}: each (N, Hd)
+  float* d_x;                         // (N, in_f) or null
+};
+
+template <int RB>
+__global__ void __launch_bounds__(256) mlp_bwd_kernel(const __grid_constant__ MlpBwdParams P) {
+  extern __shared__ float sm[];
+  const int Hd = P.Hd, N = P.N, L = P.L;
+  float* ga = sm;                   // max(out_f, Hd) x RB
+  float* gb = ga + max(P.out_f, Hd) * RB;
+  const int k = threadIdx.x, nth = blockDim.x;
+  const int row0 = blockIdx.x * RB;
+  for (int idx = k; idx < P.out_f * RB; idx += nth) {
+    const int j = idx / RB, r = idx - j * RB, row = row0 + r;
+    ga[idx] = row < N ? P.g_out[(size_t)row * P.out_f + j] : 0.f;
+  }
+  __syncthreads();
+  const float* src = ga;
+  float* dst = gb;
+  int nsrc = P.out_f;
+  for (int l = L - 1; l >= 1; --l) {   // d_{l} = W_{l+1}^T d_{l+1} * act'(h_l)
+    for (int i = k; i < Hd; i += nth) {
+      float acc[RB];
+      col_dot_rows<RB>(P.w[l], Hd, i, src, nsrc, acc);
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int row = row0 + r;
+        float g = 0.f;
+        if (row < N) {
+          g = acc[r] * act_grad_from_output(P.stash[(size_t)row * P.stash_ld + (l - 1) * Hd + i], P.act);
+          P.d_h[l - 1][(size_t)row * Hd + i] = g;
+        }
+        dst[i * RB + r] = g;
+      }
+    }
+    __syncthreads();
+    const float* tmp = src;
+    src = dst;
+    dst = const_cast<float*>(tmp);
+    nsrc = Hd;
+  }
+  if (P.d_x) {
+    for (int i = k; i < P.in_f; i += nth) {
+      float acc[RB];
+      col_dot_rows<RB>(P.w[0], P.in_f, i, src, Hd, acc);
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+        if (row0 + r < N) P.d_x[(size_t)(row0 + r) * P.in_f + i] = acc[r];
+    }
+  }
+}
+
+// =====================================================================================================
+// Backward of the MC tanh-Normal entropy (elementwise.cuh): d entropy[m] / d mean[m,a], d std[m,a].
+//   x = atanh(clamp(tanh(u))), u = mean + std*eps;  dx/du = (1 - y^2) / (1 - yc^2) inside the clamp, else 0
+//   log p = -(x-mu)^2/(2 s^2) - log s - c + 2x + 2 softplus(-2x) - 2 log 2     (d/dx of the tail = 2 tanh(x))
+// =====================================================================================================
+__global__ void __launch_bounds__(256) tanh_normal_entropy_bwd_kernel(const float* __restrict__ mean,
+                                                                      const float* __restrict__ std_,
+                                                                      const float* __restrict__ eps,
+                                                                      const float* __restrict__ g_ent,
+                                                                      float* __restrict__ d_mean, float* __restrict__ d_std,
+                                                                      int M, int A, int K) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (m, a)
+  if (idx >= M * A) return;
+  const int m = idx / A, a = idx - m * A;
+  const float mu = mean[idx], sd = std_[idx];
+  const float inv_var = 1.f / (sd * sd);
+  float gm = 0.f, gs = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float e = __ldg(eps + ((size_t)k * M + m) * A + a);
+    const float y = tanhf(mu + sd * e);
+    const bool inside = fabsf(y) <= 0.99999997f;
+    const float yc = fabsf(y) <= 1.f ? fminf(fmaxf(y, -0.99999997f), 0.99999997f) : y;
+    const float x = atanhf(yc);
+    const float dxdu = inside ? (1.f - y * y) / (1.f - yc * yc) : 0.f;
+    const float d = x - mu;
+    const float dlp_dx = -d * inv_var + 2.f * tanhf(x);
+    gm += dlp_dx * dxdu + d * inv_var;                          // d log p / d mu
+    gs += dlp_dx * dxdu * e + d * d * inv_var / sd - 1.f / sd;  // d log p / d std
+  }
+  const float w = -g_ent[m] / (float)K;
+  d_mean[idx] = w * gm;
+  d_std[idx] = w * gs;
+}
+
+}  // namespace rb

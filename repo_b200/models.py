@@ -34,8 +34,8 @@ class _ScalarHead(nn.Module):
     def forward(self, belief, state):
         if torch.is_grad_enabled() and (belief.requires_grad or state.requires_grad or
                                         any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(f"{type(self).__name__}.forward: backward kernels are not built yet; "
-                                      "call under torch.no_grad()")
+            from . import autograd as _ag
+            return _ag.mlp(self, 4, 1, belief, state, self.activation_function).squeeze(1)
         return ops.head_fwd({k: v for k, v in self.named_parameters()}, belief, state, act=self.activation_function)
 
 
@@ -65,3 +65,61 @@ class ActorModel(nn.Module):
         self._min_std = min_std
         self._init_std = init_std
         self._mean_scale = mean_scale
+
+    def forward(self, belief, state):
+        """actor_critic.py:76-87 -> (action_mean, action_std).  The 5-layer trunk runs on the layer machine
+        (differentiable: hand-written backward); the two 2A-wide squashing ops are elementwise torch."""
+        from . import autograd as _ag
+        A2 = self.fc5.out_features
+        raw = _ag.mlp(self, 5, A2, belief, state, "elu")
+        m_raw, s_raw = torch.chunk(raw, 2, dim=1)
+        mean = self._mean_scale * torch.tanh(m_raw / self._mean_scale)
+        std = torch.nn.functional.softplus(s_raw + self._init_std) + self._min_std
+        return mean, std
+
+    def get_action_dist(self, belief, state):
+        return TanhNormalDist(*self.forward(belief, state))
+
+    def get_action(self, belief, state, det=False):
+        dist = self.get_action_dist(belief, state)
+        return dist.mode() if det else dist.rsample()
+
+
+class TanhNormalDist:
+    """SampleDist(Independent(TransformedDistribution(Normal(mean,std), TanhBijector), 1)) with the reference's
+    100-sample Monte-Carlo statistics (models/utils.py:112-163, actor_critic.py:89-95)."""
+
+    def __init__(self, mean, std, samples=100):
+        self.mean_, self.std_, self._samples = mean, std, samples
+
+    def rsample(self, eps=None):
+        eps = torch.randn_like(self.mean_) if eps is None else eps
+        return torch.tanh(self.mean_ + self.std_ * eps)
+
+    sample = rsample
+
+    def entropy(self, eps=None):
+        """-(1/K) sum_k log p(y_k): fused CUDA kernel forward and backward (models/utils.py:160-163)."""
+        from . import autograd as _ag
+        if eps is None:
+            eps = torch.randn((self._samples,) + tuple(self.mean_.shape), device=self.mean_.device)
+        return _ag.EntropyFn.apply(self.mean_, self.std_, eps)
+
+    def log_prob(self, y):
+        import math
+        yc = torch.where(y.abs() <= 1.0, torch.clamp(y, -0.99999997, 0.99999997), y)
+        x = torch.atanh(yc)
+        base = -((x - self.mean_) ** 2) / (2 * self.std_ ** 2) - self.std_.log() - math.log(math.sqrt(2 * math.pi))
+        ladj = 2.0 * (math.log(2.0) - x - torch.nn.functional.softplus(-2.0 * x))
+        return (base - ladj).sum(-1)
+
+    def mean(self):
+        eps = torch.randn((self._samples,) + tuple(self.mean_.shape), device=self.mean_.device)
+        return torch.tanh(self.mean_ + self.std_ * eps).mean(0)
+
+    def mode(self):
+        """models/utils.py:149-158: the most likely of 100 samples (acting path, B=1)."""
+        eps = torch.randn((self._samples,) + tuple(self.mean_.shape), device=self.mean_.device)
+        samples = torch.tanh(self.mean_ + self.std_ * eps)
+        idx = torch.argmax(self.log_prob(samples), 0)
+        return samples[idx, torch.arange(samples.shape[1], device=samples.device)]

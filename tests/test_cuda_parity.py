@@ -409,3 +409,115 @@ def test_imagine_backward_matches_autograd_of_the_oracle(dev, name):
         cmp(dict(m.named_parameters())[k].grad, w.grad, k)
     cmp(gb0.grad, b0.grad, "start belief")
     cmp(gs0.grad, s0.grad, "start state")
+
+
+def test_heads_actor_entropy_under_autograd(dev):
+    """RewardModel/ValueModel.forward, ActorModel.forward and SampleDist.entropy as differentiable ops:
+    values and gradients (parameters and inputs) vs fp64 autograd through the oracle."""
+    from repo_b200.models import ActorModel, RewardModel
+    d = O.DEFAULT_DIMS
+    D, S, A, Hd = d["belief"], d["state"], d["action"], d["hidden"]
+    N = 77
+    rs = np.random.RandomState(21)
+    b = torch.from_numpy((rs.standard_normal((N, D)) * 0.4).astype(np.float32))
+    s = torch.from_numpy(rs.standard_normal((N, S)).astype(np.float32))
+    eps = torch.from_numpy(rs.standard_normal((100, N, A)).astype(np.float32))
+    PR = O.make_mlp_params(31, D + S, Hd, 1, 3, 1.5)
+    PA = O.make_mlp_params(32, D + S, Hd, 2 * A, 4, 1.5)
+
+    # fp64 reference
+    pr64 = {k: v.double().requires_grad_(True) for k, v in PR.items()}
+    pa64 = {k: v.double().requires_grad_(True) for k, v in PA.items()}
+    b64, s64 = b.double().requires_grad_(True), s.double().requires_grad_(True)
+    r64 = O.head_forward(pr64, b64, s64)
+    mean64, std64 = O.actor_forward(pa64, b64, s64)
+    ent64 = O.tanh_normal_entropy(mean64, std64, eps.double())
+    (r64.sum() * 0.7 + ent64.mean() * 3.0 + (mean64 * std64).sum() * 0.1).backward()
+
+    rm, am = RewardModel(D, S, Hd, "elu").to(dev), ActorModel(D, S, Hd, A, "elu").to(dev)
+    rm.load_state_dict(PR), am.load_state_dict(PA)
+    gb, gs = b.to(dev).requires_grad_(True), s.to(dev).requires_grad_(True)
+    r = rm(gb, gs)
+    dist = am.get_action_dist(gb, gs)
+    ent = dist.entropy(eps.to(dev))
+    close(r, r64.detach().float(), "reward head")
+    close(dist.mean_, mean64.detach().float(), "actor mean")
+    close(dist.std_, std64.detach().float(), "actor std")
+    close(ent, ent64.detach().float(), "entropy", atol=2e-3)
+    (r.sum() * 0.7 + ent.mean() * 3.0 + (dist.mean_ * dist.std_).sum() * 0.1).backward()
+
+    def cmp(got, want, nm):
+        scale = float(want.abs().max()) + 1e-12
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-4, err_msg=nm)
+
+    for k, w in pr64.items():
+        cmp(dict(rm.named_parameters())[k].grad, w.grad, "reward." + k)
+    for k, w in pa64.items():
+        cmp(dict(am.named_parameters())[k].grad, w.grad, "actor." + k)
+    cmp(gb.grad, b64.grad, "d belief")
+    cmp(gs.grad, s64.grad, "d state")
+
+
+def test_train_actor_critic_matches_reference_trainer(dev):
+    """The reference's own Dreamer.train_actor_critic (dreamer.py:304-381), run unmodified on CPU with
+    injected noise (oracle/make_golden_trainer.py), against the same update composed from this
+    package: imagine (fused kernel, autograd), heads, MC entropy, lambda-return, losses."""
+    from repo_b200 import losses
+    from repo_b200.models import ActorModel, RewardModel, ValueModel, bottle
+    from repo_b200.rssm import TransitionModel
+    g, meta = C.load("train_actor_critic")
+    seed, N, H = int(meta["seed"]), int(meta["N"]), int(meta["H"])
+    D, S, A, Hd = 200, 30, 6, 200
+    tm = TransitionModel(D, S, A, Hd, 1024, "elu").to(dev)
+    tm.load_state_dict(O.make_transition_params(seed))
+    actor, reward, value = ActorModel(D, S, Hd, A, "elu").to(dev), RewardModel(D, S, Hd, "elu").to(dev), ValueModel(D, S, Hd, "elu").to(dev)
+    actor.load_state_dict(O.make_mlp_params(seed + 1, D + S, Hd, 2 * A, 4))
+    reward.load_state_dict(O.make_mlp_params(seed + 2, D + S, Hd, 1, 3))
+    value.load_state_dict(O.make_mlp_params(seed + 3, D + S, Hd, 1, 3))
+    x = O.make_imagine_inputs(seed + 20, N, H)
+    eps_ent = torch.from_numpy(np.random.RandomState(seed + 30).standard_normal((100, (H - 1) * N, A)).astype(np.float32)).to(dev)
+
+    def freeze(mods):  # FreezeParameters (common/utils.py:47-58)
+        ps = [p for m in mods for p in m.parameters()]
+        old = [p.requires_grad for p in ps]
+        for p in ps:
+            p.requires_grad = False
+        return ps, old
+
+    def unfreeze(ps, old):
+        for p, o in zip(ps, old):
+            p.requires_grad = o
+
+    fz = freeze([tm, reward])
+    imag_b, imag_s, imag_m, imag_sd = tm.imagine(x["belief"].to(dev), x["state"].to(dev), actor, H,
+                                                 eps_action=x["eps_action"].to(dev), eps_prior=x["eps_prior"].to(dev))
+    fz2 = freeze([value])
+    reward_preds = bottle(reward, (imag_b, imag_s))
+    value_preds = bottle(value, (imag_b, imag_s))
+    unfreeze(*fz2)
+    unfreeze(*fz)
+    action_entropy = actor.get_action_dist(imag_b.flatten(0, 1), imag_s.flatten(0, 1)).entropy(eps_ent).mean()
+    latent_entropy = torch.distributions.Independent(torch.distributions.Normal(imag_m, imag_sd), 1).entropy().mean()
+    from oracle.rssm_oracle import lambda_return  # checker-side helper: same arithmetic as common/utils.py:61-71
+    discounts = 0.99 * torch.ones_like(reward_preds)
+    returns = lambda_return(reward_preds[:-1], value_preds[:-1], discounts[:-1], value_preds[-1], 0.95)
+    actor_loss = losses.actor_loss(returns, action_entropy, latent_entropy, 3e-4, 0.0)
+    actor_loss.backward()
+    vp = bottle(value, (imag_b[:-1].detach(), imag_s[:-1].detach()))
+    value_loss = losses.value_loss(vp, returns.detach())
+    value_loss.backward()
+
+    np.testing.assert_allclose(actor_loss.item(), g["log_actor_loss"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(value_loss.item(), g["log_value_loss"], rtol=1e-3)
+    np.testing.assert_allclose(action_entropy.item(), g["log_action_entropy"], rtol=1e-3)
+    np.testing.assert_allclose(latent_entropy.item(), g["log_latent_entropy"], rtol=1e-3)
+    for k, p in actor.named_parameters():
+        w = g["actor_grad_" + k]
+        scale = np.abs(w).max() + 1e-12
+        np.testing.assert_allclose(p.grad.cpu().numpy() / scale, w / scale, rtol=2e-3, atol=1e-3, err_msg="actor " + k)
+    for k, p in value.named_parameters():
+        w = g["value_grad_" + k]
+        scale = np.abs(w).max() + 1e-12
+        np.testing.assert_allclose(p.grad.cpu().numpy() / scale, w / scale, rtol=2e-3, atol=1e-3, err_msg="value " + k)
+    for p in list(tm.parameters()) + list(reward.parameters()):
+        assert p.grad is None  # frozen at call time (dreamer.py:306,315)
