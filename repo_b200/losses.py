@@ -51,3 +51,17 @@ def actor_loss(returns: torch.Tensor, action_entropy: torch.Tensor, latent_entro
 def value_loss(value_pred: torch.Tensor, returns: torch.Tensor) -> torch.Tensor:
     """dreamer.py:362-368 on imag[:-1]."""
     return normal_unit_nll(value_pred, returns).mean()
+
+
+def lambda_return(rewards: torch.Tensor, values: torch.Tensor, discounts: torch.Tensor, bootstrap: torch.Tensor,
+                  lambda_: float = 0.95) -> torch.Tensor:
+    """common/utils.py:61-71 — differentiable (plain tensor ops over the H-2 horizon rows).  The forward-only
+    fused version lives at the end of the imagine kernel (`TransitionModel.imagine(..., reward_model=, value_model=)`)."""
+    next_values = torch.cat([values[1:], bootstrap[None]], 0)
+    inputs = rewards + discounts * next_values * (1 - lambda_)
+    last = bootstrap
+    outputs = []
+    for t in reversed(range(inputs.shape[0])):
+        last = inputs[t] + discounts[t] * lambda_ * last
+        outputs.append(last)
+    return torch.stack(list(reversed(outputs)), 0)

@@ -498,9 +498,8 @@ def test_train_actor_critic_matches_reference_trainer(dev):
     unfreeze(*fz)
     action_entropy = actor.get_action_dist(imag_b.flatten(0, 1), imag_s.flatten(0, 1)).entropy(eps_ent).mean()
     latent_entropy = torch.distributions.Independent(torch.distributions.Normal(imag_m, imag_sd), 1).entropy().mean()
-    from oracle.rssm_oracle import lambda_return  # checker-side helper: same arithmetic as common/utils.py:61-71
     discounts = 0.99 * torch.ones_like(reward_preds)
-    returns = lambda_return(reward_preds[:-1], value_preds[:-1], discounts[:-1], value_preds[-1], 0.95)
+    returns = losses.lambda_return(reward_preds[:-1], value_preds[:-1], discounts[:-1], value_preds[-1], 0.95)
     actor_loss = losses.actor_loss(returns, action_entropy, latent_entropy, 3e-4, 0.0)
     actor_loss.backward()
     vp = bottle(value, (imag_b[:-1].detach(), imag_s[:-1].detach()))
