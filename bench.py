@@ -29,7 +29,7 @@ FLOP_PER_STEP = 1_440_000      # algorithmic forward FLOPs per
 BYTES_PER_STEP = 1_312         # algorithmic HBM bytes per imagined latent step
 HORIZON = 15
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture (profiles/), by rows
-TRAFFIC_BYTES = {}
+TRAFFIC_BYTES = {75776: 238_559_232 + 1_277_413_000}  # profiles/r01_rssm_rows_kernel_75776x14_ncu_full.txt
 DIMS = dict(belief=200, state=30, action=6, hidden=200, embed=1024)
 
 
@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -218,7 +218,6 @@ def run_gpu(a):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
 
     # kernel-only duration of the layer machine (roofline numerator): events around each launch
     kms = []
@@ -255,6 +254,7 @@ def run_gpu(a):
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None  # sampled across both timed loops (device-resident and e2e)
 
     t = torch.tensor([ms, e2e_ms, kernel_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -284,8 +284,53 @@ def run_gpu(a):
 
         img_ms = timeit(lambda: ops.imagine_fwd(P, PA, PR, PV, *xa, HORIZON))
         obs_ms = timeit(lambda: ops.observe_fwd(P, *oa))
+
+        # RSSM part of one training iteration at the RePo default shapes, forward + hand-written backward:
+        #   world model : observe (BPTT over 49 steps) with the RePo KL term + a reward-like read of the latents
+        #   actor-critic: Dreamer.train_actor_critic (imagine, heads, 100-sample entropy, lambda-return, both backward passes)
+        from repo_b200 import losses
+        from repo_b200.models import bottle
+        log_beta = torch.tensor(-11.5, device=dev, requires_grad=True)
+        emb = oa[3].clone().requires_grad_(True)
+
+        def wm_update():
+            outs = model.observe(oa[0], oa[1], oa[2], emb, oa[4], eps_prior=oa[5], eps_post=oa[6])
+            kl = losses.repo_kl_terms(_kl(outs), log_beta)
+            (kl["kl_loss"] + 1e-3 * (outs[0].mean() + outs[4].mean())).backward()
+            model.zero_grad(set_to_none=True)
+            emb.grad = None
+
+        def _kl(o):
+            vr = (o[6] / o[3]) ** 2
+            return (0.5 * (vr + ((o[5] - o[2]) / o[3]) ** 2 - 1 - vr.log())).sum(2)
+
+        eps_ent = torch.randn(100, 14 * 2450, A, device=dev)
+        tparams = list(model.parameters()) + list(reward.parameters())
+
+        def ac_update():
+            for p_ in tparams:
+                p_.requires_grad = False
+            ib, is_, im, isd = model.imagine(xa[0], xa[1], actor, HORIZON, eps_action=xa[2], eps_prior=xa[3])
+            for p_ in value.parameters():
+                p_.requires_grad = False
+            rp, vp = bottle(reward, (ib, is_)), bottle(value, (ib, is_))
+            for p_ in list(value.parameters()) + tparams:
+                p_.requires_grad = True
+            ent = actor.get_action_dist(ib.flatten(0, 1), is_.flatten(0, 1)).entropy(eps_ent).mean()
+            ret = losses.lambda_return(rp[:-1], vp[:-1], 0.99 * torch.ones_like(rp[:-1]), vp[-1], 0.95)
+            losses.actor_loss(ret, ent, torch.zeros((), device=dev)).backward()
+            losses.value_loss(bottle(value, (ib[:-1].detach(), is_[:-1].detach())), ret.detach()).backward()
+            actor.zero_grad(set_to_none=True)
+            value.zero_grad(set_to_none=True)
+
+        wm_ms = timeit(wm_update, 5)
+        ac_ms = timeit(ac_update, 5)
         default_shape = {"imagine_2450x14_ms": img_ms, "imagine_steps_per_s": 2450 * 14 / img_ms * 1e3,
-                         "observe_49x50_ms": obs_ms, "observe_row_steps_per_s": 2450 / obs_ms * 1e3}
+                         "observe_49x50_ms": obs_ms, "observe_row_steps_per_s": 2450 / obs_ms * 1e3,
+                         "world_model_rssm_update_ms": wm_ms, "actor_critic_update_ms": ac_ms,
+                         "actor_critic_update_steps_per_s": 2450 * 14 / ac_ms * 1e3,
+                         "note": "update timings = forward + hand-written backward of the RSSM path (observe BPTT incl. KL; "
+                                 "imagine + heads + MC entropy + lambda-return); conv encoder/decoder and Adam are outside this path"}
 
     if world > 1:
         dist.barrier()

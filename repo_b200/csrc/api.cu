@@ -672,8 +672,8 @@ int repo_b200_observe_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   P.g_post_s = g_post_states; P.g_post_m = g_post_means; P.g_post_sd = g_post_std_devs;
   P.d_q = d_q; P.d_hq = d_hq; P.d_p = d_p; P.d_hp = d_hp; P.d_gi = d_gi; P.d_gh = d_gh; P.d_e = d_e;
   P.d_init_belief = d_prev_belief; P.d_init_state = d_prev_state;
-  const size_t smem = (size_t)(10 * P.D + 5 * P.S + P.Hd) * sizeof(float);
-  observe_bwd_kernel<<<batch, 256, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  const size_t smem = (size_t)(10 * P.D + 5 * P.S + P.Hd + kObsGroups * 256) * sizeof(float);
+  observe_bwd_kernel<<<batch, 256 * kObsGroups, smem, static_cast<cudaStream_t>(stream)>>>(P);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

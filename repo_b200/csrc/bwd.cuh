@@ -42,21 +42,41 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
   return y > 0.f ? 1.f : 0.f;
 }
 
-// out[k] = sum_j W[j*ld + k] * dy[j], j < n  (dy in shared memory, W column walk is coalesced over k)
-__device__ __forceinline__ float col_dot(const float* __restrict__ W, int ld, int k, const float* dy, int n) {
+// out[k] = sum_j W[j*ld + k] * dy[j], j in [j0, j1)  (dy in shared memory, W column walk is coalesced over k)
+__device__ __forceinline__ float col_dot(const float* __restrict__ W, int ld, int k, const float* dy, int j0, int j1) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int j = 0;
-  for (; j + 4 <= n; j += 4) {
+  int j = j0;
+#pragma unroll 2
+  for (; j + 4 <= j1; j += 4) {
     a0 = fmaf(__ldg(W + (size_t)j * ld + k), dy[j], a0);
     a1 = fmaf(__ldg(W + (size_t)(j + 1) * ld + k), dy[j + 1], a1);
     a2 = fmaf(__ldg(W + (size_t)(j + 2) * ld + k), dy[j + 2], a2);
     a3 = fmaf(__ldg(W + (size_t)(j + 3) * ld + k), dy[j + 3], a3);
   }
-  for (; j < n; ++j) a0 = fmaf(__ldg(W + (size_t)j * ld + k), dy[j], a0);
+  for (; j < j1; ++j) a0 = fmaf(__ldg(W + (size_t)j * ld + k), dy[j], a0);
   return (a0 + a1) + (a2 + a3);
 }
 
-__global__ void __launch_bounds__(256) observe_bwd_kernel(const __grid_constant__ ObsBwdParams P) {
+constexpr int kObsGroups = 4;  // thread groups of 256 splitting the reduction range (loads in flight x4)
+
+// Every thread calls this; group g walks its quarter of j for column k, partials meet in shared memory.
+// Returns the full sum to group 0 (other groups get garbage).  Contains two __syncthreads.
+__device__ __forceinline__ float col_dot_split(const float* __restrict__ W, int ld, int k, int kmax, const float* dy,
+                                               int n, float* part, int g) {
+  const int per = (n + kObsGroups - 1) / kObsGroups;
+  const int j0 = min(n, g * per), j1 = min(n, j0 + per);
+  part[g * 256 + k] = (k < kmax) ? col_dot(W, ld, k, dy, j0, j1) : 0.f;
+  __syncthreads();
+  float v = 0.f;
+  if (g == 0) {
+#pragma unroll
+    for (int i = 0; i < kObsGroups; ++i) v += part[i * 256 + k];
+  }
+  __syncthreads();
+  return v;
+}
+
+__global__ void __launch_bounds__(256 * kObsGroups) observe_bwd_kernel(const __grid_constant__ ObsBwdParams P) {
   extern __shared__ float sm[];
   const int D = P.D, S = P.S, A = P.A, Hd = P.Hd, T = P.T, B = P.B;
   float* db = sm;            // D   recurrent dL/d belief_{t}
@@ -68,89 +88,102 @@ __global__ void __launch_bounds__(256) observe_bwd_kernel(const __grid_constant_
   float* dgi = dba + D;      // 3D
   float* dgh = dgi + 3 * D;  // 3D
   float* de = dgh + 3 * D;   // D
-  const int b = blockIdx.x, k = threadIdx.x;
-  const int nth = blockDim.x;
-  for (int i = k; i < D; i += nth) db[i] = 0.f;
-  for (int i = k; i < S; i += nth) ds[i] = 0.f;
+  float* part = de + D;      // kObsGroups * 256 partial sums
+  const int b = blockIdx.x, k = threadIdx.x & 255, g = threadIdx.x >> 8;
+  const bool lead = g == 0;
+  if (lead && k < D) db[k] = 0.f;
+  if (lead && k < S) ds[k] = 0.f;
   __syncthreads();
 
   for (int t = T - 1; t >= 0; --t) {
     const size_t tb = (size_t)t * B + b;
     const float* st = P.stash + tb * P.stash_ld;
     // ---- Gaussian heads: gradient of [mean | raw std] ----
-    for (int j = k; j < S; j += nth) {
+    if (lead && k < S) {
+      const int j = k;
       const size_t o = tb * S + j;
       if (P.with_obs) {
         const float gs = (P.g_post_s ? P.g_post_s[o] : 0.f) + ds[j];  // the posterior sample feeds step t+1
         const float dmu = (P.g_post_m ? P.g_post_m[o] : 0.f) + gs;
         const float dsd = (P.g_post_sd ? P.g_post_sd[o] : 0.f) + gs * P.eps_post[o];
-        dq[j] = dmu;
-        dq[S + j] = dsd * (1.f - __expf(-(P.post_sd[o] - P.min_std)));  // softplus' = 1 - exp(-softplus)
+        const float draw = dsd * (1.f - __expf(-(P.post_sd[o] - P.min_std)));  // softplus' = 1 - exp(-softplus)
+        dq[j] = dmu; dq[S + j] = draw;
+        P.d_q[tb * 2 * S + j] = dmu; P.d_q[tb * 2 * S + S + j] = draw;
       }
       const float gsp = (P.g_prior_s ? P.g_prior_s[o] : 0.f) + (P.with_obs ? 0.f : ds[j]);
       const float dmup = (P.g_prior_m ? P.g_prior_m[o] : 0.f) + gsp;
       const float dsdp = (P.g_prior_sd ? P.g_prior_sd[o] : 0.f) + gsp * P.eps_prior[o];
-      dp[j] = dmup;
-      dp[S + j] = dsdp * (1.f - __expf(-(P.prior_sd[o] - P.min_std)));
+      const float drawp = dsdp * (1.f - __expf(-(P.prior_sd[o] - P.min_std)));
+      dp[j] = dmup; dp[S + j] = drawp;
+      P.d_p[tb * 2 * S + j] = dmup; P.d_p[tb * 2 * S + S + j] = drawp;
     }
+    if (lead && k < D) dba[k] = (P.g_beliefs ? P.g_beliefs[tb * D + k] : 0.f) + db[k];
     __syncthreads();
-    if (P.with_obs)
-      for (int j = k; j < 2 * S; j += nth) P.d_q[tb * 2 * S + j] = dq[j];
-    for (int j = k; j < 2 * S; j += nth) P.d_p[tb * 2 * S + j] = dp[j];
     // ---- posterior hidden layer ----
-    for (int i = k; i < D; i += nth) dba[i] = (P.g_beliefs ? P.g_beliefs[tb * D + i] : 0.f) + db[i];
     if (P.with_obs) {
-      for (int i = k; i < Hd; i += nth) {
-        const float g = col_dot(P.w_q2, Hd, i, dq, 2 * S) * act_grad_from_output(st[5 * D + Hd + i], P.act);
-        dh[i] = g;
-        P.d_hq[tb * Hd + i] = g;
+      float v = col_dot_split(P.w_q2, Hd, k, Hd, dq, 2 * S, part, g);
+      if (lead && k < Hd) {
+        v *= act_grad_from_output(st[5 * D + Hd + k], P.act);
+        dh[k] = v;
+        P.d_hq[tb * Hd + k] = v;
       }
       __syncthreads();
-      for (int i = k; i < D; i += nth) dba[i] += col_dot(P.w_q1, D + P.E, i, dh, Hd);
+      v = col_dot_split(P.w_q1, D + P.E, k, D, dh, Hd, part, g);
+      if (lead && k < D) dba[k] += v;
       __syncthreads();
     }
     // ---- prior hidden layer ----
-    for (int i = k; i < Hd; i += nth) {
-      const float g = col_dot(P.w_p2, Hd, i, dp, 2 * S) * act_grad_from_output(st[5 * D + i], P.act);
-      dh[i] = g;
-      P.d_hp[tb * Hd + i] = g;
+    {
+      float v = col_dot_split(P.w_p2, Hd, k, Hd, dp, 2 * S, part, g);
+      if (lead && k < Hd) {
+        v *= act_grad_from_output(st[5 * D + k], P.act);
+        dh[k] = v;
+        P.d_hp[tb * Hd + k] = v;
+      }
+      __syncthreads();
+      v = col_dot_split(P.w_p1, D, k, D, dh, Hd, part, g);
+      if (lead && k < D) dba[k] += v;
+      __syncthreads();
     }
-    __syncthreads();
-    for (int i = k; i < D; i += nth) dba[i] += col_dot(P.w_p1, D, i, dh, Hd);
-    __syncthreads();
     // ---- GRU cell ----
-    for (int i = k; i < D; i += nth) {
+    if (lead && k < D) {
+      const int i = k;
       const float r = st[D + i], z = st[2 * D + i], n = st[3 * D + i], hn = st[4 * D + i];
       const float bprev = t > 0 ? P.beliefs[(tb - B) * D + i] : (P.init_belief ? P.init_belief[(size_t)b * D + i] : 0.f);
-      const float g = dba[i];
-      const float dnp = g * (1.f - z) * (1.f - n * n);
-      const float dzp = g * (bprev - n) * z * (1.f - z);
+      const float gg = dba[i];
+      const float dnp = gg * (1.f - z) * (1.f - n * n);
+      const float dzp = gg * (bprev - n) * z * (1.f - z);
       const float drp = dnp * hn * r * (1.f - r);
       dgi[i] = drp; dgi[D + i] = dzp; dgi[2 * D + i] = dnp;
       dgh[i] = drp; dgh[D + i] = dzp; dgh[2 * D + i] = dnp * r;
-      db[i] = g * z;  // direct path to belief_{t-1}; W_hh^T dgh is added below
+      db[i] = gg * z;  // direct path to belief_{t-1}; W_hh^T dgh is added below
       float* o_gi = P.d_gi + tb * 3 * D;
       float* o_gh = P.d_gh + tb * 3 * D;
       o_gi[i] = drp; o_gi[D + i] = dzp; o_gi[2 * D + i] = dnp;
       o_gh[i] = drp; o_gh[D + i] = dzp; o_gh[2 * D + i] = dnp * r;
     }
     __syncthreads();
-    for (int i = k; i < D; i += nth) {
-      const float g = col_dot(P.w_ih, D, i, dgi, 3 * D) * act_grad_from_output(st[i], P.act);
-      de[i] = g;
-      P.d_e[tb * D + i] = g;
-      db[i] += col_dot(P.w_hh, D, i, dgh, 3 * D);
+    {
+      float v = col_dot_split(P.w_ih, D, k, D, dgi, 3 * D, part, g);
+      if (lead && k < D) {
+        v *= act_grad_from_output(st[k], P.act);
+        de[k] = v;
+        P.d_e[tb * D + k] = v;
+      }
+      v = col_dot_split(P.w_hh, D, k, D, dgh, 3 * D, part, g);
+      if (lead && k < D) db[k] += v;
+      __syncthreads();
     }
-    __syncthreads();
     // ---- state that entered this step: s_{t-1} * nonterm[t] ----
-    const float nt = P.nonterm ? P.nonterm[tb] : 1.f;
-    for (int j = k; j < S; j += nth) ds[j] = col_dot(P.w_e, S + A, j, de, D) * nt;
-    __syncthreads();
+    {
+      const float nt = P.nonterm ? P.nonterm[tb] : 1.f;
+      const float v = col_dot_split(P.w_e, S + A, k, S, de, D, part, g);
+      if (lead && k < S) ds[k] = v * nt;
+      __syncthreads();
+    }
   }
-  if (P.d_init_belief)
-    for (int i = k; i < D; i += nth) P.d_init_belief[(size_t)b * D + i] = db[i];
-  if (P.d_init_state)
-    for (int j = k; j < S; j += nth) P.d_init_state[(size_t)b * S + j] = ds[j];
+  if (lead && P.d_init_belief && k < D) P.d_init_belief[(size_t)b * D + k] = db[k];
+  if (lead && P.d_init_state && k < S) P.d_init_state[(size_t)b * S + k] = ds[k];
 }
 
 }  // namespace rb
@@ -185,8 +218,18 @@ __device__ __forceinline__ void col_dot_rows(const float* __restrict__ W, int ld
                                              float (&acc)[RB]) {
 #pragma unroll
   for (int r = 0; r < RB; ++r) acc[r] = 0.f;
-#pragma unroll 4
-  for (int j = 0; j < n; ++j) {
+  int j = 0;
+  for (; j + 8 <= n; j += 8) {   // 8 independent weight loads in flight per thread
+    float w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = __ldg(W + (size_t)(j + u) * ld + k);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int r = 0; r < RB; ++r) acc[r] = fmaf(w[u], dy[(j + u) * RB + r], acc[r]);
+    }
+  }
+  for (; j < n; ++j) {
     const float w = __ldg(W + (size_t)j * ld + k);
 #pragma unroll
     for (int r = 0; r < RB; ++r) acc[r] = fmaf(w, dy[j * RB + r], acc[r]);
