@@ -131,10 +131,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
   d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
-// Instruction descriptor for kind::f16: fp16 A/B (K-major both), fp32 D, shape M x N x 16.
-__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+// Instruction descriptor for kind::f16: 16-bit A/B (K-major both; format 0 = fp16, 1 = bf16, chosen per
+// operand), fp32 D, shape M x N x 16.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, uint32_t a_fmt = 0, uint32_t b_fmt = 0) {
   return (1u << 4)                                  // D format: f32
-         | (0u << 7) | (0u << 10)                   // A, B format: f16
+         | (a_fmt << 7) | (b_fmt << 10)             // A, B format
          | (0u << 15) | (0u << 16)                  // A, B K-major
          | (static_cast<uint32_t>(N >> 3) << 17)    // N / 8
          | (static_cast<uint32_t>(M >> 4) << 24);   // M / 16

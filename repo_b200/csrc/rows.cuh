@@ -93,7 +93,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// two floats -> packed fp16 hi pair and lo pair (element 0 in the low half)
+// two floats -> packed fp16 hi pair and lo pair (element 0 in the low half).  Both halves must be fp16:
+// tcgen05 kind::f16 rejects mixed fp16 x bf16 operands (tried: illegal instruction), so a cheap
+// bf16-by-truncation lo half is not an option.
 __device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
   const __half2 h = *reinterpret_cast<const __half2*>(&hi);
@@ -170,10 +172,15 @@ __device__ __forceinline__ void st_row16(float* dst, const float* v, int n_valid
       if (i < n_valid) dst[i] = v[i];
   }
 }
-// branch-free activations (all 16 lanes of a chunk stay independent -> ILP across elements)
+// branch-free activations (all 16 lanes of a chunk stay independent -> ILP across elements).
+// (An FMA-pipe polynomial exp for every other element was tried to unload the XU pipe: it made the
+// stage 45% slower — the epilogue is issue/latency-bound, extra instructions cost more than MUFU.)
 template <int ACT>
 __device__ __forceinline__ float act_bf(float x) {
-  if (ACT == ACT_ELU) return fmaxf(x, 0.f) + (ex2_f(fminf(x, 0.f) * 1.4426950408889634f) - 1.f);
+  if (ACT == ACT_ELU) {
+    const float m = ex2_f(x * 1.4426950408889634f) - 1.f;  // garbage (inf) for large x is selected away
+    return x > 0.f ? x : m;
+  }
   return fmaxf(x, 0.f);
 }
 
