@@ -459,6 +459,18 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         tc_fence_after();
         epi_sync();  // staged biases visible to every epilogue warp
         if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2] = clock64();
+        // The proxy fence before the hand-off also waits for this thread's outstanding GLOBAL stores, and the
+        // output rows are `feature`-strided (32 sectors per store instruction).  Stages with outputs therefore
+        // write their smem/TMEM operands first, hand the stage back, and only then store the outputs, which
+        // drain while the next stage's MMAs run.
+        bool handed = false;
+        auto handoff = [&] {
+          fence_proxy_async_smem();
+          tc_fence_before();
+          if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2 + 1] = clock64();
+          mbar_arrive(bar_act);
+          handed = true;
+        };
 
         switch (st.epi) {
           case R_ACT_H: {
@@ -482,11 +494,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
           case R_GRU: {
             // accumulator: r at [0,W), z at [W,2W), i_n at [2W,3W), h_n at [3W,4W), W = st.width
             const int W = st.width, u0 = st.unit0, nu = st.nfeat;  // nu valid units in this chunk
+            const bool last_chunk = (st.flags & RF_LAST_CHUNK) != 0;
+            float bnew[2][16];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const int c = (half + 2 * k) * 16;
               if (c < nu) {
-                const int nv = min(16, nu - c);
                 float vr[16], vz[16], vi[16], vh[16], bb[16];
                 tmem_ld16(tacc + c, vr);
                 tmem_ld16(tacc + W + c, vz);
@@ -506,10 +519,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const float nn = tanh_f(vi[i] + bb[i] + vh[i]);
-                  vi[i] = nn + vz[i] * (pre[16 * k + i] - nn);   // (1-z)*n + z*b_prev
+                  bnew[k][i] = nn + vz[i] * (pre[16 * k + i] - nn);   // (1-z)*n + z*b_prev
                 }
-                if (row_ok) st_row16(V.beliefs + (trow + row) * D + u0 + c, vi, nv);
               }
+            }
+            if (!last_chunk) handoff();  // X is untouched by this chunk: the accumulators are all the issuer waits for
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int c = (half + 2 * k) * 16;
+              if (c < nu && row_ok) st_row16(V.beliefs + (trow + row) * D + u0 + c, bnew[k], min(16, nu - c));
             }
             if (st.flags & RF_LAST_CHUNK) {
               // every chunk's MMAs are done: now the belief slot of X may be overwritten.  Rows were
@@ -552,6 +570,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               float* o_sd = post ? V.post_sd : V.prior_sd;
               const bool want_kl = post && V.kl != nullptr;
               float kl = 0.f;
+              float keep_s[32], keep_m[32], keep_sd[32];  // outputs, stored after the hand-off
               auto chunk = [&](const int c, const float* e) {
                 const int nv = min(16, S - c);
                 float vm[16], vs[16], pm[16], psd[16];
@@ -580,11 +599,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
                     }
                   }
                 }
-                if (row_ok) {
-                  st_row16(o_s + o, smp, nv);
-                  st_row16(o_m + o, vm, nv);
-                  st_row16(o_sd + o, vs, nv);
-                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { keep_s[c + i] = smp[i]; keep_m[c + i] = vm[i]; keep_sd[c + i] = vs[i]; }
                 if (st.flags & SF_WRITES_STATE) {
                   if (((D + c) & 1) == 0) {
 #pragma unroll
@@ -601,7 +617,19 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               };
               chunk(0, pre);                      // S <= 32 here (wider states run on the vm.cuh kernel)
               if (S > 16) chunk(16, pre + 16);
-              if (want_kl && row_ok) V.kl[trow + row] = kl;
+              handoff();
+              if (row_ok) {
+                const size_t o = (trow + row) * S;
+                st_row16(o_s + o, keep_s, min(16, S));
+                st_row16(o_m + o, keep_m, min(16, S));
+                st_row16(o_sd + o, keep_sd, min(16, S));
+                if (S > 16) {
+                  st_row16(o_s + o + 16, keep_s + 16, S - 16);
+                  st_row16(o_m + o + 16, keep_m + 16, S - 16);
+                  st_row16(o_sd + o + 16, keep_sd + 16, S - 16);
+                }
+                if (want_kl) V.kl[trow + row] = kl;
+              }
             } else if ((st.flags & SF_LOADS_ACTION) && has_next && row_ok) {
               for (int j = 0; j < A; ++j) x_put(x_hi, x_lo, r, D + S + j, __ldg(V.actions_in + (trow + N + row) * A + j));
             }
@@ -622,10 +650,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
                 const float sd = softplus_f(vs[i] + bias[W + i] + V.a_init_std) + V.a_min_std;
                 vm[i] = tanh_f(mean + sd * pre[i]);
               }
-              if (row_ok && V.actions_out) st_row16(V.actions_out + o, vm, A);
 #pragma unroll
               for (int i = 0; i < 16; ++i)
                 if (i < A) x_put(x_hi, x_lo, r, D + S + i, vm[i]);
+              handoff();
+              if (row_ok && V.actions_out) st_row16(V.actions_out + o, vm, A);
             }
           } break;
 
@@ -641,10 +670,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
           default: break;
         }
 
-        fence_proxy_async_smem();
-        tc_fence_before();
-        if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2 + 1] = clock64();
-        mbar_arrive(bar_act);
+        if (!handed) handoff();
         // fetch for the next stage while its MMAs run
         buf ^= 1;
         {
