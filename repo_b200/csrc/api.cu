@@ -211,14 +211,21 @@ int launch_nt(const VmParams& P, cudaStream_t st) {
   return 0;
 }
 
-// rows per CTA: the largest tile that still gives every SM a CTA (weights are re-streamed per
-// CTA, so bigger tiles amortise them; smaller tiles spread a small batch over the chip)
+// rows per CTA for the vm kernel.  Measured per-step cost of one CTA is ~(60 + NT) us (the MMA phase is bound by
+// re-reading the 128-feature weight tiles, the epilogue scales with the rows), and CTAs run in waves of one per
+// SM — so pick the tile that minimises waves x per-CTA cost (2450 rows: 32-row tiles = 77 CTAs in one wave beat
+// 16-row tiles = 154 CTAs in two).
 int pick_row_tile(int rows, int max_acc_tiles, int kx16, int kh16, int requested) {
   int nt = 64;
   if (requested == 16 || requested == 32 || requested == 64) nt = requested;
   else {
     const int sms = std::max(1, sm_count());
-    while (nt > 16 && cdiv(rows, nt) < sms) nt >>= 1;
+    double best = 1e30;
+    for (int cand : {64, 32, 16}) {
+      const int waves = cdiv(cdiv(rows, cand), sms);
+      const double cost = waves * (60.0 + cand);
+      if (cost < best - 1e-9) { best = cost; nt = cand; }
+    }
   }
   while (nt > 16 && (max_acc_tiles * nt > (int)kTmemCols || vm_smem_bytes(nt, kx16, kh16) > 227 * 1024)) nt >>= 1;
   return nt;

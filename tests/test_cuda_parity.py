@@ -520,3 +520,29 @@ def test_train_actor_critic_matches_reference_trainer(dev):
         np.testing.assert_allclose(p.grad.cpu().numpy() / scale, w / scale, rtol=2e-3, atol=1e-3, err_msg="value " + k)
     for p in list(tm.parameters()) + list(reward.parameters()):
         assert p.grad is None  # frozen at call time (dreamer.py:306,315)
+
+
+def test_wide_state_and_action_use_the_vm_kernel(ops, dev):
+    """state > 32 / action > 16 are outside the 128-row kernel's register budget: the library must route them
+    to the vm kernel (KL summed across warps) and still match the oracle."""
+    dims = dict(belief=96, state=40, action=20, hidden=72, embed=48)
+    params = O.make_transition_params(61, dims, 1.3)
+    x = O.make_observe_inputs(62, 7, 150, dims, p_done=0.1)
+    g = lambda k: x[k].to(dev)
+    for rt in (0, 128):
+        outs, kl, _ = ops.observe_fwd(cu(params, dev), g("prev_belief"), g("prev_state"), g("actions"), g("embeds"),
+                                      g("nonterms"), g("eps_prior"), g("eps_post"), row_tile=rt)
+        want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"],
+                         x["eps_prior"], x["eps_post"])
+        for nm, o, w in zip(C.OBS_NAMES, outs, want):
+            close(o, w, f"wide {nm} rt={rt}")
+        close(kl, O.kl_sum(want[5], want[6], want[2], want[3]), "wide kl", atol=1e-3)
+    D, S, A, Hd = dims["belief"], dims["state"], dims["action"], dims["hidden"]
+    actor = O.make_mlp_params(63, D + S, Hd, 2 * A, 4, 1.3)
+    reward = O.make_mlp_params(64, D + S, Hd, 1, 3, 1.3)
+    value = O.make_mlp_params(65, D + S, Hd, 1, 3, 1.3)
+    xi = O.make_imagine_inputs(66, 300, 6, dims)
+    out = run_imagine(ops, dev, params, actor, reward, value, xi, 6, row_tile=128)
+    wi = O.imagine(params, actor, xi["belief"], xi["state"], xi["eps_action"], xi["eps_prior"], 6)
+    for nm, w in zip(C.IMG_NAMES + ["actions"], wi):
+        close(out[nm], w, f"wide imagine {nm}")
