@@ -167,6 +167,16 @@ int repo_b200_tanh_normal_entropy_bwd(const float* mean, const float* std_dev, c
                                       const float* g_entropy, float* d_mean, float* d_std, int m, int action,
                                       int samples, void* stream);
 
+/* ---- optimiser tail over one flat fp32 bucket: nn.utils.clip_grad_norm_ + Adam.step as the trainers call them
+ * (dreamer.py:286-289, 356-359, 370-373; repo.py:87-96), torch defaults (no weight decay, no amsgrad).
+ * repo_b200_sqnorm_accumulate adds sum(grad^2) to *sqnorm (device scalar, zero it first);
+ * repo_b200_adam_clip_step scales grad by min(1, max_norm / (sqrt(*sqnorm) + 1e-6)) (sqnorm NULL or max_norm <= 0:
+ * no clipping) and applies the bias-corrected Adam update of 1-based `step`.  No host synchronisation. */
+int repo_b200_sqnorm_accumulate(const float* grad, long long n, float* sqnorm, void* stream);
+int repo_b200_adam_clip_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                             const float* sqnorm, float max_norm, float lr, float beta1, float beta2, float eps,
+                             int step, void* stream);
+
 /* ---- replay gather: the index bookkeeping of SequenceReplayBuffer.sample (common/buffers.py:156-166) after
  * `np.random.choice` (start_inds, drawn on the host so the RNG stream is the reference's), fused with
  * preprocess (common/utils.py:74-80: x/255*2-1 in numpy's operation order) and nonterms = 1 - dones

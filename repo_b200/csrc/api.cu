@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -15,6 +16,7 @@
 #include "rows.cuh"
 #include "elementwise.cuh"
 #include "bwd.cuh"
+#include "optim.cuh"
 
 using namespace rb;
 
@@ -725,6 +727,29 @@ int repo_b200_imagine_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
     configured = smem;
   }
   imagine_bwd_kernel<RB><<<cdiv(n_rows, RB), 256, smem, static_cast<cudaStream_t>(stream)>>>(P);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int repo_b200_sqnorm_accumulate(const float* grad, long long n, float* sqnorm, void* stream) {
+  if (n < 0) return fail(-1, "sqnorm: bad size");
+  if (n == 0) return 0;
+  if (!grad || !sqnorm) return fail(-1, "sqnorm: NULL pointer");
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  sqnorm_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad, n, sqnorm);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int repo_b200_adam_clip_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, const float* sqnorm,
+                             float max_norm, float lr, float beta1, float beta2, float eps, int step, void* stream) {
+  if (n < 0 || step < 1) return fail(-1, "adam: bad size / step");
+  if (n == 0) return 0;
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return fail(-1, "adam: NULL pointer");
+  const double bc1 = 1.0 - std::pow((double)beta1, step), bc2 = 1.0 - std::pow((double)beta2, step);
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  adam_clip_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, sqnorm, max_norm,
+                                                                         lr, beta1, beta2, eps, (float)bc1, (float)std::sqrt(bc2));
   CUDA_OK(cudaGetLastError());
   return 0;
 }

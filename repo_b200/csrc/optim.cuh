@@ -1,0 +1,51 @@
+// Optimiser tail of every update (dreamer.py:286-289, 356-359, 370-373; repo.py:87-96):
+// clip_grad_norm_(params, max_norm) followed by Adam.step, over ONE flat fp32 bucket per parameter group
+// (the same bucket the data-parallel all-reduce works on), with no host synchronisation: the squared norm
+// stays on the device and the clip coefficient is recomputed by every thread of the update kernel.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace rb {
+
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float acc = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = g[i];
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  __shared__ float warp_sums[8];
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = warp_sums[threadIdx.x];
+#pragma unroll
+    for (int s = 4; s > 0; s >>= 1) v += __shfl_xor_sync(0xffu, v, s);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+// torch semantics: clip_coef = min(1, max_norm / (||g|| + 1e-6)); Adam with bias correction
+//   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, long long n, const float* __restrict__ sqnorm,
+                                                        float max_norm, float lr, float b1, float b2, float eps,
+                                                        float bc1, float bc2_sqrt) {
+  float coef = 1.f;
+  if (sqnorm && max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(*sqnorm) + 1e-6f));
+  const float step_size = lr / bc1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * coef;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    g[i] = gi;  // like clip_grad_norm_, the clipped gradient is left in place
+    p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
+}  // namespace rb

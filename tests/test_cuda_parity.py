@@ -546,3 +546,32 @@ def test_wide_state_and_action_use_the_vm_kernel(ops, dev):
     wi = O.imagine(params, actor, xi["belief"], xi["state"], xi["eps_action"], xi["eps_prior"], 6)
     for nm, w in zip(C.IMG_NAMES + ["actions"], wi):
         close(out[nm], w, f"wide imagine {nm}")
+
+
+def test_flat_adam_matches_clip_grad_norm_plus_torch_adam(dev):
+    """repo_b200.optim.FlatAdam == nn.utils.clip_grad_norm_(params, c) + torch.optim.Adam.step
+    (dreamer.py:286-289), including steps where the clip is active, over several iterations."""
+    from repo_b200.optim import FlatAdam
+    torch.manual_seed(0)
+    shapes = [(200, 36), (200,), (600, 200), (600,), (1,), (60, 200)]
+    ref = [torch.nn.Parameter(torch.randn(s, device=dev) * 0.1) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    opt_ref = torch.optim.Adam(ref, lr=3e-4)
+    opt = FlatAdam(mine, lr=3e-4, max_grad_norm=100.0)
+    for it in range(5):
+        scale = 1000.0 if it % 2 == 0 else 0.01  # alternate clipped / unclipped steps
+        grads = [torch.randn(s, device=dev) * scale for s in shapes]
+        opt_ref.zero_grad()
+        opt.zero_grad()
+        for p, q, g in zip(ref, mine, grads):
+            p.grad = g.clone()
+            (q * g).sum().backward()  # autograd accumulates into the flat bucket views
+        total = torch.nn.utils.clip_grad_norm_(ref, 100.0)
+        opt_ref.step()
+        opt.step()
+        np.testing.assert_allclose(opt.grad_norm().item(), total.item(), rtol=1e-5)
+        for p, q in zip(ref, mine):
+            np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().cpu().numpy(), rtol=2e-5, atol=2e-7)
+    sd = opt.state_dict()
+    assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and sd["param_groups"][0]["lr"] == 3e-4
+    np.testing.assert_allclose(sd["state"][2]["exp_avg"].cpu().numpy(), opt_ref.state_dict()["state"][2]["exp_avg"].cpu().numpy(), rtol=1e-4, atol=1e-6)
