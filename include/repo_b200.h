@@ -167,6 +167,18 @@ int repo_b200_tanh_normal_entropy_bwd(const float* mean, const float* std_dev, c
                                       const float* g_entropy, float* d_mean, float* d_std, int m, int action,
                                       int samples, void* stream);
 
+/* ---- conv_gemm: one Conv2d / ConvTranspose2d parity class as an implicit GEMM (VisualEncoder encoder.py:21-41,
+ * VisualObservationModel decoder.py:28-48).  `map` is the 26-int ConvMap of repo_b200/csrc/vm.cuh (row grid, input
+ * layout/dims, tap window, input/output pixel maps, relu/accumulate); w_mat is (cout, ntaps*C) with columns ordered
+ * (tap, cin); workspace >= repo_b200_linear_workspace_bytes(ntaps*C, cout).  Built by repo_b200/conv.py. */
+int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, float* out, int frames, int cout,
+                        const int* map, void* workspace, size_t workspace_bytes, void* stream);
+
+/* backward helpers with the same map: im2col materialises the gathered rows (rows = frames*RA*RB, ntaps*C columns)
+ * for the weight-gradient GEMM; col2im is the adjoint gather onto an NHWC (frames,H,W,C) input gradient. */
+int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream);
+int repo_b200_col2im(const float* d_col, float* d_input, int frames, int accumulate, const int* map, void* stream);
+
 /* ---- optimiser tail over one flat fp32 bucket: nn.utils.clip_grad_norm_ + Adam.step as the trainers call them
  * (dreamer.py:286-289, 356-359, 370-373; repo.py:87-96), torch defaults (no weight decay, no amsgrad).
  * repo_b200_sqnorm_accumulate adds sum(grad^2) to *sqnorm (device scalar, zero it first);

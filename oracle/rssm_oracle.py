@@ -277,3 +277,24 @@ def shift_for_observe(actions, embeds, nonterms):
     return actions[:-1], embeds[1:], nonterms[:-1]
 
 
+
+
+# ----------------------------------------------------------------------------
+# conv stacks (second tier): restated with torch's conv ops, which is where the
+# reference's arithmetic lives (encoder.py:26-41, decoder.py:35-48)
+# ----------------------------------------------------------------------------
+
+def visual_encoder(p: Params, obs):
+    """encoder.py:34-41 with the default embedding_size == 1024 (fc = Identity)."""
+    h = obs
+    for i in range(1, 5):
+        h = F.relu(F.conv2d(h, p[f"conv{i}.weight"], p[f"conv{i}.bias"], stride=2))
+    return h.reshape(-1, 1024)
+
+
+def visual_decoder(p: Params, belief, state):
+    """decoder.py:41-48: fc1 without activation, then 4 transposed convolutions (ReLU on the first three)."""
+    h = F.linear(torch.cat([belief, state], 1), p["fc1.weight"], p["fc1.bias"]).reshape(-1, p["fc1.weight"].shape[0], 1, 1)
+    for i in range(1, 4):
+        h = F.relu(F.conv_transpose2d(h, p[f"conv{i}.weight"], p[f"conv{i}.bias"], stride=2))
+    return F.conv_transpose2d(h, p["conv4.weight"], p["conv4.bias"], stride=2)

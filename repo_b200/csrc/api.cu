@@ -754,6 +754,59 @@ int repo_b200_adam_clip_step(float* param, float* grad, float* exp_avg, float* e
   return 0;
 }
 
+// ---- (transposed) convolution as implicit GEMM on the vm machine
+int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, float* out, int frames, int cout,
+                        const int* map /* ConvMap as 26 ints */, void* ws, size_t ws_bytes, void* stream) {
+  if (!input || !w_mat || !out || !map || !ws) return fail(-1, "conv: NULL pointer");
+  ConvMap cm;
+  static_assert(sizeof(ConvMap) == 26 * sizeof(int), "ConvMap layout");
+  std::memcpy(&cm, map, sizeof(cm));
+  cm.enabled = 1;
+  if (cm.ntaps < 1 || cm.C < 1 || cout < 1 || cout > 1024) return fail(-1, "conv: bad sizes");
+  const int K = cm.ntaps * cm.C;
+  const long long rows = (long long)frames * cm.RA * cm.RB;
+  if (rows <= 0) return 0;
+  if (rows > 0x7fffffffLL) return fail(-1, "conv: too many rows");
+  if (K > 1900) return fail(-1, "conv: K = %d per launch exceeds the shared-memory budget (split the taps)", K);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Builder bl;
+  build_linear(bl, w_mat, bias, K, 0, K, cout);
+  int rc = bl.bind_and_pack(ws, ws_bytes, true, st);
+  if (rc) return rc;
+  VmParams& P = bl.P;
+  P.n_steps = 1;
+  P.N = (int)rows;
+  P.init_x = input; P.init_x_cols = K; P.init_x_ld = K;
+  P.out = out; P.out_ld = cout;
+  P.conv = cm;
+  return launch(P, bl.max_acc_tiles, 0, st);
+}
+
+int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream) {
+  if (!input || !col || !map) return fail(-1, "im2col: NULL pointer");
+  ConvMap cm;
+  std::memcpy(&cm, map, sizeof(cm));
+  const long long rows = (long long)frames * cm.RA * cm.RB;
+  if (rows <= 0) return 0;
+  const long long total = rows * cm.ntaps * cm.C;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  im2col_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(input, col, rows, cm);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int repo_b200_col2im(const float* d_col, float* d_input, int frames, int accumulate, const int* map, void* stream) {
+  if (!d_col || !d_input || !map) return fail(-1, "col2im: NULL pointer");
+  ConvMap cm;
+  std::memcpy(&cm, map, sizeof(cm));
+  const long long total = (long long)frames * cm.H * cm.W * cm.C;
+  if (total <= 0) return 0;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  col2im_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_col, d_input, frames, accumulate, cm);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ---- generic MLP on [belief | state]: forward through the layer machine, backward on the SIMT kernel
 static void build_mlp(Builder& b, const repo_b200_dims* d, const repo_b200_mlp_weights* M, int out_f, int act, bool stash) {
   const int D = d->belief, S = d->state, Hd = d->hidden;

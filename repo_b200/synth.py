@@ -85,3 +85,30 @@ def make_imagine_inputs(seed: int, N: int, horizon: int, dims=DEFAULT_DIMS):
         eps_action=f(rs.standard_normal((horizon - 1, N, A))),
         eps_prior=f(rs.standard_normal((horizon - 1, N, S))),
     )
+
+
+def make_conv_params(which: str, seed: int) -> Params:
+    """VisualEncoder (encoder.py:26-29) / VisualObservationModel (decoder.py:35-39) parameters with torch's default
+    init distribution (U(+-1/sqrt(fan_in))), from numpy."""
+    rs = np.random.RandomState(seed)
+    p: Params = {}
+    if which == "encoder":
+        for i, (ci, co) in enumerate([(3, 32), (32, 64), (64, 128), (128, 256)], 1):
+            b = 1.0 / math.sqrt(ci * 16)
+            p[f"conv{i}.weight"] = _uniform(rs, (co, ci, 4, 4), b)
+            p[f"conv{i}.bias"] = _uniform(rs, (co,), b)
+    else:
+        b = 1.0 / math.sqrt(230)
+        p["fc1.weight"], p["fc1.bias"] = _uniform(rs, (1024, 230), b), _uniform(rs, (1024,), b)
+        for i, (ci, co, k) in enumerate([(1024, 128, 5), (128, 64, 5), (64, 32, 6), (32, 3, 6)], 1):
+            b = 1.0 / math.sqrt(co * k * k)  # ConvTranspose2d fan_in is computed on dim 1 of its (cin, cout, k, k) weight
+            p[f"conv{i}.weight"] = _uniform(rs, (ci, co, k, k), b)
+            p[f"conv{i}.bias"] = _uniform(rs, (co,), b)
+    return p
+
+
+def make_frames(seed: int, n: int, hw=(64, 64)) -> torch.Tensor:
+    """n preprocessed frames: uint8 U{0..255} -> x/255*2-1 (common/utils.py:74-80)."""
+    rs = np.random.RandomState(seed)
+    u8 = rs.randint(0, 256, (n, 3) + tuple(hw)).astype(np.uint8)
+    return torch.from_numpy(((u8.astype(np.float32) / 255) * 2) - 1.0)
