@@ -186,3 +186,140 @@ class VisualEncoder(nn.Module):
         if isinstance(self.fc, nn.Identity):
             return hidden
         raise NotImplementedError("embedding_size != 1024 needs the extra Linear; not wired to the machine yet")
+
+
+# ------------------------------------------------------------------------------------------------- decoder
+def _deconv_classes(cin, hin, win, k, out_nchw, relu):
+    """The four output-parity classes of ConvTranspose2d(k, stride 2): (py, px, ConvMap)."""
+    ho, wo = (hin - 1) * 2 + k, (win - 1) * 2 + k
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            th, tw = (k - py + 1) // 2, (k - px + 1) // 2
+            ra, rb = (ho - py + 1) // 2, (wo - px + 1) // 2
+            out.append((py, px, ConvMap(RA=ra, RB=rb, in_nchw=0, C=cin, H=hin, W=win, TH=th, TW=tw, sy=1, sx=1, dy=-1, dx=-1,
+                                        out_nchw=int(out_nchw), Ho=ho, Wo=wo, osy=2, osx=2, oy0=py, ox0=px, relu=int(relu))))
+    return ho, wo, out
+
+
+def _deconv_wmat(w, py, px):  # (Cin, Cout, k, k) -> class matrix (Cout, (th, tw, cin))
+    sub = w[:, :, py::2, px::2]
+    return sub.permute(1, 2, 3, 0).reshape(w.shape[1], -1).contiguous()
+
+
+_DEC = [(1024, 128, 5), (128, 64, 5), (64, 32, 6), (32, 3, 6)]
+
+
+class _DecoderFn(torch.autograd.Function):
+    """fc1 -> view(1024,1,1) -> 4 x ConvTranspose2d (decoder.py:41-48)."""
+
+    @staticmethod
+    def forward(ctx, belief, state, *params):
+        from . import ops
+        fc_w, fc_b = params[0], params[1]
+        ws, bs = params[2::2], params[3::2]
+        F_ = belief.shape[0]
+        xin = torch.cat([_need_cuda(belief.detach(), "belief"), _need_cuda(state.detach(), "state")], 1)
+        h = ops.linear(xin, fc_w.detach().contiguous(), fc_b.detach().contiguous())      # (F, 1024), no activation
+        # layer 1: 1x1 input -> 5x5 output is a plain GEMM; features ordered (kh, kw, co) = NHWC (F,5,5,128)
+        k1, co1 = ws[0].shape[2], ws[0].shape[1]
+        w1 = ws[0].detach().permute(2, 3, 1, 0).reshape(k1 * k1 * co1, -1).contiguous()
+        b1 = bs[0].detach().repeat(k1 * k1).contiguous()
+        a1 = torch.empty(F_, k1, k1, co1, device=h.device, dtype=torch.float32)
+        conv_gemm(h, w1, b1, a1, F_, k1 * k1 * co1,
+                  ConvMap(RA=1, RB=1, in_nchw=0, C=h.shape[1], H=1, W=1, TH=1, TW=1, sy=1, sx=1, dy=1, dx=1, Ho=1, Wo=1, relu=1))
+        acts, layer_maps = [xin, h, a1], []
+        hin = k1
+        for li in (1, 2, 3):
+            cin, cout, k = _DEC[li]
+            last = li == 3
+            ho, wo, classes = _deconv_classes(cin, hin, hin, k, out_nchw=last, relu=not last)
+            out = torch.empty((F_, cout, ho, wo) if last else (F_, ho, wo, cout), device=h.device, dtype=torch.float32)
+            for py, px, cm in classes:
+                conv_gemm(acts[-1], _deconv_wmat(ws[li].detach(), py, px), bs[li].detach().contiguous(), out, F_, cout, cm)
+            acts.append(out)
+            layer_maps.append(classes)
+            hin = ho
+        ctx.layer_maps = layer_maps
+        ctx.belief_size = belief.shape[1]
+        ctx.save_for_backward(*acts, *params)
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        acts, params = saved[:6], saved[6:]
+        xin, h, a1, a2, a3, out = acts
+        fc_w, fc_b = params[0], params[1]
+        ws, bs = params[2::2], params[3::2]
+        F_ = xin.shape[0]
+        need = ctx.needs_input_grad
+        grads = [None] * len(params)
+        layer_in = [a1, a2, a3]
+        # gradient of the last layer's output (NCHW, no activation) as NHWC
+        g_nhwc = g.contiguous().float().permute(0, 2, 3, 1).contiguous()
+        for li in (3, 2, 1):
+            x = layer_in[li - 1]
+            classes = ctx.layer_maps[li - 1]
+            if need[2 + 2 * li + 1]:
+                grads[2 * li + 3] = g_nhwc.sum((0, 1, 2))
+            dw = torch.zeros_like(ws[li]) if need[2 + 2 * li] else None
+            d_in = torch.empty_like(x)
+            first = True
+            for py, px, cm in classes:
+                gc = g_nhwc[:, py::2, px::2, :].reshape(-1, g_nhwc.shape[-1])
+                if dw is not None:
+                    col = im2col(x, F_, cm)
+                    dwm = (gc.t() @ col).reshape(ws[li].shape[1], cm.TH, cm.TW, ws[li].shape[0])  # (co, th, tw, ci)
+                    dw[:, :, py::2, px::2] = dwm.permute(3, 0, 1, 2)
+                    del col
+                d_col = gc @ _deconv_wmat(ws[li], py, px)
+                col2im(d_col, d_in, F_, cm, accumulate=not first)
+                first = False
+                del d_col
+            if dw is not None:
+                grads[2 * li + 2] = dw
+            g_nhwc = d_in * (x > 0)  # ReLU of the layer that produced x
+        # layer 1 (plain GEMM) and fc1
+        k1, co1 = ws[0].shape[2], ws[0].shape[1]
+        g1 = g_nhwc.reshape(F_, k1 * k1 * co1)
+        w1 = ws[0].permute(2, 3, 1, 0).reshape(k1 * k1 * co1, -1)
+        if need[2 + 2]:
+            grads[2] = (g1.t() @ h).reshape(k1, k1, co1, -1).permute(3, 2, 0, 1).contiguous()
+        if need[2 + 3]:
+            grads[3] = g1.reshape(F_, k1 * k1, co1).sum((0, 1))
+        d_h = g1 @ w1
+        if need[2]:
+            grads[0] = d_h.t() @ xin
+        if need[3]:
+            grads[1] = d_h.sum(0)
+        gb = gs = None
+        if need[0] or need[1]:
+            d_x = d_h @ fc_w
+            gb, gs = d_x[:, :ctx.belief_size].contiguous(), d_x[:, ctx.belief_size:].contiguous()
+        return (gb if need[0] else None, gs if need[1] else None, *grads)
+
+
+class VisualObservationModel(nn.Module):
+    """decoder.py:28-48 — Linear(belief+state -> 1024, no activation) -> ConvTranspose2d(1024->128 k5, 128->64 k5,
+    64->32 k6, 32->3 k6; stride 2, ReLU on the first three): 1 -> 5 -> 13 -> 30 -> 64 pixels."""
+
+    def __init__(self, belief_size, state_size, embedding_size, activation_function="relu"):
+        super().__init__()
+        if activation_function != "relu":
+            raise RuntimeError("the fused conv epilogue implements ReLU (cnn_activation_function default, train_repo.py:32)")
+        if embedding_size != 1024:
+            raise RuntimeError("VisualObservationModel kernels are sized for embedding_size == 1024")
+        self.embedding_size = embedding_size
+        self.belief_size = belief_size
+        self.fc1 = nn.Linear(belief_size + state_size, embedding_size)
+        self.conv1 = nn.ConvTranspose2d(embedding_size, 128, 5, stride=2)
+        self.conv2 = nn.ConvTranspose2d(128, 64, 5, stride=2)
+        self.conv3 = nn.ConvTranspose2d(64, 32, 6, stride=2)
+        self.conv4 = nn.ConvTranspose2d(32, 3, 6, stride=2)
+
+    def forward(self, belief, state):
+        params = [self.fc1.weight, self.fc1.bias]
+        for c in (self.conv1, self.conv2, self.conv3, self.conv4):
+            params += [c.weight, c.bias]
+        return _DecoderFn.apply(belief, state, *params)

@@ -762,7 +762,7 @@ int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bia
   static_assert(sizeof(ConvMap) == 26 * sizeof(int), "ConvMap layout");
   std::memcpy(&cm, map, sizeof(cm));
   cm.enabled = 1;
-  if (cm.ntaps < 1 || cm.C < 1 || cout < 1 || cout > 1024) return fail(-1, "conv: bad sizes");
+  if (cm.ntaps < 1 || cm.C < 1 || cout < 1 || cout > 4096) return fail(-1, "conv: bad sizes");
   const int K = cm.ntaps * cm.C;
   const long long rows = (long long)frames * cm.RA * cm.RB;
   if (rows <= 0) return 0;

@@ -53,3 +53,35 @@ def test_visual_encoder_backward_matches_autograd(dev):
     (enc(x.to(dev)) * R.to(dev)).sum().backward()
     for k, w in p64.items():
         rel_close(dict(enc.named_parameters())[k].grad, w.grad, "encoder grad " + k, rtol=2e-3, floor=3e-4)
+
+
+def test_visual_decoder_forward_matches_reference(dev):
+    from repo_b200.conv import VisualObservationModel
+    g, _ = C.load("conv_stacks")
+    p = synth.make_conv_params("decoder", 701)
+    dec = VisualObservationModel(200, 30, 1024).to(dev)
+    dec.load_state_dict(p)
+    xi = synth.make_imagine_inputs(703, 3, 2)
+    with torch.no_grad():
+        o = dec(xi["belief"].to(dev), xi["state"].to(dev))
+    assert o.shape == (3, 3, 64, 64)
+    rel_close(o, g["recon"], "recon vs reference VisualObservationModel")
+    rel_close(o, O.visual_decoder(p, xi["belief"], xi["state"]), "recon vs oracle")
+
+
+def test_visual_decoder_backward_matches_autograd(dev):
+    from repo_b200.conv import VisualObservationModel
+    p = synth.make_conv_params("decoder", 720)
+    xi = synth.make_imagine_inputs(721, 4, 2)
+    R = torch.from_numpy(np.random.RandomState(2).standard_normal((4, 3, 64, 64)).astype(np.float32))
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    b64, s64 = xi["belief"].double().requires_grad_(True), xi["state"].double().requires_grad_(True)
+    (O.visual_decoder(p64, b64, s64) * R.double()).sum().backward()
+    dec = VisualObservationModel(200, 30, 1024).to(dev)
+    dec.load_state_dict(p)
+    gb, gs = xi["belief"].to(dev).requires_grad_(True), xi["state"].to(dev).requires_grad_(True)
+    (dec(gb, gs) * R.to(dev)).sum().backward()
+    for k, w in p64.items():
+        rel_close(dict(dec.named_parameters())[k].grad, w.grad, "decoder grad " + k, rtol=2e-3, floor=3e-4)
+    rel_close(gb.grad, b64.grad, "d belief", rtol=2e-3, floor=3e-4)
+    rel_close(gs.grad, s64.grad, "d state", rtol=2e-3, floor=3e-4)
