@@ -167,12 +167,16 @@ int repo_b200_tanh_normal_entropy_bwd(const float* mean, const float* std_dev, c
                                       const float* g_entropy, float* d_mean, float* d_std, int m, int action,
                                       int samples, void* stream);
 
-/* ---- conv_gemm: one Conv2d / ConvTranspose2d parity class as an implicit GEMM (VisualEncoder encoder.py:21-41,
- * VisualObservationModel decoder.py:28-48).  `map` is the 26-int ConvMap of repo_b200/csrc/vm.cuh (row grid, input
- * layout/dims, tap window, input/output pixel maps, relu/accumulate); w_mat is (cout, ntaps*C) with columns ordered
- * (tap, cin); workspace >= repo_b200_linear_workspace_bytes(ntaps*C, cout).  Built by repo_b200/conv.py. */
-int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, float* out, int frames, int cout,
-                        const int* map, void* workspace, size_t workspace_bytes, void* stream);
+/* ---- conv_gemm: one Conv2d / ConvTranspose2d layer as an implicit GEMM on tcgen05 (VisualEncoder encoder.py:21-41,
+ * VisualObservationModel decoder.py:28-48), also used for the data gradients of those layers.  `map` is the 27-int
+ * ConvMap of repo_b200/csrc/vm.cuh (row grid, input layout/dims, tap window, input/output pixel maps, relu, shuffle);
+ * w_mat is (n_total, ntaps*C) with columns ordered (tap, cin); with map.shuffle the n_total = 4*cout features are the
+ * (py, px, cout) sub-pixel classes of a stride-2 transposed convolution.  relu_mask (nullable, laid out like out)
+ * zeroes outputs where mask <= 0.  workspace >= repo_b200_conv_workspace_bytes(ntaps*C, n_total).
+ * Built by repo_b200/conv.py. */
+size_t repo_b200_conv_workspace_bytes(int k, int n_total);
+int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, const float* relu_mask, float* out,
+                        int frames, int n_total, const int* map, void* workspace, size_t workspace_bytes, void* stream);
 
 /* backward helpers with the same map: im2col materialises the gathered rows (rows = frames*RA*RB, ntaps*C columns)
  * for the weight-gradient GEMM; col2im is the adjoint gather onto an NHWC (frames,H,W,C) input gradient. */

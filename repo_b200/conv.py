@@ -1,19 +1,22 @@
 """Convolutional encoder / decoder of the pixel world model, cuDNN-free (reference:
 algorithms/repo/models/encoder.py:21-41 `VisualEncoder`, decoder.py:28-48 `VisualObservationModel`).
 
-Every Conv2d / ConvTranspose2d runs as an IMPLICIT GEMM on the tcgen05 layer machine (vm.cuh): the
-machine's operand loader gathers each output position's receptive field straight from the input tensor
-(no materialised im2col), the products are the same fp16 hi/lo three-MMA scheme as the RSSM layers, and
-the store epilogue adds the bias, applies ReLU and scatters onto the output grid.  Activations between
-layers are NHWC (channels contiguous = the GEMM's feature dimension).
+Every Conv2d / ConvTranspose2d — and the data gradient of each — runs as an IMPLICIT GEMM on tcgen05
+(repo_b200/csrc/conv.cuh): gather warps build each output position's receptive field straight from the
+input tensor into the MMA operand ring (no materialised im2col), the products are the same fp16 hi/lo
+three-MMA scheme as the RSSM layers, and the epilogue adds the bias, applies ReLU (or the ReLU mask of the
+layer below, in backward) and scatters onto the output grid.  Activations between layers are NHWC
+(channels contiguous = the GEMM's K / feature dimension).
 
 * Conv2d(k4, s2): row = output pixel, taps = 4x4, input pixel = 2*o + tap.
-* ConvTranspose2d(k, s2): four parity classes of the output grid; class (py,px) only sees taps kh = py+2*th,
-  kw = px+2*tw, i.e. a stride-1 gather with input pixel = o' - t.  Each class is one GEMM launch.
+* ConvTranspose2d(k, s2) = one stride-1 gather over T = ceil(k/2) taps per axis whose 4*Cout features are the
+  four output-parity classes (py, px): class (py, px) uses kernel taps kh = py + 2*th, kw = px + 2*tw (zero
+  where kh >= k), input pixel = o' - t, and the epilogue pixel-shuffles (o', py) -> 2*o' + py.
+* Data gradients are the adjoint maps: for Conv2d(s2) a sub-pixel (shuffle) conv of the output gradient with
+  2x2 taps; for ConvTranspose2d a stride-1 conv (taps +t) over the un-shuffled output gradient.
 
-Backward: weight gradients are GEMMs of the output gradient against the (materialised, backward-only)
-gathered rows; data gradients are a GEMM with the weight matrix followed by the col2im gather.  Those are
-plain GEMMs (torch.matmul / cuBLAS); the gathers are hand-written kernels (elementwise.cuh)."""
+Weight gradients are GEMMs of the output gradient against the gathered rows, which are materialised for
+backward only (`im2col`, elementwise.cuh) and multiplied by cuBLAS (plain library GEMM)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -22,11 +25,12 @@ from typing import List, Optional
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import _lib
 
 _MAP_FIELDS = ("enabled RA RB in_nchw C H W TH TW tap0 ntaps sy sx dy dx y0 x0 "
-               "out_nchw Ho Wo osy osx oy0 ox0 relu accumulate").split()
+               "out_nchw Ho Wo osy osx oy0 ox0 relu accumulate shuffle").split()
 
 
 @dataclass
@@ -34,7 +38,7 @@ class ConvMap:
     RA: int; RB: int; in_nchw: int; C: int; H: int; W: int; TH: int; TW: int
     sy: int; sx: int; dy: int; dx: int; y0: int = 0; x0: int = 0
     out_nchw: int = 0; Ho: int = 0; Wo: int = 0; osy: int = 1; osx: int = 1; oy0: int = 0; ox0: int = 0
-    relu: int = 0; accumulate: int = 0; tap0: int = 0; ntaps: int = 0; enabled: int = 1
+    relu: int = 0; accumulate: int = 0; tap0: int = 0; ntaps: int = 0; enabled: int = 1; shuffle: int = 0
 
     def carray(self, **over):
         vals = {f: getattr(self, f) for f in _MAP_FIELDS}
@@ -62,26 +66,16 @@ def _need_cuda(t, name):
     return t.contiguous()
 
 
-_MAX_K = 1024  # columns per launch (shared-memory budget of the operand buffer); more taps -> accumulate passes
-
-
-def conv_gemm(x, w_mat, bias, out, frames, cout, cmap: ConvMap):
-    """out (+)= gather(x) @ w_mat^T + bias through the layer machine; splits the taps when K is too large."""
+def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=None):
+    """out = epilogue(gather(x) @ w_mat^T + bias) on the tcgen05 conv kernel (one launch + the weight packing)."""
     L = _lib.lib()
-    taps = cmap.TH * cmap.TW
-    per = max(1, _MAX_K // cmap.C)
-    t0 = 0
-    first = True
-    while t0 < taps:
-        n = min(per, taps - t0)
-        last = t0 + n == taps
-        wm = w_mat[:, t0 * cmap.C:(t0 + n) * cmap.C].contiguous()
-        ws = torch.empty(L.repo_b200_linear_workspace_bytes(n * cmap.C, cout), dtype=torch.uint8, device=x.device)
-        m = cmap.carray(tap0=t0, ntaps=n, relu=cmap.relu if last else 0, accumulate=(cmap.accumulate if first else 1))
-        rc = L.repo_b200_conv_gemm(_p(x), _p(wm), _p(bias) if last else None, _p(out), frames, cout, m, _p(ws), ws.numel(), _stream())
-        _lib.check(rc, "repo_b200_conv_gemm")
-        t0 += n
-        first = False
+    if w_mat.shape != (n_total, cmap.K):
+        raise RuntimeError(f"conv_gemm: weight matrix {tuple(w_mat.shape)} != ({n_total}, {cmap.K})")
+    w_mat = w_mat.contiguous()
+    ws = torch.empty(L.repo_b200_conv_workspace_bytes(cmap.K, n_total), dtype=torch.uint8, device=x.device)
+    rc = L.repo_b200_conv_gemm(_p(x), _p(w_mat), _p(bias), _p(relu_mask), _p(out), frames, n_total, cmap.carray(),
+                               _p(ws), ws.numel(), _stream())
+    _lib.check(rc, "repo_b200_conv_gemm")
     return out
 
 
@@ -89,11 +83,6 @@ def im2col(x, frames, cmap: ConvMap):
     col = torch.empty(frames * cmap.RA * cmap.RB, cmap.K, device=x.device, dtype=torch.float32)
     _lib.check(_lib.lib().repo_b200_im2col(_p(x), _p(col), frames, cmap.carray(), _stream()), "repo_b200_im2col")
     return col
-
-
-def col2im(d_col, d_in, frames, cmap: ConvMap, accumulate=False):
-    _lib.check(_lib.lib().repo_b200_col2im(_p(d_col), _p(d_in), frames, int(accumulate), cmap.carray(), _stream()), "repo_b200_col2im")
-    return d_in
 
 
 # ------------------------------------------------------------------------------------------------- encoder
@@ -139,29 +128,32 @@ class _EncoderFn(torch.autograd.Function):
         ws, bs = params[0::2], params[1::2]
         F_ = acts[0].shape[0]
         grads = [None] * 8
-        # gradient w.r.t. the last activation, as NHWC rows
-        cm = maps[3]
-        gl = (g.reshape(acts[4].shape) * (acts[4] > 0)).permute(0, 2, 3, 1).reshape(F_ * cm.Ho * cm.Wo, -1).contiguous()
+        # gradient w.r.t. the last pre-activation, NHWC
+        gp = (g.reshape(acts[4].shape) * (acts[4] > 0)).permute(0, 2, 3, 1).contiguous()
         for i in range(3, -1, -1):
             cm = maps[i]
-            col = im2col(acts[i], F_, cm)
+            cout, cin, k = ws[i].shape[0], ws[i].shape[1], ws[i].shape[2]
+            gl = gp.reshape(-1, cout)
             if ctx.needs_input_grad[1 + 2 * i]:
-                k = ws[i].shape[2]
-                grads[2 * i] = (gl.t() @ col).reshape(ws[i].shape[0], k, k, ws[i].shape[1]).permute(0, 3, 1, 2).contiguous()
+                col = im2col(acts[i], F_, cm)
+                grads[2 * i] = (gl.t() @ col).reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
+                del col
             if ctx.needs_input_grad[2 + 2 * i]:
                 grads[2 * i + 1] = gl.sum(0)
-            del col
             if i == 0:
                 break
-            d_col = gl @ _conv_wmat(ws[i])
-            d_in = torch.empty_like(acts[i])
-            col2im(d_col, d_in, F_, cm)
-            del d_col
-            gl = (d_in * (acts[i] > 0)).reshape(-1, acts[i].shape[-1])
-        g_obs = None
+            # data gradient = sub-pixel conv of gp with 2x2 taps; features (py, px, ci); masked by the ReLU below
+            x = acts[i]
+            H, W = x.shape[1], x.shape[2]
+            dmap = ConvMap(RA=(H + 1) // 2, RB=(W + 1) // 2, in_nchw=0, C=cout, H=cm.Ho, W=cm.Wo, TH=2, TW=2, sy=1, sx=1,
+                           dy=-1, dx=-1, Ho=H, Wo=W, osy=2, osx=2, shuffle=1)
+            wd = ws[i].reshape(cout, cin, 2, 2, 2, 2).permute(3, 5, 1, 2, 4, 0).reshape(4 * cin, 4 * cout)
+            d_in = torch.empty_like(x)
+            conv_gemm(gp, wd, None, d_in, F_, 4 * cin, dmap, relu_mask=x)
+            gp = d_in
         if ctx.needs_input_grad[0]:
             raise NotImplementedError("gradient w.r.t. the pixel observation is not needed by any trainer")
-        return (g_obs, *grads)
+        return (None, *grads)
 
 
 class VisualEncoder(nn.Module):
@@ -189,25 +181,38 @@ class VisualEncoder(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------- decoder
-def _deconv_classes(cin, hin, win, k, out_nchw, relu):
-    """The four output-parity classes of ConvTranspose2d(k, stride 2): (py, px, ConvMap)."""
-    ho, wo = (hin - 1) * 2 + k, (win - 1) * 2 + k
-    out = []
-    for py in (0, 1):
-        for px in (0, 1):
-            th, tw = (k - py + 1) // 2, (k - px + 1) // 2
-            ra, rb = (ho - py + 1) // 2, (wo - px + 1) // 2
-            out.append((py, px, ConvMap(RA=ra, RB=rb, in_nchw=0, C=cin, H=hin, W=win, TH=th, TW=tw, sy=1, sx=1, dy=-1, dx=-1,
-                                        out_nchw=int(out_nchw), Ho=ho, Wo=wo, osy=2, osx=2, oy0=py, ox0=px, relu=int(relu))))
-    return ho, wo, out
-
-
-def _deconv_wmat(w, py, px):  # (Cin, Cout, k, k) -> class matrix (Cout, (th, tw, cin))
-    sub = w[:, :, py::2, px::2]
-    return sub.permute(1, 2, 3, 0).reshape(w.shape[1], -1).contiguous()
-
-
 _DEC = [(1024, 128, 5), (128, 64, 5), (64, 32, 6), (32, 3, 6)]
+
+
+def _deconv_map(cin, hin, win, k, out_nchw, relu):
+    """ConvTranspose2d(k, stride 2) as a stride-1 gather with T = ceil(k/2) taps and sub-pixel (shuffle) store."""
+    ho, wo, T = (hin - 1) * 2 + k, (win - 1) * 2 + k, (k + 1) // 2
+    return ConvMap(RA=(ho + 1) // 2, RB=(wo + 1) // 2, in_nchw=0, C=cin, H=hin, W=win, TH=T, TW=T, sy=1, sx=1, dy=-1, dx=-1,
+                   out_nchw=int(out_nchw), Ho=ho, Wo=wo, osy=2, osx=2, relu=int(relu), shuffle=1)
+
+
+def _deconv_wmat(w):
+    """(Cin, Cout, k, k) -> ((py, px, cout), (th, tw, cin)) with W[ci, co, py + 2 th, px + 2 tw], zero where kh >= k."""
+    cin, cout, k = w.shape[0], w.shape[1], w.shape[2]
+    T = (k + 1) // 2
+    wp = F.pad(w, (0, 2 * T - k, 0, 2 * T - k))
+    return wp.reshape(cin, cout, T, 2, T, 2).permute(3, 5, 1, 2, 4, 0).reshape(4 * cout, T * T * cin)
+
+
+def _deconv_wgrad(dwm, cin, cout, k):
+    """inverse of `_deconv_wmat` for the gradient."""
+    T = (k + 1) // 2
+    return dwm.reshape(2, 2, cout, T, T, cin).permute(5, 2, 3, 0, 4, 1).reshape(cin, cout, 2 * T, 2 * T)[:, :, :k, :k].contiguous()
+
+
+def _unshuffle(g, ra, rb, cpad):
+    """(F, Ho, Wo, C) NHWC -> (F, RA, RB, cpad >= 4C) rows of sub-pixel classes (py, px, c); zero outside the grid."""
+    F_, ho, wo, c = g.shape
+    gp = F.pad(g, (0, 0, 0, 2 * rb - wo, 0, 2 * ra - ho))
+    gp = gp.reshape(F_, ra, 2, rb, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(F_, ra, rb, 4 * c)
+    if cpad > 4 * c:
+        gp = F.pad(gp, (0, cpad - 4 * c))
+    return gp.contiguous()
 
 
 class _DecoderFn(torch.autograd.Function):
@@ -221,26 +226,24 @@ class _DecoderFn(torch.autograd.Function):
         F_ = belief.shape[0]
         xin = torch.cat([_need_cuda(belief.detach(), "belief"), _need_cuda(state.detach(), "state")], 1)
         h = ops.linear(xin, fc_w.detach().contiguous(), fc_b.detach().contiguous())      # (F, 1024), no activation
-        # layer 1: 1x1 input -> 5x5 output is a plain GEMM; features ordered (kh, kw, co) = NHWC (F,5,5,128)
+        # layer 1: 1x1 input -> k x k output is a plain GEMM; features ordered (kh, kw, co) = NHWC (F,k,k,128)
         k1, co1 = ws[0].shape[2], ws[0].shape[1]
-        w1 = ws[0].detach().permute(2, 3, 1, 0).reshape(k1 * k1 * co1, -1).contiguous()
-        b1 = bs[0].detach().repeat(k1 * k1).contiguous()
+        w1 = ws[0].detach().permute(2, 3, 1, 0).reshape(k1 * k1 * co1, -1)
         a1 = torch.empty(F_, k1, k1, co1, device=h.device, dtype=torch.float32)
-        conv_gemm(h, w1, b1, a1, F_, k1 * k1 * co1,
+        conv_gemm(h, w1, bs[0].detach().repeat(k1 * k1), a1, F_, k1 * k1 * co1,
                   ConvMap(RA=1, RB=1, in_nchw=0, C=h.shape[1], H=1, W=1, TH=1, TW=1, sy=1, sx=1, dy=1, dx=1, Ho=1, Wo=1, relu=1))
-        acts, layer_maps = [xin, h, a1], []
+        acts, maps = [xin, h, a1], []
         hin = k1
         for li in (1, 2, 3):
-            cin, cout, k = _DEC[li]
+            cin, cout, k = ws[li].shape[0], ws[li].shape[1], ws[li].shape[2]
             last = li == 3
-            ho, wo, classes = _deconv_classes(cin, hin, hin, k, out_nchw=last, relu=not last)
-            out = torch.empty((F_, cout, ho, wo) if last else (F_, ho, wo, cout), device=h.device, dtype=torch.float32)
-            for py, px, cm in classes:
-                conv_gemm(acts[-1], _deconv_wmat(ws[li].detach(), py, px), bs[li].detach().contiguous(), out, F_, cout, cm)
+            cm = _deconv_map(cin, hin, hin, k, out_nchw=last, relu=not last)
+            out = torch.empty((F_, cout, cm.Ho, cm.Wo) if last else (F_, cm.Ho, cm.Wo, cout), device=h.device, dtype=torch.float32)
+            conv_gemm(acts[-1], _deconv_wmat(ws[li].detach()), bs[li].detach().repeat(4), out, F_, 4 * cout, cm)
             acts.append(out)
-            layer_maps.append(classes)
-            hin = ho
-        ctx.layer_maps = layer_maps
+            maps.append(cm)
+            hin = cm.Ho
+        ctx.maps = maps
         ctx.belief_size = belief.shape[1]
         ctx.save_for_backward(*acts, *params)
         return acts[-1]
@@ -256,33 +259,33 @@ class _DecoderFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         grads = [None] * len(params)
         layer_in = [a1, a2, a3]
-        # gradient of the last layer's output (NCHW, no activation) as NHWC
-        g_nhwc = g.contiguous().float().permute(0, 2, 3, 1).contiguous()
+        gp = g.contiguous().float().permute(0, 2, 3, 1).contiguous()  # last layer has no activation; NHWC
         for li in (3, 2, 1):
-            x = layer_in[li - 1]
-            classes = ctx.layer_maps[li - 1]
+            x, cm = layer_in[li - 1], ctx.maps[li - 1]
+            cin, cout, k = ws[li].shape[0], ws[li].shape[1], ws[li].shape[2]
+            T = cm.TH
             if need[2 + 2 * li + 1]:
-                grads[2 * li + 3] = g_nhwc.sum((0, 1, 2))
-            dw = torch.zeros_like(ws[li]) if need[2 + 2 * li] else None
+                grads[2 * li + 3] = gp.sum((0, 1, 2))
+            cpad = (4 * cout + 7) // 8 * 8
+            G = _unshuffle(gp, cm.RA, cm.RB, cpad)                     # (F, RA, RB, cpad)
+            if need[2 + 2 * li]:
+                col = im2col(x, F_, cm)
+                dwm = G.reshape(-1, cpad)[:, :4 * cout].t() @ col
+                grads[2 * li + 2] = _deconv_wgrad(dwm, cin, cout, k)
+                del col
+            # data gradient: stride-1 conv over G with taps +t, masked by the ReLU that produced x
+            wm = _deconv_wmat(ws[li]).reshape(4 * cout, T, T, cin)
+            if cpad > 4 * cout:
+                wm = F.pad(wm, (0, 0, 0, 0, 0, 0, 0, cpad - 4 * cout))
+            wd = wm.permute(3, 1, 2, 0).reshape(cin, T * T * cpad)
+            dmap = ConvMap(RA=cm.H, RB=cm.W, in_nchw=0, C=cpad, H=cm.RA, W=cm.RB, TH=T, TW=T, sy=1, sx=1, dy=1, dx=1,
+                           Ho=cm.H, Wo=cm.W)
             d_in = torch.empty_like(x)
-            first = True
-            for py, px, cm in classes:
-                gc = g_nhwc[:, py::2, px::2, :].reshape(-1, g_nhwc.shape[-1])
-                if dw is not None:
-                    col = im2col(x, F_, cm)
-                    dwm = (gc.t() @ col).reshape(ws[li].shape[1], cm.TH, cm.TW, ws[li].shape[0])  # (co, th, tw, ci)
-                    dw[:, :, py::2, px::2] = dwm.permute(3, 0, 1, 2)
-                    del col
-                d_col = gc @ _deconv_wmat(ws[li], py, px)
-                col2im(d_col, d_in, F_, cm, accumulate=not first)
-                first = False
-                del d_col
-            if dw is not None:
-                grads[2 * li + 2] = dw
-            g_nhwc = d_in * (x > 0)  # ReLU of the layer that produced x
+            conv_gemm(G, wd, None, d_in, F_, cin, dmap, relu_mask=x)
+            gp = d_in
         # layer 1 (plain GEMM) and fc1
         k1, co1 = ws[0].shape[2], ws[0].shape[1]
-        g1 = g_nhwc.reshape(F_, k1 * k1 * co1)
+        g1 = gp.reshape(F_, k1 * k1 * co1)
         w1 = ws[0].permute(2, 3, 1, 0).reshape(k1 * k1 * co1, -1)
         if need[2 + 2]:
             grads[2] = (g1.t() @ h).reshape(k1, k1, co1, -1).permute(3, 2, 0, 1).contiguous()

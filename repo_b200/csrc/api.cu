@@ -14,6 +14,7 @@
 #include "pack.cuh"
 #include "vm.cuh"
 #include "rows.cuh"
+#include "conv.cuh"
 #include "elementwise.cuh"
 #include "bwd.cuh"
 #include "optim.cuh"
@@ -755,31 +756,81 @@ int repo_b200_adam_clip_step(float* param, float* grad, float* exp_avg, float* e
 }
 
 // ---- (transposed) convolution as implicit GEMM on the vm machine
-int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, float* out, int frames, int cout,
-                        const int* map /* ConvMap as 26 ints */, void* ws, size_t ws_bytes, void* stream) {
+// ---- implicit-GEMM convolution (conv.cuh).  Workspace = packed fp16 hi/lo weights + padded bias.
+static void conv_geometry(int K, int n_total, int& k16, int& NP, int& n_tiles) {
+  k16 = cdiv(K, 16);
+  NP = n_total <= 256 ? cdiv(n_total, 16) * 16 : 256;
+  n_tiles = cdiv(n_total, NP);
+}
+
+size_t repo_b200_conv_workspace_bytes(int K, int n_total) {
+  if (K < 1 || n_total < 1) return 0;
+  int k16, NP, n_tiles;
+  conv_geometry(K, n_total, k16, NP, n_tiles);
+  return (size_t)n_tiles * k16 * NP * 64 + (size_t)n_tiles * NP * sizeof(float) + 256;
+}
+
+int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, const float* relu_mask, float* out,
+                        int frames, int n_total, const int* map /* ConvMap as 27 ints */, void* ws, size_t ws_bytes,
+                        void* stream) {
   if (!input || !w_mat || !out || !map || !ws) return fail(-1, "conv: NULL pointer");
   ConvMap cm;
-  static_assert(sizeof(ConvMap) == 26 * sizeof(int), "ConvMap layout");
+  static_assert(sizeof(ConvMap) == 27 * sizeof(int), "ConvMap layout");
   std::memcpy(&cm, map, sizeof(cm));
   cm.enabled = 1;
-  if (cm.ntaps < 1 || cm.C < 1 || cout < 1 || cout > 4096) return fail(-1, "conv: bad sizes");
+  if (cm.tap0 != 0 || cm.ntaps != cm.TH * cm.TW || cm.accumulate) return fail(-1, "conv: partial tap windows are not supported");
+  if (cm.ntaps < 1 || cm.C < 1 || n_total < 1 || n_total > 256 * kMaxRowsJobs) return fail(-1, "conv: bad sizes");
+  if (cm.shuffle && (n_total % 4)) return fail(-1, "conv: sub-pixel store needs 4*cout features");
+  if ((reinterpret_cast<uintptr_t>(input) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (relu_mask && (reinterpret_cast<uintptr_t>(relu_mask) & 15)))
+    return fail(-1, "conv: tensors must be 16-byte aligned");
   const int K = cm.ntaps * cm.C;
   const long long rows = (long long)frames * cm.RA * cm.RB;
   if (rows <= 0) return 0;
-  if (rows > 0x7fffffffLL) return fail(-1, "conv: too many rows");
-  if (K > 1900) return fail(-1, "conv: K = %d per launch exceeds the shared-memory budget (split the taps)", K);
+  if (rows > 0x7fffffffLL - 128) return fail(-1, "conv: too many rows");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  Builder bl;
-  build_linear(bl, w_mat, bias, K, 0, K, cout);
-  int rc = bl.bind_and_pack(ws, ws_bytes, true, st);
-  if (rc) return rc;
-  VmParams& P = bl.P;
-  P.n_steps = 1;
-  P.N = (int)rows;
-  P.init_x = input; P.init_x_cols = K; P.init_x_ld = K;
-  P.out = out; P.out_ld = cout;
-  P.conv = cm;
-  return launch(P, bl.max_acc_tiles, 0, st);
+  ConvParams P{};
+  conv_geometry(K, n_total, P.k16, P.NP, P.n_tiles);
+  if (ws_bytes < repo_b200_conv_workspace_bytes(K, n_total)) return fail(-2, "conv: workspace too small");
+  uint8_t* wblob = static_cast<uint8_t*>(ws);
+  float* bias_p = reinterpret_cast<float*>(wblob + (size_t)P.n_tiles * P.k16 * P.NP * 64);
+  {
+    PackRowsArgs pa{};
+    BiasRowsArgs ba{};
+    pa.wblob = wblob;
+    ba.bias = bias_p;
+    for (int nt = 0; nt < P.n_tiles; ++nt) {
+      PackRowsJob& j = pa.jobs[nt];
+      j.w = w_mat; j.ld = K; j.col0 = 0; j.ncols = K; j.kofs = 0; j.ksl = P.k16; j.n_pad = P.NP; j.nseg = 1;
+      j.seg_src[0] = nt * P.NP; j.seg_n[0] = std::min(P.NP, n_total - nt * P.NP); j.seg_dst[0] = 0;
+      j.dst_off16 = (uint32_t)((size_t)nt * P.k16 * P.NP * 4);
+      j.blk0 = nt * P.k16;
+      BiasRowsJob& b = ba.jobs[nt];
+      b.a = bias; b.b = nullptr; b.a_off = nt * P.NP; b.b_off = 0; b.n = j.seg_n[0]; b.n_pad = P.NP; b.dst_off = nt * P.NP;
+    }
+    pa.n_jobs = ba.n_jobs = P.n_tiles;
+    pack_rows_weights_kernel<<<P.n_tiles * P.k16, 256, 0, st>>>(pa);
+    pack_rows_bias_kernel<<<P.n_tiles, 256, 0, st>>>(ba);
+    CUDA_OK(cudaGetLastError());
+  }
+  P.x = input; P.wblob = wblob; P.bias = bias_p; P.relu_mask = relu_mask; P.out = out;
+  P.cm = cm;
+  P.n_rows = (int)rows; P.K = K; P.n_total = n_total;
+  P.cout = cm.shuffle ? n_total / 4 : n_total;
+  P.kc16 = P.NP <= 128 ? 4 : 2;
+  P.stage_bytes = conv_stage_bytes(P.kc16, P.NP);
+  P.n_stages = std::min(kCvMaxStages, (200 * 1024) / P.stage_bytes);
+  const size_t smem = (size_t)P.n_stages * P.stage_bytes + 256;
+  static size_t configured = 0;
+  if (smem > configured) {
+    CUDA_OK(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int items = cdiv((int)rows, 128) * P.n_tiles;
+  const int grid = std::min(items, std::max(1, sm_count()));
+  conv_rows_kernel<<<grid, kCvThreads, smem, st>>>(P);
+  CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream) {

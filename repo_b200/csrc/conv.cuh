@@ -1,0 +1,306 @@
+// Implicit-GEMM convolution for the pixel encoder / decoder (reference: algorithms/repo/models/encoder.py:21-41,
+// decoder.py:28-48), cuDNN-free.  One persistent CTA per SM walks (row tile, feature tile) work items:
+//
+//   rows   = output positions (frame, a, b)            -> M = 128 TMEM lanes
+//   K      = (tap_y, tap_x, channel) receptive field    -> gathered on the fly from the input tensor
+//   N      = output features (<= 256 per tile)          -> weights are the B operand, streamed through a ring
+//
+// Warp roles:  warp 0  weight loader  (1-D bulk copies of pre-packed fp16 hi/lo slabs)
+//              warp 1  MMA issuer     (tcgen05.mma kind::f16, three products per k16 slab: hi*hi + lo*hi + hi*lo)
+//              warps 4-7   epilogue   (TMEM -> bias / ReLU / mask -> global; thread = output position)
+//              warps 8-15  gatherers  (global fp32 -> fp16 hi/lo core matrices in the ring stage)
+// The accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of item i overlaps the
+// gather + MMAs of item i+1.
+//
+// ConvTranspose2d(k, stride 2) runs as ONE stride-1 gather over ceil(k/2)^2 taps that produces all four output
+// parity classes at once (features = (py, px, cout), weights zero where a class has no tap); the epilogue
+// "pixel-shuffles" them onto the 2x finer output grid (ConvMap.shuffle).
+#pragma once
+#include "ptx.cuh"
+#include "rows.cuh"
+#include "vm.cuh"
+
+namespace rb {
+
+constexpr int kCvThreads = 512;
+constexpr int kCvProducers = 256;
+constexpr int kCvEpi = 128;
+constexpr int kCvMaxStages = 4;
+constexpr int kCvAccCols = 256;
+
+struct ConvParams {
+  const float* x;          // input activations
+  const uint8_t* wblob;    // n_tiles x k16 slabs of NP*64 bytes: [hi: 2 k-groups x NP x 16 B][lo: same]
+  const float* bias;       // n_tiles*NP floats (padded with zeros)
+  const float* relu_mask;  // optional, indexed like `out`: out = mask > 0 ? y : 0 (backward through a ReLU)
+  float* out;
+  ConvMap cm;
+  int n_rows, K, k16;      // GEMM rows, real K, k16 slabs
+  int n_total, NP, n_tiles;  // output features, features per tile (multiple of 16, <= 256), tiles
+  int cout;                // channels per output pixel (n_total, or n_total/4 when cm.shuffle)
+  int kc16, n_stages, stage_bytes;  // ring geometry: k16 slabs per stage, stages, bytes per stage
+};
+
+__host__ __device__ inline int conv_stage_bytes(int kc16, int NP) { return kc16 * (8192 + NP * 64); }
+
+// eight consecutive k of one row -> v[8] (zeros outside the image / beyond K)
+__device__ __forceinline__ void conv_gather8(const ConvParams& P, float* v, int k0, bool valid, int fr, int ay, int bx) {
+  const ConvMap& cm = P.cm;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  if (!valid) return;
+  if (!cm.in_nchw && (cm.C & 7) == 0) {
+    const int tap = k0 / cm.C, ci = k0 - tap * cm.C;
+    if (tap >= cm.ntaps) return;
+    const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
+    const int iy = ay + ty * cm.dy, ix = bx + tx * cm.dx;
+    if (iy < 0 || iy >= cm.H || ix < 0 || ix >= cm.W) return;
+    const float4* src = reinterpret_cast<const float4*>(P.x + (((size_t)fr * cm.H + iy) * cm.W + ix) * cm.C + ci);
+    const float4 p0 = __ldg(src), p1 = __ldg(src + 1);
+    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w;
+    v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+    return;
+  }
+  int tap = k0 / cm.C, ci = k0 - tap * cm.C;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (tap < cm.ntaps) {
+      const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
+      const int iy = ay + ty * cm.dy, ix = bx + tx * cm.dx;
+      if (iy >= 0 && iy < cm.H && ix >= 0 && ix < cm.W) {
+        const size_t o = cm.in_nchw ? (((size_t)fr * cm.C + ci) * cm.H + iy) * cm.W + ix
+                                    : (((size_t)fr * cm.H + iy) * cm.W + ix) * cm.C + ci;
+        v[i] = __ldg(P.x + o);
+      }
+    }
+    if (++ci == cm.C) { ci = 0; ++tap; }
+  }
+}
+
+__global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_constant__ ConvParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)P.n_stages * P.stage_bytes);
+  // bars: [0,4) full, [4,8) empty, [8,10) acc_full, [10,12) acc_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 4);
+  const uint32_t bar_accf = smem_u32(bars + 8), bar_acce = smem_u32(bars + 10);
+  const ConvMap& cm = P.cm;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kCvMaxStages; ++i) {
+      mbar_init(bar_full + 8 * i, kCvProducers + 1);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_accf + 8 * i, 1);
+      mbar_init(bar_acce + 8 * i, kCvEpi);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int row_tiles = (P.n_rows + 127) / 128;
+  const int n_items = row_tiles * P.n_tiles;
+  const uint32_t slab_bytes = (uint32_t)P.NP * 64u;
+  const uint32_t a_half = (uint32_t)P.kc16 * 4096u;  // A hi region (lo follows), then the weight slabs
+  const int n_stages = P.n_stages;
+
+  // register budget per role (setmaxnreg inside each branch, see rows.cuh): 128*56 + 384*152 = 64K
+  if (warp == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    // ================================ weight loader ================================
+    uint32_t slot = 0, phase = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int n_tile = w % P.n_tiles;
+      const uint8_t* src = P.wblob + (size_t)n_tile * P.k16 * slab_bytes;
+      for (int c0 = 0; c0 < P.k16; c0 += P.kc16) {
+        const int nsl = min(P.kc16, P.k16 - c0);
+        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        if (elect_one()) {
+          const uint32_t bytes = (uint32_t)nsl * slab_bytes;
+          mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+          bulk_g2s(smem_u32(ring + (size_t)slot * P.stage_bytes + 2 * a_half), src + (size_t)c0 * slab_bytes, bytes,
+                   bar_full + 8 * slot);
+        }
+        __syncwarp();
+        if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    // ================================ MMA issuer ================================
+    uint32_t slot = 0, phase = 0, item = 0;
+    const uint32_t idesc = make_idesc_f16(128, P.NP);
+    const uint32_t w_lbo = (uint32_t)P.NP * 16u, w_lo = w_lbo * 2u;
+    const uint32_t ring_a = smem_u32(ring);
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
+      const uint32_t buf = item & 1u, use = item >> 1;
+      mbar_wait(bar_acce + 8 * buf, (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d = tmem_base + buf * kCvAccCols;
+      uint32_t acc = 0;
+      for (int c0 = 0; c0 < P.k16; c0 += P.kc16) {
+        const int nsl = min(P.kc16, P.k16 - c0);
+        mbar_wait(bar_full + 8 * slot, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = ring_a + slot * (uint32_t)P.stage_bytes;
+          uint32_t wa = sa + 2 * a_half;
+          for (int j = 0; j < nsl; ++j) {
+            const uint64_t a_hi = make_smem_desc(sa + (uint32_t)j * 4096u, 2048, 128);
+            const uint64_t a_lo = make_smem_desc(sa + a_half + (uint32_t)j * 4096u, 2048, 128);
+            const uint64_t b_hi = make_smem_desc(wa, w_lbo, 128);
+            const uint64_t b_lo = make_smem_desc(wa + w_lo, w_lbo, 128);
+            umma_f16(d, a_hi, b_hi, idesc, (j == 0) ? acc : 1u);
+            umma_f16(d, a_lo, b_hi, idesc, 1u);
+            umma_f16(d, a_hi, b_lo, idesc, 1u);
+            wa += slab_bytes;
+          }
+          umma_commit(bar_empty + 8 * slot);
+        }
+        __syncwarp();
+        acc = 1u;
+        if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
+      }
+      if (elect_one()) umma_commit(bar_accf + 8 * buf);
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // spare warps of warpgroup 0: the dec is warpgroup-wide
+  } else if (warp >= 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    // ================================ gatherers ================================
+    const int p = threadIdx.x - 256;
+    const int r = p & 127, half = p >> 7;
+    uint32_t slot = 0, phase = 0;
+    const int per_frame = cm.RA * cm.RB;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int row = (w / P.n_tiles) * 128 + r;
+      const bool valid = row < P.n_rows;
+      const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
+      const int ay = a * cm.sy + cm.y0, bx = b * cm.sx + cm.x0;
+      for (int c0 = 0; c0 < P.k16; c0 += P.kc16) {
+        const int ngroups = 2 * min(P.kc16, P.k16 - c0);
+        float v[4][8];
+        // issue every load of this stage first (the only latency hiding a gather thread has), then convert
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int g = half + 2 * i;
+          if (g < ngroups) conv_gather8(P, v[i], c0 * 16 + g * 8, valid, fr, ay, bx);
+        }
+        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        uint8_t* a_hi = ring + (size_t)slot * P.stage_bytes;
+        uint8_t* a_lo = a_hi + a_half;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int g = half + 2 * i;
+          if (g < ngroups) {
+            uint4 h, l;
+            split2_f16(v[i][0], v[i][1], h.x, l.x);
+            split2_f16(v[i][2], v[i][3], h.y, l.y);
+            split2_f16(v[i][4], v[i][5], h.z, l.z);
+            split2_f16(v[i][6], v[i][7], h.w, l.w);
+            const uint32_t o = (uint32_t)g * 2048u + (uint32_t)r * 16u;
+            *reinterpret_cast<uint4*>(a_hi + o) = h;
+            *reinterpret_cast<uint4*>(a_lo + o) = l;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_full + 8 * slot);
+        if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    // ================================ epilogue ================================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int per_frame = cm.RA * cm.RB;
+    const int cout = P.cout;
+    uint32_t item = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
+      const uint32_t buf = item & 1u, use = item >> 1;
+      const int n_tile = w % P.n_tiles;
+      const int row = (w / P.n_tiles) * 128 + r;
+      const bool valid = row < P.n_rows;
+      const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
+      const int oy = a * cm.osy + cm.oy0, ox = b * cm.osx + cm.ox0;
+      const int n0 = n_tile * P.NP, ncols = min(P.NP, P.n_total - n0);
+      mbar_wait(bar_accf + 8 * buf, use & 1u);
+      tc_fence_after();
+      for (int c = 0; c < ncols; c += 16) {
+        float v[16];
+        tmem_ld16(tlane + buf * kCvAccCols + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        const int nb = n0 + c, cnt = min(16, ncols - c);
+        // 16 features that are contiguous in an NHWC output: vector stores
+        if (!cm.out_nchw && cnt == 16 && (cout & 15) == 0) {
+          int py = 0, px = 0, co = nb;
+          if (cm.shuffle) {
+            const int cls = nb / cout;
+            co = nb - cls * cout; py = cls >> 1; px = cls & 1;
+          }
+          const int yy = oy + py, xx = ox + px;
+          if (yy < cm.Ho && xx < cm.Wo) {
+            const size_t o = (((size_t)fr * cm.Ho + yy) * cm.Wo + xx) * cout + co;
+            const float4* bp = reinterpret_cast<const float4*>(P.bias + nb);
+            float4* op = reinterpret_cast<float4*>(P.out + o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 bb = __ldg(bp + j);
+              float4 y = make_float4(v[4 * j] + bb.x, v[4 * j + 1] + bb.y, v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+              if (cm.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+              if (P.relu_mask) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(P.relu_mask + o) + j);
+                y.x = m.x > 0.f ? y.x : 0.f; y.y = m.y > 0.f ? y.y : 0.f;
+                y.z = m.z > 0.f ? y.z : 0.f; y.w = m.w > 0.f ? y.w : 0.f;
+              }
+              op[j] = y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i < cnt) {
+              const int n = nb + i;
+              int py = 0, px = 0, co = n;
+              if (cm.shuffle) {
+                const int cls = n / cout;
+                co = n - cls * cout; py = cls >> 1; px = cls & 1;
+              }
+              const int yy = oy + py, xx = ox + px;
+              if (yy < cm.Ho && xx < cm.Wo) {
+                const size_t o = cm.out_nchw ? (((size_t)fr * cout + co) * cm.Ho + yy) * cm.Wo + xx
+                                             : (((size_t)fr * cm.Ho + yy) * cm.Wo + xx) * cout + co;
+                float y = v[i] + __ldg(P.bias + n);
+                if (cm.relu) y = fmaxf(y, 0.f);
+                if (P.relu_mask) y = __ldg(P.relu_mask + o) > 0.f ? y : 0.f;
+                P.out[o] = y;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acce + 8 * buf);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace rb

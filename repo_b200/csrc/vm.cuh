@@ -81,6 +81,7 @@ struct ConvMap {
   int sy, sx, dy, dx, y0, x0;      // input pixel: iy = a*sy + ty*dy + y0, ix = b*sx + tx*dx + x0 (out of range -> 0)
   int out_nchw, Ho, Wo, osy, osx, oy0, ox0;  // output pixel (a*osy + oy0, b*osx + ox0) on an Ho x Wo grid
   int relu, accumulate;            // store: out = (accumulate ? out : 0) + acc + bias, then ReLU
+  int shuffle;                     // conv.cuh only: features are (py, px, cout) sub-pixel classes of a 2x finer output grid
 };
 
 struct VmParams {
