@@ -178,10 +178,9 @@ size_t repo_b200_conv_workspace_bytes(int k, int n_total);
 int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, const float* relu_mask, float* out,
                         int frames, int n_total, const int* map, void* workspace, size_t workspace_bytes, void* stream);
 
-/* backward helpers with the same map: im2col materialises the gathered rows (rows = frames*RA*RB, ntaps*C columns)
- * for the weight-gradient GEMM; col2im is the adjoint gather onto an NHWC (frames,H,W,C) input gradient. */
+/* backward helper with the same map: im2col materialises the gathered rows (rows = frames*RA*RB, ntaps*C columns)
+ * for the weight-gradient GEMM. */
 int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream);
-int repo_b200_col2im(const float* d_col, float* d_input, int frames, int accumulate, const int* map, void* stream);
 
 /* ---- optimiser tail over one flat fp32 bucket: nn.utils.clip_grad_norm_ + Adam.step as the trainers call them
  * (dreamer.py:286-289, 356-359, 370-373; repo.py:87-96), torch defaults (no weight decay, no amsgrad).

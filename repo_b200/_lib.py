@@ -41,7 +41,7 @@ EXPORTS = [
     "repo_b200_head_workspace_bytes", "repo_b200_head_fwd",
     "repo_b200_tanh_normal_entropy_fwd", "repo_b200_replay_gather",
     "repo_b200_cell_workspace_bytes", "repo_b200_cell_fwd",
-    "repo_b200_sqnorm_accumulate", "repo_b200_adam_clip_step", "repo_b200_conv_workspace_bytes", "repo_b200_conv_gemm", "repo_b200_im2col", "repo_b200_col2im",
+    "repo_b200_sqnorm_accumulate", "repo_b200_adam_clip_step", "repo_b200_conv_workspace_bytes", "repo_b200_conv_gemm", "repo_b200_im2col",
     "repo_b200_mlp_workspace_bytes", "repo_b200_mlp_fwd", "repo_b200_mlp_bwd", "repo_b200_tanh_normal_entropy_bwd",
 ]
 
@@ -117,8 +117,6 @@ def lib():
     L.repo_b200_conv_gemm.restype = ci
     L.repo_b200_im2col.argtypes = [vp, vp, ci, C.POINTER(ci), vp]
     L.repo_b200_im2col.restype = ci
-    L.repo_b200_col2im.argtypes = [vp, vp, ci, ci, C.POINTER(ci), vp]
-    L.repo_b200_col2im.restype = ci
     L.repo_b200_linear_workspace_bytes.argtypes = [ci, ci]
     L.repo_b200_linear_workspace_bytes.restype = sz
     L.repo_b200_linear_fwd.argtypes = [vp, ci, ci, ci, vp, vp, ci, vp, ci, vp, sz, ci, vp]

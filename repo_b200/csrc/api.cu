@@ -820,7 +820,9 @@ int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bia
   P.kc16 = P.NP <= 128 ? 4 : 2;
   P.stage_bytes = conv_stage_bytes(P.kc16, P.NP);
   P.n_stages = std::min(kCvMaxStages, (200 * 1024) / P.stage_bytes);
-  const size_t smem = (size_t)P.n_stages * P.stage_bytes + 256;
+  const int n_ent = conv_table_entries(cm, P.k16);
+  if (n_ent > 2048) return fail(-1, "conv: K = %d needs %d gather-table entries (max 2048)", K, n_ent);
+  const size_t smem = (size_t)P.n_stages * P.stage_bytes + 128 + (size_t)n_ent * sizeof(ConvTap);
   static size_t configured = 0;
   if (smem > configured) {
     CUDA_OK(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -842,18 +844,6 @@ int repo_b200_im2col(const float* input, float* col, int frames, const int* map,
   const long long total = rows * cm.ntaps * cm.C;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
   im2col_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(input, col, rows, cm);
-  CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int repo_b200_col2im(const float* d_col, float* d_input, int frames, int accumulate, const int* map, void* stream) {
-  if (!d_col || !d_input || !map) return fail(-1, "col2im: NULL pointer");
-  ConvMap cm;
-  std::memcpy(&cm, map, sizeof(cm));
-  const long long total = (long long)frames * cm.H * cm.W * cm.C;
-  if (total <= 0) return 0;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  col2im_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_col, d_input, frames, accumulate, cm);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

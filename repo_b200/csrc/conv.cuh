@@ -41,41 +41,21 @@ struct ConvParams {
   int kc16, n_stages, stage_bytes;  // ring geometry: k16 slabs per stage, stages, bytes per stage
 };
 
-__host__ __device__ inline int conv_stage_bytes(int kc16, int NP) { return kc16 * (8192 + NP * 64); }
+// A operand (gathered rows) inside a ring stage: k-group g (8 fp16 of every row) starts at g * kCvALbo; the 32-byte
+// pad over 128 rows x 16 B rotates the banks so the gatherers' 8-byte stores (4 groups x 2 halves x 2 rows per
+// half-warp) are conflict-free.
+constexpr uint32_t kCvALbo = 2048 + 32;
+__host__ __device__ inline int conv_stage_bytes(int kc16, int NP) { return kc16 * (4 * (int)kCvALbo + NP * 64); }
 
-// eight consecutive k of one row -> v[8] (zeros outside the image / beyond K)
-__device__ __forceinline__ void conv_gather8(const ConvParams& P, float* v, int k0, bool valid, int fr, int ay, int bx) {
-  const ConvMap& cm = P.cm;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = 0.f;
-  if (!valid) return;
-  if (!cm.in_nchw && (cm.C & 7) == 0) {
-    const int tap = k0 / cm.C, ci = k0 - tap * cm.C;
-    if (tap >= cm.ntaps) return;
-    const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
-    const int iy = ay + ty * cm.dy, ix = bx + tx * cm.dx;
-    if (iy < 0 || iy >= cm.H || ix < 0 || ix >= cm.W) return;
-    const float4* src = reinterpret_cast<const float4*>(P.x + (((size_t)fr * cm.H + iy) * cm.W + ix) * cm.C + ci);
-    const float4 p0 = __ldg(src), p1 = __ldg(src + 1);
-    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w;
-    v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-    return;
-  }
-  int tap = k0 / cm.C, ci = k0 - tap * cm.C;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (tap < cm.ntaps) {
-      const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
-      const int iy = ay + ty * cm.dy, ix = bx + tx * cm.dx;
-      if (iy >= 0 && iy < cm.H && ix >= 0 && ix < cm.W) {
-        const size_t o = cm.in_nchw ? (((size_t)fr * cm.C + ci) * cm.H + iy) * cm.W + ix
-                                    : (((size_t)fr * cm.H + iy) * cm.W + ix) * cm.C + ci;
-        v[i] = __ldg(P.x + o);
-      }
-    }
-    if (++ci == cm.C) { ci = 0; ++tap; }
-  }
-}
+// Gather table, built once per CTA: the input address of (row, k) separates into a per-row base plus a per-k
+// offset, so the index divisions happen once per k instead of once per (row, k).  NHWC inputs with C % 4 == 0 use
+// one entry per channel quad (16-byte loads), anything else one entry per k (scalar loads).
+struct ConvTap {
+  int off;         // element offset from the row base
+  short tdy, tdx;  // tap displacement in pixels (sentinel -30000 beyond K: fails the bounds test)
+};
+__host__ __device__ inline bool conv_quads(const ConvMap& cm) { return !cm.in_nchw && (cm.C & 3) == 0; }
+__host__ __device__ inline int conv_table_entries(const ConvMap& cm, int k16) { return conv_quads(cm) ? k16 * 4 : k16 * 16; }
 
 __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_constant__ ConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -83,6 +63,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)P.n_stages * P.stage_bytes);
   // bars: [0,4) full, [4,8) empty, [8,10) acc_full, [10,12) acc_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  ConvTap* table = reinterpret_cast<ConvTap*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 4);
@@ -104,6 +85,22 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
+  {
+    const bool quads = conv_quads(cm);
+    const int n_ent = conv_table_entries(cm, P.k16);
+    for (int i = threadIdx.x; i < n_ent; i += kCvThreads) {
+      const int k = quads ? 4 * i : i;
+      const int tap = k / cm.C, ci = k - tap * cm.C;
+      ConvTap e{0, -30000, -30000};
+      if (tap < cm.ntaps) {
+        const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
+        e.tdy = (short)(ty * cm.dy);
+        e.tdx = (short)(tx * cm.dx);
+        e.off = cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.C + ci;
+      }
+      table[i] = e;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -112,7 +109,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
   const int row_tiles = (P.n_rows + 127) / 128;
   const int n_items = row_tiles * P.n_tiles;
   const uint32_t slab_bytes = (uint32_t)P.NP * 64u;
-  const uint32_t a_half = (uint32_t)P.kc16 * 4096u;  // A hi region (lo follows), then the weight slabs
+  const uint32_t a_half = (uint32_t)P.kc16 * 2u * kCvALbo;  // A hi region (lo follows), then the weight slabs
   const int n_stages = P.n_stages;
 
   // register budget per role (setmaxnreg inside each branch, see rows.cuh): 128*56 + 384*152 = 64K
@@ -157,8 +154,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
           const uint32_t sa = ring_a + slot * (uint32_t)P.stage_bytes;
           uint32_t wa = sa + 2 * a_half;
           for (int j = 0; j < nsl; ++j) {
-            const uint64_t a_hi = make_smem_desc(sa + (uint32_t)j * 4096u, 2048, 128);
-            const uint64_t a_lo = make_smem_desc(sa + a_half + (uint32_t)j * 4096u, 2048, 128);
+            const uint64_t a_hi = make_smem_desc(sa + (uint32_t)j * 2u * kCvALbo, kCvALbo, 128);
+            const uint64_t a_lo = make_smem_desc(sa + a_half + (uint32_t)j * 2u * kCvALbo, kCvALbo, 128);
             const uint64_t b_hi = make_smem_desc(wa, w_lbo, 128);
             const uint64_t b_lo = make_smem_desc(wa + w_lo, w_lbo, 128);
             umma_f16(d, a_hi, b_hi, idesc, (j == 0) ? acc : 1u);
@@ -180,39 +177,76 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
   } else if (warp >= 8) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     // ================================ gatherers ================================
+    // Thread p owns channel quad q = p % 8 of rows rs + 32 j (j < 4): a warp instruction reads 4 rows x 128
+    // contiguous bytes, and each stage pass hh covers 32 k of every row.  Gather warps are instruction-issue bound
+    // (two per scheduler), so everything that does not depend on both row and k is hoisted: row bases here,
+    // k offsets in the table.
     const int p = threadIdx.x - 256;
-    const int r = p & 127, half = p >> 7;
+    const int q = p & 7, rs = p >> 3;
+    const bool quads = conv_quads(cm);
     uint32_t slot = 0, phase = 0;
     const int per_frame = cm.RA * cm.RB;
+    const uint32_t st_off = (uint32_t)(q >> 1) * kCvALbo + (uint32_t)(q & 1) * 8u + (uint32_t)rs * 16u;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      const int row = (w / P.n_tiles) * 128 + r;
-      const bool valid = row < P.n_rows;
-      const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
-      const int ay = a * cm.sy + cm.y0, bx = b * cm.sx + cm.x0;
+      const float* base[4];
+      int ay[4], bx[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = (w / P.n_tiles) * 128 + rs + 32 * j;
+        const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
+        ay[j] = row < P.n_rows ? a * cm.sy + cm.y0 : -30000;   // rows past the end fail every bounds test
+        bx[j] = b * cm.sx + cm.x0;
+        const long long e = cm.in_nchw ? ((long long)fr * cm.C * cm.H + ay[j]) * cm.W + bx[j]
+                                       : (((long long)fr * cm.H + ay[j]) * cm.W + bx[j]) * cm.C;
+        base[j] = P.x + (row < P.n_rows ? e : 0);
+      }
       for (int c0 = 0; c0 < P.k16; c0 += P.kc16) {
-        const int ngroups = 2 * min(P.kc16, P.k16 - c0);
-        float v[4][8];
+        const int kchunk = 16 * min(P.kc16, P.k16 - c0);  // k covered by this stage
+        float4 v[2][4];
         // issue every load of this stage first (the only latency hiding a gather thread has), then convert
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int g = half + 2 * i;
-          if (g < ngroups) conv_gather8(P, v[i], c0 * 16 + g * 8, valid, fr, ay, bx);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int kl = hh * 32 + q * 4;
+          if (kl < kchunk) {
+            if (quads) {
+              const ConvTap e = table[(c0 * 16 + kl) >> 2];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const bool ok = (unsigned)(ay[j] + e.tdy) < (unsigned)cm.H && (unsigned)(bx[j] + e.tdx) < (unsigned)cm.W;
+                v[hh][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) v[hh][j] = __ldg(reinterpret_cast<const float4*>(base[j] + e.off));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float el[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const ConvTap e = table[c0 * 16 + kl + i];
+                  const bool ok = (unsigned)(ay[j] + e.tdy) < (unsigned)cm.H && (unsigned)(bx[j] + e.tdx) < (unsigned)cm.W;
+                  el[i] = 0.f;
+                  if (ok) el[i] = __ldg(base[j] + e.off);
+                }
+                v[hh][j] = make_float4(el[0], el[1], el[2], el[3]);
+              }
+            }
+          }
         }
         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-        uint8_t* a_hi = ring + (size_t)slot * P.stage_bytes;
+        uint8_t* a_hi = ring + (size_t)slot * P.stage_bytes + st_off;
         uint8_t* a_lo = a_hi + a_half;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int g = half + 2 * i;
-          if (g < ngroups) {
-            uint4 h, l;
-            split2_f16(v[i][0], v[i][1], h.x, l.x);
-            split2_f16(v[i][2], v[i][3], h.y, l.y);
-            split2_f16(v[i][4], v[i][5], h.z, l.z);
-            split2_f16(v[i][6], v[i][7], h.w, l.w);
-            const uint32_t o = (uint32_t)g * 2048u + (uint32_t)r * 16u;
-            *reinterpret_cast<uint4*>(a_hi + o) = h;
-            *reinterpret_cast<uint4*>(a_lo + o) = l;
+        for (int hh = 0; hh < 2; ++hh) {
+          if (hh * 32 + q * 4 < kchunk) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint2 h, l;
+              split2_f16(v[hh][j].x, v[hh][j].y, h.x, l.x);
+              split2_f16(v[hh][j].z, v[hh][j].w, h.y, l.y);
+              const uint32_t o = (uint32_t)hh * 4u * kCvALbo + (uint32_t)j * 512u;
+              *reinterpret_cast<uint2*>(a_hi + o) = h;
+              *reinterpret_cast<uint2*>(a_lo + o) = l;
+            }
           }
         }
         fence_proxy_async_smem();

@@ -90,9 +90,8 @@ __global__ void __launch_bounds__(128) replay_gather_kernel(const uint8_t* __res
 
 namespace rb {
 
-// Backward helpers of the implicit-GEMM convolutions (same ConvMap as the forward gather in vm.cuh).
-// im2col materialises the gathered rows (needed once per layer for the weight-gradient GEMM dW = g^T col);
-// col2im is its adjoint as a GATHER (no atomics): every input element sums the d_col entries that read it.
+// Backward helper of the implicit-GEMM convolutions (same ConvMap as the forward gather in conv.cuh):
+// im2col materialises the gathered rows, needed once per layer for the weight-gradient GEMM dW = g^T col.
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ in, float* __restrict__ col, long long rows,
                                                      const __grid_constant__ ConvMap cm) {
   const int K = cm.ntaps * cm.C;
@@ -109,32 +108,6 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ i
     if (iy >= 0 && iy < cm.H && ix >= 0 && ix < cm.W)
       v = cm.in_nchw ? in[(((size_t)fr * cm.C + ci) * cm.H + iy) * cm.W + ix] : in[(((size_t)fr * cm.H + iy) * cm.W + ix) * cm.C + ci];
     col[idx] = v;
-  }
-}
-
-// d_in[f, iy, ix, ci] (NHWC) (+)= sum over (a, b, tap) with (a*sy + ty*dy + y0, b*sx + tx*dx + x0) == (iy, ix) of
-// d_col[(f, a, b), (tap, ci)]
-__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d_col, float* __restrict__ d_in, int frames,
-                                                     int accumulate, const __grid_constant__ ConvMap cm) {
-  const int K = cm.ntaps * cm.C;
-  const long long total = (long long)frames * cm.H * cm.W * cm.C;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int ci = (int)(idx % cm.C);
-    long long p = idx / cm.C;
-    const int ix = (int)(p % cm.W);
-    p /= cm.W;
-    const int iy = (int)(p % cm.H), fr = (int)(p / cm.H);
-    float acc = accumulate ? d_in[idx] : 0.f;
-    for (int tl = 0; tl < cm.ntaps; ++tl) {
-      const int tap = cm.tap0 + tl, ty = tap / cm.TW, tx = tap - ty * cm.TW;
-      const int ny = iy - cm.y0 - ty * cm.dy, nx = ix - cm.x0 - tx * cm.dx;
-      if (ny % cm.sy != 0 || nx % cm.sx != 0) continue;
-      const int a = ny / cm.sy, b = nx / cm.sx;
-      if (ny < 0 || nx < 0 || a >= cm.RA || b >= cm.RB) continue;
-      acc += d_col[(((size_t)fr * cm.RA + a) * cm.RB + b) * K + tl * cm.C + ci];
-    }
-    d_in[idx] = acc;
   }
 }
 

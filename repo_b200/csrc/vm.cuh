@@ -69,10 +69,10 @@ struct VmStage {
   uint16_t pad2;
 };
 
-// Implicit-GEMM view of a (transposed) convolution for the linear program: row n of X is one output position,
-// its columns are the receptive field gathered straight from the input tensor (no materialised im2col), and
-// the store epilogue scatters features back onto the output grid.  Stride-2 Conv2d: sy=sx=2, dy=dx=+1.
-// ConvTranspose2d is run as 4 parity classes of the output grid, each a stride-1 gather with dy=dx=-1.
+// Implicit-GEMM view of a (transposed) convolution (conv.cuh): GEMM row n is one output position, its columns are
+// the receptive field gathered straight from the input tensor (no materialised im2col), and the store epilogue
+// scatters features back onto the output grid.  Stride-2 Conv2d: sy=sx=2, dy=dx=+1.  Stride-2 ConvTranspose2d:
+// stride-1 gather with dy=dx=-1 whose features are the four sub-pixel classes (shuffle = 1).
 struct ConvMap {
   int enabled;
   int RA, RB;                      // per-frame row grid: n -> (frame, a, b), n = (frame*RA + a)*RB + b
@@ -116,7 +116,6 @@ struct VmParams {
   float* returns;            // (T-1, N) or null
   float* out; int out_ld;    // EPI_STORE
   int dbg_flags;             // bring-up only: bit0 swaps LBO/SBO in the smem descriptors
-  ConvMap conv;              // linear program only: implicit-GEMM gather / scatter (enabled = 0: plain matrix)
   float* stash; int stash_ld; // backward stash: (T, N, stash_ld) activations the reverse pass needs, or null
   long long* dbg_clock;      // profiling only: CTA 0 writes [step][stage][2] clock64 stamps (epilogue begin/end)
   VmStage stages[kMaxStages];
@@ -348,26 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
       uint4* z = reinterpret_cast<uint4*>(x_hi);
       for (uint32_t i = et; i < words; i += kEpiThreads) z[i] = make_uint4(0, 0, 0, 0);
       epi_sync();
-      if (P.init_x && P.conv.enabled) {
-        // implicit GEMM: one work item = (row, tap); its C channels are contiguous in an NHWC input
-        const ConvMap& cm = P.conv;
-        for (int idx = et; idx < NT * cm.ntaps; idx += kEpiThreads) {
-          const int n = idx / cm.ntaps, tl = idx - n * cm.ntaps, row = row0 + n;
-          if (row >= N) continue;
-          const int tap = cm.tap0 + tl, ty = tap / cm.TW, tx = tap - ty * cm.TW;
-          const int fr = row / (cm.RA * cm.RB), rem = row - fr * (cm.RA * cm.RB), a = rem / cm.RB, b = rem - a * cm.RB;
-          const int iy = a * cm.sy + ty * cm.dy + cm.y0, ix = b * cm.sx + tx * cm.dx + cm.x0;
-          const bool inb = iy >= 0 && iy < cm.H && ix >= 0 && ix < cm.W;
-          if (!inb) continue;  // X was zero-filled
-          if (cm.in_nchw) {
-            const float* src = P.init_x + ((size_t)fr * cm.C * cm.H + iy) * cm.W + ix;
-            for (int ci = 0; ci < cm.C; ++ci) TL::put(x_hi, x_lo, n, tl * cm.C + ci, __ldg(src + (size_t)ci * cm.H * cm.W));
-          } else {
-            const float* src = P.init_x + (((size_t)fr * cm.H + iy) * cm.W + ix) * cm.C;
-            for (int ci = 0; ci < cm.C; ++ci) TL::put(x_hi, x_lo, n, tl * cm.C + ci, __ldg(src + ci));
-          }
-        }
-      } else if (P.init_x) {
+      if (P.init_x) {
         for (int idx = et; idx < NT * P.init_x_cols; idx += kEpiThreads) {
           const int n = idx / P.init_x_cols, k = idx - n * P.init_x_cols, row = row0 + n;
           if (row < N) TL::put(x_hi, x_lo, n, k, P.init_x[(size_t)row * P.init_x_ld + k]);
@@ -424,27 +404,11 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
                 float v[16];
                 tmem_ld16(tacc + tile * NT + c * 16, v);
                 tmem_ld_wait();
-                if (vf && !P.conv.enabled) {
+                if (vf) {
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
                     const int row = row0 + c * 16 + i;
                     if (row < N) P.out[(size_t)row * P.out_ld + f] = v[i] + bias;
-                  }
-                } else if (vf) {
-                  const ConvMap& cm = P.conv;
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    const int row = row0 + c * 16 + i;
-                    if (row < N) {
-                      const int fr = row / (cm.RA * cm.RB), rem = row - fr * (cm.RA * cm.RB), a = rem / cm.RB, b = rem - a * cm.RB;
-                      const int oy = a * cm.osy + cm.oy0, ox = b * cm.osx + cm.ox0;
-                      const size_t o = cm.out_nchw ? (((size_t)fr * st.nfeat + f) * cm.Ho + oy) * cm.Wo + ox
-                                                   : (((size_t)fr * cm.Ho + oy) * cm.Wo + ox) * st.nfeat + f;
-                      float y = v[i] + bias;
-                      if (cm.accumulate) y += P.out[o];
-                      if (cm.relu) y = fmaxf(y, 0.f);
-                      P.out[o] = y;
-                    }
                   }
                 }
               }
