@@ -172,11 +172,14 @@ int repo_b200_tanh_normal_entropy_bwd(const float* mean, const float* std_dev, c
  * ConvMap of repo_b200/csrc/vm.cuh (row grid, input layout/dims, tap window, input/output pixel maps, relu, shuffle);
  * w_mat is (n_total, ntaps*C) with columns ordered (tap, cin); with map.shuffle the n_total = 4*cout features are the
  * (py, px, cout) sub-pixel classes of a stride-2 transposed convolution.  relu_mask (nullable, laid out like out)
- * zeroes outputs where mask <= 0.  workspace >= repo_b200_conv_workspace_bytes(ntaps*C, n_total).
+ * zeroes outputs where mask <= 0.  scales (nullable) = device floats [s_x, s_w, 1/(s_x*s_w)]: input and weights are
+ * multiplied by s_x / s_w before the fp16 hi/lo split and the accumulator by the third entry (powers of two that keep
+ * small-magnitude gradients inside fp16's normal range).  workspace >= repo_b200_conv_workspace_bytes(ntaps*C, n_total).
  * Built by repo_b200/conv.py. */
 size_t repo_b200_conv_workspace_bytes(int k, int n_total);
-int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, const float* relu_mask, float* out,
-                        int frames, int n_total, const int* map, void* workspace, size_t workspace_bytes, void* stream);
+int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, const float* relu_mask,
+                        const float* scales, float* out, int frames, int n_total, const int* map, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* backward helper with the same map: im2col materialises the gathered rows (rows = frames*RA*RB, ntaps*C columns)
  * for the weight-gradient GEMM. */

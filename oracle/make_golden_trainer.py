@@ -63,9 +63,72 @@ def config():
     return c
 
 
+def train_dynamics_fixture(algo_name):
+    """`Dreamer.train_dynamics` (dreamer.py:241-303) / `RePo.train_dynamics` (repo.py:25-112) run UNMODIFIED on pixel
+    observations at a small batch (B=3, T=5); the gradients are captured just before `clip_grad_norm_` and the
+    optimiser steps are disabled."""
+    from algorithms.repo.repo import RePo
+    cfg = config()
+    # free_nats / init_beta are moved off their defaults so the KL term carries visible gradient at this tiny batch
+    cfg.update(algo=algo_name, pixel_obs=True, batch_size=3, chunk_size=5, free_nats=0.1, init_beta=0.3)
+    env = types.SimpleNamespace(observation_space=Space((3, 64, 64)), action_space=Space((6,)))
+    log = FakeLogger()
+    algo = (RePo if algo_name == "repo" else Dreamer)(cfg, env, env, log)
+    D, S, A, Hd = 200, 30, 6, 200
+    seed = 500
+    algo.transition_model.load_state_dict(O.make_transition_params(seed))
+    algo.reward_model.load_state_dict(O.make_mlp_params(seed + 2, D + S, Hd, 1, 3))
+    algo.encoder.load_state_dict(O.make_conv_params("encoder", seed + 4))
+    algo.obs_model.load_state_dict(O.make_conv_params("decoder", seed + 5))
+    algo.model_optimizer.step = lambda *a, **k: None
+    if algo_name == "repo":
+        algo.beta_optimizer.step = lambda *a, **k: None
+    T, B = cfg.chunk_size, cfg.batch_size
+    batch = O.make_train_batch(seed + 10, T, B, A)
+    eps = O.make_observe_inputs(seed + 11, T, B)
+    queue = []
+    for t in range(T - 1):
+        queue += [eps["eps_prior"][t], eps["eps_post"][t]]
+    grads = {}
+    import torch.nn as nn
+    orig_clip = nn.utils.clip_grad_norm_
+
+    def capture(params, max_norm, *a, **k):
+        params = list(params)
+        named = {}
+        for prefix, mod in (("encoder", algo.encoder), ("transition_model", algo.transition_model),
+                            ("obs_model", algo.obs_model), ("reward_model", algo.reward_model)):
+            for kname, p in mod.named_parameters():
+                named[prefix + "." + kname] = p.grad.detach().clone().numpy()
+        grads.update(named)
+        return orig_clip(params, max_norm, *a, **k)
+
+    nn.utils.clip_grad_norm_ = capture
+    try:
+        with NoiseInjector(queue):
+            beliefs, states = algo.train_dynamics(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"])
+    finally:
+        nn.utils.clip_grad_norm_ = orig_clip
+    save = {"log_" + k.split("/")[1]: np.float64(v) for k, v in log.rec.items()}
+    for k, v in grads.items():  # big tensors: every 97th element + the L2 norm (keeps the fixture small)
+        flat = v.reshape(-1)
+        save["gradnorm_" + k] = np.float64(np.sqrt((flat.astype(np.float64) ** 2).sum()))
+        save["grad_" + k] = flat[::97].copy() if flat.size > 65536 else v
+    save["beliefs"] = beliefs.numpy()
+    save["posterior_states"] = states.numpy()
+    if algo_name == "repo":
+        save["grad_log_beta"] = algo.log_beta.grad.numpy()
+    save.update(meta_seed=seed, meta_T=T, meta_B=B, meta_free_nats=cfg.free_nats, meta_init_beta=cfg.init_beta)
+    np.savez_compressed(os.path.join(OUT, f"train_dynamics_{algo_name}.npz"), **save)
+    print(algo_name, {k: float(v) for k, v in log.rec.items()})
+    print("  model grad norm", float(np.sqrt(sum((g.astype(np.float64) ** 2).sum() for g in grads.values()))))
+
+
 def main():
     torch.set_num_threads(1)
     set_gpu_mode(False)
+    train_dynamics_fixture("dreamer")
+    train_dynamics_fixture("repo")
     cfg = config()
     env = types.SimpleNamespace(observation_space=Space((24,)), action_space=Space((6,)))
     log = FakeLogger()

@@ -113,7 +113,7 @@ def lib():
     L.repo_b200_adam_clip_step.restype = ci
     L.repo_b200_conv_workspace_bytes.argtypes = [ci, ci]
     L.repo_b200_conv_workspace_bytes.restype = sz
-    L.repo_b200_conv_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, C.POINTER(ci), vp, sz, vp]
+    L.repo_b200_conv_gemm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, C.POINTER(ci), vp, sz, vp]
     L.repo_b200_conv_gemm.restype = ci
     L.repo_b200_im2col.argtypes = [vp, vp, ci, C.POINTER(ci), vp]
     L.repo_b200_im2col.restype = ci

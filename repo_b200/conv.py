@@ -66,14 +66,26 @@ def _need_cuda(t, name):
     return t.contiguous()
 
 
-def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=None):
-    """out = epilogue(gather(x) @ w_mat^T + bias) on the tcgen05 conv kernel (one launch + the weight packing)."""
+def _pow2_scale(t):
+    """Power of two that maps max|t| to about 2^14 (device scalar, no host sync)."""
+    amax = t.detach().abs().amax().clamp_min(1e-30)
+    return torch.exp2(torch.floor(torch.log2(16384.0 / amax)))
+
+
+def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=None, rescale=False):
+    """out = epilogue(gather(x) @ w_mat^T + bias) on the tcgen05 conv kernel (one launch + the weight packing).
+    rescale=True lifts both operands into fp16's normal range before the hi/lo split (used for gradients, whose
+    magnitudes sit far below fp16's 6e-5 normal threshold) and undoes it on the accumulator."""
     L = _lib.lib()
+    scales = None
+    if rescale:
+        sx, sw = _pow2_scale(x), _pow2_scale(w_mat)
+        scales = torch.stack([sx, sw, 1.0 / (sx * sw)]).float().contiguous()
     if w_mat.shape != (n_total, cmap.K):
         raise RuntimeError(f"conv_gemm: weight matrix {tuple(w_mat.shape)} != ({n_total}, {cmap.K})")
     w_mat = w_mat.contiguous()
     ws = torch.empty(L.repo_b200_conv_workspace_bytes(cmap.K, n_total), dtype=torch.uint8, device=x.device)
-    rc = L.repo_b200_conv_gemm(_p(x), _p(w_mat), _p(bias), _p(relu_mask), _p(out), frames, n_total, cmap.carray(),
+    rc = L.repo_b200_conv_gemm(_p(x), _p(w_mat), _p(bias), _p(relu_mask), _p(scales), _p(out), frames, n_total, cmap.carray(),
                                _p(ws), ws.numel(), _stream())
     _lib.check(rc, "repo_b200_conv_gemm")
     return out
@@ -149,7 +161,7 @@ class _EncoderFn(torch.autograd.Function):
                            dy=-1, dx=-1, Ho=H, Wo=W, osy=2, osx=2, shuffle=1)
             wd = ws[i].reshape(cout, cin, 2, 2, 2, 2).permute(3, 5, 1, 2, 4, 0).reshape(4 * cin, 4 * cout)
             d_in = torch.empty_like(x)
-            conv_gemm(gp, wd, None, d_in, F_, 4 * cin, dmap, relu_mask=x)
+            conv_gemm(gp, wd, None, d_in, F_, 4 * cin, dmap, relu_mask=x, rescale=True)
             gp = d_in
         if ctx.needs_input_grad[0]:
             raise NotImplementedError("gradient w.r.t. the pixel observation is not needed by any trainer")
@@ -281,7 +293,7 @@ class _DecoderFn(torch.autograd.Function):
             dmap = ConvMap(RA=cm.H, RB=cm.W, in_nchw=0, C=cpad, H=cm.RA, W=cm.RB, TH=T, TW=T, sy=1, sx=1, dy=1, dx=1,
                            Ho=cm.H, Wo=cm.W)
             d_in = torch.empty_like(x)
-            conv_gemm(G, wd, None, d_in, F_, cin, dmap, relu_mask=x)
+            conv_gemm(G, wd, None, d_in, F_, cin, dmap, relu_mask=x, rescale=True)
             gp = d_in
         # layer 1 (plain GEMM) and fc1
         k1, co1 = ws[0].shape[2], ws[0].shape[1]

@@ -770,9 +770,9 @@ size_t repo_b200_conv_workspace_bytes(int K, int n_total) {
   return (size_t)n_tiles * k16 * NP * 64 + (size_t)n_tiles * NP * sizeof(float) + 256;
 }
 
-int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, const float* relu_mask, float* out,
-                        int frames, int n_total, const int* map /* ConvMap as 27 ints */, void* ws, size_t ws_bytes,
-                        void* stream) {
+int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, const float* relu_mask,
+                        const float* scales, float* out, int frames, int n_total, const int* map /* ConvMap as 27 ints */,
+                        void* ws, size_t ws_bytes, void* stream) {
   if (!input || !w_mat || !out || !map || !ws) return fail(-1, "conv: NULL pointer");
   ConvMap cm;
   static_assert(sizeof(ConvMap) == 27 * sizeof(int), "ConvMap layout");
@@ -798,6 +798,7 @@ int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bia
     PackRowsArgs pa{};
     BiasRowsArgs ba{};
     pa.wblob = wblob;
+    pa.scale = scales ? scales + 1 : nullptr;
     ba.bias = bias_p;
     for (int nt = 0; nt < P.n_tiles; ++nt) {
       PackRowsJob& j = pa.jobs[nt];
@@ -813,7 +814,7 @@ int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bia
     pack_rows_bias_kernel<<<P.n_tiles, 256, 0, st>>>(ba);
     CUDA_OK(cudaGetLastError());
   }
-  P.x = input; P.wblob = wblob; P.bias = bias_p; P.relu_mask = relu_mask; P.out = out;
+  P.x = input; P.wblob = wblob; P.bias = bias_p; P.relu_mask = relu_mask; P.scales = scales; P.out = out;
   P.cm = cm;
   P.n_rows = (int)rows; P.K = K; P.n_total = n_total;
   P.cout = cm.shuffle ? n_total / 4 : n_total;

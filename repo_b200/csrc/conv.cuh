@@ -33,6 +33,9 @@ struct ConvParams {
   const uint8_t* wblob;    // n_tiles x k16 slabs of NP*64 bytes: [hi: 2 k-groups x NP x 16 B][lo: same]
   const float* bias;       // n_tiles*NP floats (padded with zeros)
   const float* relu_mask;  // optional, indexed like `out`: out = mask > 0 ? y : 0 (backward through a ReLU)
+  // optional device floats [s_x, s_w, 1/(s_x*s_w)]: powers of two that lift both operands into fp16's normal range
+  // before the hi/lo split (gradients are far below 6e-5, where fp16 has no mantissa left); undone in the epilogue
+  const float* scales;
   float* out;
   ConvMap cm;
   int n_rows, K, k16;      // GEMM rows, real K, k16 slabs
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
     uint32_t slot = 0, phase = 0;
     const int per_frame = cm.RA * cm.RB;
     const uint32_t st_off = (uint32_t)(q >> 1) * kCvALbo + (uint32_t)(q & 1) * 8u + (uint32_t)rs * 16u;
+    const float xs = P.scales ? __ldg(P.scales) : 1.f;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const float* base[4];
       int ay[4], bx[4];
@@ -241,8 +245,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint2 h, l;
-              split2_f16(v[hh][j].x, v[hh][j].y, h.x, l.x);
-              split2_f16(v[hh][j].z, v[hh][j].w, h.y, l.y);
+              split2_f16(v[hh][j].x * xs, v[hh][j].y * xs, h.x, l.x);
+              split2_f16(v[hh][j].z * xs, v[hh][j].w * xs, h.y, l.y);
               const uint32_t o = (uint32_t)hh * 4u * kCvALbo + (uint32_t)j * 512u;
               *reinterpret_cast<uint2*>(a_hi + o) = h;
               *reinterpret_cast<uint2*>(a_lo + o) = l;
@@ -262,6 +266,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int per_frame = cm.RA * cm.RB;
     const int cout = P.cout;
+    const float unscale = P.scales ? __ldg(P.scales + 2) : 1.f;
     uint32_t item = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
       const uint32_t buf = item & 1u, use = item >> 1;
@@ -294,7 +299,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 bb = __ldg(bp + j);
-              float4 y = make_float4(v[4 * j] + bb.x, v[4 * j + 1] + bb.y, v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+              float4 y = make_float4(fmaf(v[4 * j], unscale, bb.x), fmaf(v[4 * j + 1], unscale, bb.y),
+                                     fmaf(v[4 * j + 2], unscale, bb.z), fmaf(v[4 * j + 3], unscale, bb.w));
               if (cm.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
               if (P.relu_mask) {
                 const float4 m = __ldg(reinterpret_cast<const float4*>(P.relu_mask + o) + j);
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
               if (yy < cm.Ho && xx < cm.Wo) {
                 const size_t o = cm.out_nchw ? (((size_t)fr * cout + co) * cm.Ho + yy) * cm.Wo + xx
                                              : (((size_t)fr * cm.Ho + yy) * cm.Wo + xx) * cout + co;
-                float y = v[i] + __ldg(P.bias + n);
+                float y = fmaf(v[i], unscale, __ldg(P.bias + n));
                 if (cm.relu) y = fmaxf(y, 0.f);
                 if (P.relu_mask) y = __ldg(P.relu_mask + o) > 0.f ? y : 0.f;
                 P.out[o] = y;

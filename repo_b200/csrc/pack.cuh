@@ -92,6 +92,7 @@ struct PackRowsArgs {
   PackRowsJob jobs[kMaxRowsJobs];
   int n_jobs;
   uint8_t* wblob;
+  const float* scale;  // optional device scalar: weights are multiplied by it before the fp16 split (conv.cuh)
 };
 struct BiasRowsArgs {
   BiasRowsJob jobs[64];
@@ -111,6 +112,7 @@ __global__ void __launch_bounds__(256) pack_rows_weights_kernel(const __grid_con
     if (m >= j.seg_dst[s] && m < j.seg_dst[s] + j.seg_n[s]) src_row = j.seg_src[s] + (m - j.seg_dst[s]);
   uint8_t* dst = a.wblob + (size_t)j.dst_off16 * 16 + (size_t)slab * j.n_pad * 64;
   const float* src = j.w + (size_t)(src_row < 0 ? 0 : src_row) * j.ld + j.col0;
+  const float ws = a.scale ? *a.scale : 1.f;
 #pragma unroll
   for (int kg = 0; kg < 2; ++kg) {
     __align__(16) __half hi[8];
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256) pack_rows_weights_kernel(const __grid_con
 #pragma unroll
     for (int kk = 0; kk < 8; ++kk) {
       const int kc = slab * 16 + kg * 8 + kk - j.kofs;
-      const float v = (src_row >= 0 && kc >= 0 && kc < j.ncols) ? src[kc] : 0.f;
+      const float v = (src_row >= 0 && kc >= 0 && kc < j.ncols) ? src[kc] * ws : 0.f;
       split_f16(v, hi[kk], lo[kk]);
     }
     *reinterpret_cast<uint4*>(dst + kg * j.n_pad * 16 + m * 16) = *reinterpret_cast<const uint4*>(hi);

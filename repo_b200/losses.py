@@ -30,6 +30,14 @@ def repo_kl_terms(kl_tb: torch.Tensor, log_beta: torch.Tensor, prior_train_steps
             "beta_loss": -log_beta * kl_viol.detach()}
 
 
+def kl_normal(mean_p, std_p, mean_q, std_q) -> torch.Tensor:
+    """KL(N(mean_p, std_p) || N(mean_q, std_q)) elementwise, torch's `_kl_normal_normal` formula
+    (torch/distributions/kl.py; called at repo.py:63-79, dreamer.py:278-281).  Differentiable tensor ops."""
+    var_ratio = (std_p / std_q) ** 2
+    t1 = ((mean_p - mean_q) / std_q) ** 2
+    return 0.5 * (var_ratio + t1 - 1 - var_ratio.log())
+
+
 def normal_unit_nll(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """-Normal(pred, 1).log_prob(target) elementwise, constant kept (repo.py:60-61, dreamer.py:365-368)."""
     return 0.5 * (pred - target) ** 2 + 0.5 * math.log(2 * math.pi)

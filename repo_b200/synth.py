@@ -112,3 +112,13 @@ def make_frames(seed: int, n: int, hw=(64, 64)) -> torch.Tensor:
     rs = np.random.RandomState(seed)
     u8 = rs.randint(0, 256, (n, 3) + tuple(hw)).astype(np.uint8)
     return torch.from_numpy(((u8.astype(np.float32) / 255) * 2) - 1.0)
+
+
+def make_train_batch(seed: int, T: int, B: int, action: int = 6, p_done=1 / 500.0):
+    """One replay batch of SURVEY §8(d) Config 1: preprocessed frames (T,B,3,64,64), actions U(-1,1), rewards U(0,2),
+    nonterms = 1 - Bernoulli(1/500)."""
+    rs = np.random.RandomState(seed)
+    f = lambda a: torch.from_numpy(a.astype(np.float32))
+    u8 = rs.randint(0, 256, (T, B, 3, 64, 64)).astype(np.uint8)
+    return dict(obs=f((u8.astype(np.float32) / 255) * 2 - 1.0), actions=f(rs.uniform(-1, 1, (T, B, action))),
+                rewards=f(rs.uniform(0, 2, (T, B, 1))), nonterms=f(rs.uniform(0, 1, (T, B, 1)) >= p_done))

@@ -1,0 +1,190 @@
+"""The two update functions every algorithm in algorithms/repo runs, composed from this package's modules
+(reference: `Dreamer.build_models` dreamer.py:50-139, `Dreamer.train_dynamics` :241-303, `RePo.train_dynamics`
+repo.py:25-112, `Dreamer.train_actor_critic` dreamer.py:304-381).
+
+`Agent` owns the same sub-modules under the same attribute names (`encoder`, `transition_model`, `obs_model`,
+`reward_model`, `actor_model`, `value_model`, `log_beta`), groups the parameters the way the reference's three Adam
+instances do, and returns the reference's `train/*` log entries as 0-d device tensors in `self.logs` (no `.item()`
+syncs inside the update).  Noise can be injected (`eps_*`) for parity; otherwise it is drawn on the device.
+
+Scope: pixel observations (VisualEncoder / VisualObservationModel) — the configuration every headline run uses
+(`pixel_obs=True`, train_repo.py:18).  `algo` selects the KL / reconstruction wiring:
+  "dreamer": recon reads the latents (gradients reach the RSSM), KL = mean(max(kl, free_nats))
+  "repo"   : recon reads DETACHED latents, KL is the dual-variable constraint with split stop-gradients
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import losses
+from .conv import VisualEncoder, VisualObservationModel
+from .models import ActorModel, RewardModel, ValueModel, bottle
+from .optim import FlatAdam
+from .rssm import TransitionModel
+
+
+@dataclass
+class Config:
+    """experiments/train_repo.py:8-76 defaults (only the fields the two updates read)."""
+    belief_size: int = 200
+    state_size: int = 30
+    hidden_size: int = 200
+    embedding_size: int = 1024
+    dense_activation_function: str = "elu"
+    cnn_activation_function: str = "relu"
+    batch_size: int = 50
+    chunk_size: int = 50
+    horizon: int = 15
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    action_ent_coef: float = 3e-4
+    latent_ent_coef: float = 0.0
+    free_nats: float = 3.0
+    model_lr: float = 3e-4
+    actor_lr: float = 8e-5
+    value_lr: float = 8e-5
+    grad_clip_norm: float = 100.0
+    target_kl: float = 3.0
+    beta_lr: float = 1e-4
+    init_beta: float = 1e-5
+    prior_train_steps: int = 5
+
+
+class _Frozen:
+    """FreezeParameters (common/utils.py:47-58): requires_grad False inside the block, restored after."""
+
+    def __init__(self, modules):
+        self.params = [p for m in modules for p in m.parameters()]
+
+    def __enter__(self):
+        self.old = [p.requires_grad for p in self.params]
+        for p in self.params:
+            p.requires_grad = False
+
+    def __exit__(self, *exc):
+        for p, o in zip(self.params, self.old):
+            p.requires_grad = o
+
+
+class Agent:
+    def __init__(self, config: Config, action_size: int, algo: str = "repo", device="cuda"):
+        if algo not in ("repo", "dreamer"):
+            raise ValueError(f"algo {algo!r}: expected 'repo' or 'dreamer'")
+        c = self.c = config
+        self.algo = algo
+        self.device = torch.device(device)
+        dev = self.device
+        self.encoder = VisualEncoder(c.embedding_size, c.cnn_activation_function).to(dev)
+        self.transition_model = TransitionModel(c.belief_size, c.state_size, action_size, c.hidden_size, c.embedding_size,
+                                                c.dense_activation_function).to(dev)
+        self.obs_model = VisualObservationModel(c.belief_size, c.state_size, c.embedding_size, c.cnn_activation_function).to(dev)
+        self.reward_model = RewardModel(c.belief_size, c.state_size, c.hidden_size, c.dense_activation_function).to(dev)
+        self.actor_model = ActorModel(c.belief_size, c.state_size, c.hidden_size, action_size, c.dense_activation_function).to(dev)
+        self.value_model = ValueModel(c.belief_size, c.state_size, c.hidden_size, c.dense_activation_function).to(dev)
+        self.log_beta = torch.tensor(np.log(c.init_beta), dtype=torch.float32, device=dev, requires_grad=True)  # repo.py:17-23
+        self.logs: Dict[str, torch.Tensor] = {}
+        self._opt = None
+
+    # parameter groups of the reference's optimisers (dreamer.py:89-96, 106, 114; repo.py:23)
+    @property
+    def model_params(self):
+        return (list(self.encoder.parameters()) + list(self.transition_model.parameters())
+                + list(self.obs_model.parameters()) + list(self.reward_model.parameters()))
+
+    def optimizers(self):
+        """Flat-bucket clip + Adam per parameter group, created on first use (re-points the parameters)."""
+        if self._opt is None:
+            c = self.c
+            self._opt = {
+                "model": FlatAdam(self.model_params, c.model_lr, max_grad_norm=c.grad_clip_norm),
+                "actor": FlatAdam(self.actor_model.parameters(), c.actor_lr, max_grad_norm=c.grad_clip_norm),
+                "value": FlatAdam(self.value_model.parameters(), c.value_lr, max_grad_norm=c.grad_clip_norm),
+                "beta": torch.optim.Adam([self.log_beta], lr=c.beta_lr),
+            }
+        return self._opt
+
+    # ------------------------------------------------------------------ world model
+    def train_dynamics(self, obs, actions, rewards, nonterms, *, eps_prior=None, eps_post=None, step=True):
+        """obs (T,B,3,64,64) preprocessed floats, actions (T,B,A), rewards (T,B,1), nonterms (T,B,1).
+        Returns (beliefs.detach(), posterior_states.detach()) like the reference; logs in `self.logs`."""
+        c = self.c
+        B = obs.shape[1]
+        init_belief = torch.zeros(B, c.belief_size, device=self.device)
+        init_state = torch.zeros(B, c.state_size, device=self.device)
+        embeds = bottle(self.encoder, (obs,))
+        (beliefs, prior_states, prior_means, prior_std_devs, posterior_states, posterior_means,
+         posterior_std_devs) = self.transition_model.observe(init_belief, init_state, actions[:-1], embeds[1:], nonterms[:-1],
+                                                             eps_prior=eps_prior, eps_post=eps_post)
+        if self.algo == "repo":  # repo.py:46-48: reconstruction only probes the latents
+            recon = bottle(self.obs_model, (beliefs.detach(), posterior_states.detach()))
+        else:
+            recon = bottle(self.obs_model, (beliefs, posterior_states))
+        obs_loss = losses.normal_unit_nll(recon, obs[1:]).sum((2, 3, 4)).mean((0, 1))
+        reward_loss = losses.reward_loss(bottle(self.reward_model, (beliefs, posterior_states)), rewards, nonterms)
+        logs = {"train/obs_loss": obs_loss.detach(), "train/reward_loss": reward_loss.detach()}
+        if self.algo == "repo":
+            kl_prior = losses.kl_normal(posterior_means.detach(), posterior_std_devs.detach(), prior_means, prior_std_devs).sum(2).mean((0, 1))
+            kl_post = losses.kl_normal(posterior_means, posterior_std_devs, prior_means.detach(), prior_std_devs.detach()).sum(2).mean((0, 1))
+            alpha = c.prior_train_steps / (1 + c.prior_train_steps)
+            kl_div = alpha * kl_prior + (1 - alpha) * kl_post
+            kl_viol = kl_div - c.target_kl
+            kl_loss = self.log_beta.exp().detach() * kl_viol
+            beta_loss = -self.log_beta * kl_viol.detach()
+            logs.update({"train/kl_div": kl_div.detach(), "train/beta": self.log_beta.exp().detach(),
+                         "train/beta_loss": beta_loss.detach()})
+        else:
+            kl_div = losses.kl_normal(posterior_means, posterior_std_devs, prior_means, prior_std_devs).sum(2)
+            kl_loss = torch.clamp(kl_div, min=c.free_nats).mean((0, 1))
+            beta_loss = None
+        model_loss = obs_loss + reward_loss + kl_loss
+        logs.update({"train/kl_loss": kl_loss.detach(), "train/model_loss": model_loss.detach()})
+        opt = self.optimizers() if step else None
+        if step:
+            opt["model"].zero_grad()
+        model_loss.backward()
+        if step:
+            opt["model"].step()
+        if beta_loss is not None:
+            if step:
+                opt["beta"].zero_grad()
+            beta_loss.backward()
+            if step:
+                opt["beta"].step()
+        self.logs.update(logs)
+        return beliefs.detach(), posterior_states.detach()
+
+    # ------------------------------------------------------------------ actor-critic
+    def train_actor_critic(self, beliefs, states, *, eps_action=None, eps_prior=None, eps_entropy=None, step=True):
+        """dreamer.py:304-381 on flattened start rows (N, D), (N, S)."""
+        c = self.c
+        opt = self.optimizers() if step else None
+        with _Frozen([self.transition_model, self.reward_model]):
+            imag_b, imag_s, imag_m, imag_sd = self.transition_model.imagine(beliefs, states, self.actor_model, c.horizon,
+                                                                             eps_action=eps_action, eps_prior=eps_prior)
+            with _Frozen([self.value_model]):
+                reward_preds = bottle(self.reward_model, (imag_b, imag_s))
+                value_preds = bottle(self.value_model, (imag_b, imag_s))
+        action_entropy = self.actor_model.get_action_dist(imag_b.flatten(0, 1), imag_s.flatten(0, 1)).entropy(eps_entropy).mean()
+        latent_entropy = torch.distributions.Independent(torch.distributions.Normal(imag_m, imag_sd), 1).entropy().mean()
+        discounts = c.gamma * torch.ones_like(reward_preds)
+        returns = losses.lambda_return(reward_preds[:-1], value_preds[:-1], discounts[:-1], value_preds[-1], c.gae_lambda)
+        actor_loss = losses.actor_loss(returns, action_entropy, latent_entropy, c.action_ent_coef, c.latent_ent_coef)
+        if step:
+            opt["actor"].zero_grad()
+        actor_loss.backward()
+        if step:
+            opt["actor"].step()
+        value_pred = bottle(self.value_model, (imag_b[:-1].detach(), imag_s[:-1].detach()))
+        value_loss = losses.value_loss(value_pred, returns.detach())
+        if step:
+            opt["value"].zero_grad()
+        value_loss.backward()
+        if step:
+            opt["value"].step()
+        self.logs.update({"train/actor_loss": actor_loss.detach(), "train/value_loss": value_loss.detach(),
+                          "train/action_entropy": action_entropy.detach(), "train/latent_entropy": latent_entropy.detach()})
+        return returns.detach()

@@ -1,0 +1,57 @@
+"""GPU: the world-model update composed from this package (repo_b200/trainer.py: conv encoder -> observe kernel ->
+conv decoder / reward head / KL -> hand-written backward passes) against the reference's own, unmodified
+`Dreamer.train_dynamics` (dreamer.py:241-303) and `RePo.train_dynamics` (repo.py:25-112) run on CPU with the same
+weights, batch and injected noise (oracle/make_golden_trainer.py).  Tolerance rtol 1e-3 on the logged scalars and on
+every gradient relative to that tensor's largest entry; big tensors are compared on the fixture's strided subsample
+plus their L2 norm."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rssm_oracle as O
+from tests import _cases as C
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("algo", ["dreamer", "repo"])
+def test_train_dynamics_matches_reference_trainer(algo):
+    from repo_b200.trainer import Agent, Config
+    dev = torch.device("cuda:0")
+    g, meta = C.load(f"train_dynamics_{algo}")
+    seed, T, B = int(meta["seed"]), int(meta["T"]), int(meta["B"])
+    D, S, A, Hd = 200, 30, 6, 200
+    cfg = Config(batch_size=B, chunk_size=T, free_nats=float(meta["free_nats"]), init_beta=float(meta["init_beta"]))
+    agent = Agent(cfg, A, algo=algo, device=dev)
+    agent.transition_model.load_state_dict(O.make_transition_params(seed))
+    agent.reward_model.load_state_dict(O.make_mlp_params(seed + 2, D + S, Hd, 1, 3))
+    agent.encoder.load_state_dict(O.make_conv_params("encoder", seed + 4))
+    agent.obs_model.load_state_dict(O.make_conv_params("decoder", seed + 5))
+    batch = {k: v.to(dev) for k, v in O.make_train_batch(seed + 10, T, B, A).items()}
+    eps = O.make_observe_inputs(seed + 11, T, B)
+    beliefs, states = agent.train_dynamics(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"],
+                                           eps_prior=eps["eps_prior"].to(dev), eps_post=eps["eps_post"].to(dev), step=False)
+    for k, v in g.items():
+        if k.startswith("log_"):
+            np.testing.assert_allclose(agent.logs["train/" + k[4:]].item(), v, rtol=1e-3, atol=1e-5, err_msg=k)
+    np.testing.assert_allclose(beliefs.cpu().numpy(), g["beliefs"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(states.cpu().numpy(), g["posterior_states"], rtol=1e-3, atol=1e-4)
+    mods = {"encoder": agent.encoder, "transition_model": agent.transition_model, "obs_model": agent.obs_model,
+            "reward_model": agent.reward_model}
+    checked = 0
+    for prefix, mod in mods.items():
+        for name, p in mod.named_parameters():
+            key = f"{prefix}.{name}"
+            want = g["grad_" + key]
+            assert p.grad is not None, key
+            got = p.grad.detach().cpu().numpy()
+            norm = float(np.sqrt((got.astype(np.float64) ** 2).sum()))
+            np.testing.assert_allclose(norm, g["gradnorm_" + key], rtol=1e-3, err_msg="norm " + key)
+            if want.shape != got.shape:
+                got = got.reshape(-1)[::97]
+            scale = np.abs(want).max() + 1e-30
+            np.testing.assert_allclose(got / scale, want / scale, rtol=1e-3, atol=1e-3, err_msg=key)
+            checked += 1
+    assert checked == 8 + 14 + 10 + 8  # encoder, transition model, decoder, reward head
+    if algo == "repo":
+        np.testing.assert_allclose(agent.log_beta.grad.item(), g["grad_log_beta"], rtol=1e-3)
