@@ -181,6 +181,12 @@ int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bia
                         const float* scales, float* out, int frames, int n_total, const int* map, void* workspace,
                         size_t workspace_bytes, void* stream);
 
+/* weight gradient of the same implicit GEMM: dw (n_total, ntaps*C) = grad_rows^T @ gather(input), grad_rows being the
+ * (frames*RA*RB, g_ld) output-gradient rows (n_total <= 256 columns used).  Row slices are summed with fp32 atomics
+ * (dw is zeroed by the call).  scales (nullable) = [s_input, s_grad, 1/(s_input*s_grad)] as in conv_gemm. */
+int repo_b200_conv_wgrad(const float* input, const float* grad_rows, const float* scales, float* dw, int frames,
+                         int n_total, int g_ld, const int* map, void* stream);
+
 /* backward helper with the same map: im2col materialises the gathered rows (rows = frames*RA*RB, ntaps*C columns)
  * for the weight-gradient GEMM. */
 int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream);

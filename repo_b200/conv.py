@@ -15,8 +15,10 @@ layer below, in backward) and scatters onto the output grid.  Activations betwee
 * Data gradients are the adjoint maps: for Conv2d(s2) a sub-pixel (shuffle) conv of the output gradient with
   2x2 taps; for ConvTranspose2d a stride-1 conv (taps +t) over the un-shuffled output gradient.
 
-Weight gradients are GEMMs of the output gradient against the gathered rows, which are materialised for
-backward only (`im2col`, elementwise.cuh) and multiplied by cuBLAS (plain library GEMM)."""
+* Weight gradients contract over the rows: dW = G^T @ gather(x) on a second tcgen05 kernel (`conv_wgrad`) whose
+  operands are MN-major (row-contiguous) and whose row slices are summed with fp32 atomics.
+Gradient operands are rescaled by powers of two into fp16's normal range before the hi/lo split.  `im2col`
+(elementwise.cuh) only remains as a test/debug helper."""
 from __future__ import annotations
 
 import ctypes as C
@@ -91,6 +93,20 @@ def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=Non
     return out
 
 
+def conv_wgrad(x, grad_rows, frames, n_total, cmap: ConvMap):
+    """dW (n_total, K) = grad_rows^T @ gather(x) on the tcgen05 weight-gradient kernel (no materialised im2col).
+    grad_rows is (frames*RA*RB, ld >= n_total) fp32; both operands are rescaled into fp16's normal range."""
+    if grad_rows.dim() != 2 or not grad_rows.is_contiguous():
+        raise RuntimeError("conv_wgrad: grad_rows must be a contiguous 2-D tensor")
+    sx, sg = _pow2_scale(x), _pow2_scale(grad_rows)
+    scales = torch.stack([sx, sg, 1.0 / (sx * sg)]).float().contiguous()
+    dw = torch.empty(n_total, cmap.K, device=x.device, dtype=torch.float32)
+    rc = _lib.lib().repo_b200_conv_wgrad(_p(x), _p(grad_rows), _p(scales), _p(dw), frames, n_total, grad_rows.shape[1],
+                                         cmap.carray(), _stream())
+    _lib.check(rc, "repo_b200_conv_wgrad")
+    return dw
+
+
 def im2col(x, frames, cmap: ConvMap):
     col = torch.empty(frames * cmap.RA * cmap.RB, cmap.K, device=x.device, dtype=torch.float32)
     _lib.check(_lib.lib().repo_b200_im2col(_p(x), _p(col), frames, cmap.carray(), _stream()), "repo_b200_im2col")
@@ -147,9 +163,7 @@ class _EncoderFn(torch.autograd.Function):
             cout, cin, k = ws[i].shape[0], ws[i].shape[1], ws[i].shape[2]
             gl = gp.reshape(-1, cout)
             if ctx.needs_input_grad[1 + 2 * i]:
-                col = im2col(acts[i], F_, cm)
-                grads[2 * i] = (gl.t() @ col).reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
-                del col
+                grads[2 * i] = conv_wgrad(acts[i], gl, F_, cout, cm).reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
             if ctx.needs_input_grad[2 + 2 * i]:
                 grads[2 * i + 1] = gl.sum(0)
             if i == 0:
@@ -281,10 +295,8 @@ class _DecoderFn(torch.autograd.Function):
             cpad = (4 * cout + 7) // 8 * 8
             G = _unshuffle(gp, cm.RA, cm.RB, cpad)                     # (F, RA, RB, cpad)
             if need[2 + 2 * li]:
-                col = im2col(x, F_, cm)
-                dwm = G.reshape(-1, cpad)[:, :4 * cout].t() @ col
+                dwm = conv_wgrad(x, G.reshape(-1, cpad), F_, 4 * cout, cm)
                 grads[2 * li + 2] = _deconv_wgrad(dwm, cin, cout, k)
-                del col
             # data gradient: stride-1 conv over G with taps +t, masked by the ReLU that produced x
             wm = _deconv_wmat(ws[li]).reshape(4 * cout, T, T, cin)
             if cpad > 4 * cout:

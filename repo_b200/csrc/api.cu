@@ -836,6 +836,63 @@ int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bia
   return 0;
 }
 
+int repo_b200_conv_wgrad(const float* input, const float* grad_rows, const float* scales, float* dw, int frames,
+                         int n_total, int g_ld, const int* map /* ConvMap as 27 ints */, void* stream) {
+  if (!input || !grad_rows || !dw || !map) return fail(-1, "conv_wgrad: NULL pointer");
+  ConvMap cm;
+  std::memcpy(&cm, map, sizeof(cm));
+  cm.enabled = 1;
+  if (cm.tap0 != 0 || cm.ntaps != cm.TH * cm.TW) return fail(-1, "conv_wgrad: partial tap windows are not supported");
+  if (cm.ntaps < 1 || cm.C < 1 || n_total < 1 || n_total > 256 || (n_total & 3) || g_ld < n_total || (g_ld & 3))
+    return fail(-1, "conv_wgrad: n_total must be a multiple of 4 and <= 256 (got %d, row stride %d)", n_total, g_ld);
+  if ((reinterpret_cast<uintptr_t>(input) & 15) || (reinterpret_cast<uintptr_t>(grad_rows) & 15))
+    return fail(-1, "conv_wgrad: tensors must be 16-byte aligned");
+  const int K = cm.ntaps * cm.C;
+  const long long rows = (long long)frames * cm.RA * cm.RB;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)n_total * K * sizeof(float), st));
+  if (rows <= 0) return 0;
+  if (rows > 0x7fffffffLL - 128) return fail(-1, "conv_wgrad: too many rows");
+  WgradParams P{};
+  P.x = input; P.g = grad_rows; P.dw = dw; P.scales = scales; P.cm = cm;
+  P.n_rows = (int)rows; P.K = K; P.k16 = cdiv(K, 16); P.n_total = n_total; P.g_ld = g_ld;
+  P.NP = cdiv(n_total, 16) * 16;
+  const int n_ent = conv_table_entries(cm, P.k16);
+  if (n_ent > 2048) return fail(-1, "conv_wgrad: K = %d needs %d gather-table entries (max 2048)", K, n_ent);
+  // super tiles: mt k-tiles of 128 share one CTA's TMEM (mt * NP <= 512 columns) and ring stage
+  const int m_tiles = cdiv(K, 128);
+  const int mt_max = P.NP <= 128 ? 4 : 2;
+  P.n_super = cdiv(m_tiles, mt_max);
+  if (P.n_super > kWgMaxSuper) return fail(-1, "conv_wgrad: K = %d too large", K);
+  const int base = m_tiles / P.n_super, extra = m_tiles % P.n_super;
+  const int stages_total = cdiv((int)rows, kWgRows);
+  const int sms = std::max(1, sm_count());
+  int m = 0, cta = 0, mt_top = 0;
+  for (int s = 0; s < P.n_super; ++s) {
+    P.m0[s] = m;
+    P.mt[s] = base + (s < extra ? 1 : 0);
+    m += P.mt[s];
+    mt_top = std::max(mt_top, P.mt[s]);
+    P.cta0[s] = cta;
+    const int splits = std::max(1, std::min(stages_total, (sms * P.mt[s] + m_tiles / 2) / m_tiles));
+    cta += splits;
+  }
+  P.cta0[P.n_super] = cta;
+  P.kt_max = 128 * mt_top;
+  P.stage_bytes = wgrad_stage_bytes(P.kt_max, P.NP);
+  P.n_stages = std::min(kCvMaxStages, (200 * 1024) / P.stage_bytes);
+  if (P.n_stages < 1) return fail(-1, "conv_wgrad: stage does not fit shared memory");
+  const size_t smem = (size_t)P.n_stages * P.stage_bytes + 128 + (size_t)n_ent * sizeof(ConvTap);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  conv_wgrad_kernel<<<cta, kCvThreads, smem, st>>>(P);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream) {
   if (!input || !col || !map) return fail(-1, "im2col: NULL pointer");
   ConvMap cm;

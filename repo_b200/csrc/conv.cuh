@@ -343,4 +343,250 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// =================================================================================================
+// Weight gradient of the same implicit GEMM:  dW[n, k] = sum_rows G[row, n] * X[row, k]
+// (G = output gradient rows, X = the gathered receptive fields, never materialised).
+//
+// The contraction runs over ROWS, so both operands are "MN-major" for tcgen05 (the M / N index is the
+// contiguous one in memory): A = X^T with M = k (tiles of 128), B = G^T with N = n (<= 256), 16 rows per MMA.
+// smem core matrix = 8 rows x 16 bytes (8 consecutive k, or n, of one row); SBO = stride between 8-k groups
+// (padded to 160 B so the gather threads' 8-byte stores rotate over all banks), LBO = stride between 8-row
+// groups.  One CTA owns a "super tile" of mt k-tiles x all n in TMEM (mt * NP <= 512 columns) and a slice of
+// the rows; slices are summed with fp32 atomics into the zero-initialised dW.
+// =================================================================================================
+constexpr int kWgRows = 32;           // rows per ring stage (two MMA K-slabs)
+constexpr uint32_t kWgSbo = 160;
+constexpr int kWgMaxSuper = 16;
+
+struct WgradParams {
+  const float* x;        // layer input (gather source)
+  const float* g;        // output-gradient rows (n_rows, g_ld)
+  float* dw;             // (n_total, K) fp32, zero-initialised
+  const float* scales;   // optional device floats [s_x, s_g, 1/(s_x*s_g)]
+  ConvMap cm;
+  int n_rows, K, k16, n_total, g_ld, NP;
+  int n_super;                       // super tiles
+  int m0[kWgMaxSuper], mt[kWgMaxSuper];   // first 128-k tile and tile count of each super tile
+  int cta0[kWgMaxSuper + 1];         // first CTA of each super tile (prefix sums of the row splits)
+  int kt_max;                        // 128 * max(mt): k extent the stage is laid out for
+  int n_stages, stage_bytes;
+};
+
+__host__ __device__ inline int wgrad_stage_bytes(int kt, int NP) { return (int)kWgSbo * (kt + NP); }
+
+__global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_constant__ WgradParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)P.n_stages * P.stage_bytes);
+  // bars: [0,4) full, [4,8) empty, [8] acc_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  ConvTap* table = reinterpret_cast<ConvTap*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 4), bar_accf = smem_u32(bars + 8);
+  const ConvMap& cm = P.cm;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kCvMaxStages; ++i) {
+      mbar_init(bar_full + 8 * i, kCvProducers);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    mbar_init(bar_accf, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  const bool quads = conv_quads(cm);
+  {
+    const int n_ent = conv_table_entries(cm, P.k16);
+    for (int i = threadIdx.x; i < n_ent; i += kCvThreads) {
+      const int k = quads ? 4 * i : i;
+      const int tap = k / cm.C, ci = k - tap * cm.C;
+      ConvTap e{0, -30000, -30000};
+      if (tap < cm.ntaps) {
+        const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
+        e.tdy = (short)(ty * cm.dy);
+        e.tdx = (short)(tx * cm.dx);
+        e.off = cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.C + ci;
+      }
+      table[i] = e;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // which super tile / row slice is this CTA
+  int s = 0;
+  while (s + 1 < P.n_super && (int)blockIdx.x >= P.cta0[s + 1]) ++s;
+  const int splits = P.cta0[s + 1] - P.cta0[s], split = blockIdx.x - P.cta0[s];
+  const int m0 = P.m0[s], mt = P.mt[s];
+  const int stages_total = (P.n_rows + kWgRows - 1) / kWgRows;
+  const int per = (stages_total + splits - 1) / splits;
+  const int st0 = split * per, st1 = min(stages_total, st0 + per);
+  const int kt = mt * 128;                                   // k extent of this CTA
+  const uint32_t lbo_a = (uint32_t)(P.kt_max / 8) * kWgSbo, lbo_b = (uint32_t)(P.NP / 8) * kWgSbo;
+  const uint32_t a_half = 4u * lbo_a, b_half = 4u * lbo_b;   // hi region bytes (lo follows)
+  const int n_stages = P.n_stages;
+
+  if (warp == 1) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    // ================================ MMA issuer ================================
+    uint32_t slot = 0, phase = 0;
+    const uint32_t idesc = make_idesc_f16(128, P.NP) | (1u << 15) | (1u << 16);   // A and B MN-major
+    const uint32_t ring_a = smem_u32(ring);
+    uint32_t first = 1;
+    for (int st = st0; st < st1; ++st) {
+      mbar_wait(bar_full + 8 * slot, phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = ring_a + slot * (uint32_t)P.stage_bytes;
+        const uint32_t sb = sa + 2 * a_half;
+        for (int slab = 0; slab < kWgRows / 16; ++slab) {
+          const uint64_t b_hi = make_smem_desc(sb + (uint32_t)slab * 2u * lbo_b, lbo_b, kWgSbo);
+          const uint64_t b_lo = make_smem_desc(sb + b_half + (uint32_t)slab * 2u * lbo_b, lbo_b, kWgSbo);
+          for (int t = 0; t < mt; ++t) {
+            const uint32_t ao = (uint32_t)slab * 2u * lbo_a + (uint32_t)t * 16u * kWgSbo;
+            const uint64_t a_hi = make_smem_desc(sa + ao, lbo_a, kWgSbo);
+            const uint64_t a_lo = make_smem_desc(sa + a_half + ao, lbo_a, kWgSbo);
+            const uint32_t d = tmem_base + (uint32_t)(t * P.NP);
+            umma_f16(d, a_hi, b_hi, idesc, (first && slab == 0) ? 0u : 1u);
+            umma_f16(d, a_lo, b_hi, idesc, 1u);
+            umma_f16(d, a_hi, b_lo, idesc, 1u);
+          }
+        }
+        umma_commit(bar_empty + 8 * slot);
+      }
+      __syncwarp();
+      first = 0;
+      if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(bar_accf);
+    __syncwarp();
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  } else if (warp >= 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    // ================================ gatherers ================================
+    // thread p owns quad q = p % 8 of every 32-wide k (or n) block of row rs = p / 8 of the stage
+    const int p = threadIdx.x - 256;
+    const int q = p & 7, rs = p >> 3;
+    uint32_t slot = 0, phase = 0;
+    const int per_frame = cm.RA * cm.RB;
+    const float xs = P.scales ? __ldg(P.scales) : 1.f, gs = P.scales ? __ldg(P.scales + 1) : 1.f;
+    const uint32_t row_off = (uint32_t)(rs & 7) * 16u + (uint32_t)(q & 1) * 8u + (uint32_t)(q >> 1) * kWgSbo;
+    const uint32_t a_off = (uint32_t)(rs >> 3) * lbo_a + row_off, b_off = (uint32_t)(rs >> 3) * lbo_b + row_off;
+    const int kblocks = kt / 32, nblocks = P.NP / 32 + ((P.NP & 31) ? 1 : 0);
+    for (int st = st0; st < st1; ++st) {
+      const int row = st * kWgRows + rs;
+      const bool valid = row < P.n_rows;
+      const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
+      const int ay = valid ? a * cm.sy + cm.y0 : -30000, bx = b * cm.sx + cm.x0;
+      const long long e0 = cm.in_nchw ? ((long long)fr * cm.C * cm.H + ay) * cm.W + bx
+                                      : (((long long)fr * cm.H + ay) * cm.W + bx) * cm.C;
+      const float* base = P.x + (valid ? e0 : 0);
+      mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+      uint8_t* sa = ring + (size_t)slot * P.stage_bytes;
+      uint8_t* sb = sa + 2 * a_half;
+      for (int kb0 = 0; kb0 < kblocks; kb0 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int kb = kb0 + i;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kb < kblocks) {
+            const int k = m0 * 128 + kb * 32 + q * 4;
+            if (k < P.k16 * 16) {
+              if (quads) {
+                const ConvTap e = table[k >> 2];
+                const bool ok = (unsigned)(ay + e.tdy) < (unsigned)cm.H && (unsigned)(bx + e.tdx) < (unsigned)cm.W;
+                if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(base + e.off));
+              } else {
+                float el[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const ConvTap e = table[k + c];
+                  const bool ok = (unsigned)(ay + e.tdy) < (unsigned)cm.H && (unsigned)(bx + e.tdx) < (unsigned)cm.W;
+                  el[c] = 0.f;
+                  if (ok) el[c] = __ldg(base + e.off);
+                }
+                v[i] = make_float4(el[0], el[1], el[2], el[3]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int kb = kb0 + i;
+          if (kb < kblocks) {
+            uint2 h, l;
+            split2_f16(v[i].x * xs, v[i].y * xs, h.x, l.x);
+            split2_f16(v[i].z * xs, v[i].w * xs, h.y, l.y);
+            const uint32_t o = a_off + (uint32_t)kb * 4u * kWgSbo;
+            *reinterpret_cast<uint2*>(sa + o) = h;
+            *reinterpret_cast<uint2*>(sa + a_half + o) = l;
+          }
+        }
+      }
+      // output-gradient rows
+      {
+        float4 v[8];
+        const float* grow = P.g + (size_t)(valid ? row : 0) * P.g_ld;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = i * 32 + q * 4;
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < nblocks && valid && n < P.n_total) v[i] = __ldg(reinterpret_cast<const float4*>(grow + n));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = i * 32 + q * 4;
+          if (i < nblocks && n < P.NP) {
+            uint2 h, l;
+            split2_f16(v[i].x * gs, v[i].y * gs, h.x, l.x);
+            split2_f16(v[i].z * gs, v[i].w * gs, h.y, l.y);
+            const uint32_t o = b_off + (uint32_t)i * 4u * kWgSbo;
+            *reinterpret_cast<uint2*>(sb + o) = h;
+            *reinterpret_cast<uint2*>(sb + b_half + o) = l;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_full + 8 * slot);
+      if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    // ================================ epilogue ================================
+    if (st1 > st0) {
+      const int qd = warp & 3;
+      const uint32_t tlane = tmem_base + ((uint32_t)(qd * 32) << 16);
+      const float unscale = P.scales ? __ldg(P.scales + 2) : 1.f;
+      mbar_wait(bar_accf, 0);
+      tc_fence_after();
+      for (int t = 0; t < mt; ++t) {
+        const int k = (m0 + t) * 128 + qd * 32 + lane;
+        for (int c = 0; c < P.n_total; c += 16) {
+          float v[16];
+          tmem_ld16(tlane + (uint32_t)(t * P.NP + c), v);
+          tmem_ld_wait();
+          if (k < P.K) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c + i < P.n_total) atomicAdd(P.dw + (size_t)(c + i) * P.K + k, v[i] * unscale);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace rb
