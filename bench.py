@@ -303,52 +303,36 @@ def run_gpu(a):
         img_ms = timeit(lambda: ops.imagine_fwd(P, PA, PR, PV, *xa, HORIZON))
         obs_ms = timeit(lambda: ops.observe_fwd(P, *oa))
 
-        # RSSM part of one training iteration at the RePo default shapes, forward + hand-written backward:
-        #   world model : observe (BPTT over 49 steps) with the RePo KL term + a reward-like read of the latents
-        #   actor-critic: Dreamer.train_actor_critic (imagine, heads, 100-sample entropy, lambda-return, both backward passes)
-        from repo_b200 import losses
-        from repo_b200.models import bottle
-        log_beta = torch.tensor(-11.5, device=dev, requires_grad=True)
-        emb = oa[3].clone().requires_grad_(True)
+        # One full training iteration at the RePo default shapes (SURVEY §8d Metric 2 / Config 2), through the
+        # trainer-level API (repo_b200/trainer.py): conv encoder -> observe (BPTT over 49 steps) -> conv decoder /
+        # reward head / KL -> hand-written backward passes -> global-norm clip + Adam on flat buckets; then
+        # Dreamer.train_actor_critic (imagine, heads, 100-sample entropy, lambda-return, both backward passes + Adam).
+        from repo_b200.trainer import Agent, Config
+        batch = {k: v.to(dev) for k, v in O.make_train_batch(7, 50, 50, A).items()}
+        upd = {}
+        for algo in ("repo", "dreamer"):
+            agent = Agent(Config(), A, algo=algo, device=dev)
+            agent.transition_model.load_state_dict(O.make_transition_params(1))
+            agent.optimizers()
+            state = {}
 
-        def wm_update():
-            outs = model.observe(oa[0], oa[1], oa[2], emb, oa[4], eps_prior=oa[5], eps_post=oa[6])
-            kl = losses.repo_kl_terms(_kl(outs), log_beta)
-            (kl["kl_loss"] + 1e-3 * (outs[0].mean() + outs[4].mean())).backward()
-            model.zero_grad(set_to_none=True)
-            emb.grad = None
+            def wm_update():
+                state["b"], state["s"] = agent.train_dynamics(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"])
 
-        def _kl(o):
-            vr = (o[6] / o[3]) ** 2
-            return (0.5 * (vr + ((o[5] - o[2]) / o[3]) ** 2 - 1 - vr.log())).sum(2)
+            def ac_update():
+                agent.train_actor_critic(state["b"].flatten(0, 1), state["s"].flatten(0, 1))
 
-        eps_ent = torch.randn(100, 14 * 2450, A, device=dev)
-        tparams = list(model.parameters()) + list(reward.parameters())
-
-        def ac_update():
-            for p_ in tparams:
-                p_.requires_grad = False
-            ib, is_, im, isd = model.imagine(xa[0], xa[1], actor, HORIZON, eps_action=xa[2], eps_prior=xa[3])
-            for p_ in value.parameters():
-                p_.requires_grad = False
-            rp, vp = bottle(reward, (ib, is_)), bottle(value, (ib, is_))
-            for p_ in list(value.parameters()) + tparams:
-                p_.requires_grad = True
-            ent = actor.get_action_dist(ib.flatten(0, 1), is_.flatten(0, 1)).entropy(eps_ent).mean()
-            ret = losses.lambda_return(rp[:-1], vp[:-1], 0.99 * torch.ones_like(rp[:-1]), vp[-1], 0.95)
-            losses.actor_loss(ret, ent, torch.zeros((), device=dev)).backward()
-            losses.value_loss(bottle(value, (ib[:-1].detach(), is_[:-1].detach())), ret.detach()).backward()
-            actor.zero_grad(set_to_none=True)
-            value.zero_grad(set_to_none=True)
-
-        wm_ms = timeit(wm_update, 5)
-        ac_ms = timeit(ac_update, 5)
+            upd[algo + "_world_model_update_ms"] = timeit(wm_update, 5)
+            if algo == "repo":
+                upd["actor_critic_update_ms"] = timeit(ac_update, 5)
+            del agent
+        ac_ms = upd["actor_critic_update_ms"]
         default_shape = {"imagine_2450x14_ms": img_ms, "imagine_steps_per_s": 2450 * 14 / img_ms * 1e3,
                          "observe_49x50_ms": obs_ms, "observe_row_steps_per_s": 2450 / obs_ms * 1e3,
-                         "world_model_rssm_update_ms": wm_ms, "actor_critic_update_ms": ac_ms,
-                         "actor_critic_update_steps_per_s": 2450 * 14 / ac_ms * 1e3,
-                         "note": "update timings = forward + hand-written backward of the RSSM path (observe BPTT incl. KL; "
-                                 "imagine + heads + MC entropy + lambda-return); conv encoder/decoder and Adam are outside this path"}
+                         **upd, "actor_critic_update_steps_per_s": 2450 * 14 / ac_ms * 1e3,
+                         "note": "world_model_update = Agent.train_dynamics on a (50,50,3,64,64) batch: conv encoder + observe + conv "
+                                 "decoder + reward/KL losses, all backward passes, clip + Adam; actor_critic_update = "
+                                 "Agent.train_actor_critic on the 2450 resulting start rows incl. both Adam steps"}
 
     if world > 1:
         dist.barrier()

@@ -187,6 +187,11 @@ int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bia
 int repo_b200_conv_wgrad(const float* input, const float* grad_rows, const float* scales, float* dw, int frames,
                          int n_total, int g_ld, const int* map, void* stream);
 
+/* scales[which] = 2^floor(log2(target / max|x|)) and scales[2] = 1 / (scales[0] * scales[1]) in one read-only pass
+ * (the `scales` triple of conv_gemm / conv_wgrad; initialise it to {1, 1, 1}).  scratch = 8 zeroed device bytes,
+ * left zeroed again.  No host synchronisation. */
+int repo_b200_pow2_scale(const float* x, long long n, float target, int which, float* scales, void* scratch, void* stream);
+
 /* backward helper with the same map: im2col materialises the gathered rows (rows = frames*RA*RB, ntaps*C columns)
  * for the weight-gradient GEMM. */
 int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream);

@@ -68,21 +68,33 @@ def _need_cuda(t, name):
     return t.contiguous()
 
 
-def _pow2_scale(t):
-    """Power of two that maps max|t| to about 2^14 (device scalar, no host sync)."""
-    amax = t.detach().abs().amax().clamp_min(1e-30)
-    return torch.exp2(torch.floor(torch.log2(16384.0 / amax)))
+_SCRATCH = {}
 
 
-def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=None, rescale=False):
+def grad_scales(g):
+    """Device triple [1, s_g, 1/s_g] with s_g = 2^floor(log2(2^14 / max|g|)): lifts a gradient tensor into fp16's
+    normal range before the hi/lo split (gradients sit far below fp16's 6e-5 normal threshold, where the split has no
+    mantissa left).  Activations and weights are O(1e-2..1) and keep scale 1.  One fused read-only pass, no host sync."""
+    dev = g.device
+    if dev not in _SCRATCH:
+        _SCRATCH[dev] = torch.zeros(2, dtype=torch.int32, device=dev)
+    scales = torch.ones(3, dtype=torch.float32, device=dev)
+    g = g.contiguous()
+    rc = _lib.lib().repo_b200_pow2_scale(_p(g), g.numel(), 16384.0, 1, _p(scales), _p(_SCRATCH[dev]), _stream())
+    _lib.check(rc, "repo_b200_pow2_scale")
+    return scales
+
+
+def _as_input_side(scales):
+    """[1, s, 1/s] -> [s, 1, 1/s]: the same gradient scale when the gradient is the GATHERED operand (data gradients)."""
+    return scales[[1, 0, 2]]
+
+
+def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=None, scales=None):
     """out = epilogue(gather(x) @ w_mat^T + bias) on the tcgen05 conv kernel (one launch + the weight packing).
-    rescale=True lifts both operands into fp16's normal range before the hi/lo split (used for gradients, whose
-    magnitudes sit far below fp16's 6e-5 normal threshold) and undoes it on the accumulator."""
+    `scales` = device triple [s_x, s_w, 1/(s_x*s_w)] (see `grad_scales`; the gradient is the gathered operand here,
+    so callers pass the triple with the slots swapped) applied before the hi/lo split and undone on the accumulator."""
     L = _lib.lib()
-    scales = None
-    if rescale:
-        sx, sw = _pow2_scale(x), _pow2_scale(w_mat)
-        scales = torch.stack([sx, sw, 1.0 / (sx * sw)]).float().contiguous()
     if w_mat.shape != (n_total, cmap.K):
         raise RuntimeError(f"conv_gemm: weight matrix {tuple(w_mat.shape)} != ({n_total}, {cmap.K})")
     w_mat = w_mat.contiguous()
@@ -93,13 +105,13 @@ def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=Non
     return out
 
 
-def conv_wgrad(x, grad_rows, frames, n_total, cmap: ConvMap):
+def conv_wgrad(x, grad_rows, frames, n_total, cmap: ConvMap, scales=None):
     """dW (n_total, K) = grad_rows^T @ gather(x) on the tcgen05 weight-gradient kernel (no materialised im2col).
-    grad_rows is (frames*RA*RB, ld >= n_total) fp32; both operands are rescaled into fp16's normal range."""
+    grad_rows is (frames*RA*RB, ld >= n_total) fp32; `scales` = [s_x, s_g, 1/(s_x*s_g)] from `grad_scales`."""
     if grad_rows.dim() != 2 or not grad_rows.is_contiguous():
         raise RuntimeError("conv_wgrad: grad_rows must be a contiguous 2-D tensor")
-    sx, sg = _pow2_scale(x), _pow2_scale(grad_rows)
-    scales = torch.stack([sx, sg, 1.0 / (sx * sg)]).float().contiguous()
+    if scales is None:
+        scales = grad_scales(grad_rows)
     dw = torch.empty(n_total, cmap.K, device=x.device, dtype=torch.float32)
     rc = _lib.lib().repo_b200_conv_wgrad(_p(x), _p(grad_rows), _p(scales), _p(dw), frames, n_total, grad_rows.shape[1],
                                          cmap.carray(), _stream())
@@ -162,8 +174,9 @@ class _EncoderFn(torch.autograd.Function):
             cm = maps[i]
             cout, cin, k = ws[i].shape[0], ws[i].shape[1], ws[i].shape[2]
             gl = gp.reshape(-1, cout)
+            sc = grad_scales(gp)                      # [1, s_g, 1/s_g]
             if ctx.needs_input_grad[1 + 2 * i]:
-                grads[2 * i] = conv_wgrad(acts[i], gl, F_, cout, cm).reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
+                grads[2 * i] = conv_wgrad(acts[i], gl, F_, cout, cm, sc).reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
             if ctx.needs_input_grad[2 + 2 * i]:
                 grads[2 * i + 1] = gl.sum(0)
             if i == 0:
@@ -175,7 +188,7 @@ class _EncoderFn(torch.autograd.Function):
                            dy=-1, dx=-1, Ho=H, Wo=W, osy=2, osx=2, shuffle=1)
             wd = ws[i].reshape(cout, cin, 2, 2, 2, 2).permute(3, 5, 1, 2, 4, 0).reshape(4 * cin, 4 * cout)
             d_in = torch.empty_like(x)
-            conv_gemm(gp, wd, None, d_in, F_, 4 * cin, dmap, relu_mask=x, rescale=True)
+            conv_gemm(gp, wd, None, d_in, F_, 4 * cin, dmap, relu_mask=x, scales=_as_input_side(sc))
             gp = d_in
         if ctx.needs_input_grad[0]:
             raise NotImplementedError("gradient w.r.t. the pixel observation is not needed by any trainer")
@@ -294,8 +307,9 @@ class _DecoderFn(torch.autograd.Function):
                 grads[2 * li + 3] = gp.sum((0, 1, 2))
             cpad = (4 * cout + 7) // 8 * 8
             G = _unshuffle(gp, cm.RA, cm.RB, cpad)                     # (F, RA, RB, cpad)
+            sc = grad_scales(G)
             if need[2 + 2 * li]:
-                dwm = conv_wgrad(x, G.reshape(-1, cpad), F_, 4 * cout, cm)
+                dwm = conv_wgrad(x, G.reshape(-1, cpad), F_, 4 * cout, cm, sc)
                 grads[2 * li + 2] = _deconv_wgrad(dwm, cin, cout, k)
             # data gradient: stride-1 conv over G with taps +t, masked by the ReLU that produced x
             wm = _deconv_wmat(ws[li]).reshape(4 * cout, T, T, cin)
@@ -305,7 +319,7 @@ class _DecoderFn(torch.autograd.Function):
             dmap = ConvMap(RA=cm.H, RB=cm.W, in_nchw=0, C=cpad, H=cm.RA, W=cm.RB, TH=T, TW=T, sy=1, sx=1, dy=1, dx=1,
                            Ho=cm.H, Wo=cm.W)
             d_in = torch.empty_like(x)
-            conv_gemm(G, wd, None, d_in, F_, cin, dmap, relu_mask=x, rescale=True)
+            conv_gemm(G, wd, None, d_in, F_, cin, dmap, relu_mask=x, scales=_as_input_side(sc))
             gp = d_in
         # layer 1 (plain GEMM) and fc1
         k1, co1 = ws[0].shape[2], ws[0].shape[1]

@@ -893,6 +893,16 @@ int repo_b200_conv_wgrad(const float* input, const float* grad_rows, const float
   return 0;
 }
 
+int repo_b200_pow2_scale(const float* x, long long n, float target, int which, float* scales, void* scratch, void* stream) {
+  if (!x || !scales || !scratch || (which != 0 && which != 1)) return fail(-1, "pow2_scale: bad argument");
+  if (reinterpret_cast<uintptr_t>(x) & 15) return fail(-1, "pow2_scale: tensor must be 16-byte aligned");
+  if (n <= 0) return 0;
+  const int blocks = (int)std::min<long long>((n / 4 + 255) / 256 + 1, (long long)std::max(1, sm_count()) * 8);
+  absmax_scale_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n, static_cast<unsigned*>(scratch), target, scales, which);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream) {
   if (!input || !col || !map) return fail(-1, "im2col: NULL pointer");
   ConvMap cm;

@@ -111,4 +111,40 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ i
   }
 }
 
+// Power-of-two operand scales for the gradient convolutions (conv.cuh): one read-only pass finds max|x|, the
+// last block to finish turns it into s = 2^floor(log2(target / max|x|)).  scales = [s_a, s_b, 1/(s_a*s_b)];
+// `which` selects the slot this tensor fills (the other one must already hold its value, 1 by default).
+__global__ void __launch_bounds__(256) absmax_scale_kernel(const float* __restrict__ x, long long n, unsigned* scratch /* [2]: max bits, blocks done */,
+                                                           float target, float* __restrict__ scales, int which) {
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(x4 + i);
+    m = fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fmaxf(fabsf(v.y), fabsf(v.z)), fabsf(v.w)));
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+  __shared__ float wm[8];
+  __shared__ bool last;
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, wm[i]);
+    atomicMax(scratch, __float_as_uint(m));   // non-negative floats order like their bit patterns
+    __threadfence();
+    last = atomicAdd(scratch + 1, 1u) == gridDim.x - 1;
+    if (last) {
+      const float amax = fmaxf(__uint_as_float(atomicMax(scratch, 0u)), 1e-30f);
+      const float s = exp2f(floorf(log2f(target / amax)));
+      scales[which] = s;
+      scales[2] = 1.f / (s * scales[1 - which]);
+      scratch[0] = 0u;
+      scratch[1] = 0u;   // ready for the next call on this stream
+    }
+  }
+}
+
 }  // namespace rb

@@ -85,3 +85,30 @@ def test_visual_decoder_backward_matches_autograd(dev):
         rel_close(dict(dec.named_parameters())[k].grad, w.grad, "decoder grad " + k, rtol=2e-3, floor=3e-4)
     rel_close(gb.grad, b64.grad, "d belief", rtol=2e-3, floor=3e-4)
     rel_close(gs.grad, s64.grad, "d state", rtol=2e-3, floor=3e-4)
+
+
+@pytest.mark.parametrize("case", ["enc1_nchw_c3", "enc2_stride2", "enc4_k2048_n256", "dec2_k1152_n256", "dec3_k576_n128", "dec4_n12_ld16"])
+def test_conv_wgrad_matches_materialised_gemm(dev, case):
+    """tcgen05 weight-gradient kernel (MN-major operands, atomic row-slice reduction) against im2col + fp64 GEMM, with
+    gradient magnitudes (1e-6) far below fp16's normal range to exercise the power-of-two operand scaling."""
+    from repo_b200 import conv as cv
+    Fr = 5
+    enc = cv._enc_maps((64, 64))
+    shapes = {
+        "enc1_nchw_c3": ((Fr, 3, 64, 64), enc[0], 32, None),
+        "enc2_stride2": ((Fr, 31, 31, 32), enc[1], 64, None),
+        "enc4_k2048_n256": ((Fr, 6, 6, 128), enc[3], 256, None),
+        "dec2_k1152_n256": ((Fr, 5, 5, 128), cv._deconv_map(128, 5, 5, 5, False, True), 256, None),
+        "dec3_k576_n128": ((Fr, 13, 13, 64), cv._deconv_map(64, 13, 13, 6, False, True), 128, None),
+        "dec4_n12_ld16": ((Fr, 30, 30, 32), cv._deconv_map(32, 30, 30, 6, True, False), 12, 16),
+    }
+    xs, cm, n_total, ld = shapes[case]
+    rs = np.random.RandomState(11)
+    x = torch.from_numpy(rs.standard_normal(xs).astype(np.float32)).to(dev)
+    rows = Fr * cm.RA * cm.RB
+    g = torch.zeros(rows, ld or n_total, device=dev)
+    g[:, :n_total] = torch.from_numpy((rs.standard_normal((rows, n_total)) * 1e-6).astype(np.float32)).to(dev)
+    want = g[:, :n_total].double().t() @ cv.im2col(x, Fr, cm).double()
+    got = cv.conv_wgrad(x, g, Fr, n_total, cm)
+    assert got.shape == (n_total, cm.K)
+    rel_close(got, want.cpu().numpy(), case, rtol=1e-3, floor=1e-5)
