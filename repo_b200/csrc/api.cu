@@ -826,12 +826,14 @@ int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bia
   const size_t smem = (size_t)P.n_stages * P.stage_bytes + 128 + (size_t)n_ent * sizeof(ConvTap);
   static size_t configured = 0;
   if (smem > configured) {
-    CUDA_OK(cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(conv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(conv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const int items = cdiv((int)rows, 128) * P.n_tiles;
   const int grid = std::min(items, std::max(1, sm_count()));
-  conv_rows_kernel<<<grid, kCvThreads, smem, st>>>(P);
+  if (scales) conv_rows_kernel<true><<<grid, kCvThreads, smem, st>>>(P);
+  else conv_rows_kernel<false><<<grid, kCvThreads, smem, st>>>(P);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

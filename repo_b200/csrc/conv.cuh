@@ -22,8 +22,8 @@
 
 namespace rb {
 
-constexpr int kCvThreads = 512;
-constexpr int kCvProducers = 256;
+constexpr int kCvThreads = 768;    // warps 0-3 loader / MMA / spare, 4-7 epilogue, 8-23 gatherers
+constexpr int kCvProducers = 512;
 constexpr int kCvEpi = 128;
 constexpr int kCvMaxStages = 4;
 constexpr int kCvAccCols = 256;
@@ -54,12 +54,20 @@ __host__ __device__ inline int conv_stage_bytes(int kc16, int NP) { return kc16 
 // offset, so the index divisions happen once per k instead of once per (row, k).  NHWC inputs with C % 4 == 0 use
 // one entry per channel quad (16-byte loads), anything else one entry per k (scalar loads).
 struct ConvTap {
-  int off;         // element offset from the row base
+  int off;         // BYTE offset from the row base
   short tdy, tdx;  // tap displacement in pixels (sentinel -30000 beyond K: fails the bounds test)
 };
 __host__ __device__ inline bool conv_quads(const ConvMap& cm) { return !cm.in_nchw && (cm.C & 3) == 0; }
 __host__ __device__ inline int conv_table_entries(const ConvMap& cm, int k16) { return conv_quads(cm) ? k16 * 4 : k16 * 16; }
 
+// opaque 64-bit value: keeps a precomputed row pointer in registers instead of letting the compiler re-derive it
+// from the kernel parameter on every use
+__device__ __forceinline__ uint64_t opaque(uint64_t v) {
+  asm volatile("" : "+l"(v));
+  return v;
+}
+
+template <bool SCALED>
 __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_constant__ ConvParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem;
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
         const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
         e.tdy = (short)(ty * cm.dy);
         e.tdx = (short)(tx * cm.dx);
-        e.off = cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.C + ci;
+        e.off = 4 * (cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.C + ci);
       }
       table[i] = e;
     }
@@ -115,9 +123,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
   const uint32_t a_half = (uint32_t)P.kc16 * 2u * kCvALbo;  // A hi region (lo follows), then the weight slabs
   const int n_stages = P.n_stages;
 
-  // register budget per role (setmaxnreg inside each branch, see rows.cuh): 128*56 + 384*152 = 64K
+  // register budget per role (setmaxnreg inside each branch, see rows.cuh): launch pool 768*80: 128*40 + 128*88 + 512*88
   if (warp == 0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // ================================ weight loader ================================
     uint32_t slot = 0, phase = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
@@ -137,7 +145,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // ================================ MMA issuer ================================
     uint32_t slot = 0, phase = 0, item = 0;
     const uint32_t idesc = make_idesc_f16(128, P.NP);
@@ -176,37 +184,36 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
       __syncwarp();
     }
   } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // spare warps of warpgroup 0: the dec is warpgroup-wide
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // spare warps of warpgroup 0: the dec is warpgroup-wide
   } else if (warp >= 8) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // ================================ gatherers ================================
-    // Thread p owns channel quad q = p % 8 of rows rs + 32 j (j < 4): a warp instruction reads 4 rows x 128
-    // contiguous bytes, and each stage pass hh covers 32 k of every row.  Gather warps are instruction-issue bound
-    // (two per scheduler), so everything that does not depend on both row and k is hoisted: row bases here,
-    // k offsets in the table.
+    // Thread p owns channel quad q = p % 8 of rows rs and rs + 64: a warp instruction reads 4 rows x 128
+    // contiguous bytes, and each stage pass hh covers 32 k of every row.  Gather warps are instruction-issue bound,
+    // so everything that does not depend on both row and k is hoisted: row pointers here, k offsets in the table.
     const int p = threadIdx.x - 256;
     const int q = p & 7, rs = p >> 3;
     const bool quads = conv_quads(cm);
     uint32_t slot = 0, phase = 0;
     const int per_frame = cm.RA * cm.RB;
     const uint32_t st_off = (uint32_t)(q >> 1) * kCvALbo + (uint32_t)(q & 1) * 8u + (uint32_t)rs * 16u;
-    const float xs = P.scales ? __ldg(P.scales) : 1.f;
+    const float xs = SCALED ? __ldg(P.scales) : 1.f;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      const float* base[4];
-      int ay[4], bx[4];
+      uint64_t base[2];
+      int ay[2], bx[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int row = (w / P.n_tiles) * 128 + rs + 32 * j;
+      for (int j = 0; j < 2; ++j) {
+        const int row = (w / P.n_tiles) * 128 + rs + 64 * j;
         const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
         ay[j] = row < P.n_rows ? a * cm.sy + cm.y0 : -30000;   // rows past the end fail every bounds test
         bx[j] = b * cm.sx + cm.x0;
         const long long e = cm.in_nchw ? ((long long)fr * cm.C * cm.H + ay[j]) * cm.W + bx[j]
                                        : (((long long)fr * cm.H + ay[j]) * cm.W + bx[j]) * cm.C;
-        base[j] = P.x + (row < P.n_rows ? e : 0);
+        base[j] = opaque(reinterpret_cast<uint64_t>(P.x + (row < P.n_rows ? e : 0)));
       }
       for (int c0 = 0; c0 < P.k16; c0 += P.kc16) {
         const int kchunk = 16 * min(P.kc16, P.k16 - c0);  // k covered by this stage
-        float4 v[2][4];
+        float4 v[2][2];
         // issue every load of this stage first (the only latency hiding a gather thread has), then convert
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -214,22 +221,23 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
           if (kl < kchunk) {
             if (quads) {
               const ConvTap e = table[(c0 * 16 + kl) >> 2];
+              const long long ob = e.off;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < 2; ++j) {
                 const bool ok = (unsigned)(ay[j] + e.tdy) < (unsigned)cm.H && (unsigned)(bx[j] + e.tdx) < (unsigned)cm.W;
                 v[hh][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok) v[hh][j] = __ldg(reinterpret_cast<const float4*>(base[j] + e.off));
+                if (ok) v[hh][j] = __ldg(reinterpret_cast<const float4*>(base[j] + ob));
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < 2; ++j) {
                 float el[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const ConvTap e = table[c0 * 16 + kl + i];
                   const bool ok = (unsigned)(ay[j] + e.tdy) < (unsigned)cm.H && (unsigned)(bx[j] + e.tdx) < (unsigned)cm.W;
                   el[i] = 0.f;
-                  if (ok) el[i] = __ldg(base[j] + e.off);
+                  if (ok) el[i] = __ldg(reinterpret_cast<const float*>(base[j] + (long long)e.off));
                 }
                 v[hh][j] = make_float4(el[0], el[1], el[2], el[3]);
               }
@@ -243,11 +251,13 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
         for (int hh = 0; hh < 2; ++hh) {
           if (hh * 32 + q * 4 < kchunk) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
+              float4 x4 = v[hh][j];
+              if (SCALED) { x4.x *= xs; x4.y *= xs; x4.z *= xs; x4.w *= xs; }
               uint2 h, l;
-              split2_f16(v[hh][j].x * xs, v[hh][j].y * xs, h.x, l.x);
-              split2_f16(v[hh][j].z * xs, v[hh][j].w * xs, h.y, l.y);
-              const uint32_t o = (uint32_t)hh * 4u * kCvALbo + (uint32_t)j * 512u;
+              split2_f16(x4.x, x4.y, h.x, l.x);
+              split2_f16(x4.z, x4.w, h.y, l.y);
+              const uint32_t o = (uint32_t)hh * 4u * kCvALbo + (uint32_t)j * 1024u;
               *reinterpret_cast<uint2*>(a_hi + o) = h;
               *reinterpret_cast<uint2*>(a_lo + o) = l;
             }
@@ -259,14 +269,14 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // ================================ epilogue ================================
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int per_frame = cm.RA * cm.RB;
     const int cout = P.cout;
-    const float unscale = P.scales ? __ldg(P.scales + 2) : 1.f;
+    const float unscale = SCALED ? __ldg(P.scales + 2) : 1.f;
     uint32_t item = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
       const uint32_t buf = item & 1u, use = item >> 1;
@@ -351,12 +361,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
 // The contraction runs over ROWS, so both operands are "MN-major" for tcgen05 (the M / N index is the
 // contiguous one in memory): A = X^T with M = k (tiles of 128), B = G^T with N = n (<= 256), 16 rows per MMA.
 // smem core matrix = 8 rows x 16 bytes (8 consecutive k, or n, of one row); SBO = stride between 8-k groups
-// (padded to 160 B so the gather threads' 8-byte stores rotate over all banks), LBO = stride between 8-row
+// (padded to 144 B so the gather threads' 8-byte stores rotate over all banks), LBO = stride between 8-row
 // groups.  One CTA owns a "super tile" of mt k-tiles x all n in TMEM (mt * NP <= 512 columns) and a slice of
 // the rows; slices are summed with fp32 atomics into the zero-initialised dW.
 // =================================================================================================
 constexpr int kWgRows = 32;           // rows per ring stage (two MMA K-slabs)
-constexpr uint32_t kWgSbo = 160;
+constexpr uint32_t kWgSbo = 144;
 constexpr int kWgMaxSuper = 16;
 
 struct WgradParams {
@@ -410,7 +420,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
         const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
         e.tdy = (short)(ty * cm.dy);
         e.tdx = (short)(tx * cm.dx);
-        e.off = cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.C + ci;
+        e.off = 4 * (cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.C + ci);
       }
       table[i] = e;
     }
@@ -434,7 +444,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
   const int n_stages = P.n_stages;
 
   if (warp == 1) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // ================================ MMA issuer ================================
     uint32_t slot = 0, phase = 0;
     const uint32_t idesc = make_idesc_f16(128, P.NP) | (1u << 15) | (1u << 16);   // A and B MN-major
@@ -468,19 +478,19 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
     if (elect_one()) umma_commit(bar_accf);
     __syncwarp();
   } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   } else if (warp >= 8) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // ================================ gatherers ================================
-    // thread p owns quad q = p % 8 of every 32-wide k (or n) block of row rs = p / 8 of the stage
+    // thread p owns quad q = p % 16 of every 64-wide k (or n) block of row rs = p / 16 of the stage
     const int p = threadIdx.x - 256;
-    const int q = p & 7, rs = p >> 3;
+    const int q = p & 15, rs = p >> 4;
     uint32_t slot = 0, phase = 0;
     const int per_frame = cm.RA * cm.RB;
     const float xs = P.scales ? __ldg(P.scales) : 1.f, gs = P.scales ? __ldg(P.scales + 1) : 1.f;
     const uint32_t row_off = (uint32_t)(rs & 7) * 16u + (uint32_t)(q & 1) * 8u + (uint32_t)(q >> 1) * kWgSbo;
     const uint32_t a_off = (uint32_t)(rs >> 3) * lbo_a + row_off, b_off = (uint32_t)(rs >> 3) * lbo_b + row_off;
-    const int kblocks = kt / 32, nblocks = P.NP / 32 + ((P.NP & 31) ? 1 : 0);
+    const int kblocks = kt / 64, nblocks = (P.NP + 63) / 64;
     for (int st = st0; st < st1; ++st) {
       const int row = st * kWgRows + rs;
       const bool valid = row < P.n_rows;
@@ -488,23 +498,23 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
       const int ay = valid ? a * cm.sy + cm.y0 : -30000, bx = b * cm.sx + cm.x0;
       const long long e0 = cm.in_nchw ? ((long long)fr * cm.C * cm.H + ay) * cm.W + bx
                                       : (((long long)fr * cm.H + ay) * cm.W + bx) * cm.C;
-      const float* base = P.x + (valid ? e0 : 0);
+      const uint64_t base = opaque(reinterpret_cast<uint64_t>(P.x + (valid ? e0 : 0)));
       mbar_wait(bar_empty + 8 * slot, phase ^ 1);
       uint8_t* sa = ring + (size_t)slot * P.stage_bytes;
       uint8_t* sb = sa + 2 * a_half;
-      for (int kb0 = 0; kb0 < kblocks; kb0 += 8) {
-        float4 v[8];
+      for (int kb0 = 0; kb0 < kblocks; kb0 += 4) {
+        float4 v[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const int kb = kb0 + i;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (kb < kblocks) {
-            const int k = m0 * 128 + kb * 32 + q * 4;
+            const int k = m0 * 128 + kb * 64 + q * 4;
             if (k < P.k16 * 16) {
               if (quads) {
                 const ConvTap e = table[k >> 2];
                 const bool ok = (unsigned)(ay + e.tdy) < (unsigned)cm.H && (unsigned)(bx + e.tdx) < (unsigned)cm.W;
-                if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(base + e.off));
+                if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(base + (long long)e.off));
               } else {
                 float el[4];
 #pragma unroll
@@ -512,7 +522,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
                   const ConvTap e = table[k + c];
                   const bool ok = (unsigned)(ay + e.tdy) < (unsigned)cm.H && (unsigned)(bx + e.tdx) < (unsigned)cm.W;
                   el[c] = 0.f;
-                  if (ok) el[c] = __ldg(base + e.off);
+                  if (ok) el[c] = __ldg(reinterpret_cast<const float*>(base + (long long)e.off));
                 }
                 v[i] = make_float4(el[0], el[1], el[2], el[3]);
               }
@@ -520,13 +530,13 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const int kb = kb0 + i;
           if (kb < kblocks) {
             uint2 h, l;
             split2_f16(v[i].x * xs, v[i].y * xs, h.x, l.x);
             split2_f16(v[i].z * xs, v[i].w * xs, h.y, l.y);
-            const uint32_t o = a_off + (uint32_t)kb * 4u * kWgSbo;
+            const uint32_t o = a_off + (uint32_t)kb * 8u * kWgSbo;
             *reinterpret_cast<uint2*>(sa + o) = h;
             *reinterpret_cast<uint2*>(sa + a_half + o) = l;
           }
@@ -534,22 +544,22 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
       }
       // output-gradient rows
       {
-        float4 v[8];
+        float4 v[4];
         const float* grow = P.g + (size_t)(valid ? row : 0) * P.g_ld;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = i * 32 + q * 4;
+        for (int i = 0; i < 4; ++i) {
+          const int n = i * 64 + q * 4;
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (i < nblocks && valid && n < P.n_total) v[i] = __ldg(reinterpret_cast<const float4*>(grow + n));
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = i * 32 + q * 4;
+        for (int i = 0; i < 4; ++i) {
+          const int n = i * 64 + q * 4;
           if (i < nblocks && n < P.NP) {
             uint2 h, l;
             split2_f16(v[i].x * gs, v[i].y * gs, h.x, l.x);
             split2_f16(v[i].z * gs, v[i].w * gs, h.y, l.y);
-            const uint32_t o = b_off + (uint32_t)i * 4u * kWgSbo;
+            const uint32_t o = b_off + (uint32_t)i * 8u * kWgSbo;
             *reinterpret_cast<uint2*>(sb + o) = h;
             *reinterpret_cast<uint2*>(sb + b_half + o) = l;
           }
@@ -560,7 +570,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
       if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // ================================ epilogue ================================
     if (st1 > st0) {
       const int qd = warp & 3;
