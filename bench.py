@@ -310,9 +310,11 @@ def run_gpu(a):
         from repo_b200.trainer import Agent, Config
         batch = {k: v.to(dev) for k, v in O.make_train_batch(7, 50, 50, A).items()}
         upd = {}
-        for algo in ("repo", "dreamer"):
+        for algo in ("repo", "dreamer", "tia"):
             agent = Agent(Config(), A, algo=algo, device=dev)
             agent.transition_model.load_state_dict(O.make_transition_params(1))
+            if algo == "tia":
+                agent.distractor_transition_model.load_state_dict(O.make_transition_params(2))
             agent.optimizers()
             state = {}
 

@@ -192,6 +192,15 @@ int repo_b200_conv_wgrad(const float* input, const float* grad_rows, const float
  * left zeroed again.  No host synchronisation. */
 int repo_b200_pow2_scale(const float* x, long long n, float target, int which, float* scales, void* scratch, void* stream);
 
+/* ---- TIA mask mixing (tia.py:72,124-127): t_out / d_out are the (frames,6,H,W) outputs of the task / distractor
+ * TIAObservationModel (decoder.py:154-175; channels 0-2 reconstruction, 3-5 mask features), w (6) and b (1) the 1x1
+ * mask-head convolution.  mask = sigmoid(w . [t_mask | d_mask] + b) (frames,H,W); recon = t*mask + d*(1-mask)
+ * (frames,3,H,W).  hw = H*W.  The backward writes both (frames,6,H,W) input gradients and g_wb = [d_w(6), d_b]. */
+int repo_b200_tia_mix_fwd(const float* t_out, const float* d_out, const float* w, const float* b, float* recon, float* mask,
+                          long long frames, int hw, void* stream);
+int repo_b200_tia_mix_bwd(const float* t_out, const float* d_out, const float* w, const float* mask, const float* g_recon,
+                          float* g_t_out, float* g_d_out, float* g_wb, long long frames, int hw, void* stream);
+
 /* backward helper with the same map: im2col materialises the gathered rows (rows = frames*RA*RB, ntaps*C columns)
  * for the weight-gradient GEMM. */
 int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream);

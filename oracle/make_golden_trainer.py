@@ -68,18 +68,30 @@ def train_dynamics_fixture(algo_name):
     observations at a small batch (B=3, T=5); the gradients are captured just before `clip_grad_norm_` and the
     optimiser steps are disabled."""
     from algorithms.repo.repo import RePo
+    from algorithms.repo.tia import TIA
     cfg = config()
     # free_nats / init_beta are moved off their defaults so the KL term carries visible gradient at this tiny batch
     cfg.update(algo=algo_name, pixel_obs=True, batch_size=3, chunk_size=5, free_nats=0.1, init_beta=0.3)
     env = types.SimpleNamespace(observation_space=Space((3, 64, 64)), action_space=Space((6,)))
     log = FakeLogger()
-    algo = (RePo if algo_name == "repo" else Dreamer)(cfg, env, env, log)
+    algo = {"repo": RePo, "dreamer": Dreamer, "tia": TIA}[algo_name](cfg, env, env, log)
     D, S, A, Hd = 200, 30, 6, 200
     seed = 500
     algo.transition_model.load_state_dict(O.make_transition_params(seed))
     algo.reward_model.load_state_dict(O.make_mlp_params(seed + 2, D + S, Hd, 1, 3))
     algo.encoder.load_state_dict(O.make_conv_params("encoder", seed + 4))
-    algo.obs_model.load_state_dict(O.make_conv_params("decoder", seed + 5))
+    algo.obs_model.load_state_dict(O.make_conv_params("decoder", seed + 5, out_channels=6 if algo_name == "tia" else 3))
+    groups = [("encoder", algo.encoder), ("transition_model", algo.transition_model), ("obs_model", algo.obs_model),
+              ("reward_model", algo.reward_model)]
+    if algo_name == "tia":
+        algo.distractor_transition_model.load_state_dict(O.make_transition_params(seed + 6))
+        algo.distractor_obs_model.load_state_dict(O.make_conv_params("decoder", seed + 7, out_channels=6))
+        algo.distractor_only_obs_model.load_state_dict(O.make_conv_params("decoder", seed + 8))
+        algo.distractor_reward_model.load_state_dict(O.make_mlp_params(seed + 9, D + S, Hd, 1, 3))
+        algo.mask_head.load_state_dict(O.make_mask_head_params(seed + 12))
+        groups += [("distractor_transition_model", algo.distractor_transition_model), ("distractor_obs_model", algo.distractor_obs_model),
+                   ("distractor_only_obs_model", algo.distractor_only_obs_model), ("distractor_reward_model", algo.distractor_reward_model),
+                   ("mask_head", algo.mask_head)]
     algo.model_optimizer.step = lambda *a, **k: None
     if algo_name == "repo":
         algo.beta_optimizer.step = lambda *a, **k: None
@@ -89,18 +101,21 @@ def train_dynamics_fixture(algo_name):
     queue = []
     for t in range(T - 1):
         queue += [eps["eps_prior"][t], eps["eps_post"][t]]
+    if algo_name == "tia":  # the distractor model's observe draws after the task model's (tia.py:100-121)
+        eps_d = O.make_observe_inputs(seed + 13, T, B)
+        for t in range(T - 1):
+            queue += [eps_d["eps_prior"][t], eps_d["eps_post"][t]]
     grads = {}
     import torch.nn as nn
     orig_clip = nn.utils.clip_grad_norm_
 
     def capture(params, max_norm, *a, **k):
         params = list(params)
-        named = {}
-        for prefix, mod in (("encoder", algo.encoder), ("transition_model", algo.transition_model),
-                            ("obs_model", algo.obs_model), ("reward_model", algo.reward_model)):
-            for kname, p in mod.named_parameters():
-                named[prefix + "." + kname] = p.grad.detach().clone().numpy()
-        grads.update(named)
+        if not grads:  # first call = the model loss; TIA's later calls belong to the distractor-reward phase
+            for prefix, mod in groups:
+                for kname, p in mod.named_parameters():
+                    if p.grad is not None:
+                        grads[prefix + "." + kname] = p.grad.detach().clone().numpy()
         return orig_clip(params, max_norm, *a, **k)
 
     nn.utils.clip_grad_norm_ = capture
@@ -129,6 +144,7 @@ def main():
     set_gpu_mode(False)
     train_dynamics_fixture("dreamer")
     train_dynamics_fixture("repo")
+    train_dynamics_fixture("tia")
     cfg = config()
     env = types.SimpleNamespace(observation_space=Space((24,)), action_space=Space((6,)))
     log = FakeLogger()

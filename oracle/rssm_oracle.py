@@ -46,7 +46,7 @@ Params = Dict[str, torch.Tensor]
 
 # seeded synthetic weights / inputs live in repo_b200/synth.py (pure numpy generators, no arithmetic)
 from repo_b200.synth import (DEFAULT_DIMS, make_transition_params, make_mlp_params, make_observe_inputs,  # noqa: E402,F401
-                             make_imagine_inputs, make_conv_params, make_frames, make_train_batch)
+                             make_imagine_inputs, make_conv_params, make_frames, make_train_batch, make_mask_head_params)
 
 
 def cast_params(p: Params, dtype) -> Params:

@@ -341,6 +341,41 @@ class _DecoderFn(torch.autograd.Function):
         return (gb if need[0] else None, gs if need[1] else None, *grads)
 
 
+class _TiaMixFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t_out, d_out, weight, bias):
+        t_out, d_out = _need_cuda(t_out.detach(), "t_out"), _need_cuda(d_out.detach(), "d_out")
+        F_, _, H, W = t_out.shape
+        recon = torch.empty(F_, 3, H, W, device=t_out.device, dtype=torch.float32)
+        mask = torch.empty(F_, 1, H, W, device=t_out.device, dtype=torch.float32)
+        w = weight.detach().reshape(-1).contiguous()
+        rc = _lib.lib().repo_b200_tia_mix_fwd(_p(t_out), _p(d_out), _p(w), _p(bias.detach().contiguous()), _p(recon), _p(mask),
+                                              F_, H * W, _stream())
+        _lib.check(rc, "repo_b200_tia_mix_fwd")
+        ctx.save_for_backward(t_out, d_out, w, mask)
+        ctx.mark_non_differentiable(mask)
+        return recon, mask
+
+    @staticmethod
+    def backward(ctx, g, _g_mask):
+        t_out, d_out, w, mask = ctx.saved_tensors
+        F_, _, H, W = t_out.shape
+        g_t, g_d = torch.empty_like(t_out), torch.empty_like(d_out)
+        g_wb = torch.empty(7, device=t_out.device, dtype=torch.float32)
+        rc = _lib.lib().repo_b200_tia_mix_bwd(_p(t_out), _p(d_out), _p(w), _p(mask), _p(g.contiguous()), _p(g_t), _p(g_d), _p(g_wb),
+                                              F_, H * W, _stream())
+        _lib.check(rc, "repo_b200_tia_mix_bwd")
+        return g_t, g_d, g_wb[:6].reshape(1, 6, 1, 1), g_wb[6:7]
+
+
+def tia_mix(t_out, d_out, mask_head):
+    """tia.py:124-127 in one kernel: `mask_head` is the reference's nn.Sequential(nn.Conv2d(6, 1, 1), nn.Sigmoid())
+    (tia.py:72) used as the parameter holder; t_out / d_out are the un-chunked (F,6,H,W) decoder outputs.
+    Returns (recon, mask)."""
+    conv = mask_head[0]
+    return _TiaMixFn.apply(t_out, d_out, conv.weight, conv.bias)
+
+
 class VisualObservationModel(nn.Module):
     """decoder.py:28-48 — Linear(belief+state -> 1024, no activation) -> ConvTranspose2d(1024->128 k5, 128->64 k5,
     64->32 k6, 32->3 k6; stride 2, ReLU on the first three): 1 -> 5 -> 13 -> 30 -> 64 pixels."""
@@ -364,3 +399,20 @@ class VisualObservationModel(nn.Module):
         for c in (self.conv1, self.conv2, self.conv3, self.conv4):
             params += [c.weight, c.bias]
         return _DecoderFn.apply(belief, state, *params)
+
+
+class TIAObservationModel(VisualObservationModel):
+    """decoder.py:154-175 — the same stack with 6 output channels, returned as (recon, mask) channel halves.
+    `forward_full` returns the un-chunked (F,6,64,64) tensor for `tia_mix`."""
+
+    def __init__(self, belief_size, state_size, embedding_size, activation_function="relu"):
+        super().__init__(belief_size, state_size, embedding_size, activation_function)
+        self.conv4 = nn.ConvTranspose2d(32, 6, 6, stride=2)
+
+    def forward_full(self, belief, state):
+        return super().forward(belief, state)
+
+    def forward(self, belief, state):
+        out = super().forward(belief, state)
+        recon, mask = out.chunk(2, 1)
+        return recon, mask

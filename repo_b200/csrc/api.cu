@@ -905,6 +905,30 @@ int repo_b200_pow2_scale(const float* x, long long n, float target, int which, f
   return 0;
 }
 
+int repo_b200_tia_mix_fwd(const float* t_out, const float* d_out, const float* w, const float* b, float* recon, float* mask,
+                          long long frames, int hw, void* stream) {
+  if (!t_out || !d_out || !w || !b || !recon || !mask) return fail(-1, "tia_mix_fwd: NULL pointer");
+  const long long total = frames * hw;
+  if (total <= 0) return 0;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)std::max(1, sm_count()) * 16);
+  tia_mix_fwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(t_out, d_out, w, b, recon, mask, frames, hw);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int repo_b200_tia_mix_bwd(const float* t_out, const float* d_out, const float* w, const float* mask, const float* g_recon,
+                          float* g_t_out, float* g_d_out, float* g_wb, long long frames, int hw, void* stream) {
+  if (!t_out || !d_out || !w || !mask || !g_recon || !g_t_out || !g_d_out || !g_wb) return fail(-1, "tia_mix_bwd: NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaMemsetAsync(g_wb, 0, 7 * sizeof(float), st));
+  const long long total = frames * hw;
+  if (total <= 0) return 0;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)std::max(1, sm_count()) * 8);
+  tia_mix_bwd_kernel<<<blocks, 256, 0, st>>>(t_out, d_out, w, mask, g_recon, g_t_out, g_d_out, g_wb, frames, hw);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream) {
   if (!input || !col || !map) return fail(-1, "im2col: NULL pointer");
   ConvMap cm;

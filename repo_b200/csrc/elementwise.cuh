@@ -147,4 +147,78 @@ __global__ void __launch_bounds__(256) absmax_scale_kernel(const float* __restri
   }
 }
 
+// TIA mask mixing (tia.py:72,124-127): mask = sigmoid(Conv2d(6,1,1)(cat(t_mask, d_mask))), recon = t*mask + d*(1-mask).
+// t_out / d_out are the (F,6,H,W) NCHW outputs of the two TIAObservationModels: channels 0-2 reconstruction, 3-5 mask
+// features.  One thread per pixel.
+__global__ void __launch_bounds__(256) tia_mix_fwd_kernel(const float* __restrict__ t_out, const float* __restrict__ d_out,
+                                                          const float* __restrict__ w /* 6 */, const float* __restrict__ b,
+                                                          float* __restrict__ recon /* (F,3,H,W) */, float* __restrict__ mask /* (F,H,W) */,
+                                                          long long frames, int hw) {
+  const long long total = frames * hw;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const long long fr = idx / hw;
+    const int px = (int)(idx - fr * hw);
+    const float* tp = t_out + fr * 6 * hw + px;
+    const float* dp = d_out + fr * 6 * hw + px;
+    float z = b[0];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) z += w[c] * tp[(3 + c) * hw] + w[3 + c] * dp[(3 + c) * hw];
+    const float m = 1.f / (1.f + expf(-z));
+    mask[idx] = m;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) recon[(fr * 3 + c) * hw + px] = tp[c * hw] * m + dp[c * hw] * (1.f - m);
+  }
+}
+
+// backward: g (F,3,H,W) -> d_t_out, d_d_out (F,6,H,W) and d_w[6], d_b (atomically accumulated; zero them first)
+__global__ void __launch_bounds__(256) tia_mix_bwd_kernel(const float* __restrict__ t_out, const float* __restrict__ d_out,
+                                                          const float* __restrict__ w, const float* __restrict__ mask,
+                                                          const float* __restrict__ g, float* __restrict__ g_t, float* __restrict__ g_d,
+                                                          float* __restrict__ g_wb /* 7 */, long long frames, int hw) {
+  const long long total = frames * hw;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float acc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const long long fr = idx / hw;
+    const int px = (int)(idx - fr * hw);
+    const float* tp = t_out + fr * 6 * hw + px;
+    const float* dp = d_out + fr * 6 * hw + px;
+    float* gt = g_t + fr * 6 * hw + px;
+    float* gd = g_d + fr * 6 * hw + px;
+    const float m = mask[idx];
+    float dm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float gc = g[(fr * 3 + c) * hw + px];
+      gt[c * hw] = gc * m;
+      gd[c * hw] = gc * (1.f - m);
+      dm += gc * (tp[c * hw] - dp[c * hw]);
+    }
+    const float dz = dm * m * (1.f - m);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      gt[(3 + c) * hw] = dz * w[c];
+      gd[(3 + c) * hw] = dz * w[3 + c];
+      acc[c] += dz * tp[(3 + c) * hw];
+      acc[3 + c] += dz * dp[(3 + c) * hw];
+    }
+    acc[6] += dz;
+  }
+  __shared__ float red[8][7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {
+    float v = 0.f;
+    for (int wv = 0; wv < 8; ++wv) v += red[wv][threadIdx.x];
+    atomicAdd(g_wb + threadIdx.x, v);
+  }
+}
+
 }  // namespace rb

@@ -87,7 +87,14 @@ def make_imagine_inputs(seed: int, N: int, horizon: int, dims=DEFAULT_DIMS):
     )
 
 
-def make_conv_params(which: str, seed: int) -> Params:
+def make_mask_head_params(seed: int) -> Params:
+    """nn.Sequential(nn.Conv2d(6, 1, 1), nn.Sigmoid()) (tia.py:72)."""
+    rs = np.random.RandomState(seed)
+    b = 1.0 / math.sqrt(6)
+    return {"0.weight": _uniform(rs, (1, 6, 1, 1), b), "0.bias": _uniform(rs, (1,), b)}
+
+
+def make_conv_params(which: str, seed: int, out_channels: int = 3) -> Params:
     """VisualEncoder (encoder.py:26-29) / VisualObservationModel (decoder.py:35-39) parameters with torch's default
     init distribution (U(+-1/sqrt(fan_in))), from numpy."""
     rs = np.random.RandomState(seed)
@@ -100,7 +107,7 @@ def make_conv_params(which: str, seed: int) -> Params:
     else:
         b = 1.0 / math.sqrt(230)
         p["fc1.weight"], p["fc1.bias"] = _uniform(rs, (1024, 230), b), _uniform(rs, (1024,), b)
-        for i, (ci, co, k) in enumerate([(1024, 128, 5), (128, 64, 5), (64, 32, 6), (32, 3, 6)], 1):
+        for i, (ci, co, k) in enumerate([(1024, 128, 5), (128, 64, 5), (64, 32, 6), (32, out_channels, 6)], 1):
             b = 1.0 / math.sqrt(co * k * k)  # ConvTranspose2d fan_in is computed on dim 1 of its (cin, cout, k, k) weight
             p[f"conv{i}.weight"] = _uniform(rs, (ci, co, k, k), b)
             p[f"conv{i}.bias"] = _uniform(rs, (co,), b)

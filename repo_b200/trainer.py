@@ -11,6 +11,9 @@ Scope: pixel observations (VisualEncoder / VisualObservationModel) — the confi
 (`pixel_obs=True`, train_repo.py:18).  `algo` selects the KL / reconstruction wiring:
   "dreamer": recon reads the latents (gradients reach the RSSM), KL = mean(max(kl, free_nats))
   "repo"   : recon reads DETACHED latents, KL is the dual-variable constraint with split stop-gradients
+  "tia"    : task + distractor RSSMs observed on the same embeddings, two TIA decoders mixed by the mask head, a
+             distractor-only decoder, adversarial distractor reward head (`TIA.build_models` tia.py:18-91,
+             `TIA.train_dynamics` tia.py:93-201)
 """
 from __future__ import annotations
 
@@ -19,9 +22,10 @@ from typing import Dict, Optional
 
 import numpy as np
 import torch
+import torch.nn as nn
 
 from . import losses
-from .conv import VisualEncoder, VisualObservationModel
+from .conv import TIAObservationModel, VisualEncoder, VisualObservationModel, tia_mix
 from .models import ActorModel, RewardModel, ValueModel, bottle
 from .optim import FlatAdam
 from .rssm import TransitionModel
@@ -52,6 +56,9 @@ class Config:
     beta_lr: float = 1e-4
     init_beta: float = 1e-5
     prior_train_steps: int = 5
+    tia_obs_coef: float = 1.0
+    tia_adv_coef: float = 1.0
+    tia_reward_train_steps: int = 1
 
 
 class _Frozen:
@@ -72,8 +79,8 @@ class _Frozen:
 
 class Agent:
     def __init__(self, config: Config, action_size: int, algo: str = "repo", device="cuda"):
-        if algo not in ("repo", "dreamer"):
-            raise ValueError(f"algo {algo!r}: expected 'repo' or 'dreamer'")
+        if algo not in ("repo", "dreamer", "tia"):
+            raise ValueError(f"algo {algo!r}: expected 'repo', 'dreamer' or 'tia'")
         c = self.c = config
         self.algo = algo
         self.device = torch.device(device)
@@ -86,14 +93,28 @@ class Agent:
         self.actor_model = ActorModel(c.belief_size, c.state_size, c.hidden_size, action_size, c.dense_activation_function).to(dev)
         self.value_model = ValueModel(c.belief_size, c.state_size, c.hidden_size, c.dense_activation_function).to(dev)
         self.log_beta = torch.tensor(np.log(c.init_beta), dtype=torch.float32, device=dev, requires_grad=True)  # repo.py:17-23
+        if algo == "tia":  # tia.py:26-76
+            self.obs_model = TIAObservationModel(c.belief_size, c.state_size, c.embedding_size, c.cnn_activation_function).to(dev)
+            self.distractor_transition_model = TransitionModel(c.belief_size, c.state_size, action_size, c.hidden_size,
+                                                               c.embedding_size, c.dense_activation_function).to(dev)
+            self.distractor_obs_model = TIAObservationModel(c.belief_size, c.state_size, c.embedding_size,
+                                                            c.cnn_activation_function).to(dev)
+            self.distractor_only_obs_model = VisualObservationModel(c.belief_size, c.state_size, c.embedding_size,
+                                                                    c.cnn_activation_function).to(dev)
+            self.distractor_reward_model = RewardModel(c.belief_size, c.state_size, c.hidden_size, c.dense_activation_function).to(dev)
+            self.mask_head = nn.Sequential(nn.Conv2d(6, 1, 1), nn.Sigmoid()).to(dev)  # parameter holder; runs in tia_mix
         self.logs: Dict[str, torch.Tensor] = {}
         self._opt = None
 
     # parameter groups of the reference's optimisers (dreamer.py:89-96, 106, 114; repo.py:23)
     @property
     def model_params(self):
-        return (list(self.encoder.parameters()) + list(self.transition_model.parameters())
-                + list(self.obs_model.parameters()) + list(self.reward_model.parameters()))
+        if self.algo == "tia":  # tia.py:74-85
+            mods = [self.encoder, self.transition_model, self.reward_model, self.obs_model, self.distractor_transition_model,
+                    self.distractor_reward_model, self.distractor_obs_model, self.distractor_only_obs_model, self.mask_head]
+        else:
+            mods = [self.encoder, self.transition_model, self.obs_model, self.reward_model]
+        return [p for m in mods for p in m.parameters()]
 
     def optimizers(self):
         """Flat-bucket clip + Adam per parameter group, created on first use (re-points the parameters)."""
@@ -108,9 +129,11 @@ class Agent:
         return self._opt
 
     # ------------------------------------------------------------------ world model
-    def train_dynamics(self, obs, actions, rewards, nonterms, *, eps_prior=None, eps_post=None, step=True):
+    def train_dynamics(self, obs, actions, rewards, nonterms, *, eps_prior=None, eps_post=None, step=True, **tia_eps):
         """obs (T,B,3,64,64) preprocessed floats, actions (T,B,A), rewards (T,B,1), nonterms (T,B,1).
         Returns (beliefs.detach(), posterior_states.detach()) like the reference; logs in `self.logs`."""
+        if self.algo == "tia":
+            return self._train_dynamics_tia(obs, actions, rewards, nonterms, eps_prior, eps_post, step, **tia_eps)
         c = self.c
         B = obs.shape[1]
         init_belief = torch.zeros(B, c.belief_size, device=self.device)
@@ -156,6 +179,64 @@ class Agent:
                 opt["beta"].step()
         self.logs.update(logs)
         return beliefs.detach(), posterior_states.detach()
+
+    def _train_dynamics_tia(self, obs, actions, rewards, nonterms, eps_prior, eps_post, step, eps_prior_d=None, eps_post_d=None):
+        """tia.py:93-201."""
+        c = self.c
+        B = obs.shape[1]
+        init_belief = torch.zeros(B, c.belief_size, device=self.device)
+        init_state = torch.zeros(B, c.state_size, device=self.device)
+        embeds = bottle(self.encoder, (obs,))
+        (t_beliefs, _, t_prior_means, t_prior_std_devs, t_post_states, t_post_means, t_post_std_devs) = \
+            self.transition_model.observe(init_belief, init_state, actions[:-1], embeds[1:], nonterms[:-1],
+                                          eps_prior=eps_prior, eps_post=eps_post)
+        (d_beliefs, _, d_prior_means, d_prior_std_devs, d_post_states, d_post_means, d_post_std_devs) = \
+            self.distractor_transition_model.observe(init_belief, init_state, actions[:-1], embeds[1:], nonterms[:-1],
+                                                     eps_prior=eps_prior_d, eps_post=eps_post_d)
+        # reconstruction through the mask head (one fused kernel for sigmoid(conv1x1) and the mix)
+        t_full = bottle(self.obs_model.forward_full, (t_beliefs, t_post_states))
+        d_full = bottle(self.distractor_obs_model.forward_full, (d_beliefs, d_post_states))
+        recon, _ = tia_mix(t_full.flatten(0, 1), d_full.flatten(0, 1), self.mask_head)
+        recon = recon.reshape(obs.shape[0] - 1, B, *recon.shape[1:])
+        obs_loss = losses.normal_unit_nll(recon, obs[1:]).sum((2, 3, 4)).mean((0, 1))
+        d_only_recon = bottle(self.distractor_only_obs_model, (d_beliefs, d_post_states))
+        d_obs_loss = losses.normal_unit_nll(d_only_recon, obs[1:]).sum((2, 3, 4)).mean((0, 1))
+        # rewards: the distractor head is frozen here so that only the latents are pushed away from reward information
+        rewards_tgt = rewards[:-1].squeeze(-1)
+        mask = nonterms[:-1].squeeze(-1)
+        t_reward = bottle(self.reward_model, (t_beliefs, t_post_states))
+        with _Frozen([self.distractor_reward_model]):
+            d_reward = bottle(self.distractor_reward_model, (d_beliefs, d_post_states))
+        t_reward_loss = (losses.normal_unit_nll(t_reward, rewards_tgt) * mask).mean((0, 1))
+        d_reward_loss = (-losses.normal_unit_nll(d_reward, rewards_tgt) * mask).mean((0, 1))
+        reward_loss = t_reward_loss + c.tia_adv_coef * d_reward_loss
+        t_kl_div = losses.kl_normal(t_post_means, t_post_std_devs, t_prior_means, t_prior_std_devs).sum(2)
+        d_kl_div = losses.kl_normal(d_post_means, d_post_std_devs, d_prior_means, d_prior_std_devs).sum(2)
+        kl_loss = torch.clamp(t_kl_div, min=c.free_nats).mean((0, 1)) + torch.clamp(d_kl_div, min=c.free_nats).mean((0, 1))
+        model_loss = obs_loss + c.tia_obs_coef * d_obs_loss + reward_loss + kl_loss
+        opt = self.optimizers() if step else None
+        if step:
+            opt["model"].zero_grad()
+        model_loss.backward()
+        if step:
+            opt["model"].step()
+        logs = {"train/obs_loss": obs_loss.detach(), "train/d_obs_loss": d_obs_loss.detach(), "train/reward_loss": reward_loss.detach(),
+                "train/t_reward_loss": t_reward_loss.detach(), "train/kl_loss": kl_loss.detach(),
+                "train/t_kl_div": t_kl_div.mean().detach(), "train/d_kl_div": d_kl_div.mean().detach(),
+                "train/model_loss": model_loss.detach()}
+        # second phase (tia.py:180-191): fit the distractor reward head on detached latents.  The reference runs the whole
+        # model optimiser again; with the pinned torch 1.12.1 (`zero_grad` leaves zero tensors) that Adam step also moves every
+        # other model parameter by its momentum, which is what the flat bucket reproduces (SURVEY §8 quirk 11).
+        for _ in range(c.tia_reward_train_steps):
+            d_reward = bottle(self.distractor_reward_model, (d_beliefs.detach(), d_post_states.detach()))
+            d_reward_loss = (losses.normal_unit_nll(d_reward, rewards_tgt) * mask).mean((0, 1))
+            if step:
+                opt["model"].zero_grad()
+                d_reward_loss.backward()
+                opt["model"].step()
+        logs["train/d_reward_loss"] = d_reward_loss.detach()
+        self.logs.update(logs)
+        return t_beliefs.detach(), t_post_states.detach()
 
     # ------------------------------------------------------------------ actor-critic
     def train_actor_critic(self, beliefs, states, *, eps_action=None, eps_prior=None, eps_entropy=None, step=True):

@@ -14,7 +14,7 @@ from tests import _cases as C
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("algo", ["dreamer", "repo"])
+@pytest.mark.parametrize("algo", ["dreamer", "repo", "tia"])
 def test_train_dynamics_matches_reference_trainer(algo):
     from repo_b200.trainer import Agent, Config
     dev = torch.device("cuda:0")
@@ -26,18 +26,29 @@ def test_train_dynamics_matches_reference_trainer(algo):
     agent.transition_model.load_state_dict(O.make_transition_params(seed))
     agent.reward_model.load_state_dict(O.make_mlp_params(seed + 2, D + S, Hd, 1, 3))
     agent.encoder.load_state_dict(O.make_conv_params("encoder", seed + 4))
-    agent.obs_model.load_state_dict(O.make_conv_params("decoder", seed + 5))
+    agent.obs_model.load_state_dict(O.make_conv_params("decoder", seed + 5, out_channels=6 if algo == "tia" else 3))
+    mods = {"encoder": agent.encoder, "transition_model": agent.transition_model, "obs_model": agent.obs_model,
+            "reward_model": agent.reward_model}
+    extra = {}
+    if algo == "tia":
+        agent.distractor_transition_model.load_state_dict(O.make_transition_params(seed + 6))
+        agent.distractor_obs_model.load_state_dict(O.make_conv_params("decoder", seed + 7, out_channels=6))
+        agent.distractor_only_obs_model.load_state_dict(O.make_conv_params("decoder", seed + 8))
+        agent.distractor_reward_model.load_state_dict(O.make_mlp_params(seed + 9, D + S, Hd, 1, 3))
+        agent.mask_head.load_state_dict(O.make_mask_head_params(seed + 12))
+        mods.update({"distractor_transition_model": agent.distractor_transition_model, "distractor_obs_model": agent.distractor_obs_model,
+                     "distractor_only_obs_model": agent.distractor_only_obs_model, "mask_head": agent.mask_head})
+        eps_d = O.make_observe_inputs(seed + 13, T, B)
+        extra = dict(eps_prior_d=eps_d["eps_prior"].to(dev), eps_post_d=eps_d["eps_post"].to(dev))
     batch = {k: v.to(dev) for k, v in O.make_train_batch(seed + 10, T, B, A).items()}
     eps = O.make_observe_inputs(seed + 11, T, B)
     beliefs, states = agent.train_dynamics(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"],
-                                           eps_prior=eps["eps_prior"].to(dev), eps_post=eps["eps_post"].to(dev), step=False)
+                                           eps_prior=eps["eps_prior"].to(dev), eps_post=eps["eps_post"].to(dev), step=False, **extra)
     for k, v in g.items():
         if k.startswith("log_"):
             np.testing.assert_allclose(agent.logs["train/" + k[4:]].item(), v, rtol=1e-3, atol=1e-5, err_msg=k)
     np.testing.assert_allclose(beliefs.cpu().numpy(), g["beliefs"], rtol=1e-3, atol=1e-5)
     np.testing.assert_allclose(states.cpu().numpy(), g["posterior_states"], rtol=1e-3, atol=1e-4)
-    mods = {"encoder": agent.encoder, "transition_model": agent.transition_model, "obs_model": agent.obs_model,
-            "reward_model": agent.reward_model}
     checked = 0
     for prefix, mod in mods.items():
         for name, p in mod.named_parameters():
@@ -52,6 +63,9 @@ def test_train_dynamics_matches_reference_trainer(algo):
             scale = np.abs(want).max() + 1e-30
             np.testing.assert_allclose(got / scale, want / scale, rtol=1e-3, atol=1e-3, err_msg=key)
             checked += 1
-    assert checked == 8 + 14 + 10 + 8  # encoder, transition model, decoder, reward head
+    # encoder, transition model, decoder, reward head (+ TIA: distractor RSSM, two more decoders, mask head)
+    assert checked == 8 + 14 + 10 + 8 + ((14 + 10 + 10 + 2) if algo == "tia" else 0)
+    if algo == "tia":  # frozen while the model loss is built (tia.py:152-154)
+        assert all(p.grad is None for p in agent.distractor_reward_model.parameters())
     if algo == "repo":
         np.testing.assert_allclose(agent.log_beta.grad.item(), g["grad_log_beta"], rtol=1e-3)
