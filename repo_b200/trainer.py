@@ -7,6 +7,12 @@ repo.py:25-112, `Dreamer.train_actor_critic` dreamer.py:304-381).
 instances do, and returns the reference's `train/*` log entries as 0-d device tensors in `self.logs` (no `.item()`
 syncs inside the update).  Noise can be injected (`eps_*`) for parity; otherwise it is drawn on the device.
 
+Data parallel: every rank builds the same Agent and passes its own batch columns (`parallel.shard_rows`,
+uneven shards allowed).  `config.batch_size` stays the GLOBAL batch: each rank scales its losses by
+B_local / batch_size, the flat gradient buckets are SUM-all-reduced inside `FlatAdam.step` (one collective per
+parameter group; `log_beta`'s 1-element gradient separately), and every rank applies the identical clip + Adam.
+Logged scalars are stored pre-weighted, so a SUM-reduce (`reduced_logs`) gives the global values.
+
 Scope: pixel observations (VisualEncoder / VisualObservationModel) — the configuration every headline run uses
 (`pixel_obs=True`, train_repo.py:18).  `algo` selects the KL / reconstruction wiring:
   "dreamer": recon reads the latents (gradients reach the RSSM), KL = mean(max(kl, free_nats))
@@ -106,6 +112,31 @@ class Agent:
         self.logs: Dict[str, torch.Tensor] = {}
         self._opt = None
 
+    # ------------------------------------------------------------------ data parallel helpers
+    @staticmethod
+    def _world():
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _weight(self, local_batch: int) -> float:
+        """rows_local / rows_global for the means over (t, b): 1 on a single process."""
+        return local_batch / self.c.batch_size if self._world() > 1 else 1.0
+
+    def _reduce_scalar_grad(self, t: torch.Tensor):
+        if self._world() > 1 and t.grad is not None:
+            import torch.distributed as dist
+            dist.all_reduce(t.grad, op=dist.ReduceOp.SUM)
+
+    def reduced_logs(self) -> Dict[str, torch.Tensor]:
+        """Global values of the logged scalars (one all-reduce of the stacked, pre-weighted entries)."""
+        keys = sorted(self.logs)
+        if self._world() == 1 or not keys:
+            return dict(self.logs)
+        import torch.distributed as dist
+        flat = torch.stack([self.logs[k].float() for k in keys])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        return {k: flat[i] for i, k in enumerate(keys)}
+
     # parameter groups of the reference's optimisers (dreamer.py:89-96, 106, 114; repo.py:23)
     @property
     def model_params(self):
@@ -165,18 +196,22 @@ class Agent:
             beta_loss = None
         model_loss = obs_loss + reward_loss + kl_loss
         logs.update({"train/kl_loss": kl_loss.detach(), "train/model_loss": model_loss.detach()})
+        w = self._weight(B)
         opt = self.optimizers() if step else None
         if step:
             opt["model"].zero_grad()
-        model_loss.backward()
+        (model_loss * w).backward()
         if step:
             opt["model"].step()
         if beta_loss is not None:
             if step:
                 opt["beta"].zero_grad()
-            beta_loss.backward()
+            (beta_loss * w).backward()
+            self._reduce_scalar_grad(self.log_beta)
             if step:
                 opt["beta"].step()
+        if w != 1.0:  # kl_loss / beta_loss / beta carry constants: weight them too so that the SUM over ranks is global
+            logs = {k: v * w for k, v in logs.items()}
         self.logs.update(logs)
         return beliefs.detach(), posterior_states.detach()
 
@@ -214,10 +249,11 @@ class Agent:
         d_kl_div = losses.kl_normal(d_post_means, d_post_std_devs, d_prior_means, d_prior_std_devs).sum(2)
         kl_loss = torch.clamp(t_kl_div, min=c.free_nats).mean((0, 1)) + torch.clamp(d_kl_div, min=c.free_nats).mean((0, 1))
         model_loss = obs_loss + c.tia_obs_coef * d_obs_loss + reward_loss + kl_loss
+        w = self._weight(B)
         opt = self.optimizers() if step else None
         if step:
             opt["model"].zero_grad()
-        model_loss.backward()
+        (model_loss * w).backward()
         if step:
             opt["model"].step()
         logs = {"train/obs_loss": obs_loss.detach(), "train/d_obs_loss": d_obs_loss.detach(), "train/reward_loss": reward_loss.detach(),
@@ -232,9 +268,11 @@ class Agent:
             d_reward_loss = (losses.normal_unit_nll(d_reward, rewards_tgt) * mask).mean((0, 1))
             if step:
                 opt["model"].zero_grad()
-                d_reward_loss.backward()
+                (d_reward_loss * w).backward()
                 opt["model"].step()
         logs["train/d_reward_loss"] = d_reward_loss.detach()
+        if w != 1.0:
+            logs = {k: v * w for k, v in logs.items()}
         self.logs.update(logs)
         return t_beliefs.detach(), t_post_states.detach()
 
@@ -254,18 +292,19 @@ class Agent:
         discounts = c.gamma * torch.ones_like(reward_preds)
         returns = losses.lambda_return(reward_preds[:-1], value_preds[:-1], discounts[:-1], value_preds[-1], c.gae_lambda)
         actor_loss = losses.actor_loss(returns, action_entropy, latent_entropy, c.action_ent_coef, c.latent_ent_coef)
+        w = self._weight(beliefs.shape[0] / max(1, c.chunk_size - 1))  # start rows = (T-1) * B_local
         if step:
             opt["actor"].zero_grad()
-        actor_loss.backward()
+        (actor_loss * w).backward()
         if step:
             opt["actor"].step()
         value_pred = bottle(self.value_model, (imag_b[:-1].detach(), imag_s[:-1].detach()))
         value_loss = losses.value_loss(value_pred, returns.detach())
         if step:
             opt["value"].zero_grad()
-        value_loss.backward()
+        (value_loss * w).backward()
         if step:
             opt["value"].step()
-        self.logs.update({"train/actor_loss": actor_loss.detach(), "train/value_loss": value_loss.detach(),
-                          "train/action_entropy": action_entropy.detach(), "train/latent_entropy": latent_entropy.detach()})
+        self.logs.update({"train/actor_loss": actor_loss.detach() * w, "train/value_loss": value_loss.detach() * w,
+                          "train/action_entropy": action_entropy.detach() * w, "train/latent_entropy": latent_entropy.detach() * w})
         return returns.detach()
