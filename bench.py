@@ -327,6 +327,13 @@ def run_gpu(a):
             upd[algo + "_world_model_update_ms"] = timeit(wm_update, 5)
             if algo == "repo":
                 upd["actor_critic_update_ms"] = timeit(ac_update, 5)
+                lat = list(agent.init_latent_and_action())
+                frame = batch["obs"][0, :1].contiguous()
+
+                def act_step():
+                    lat[0], lat[1], lat[2] = agent.update_latent_and_select_action(lat[0], lat[1], lat[2], frame)
+
+                upd["acting_step_ms"] = timeit(act_step, 20)
             del agent
         ac_ms = upd["actor_critic_update_ms"]
         default_shape = {"imagine_2450x14_ms": img_ms, "imagine_steps_per_s": 2450 * 14 / img_ms * 1e3,

@@ -49,6 +49,7 @@ class Config:
     batch_size: int = 50
     chunk_size: int = 50
     horizon: int = 15
+    action_noise: float = 0.0
     gamma: float = 0.99
     gae_lambda: float = 0.95
     action_ent_coef: float = 3e-4
@@ -158,6 +159,25 @@ class Agent:
                 "beta": torch.optim.Adam([self.log_beta], lr=c.beta_lr),
             }
         return self._opt
+
+    # ------------------------------------------------------------------ acting path
+    def init_latent_and_action(self):
+        """dreamer.py:169-173."""
+        z = lambda n: torch.zeros(1, n, device=self.device)
+        return z(self.c.belief_size), z(self.c.state_size), z(self.transition_model.action_size)
+
+    @torch.no_grad()
+    def update_latent_and_select_action(self, belief, posterior_state, action, obs, explore=False, *, eps_prior=None,
+                                        eps_post=None):
+        """dreamer.py:175-196: one posterior step on the encoded frame (T=1, B=1, no nonterminal mask), then the actor:
+        the most likely of 100 samples when evaluating, one sample (+ clipped Gaussian action noise) when exploring."""
+        embed = self.encoder(obs).unsqueeze(0)
+        outs = self.transition_model.observe(belief, posterior_state, action.unsqueeze(0), embed, eps_prior=eps_prior, eps_post=eps_post)
+        belief, posterior_state = outs[0].squeeze(0), outs[4].squeeze(0)
+        action = self.actor_model.get_action(belief, posterior_state, det=not explore)
+        if explore:
+            action = torch.clamp(action + torch.randn_like(action) * self.c.action_noise, -1, 1)
+        return belief, posterior_state, action
 
     # ------------------------------------------------------------------ world model
     def train_dynamics(self, obs, actions, rewards, nonterms, *, eps_prior=None, eps_post=None, step=True, **tia_eps):

@@ -69,3 +69,36 @@ def test_train_dynamics_matches_reference_trainer(algo):
         assert all(p.grad is None for p in agent.distractor_reward_model.parameters())
     if algo == "repo":
         np.testing.assert_allclose(agent.log_beta.grad.item(), g["grad_log_beta"], rtol=1e-3)
+
+
+def test_acting_step_matches_oracle():
+    """dreamer.py:175-196 at T=1, B=1: encoder -> one posterior step -> actor, against the oracle on the same noise."""
+    from repo_b200.trainer import Agent, Config
+    from repo_b200 import synth
+    dev = torch.device("cuda:0")
+    agent = Agent(Config(), 6, algo="repo", device=dev)
+    pt, pa, pe = O.make_transition_params(800), O.make_mlp_params(801, 230, 200, 12, 4), O.make_conv_params("encoder", 802)
+    agent.transition_model.load_state_dict(pt)
+    agent.actor_model.load_state_dict(pa)
+    agent.encoder.load_state_dict(pe)
+    belief, state, action = agent.init_latent_and_action()
+    assert belief.shape == (1, 200) and state.shape == (1, 30) and action.shape == (1, 6)
+    rs = np.random.RandomState(803)
+    ob, os_, oa = belief.cpu(), state.cpu(), action.cpu()
+    for step in range(3):
+        frame = synth.make_frames(810 + step, 1)
+        e1 = torch.from_numpy(rs.standard_normal((1, 1, 30)).astype(np.float32))
+        e2 = torch.from_numpy(rs.standard_normal((1, 1, 30)).astype(np.float32))
+        belief, state, action = agent.update_latent_and_select_action(belief, state, action, frame.to(dev), explore=False,
+                                                                      eps_prior=e1.to(dev), eps_post=e2.to(dev))
+        want = O.observe(pt, ob, os_, oa.unsqueeze(0), O.visual_encoder(pe, frame).unsqueeze(0), None, e1, e2)
+        ob, os_ = want[0][0], want[4][0]
+        np.testing.assert_allclose(belief.cpu().numpy(), ob.numpy(), rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(state.cpu().numpy(), os_.numpy(), rtol=1e-3, atol=1e-4)
+        assert action.shape == (1, 6) and float(action.abs().max()) <= 1.0
+        mean, std = O.actor_forward(pa, ob, os_)
+        with torch.no_grad():
+            m2, s2 = agent.actor_model(belief, state)
+        np.testing.assert_allclose(m2.cpu().numpy(), mean.numpy(), rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(s2.cpu().numpy(), std.numpy(), rtol=1e-3, atol=1e-4)
+        oa = action.cpu()  # the 100-sample mode is random: feed the chosen action to both sides
