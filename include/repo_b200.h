@@ -177,15 +177,20 @@ int repo_b200_tanh_normal_entropy_bwd(const float* mean, const float* std_dev, c
  * small-magnitude gradients inside fp16's normal range).  workspace >= repo_b200_conv_workspace_bytes(ntaps*C, n_total).
  * Built by repo_b200/conv.py. */
 size_t repo_b200_conv_workspace_bytes(int k, int n_total);
-int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, const float* relu_mask,
-                        const float* scales, float* out, int frames, int n_total, const int* map, void* workspace,
-                        size_t workspace_bytes, void* stream);
+/* hl_flags: operands in split-activation format — a tensor stored as two fp16 planes, hi then lo (x = hi + lo, the
+ * exact operand pair the tensor cores consume), each laid out like the fp32 tensor, lo plane directly after the hi
+ * plane.  bit0: input, bit1: output, bit2: relu_mask.  Used for the activations between layers: the producing
+ * epilogue splits once and every consumer (next layer, weight gradient) gathers with plain 16-byte copies. */
+int repo_b200_conv_gemm(const void* input, const float* w_mat, const float* bias, const void* relu_mask,
+                        const float* scales, void* out, int frames, int n_total, const int* map, int hl_flags,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* weight gradient of the same implicit GEMM: dw (n_total, ntaps*C) = grad_rows^T @ gather(input), grad_rows being the
  * (frames*RA*RB, g_ld) output-gradient rows (n_total <= 256 columns used).  Row slices are summed with fp32 atomics
- * (dw is zeroed by the call).  scales (nullable) = [s_input, s_grad, 1/(s_input*s_grad)] as in conv_gemm. */
-int repo_b200_conv_wgrad(const float* input, const float* grad_rows, const float* scales, float* dw, int frames,
-                         int n_total, int g_ld, const int* map, void* stream);
+ * (dw is zeroed by the call).  scales (nullable) = [s_input, s_grad, 1/(s_input*s_grad)] as in conv_gemm; input_hl:
+ * the input is in split-activation format (then s_input must be 1). */
+int repo_b200_conv_wgrad(const void* input, const float* grad_rows, const float* scales, float* dw, int frames,
+                         int n_total, int g_ld, const int* map, int input_hl, void* stream);
 
 /* scales[which] = 2^floor(log2(target / max|x|)) and scales[2] = 1 / (scales[0] * scales[1]) in one read-only pass
  * (the `scales` triple of conv_gemm / conv_wgrad; initialise it to {1, 1, 1}).  scratch = 8 zeroed device bytes,

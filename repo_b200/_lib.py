@@ -113,9 +113,9 @@ def lib():
     L.repo_b200_adam_clip_step.restype = ci
     L.repo_b200_conv_workspace_bytes.argtypes = [ci, ci]
     L.repo_b200_conv_workspace_bytes.restype = sz
-    L.repo_b200_conv_gemm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, C.POINTER(ci), vp, sz, vp]
+    L.repo_b200_conv_gemm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, C.POINTER(ci), ci, vp, sz, vp]
     L.repo_b200_conv_gemm.restype = ci
-    L.repo_b200_conv_wgrad.argtypes = [vp, vp, vp, vp, ci, ci, ci, C.POINTER(ci), vp]
+    L.repo_b200_conv_wgrad.argtypes = [vp, vp, vp, vp, ci, ci, ci, C.POINTER(ci), ci, vp]
     L.repo_b200_conv_wgrad.restype = ci
     L.repo_b200_pow2_scale.argtypes = [vp, C.c_longlong, C.c_float, ci, vp, vp, vp]
     L.repo_b200_pow2_scale.restype = ci

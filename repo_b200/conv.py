@@ -90,17 +90,33 @@ def _as_input_side(scales):
     return scales[[1, 0, 2]]
 
 
+def hl_empty(shape, device):
+    """Split-activation ("HL") tensor: fp16 planes [hi, lo] of an NHWC activation, x = hi + lo — the operand pair the
+    tensor cores consume.  The producing conv epilogue writes it; consumers gather it with 16-byte copies."""
+    return torch.empty((2,) + tuple(shape), device=device, dtype=torch.float16)
+
+
+def hl_to_float(t):
+    return t[0].float() + t[1].float()
+
+
+def _is_hl(t):
+    return t is not None and t.dtype == torch.float16
+
+
 def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=None, scales=None):
     """out = epilogue(gather(x) @ w_mat^T + bias) on the tcgen05 conv kernel (one launch + the weight packing).
-    `scales` = device triple [s_x, s_w, 1/(s_x*s_w)] (see `grad_scales`; the gradient is the gathered operand here,
-    so callers pass the triple with the slots swapped) applied before the hi/lo split and undone on the accumulator."""
+    x / out / relu_mask may be HL tensors (`hl_empty`).  `scales` = device triple [s_x, s_w, 1/(s_x*s_w)] (see
+    `grad_scales`; the gradient is the gathered operand here, so callers pass the triple with the slots swapped)
+    applied before the hi/lo split and undone on the accumulator."""
     L = _lib.lib()
+    flags = int(_is_hl(x)) | (int(_is_hl(out)) << 1) | (int(_is_hl(relu_mask)) << 2)
     if w_mat.shape != (n_total, cmap.K):
         raise RuntimeError(f"conv_gemm: weight matrix {tuple(w_mat.shape)} != ({n_total}, {cmap.K})")
     w_mat = w_mat.contiguous()
     ws = torch.empty(L.repo_b200_conv_workspace_bytes(cmap.K, n_total), dtype=torch.uint8, device=x.device)
     rc = L.repo_b200_conv_gemm(_p(x), _p(w_mat), _p(bias), _p(relu_mask), _p(scales), _p(out), frames, n_total, cmap.carray(),
-                               _p(ws), ws.numel(), _stream())
+                               flags, _p(ws), ws.numel(), _stream())
     _lib.check(rc, "repo_b200_conv_gemm")
     return out
 
@@ -114,7 +130,7 @@ def conv_wgrad(x, grad_rows, frames, n_total, cmap: ConvMap, scales=None):
         scales = grad_scales(grad_rows)
     dw = torch.empty(n_total, cmap.K, device=x.device, dtype=torch.float32)
     rc = _lib.lib().repo_b200_conv_wgrad(_p(x), _p(grad_rows), _p(scales), _p(dw), frames, n_total, grad_rows.shape[1],
-                                         cmap.carray(), _stream())
+                                         cmap.carray(), int(_is_hl(x)), _stream())
     _lib.check(rc, "repo_b200_conv_wgrad")
     return dw
 
@@ -152,8 +168,9 @@ class _EncoderFn(torch.autograd.Function):
         acts = [x]
         for i, cm in enumerate(maps):
             cout = ws[i].shape[0]
-            shape = (F_, cout, cm.Ho, cm.Wo) if cm.out_nchw else (F_, cm.Ho, cm.Wo, cout)
-            out = torch.empty(shape, device=x.device, dtype=torch.float32)
+            # intermediate activations live in split (fp16 hi/lo) format; only the final embedding is fp32 NCHW
+            out = torch.empty((F_, cout, cm.Ho, cm.Wo), device=x.device, dtype=torch.float32) if cm.out_nchw \
+                else hl_empty((F_, cm.Ho, cm.Wo, cout), x.device)
             conv_gemm(acts[-1], _conv_wmat(ws[i].detach()), bs[i].detach().contiguous(), out, F_, cout, cm)
             acts.append(out)
         ctx.maps = maps
@@ -182,12 +199,12 @@ class _EncoderFn(torch.autograd.Function):
             if i == 0:
                 break
             # data gradient = sub-pixel conv of gp with 2x2 taps; features (py, px, ci); masked by the ReLU below
-            x = acts[i]
-            H, W = x.shape[1], x.shape[2]
+            x = acts[i]                                # HL (2, F, H, W, C)
+            H, W = x.shape[2], x.shape[3]
             dmap = ConvMap(RA=(H + 1) // 2, RB=(W + 1) // 2, in_nchw=0, C=cout, H=cm.Ho, W=cm.Wo, TH=2, TW=2, sy=1, sx=1,
                            dy=-1, dx=-1, Ho=H, Wo=W, osy=2, osx=2, shuffle=1)
             wd = ws[i].reshape(cout, cin, 2, 2, 2, 2).permute(3, 5, 1, 2, 4, 0).reshape(4 * cin, 4 * cout)
-            d_in = torch.empty_like(x)
+            d_in = torch.empty(x.shape[1:], device=x.device, dtype=torch.float32)
             conv_gemm(gp, wd, None, d_in, F_, 4 * cin, dmap, relu_mask=x, scales=_as_input_side(sc))
             gp = d_in
         if ctx.needs_input_grad[0]:
@@ -268,7 +285,7 @@ class _DecoderFn(torch.autograd.Function):
         # layer 1: 1x1 input -> k x k output is a plain GEMM; features ordered (kh, kw, co) = NHWC (F,k,k,128)
         k1, co1 = ws[0].shape[2], ws[0].shape[1]
         w1 = ws[0].detach().permute(2, 3, 1, 0).reshape(k1 * k1 * co1, -1)
-        a1 = torch.empty(F_, k1, k1, co1, device=h.device, dtype=torch.float32)
+        a1 = hl_empty((F_, k1, k1, co1), h.device)
         conv_gemm(h, w1, bs[0].detach().repeat(k1 * k1), a1, F_, k1 * k1 * co1,
                   ConvMap(RA=1, RB=1, in_nchw=0, C=h.shape[1], H=1, W=1, TH=1, TW=1, sy=1, sx=1, dy=1, dx=1, Ho=1, Wo=1, relu=1))
         acts, maps = [xin, h, a1], []
@@ -277,7 +294,8 @@ class _DecoderFn(torch.autograd.Function):
             cin, cout, k = ws[li].shape[0], ws[li].shape[1], ws[li].shape[2]
             last = li == 3
             cm = _deconv_map(cin, hin, hin, k, out_nchw=last, relu=not last)
-            out = torch.empty((F_, cout, cm.Ho, cm.Wo) if last else (F_, cm.Ho, cm.Wo, cout), device=h.device, dtype=torch.float32)
+            out = torch.empty((F_, cout, cm.Ho, cm.Wo), device=h.device, dtype=torch.float32) if last \
+                else hl_empty((F_, cm.Ho, cm.Wo, cout), h.device)
             conv_gemm(acts[-1], _deconv_wmat(ws[li].detach()), bs[li].detach().repeat(4), out, F_, 4 * cout, cm)
             acts.append(out)
             maps.append(cm)
@@ -318,7 +336,7 @@ class _DecoderFn(torch.autograd.Function):
             wd = wm.permute(3, 1, 2, 0).reshape(cin, T * T * cpad)
             dmap = ConvMap(RA=cm.H, RB=cm.W, in_nchw=0, C=cpad, H=cm.RA, W=cm.RB, TH=T, TW=T, sy=1, sx=1, dy=1, dx=1,
                            Ho=cm.H, Wo=cm.W)
-            d_in = torch.empty_like(x)
+            d_in = torch.empty(x.shape[1:], device=x.device, dtype=torch.float32)
             conv_gemm(G, wd, None, d_in, F_, cin, dmap, relu_mask=x, scales=_as_input_side(sc))
             gp = d_in
         # layer 1 (plain GEMM) and fc1

@@ -770,9 +770,12 @@ size_t repo_b200_conv_workspace_bytes(int K, int n_total) {
   return (size_t)n_tiles * k16 * NP * 64 + (size_t)n_tiles * NP * sizeof(float) + 256;
 }
 
-int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bias, const float* relu_mask,
-                        const float* scales, float* out, int frames, int n_total, const int* map /* ConvMap as 27 ints */,
-                        void* ws, size_t ws_bytes, void* stream) {
+int repo_b200_conv_gemm(const void* input_, const float* w_mat, const float* bias, const void* relu_mask_,
+                        const float* scales, void* out_, int frames, int n_total, const int* map /* ConvMap as 27 ints */,
+                        int hl_flags, void* ws, size_t ws_bytes, void* stream) {
+  const float* input = static_cast<const float*>(input_);
+  const float* relu_mask = static_cast<const float*>(relu_mask_);
+  float* out = static_cast<float*>(out_);
   if (!input || !w_mat || !out || !map || !ws) return fail(-1, "conv: NULL pointer");
   ConvMap cm;
   static_assert(sizeof(ConvMap) == 27 * sizeof(int), "ConvMap layout");
@@ -818,10 +821,19 @@ int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bia
   P.cm = cm;
   P.n_rows = (int)rows; P.K = K; P.n_total = n_total;
   P.cout = cm.shuffle ? n_total / 4 : n_total;
+  // split-activation (fp16 hi/lo plane) operands: bit0 input, bit1 output, bit2 relu mask
+  P.in_hl = hl_flags & 1; P.out_hl = (hl_flags >> 1) & 1; P.mask_hl = (hl_flags >> 2) & 1;
+  if (P.in_hl && (cm.in_nchw || (cm.C & 7) || scales)) return fail(-1, "conv: HL input needs NHWC, C %% 8 == 0 and no operand scaling");
+  if ((P.out_hl || P.mask_hl) && (cm.out_nchw || (P.cout & 15) || (P.NP & 15)))
+    return fail(-1, "conv: HL output / mask needs an NHWC output with cout %% 16 == 0");
+  if (P.mask_hl && !relu_mask) return fail(-1, "conv: mask_hl without a mask");
+  P.in_lo_bytes = (long long)frames * cm.H * cm.W * cm.C * 2;
+  P.out_lo_elems = P.mask_lo_elems = (long long)frames * cm.Ho * cm.Wo * P.cout;
+  P.a_lbo = P.in_hl ? kCvALboHL : kCvALbo;
   P.kc16 = P.NP <= 128 ? 4 : 2;
   P.stage_bytes = conv_stage_bytes(P.kc16, P.NP);
   P.n_stages = std::min(kCvMaxStages, (200 * 1024) / P.stage_bytes);
-  const int n_ent = conv_table_entries(cm, P.k16);
+  const int n_ent = conv_table_entries(cm, P.k16, P.in_hl);
   if (n_ent > 2048) return fail(-1, "conv: K = %d needs %d gather-table entries (max 2048)", K, n_ent);
   const size_t smem = (size_t)P.n_stages * P.stage_bytes + 128 + (size_t)n_ent * sizeof(ConvTap);
   static size_t configured = 0;
@@ -838,8 +850,9 @@ int repo_b200_conv_gemm(const float* input, const float* w_mat, const float* bia
   return 0;
 }
 
-int repo_b200_conv_wgrad(const float* input, const float* grad_rows, const float* scales, float* dw, int frames,
-                         int n_total, int g_ld, const int* map /* ConvMap as 27 ints */, void* stream) {
+int repo_b200_conv_wgrad(const void* input_, const float* grad_rows, const float* scales, float* dw, int frames,
+                         int n_total, int g_ld, const int* map /* ConvMap as 27 ints */, int input_hl, void* stream) {
+  const float* input = static_cast<const float*>(input_);
   if (!input || !grad_rows || !dw || !map) return fail(-1, "conv_wgrad: NULL pointer");
   ConvMap cm;
   std::memcpy(&cm, map, sizeof(cm));
@@ -859,7 +872,10 @@ int repo_b200_conv_wgrad(const float* input, const float* grad_rows, const float
   P.x = input; P.g = grad_rows; P.dw = dw; P.scales = scales; P.cm = cm;
   P.n_rows = (int)rows; P.K = K; P.k16 = cdiv(K, 16); P.n_total = n_total; P.g_ld = g_ld;
   P.NP = cdiv(n_total, 16) * 16;
-  const int n_ent = conv_table_entries(cm, P.k16);
+  P.x_hl = input_hl ? 1 : 0;
+  if (P.x_hl && (cm.in_nchw || (cm.C & 7))) return fail(-1, "conv_wgrad: HL input needs NHWC and C %% 8 == 0");
+  P.x_lo_bytes = (long long)frames * cm.H * cm.W * cm.C * 2;
+  const int n_ent = conv_table_entries(cm, P.k16, P.x_hl);
   if (n_ent > 2048) return fail(-1, "conv_wgrad: K = %d needs %d gather-table entries (max 2048)", K, n_ent);
   // super tiles: mt k-tiles of 128 share one CTA's TMEM (mt * NP <= 512 columns) and ring stage
   const int m_tiles = cdiv(K, 128);

@@ -37,6 +37,11 @@ struct ConvParams {
   // before the hi/lo split (gradients are far below 6e-5, where fp16 has no mantissa left); undone in the epilogue
   const float* scales;
   float* out;
+  // Split-activation format ("HL"): a tensor stored as two fp16 planes, hi then lo (x = hi + lo), each laid out like
+  // the fp32 tensor would be.  The producing epilogue splits once; gathers of HL inputs are pure 16-byte copies.
+  int in_hl, out_hl, mask_hl;         // x / out / relu_mask are HL (pointers address the hi plane)
+  long long in_lo_bytes, out_lo_elems, mask_lo_elems;  // distance from the hi plane to the lo plane
+  uint32_t a_lbo;                     // byte stride between k-groups of the gathered operand inside a ring stage
   ConvMap cm;
   int n_rows, K, k16;      // GEMM rows, real K, k16 slabs
   int n_total, NP, n_tiles;  // output features, features per tile (multiple of 16, <= 256), tiles
@@ -47,7 +52,8 @@ struct ConvParams {
 // A operand (gathered rows) inside a ring stage: k-group g (8 fp16 of every row) starts at g * kCvALbo; the 32-byte
 // pad over 128 rows x 16 B rotates the banks so the gatherers' 8-byte stores (4 groups x 2 halves x 2 rows per
 // half-warp) are conflict-free.
-constexpr uint32_t kCvALbo = 2048 + 32;
+constexpr uint32_t kCvALbo = 2048 + 32;     // fp32 inputs: 8-byte stores, 4 k-groups x 2 halves x 2 rows per half-warp
+constexpr uint32_t kCvALboHL = 2048 + 16;   // HL inputs: 16-byte stores, 8 k-groups of one row per quarter-warp
 __host__ __device__ inline int conv_stage_bytes(int kc16, int NP) { return kc16 * (4 * (int)kCvALbo + NP * 64); }
 
 // Gather table, built once per CTA: the input address of (row, k) separates into a per-row base plus a per-k
@@ -58,7 +64,27 @@ struct ConvTap {
   short tdy, tdx;  // tap displacement in pixels (sentinel -30000 beyond K: fails the bounds test)
 };
 __host__ __device__ inline bool conv_quads(const ConvMap& cm) { return !cm.in_nchw && (cm.C & 3) == 0; }
-__host__ __device__ inline int conv_table_entries(const ConvMap& cm, int k16) { return conv_quads(cm) ? k16 * 4 : k16 * 16; }
+// entries: one per k (scalar path), per channel quad (fp32 NHWC), or per channel oct (HL input, C % 8 == 0)
+__host__ __device__ inline int conv_table_entries(const ConvMap& cm, int k16, int in_hl = 0) {
+  return in_hl ? k16 * 2 : (conv_quads(cm) ? k16 * 4 : k16 * 16);
+}
+__device__ __forceinline__ void conv_build_table(ConvTap* table, const ConvMap& cm, int k16, int in_hl, int tid, int nthreads) {
+  const bool quads = conv_quads(cm);
+  const int n_ent = conv_table_entries(cm, k16, in_hl);
+  const int kstep = in_hl ? 8 : (quads ? 4 : 1), esz = in_hl ? 2 : 4;
+  for (int i = tid; i < n_ent; i += nthreads) {
+    const int k = kstep * i;
+    const int tap = k / cm.C, ci = k - tap * cm.C;
+    ConvTap e{0, -30000, -30000};
+    if (tap < cm.ntaps) {
+      const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
+      e.tdy = (short)(ty * cm.dy);
+      e.tdx = (short)(tx * cm.dx);
+      e.off = esz * (cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.C + ci);
+    }
+    table[i] = e;
+  }
+}
 
 // opaque 64-bit value: keeps a precomputed row pointer in registers instead of letting the compiler re-derive it
 // from the kernel parameter on every use
@@ -96,22 +122,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
-  {
-    const bool quads = conv_quads(cm);
-    const int n_ent = conv_table_entries(cm, P.k16);
-    for (int i = threadIdx.x; i < n_ent; i += kCvThreads) {
-      const int k = quads ? 4 * i : i;
-      const int tap = k / cm.C, ci = k - tap * cm.C;
-      ConvTap e{0, -30000, -30000};
-      if (tap < cm.ntaps) {
-        const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
-        e.tdy = (short)(ty * cm.dy);
-        e.tdx = (short)(tx * cm.dx);
-        e.off = 4 * (cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.C + ci);
-      }
-      table[i] = e;
-    }
-  }
+  conv_build_table(table, cm, P.k16, P.in_hl, threadIdx.x, kCvThreads);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -120,7 +131,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
   const int row_tiles = (P.n_rows + 127) / 128;
   const int n_items = row_tiles * P.n_tiles;
   const uint32_t slab_bytes = (uint32_t)P.NP * 64u;
-  const uint32_t a_half = (uint32_t)P.kc16 * 2u * kCvALbo;  // A hi region (lo follows), then the weight slabs
+  const uint32_t a_lbo = P.a_lbo;
+  const uint32_t a_half = (uint32_t)P.kc16 * 2u * kCvALbo;  // A hi region (lo follows), then the weight slabs (sized for the larger stride)
   const int n_stages = P.n_stages;
 
   // register budget per role (setmaxnreg inside each branch, see rows.cuh): launch pool 768*80: 128*40 + 128*88 + 512*88
@@ -165,8 +177,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
           const uint32_t sa = ring_a + slot * (uint32_t)P.stage_bytes;
           uint32_t wa = sa + 2 * a_half;
           for (int j = 0; j < nsl; ++j) {
-            const uint64_t a_hi = make_smem_desc(sa + (uint32_t)j * 2u * kCvALbo, kCvALbo, 128);
-            const uint64_t a_lo = make_smem_desc(sa + a_half + (uint32_t)j * 2u * kCvALbo, kCvALbo, 128);
+            const uint64_t a_hi = make_smem_desc(sa + (uint32_t)j * 2u * a_lbo, a_lbo, 128);
+            const uint64_t a_lo = make_smem_desc(sa + a_half + (uint32_t)j * 2u * a_lbo, a_lbo, 128);
             const uint64_t b_hi = make_smem_desc(wa, w_lbo, 128);
             const uint64_t b_lo = make_smem_desc(wa + w_lo, w_lbo, 128);
             umma_f16(d, a_hi, b_hi, idesc, (j == 0) ? acc : 1u);
@@ -196,6 +208,80 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
     const bool quads = conv_quads(cm);
     uint32_t slot = 0, phase = 0;
     const int per_frame = cm.RA * cm.RB;
+    if (P.in_hl) {
+      // HL input: thread p copies channel oct q (16 bytes of the hi plane + 16 of the lo plane) of rows rs and rs + 64.
+      // The loads run ONE CHUNK AHEAD of the stores (register double buffer), so the global-load latency of chunk c+1
+      // overlaps the barrier wait + shared stores of chunk c instead of serialising with them.
+      const uint32_t st_hl = (uint32_t)q * a_lbo + (uint32_t)rs * 16u;
+      const long long lo_delta = P.in_lo_bytes;
+      uint64_t base[2] = {0, 0};
+      int ay[2] = {-30000, -30000}, bx[2] = {0, 0};
+      int w_l = blockIdx.x, c0_l = 0;               // load cursor
+      auto rows_of = [&](int w) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int row = (w / P.n_tiles) * 128 + rs + 64 * j;
+          const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
+          ay[j] = row < P.n_rows ? a * cm.sy + cm.y0 : -30000;
+          bx[j] = b * cm.sx + cm.x0;
+          const long long e = (((long long)fr * cm.H + ay[j]) * cm.W + bx[j]) * cm.C * 2;
+          base[j] = opaque(reinterpret_cast<uint64_t>(P.x) + (row < P.n_rows ? e : 0));
+        }
+      };
+      auto load = [&](uint4* vh, uint4* vl) -> int {   // loads chunk (w_l, c0_l), advances the cursor, returns its k extent
+        const int kchunk = 16 * min(P.kc16, P.k16 - c0_l);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { vh[j] = make_uint4(0, 0, 0, 0); vl[j] = make_uint4(0, 0, 0, 0); }
+        if (q * 8 < kchunk) {
+          const ConvTap e = table[(c0_l * 16 + q * 8) >> 3];
+          const long long ob = e.off;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const bool ok = (unsigned)(ay[j] + e.tdy) < (unsigned)cm.H && (unsigned)(bx[j] + e.tdx) < (unsigned)cm.W;
+            if (ok) {
+              vh[j] = __ldg(reinterpret_cast<const uint4*>(base[j] + ob));
+              vl[j] = __ldg(reinterpret_cast<const uint4*>(base[j] + ob + lo_delta));
+            }
+          }
+        }
+        c0_l += P.kc16;
+        if (c0_l >= P.k16) {
+          c0_l = 0;
+          w_l += gridDim.x;
+          if (w_l < n_items) rows_of(w_l);
+        }
+        return kchunk;
+      };
+      bool have = w_l < n_items;
+      uint4 ch[2], cl[2];
+      int ck = 0;
+      if (have) {
+        rows_of(w_l);
+        ck = load(ch, cl);
+      }
+      while (have) {
+        const bool have_next = w_l < n_items;
+        uint4 nh[2], nl[2];
+        int nk = 0;
+        if (have_next) nk = load(nh, nl);
+        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        if (q * 8 < ck) {
+          uint8_t* a_hi = ring + (size_t)slot * P.stage_bytes + st_hl;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            *reinterpret_cast<uint4*>(a_hi + j * 1024) = ch[j];
+            *reinterpret_cast<uint4*>(a_hi + a_half + j * 1024) = cl[j];
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bar_full + 8 * slot);
+        if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { ch[j] = nh[j]; cl[j] = nl[j]; }
+        ck = nk;
+        have = have_next;
+      }
+    } else {
     const uint32_t st_off = (uint32_t)(q >> 1) * kCvALbo + (uint32_t)(q & 1) * 8u + (uint32_t)rs * 16u;
     const float xs = SCALED ? __ldg(P.scales) : 1.f;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
@@ -268,6 +354,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
         if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
       }
     }
+    }  // fp32 input
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // ================================ epilogue ================================
@@ -305,19 +392,55 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
           if (yy < cm.Ho && xx < cm.Wo) {
             const size_t o = (((size_t)fr * cm.Ho + yy) * cm.Wo + xx) * cout + co;
             const float4* bp = reinterpret_cast<const float4*>(P.bias + nb);
-            float4* op = reinterpret_cast<float4*>(P.out + o);
+            float y[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 bb = __ldg(bp + j);
-              float4 y = make_float4(fmaf(v[4 * j], unscale, bb.x), fmaf(v[4 * j + 1], unscale, bb.y),
-                                     fmaf(v[4 * j + 2], unscale, bb.z), fmaf(v[4 * j + 3], unscale, bb.w));
-              if (cm.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-              if (P.relu_mask) {
-                const float4 m = __ldg(reinterpret_cast<const float4*>(P.relu_mask + o) + j);
-                y.x = m.x > 0.f ? y.x : 0.f; y.y = m.y > 0.f ? y.y : 0.f;
-                y.z = m.z > 0.f ? y.z : 0.f; y.w = m.w > 0.f ? y.w : 0.f;
+              y[4 * j] = fmaf(v[4 * j], unscale, bb.x); y[4 * j + 1] = fmaf(v[4 * j + 1], unscale, bb.y);
+              y[4 * j + 2] = fmaf(v[4 * j + 2], unscale, bb.z); y[4 * j + 3] = fmaf(v[4 * j + 3], unscale, bb.w);
+            }
+            if (cm.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
+            }
+            if (P.relu_mask) {
+              if (P.mask_hl) {  // sign of the hi plane = sign of the activation
+                const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(P.relu_mask) + o);
+                const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+                const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&mw[i]));
+                  y[2 * i] = f.x > 0.f ? y[2 * i] : 0.f;
+                  y[2 * i + 1] = f.y > 0.f ? y[2 * i + 1] : 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 m = __ldg(reinterpret_cast<const float4*>(P.relu_mask + o) + j);
+                  y[4 * j] = m.x > 0.f ? y[4 * j] : 0.f; y[4 * j + 1] = m.y > 0.f ? y[4 * j + 1] : 0.f;
+                  y[4 * j + 2] = m.z > 0.f ? y[4 * j + 2] : 0.f; y[4 * j + 3] = m.w > 0.f ? y[4 * j + 3] : 0.f;
+                }
               }
-              op[j] = y;
+            }
+            if (P.out_hl) {
+              uint32_t h[8], l[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                split2_f16(y[2 * i], y[2 * i + 1], h[i], l[i]);
+                // the hi plane doubles as the ReLU mask of the backward pass (sign of the activation): a positive value
+                // below fp16's smallest subnormal must not vanish, so it is stored as that subnormal (6e-8 absolute)
+                if (y[2 * i] > 0.f && (h[i] & 0x7fffu) == 0u) h[i] |= 1u;
+                if (y[2 * i + 1] > 0.f && (h[i] & 0x7fff0000u) == 0u) h[i] |= 0x10000u;
+              }
+              uint4* hp = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(P.out) + o);
+              uint4* lp = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(P.out) + P.out_lo_elems + o);
+              hp[0] = make_uint4(h[0], h[1], h[2], h[3]); hp[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              lp[0] = make_uint4(l[0], l[1], l[2], l[3]); lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
+            } else {
+              float4* op = reinterpret_cast<float4*>(P.out + o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
             }
           }
         } else {
@@ -374,6 +497,8 @@ struct WgradParams {
   const float* g;        // output-gradient rows (n_rows, g_ld)
   float* dw;             // (n_total, K) fp32, zero-initialised
   const float* scales;   // optional device floats [s_x, s_g, 1/(s_x*s_g)]
+  int x_hl;              // x is in split-activation format (fp16 hi plane at x, lo plane x_lo_bytes further)
+  long long x_lo_bytes;
   ConvMap cm;
   int n_rows, K, k16, n_total, g_ld, NP;
   int n_super;                       // super tiles
@@ -410,21 +535,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
     tmem_relinquish();
   }
   const bool quads = conv_quads(cm);
-  {
-    const int n_ent = conv_table_entries(cm, P.k16);
-    for (int i = threadIdx.x; i < n_ent; i += kCvThreads) {
-      const int k = quads ? 4 * i : i;
-      const int tap = k / cm.C, ci = k - tap * cm.C;
-      ConvTap e{0, -30000, -30000};
-      if (tap < cm.ntaps) {
-        const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
-        e.tdy = (short)(ty * cm.dy);
-        e.tdx = (short)(tx * cm.dx);
-        e.off = 4 * (cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.C + ci);
-      }
-      table[i] = e;
-    }
-  }
+  conv_build_table(table, cm, P.k16, P.x_hl, threadIdx.x, kCvThreads);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -502,6 +613,34 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
       mbar_wait(bar_empty + 8 * slot, phase ^ 1);
       uint8_t* sa = ring + (size_t)slot * P.stage_bytes;
       uint8_t* sb = sa + 2 * a_half;
+      if (P.x_hl) {
+        // HL input: 16 lanes x one channel oct each = 128 k per pass, pure 16-byte copies of both planes
+        const uint64_t bh = opaque(reinterpret_cast<uint64_t>(P.x) + (valid ? e0 * 2 : 0));
+        uint4 vh[4], vl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vh[i] = make_uint4(0, 0, 0, 0);
+          vl[i] = make_uint4(0, 0, 0, 0);
+          const int k = m0 * 128 + i * 128 + q * 8;
+          if (i * 128 < kt && k < P.k16 * 16) {
+            const ConvTap e = table[k >> 3];
+            const bool ok = (unsigned)(ay + e.tdy) < (unsigned)cm.H && (unsigned)(bx + e.tdx) < (unsigned)cm.W;
+            if (ok) {
+              vh[i] = __ldg(reinterpret_cast<const uint4*>(bh + (long long)e.off));
+              vl[i] = __ldg(reinterpret_cast<const uint4*>(bh + (long long)e.off + P.x_lo_bytes));
+            }
+          }
+        }
+        const uint32_t o0 = (uint32_t)(rs >> 3) * lbo_a + (uint32_t)(rs & 7) * 16u + (uint32_t)q * kWgSbo;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i * 128 < kt) {
+            const uint32_t o = o0 + (uint32_t)i * 16u * kWgSbo;
+            *reinterpret_cast<uint4*>(sa + o) = vh[i];
+            *reinterpret_cast<uint4*>(sa + a_half + o) = vl[i];
+          }
+        }
+      } else
       for (int kb0 = 0; kb0 < kblocks; kb0 += 4) {
         float4 v[4];
 #pragma unroll

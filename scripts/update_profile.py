@@ -35,4 +35,10 @@ for name, fn in (("train_dynamics", wm), ("train_actor_critic", ac)):
     for e in evs:
         if e.self_device_time_total > 0:
             print(f"{e.self_device_time_total/1e3:9.3f} ms  x{e.count:<4d} {e.key[:110]}")
-    print(f"{tot/1e3:9.3f} ms total device time")
+    ksum = sum(e.self_device_time_total for e in prof.key_averages() if e.self_cpu_time_total == 0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    print(f"{ksum/1e3:9.3f} ms sum of kernel durations; {e0.elapsed_time(e1)/5:9.3f} ms wall per call (no profiler)")

@@ -112,3 +112,47 @@ def test_conv_wgrad_matches_materialised_gemm(dev, case):
     got = cv.conv_wgrad(x, g, Fr, n_total, cm)
     assert got.shape == (n_total, cm.K)
     rel_close(got, want.cpu().numpy(), case, rtol=1e-3, floor=1e-5)
+
+
+def test_split_activation_format_is_equivalent_to_fp32(dev):
+    """HL (fp16 hi/lo plane) operands: gathering an HL input, writing an HL output and masking with an HL activation must
+    reproduce the fp32 paths (bit-exact for the gather / mask, 1 ulp for the re-joined output), and tiny positive
+    activations must survive in the hi plane (it doubles as the ReLU mask of the backward pass)."""
+    from repo_b200 import conv as cv
+    torch.manual_seed(0)
+    F_ = 7
+
+    def to_hl(x):
+        hi = x.half()
+        return torch.stack([hi, (x - hi.float()).half()]).contiguous()
+
+    cm3 = cv._deconv_map(64, 13, 13, 6, False, True)
+    a2 = torch.relu(torch.randn(F_, 13, 13, 64, device=dev))
+    w3, b3 = torch.randn(128, cm3.K, device=dev) * 0.05, torch.randn(128, device=dev) * 0.1
+    y_f, y_hl_in = torch.empty(F_, 30, 30, 32, device=dev), torch.empty(F_, 30, 30, 32, device=dev)
+    y_hl_out = cv.hl_empty((F_, 30, 30, 32), dev)
+    cv.conv_gemm(a2, w3, b3, y_f, F_, 128, cm3)
+    cv.conv_gemm(to_hl(a2), w3, b3, y_hl_in, F_, 128, cm3)
+    cv.conv_gemm(to_hl(a2), w3, b3, y_hl_out, F_, 128, cm3)
+    assert torch.equal(y_f, y_hl_in)
+    assert (cv.hl_to_float(y_hl_out) - y_f).abs().max().item() <= 2.4e-7 * max(1.0, y_f.abs().max().item())
+    assert torch.equal(y_hl_out[0] > 0, y_f > 0)          # mask semantics preserved, incl. values below fp16's range
+    # tiny positive outputs: bias 1e-9 on zero weights -> relu output 1e-9 must still read as "positive"
+    tiny = cv.hl_empty((F_, 30, 30, 32), dev)
+    cv.conv_gemm(a2, torch.zeros_like(w3), torch.full((128,), 1e-9, device=dev), tiny, F_, 128, cm3)
+    assert bool((tiny[0] > 0).all())
+    # data gradient with an fp32 vs HL ReLU mask
+    cm4 = cv._deconv_map(32, 30, 30, 6, True, False)
+    G = torch.randn(F_, cm4.RA, cm4.RB, 16, device=dev) * 1e-4
+    wd = torch.randn(32, 9 * 16, device=dev) * 0.05
+    a3 = torch.relu(torch.randn(F_, 30, 30, 32, device=dev))
+    dmap = cv.ConvMap(RA=30, RB=30, in_nchw=0, C=16, H=cm4.RA, W=cm4.RB, TH=3, TW=3, sy=1, sx=1, dy=1, dx=1, Ho=30, Wo=30)
+    sc = cv._as_input_side(cv.grad_scales(G))
+    o1, o2 = torch.empty(F_, 30, 30, 32, device=dev), torch.empty(F_, 30, 30, 32, device=dev)
+    cv.conv_gemm(G, wd, None, o1, F_, 32, dmap, relu_mask=a3, scales=sc)
+    cv.conv_gemm(G, wd, None, o2, F_, 32, dmap, relu_mask=to_hl(a3), scales=sc)
+    assert torch.equal(o1, o2)
+    # weight gradient with an fp32 vs HL input
+    g = torch.randn(F_ * cm3.RA * cm3.RB, 128, device=dev) * 1e-5
+    d1, d2 = cv.conv_wgrad(a2, g, F_, 128, cm3), cv.conv_wgrad(to_hl(a2), g, F_, 128, cm3)
+    assert ((d1 - d2).abs().max() / d1.abs().max()).item() < 2e-6   # atomics: summation order differs run to run
