@@ -206,6 +206,12 @@ int repo_b200_tia_mix_fwd(const float* t_out, const float* d_out, const float* w
 int repo_b200_tia_mix_bwd(const float* t_out, const float* d_out, const float* w, const float* mask, const float* g_recon,
                           float* g_t_out, float* g_d_out, float* g_wb, long long frames, int hw, void* stream);
 
+/* backward glue of a stride-2 ConvTranspose2d: G (frames,RA,RB,cpad) with G[(f,a,b),(py,px,c)] = g[f,2a+py,2b+px,c]
+ * (zero outside the Ho x Wo grid and in the padding columns; g is NHWC, or NCHW when g_nchw) and the bias gradient
+ * db[c] = sum of g over frames and pixels, in one pass.  cpad >= 4*channels must divide 256. */
+int repo_b200_grad_unshuffle(const float* g, int g_nchw, float* G, float* db, int frames, int RA, int RB, int Ho, int Wo,
+                             int channels, int cpad, void* stream);
+
 /* backward helper with the same map: im2col materialises the gathered rows (rows = frames*RA*RB, ntaps*C columns)
  * for the weight-gradient GEMM. */
 int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream);

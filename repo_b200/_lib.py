@@ -41,7 +41,7 @@ EXPORTS = [
     "repo_b200_head_workspace_bytes", "repo_b200_head_fwd",
     "repo_b200_tanh_normal_entropy_fwd", "repo_b200_replay_gather",
     "repo_b200_cell_workspace_bytes", "repo_b200_cell_fwd",
-    "repo_b200_sqnorm_accumulate", "repo_b200_adam_clip_step", "repo_b200_conv_workspace_bytes", "repo_b200_conv_gemm", "repo_b200_conv_wgrad", "repo_b200_pow2_scale", "repo_b200_tia_mix_fwd", "repo_b200_tia_mix_bwd", "repo_b200_im2col",
+    "repo_b200_sqnorm_accumulate", "repo_b200_adam_clip_step", "repo_b200_conv_workspace_bytes", "repo_b200_conv_gemm", "repo_b200_conv_wgrad", "repo_b200_pow2_scale", "repo_b200_grad_unshuffle", "repo_b200_tia_mix_fwd", "repo_b200_tia_mix_bwd", "repo_b200_im2col",
     "repo_b200_mlp_workspace_bytes", "repo_b200_mlp_fwd", "repo_b200_mlp_bwd", "repo_b200_tanh_normal_entropy_bwd",
 ]
 
@@ -123,6 +123,8 @@ def lib():
     L.repo_b200_tia_mix_fwd.restype = ci
     L.repo_b200_tia_mix_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_longlong, ci, vp]
     L.repo_b200_tia_mix_bwd.restype = ci
+    L.repo_b200_grad_unshuffle.argtypes = [vp, ci, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
+    L.repo_b200_grad_unshuffle.restype = ci
     L.repo_b200_im2col.argtypes = [vp, vp, ci, C.POINTER(ci), vp]
     L.repo_b200_im2col.restype = ci
     L.repo_b200_linear_workspace_bytes.argtypes = [ci, ci]

@@ -261,14 +261,27 @@ def _deconv_wgrad(dwm, cin, cout, k):
     return dwm.reshape(2, 2, cout, T, T, cin).permute(5, 2, 3, 0, 4, 1).reshape(cin, cout, 2 * T, 2 * T)[:, :, :k, :k].contiguous()
 
 
-def _unshuffle(g, ra, rb, cpad):
-    """(F, Ho, Wo, C) NHWC -> (F, RA, RB, cpad >= 4C) rows of sub-pixel classes (py, px, c); zero outside the grid."""
-    F_, ho, wo, c = g.shape
-    gp = F.pad(g, (0, 0, 0, 2 * rb - wo, 0, 2 * ra - ho))
-    gp = gp.reshape(F_, ra, 2, rb, 2, c).permute(0, 1, 3, 2, 4, 5).reshape(F_, ra, rb, 4 * c)
-    if cpad > 4 * c:
-        gp = F.pad(gp, (0, cpad - 4 * c))
-    return gp.contiguous()
+def _cpad(cout):
+    """columns of the un-shuffled gradient: 4*cout rounded up to a divisor of 256 (>= 16)"""
+    n = 16
+    while n < 4 * cout:
+        n *= 2
+    return n
+
+
+def _unshuffle(g, ra, rb, cpad, nchw=False):
+    """(F, Ho, Wo, C) NHWC (or (F, C, Ho, Wo) with nchw) -> G (F, RA, RB, cpad) rows of sub-pixel classes (py, px, c), zero
+    outside the grid / in the padding, and the bias gradient sum(g) per channel — one fused pass."""
+    g = g.contiguous()
+    if nchw:
+        F_, c, ho, wo = g.shape
+    else:
+        F_, ho, wo, c = g.shape
+    G = torch.empty(F_, ra, rb, cpad, device=g.device, dtype=torch.float32)
+    db = torch.empty(c, device=g.device, dtype=torch.float32)
+    rc = _lib.lib().repo_b200_grad_unshuffle(_p(g), int(nchw), _p(G), _p(db), F_, ra, rb, ho, wo, c, cpad, _stream())
+    _lib.check(rc, "repo_b200_grad_unshuffle")
+    return G, db
 
 
 class _DecoderFn(torch.autograd.Function):
@@ -316,15 +329,15 @@ class _DecoderFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         grads = [None] * len(params)
         layer_in = [a1, a2, a3]
-        gp = g.contiguous().float().permute(0, 2, 3, 1).contiguous()  # last layer has no activation; NHWC
+        gp = g.contiguous().float()           # last layer has no activation; (F, C, 64, 64) NCHW, later layers NHWC
         for li in (3, 2, 1):
             x, cm = layer_in[li - 1], ctx.maps[li - 1]
             cin, cout, k = ws[li].shape[0], ws[li].shape[1], ws[li].shape[2]
             T = cm.TH
+            cpad = _cpad(cout)
+            G, db = _unshuffle(gp, cm.RA, cm.RB, cpad, nchw=(li == 3))  # (F, RA, RB, cpad) + bias gradient
             if need[2 + 2 * li + 1]:
-                grads[2 * li + 3] = gp.sum((0, 1, 2))
-            cpad = (4 * cout + 7) // 8 * 8
-            G = _unshuffle(gp, cm.RA, cm.RB, cpad)                     # (F, RA, RB, cpad)
+                grads[2 * li + 3] = db
             sc = grad_scales(G)
             if need[2 + 2 * li]:
                 dwm = conv_wgrad(x, G.reshape(-1, cpad), F_, 4 * cout, cm, sc)

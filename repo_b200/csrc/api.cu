@@ -945,6 +945,21 @@ int repo_b200_tia_mix_bwd(const float* t_out, const float* d_out, const float* w
   return 0;
 }
 
+int repo_b200_grad_unshuffle(const float* g, int g_nchw, float* G, float* db, int frames, int RA, int RB, int Ho, int Wo,
+                             int channels, int cpad, void* stream) {
+  if (!g || !G || !db) return fail(-1, "grad_unshuffle: NULL pointer");
+  if (cpad < 4 * channels || cpad > 256 || (256 % cpad)) return fail(-1, "grad_unshuffle: cpad must divide 256 and hold 4*channels");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaMemsetAsync(db, 0, channels * sizeof(float), st));
+  const long long rows = (long long)frames * RA * RB;
+  if (rows <= 0) return 0;
+  const long long total = rows * cpad;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)std::max(1, sm_count()) * 16);
+  grad_unshuffle_kernel<<<blocks, 256, 0, st>>>(g, g_nchw, G, db, rows, RA, RB, Ho, Wo, channels, cpad);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int repo_b200_im2col(const float* input, float* col, int frames, const int* map, void* stream) {
   if (!input || !col || !map) return fail(-1, "im2col: NULL pointer");
   ConvMap cm;

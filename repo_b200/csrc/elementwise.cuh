@@ -221,4 +221,40 @@ __global__ void __launch_bounds__(256) tia_mix_bwd_kernel(const float* __restric
   }
 }
 
+// Backward glue of the sub-pixel transposed convolution (conv.py): G[(f,a,b), (py,px,c)] = g[f, 2a+py, 2b+px, c]
+// (zero outside the Ho x Wo grid and in the channel padding up to cpad), plus the bias gradient db[c] = sum g — one
+// pass over the gradient instead of pad / permute / contiguous / sum.  Thread t owns column n = t % cpad (block and
+// grid strides are multiples of cpad), so its partial bias sum stays in a register.
+__global__ void __launch_bounds__(256) grad_unshuffle_kernel(const float* __restrict__ g, int g_nchw, float* __restrict__ G,
+                                                             float* __restrict__ db /* C, zeroed */, long long rows /* F*RA*RB */,
+                                                             int RA, int RB, int Ho, int Wo, int C, int cpad) {
+  const long long total = rows * cpad;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int n = threadIdx.x % cpad;   // blockDim.x % cpad == 0
+  const int cls = n / C, c = n - cls * C, py = cls >> 1, px = cls & 1;
+  const bool live = n < 4 * C;
+  float acc = 0.f;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const long long row = idx / cpad;
+    const int b = (int)(row % RB);
+    const long long t = row / RB;
+    const int a = (int)(t % RA);
+    const long long fr = t / RA;
+    const int y = 2 * a + py, x = 2 * b + px;
+    float v = 0.f;
+    if (live && y < Ho && x < Wo)
+      v = g_nchw ? g[((fr * C + c) * Ho + y) * Wo + x] : g[((fr * Ho + y) * Wo + x) * C + c];
+    G[idx] = v;
+    acc += v;
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < cpad && live) {
+    float v = 0.f;
+    for (int i = threadIdx.x; i < 256; i += cpad) v += red[i];
+    atomicAdd(db + c, v);
+  }
+}
+
 }  // namespace rb
