@@ -168,7 +168,7 @@ int repo_b200_tanh_normal_entropy_bwd(const float* mean, const float* std_dev, c
                                       int samples, void* stream);
 
 /* ---- conv_gemm: one Conv2d / ConvTranspose2d layer as an implicit GEMM on tcgen05 (VisualEncoder encoder.py:21-41,
- * VisualObservationModel decoder.py:28-48), also used for the data gradients of those layers.  `map` is the 27-int
+ * VisualObservationModel decoder.py:28-48), also used for the data gradients of those layers.  `map` is the 28-int
  * ConvMap of repo_b200/csrc/vm.cuh (row grid, input layout/dims, tap window, input/output pixel maps, relu, shuffle);
  * w_mat is (n_total, ntaps*C) with columns ordered (tap, cin); with map.shuffle the n_total = 4*cout features are the
  * (py, px, cout) sub-pixel classes of a stride-2 transposed convolution.  relu_mask (nullable, laid out like out)

@@ -4,8 +4,8 @@ forward  : the persistent observe kernel, which additionally stashes the per-ste
 backward : `repo_b200_observe_bwd` — one persistent reverse-time kernel (bwd.cuh) that carries the
            recurrent gradients (belief, state) through the GRU / Gaussian heads and emits the gradient
            of every pre-activation per (t,b);
-weights  : dW = dpre^T @ layer_input are plain batched GEMMs over those tensors (cuBLAS via
-           torch.matmul — library GEMMs, not part of the fused recurrence), bias grads are sums.
+weights  : dW = dpre^T @ layer_input over all (t,row) samples runs on the tcgen05 weight-gradient kernel
+           (`conv.wgrad_gemm`: same fp16 hi/lo arithmetic, contraction over rows); bias grads are sums.
 
 Reproduces what autograd gives the reference for rssm.py:116-133: gradients reach every
 TransitionModel parameter via BPTT over all T-1 steps and reach `observations` (the encoder);
@@ -20,6 +20,15 @@ from typing import List, Optional
 import torch
 
 from . import _lib, ops
+
+
+def _wgrad(dpre, x):
+    """dW = dpre^T @ x.  Feature counts that are multiples of 4 run on the tcgen05 weight-gradient kernel; the 1-wide
+    scalar heads (a 1 x K result) stay a library GEMV."""
+    if dpre.shape[1] % 4 == 0:
+        from .conv import wgrad_gemm
+        return wgrad_gemm(dpre, x)
+    return dpre.t() @ x
 
 PARAM_KEYS = [k for _, k in ops._RSSM_KEYS]
 
@@ -90,7 +99,7 @@ class ObserveFn(torch.autograd.Function):
 
         def lin(wkey, bkey, dpre, inp):
             if need[wkey]:
-                gp[wkey] = flat(dpre).t() @ flat(inp)
+                gp[wkey] = _wgrad(flat(dpre), flat(inp))
             if need[bkey]:
                 gp[bkey] = flat(dpre).sum(0)
 
@@ -183,7 +192,7 @@ class ImagineFn(torch.autograd.Function):
 
         def lin(wkey, bkey, dpre, inp):
             if need[wkey]:
-                gp[wkey] = flat(dpre).t() @ flat(inp)
+                gp[wkey] = _wgrad(flat(dpre), flat(inp))
             if need[bkey]:
                 gp[bkey] = flat(dpre).sum(0)
 
@@ -262,7 +271,7 @@ class MlpFn(torch.autograd.Function):
         dpre = dh[:L_layers - 1] + [g_out]
         for i in range(L_layers):
             need_w, need_b = ctx.needs_input_grad[4 + 2 * i], ctx.needs_input_grad[5 + 2 * i]
-            grads.append(dpre[i].t() @ inputs[i] if need_w else None)
+            grads.append(_wgrad(dpre[i], inputs[i]) if need_w else None)
             grads.append(dpre[i].sum(0) if need_b else None)
         gb = dx[:, :d.belief] if (need_x and ctx.needs_input_grad[2]) else None
         gs = dx[:, d.belief:] if (need_x and ctx.needs_input_grad[3]) else None

@@ -32,7 +32,7 @@ import torch.nn.functional as F
 from . import _lib
 
 _MAP_FIELDS = ("enabled RA RB in_nchw C H W TH TW tap0 ntaps sy sx dy dx y0 x0 "
-               "out_nchw Ho Wo osy osx oy0 ox0 relu accumulate shuffle").split()
+               "out_nchw Ho Wo osy osx oy0 ox0 relu accumulate shuffle pix").split()
 
 
 @dataclass
@@ -40,7 +40,7 @@ class ConvMap:
     RA: int; RB: int; in_nchw: int; C: int; H: int; W: int; TH: int; TW: int
     sy: int; sx: int; dy: int; dx: int; y0: int = 0; x0: int = 0
     out_nchw: int = 0; Ho: int = 0; Wo: int = 0; osy: int = 1; osx: int = 1; oy0: int = 0; ox0: int = 0
-    relu: int = 0; accumulate: int = 0; tap0: int = 0; ntaps: int = 0; enabled: int = 1; shuffle: int = 0
+    relu: int = 0; accumulate: int = 0; tap0: int = 0; ntaps: int = 0; enabled: int = 1; shuffle: int = 0; pix: int = 0
 
     def carray(self, **over):
         vals = {f: getattr(self, f) for f in _MAP_FIELDS}
@@ -133,6 +133,42 @@ def conv_wgrad(x, grad_rows, frames, n_total, cmap: ConvMap, scales=None):
                                          cmap.carray(), int(_is_hl(x)), _stream())
     _lib.check(rc, "repo_b200_conv_wgrad")
     return dw
+
+
+def wgrad_gemm(dpre, x):
+    """dW (n, k) = dpre^T @ x for 2-D fp32 operands — the weight gradient of a Linear layer over all (t, row) samples —
+    on the tcgen05 weight-gradient kernel (fp16 hi/lo three-product arithmetic, gradient operand rescaled by a power of
+    two).  `x` may be a column window of a wider row-major matrix (e.g. a slice of the activation stash); n > 256 is
+    processed in 256-column slices of dpre."""
+    rows, n = dpre.shape
+    k = x.shape[1]
+    if x.shape[0] != rows:
+        raise RuntimeError("wgrad_gemm: row counts differ")
+    if rows == 0:
+        return torch.zeros(n, k, device=dpre.device, dtype=torch.float32)
+    dpre = _need_cuda(dpre, "dpre")
+    if x.stride(1) != 1 or (x.stride(0) % 4) or (x.data_ptr() % 16) or (k % 4):
+        kp = (k + 3) // 4 * 4                      # repack: 16-byte aligned rows (zero columns do not change dW[:, :k])
+        xp = torch.zeros(rows, kp, device=x.device, dtype=torch.float32)
+        xp[:, :k] = x
+        x = xp
+    kk = x.shape[1]
+    cmap = ConvMap(RA=1, RB=1, in_nchw=0, C=kk, H=1, W=1, TH=1, TW=1, sy=1, sx=1, dy=1, dx=1, Ho=1, Wo=1, pix=x.stride(0))
+    sc = grad_scales(dpre)
+    L = _lib.lib()
+    outs = []
+    for n0 in range(0, n, 256):
+        nn_ = min(256, n - n0)
+        npad = (nn_ + 3) // 4 * 4
+        if npad != nn_ or (n % 4):
+            raise RuntimeError("wgrad_gemm: output features must be a multiple of 4")
+        dw = torch.empty(nn_, kk, device=x.device, dtype=torch.float32)
+        g_view = dpre[:, n0:]
+        rc = L.repo_b200_conv_wgrad(_p(x), C.c_void_p(g_view.data_ptr()), _p(sc), _p(dw), rows, nn_, n, cmap.carray(), 0, _stream())
+        _lib.check(rc, "repo_b200_conv_wgrad")
+        outs.append(dw)
+    dw = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+    return dw[:, :k] if kk != k else dw
 
 
 def im2col(x, frames, cmap: ConvMap):

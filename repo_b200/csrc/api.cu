@@ -778,9 +778,11 @@ int repo_b200_conv_gemm(const void* input_, const float* w_mat, const float* bia
   float* out = static_cast<float*>(out_);
   if (!input || !w_mat || !out || !map || !ws) return fail(-1, "conv: NULL pointer");
   ConvMap cm;
-  static_assert(sizeof(ConvMap) == 27 * sizeof(int), "ConvMap layout");
+  static_assert(sizeof(ConvMap) == 28 * sizeof(int), "ConvMap layout");
   std::memcpy(&cm, map, sizeof(cm));
   cm.enabled = 1;
+  if (cm.pix == 0) cm.pix = cm.C;
+  if (cm.pix < cm.C) return fail(-1, "conv: pixel stride %d < channels %d", cm.pix, cm.C);
   if (cm.tap0 != 0 || cm.ntaps != cm.TH * cm.TW || cm.accumulate) return fail(-1, "conv: partial tap windows are not supported");
   if (cm.ntaps < 1 || cm.C < 1 || n_total < 1 || n_total > 256 * kMaxRowsJobs) return fail(-1, "conv: bad sizes");
   if (cm.shuffle && (n_total % 4)) return fail(-1, "conv: sub-pixel store needs 4*cout features");
@@ -823,7 +825,7 @@ int repo_b200_conv_gemm(const void* input_, const float* w_mat, const float* bia
   P.cout = cm.shuffle ? n_total / 4 : n_total;
   // split-activation (fp16 hi/lo plane) operands: bit0 input, bit1 output, bit2 relu mask
   P.in_hl = hl_flags & 1; P.out_hl = (hl_flags >> 1) & 1; P.mask_hl = (hl_flags >> 2) & 1;
-  if (P.in_hl && (cm.in_nchw || (cm.C & 7) || scales)) return fail(-1, "conv: HL input needs NHWC, C %% 8 == 0 and no operand scaling");
+  if (P.in_hl && (cm.in_nchw || (cm.C & 7) || cm.pix != cm.C || scales)) return fail(-1, "conv: HL input needs NHWC, C %% 8 == 0 and no operand scaling");
   if ((P.out_hl || P.mask_hl) && (cm.out_nchw || (P.cout & 15) || (P.NP & 15)))
     return fail(-1, "conv: HL output / mask needs an NHWC output with cout %% 16 == 0");
   if (P.mask_hl && !relu_mask) return fail(-1, "conv: mask_hl without a mask");
@@ -857,6 +859,8 @@ int repo_b200_conv_wgrad(const void* input_, const float* grad_rows, const float
   ConvMap cm;
   std::memcpy(&cm, map, sizeof(cm));
   cm.enabled = 1;
+  if (cm.pix == 0) cm.pix = cm.C;
+  if (cm.pix < cm.C) return fail(-1, "conv: pixel stride %d < channels %d", cm.pix, cm.C);
   if (cm.tap0 != 0 || cm.ntaps != cm.TH * cm.TW) return fail(-1, "conv_wgrad: partial tap windows are not supported");
   if (cm.ntaps < 1 || cm.C < 1 || n_total < 1 || n_total > 256 || (n_total & 3) || g_ld < n_total || (g_ld & 3))
     return fail(-1, "conv_wgrad: n_total must be a multiple of 4 and <= 256 (got %d, row stride %d)", n_total, g_ld);
@@ -873,7 +877,7 @@ int repo_b200_conv_wgrad(const void* input_, const float* grad_rows, const float
   P.n_rows = (int)rows; P.K = K; P.k16 = cdiv(K, 16); P.n_total = n_total; P.g_ld = g_ld;
   P.NP = cdiv(n_total, 16) * 16;
   P.x_hl = input_hl ? 1 : 0;
-  if (P.x_hl && (cm.in_nchw || (cm.C & 7))) return fail(-1, "conv_wgrad: HL input needs NHWC and C %% 8 == 0");
+  if (P.x_hl && (cm.in_nchw || (cm.C & 7) || cm.pix != cm.C)) return fail(-1, "conv_wgrad: HL input needs NHWC and C %% 8 == 0");
   P.x_lo_bytes = (long long)frames * cm.H * cm.W * cm.C * 2;
   const int n_ent = conv_table_entries(cm, P.k16, P.x_hl);
   if (n_ent > 2048) return fail(-1, "conv_wgrad: K = %d needs %d gather-table entries (max 2048)", K, n_ent);
@@ -964,6 +968,7 @@ int repo_b200_im2col(const float* input, float* col, int frames, const int* map,
   if (!input || !col || !map) return fail(-1, "im2col: NULL pointer");
   ConvMap cm;
   std::memcpy(&cm, map, sizeof(cm));
+  if (cm.pix == 0) cm.pix = cm.C;
   const long long rows = (long long)frames * cm.RA * cm.RB;
   if (rows <= 0) return 0;
   const long long total = rows * cm.ntaps * cm.C;

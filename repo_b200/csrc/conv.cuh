@@ -63,7 +63,7 @@ struct ConvTap {
   int off;         // BYTE offset from the row base
   short tdy, tdx;  // tap displacement in pixels (sentinel -30000 beyond K: fails the bounds test)
 };
-__host__ __device__ inline bool conv_quads(const ConvMap& cm) { return !cm.in_nchw && (cm.C & 3) == 0; }
+__host__ __device__ inline bool conv_quads(const ConvMap& cm) { return !cm.in_nchw && (cm.C & 3) == 0 && (cm.pix & 3) == 0; }
 // entries: one per k (scalar path), per channel quad (fp32 NHWC), or per channel oct (HL input, C % 8 == 0)
 __host__ __device__ inline int conv_table_entries(const ConvMap& cm, int k16, int in_hl = 0) {
   return in_hl ? k16 * 2 : (conv_quads(cm) ? k16 * 4 : k16 * 16);
@@ -80,7 +80,7 @@ __device__ __forceinline__ void conv_build_table(ConvTap* table, const ConvMap& 
       const int ty = tap / cm.TW, tx = tap - ty * cm.TW;
       e.tdy = (short)(ty * cm.dy);
       e.tdx = (short)(tx * cm.dx);
-      e.off = esz * (cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.C + ci);
+      e.off = esz * (cm.in_nchw ? (ci * cm.H + e.tdy) * cm.W + e.tdx : (e.tdy * cm.W + e.tdx) * cm.pix + ci);
     }
     table[i] = e;
   }
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
           const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
           ay[j] = row < P.n_rows ? a * cm.sy + cm.y0 : -30000;
           bx[j] = b * cm.sx + cm.x0;
-          const long long e = (((long long)fr * cm.H + ay[j]) * cm.W + bx[j]) * cm.C * 2;
+          const long long e = (((long long)fr * cm.H + ay[j]) * cm.W + bx[j]) * cm.pix * 2;
           base[j] = opaque(reinterpret_cast<uint64_t>(P.x) + (row < P.n_rows ? e : 0));
         }
       };
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
         ay[j] = row < P.n_rows ? a * cm.sy + cm.y0 : -30000;   // rows past the end fail every bounds test
         bx[j] = b * cm.sx + cm.x0;
         const long long e = cm.in_nchw ? ((long long)fr * cm.C * cm.H + ay[j]) * cm.W + bx[j]
-                                       : (((long long)fr * cm.H + ay[j]) * cm.W + bx[j]) * cm.C;
+                                       : (((long long)fr * cm.H + ay[j]) * cm.W + bx[j]) * cm.pix;
         base[j] = opaque(reinterpret_cast<uint64_t>(P.x + (row < P.n_rows ? e : 0)));
       }
       for (int c0 = 0; c0 < P.k16; c0 += P.kc16) {
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
       const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
       const int ay = valid ? a * cm.sy + cm.y0 : -30000, bx = b * cm.sx + cm.x0;
       const long long e0 = cm.in_nchw ? ((long long)fr * cm.C * cm.H + ay) * cm.W + bx
-                                      : (((long long)fr * cm.H + ay) * cm.W + bx) * cm.C;
+                                      : (((long long)fr * cm.H + ay) * cm.W + bx) * cm.pix;
       const uint64_t base = opaque(reinterpret_cast<uint64_t>(P.x + (valid ? e0 : 0)));
       mbar_wait(bar_empty + 8 * slot, phase ^ 1);
       uint8_t* sa = ring + (size_t)slot * P.stage_bytes;

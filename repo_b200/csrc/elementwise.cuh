@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ i
     const int iy = a * cm.sy + ty * cm.dy + cm.y0, ix = b * cm.sx + tx * cm.dx + cm.x0;
     float v = 0.f;
     if (iy >= 0 && iy < cm.H && ix >= 0 && ix < cm.W)
-      v = cm.in_nchw ? in[(((size_t)fr * cm.C + ci) * cm.H + iy) * cm.W + ix] : in[(((size_t)fr * cm.H + iy) * cm.W + ix) * cm.C + ci];
+      v = cm.in_nchw ? in[(((size_t)fr * cm.C + ci) * cm.H + iy) * cm.W + ix] : in[(((size_t)fr * cm.H + iy) * cm.W + ix) * cm.pix + ci];
     col[idx] = v;
   }
 }

@@ -82,6 +82,8 @@ struct ConvMap {
   int out_nchw, Ho, Wo, osy, osx, oy0, ox0;  // output pixel (a*osy + oy0, b*osx + ox0) on an Ho x Wo grid
   int relu, accumulate;            // store: out = (accumulate ? out : 0) + acc + bias, then ReLU
   int shuffle;                     // conv.cuh only: features are (py, px, cout) sub-pixel classes of a 2x finer output grid
+  int pix;                         // NHWC input: elements between neighbouring pixels (>= C; lets a GEMM read a column
+                                   // window of a wider row-major matrix).  0 = C.
 };
 
 struct VmParams {
