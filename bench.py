@@ -334,6 +334,23 @@ def run_gpu(a):
                     lat[0], lat[1], lat[2] = agent.update_latent_and_select_action(lat[0], lat[1], lat[2], frame)
 
                 upd["acting_step_ms"] = timeit(act_step, 20)
+                # the same three calls captured once and replayed as CUDA graphs (repo_b200/graphs.py)
+                g_act = agent.graphed_acting(frame)
+
+                def act_graph():
+                    lat[0], lat[1], lat[2] = g_act(lat[0], lat[1], lat[2], frame)
+
+                upd["acting_step_graphed_ms"] = timeit(act_graph, 50)
+            g_wm, g_ac = agent.graphed(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"])
+            gs = {}
+
+            def wm_graph():
+                gs["b"], gs["s"] = g_wm(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"])
+
+            upd[algo + "_world_model_update_graphed_ms"] = timeit(wm_graph, 10)
+            if algo == "repo":
+                upd["actor_critic_update_graphed_ms"] = timeit(lambda: g_ac(gs["b"].flatten(0, 1), gs["s"].flatten(0, 1)), 10)
+            del g_wm, g_ac
             del agent
         ac_ms = upd["actor_critic_update_ms"]
         default_shape = {"imagine_2450x14_ms": img_ms, "imagine_steps_per_s": 2450 * 14 / img_ms * 1e3,
@@ -341,7 +358,8 @@ def run_gpu(a):
                          **upd, "actor_critic_update_steps_per_s": 2450 * 14 / ac_ms * 1e3,
                          "note": "world_model_update = Agent.train_dynamics on a (50,50,3,64,64) batch: conv encoder + observe + conv "
                                  "decoder + reward/KL losses, all backward passes, clip + Adam; actor_critic_update = "
-                                 "Agent.train_actor_critic on the 2450 resulting start rows incl. both Adam steps"}
+                                 "Agent.train_actor_critic on the 2450 resulting start rows incl. both Adam steps; *_graphed_ms = the "
+                                 "same call captured once as a CUDA graph and replayed (Agent.graphed)"}
 
     if world > 1:
         dist.barrier()

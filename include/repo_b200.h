@@ -193,7 +193,8 @@ int repo_b200_conv_wgrad(const void* input, const float* grad_rows, const float*
                          int n_total, int g_ld, const int* map, int input_hl, void* stream);
 
 /* scales[which] = 2^floor(log2(target / max|x|)) and scales[2] = 1 / (scales[0] * scales[1]) in one read-only pass
- * (the `scales` triple of conv_gemm / conv_wgrad; initialise it to {1, 1, 1}).  scratch = 8 zeroed device bytes,
+ * (the `scales` triple of conv_gemm / conv_wgrad; initialise scales[0..2] to {1, 1, 1}); scales[3..5] receive the same
+ * triple with the two operand slots swapped, so `scales` must hold 6 floats.  scratch = 8 zeroed device bytes,
  * left zeroed again.  No host synchronisation. */
 int repo_b200_pow2_scale(const float* x, long long n, float target, int which, float* scales, void* scratch, void* stream);
 
@@ -225,6 +226,11 @@ int repo_b200_sqnorm_accumulate(const float* grad, long long n, float* sqnorm, v
 int repo_b200_adam_clip_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                              const float* sqnorm, float max_norm, float lr, float beta1, float beta2, float eps,
                              int step, void* stream);
+/* same update with the step count kept on the device (*step_dev is incremented, then used for the bias corrections):
+ * safe to capture in a CUDA graph and replay. */
+int repo_b200_adam_clip_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                 const float* sqnorm, float max_norm, float lr, float beta1, float beta2, float eps,
+                                 int* step_dev, void* stream);
 
 /* ---- replay gather: the index bookkeeping of SequenceReplayBuffer.sample (common/buffers.py:156-166) after
  * `np.random.choice` (start_inds, drawn on the host so the RNG stream is the reference's), fused with

@@ -72,13 +72,13 @@ _SCRATCH = {}
 
 
 def grad_scales(g):
-    """Device triple [1, s_g, 1/s_g] with s_g = 2^floor(log2(2^14 / max|g|)): lifts a gradient tensor into fp16's
+    """Device floats [1, s_g, 1/s_g | s_g, 1, 1/s_g] (second triple: see `_as_input_side`) with s_g = 2^floor(log2(2^14 / max|g|)): lifts a gradient tensor into fp16's
     normal range before the hi/lo split (gradients sit far below fp16's 6e-5 normal threshold, where the split has no
     mantissa left).  Activations and weights are O(1e-2..1) and keep scale 1.  One fused read-only pass, no host sync."""
     dev = g.device
     if dev not in _SCRATCH:
         _SCRATCH[dev] = torch.zeros(2, dtype=torch.int32, device=dev)
-    scales = torch.ones(3, dtype=torch.float32, device=dev)
+    scales = torch.ones(6, dtype=torch.float32, device=dev)
     g = g.contiguous()
     rc = _lib.lib().repo_b200_pow2_scale(_p(g), g.numel(), 16384.0, 1, _p(scales), _p(_SCRATCH[dev]), _stream())
     _lib.check(rc, "repo_b200_pow2_scale")
@@ -87,7 +87,7 @@ def grad_scales(g):
 
 def _as_input_side(scales):
     """[1, s, 1/s] -> [s, 1, 1/s]: the same gradient scale when the gradient is the GATHERED operand (data gradients)."""
-    return scales[[1, 0, 2]]
+    return scales[3:]
 
 
 def hl_empty(shape, device):

@@ -755,6 +755,19 @@ int repo_b200_adam_clip_step(float* param, float* grad, float* exp_avg, float* e
   return 0;
 }
 
+int repo_b200_adam_clip_step_dev(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n, const float* sqnorm,
+                                 float max_norm, float lr, float beta1, float beta2, float eps, int* step_dev, void* stream) {
+  if (n < 0 || !step_dev) return fail(-1, "adam: bad size / NULL step counter");
+  if (n == 0) return 0;
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return fail(-1, "adam: NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  adam_step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  adam_clip_dev_kernel<<<blocks, 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, sqnorm, max_norm, lr, beta1, beta2, eps, step_dev);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ---- (transposed) convolution as implicit GEMM on the vm machine
 // ---- implicit-GEMM convolution (conv.cuh).  Workspace = packed fp16 hi/lo weights + padded bias.
 static void conv_geometry(int K, int n_total, int& k16, int& NP, int& n_tiles) {

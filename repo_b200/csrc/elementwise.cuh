@@ -112,8 +112,9 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ i
 }
 
 // Power-of-two operand scales for the gradient convolutions (conv.cuh): one read-only pass finds max|x|, the
-// last block to finish turns it into s = 2^floor(log2(target / max|x|)).  scales = [s_a, s_b, 1/(s_a*s_b)];
-// `which` selects the slot this tensor fills (the other one must already hold its value, 1 by default).
+// last block to finish turns it into s = 2^floor(log2(target / max|x|)).  scales = [s_a, s_b, 1/(s_a*s_b)] followed by the
+// same triple with a and b swapped (6 floats); `which` selects the slot this tensor fills (the other one must already
+// hold its value, 1 by default).
 __global__ void __launch_bounds__(256) absmax_scale_kernel(const float* __restrict__ x, long long n, unsigned* scratch /* [2]: max bits, blocks done */,
                                                            float target, float* __restrict__ scales, int which) {
   float m = 0.f;
@@ -141,6 +142,10 @@ __global__ void __launch_bounds__(256) absmax_scale_kernel(const float* __restri
       const float s = exp2f(floorf(log2f(target / amax)));
       scales[which] = s;
       scales[2] = 1.f / (s * scales[1 - which]);
+      // second triple with the operand slots swapped (the same tensor used as the other operand)
+      scales[3 + (1 - which)] = s;
+      scales[3 + which] = scales[1 - which];
+      scales[5] = scales[2];
       scratch[0] = 0u;
       scratch[1] = 0u;   // ready for the next call on this stream
     }

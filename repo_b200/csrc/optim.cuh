@@ -48,4 +48,29 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, f
   }
 }
 
+// Graph-safe variant: the step count lives on the device.  `adam_step_inc_kernel` (one thread) advances it, then every
+// thread of the update derives the bias corrections from it, so a captured CUDA graph replays with the right step.
+__global__ void adam_step_inc_kernel(int* step) { *step += 1; }
+
+__global__ void __launch_bounds__(256) adam_clip_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                            float* __restrict__ v, long long n, const float* __restrict__ sqnorm,
+                                                            float max_norm, float lr, float b1, float b2, float eps,
+                                                            const int* __restrict__ step) {
+  float coef = 1.f;
+  if (sqnorm && max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(*sqnorm) + 1e-6f));
+  const double t = (double)*step;
+  const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  const float step_size = lr / bc1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * coef;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    g[i] = gi;
+    p[i] -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
 }  // namespace rb

@@ -34,7 +34,7 @@ class FlatAdam:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.sqnorm = torch.zeros(1, device=dev, dtype=torch.float32)
-        self.step_count = 0
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)  # step count on the device: CUDA-graph safe
         off = 0
         self.offsets = []
         for p in self.params:
@@ -69,16 +69,24 @@ class FlatAdam:
         L = _lib.lib()
         s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         p = lambda t: C.c_void_p(t.data_ptr())
-        self.step_count += 1
         sq = None
         if self.max_grad_norm is not None:
             self.sqnorm.zero_()
             _lib.check(L.repo_b200_sqnorm_accumulate(p(self.flat_grad), self.numel, p(self.sqnorm), s), "repo_b200_sqnorm_accumulate")
             sq = p(self.sqnorm)
-        rc = L.repo_b200_adam_clip_step(p(self.flat), p(self.flat_grad), p(self.exp_avg), p(self.exp_avg_sq), self.numel, sq,
-                                        float(self.max_grad_norm or 0.0), float(self.lr), float(self.betas[0]),
-                                        float(self.betas[1]), float(self.eps), self.step_count, s)
-        _lib.check(rc, "repo_b200_adam_clip_step")
+        rc = L.repo_b200_adam_clip_step_dev(p(self.flat), p(self.flat_grad), p(self.exp_avg), p(self.exp_avg_sq), self.numel, sq,
+                                            float(self.max_grad_norm or 0.0), float(self.lr), float(self.betas[0]),
+                                            float(self.betas[1]), float(self.eps), p(self.step_dev), s)
+        _lib.check(rc, "repo_b200_adam_clip_step_dev")
+
+    @property
+    def step_count(self) -> int:
+        """Number of steps taken (reads the device counter: synchronises; checkpoints / tests only)."""
+        return int(self.step_dev.item())
+
+    @step_count.setter
+    def step_count(self, v: int):
+        self.step_dev.fill_(int(v))
 
     def grad_norm(self) -> torch.Tensor:
         """Global gradient norm seen by the last clipped step (device scalar; no sync)."""

@@ -26,6 +26,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Dict, Optional
 
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -156,9 +158,29 @@ class Agent:
                 "model": FlatAdam(self.model_params, c.model_lr, max_grad_norm=c.grad_clip_norm),
                 "actor": FlatAdam(self.actor_model.parameters(), c.actor_lr, max_grad_norm=c.grad_clip_norm),
                 "value": FlatAdam(self.value_model.parameters(), c.value_lr, max_grad_norm=c.grad_clip_norm),
-                "beta": torch.optim.Adam([self.log_beta], lr=c.beta_lr),
+                "beta": torch.optim.Adam([self.log_beta], lr=c.beta_lr, capturable=True),  # device-side step: graph safe
             }
         return self._opt
+
+    # ------------------------------------------------------------------ CUDA graphs
+    def graphed(self, obs, actions, rewards, nonterms):
+        """Capture `train_dynamics` and `train_actor_critic` (optimiser steps included) for batches shaped like the
+        example; returns (wm_step, ac_step): `beliefs, states = wm_step(obs, actions, rewards, nonterms)` and
+        `ac_step(beliefs.flatten(0, 1), states.flatten(0, 1))`, each ONE graph launch.  Outputs and `self.logs`
+        entries are static tensors overwritten by every replay."""
+        from .graphs import GraphedStep
+        self.optimizers()
+        wm = GraphedStep(lambda o, a, r, n: self.train_dynamics(o, a, r, n), [obs, actions, rewards, nonterms])
+        b, s = wm.static_outputs
+        ac = GraphedStep(lambda bb, ss: self.train_actor_critic(bb, ss), [b.flatten(0, 1), s.flatten(0, 1)])
+        return wm, ac
+
+    def graphed_acting(self, obs):
+        """Capture `update_latent_and_select_action` for one frame (B=1): `belief, state, action = act(belief, state,
+        action, obs)` is one graph launch."""
+        from .graphs import GraphedStep
+        lat = list(self.init_latent_and_action())
+        return GraphedStep(lambda b, s, a, o: self.update_latent_and_select_action(b, s, a, o), [*lat, obs])
 
     # ------------------------------------------------------------------ acting path
     def init_latent_and_action(self):
@@ -308,7 +330,9 @@ class Agent:
                 reward_preds = bottle(self.reward_model, (imag_b, imag_s))
                 value_preds = bottle(self.value_model, (imag_b, imag_s))
         action_entropy = self.actor_model.get_action_dist(imag_b.flatten(0, 1), imag_s.flatten(0, 1)).entropy(eps_entropy).mean()
-        latent_entropy = torch.distributions.Independent(torch.distributions.Normal(imag_m, imag_sd), 1).entropy().mean()
+        # Independent(Normal(mean, std), 1).entropy().mean() (dreamer.py:325-327), closed form: torch.distributions'
+        # argument validation synchronises with the host, which a CUDA-graph capture forbids
+        latent_entropy = (0.5 + 0.5 * math.log(2 * math.pi) + imag_sd.log()).sum(-1).mean()
         discounts = c.gamma * torch.ones_like(reward_preds)
         returns = losses.lambda_return(reward_preds[:-1], value_preds[:-1], discounts[:-1], value_preds[-1], c.gae_lambda)
         actor_loss = losses.actor_loss(returns, action_entropy, latent_entropy, c.action_ent_coef, c.latent_ent_coef)
