@@ -181,9 +181,13 @@ size_t repo_b200_conv_workspace_bytes(int k, int n_total);
  * exact operand pair the tensor cores consume), each laid out like the fp32 tensor, lo plane directly after the hi
  * plane.  bit0: input, bit1: output, bit2: relu_mask.  Used for the activations between layers: the producing
  * epilogue splits once and every consumer (next layer, weight gradient) gathers with plain 16-byte copies. */
+/* dense_opts (nullable, 4 ints) turns the same kernel into the dense layers of the MLP heads (actor_critic.py:20-26,76-83,
+ * decoder.py:189-195) and their data gradients: [0] apply ELU to the output (instead of map.relu), [1] treat relu_mask
+ * as the OUTPUT h of an ELU layer and multiply by its derivative (h > 0 ? 1 : h + 1), [2] row stride of `out`, [3] row
+ * stride of `relu_mask` (plain GEMM maps only; lets both be column windows of a wider row-major activation stash). */
 int repo_b200_conv_gemm(const void* input, const float* w_mat, const float* bias, const void* relu_mask,
                         const float* scales, void* out, int frames, int n_total, const int* map, int hl_flags,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        const int* dense_opts, void* workspace, size_t workspace_bytes, void* stream);
 
 /* weight gradient of the same implicit GEMM: dw (n_total, ntaps*C) = grad_rows^T @ gather(input), grad_rows being the
  * (frames*RA*RB, g_ld) output-gradient rows (n_total <= 256 columns used).  Row slices are summed with fp32 atomics

@@ -115,7 +115,7 @@ def lib():
     L.repo_b200_adam_clip_step_dev.restype = ci
     L.repo_b200_conv_workspace_bytes.argtypes = [ci, ci]
     L.repo_b200_conv_workspace_bytes.restype = sz
-    L.repo_b200_conv_gemm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, C.POINTER(ci), ci, vp, sz, vp]
+    L.repo_b200_conv_gemm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, C.POINTER(ci), ci, C.POINTER(ci), vp, sz, vp]
     L.repo_b200_conv_gemm.restype = ci
     L.repo_b200_conv_wgrad.argtypes = [vp, vp, vp, vp, ci, ci, ci, C.POINTER(ci), ci, vp]
     L.repo_b200_conv_wgrad.restype = ci

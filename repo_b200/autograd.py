@@ -224,9 +224,15 @@ def imagine(model, prev_belief, prev_state, policy, horizon, eps_action, eps_pri
     return list(outs), actions
 
 
+_DENSE_MIN_ROWS = 1024   # from here on one tcgen05 GEMM launch per layer beats the fused small-batch kernels
+
+
 class MlpFn(torch.autograd.Function):
-    """fc1..fcL on [belief|state] (RewardModel / ValueModel / ActorModel trunk): forward on the layer machine
-    with the hidden activations stashed, backward on the SIMT chain kernel + weight-gradient GEMMs."""
+    """fc1..fcL on [belief|state] (RewardModel / ValueModel / ActorModel trunk).  Small batches: forward on the layer
+    machine with the hidden activations stashed, backward on the SIMT chain kernel.  From `_DENSE_MIN_ROWS` rows (the
+    (H-1)*N imagined rows of an actor-critic update) every layer — forward and data gradient — is one dense tcgen05 GEMM
+    (`conv.dense_layer`: bias + ELU/ReLU, or the activation derivative, fused in the epilogue; activations written
+    straight into the stash).  Weight gradients: `conv.wgrad_gemm`."""
 
     @staticmethod
     def forward(ctx, act, out_f, belief, state, *params):
@@ -235,46 +241,79 @@ class MlpFn(torch.autograd.Function):
         N, D, S, Hd = belief.shape[0], belief.shape[1], state.shape[1], params[0].shape[0]
         d = _lib.Dims(D, S, 1, Hd, 1)
         lib = _lib.lib()
-        keep = ops._Keep()
-        M = ops.mlp_struct({k: v.detach() for k, v in named.items()}, L_layers, keep, "mlp")
         b, s = ops._chk(belief.detach(), "belief", (N, D)), ops._chk(state.detach(), "state", (N, S))
         out = torch.empty(N, out_f, device=b.device, dtype=torch.float32)
         stash = torch.empty(N, (L_layers - 1) * Hd, device=b.device, dtype=torch.float32)
-        if N:
+        dense = N >= _DENSE_MIN_ROWS and Hd % 4 == 0
+        x0 = None
+        if dense:
+            from .conv import dense_layer
+            pad = (-(D + S)) % 4
+            x0 = torch.cat([b, s] + ([torch.zeros(N, pad, device=b.device)] if pad else []), 1)
+            h = x0
+            for i in range(L_layers):
+                w = params[2 * i].detach()
+                if i == 0 and pad:
+                    w = torch.nn.functional.pad(w, (0, pad))
+                last = i == L_layers - 1
+                dst = out if last else stash[:, i * Hd:(i + 1) * Hd]
+                dense_layer(h, w, params[2 * i + 1].detach().contiguous(), dst, act="none" if last else act)
+                h = dst
+        elif N:
+            keep = ops._Keep()
+            M = ops.mlp_struct({k: v.detach() for k, v in named.items()}, L_layers, keep, "mlp")
             ws = torch.empty(lib.repo_b200_mlp_workspace_bytes(C.byref(d), L_layers, out_f), dtype=torch.uint8, device=b.device)
             rc = lib.repo_b200_mlp_fwd(C.byref(d), C.byref(M), ops._ptr(b), ops._ptr(s), ops._ptr(out), out_f, ops._ptr(stash), N,
                                        ops.act_kind(act), ops._ptr(ws), ws.numel(), ops._stream())
             _lib.check(rc, "repo_b200_mlp_fwd")
-        ctx.meta = (act, out_f, L_layers, d)
+        ctx.meta = (act, out_f, L_layers, d, dense)
         ctx.save_for_backward(b, s, stash, *params)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        act, out_f, L_layers, d = ctx.meta
+        act, out_f, L_layers, d, dense = ctx.meta
         b, s, stash, *params = ctx.saved_tensors
         N, Hd = b.shape[0], d.hidden
-        named = {f"fc{i + 1}.{w}": params[2 * i + j] for i in range(L_layers) for j, w in enumerate(("weight", "bias"))}
-        keep = ops._Keep()
-        M = ops.mlp_struct(named, L_layers, keep, "mlp")
         g_out = g_out.contiguous().float()
-        dh = [torch.empty(N, Hd, device=b.device) for _ in range(L_layers - 1)] + [None] * (5 - L_layers)
         need_x = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
-        dx = torch.empty(N, d.belief + d.state, device=b.device) if need_x else None
-        if N:
-            rc = _lib.lib().repo_b200_mlp_bwd(C.byref(d), C.byref(M), ops._ptr(stash), ops._ptr(g_out), out_f, ops._ptr(dh[0]),
-                                              ops._ptr(dh[1]), ops._ptr(dh[2]), ops._ptr(dh[3]), ops._ptr(dx), N,
-                                              ops.act_kind(act), ops._stream())
-            _lib.check(rc, "repo_b200_mlp_bwd")
+        dh = [None] * 4
+        dx = None
+        if dense:
+            from .conv import _as_input_side, dense_layer, grad_scales
+            g = g_out
+            for i in range(L_layers - 1, 0, -1):       # d h_i = (d pre_{i+1} @ W_{i+1}) * act'(h_i)
+                dst = torch.empty(N, Hd, device=b.device, dtype=torch.float32)
+                dense_layer(g, params[2 * i].detach().t().contiguous(), None, dst, mask=stash[:, (i - 1) * Hd:i * Hd], mask_act=act,
+                            scales=_as_input_side(grad_scales(g)))
+                dh[i - 1] = dst
+                g = dst
+            if need_x:
+                nin = d.belief + d.state
+                npad = (nin + 15) // 16 * 16
+                w1t = torch.nn.functional.pad(params[0].detach().t(), (0, 0, 0, npad - nin)).contiguous()   # (npad, Hd)
+                dx = torch.empty(N, npad, device=b.device, dtype=torch.float32)
+                dense_layer(g, w1t, None, dx, scales=_as_input_side(grad_scales(g)))
+        else:
+            named = {f"fc{i + 1}.{w}": params[2 * i + j] for i in range(L_layers) for j, w in enumerate(("weight", "bias"))}
+            keep = ops._Keep()
+            M = ops.mlp_struct(named, L_layers, keep, "mlp")
+            dh = [torch.empty(N, Hd, device=b.device) for _ in range(L_layers - 1)] + [None] * (5 - L_layers)
+            dx = torch.empty(N, d.belief + d.state, device=b.device) if need_x else None
+            if N:
+                rc = _lib.lib().repo_b200_mlp_bwd(C.byref(d), C.byref(M), ops._ptr(stash), ops._ptr(g_out), out_f, ops._ptr(dh[0]),
+                                                  ops._ptr(dh[1]), ops._ptr(dh[2]), ops._ptr(dh[3]), ops._ptr(dx), N,
+                                                  ops.act_kind(act), ops._stream())
+                _lib.check(rc, "repo_b200_mlp_bwd")
         grads = []
         inputs = [torch.cat([b, s], 1)] + [stash[:, i * Hd:(i + 1) * Hd] for i in range(L_layers - 1)]
-        dpre = dh[:L_layers - 1] + [g_out]
+        dpre = list(dh[:L_layers - 1]) + [g_out]
         for i in range(L_layers):
             need_w, need_b = ctx.needs_input_grad[4 + 2 * i], ctx.needs_input_grad[5 + 2 * i]
             grads.append(_wgrad(dpre[i], inputs[i]) if need_w else None)
             grads.append(dpre[i].sum(0) if need_b else None)
-        gb = dx[:, :d.belief] if (need_x and ctx.needs_input_grad[2]) else None
-        gs = dx[:, d.belief:] if (need_x and ctx.needs_input_grad[3]) else None
+        gb = dx[:, :d.belief].contiguous() if (need_x and ctx.needs_input_grad[2]) else None
+        gs = dx[:, d.belief:d.belief + d.state].contiguous() if (need_x and ctx.needs_input_grad[3]) else None
         return (None, None, gb, gs, *grads)
 
 

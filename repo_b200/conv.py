@@ -104,7 +104,7 @@ def _is_hl(t):
     return t is not None and t.dtype == torch.float16
 
 
-def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=None, scales=None):
+def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=None, scales=None, dense_opts=None):
     """out = epilogue(gather(x) @ w_mat^T + bias) on the tcgen05 conv kernel (one launch + the weight packing).
     x / out / relu_mask may be HL tensors (`hl_empty`).  `scales` = device triple [s_x, s_w, 1/(s_x*s_w)] (see
     `grad_scales`; the gradient is the gathered operand here, so callers pass the triple with the slots swapped)
@@ -115,8 +115,9 @@ def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=Non
         raise RuntimeError(f"conv_gemm: weight matrix {tuple(w_mat.shape)} != ({n_total}, {cmap.K})")
     w_mat = w_mat.contiguous()
     ws = torch.empty(L.repo_b200_conv_workspace_bytes(cmap.K, n_total), dtype=torch.uint8, device=x.device)
+    opts = None if dense_opts is None else (C.c_int * 4)(*[int(v) for v in dense_opts])
     rc = L.repo_b200_conv_gemm(_p(x), _p(w_mat), _p(bias), _p(relu_mask), _p(scales), _p(out), frames, n_total, cmap.carray(),
-                               flags, _p(ws), ws.numel(), _stream())
+                               flags, opts, _p(ws), ws.numel(), _stream())
     _lib.check(rc, "repo_b200_conv_gemm")
     return out
 
@@ -133,6 +134,32 @@ def conv_wgrad(x, grad_rows, frames, n_total, cmap: ConvMap, scales=None):
                                          cmap.carray(), int(_is_hl(x)), _stream())
     _lib.check(rc, "repo_b200_conv_wgrad")
     return dw
+
+
+def dense_layer(x, weight, bias, out, act="none", mask=None, mask_act="relu", scales=None):
+    """out = act(x @ weight^T + bias) [* act'(mask)] for 2-D fp32 operands on the tcgen05 conv kernel run as a plain GEMM.
+    x, out and mask may be column windows of wider row-major matrices (row strides multiples of 4, 16-byte aligned);
+    act in {"none", "relu", "elu"}; `mask` is the OUTPUT of a `mask_act` layer whose activation derivative multiplies
+    the result (backward through that layer); `scales` as in `conv_gemm` (x is the gathered operand)."""
+    rows, k = x.shape
+    n = weight.shape[0]
+    if weight.shape[1] != k:
+        raise RuntimeError("dense_layer: weight / input size mismatch")
+    if rows == 0:
+        return out
+    for t, name, width in ((x, "x", k), (out, "out", n), (mask, "mask", n)):
+        if t is None:
+            continue
+        if t.stride(1) != 1 or not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"dense_layer: {name} must be an fp32 CUDA matrix with unit column stride")
+        vector = (width % 4 == 0) if name == "x" else (width % 16 == 0 or t.stride(0) != width)
+        if vector and (t.stride(0) % 4 or t.data_ptr() % 16):
+            raise RuntimeError(f"dense_layer: {name} needs 16-byte aligned rows")
+    cmap = ConvMap(RA=1, RB=1, in_nchw=0, C=k, H=1, W=1, TH=1, TW=1, sy=1, sx=1, dy=1, dx=1, Ho=1, Wo=1,
+                   relu=int(act == "relu"), pix=x.stride(0))
+    opts = [int(act == "elu"), int(mask is not None and mask_act == "elu"), out.stride(0) if out.stride(0) != n else 0,
+            (mask.stride(0) if (mask is not None and mask.stride(0) != n) else 0)]
+    return conv_gemm(x, weight, bias, out, rows, n, cmap, relu_mask=mask, scales=scales, dense_opts=opts)
 
 
 def wgrad_gemm(dpre, x):

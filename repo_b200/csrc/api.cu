@@ -784,8 +784,9 @@ size_t repo_b200_conv_workspace_bytes(int K, int n_total) {
 }
 
 int repo_b200_conv_gemm(const void* input_, const float* w_mat, const float* bias, const void* relu_mask_,
-                        const float* scales, void* out_, int frames, int n_total, const int* map /* ConvMap as 27 ints */,
-                        int hl_flags, void* ws, size_t ws_bytes, void* stream) {
+                        const float* scales, void* out_, int frames, int n_total, const int* map /* ConvMap as 28 ints */,
+                        int hl_flags, const int* dense_opts /* nullable: act_elu, mask_elu, out_ld, mask_ld */, void* ws,
+                        size_t ws_bytes, void* stream) {
   const float* input = static_cast<const float*>(input_);
   const float* relu_mask = static_cast<const float*>(relu_mask_);
   float* out = static_cast<float*>(out_);
@@ -845,6 +846,13 @@ int repo_b200_conv_gemm(const void* input_, const float* w_mat, const float* bia
   P.in_lo_bytes = (long long)frames * cm.H * cm.W * cm.C * 2;
   P.out_lo_elems = P.mask_lo_elems = (long long)frames * cm.Ho * cm.Wo * P.cout;
   P.a_lbo = P.in_hl ? kCvALboHL : kCvALbo;
+  if (dense_opts) {
+    P.act_elu = dense_opts[0]; P.mask_elu = dense_opts[1]; P.out_ld = dense_opts[2]; P.mask_ld = dense_opts[3];
+    if ((P.out_ld || P.mask_ld) && (cm.RA != 1 || cm.RB != 1 || cm.Ho != 1 || cm.Wo != 1 || cm.shuffle || cm.out_nchw || hl_flags))
+      return fail(-1, "conv: row strides are for plain fp32 GEMM maps only");
+    if ((P.out_ld && (P.out_ld < n_total || (P.out_ld & 3))) || (P.mask_ld && (P.mask_ld < n_total || (P.mask_ld & 3))))
+      return fail(-1, "conv: row strides must be multiples of 4 and >= n_total");
+  }
   P.kc16 = P.NP <= 128 ? 4 : 2;
   P.stage_bytes = conv_stage_bytes(P.kc16, P.NP);
   P.n_stages = std::min(kCvMaxStages, (200 * 1024) / P.stage_bytes);

@@ -42,6 +42,11 @@ struct ConvParams {
   int in_hl, out_hl, mask_hl;         // x / out / relu_mask are HL (pointers address the hi plane)
   long long in_lo_bytes, out_lo_elems, mask_lo_elems;  // distance from the hi plane to the lo plane
   uint32_t a_lbo;                     // byte stride between k-groups of the gathered operand inside a ring stage
+  // dense-layer options (plain GEMM maps only): ELU instead of ReLU, the mask interpreted as a layer OUTPUT whose
+  // activation derivative multiplies the result (relu' = [h > 0], elu' = h > 0 ? 1 : h + 1), row strides so that out /
+  // mask can be column windows of wider row-major matrices (the activation stash)
+  int act_elu, mask_elu;
+  int out_ld, mask_ld;
   ConvMap cm;
   int n_rows, K, k16;      // GEMM rows, real K, k16 slabs
   int n_total, NP, n_tiles;  // output features, features per tile (multiple of 16, <= 256), tiles
@@ -381,8 +386,11 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
         tmem_ld_wait();
         if (!valid) continue;
         const int nb = n0 + c, cnt = min(16, ncols - c);
-        // 16 features that are contiguous in an NHWC output: vector stores
-        if (!cm.out_nchw && cnt == 16 && (cout & 15) == 0) {
+        // features that are contiguous in an NHWC / row-major output: vector stores, cnt/4 quads per 16-column group
+        const bool vec = !cm.out_nchw && (cnt & 3) == 0 && (cout & 3) == 0 &&
+                         ((cnt == 16 && (cout & 15) == 0) || !(cm.shuffle || P.out_hl || P.mask_hl));
+        const int nq = cnt >> 2;
+        if (vec) {
           int py = 0, px = 0, co = nb;
           if (cm.shuffle) {
             const int cls = nb / cout;
@@ -390,7 +398,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
           }
           const int yy = oy + py, xx = ox + px;
           if (yy < cm.Ho && xx < cm.Wo) {
-            const size_t o = (((size_t)fr * cm.Ho + yy) * cm.Wo + xx) * cout + co;
+            const size_t od = (((size_t)fr * cm.Ho + yy) * cm.Wo + xx) * cout + co;
+            const size_t o = P.out_ld ? (size_t)fr * P.out_ld + co : od;          // plain GEMM into a column window
+            const size_t om = P.mask_ld ? (size_t)fr * P.mask_ld + co : od;
             const float4* bp = reinterpret_cast<const float4*>(P.bias + nb);
             float y[16];
 #pragma unroll
@@ -399,13 +409,16 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
               y[4 * j] = fmaf(v[4 * j], unscale, bb.x); y[4 * j + 1] = fmaf(v[4 * j + 1], unscale, bb.y);
               y[4 * j + 2] = fmaf(v[4 * j + 2], unscale, bb.z); y[4 * j + 3] = fmaf(v[4 * j + 3], unscale, bb.w);
             }
-            if (cm.relu) {
+            if (P.act_elu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) y[i] = act_t<ACT_ELU>(y[i]);
+            } else if (cm.relu) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i], 0.f);
             }
             if (P.relu_mask) {
               if (P.mask_hl) {  // sign of the hi plane = sign of the activation
-                const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(P.relu_mask) + o);
+                const uint4* mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(P.relu_mask) + om);
                 const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
                 const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
@@ -417,9 +430,14 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
               } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float4 m = __ldg(reinterpret_cast<const float4*>(P.relu_mask + o) + j);
-                  y[4 * j] = m.x > 0.f ? y[4 * j] : 0.f; y[4 * j + 1] = m.y > 0.f ? y[4 * j + 1] : 0.f;
-                  y[4 * j + 2] = m.z > 0.f ? y[4 * j + 2] : 0.f; y[4 * j + 3] = m.w > 0.f ? y[4 * j + 3] : 0.f;
+                  if (j >= nq) break;
+                  const float4 m = __ldg(reinterpret_cast<const float4*>(P.relu_mask + om) + j);
+                  const float mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float d = mm[i] > 0.f ? 1.f : (P.mask_elu ? mm[i] + 1.f : 0.f);
+                    y[4 * j + i] *= d;
+                  }
                 }
               }
             }
@@ -440,7 +458,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
             } else {
               float4* op = reinterpret_cast<float4*>(P.out + o);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) op[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+              for (int j = 0; j < 4; ++j)
+                if (j < nq) op[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
             }
           }
         } else {
@@ -455,11 +474,16 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
               }
               const int yy = oy + py, xx = ox + px;
               if (yy < cm.Ho && xx < cm.Wo) {
-                const size_t o = cm.out_nchw ? (((size_t)fr * cout + co) * cm.Ho + yy) * cm.Wo + xx
-                                             : (((size_t)fr * cm.Ho + yy) * cm.Wo + xx) * cout + co;
+                const size_t od = cm.out_nchw ? (((size_t)fr * cout + co) * cm.Ho + yy) * cm.Wo + xx
+                                              : (((size_t)fr * cm.Ho + yy) * cm.Wo + xx) * cout + co;
+                const size_t o = P.out_ld ? (size_t)fr * P.out_ld + co : od;
                 float y = fmaf(v[i], unscale, __ldg(P.bias + n));
-                if (cm.relu) y = fmaxf(y, 0.f);
-                if (P.relu_mask) y = __ldg(P.relu_mask + o) > 0.f ? y : 0.f;
+                if (P.act_elu) y = act_t<ACT_ELU>(y);
+                else if (cm.relu) y = fmaxf(y, 0.f);
+                if (P.relu_mask) {
+                  const float m = __ldg(P.relu_mask + (P.mask_ld ? (size_t)fr * P.mask_ld + co : od));
+                  y *= m > 0.f ? 1.f : (P.mask_elu ? m + 1.f : 0.f);
+                }
                 P.out[o] = y;
               }
             }

@@ -411,13 +411,14 @@ def test_imagine_backward_matches_autograd_of_the_oracle(dev, name):
     cmp(gs0.grad, s0.grad, "start state")
 
 
-def test_heads_actor_entropy_under_autograd(dev):
+@pytest.mark.parametrize("N", [77, 1500])
+def test_heads_actor_entropy_under_autograd(dev, N):
     """RewardModel/ValueModel.forward, ActorModel.forward and SampleDist.entropy as differentiable ops:
-    values and gradients (parameters and inputs) vs fp64 autograd through the oracle."""
+    values and gradients (parameters and inputs) vs fp64 autograd through the oracle.  N = 77 runs the fused small-batch
+    kernels, N = 1500 the one-GEMM-per-layer tcgen05 path (autograd._DENSE_MIN_ROWS)."""
     from repo_b200.models import ActorModel, RewardModel
     d = O.DEFAULT_DIMS
     D, S, A, Hd = d["belief"], d["state"], d["action"], d["hidden"]
-    N = 77
     rs = np.random.RandomState(21)
     b = torch.from_numpy((rs.standard_normal((N, D)) * 0.4).astype(np.float32))
     s = torch.from_numpy(rs.standard_normal((N, S)).astype(np.float32))
