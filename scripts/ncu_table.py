@@ -8,8 +8,24 @@ rep = sys.argv[1]
 labels = sys.argv[2].split(",") if len(sys.argv) > 2 else []
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr = rows[0]
+hdr, units = rows[0], rows[1]
 c = lambda n: hdr.index(n)
+_T = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3, "nsecond": 1e-6}
+_B = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
+
+
+def scaled(name, raw):
+    """ncu picks a unit per report: bring durations to ms and byte counts to MB"""
+    try:
+        v = float(raw.replace(",", ""))
+    except ValueError:
+        return raw
+    u = units[c(name)]
+    if name == "gpu__time_duration.sum":
+        v *= _T.get(u, 1.0)
+    elif name.startswith("dram__bytes"):
+        v *= _B.get(u, 1.0)
+    return v
 tens = "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"
 cols = [("dur_ms", "gpu__time_duration.sum"), ("tensor%", tens), ("issue%", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
         ("l1tex%", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"), ("l2%", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
@@ -23,12 +39,8 @@ for i, r in enumerate(rows[2:]):
     lab = labels[i] if i < len(labels) else str(i)
     vals = []
     for n, k in cols:
-        v = r[c(k)] if k in hdr else "-"
-        try:
-            v = f"{float(v.replace(',', '')):.3f}"
-        except ValueError:
-            pass
-        vals.append(v)
-    tot += float(r[c("gpu__time_duration.sum")])
+        v = scaled(k, r[c(k)]) if k in hdr else "-"
+        vals.append(f"{v:.3f}" if isinstance(v, float) else v)
+    tot += scaled("gpu__time_duration.sum", r[c("gpu__time_duration.sum")])
     print(f"{lab:28s} {name:22s} {r[c('launch__grid_size')]:>5s} " + " ".join(f"{v:>10s}" for v in vals))
 print(f"# total {tot:.3f} ms over {len(rows) - 2} launches")
