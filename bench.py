@@ -280,8 +280,10 @@ def run_gpu(a):
     ms, e2e_ms, kernel_ms = [float(v) for v in t.tolist()]
 
     # ---- RePo default shapes (configs[1]) : forward latency of the two kernels ----
+    # (single-process runs only: the trainer-level updates all-reduce their gradient buckets, which would dead-lock
+    # against the idle ranks of a multi-GPU imagine sweep)
     default_shape = None
-    if rank == 0:
+    if rank == 0 and world == 1:
         x = O.make_imagine_inputs(5, 2450, HORIZON)
         xa = [x["belief"].to(dev), x["state"].to(dev), x["eps_action"].to(dev), x["eps_prior"].to(dev)]
         xo = O.make_observe_inputs(6, 50, 50)
