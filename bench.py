@@ -305,6 +305,20 @@ def run_gpu(a):
         img_ms = timeit(lambda: ops.imagine_fwd(P, PA, PR, PV, *xa, HORIZON))
         obs_ms = timeit(lambda: ops.observe_fwd(P, *oa))
 
+        # observe at a batch that fills the GPU (the other half of the hot path; SURVEY §8d "Roofline - observe":
+        # 1,112,000 FLOP and 5,884 B per row-step): 18,944 sequences x 49 steps through the 128-row kernel
+        OB, OT = 18944, 50
+        gen = torch.Generator(device=dev).manual_seed(11)
+        rn = lambda *sh: torch.randn(*sh, device=dev, generator=gen)
+        big = [torch.zeros(OB, D, device=dev), torch.zeros(OB, S, device=dev), rn(OT - 1, OB, A).clamp_(-1, 1), rn(OT - 1, OB, 1024),
+               torch.ones(OT - 1, OB, 1, device=dev), rn(OT - 1, OB, S), rn(OT - 1, OB, S)]
+        big_ms = timeit(lambda: ops.observe_fwd(P, *big), 3)
+        big_steps = OB * (OT - 1)
+        observe_large = {"sequences": OB, "steps": OT - 1, "ms": big_ms, "row_steps_per_s": big_steps / big_ms * 1e3,
+                         "tflops_algorithmic": big_steps * 1_112_000 / big_ms / 1e9,
+                         "hbm_gbs_algorithmic": big_steps * 5884 / big_ms / 1e6}
+        del big
+
         # One full training iteration at the RePo default shapes (SURVEY §8d Metric 2 / Config 2), through the
         # trainer-level API (repo_b200/trainer.py): conv encoder -> observe (BPTT over 49 steps) -> conv decoder /
         # reward head / KL -> hand-written backward passes -> global-norm clip + Adam on flat buckets; then
@@ -357,6 +371,7 @@ def run_gpu(a):
         ac_ms = upd["actor_critic_update_ms"]
         default_shape = {"imagine_2450x14_ms": img_ms, "imagine_steps_per_s": 2450 * 14 / img_ms * 1e3,
                          "observe_49x50_ms": obs_ms, "observe_row_steps_per_s": 2450 / obs_ms * 1e3,
+                         "observe_us_per_time_step": obs_ms * 1e3 / 49, "observe_large_batch": observe_large,
                          **upd, "actor_critic_update_steps_per_s": 2450 * 14 / ac_ms * 1e3,
                          "note": "world_model_update = Agent.train_dynamics on a (50,50,3,64,64) batch: conv encoder + observe + conv "
                                  "decoder + reward/KL losses, all backward passes, clip + Adam; actor_critic_update = "

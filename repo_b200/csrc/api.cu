@@ -512,8 +512,27 @@ bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
 }
 
 
+}  // namespace
+int conv_gemm_impl(const void* input_, const float* w_mat, int w_ld, int w_col0, const float* bias, const void* relu_mask_,
+                   const float* scales, void* out_, int frames, int n_total, ConvMap cm, int hl_flags, const int* dense_opts,
+                   void* ws, size_t ws_bytes, cudaStream_t st);
+extern "C" size_t repo_b200_conv_workspace_bytes(int K, int n_total);
+namespace {
+
+// y = x @ W[:, w_col0 : w_col0 + in_f]^T + b for row-major operands.  From 256 rows (and 16-byte aligned, 4-float
+// strided operands) this is one launch of the tcgen05 conv kernel run as a plain GEMM (K streams through its ring, so
+// the 1024-wide embedding projection keeps 128-row tiles); below that the vm machine's one-step program.
 int run_linear(const float* x, int x_ld, int rows, int in_f, const float* w, int w_ld, int w_col0, const float* b,
                int out_f, float* y, int y_ld, void* ws, size_t ws_bytes, int row_tile, cudaStream_t st) {
+  const bool aligned = !(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(y) & 15) && !(x_ld & 3) &&
+                       !(y_ld & 3) && !(in_f & 3);
+  if (rows >= 256 && row_tile == 0 && aligned && ws_bytes >= repo_b200_conv_workspace_bytes(in_f, out_f) && !(g_dbg_flags & 256)) {
+    ConvMap cm{};
+    cm.RA = cm.RB = 1; cm.C = in_f; cm.pix = x_ld; cm.H = cm.W = 1; cm.TH = cm.TW = 1; cm.ntaps = 1;
+    cm.sy = cm.sx = cm.dy = cm.dx = 1; cm.Ho = cm.Wo = 1; cm.osy = cm.osx = 1;
+    const int opts[4] = {0, 0, y_ld != out_f ? y_ld : 0, 0};
+    return conv_gemm_impl(x, w, w_ld, w_col0, b, nullptr, nullptr, y, rows, out_f, cm, 0, opts, ws, ws_bytes, st);
+  }
   if (in_f < 1 || in_f > 1900) return fail(-1, "linear: in_features %d unsupported (1..1900)", in_f);
   if (out_f < 1 || out_f > 128 * 8) return fail(-1, "linear: out_features %d unsupported (1..1024)", out_f);
   Builder bl;
@@ -552,7 +571,8 @@ int repo_b200_device_info(int* sms, int* major, int* minor) {
 }
 
 size_t repo_b200_linear_workspace_bytes(int in_f, int out_f) {
-  return (size_t)cdiv(out_f, 128) * cdiv(in_f, 16) * kSlabBytes + (size_t)cdiv(out_f, 128) * 512 + 64;
+  const size_t vm = (size_t)cdiv(out_f, 128) * cdiv(in_f, 16) * kSlabBytes + (size_t)cdiv(out_f, 128) * 512 + 64;
+  return std::max(vm, repo_b200_conv_workspace_bytes(in_f, out_f));
 }
 
 int repo_b200_linear_fwd(const float* x, int x_ld, int rows, int in_f, const float* w, const float* b, int out_f,
@@ -796,17 +816,16 @@ size_t repo_b200_conv_workspace_bytes(int K, int n_total) {
   return (size_t)n_tiles * k16 * NP * 64 + (size_t)n_tiles * NP * sizeof(float) + 256;
 }
 
-int repo_b200_conv_gemm(const void* input_, const float* w_mat, const float* bias, const void* relu_mask_,
-                        const float* scales, void* out_, int frames, int n_total, const int* map /* ConvMap as 28 ints */,
-                        int hl_flags, const int* dense_opts /* nullable: act_elu, mask_elu, out_ld, mask_ld */, void* ws,
-                        size_t ws_bytes, void* stream) {
+}  // extern "C"
+
+// w_mat: (n_total, K) window of a row-major matrix with row stride w_ld (0 = K) starting at column w_col0
+int conv_gemm_impl(const void* input_, const float* w_mat, int w_ld, int w_col0, const float* bias, const void* relu_mask_,
+                   const float* scales, void* out_, int frames, int n_total, ConvMap cm, int hl_flags, const int* dense_opts,
+                   void* ws, size_t ws_bytes, cudaStream_t st) {
   const float* input = static_cast<const float*>(input_);
   const float* relu_mask = static_cast<const float*>(relu_mask_);
   float* out = static_cast<float*>(out_);
-  if (!input || !w_mat || !out || !map || !ws) return fail(-1, "conv: NULL pointer");
-  ConvMap cm;
-  static_assert(sizeof(ConvMap) == 28 * sizeof(int), "ConvMap layout");
-  std::memcpy(&cm, map, sizeof(cm));
+  if (!input || !w_mat || !out || !ws) return fail(-1, "conv: NULL pointer");
   cm.enabled = 1;
   if (cm.pix == 0) cm.pix = cm.C;
   if (cm.pix < cm.C) return fail(-1, "conv: pixel stride %d < channels %d", cm.pix, cm.C);
@@ -820,7 +839,6 @@ int repo_b200_conv_gemm(const void* input_, const float* w_mat, const float* bia
   const long long rows = (long long)frames * cm.RA * cm.RB;
   if (rows <= 0) return 0;
   if (rows > 0x7fffffffLL - 128) return fail(-1, "conv: too many rows");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   ConvParams P{};
   conv_geometry(K, n_total, P.k16, P.NP, P.n_tiles);
   if (ws_bytes < repo_b200_conv_workspace_bytes(K, n_total)) return fail(-2, "conv: workspace too small");
@@ -834,7 +852,7 @@ int repo_b200_conv_gemm(const void* input_, const float* w_mat, const float* bia
     ba.bias = bias_p;
     for (int nt = 0; nt < P.n_tiles; ++nt) {
       PackRowsJob& j = pa.jobs[nt];
-      j.w = w_mat; j.ld = K; j.col0 = 0; j.ncols = K; j.kofs = 0; j.ksl = P.k16; j.n_pad = P.NP; j.nseg = 1;
+      j.w = w_mat; j.ld = w_ld ? w_ld : K; j.col0 = w_col0; j.ncols = K; j.kofs = 0; j.ksl = P.k16; j.n_pad = P.NP; j.nseg = 1;
       j.seg_src[0] = nt * P.NP; j.seg_n[0] = std::min(P.NP, n_total - nt * P.NP); j.seg_dst[0] = 0;
       j.dst_off16 = (uint32_t)((size_t)nt * P.k16 * P.NP * 4);
       j.blk0 = nt * P.k16;
@@ -884,6 +902,20 @@ int repo_b200_conv_gemm(const void* input_, const float* w_mat, const float* bia
   else conv_rows_kernel<false><<<grid, kCvThreads, smem, st>>>(P);
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+extern "C" {
+
+int repo_b200_conv_gemm(const void* input_, const float* w_mat, const float* bias, const void* relu_mask_,
+                        const float* scales, void* out_, int frames, int n_total, const int* map /* ConvMap as 28 ints */,
+                        int hl_flags, const int* dense_opts /* nullable: act_elu, mask_elu, out_ld, mask_ld */, void* ws,
+                        size_t ws_bytes, void* stream) {
+  if (!map) return fail(-1, "conv: NULL pointer");
+  ConvMap cm;
+  static_assert(sizeof(ConvMap) == 28 * sizeof(int), "ConvMap layout");
+  std::memcpy(&cm, map, sizeof(cm));
+  return conv_gemm_impl(input_, w_mat, 0, 0, bias, relu_mask_, scales, out_, frames, n_total, cm, hl_flags, dense_opts, ws,
+                        ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int repo_b200_conv_wgrad(const void* input_, const float* grad_rows, const float* scales, float* dw, int frames,
