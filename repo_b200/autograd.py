@@ -113,7 +113,15 @@ class ObserveFn(torch.autograd.Function):
             lin("fc_embed_belief_posterior.weight", "fc_embed_belief_posterior.bias", d_hq, torch.cat([beliefs, observations], -1))
             lin("fc_state_posterior.weight", "fc_state_posterior.bias", d_q, hq)
             if ctx.needs_input_grad[5]:
-                g_obs = (flat(d_hq) @ named["fc_embed_belief_posterior.weight"][:, D:]).reshape(T1, B, E)
+                w_obs = named["fc_embed_belief_posterior.weight"][:, D:]
+                if T1 * B >= 256 and E % 16 == 0 and Hd % 4 == 0:
+                    from .conv import _as_input_side, dense_layer, grad_scales
+                    g_obs = torch.empty(T1 * B, E, device=dev, dtype=torch.float32)
+                    dq = flat(d_hq)
+                    dense_layer(dq, w_obs.detach().t().contiguous(), None, g_obs, scales=_as_input_side(grad_scales(dq)))
+                    g_obs = g_obs.reshape(T1, B, E)
+                else:
+                    g_obs = (flat(d_hq) @ w_obs).reshape(T1, B, E)
         return (None, None, d_b0 if ctx.needs_input_grad[2] else None, d_s0 if ctx.needs_input_grad[3] else None,
                 None, g_obs, None, None, None, *[gp[k] for k in PARAM_KEYS])
 

@@ -419,19 +419,33 @@ class _DecoderFn(torch.autograd.Function):
         k1, co1 = ws[0].shape[2], ws[0].shape[1]
         g1 = gp.reshape(F_, k1 * k1 * co1)
         w1 = ws[0].permute(2, 3, 1, 0).reshape(k1 * k1 * co1, -1)
+        # these three layers are plain GEMMs: same tcgen05 kernels (contraction over frames / over features), run dense
+        big = F_ >= 256
         if need[2 + 2]:
-            grads[2] = (g1.t() @ h).reshape(k1, k1, co1, -1).permute(3, 2, 0, 1).contiguous()
+            dw1 = wgrad_gemm(g1, h) if big else g1.t() @ h
+            grads[2] = dw1.reshape(k1, k1, co1, -1).permute(3, 2, 0, 1).contiguous()
         if need[2 + 3]:
             grads[3] = g1.reshape(F_, k1 * k1, co1).sum((0, 1))
-        d_h = g1 @ w1
+        if big:
+            d_h = torch.empty(F_, w1.shape[1], device=g1.device, dtype=torch.float32)
+            dense_layer(g1, w1.t().contiguous(), None, d_h, scales=_as_input_side(grad_scales(g1)))
+        else:
+            d_h = g1 @ w1
         if need[2]:
-            grads[0] = d_h.t() @ xin
+            grads[0] = wgrad_gemm(d_h, xin) if big else d_h.t() @ xin
         if need[3]:
             grads[1] = d_h.sum(0)
         gb = gs = None
         if need[0] or need[1]:
-            d_x = d_h @ fc_w
-            gb, gs = d_x[:, :ctx.belief_size].contiguous(), d_x[:, ctx.belief_size:].contiguous()
+            nin = fc_w.shape[1]
+            if big:
+                npad = (nin + 15) // 16 * 16
+                d_x = torch.empty(F_, npad, device=g1.device, dtype=torch.float32)
+                dense_layer(d_h, F.pad(fc_w.detach().t(), (0, 0, 0, npad - nin)).contiguous(), None, d_x,
+                            scales=_as_input_side(grad_scales(d_h)))
+            else:
+                d_x = d_h @ fc_w
+            gb, gs = d_x[:, :ctx.belief_size].contiguous(), d_x[:, ctx.belief_size:nin].contiguous()
         return (gb if need[0] else None, gs if need[1] else None, *grads)
 
 

@@ -156,3 +156,27 @@ def test_split_activation_format_is_equivalent_to_fp32(dev):
     g = torch.randn(F_ * cm3.RA * cm3.RB, 128, device=dev) * 1e-5
     d1, d2 = cv.conv_wgrad(a2, g, F_, 128, cm3), cv.conv_wgrad(to_hl(a2), g, F_, 128, cm3)
     assert ((d1 - d2).abs().max() / d1.abs().max()).item() < 2e-6   # atomics: summation order differs run to run
+
+
+def test_decoder_backward_large_batch_branch_matches_small_batch_branch(dev):
+    """From 256 frames the decoder's three plain-GEMM gradients (first transposed conv and fc1) run on the tcgen05
+    kernels instead of cuBLAS: the gradients of one 256-frame batch must equal the summed gradients of its four 64-frame
+    quarters (the small-batch branch, itself checked against fp64 autograd above)."""
+    from repo_b200.conv import VisualObservationModel
+    p = synth.make_conv_params("decoder", 730)
+    xi = synth.make_imagine_inputs(731, 256, 2)
+    R = torch.from_numpy(np.random.RandomState(3).standard_normal((256, 3, 64, 64)).astype(np.float32)).to(dev) * 1e-3
+
+    def run(sl):
+        dec = VisualObservationModel(200, 30, 1024).to(dev)
+        dec.load_state_dict(p)
+        b, s = xi["belief"][sl].to(dev).requires_grad_(True), xi["state"][sl].to(dev).requires_grad_(True)
+        (dec(b, s) * R[sl]).sum().backward()
+        return {k: v.grad for k, v in dec.named_parameters()}, b.grad, s.grad
+
+    big, gb, gs = run(slice(0, 256))
+    parts = [run(slice(i, i + 64)) for i in range(0, 256, 64)]
+    for k in big:
+        rel_close(big[k], sum(pt[0][k] for pt in parts).cpu().numpy(), "decoder grad " + k, rtol=1e-3, floor=2e-4)
+    rel_close(gb, torch.cat([pt[1] for pt in parts]).cpu().numpy(), "d belief", rtol=1e-3, floor=2e-4)
+    rel_close(gs, torch.cat([pt[2] for pt in parts]).cpu().numpy(), "d state", rtol=1e-3, floor=2e-4)

@@ -342,6 +342,33 @@ def test_observe_backward_matches_autograd_of_the_oracle(dev, name):
         np.testing.assert_allclose(emb.grad.cpu().double().numpy() / scale, want_emb.numpy() / scale, rtol=1e-3, atol=2e-4)
 
 
+def test_observe_backward_large_batch_embedding_gradient(dev):
+    """From 256 (t,b) rows the gradient w.r.t. the embeddings (d_hq @ W_post[:, D:]) runs on the tcgen05 GEMM instead of
+    cuBLAS: one 60-sequence batch must give the same embedding / parameter gradients as its two 30-sequence halves."""
+    from repo_b200.rssm import TransitionModel
+    params = O.make_transition_params(77)
+    x = O.make_observe_inputs(78, 7, 60)
+    Rb = torch.from_numpy(np.random.RandomState(4).standard_normal((6, 60, 200)).astype(np.float32)).to(dev)
+
+    def run(sl):
+        tm = TransitionModel(200, 30, 6, 200, 1024, "elu").to(dev)
+        tm.load_state_dict(params)
+        g = lambda k: x[k][:, sl].to(dev) if x[k].dim() == 3 else x[k][sl].to(dev)
+        emb = g("embeds").requires_grad_(True)
+        outs = tm.observe(g("prev_belief"), g("prev_state"), g("actions"), emb, g("nonterms"), eps_prior=g("eps_prior"),
+                          eps_post=g("eps_post"))
+        ((outs[0] * Rb[:, sl]).sum() + outs[4].sum() + (outs[5] * outs[6]).sum() + outs[3].sum()).backward()
+        return {k: v.grad for k, v in tm.named_parameters()}, emb.grad
+
+    big, ge = run(slice(0, 60))
+    halves = [run(slice(0, 30)), run(slice(30, 60))]
+    close(ge, torch.cat([h[1] for h in halves], 1).cpu(), "d embeds", atol=1e-5)
+    for k in big:
+        want = (halves[0][0][k] + halves[1][0][k]).cpu()
+        scale = float(want.abs().max()) + 1e-12
+        np.testing.assert_allclose(big[k].cpu().numpy() / scale, want.numpy() / scale, rtol=1e-3, atol=2e-4, err_msg=k)
+
+
 def test_frozen_parameters_get_no_gradient(dev):
     """FreezeParameters (common/utils.py:47-58) sets requires_grad=False at call time."""
     from repo_b200.rssm import TransitionModel
