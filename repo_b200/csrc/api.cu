@@ -943,6 +943,7 @@ int repo_b200_conv_wgrad(const void* input_, const float* grad_rows, const float
   P.n_rows = (int)rows; P.K = K; P.k16 = cdiv(K, 16); P.n_total = n_total; P.g_ld = g_ld;
   P.NP = cdiv(n_total, 16) * 16;
   P.x_hl = input_hl ? 1 : 0;
+  P.dbg = g_dbg_clock;
   if (P.x_hl && (cm.in_nchw || (cm.C & 7) || cm.pix != cm.C)) return fail(-1, "conv_wgrad: HL input needs NHWC and C %% 8 == 0");
   P.x_lo_bytes = (long long)frames * cm.H * cm.W * cm.C * 2;
   const int n_ent = conv_table_entries(cm, P.k16, P.x_hl);

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kCvMaxStages; ++i) {
-      mbar_init(bar_full + 8 * i, kCvProducers + 1);
+      mbar_init(bar_full + 8 * i, kCvProducers / 32 + 1);   // one arrival per gather warp + the weight loader
       mbar_init(bar_empty + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(bar_full + 8 * slot);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * slot);   // (512 per-thread arrivals on one barrier word serialise)
         if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
 #pragma unroll
         for (int j = 0; j < 2; ++j) { ch[j] = nh[j]; cl[j] = nl[j]; }
@@ -355,7 +356,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive(bar_full + 8 * slot);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * slot);   // (512 per-thread arrivals on one barrier word serialise)
         if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
       }
     }
@@ -521,6 +523,7 @@ struct WgradParams {
   const float* g;        // output-gradient rows (n_rows, g_ld)
   float* dw;             // (n_total, K) fp32, zero-initialised
   const float* scales;   // optional device floats [s_x, s_g, 1/(s_x*s_g)]
+  long long* dbg;        // profiling only: CTA 0 writes cycle sums [issue, wait_empty, data+store, arrive | mma_wait_full, mma_issue, stages]
   int x_hl;              // x is in split-activation format (fp16 hi plane at x, lo plane x_lo_bytes further)
   long long x_lo_bytes;
   ConvMap cm;
@@ -548,7 +551,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kCvMaxStages; ++i) {
-      mbar_init(bar_full + 8 * i, kCvProducers);
+      mbar_init(bar_full + 8 * i, kCvProducers / 32);   // one arrival per gather warp
       mbar_init(bar_empty + 8 * i, 1);
     }
     mbar_init(bar_accf, 1);
@@ -585,8 +588,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
     const uint32_t idesc = make_idesc_f16(128, P.NP) | (1u << 15) | (1u << 16);   // A and B MN-major
     const uint32_t ring_a = smem_u32(ring);
     uint32_t first = 1;
+    long long m_wait = 0, m_issue = 0;
     for (int st = st0; st < st1; ++st) {
+      const long long M0 = clock64();
       mbar_wait(bar_full + 8 * slot, phase);
+      const long long M1 = clock64();
+      m_wait += M1 - M0;
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sa = ring_a + slot * (uint32_t)P.stage_bytes;
@@ -607,9 +614,11 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
         umma_commit(bar_empty + 8 * slot);
       }
       __syncwarp();
+      m_issue += clock64() - M1;
       first = 0;
       if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
     }
+    if (P.dbg && blockIdx.x == 0 && lane == 0) { P.dbg[4] = m_wait; P.dbg[5] = m_issue; }
     if (elect_one()) umma_commit(bar_accf);
     __syncwarp();
   } else if (warp < 4) {
@@ -626,17 +635,40 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
     const uint32_t row_off = (uint32_t)(rs & 7) * 16u + (uint32_t)(q & 1) * 8u + (uint32_t)(q >> 1) * kWgSbo;
     const uint32_t a_off = (uint32_t)(rs >> 3) * lbo_a + row_off, b_off = (uint32_t)(rs >> 3) * lbo_b + row_off;
     const int kblocks = kt / 64, nblocks = (P.NP + 63) / 64;
+    long long c_issue = 0, c_wait = 0, c_store = 0, c_arrive = 0;
+    // (frame, a, b) of this thread's row: divided out once, then advanced by kWgRows per stage (the gather warps are
+    // instruction-issue bound: ~6 warps per scheduler, so two integer divisions per stage are a visible cost)
+    int fr, ra, rb;
+    {
+      const int row = st0 * kWgRows + rs;
+      fr = row / per_frame;
+      const int rem = row - fr * per_frame;
+      ra = rem / cm.RB;
+      rb = rem - ra * cm.RB;
+    }
     for (int st = st0; st < st1; ++st) {
+      const long long T0 = clock64();
       const int row = st * kWgRows + rs;
       const bool valid = row < P.n_rows;
-      const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
+      const int a = ra, b = rb;
       const int ay = valid ? a * cm.sy + cm.y0 : -30000, bx = b * cm.sx + cm.x0;
       const long long e0 = cm.in_nchw ? ((long long)fr * cm.C * cm.H + ay) * cm.W + bx
                                       : (((long long)fr * cm.H + ay) * cm.W + bx) * cm.pix;
       const uint64_t base = opaque(reinterpret_cast<uint64_t>(P.x + (valid ? e0 : 0)));
-      mbar_wait(bar_empty + 8 * slot, phase ^ 1);
       uint8_t* sa = ring + (size_t)slot * P.stage_bytes;
       uint8_t* sb = sa + 2 * a_half;
+      // every global load of the stage (gathered rows AND gradient rows) is issued before the ring slot is awaited:
+      // one L2 round trip per stage, overlapped with the wait for the MMAs that still read the slot
+      float4 gv[4];
+      {
+        const float* grow = P.g + (size_t)(valid ? row : 0) * P.g_ld;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n = i * 64 + q * 4;
+          gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < nblocks && valid && n < P.n_total) gv[i] = __ldg(reinterpret_cast<const float4*>(grow + n));
+        }
+      }
       if (P.x_hl) {
         // HL input: 16 lanes x one channel oct each = 128 k per pass, pure 16-byte copies of both planes
         const uint64_t bh = opaque(reinterpret_cast<uint64_t>(P.x) + (valid ? e0 * 2 : 0));
@@ -655,6 +687,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
             }
           }
         }
+        const long long T1 = clock64();
+        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        const long long T2 = clock64();
+        c_issue += T1 - T0; c_wait += T2 - T1; c_store -= T2;
         const uint32_t o0 = (uint32_t)(rs >> 3) * lbo_a + (uint32_t)(rs & 7) * 16u + (uint32_t)q * kWgSbo;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -664,73 +700,79 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
             *reinterpret_cast<uint4*>(sa + a_half + o) = vl[i];
           }
         }
-      } else
-      for (int kb0 = 0; kb0 < kblocks; kb0 += 4) {
-        float4 v[4];
+      } else {
+        bool waited = false;
+        for (int kb0 = 0; kb0 < kblocks; kb0 += 4) {
+          float4 v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int kb = kb0 + i;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kb < kblocks) {
-            const int k = m0 * 128 + kb * 64 + q * 4;
-            if (k < P.k16 * 16) {
-              if (quads) {
-                const ConvTap e = table[k >> 2];
-                const bool ok = (unsigned)(ay + e.tdy) < (unsigned)cm.H && (unsigned)(bx + e.tdx) < (unsigned)cm.W;
-                if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(base + (long long)e.off));
-              } else {
-                float el[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const ConvTap e = table[k + c];
+          for (int i = 0; i < 4; ++i) {
+            const int kb = kb0 + i;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kb < kblocks) {
+              const int k = m0 * 128 + kb * 64 + q * 4;
+              if (k < P.k16 * 16) {
+                if (quads) {
+                  const ConvTap e = table[k >> 2];
                   const bool ok = (unsigned)(ay + e.tdy) < (unsigned)cm.H && (unsigned)(bx + e.tdx) < (unsigned)cm.W;
-                  el[c] = 0.f;
-                  if (ok) el[c] = __ldg(reinterpret_cast<const float*>(base + (long long)e.off));
+                  if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(base + (long long)e.off));
+                } else {
+                  float el[4];
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    const ConvTap e = table[k + c];
+                    const bool ok = (unsigned)(ay + e.tdy) < (unsigned)cm.H && (unsigned)(bx + e.tdx) < (unsigned)cm.W;
+                    el[c] = 0.f;
+                    if (ok) el[c] = __ldg(reinterpret_cast<const float*>(base + (long long)e.off));
+                  }
+                  v[i] = make_float4(el[0], el[1], el[2], el[3]);
                 }
-                v[i] = make_float4(el[0], el[1], el[2], el[3]);
               }
             }
           }
-        }
+          if (!waited) {
+            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+            waited = true;
+          }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int kb = kb0 + i;
-          if (kb < kblocks) {
-            uint2 h, l;
-            split2_f16(v[i].x * xs, v[i].y * xs, h.x, l.x);
-            split2_f16(v[i].z * xs, v[i].w * xs, h.y, l.y);
-            const uint32_t o = a_off + (uint32_t)kb * 8u * kWgSbo;
-            *reinterpret_cast<uint2*>(sa + o) = h;
-            *reinterpret_cast<uint2*>(sa + a_half + o) = l;
+          for (int i = 0; i < 4; ++i) {
+            const int kb = kb0 + i;
+            if (kb < kblocks) {
+              uint2 h, l;
+              split2_f16(v[i].x * xs, v[i].y * xs, h.x, l.x);
+              split2_f16(v[i].z * xs, v[i].w * xs, h.y, l.y);
+              const uint32_t o = a_off + (uint32_t)kb * 8u * kWgSbo;
+              *reinterpret_cast<uint2*>(sa + o) = h;
+              *reinterpret_cast<uint2*>(sa + a_half + o) = l;
+            }
           }
         }
       }
       // output-gradient rows
-      {
-        float4 v[4];
-        const float* grow = P.g + (size_t)(valid ? row : 0) * P.g_ld;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = i * 64 + q * 4;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < nblocks && valid && n < P.n_total) v[i] = __ldg(reinterpret_cast<const float4*>(grow + n));
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n = i * 64 + q * 4;
-          if (i < nblocks && n < P.NP) {
-            uint2 h, l;
-            split2_f16(v[i].x * gs, v[i].y * gs, h.x, l.x);
-            split2_f16(v[i].z * gs, v[i].w * gs, h.y, l.y);
-            const uint32_t o = b_off + (uint32_t)i * 8u * kWgSbo;
-            *reinterpret_cast<uint2*>(sb + o) = h;
-            *reinterpret_cast<uint2*>(sb + b_half + o) = l;
-          }
+      for (int i = 0; i < 4; ++i) {
+        const int n = i * 64 + q * 4;
+        if (i < nblocks && n < P.NP) {
+          uint2 h, l;
+          split2_f16(gv[i].x * gs, gv[i].y * gs, h.x, l.x);
+          split2_f16(gv[i].z * gs, gv[i].w * gs, h.y, l.y);
+          const uint32_t o = b_off + (uint32_t)i * 8u * kWgSbo;
+          *reinterpret_cast<uint2*>(sb + o) = h;
+          *reinterpret_cast<uint2*>(sb + b_half + o) = l;
         }
       }
+      const long long T3 = clock64();
       fence_proxy_async_smem();
-      mbar_arrive(bar_full + 8 * slot);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * slot);
+      const long long T4 = clock64();
+      if (P.x_hl) { c_store += T3; c_arrive += T4 - T3; }
       if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
+      rb += kWgRows;
+      while (rb >= cm.RB) { rb -= cm.RB; ++ra; }
+      while (ra >= cm.RA) { ra -= cm.RA; ++fr; }
+    }
+    if (P.dbg && blockIdx.x == 0 && p == 0) {
+      P.dbg[0] = c_issue; P.dbg[1] = c_wait; P.dbg[2] = c_store; P.dbg[3] = c_arrive; P.dbg[6] = st1 - st0;
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
