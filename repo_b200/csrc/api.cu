@@ -877,6 +877,7 @@ int conv_gemm_impl(const void* input_, const float* w_mat, int w_ld, int w_col0,
   P.in_lo_bytes = (long long)frames * cm.H * cm.W * cm.C * 2;
   P.out_lo_elems = P.mask_lo_elems = (long long)frames * cm.Ho * cm.Wo * P.cout;
   P.a_lbo = P.in_hl ? kCvALboHL : kCvALbo;
+  P.dbg = g_dbg_clock;
   if (dense_opts) {
     P.act_elu = dense_opts[0]; P.mask_elu = dense_opts[1]; P.out_ld = dense_opts[2]; P.mask_ld = dense_opts[3];
     if ((P.out_ld || P.mask_ld) && (cm.RA != 1 || cm.RB != 1 || cm.Ho != 1 || cm.Wo != 1 || cm.shuffle || cm.out_nchw || hl_flags))
@@ -886,10 +887,12 @@ int conv_gemm_impl(const void* input_, const float* w_mat, int w_ld, int w_col0,
   }
   P.kc16 = P.NP <= 128 ? 4 : 2;
   P.stage_bytes = conv_stage_bytes(P.kc16, P.NP);
-  P.n_stages = std::min(kCvMaxStages, (200 * 1024) / P.stage_bytes);
   const int n_ent = conv_table_entries(cm, P.k16, P.in_hl);
   if (n_ent > 2048) return fail(-1, "conv: K = %d needs %d gather-table entries (max 2048)", K, n_ent);
-  const size_t smem = (size_t)P.n_stages * P.stage_bytes + 128 + (size_t)n_ent * sizeof(ConvTap);
+  const size_t fixed = 128 + 4 * 128 * sizeof(ConvRowInfo) + kCvColEntries * sizeof(ConvCol) + (size_t)n_ent * sizeof(ConvTap);
+  P.n_stages = std::min<int>(kCvMaxStages, (int)((227 * 1024 - fixed) / P.stage_bytes));
+  if (P.n_stages < 2) return fail(-1, "conv: ring does not fit shared memory");
+  const size_t smem = (size_t)P.n_stages * P.stage_bytes + fixed;
   static size_t configured = 0;
   if (smem > configured) {
     CUDA_OK(cudaFuncSetAttribute(conv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -47,6 +47,7 @@ struct ConvParams {
   // mask can be column windows of wider row-major matrices (the activation stash)
   int act_elu, mask_elu;
   int out_ld, mask_ld;
+  long long* dbg;   // profiling only: CTA 0 writes cycle sums [mma wait_acc, wait_full, issue | gather g0 loop, wait_empty | epi wait, work | chunks, items]
   ConvMap cm;
   int n_rows, K, k16;      // GEMM rows, real K, k16 slabs
   int n_total, NP, n_tiles;  // output features, features per tile (multiple of 16, <= 256), tiles
@@ -64,6 +65,17 @@ __host__ __device__ inline int conv_stage_bytes(int kc16, int NP) { return kc16 
 // Gather table, built once per CTA: the input address of (row, k) separates into a per-row base plus a per-k
 // offset, so the index divisions happen once per k instead of once per (row, k).  NHWC inputs with C % 4 == 0 use
 // one entry per channel quad (16-byte loads), anything else one entry per k (scalar loads).
+struct ConvRowInfo {   // per GEMM row of the current item: input pointer of its origin pixel and the origin itself
+  uint64_t base;
+  int ay, bx;
+};
+struct ConvCol {       // per output feature (single feature tile): offset inside the frame, sub-pixel class, bias
+  int off;
+  short py, px;
+  float bias;
+  int pad;
+};
+constexpr int kCvColEntries = 256;
 struct ConvTap {
   int off;         // BYTE offset from the row base
   short tdy, tdx;  // tap displacement in pixels (sentinel -30000 beyond K: fails the bounds test)
@@ -105,7 +117,9 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)P.n_stages * P.stage_bytes);
   // bars: [0,4) full, [4,8) empty, [8,10) acc_full, [10,12) acc_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  ConvTap* table = reinterpret_cast<ConvTap*>(bars + 14);
+  ConvRowInfo* row_info = reinterpret_cast<ConvRowInfo*>(bars + 16);   // 4 gather groups x 128 rows
+  ConvCol* cols = reinterpret_cast<ConvCol*>(row_info + 4 * 128);      // scalar-store epilogue: one entry per feature
+  ConvTap* table = reinterpret_cast<ConvTap*>(cols + kCvColEntries);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 4);
@@ -114,7 +128,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kCvMaxStages; ++i) {
-      mbar_init(bar_full + 8 * i, kCvProducers / 32 + 1);   // one arrival per gather warp + the weight loader
+      mbar_init(bar_full + 8 * i, 4 + 1);   // the four warps of the gather group that owns the chunk + the weight loader
       mbar_init(bar_empty + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -128,6 +142,22 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
     tmem_relinquish();
   }
   conv_build_table(table, cm, P.k16, P.in_hl, threadIdx.x, kCvThreads);
+  const bool have_cols = P.n_tiles == 1 && P.n_total <= kCvColEntries;
+  if (have_cols) {
+    for (int n = threadIdx.x; n < P.n_total; n += kCvThreads) {
+      int py = 0, px = 0, co = n;
+      if (cm.shuffle) {
+        const int cls = n / P.cout;
+        co = n - cls * P.cout; py = cls >> 1; px = cls & 1;
+      }
+      ConvCol c;
+      c.off = cm.out_nchw ? (co * cm.Ho + py) * cm.Wo + px : (py * cm.Wo + px) * P.cout + co;
+      c.py = (short)py; c.px = (short)px;
+      c.bias = P.bias[n];
+      c.pad = co;
+      cols[n] = c;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -165,18 +195,24 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // ================================ MMA issuer ================================
     uint32_t slot = 0, phase = 0, item = 0;
+    long long m_acc = 0, m_full = 0, m_issue = 0, n_chunks = 0;
     const uint32_t idesc = make_idesc_f16(128, P.NP);
     const uint32_t w_lbo = (uint32_t)P.NP * 16u, w_lo = w_lbo * 2u;
     const uint32_t ring_a = smem_u32(ring);
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
       const uint32_t buf = item & 1u, use = item >> 1;
+      const long long A0 = clock64();
       mbar_wait(bar_acce + 8 * buf, (use & 1u) ^ 1u);  // epilogue has drained this accumulator
+      m_acc += clock64() - A0;
       tc_fence_after();
       const uint32_t d = tmem_base + buf * kCvAccCols;
       uint32_t acc = 0;
       for (int c0 = 0; c0 < P.k16; c0 += P.kc16) {
         const int nsl = min(P.kc16, P.k16 - c0);
+        const long long F0 = clock64();
         mbar_wait(bar_full + 8 * slot, phase);
+        const long long F1 = clock64();
+        m_full += F1 - F0; ++n_chunks;
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = ring_a + slot * (uint32_t)P.stage_bytes;
@@ -194,174 +230,153 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
           umma_commit(bar_empty + 8 * slot);
         }
         __syncwarp();
+        m_issue += clock64() - F1;
         acc = 1u;
         if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
       }
       if (elect_one()) umma_commit(bar_accf + 8 * buf);
       __syncwarp();
     }
+    if (P.dbg && blockIdx.x == 0 && lane == 0) { P.dbg[0] = m_acc; P.dbg[1] = m_full; P.dbg[2] = m_issue; P.dbg[7] = n_chunks; P.dbg[8] = item; }
   } else if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // spare warps of warpgroup 0: the dec is warpgroup-wide
   } else if (warp >= 8) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // ================================ gatherers ================================
-    // Thread p owns channel quad q = p % 8 of rows rs and rs + 64: a warp instruction reads 4 rows x 128
-    // contiguous bytes, and each stage pass hh covers 32 k of every row.  Gather warps are instruction-issue bound,
-    // so everything that does not depend on both row and k is hoisted: row pointers here, k offsets in the table.
+    // Groups of four warps, one per ring slot (n_stages = 2..4 of the four groups are active); group g builds ring
+    // chunks g, g+G, g+2G, ... of this CTA's flattened (item, chunk) sequence, so G chunks are in flight at once and
+    // every slot has exactly one producer group (a second group on the same slot could run a whole barrier phase ahead
+    // of the consumer, which the one-bit phase parity cannot express).  (With all 16 warps on the same chunk every chunk paid one full
+    // load round trip plus the whole per-chunk instruction stream before the next one could start.)  Inside a group
+    // thread pg owns channel quad / oct q = pg % 8 of rows rs + 16 j (j < 8), rs = pg / 8: a warp instruction reads
+    // 4 rows x 128 contiguous bytes.  Per-row base pointer and origin live in a per-group shared-memory block that is
+    // rebuilt when the group moves to a new item; per-k offsets come from the tap table.
     const int p = threadIdx.x - 256;
-    const int q = p & 7, rs = p >> 3;
+    const int grp = p >> 7, pg = p & 127;
+    const int q = pg & 7, rs = pg >> 3;
+    ConvRowInfo* info = row_info + grp * 128;
     const bool quads = conv_quads(cm);
-    uint32_t slot = 0, phase = 0;
     const int per_frame = cm.RA * cm.RB;
-    if (P.in_hl) {
-      // HL input: thread p copies channel oct q (16 bytes of the hi plane + 16 of the lo plane) of rows rs and rs + 64.
-      // The loads run ONE CHUNK AHEAD of the stores (register double buffer), so the global-load latency of chunk c+1
-      // overlaps the barrier wait + shared stores of chunk c instead of serialising with them.
-      const uint32_t st_hl = (uint32_t)q * a_lbo + (uint32_t)rs * 16u;
-      const long long lo_delta = P.in_lo_bytes;
-      uint64_t base[2] = {0, 0};
-      int ay[2] = {-30000, -30000}, bx[2] = {0, 0};
-      int w_l = blockIdx.x, c0_l = 0;               // load cursor
-      auto rows_of = [&](int w) {
+    const int chunks_per_item = (P.k16 + P.kc16 - 1) / P.kc16;
+    const int my_items = n_items > (int)blockIdx.x ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto group_sync = [&] { asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory"); };
+    // this group's position: item index, chunk inside the item; its ring slot is always `grp`
+    const int G = n_stages;
+    int it = grp < G ? 0 : my_items, ch = grp;
+    while (it < my_items && ch >= chunks_per_item) { ch -= chunks_per_item; ++it; }
+    const uint32_t slot = (uint32_t)grp;
+    uint32_t phase = 0;
+    int cur_item = -1;
+    const long long lo_delta = P.in_lo_bytes;
+    long long g_loop = 0, g_wait = 0;
+    const long long G0 = clock64();
+    while (it < my_items) {
+      if (it != cur_item) {
+        group_sync();   // everyone is done reading the previous item's rows
+        const int w = blockIdx.x + it * gridDim.x;
+        const int row = (w / P.n_tiles) * 128 + pg;
+        const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
+        ConvRowInfo ri;
+        ri.ay = row < P.n_rows ? a * cm.sy + cm.y0 : -30000;   // rows past the end fail every bounds test
+        ri.bx = b * cm.sx + cm.x0;
+        const long long e = cm.in_nchw ? ((long long)fr * cm.C * cm.H + ri.ay) * cm.W + ri.bx
+                                       : (((long long)fr * cm.H + ri.ay) * cm.W + ri.bx) * cm.pix;
+        ri.base = reinterpret_cast<uint64_t>(P.x) + (row < P.n_rows ? e * (P.in_hl ? 2 : 4) : 0);
+        info[pg] = ri;
+        group_sync();
+        cur_item = it;
+      }
+      const int c0 = ch * P.kc16;
+      const int kchunk = 16 * min(P.kc16, P.k16 - c0);
+      uint8_t* stage = ring + (size_t)slot * P.stage_bytes;
+      bool waited = false;
+      if (P.in_hl) {
+        const bool mine = q * 8 < kchunk;
+        ConvTap e{0, -30000, -30000};
+        if (mine) e = table[(c0 * 16 + q * 8) >> 3];
+        const long long ob = e.off;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int row = (w / P.n_tiles) * 128 + rs + 64 * j;
-          const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
-          ay[j] = row < P.n_rows ? a * cm.sy + cm.y0 : -30000;
-          bx[j] = b * cm.sx + cm.x0;
-          const long long e = (((long long)fr * cm.H + ay[j]) * cm.W + bx[j]) * cm.pix * 2;
-          base[j] = opaque(reinterpret_cast<uint64_t>(P.x) + (row < P.n_rows ? e : 0));
-        }
-      };
-      auto load = [&](uint4* vh, uint4* vl) -> int {   // loads chunk (w_l, c0_l), advances the cursor, returns its k extent
-        const int kchunk = 16 * min(P.kc16, P.k16 - c0_l);
+        for (int half = 0; half < 2; ++half) {
+          uint4 vh[4], vl[4];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) { vh[j] = make_uint4(0, 0, 0, 0); vl[j] = make_uint4(0, 0, 0, 0); }
-        if (q * 8 < kchunk) {
-          const ConvTap e = table[(c0_l * 16 + q * 8) >> 3];
-          const long long ob = e.off;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const bool ok = (unsigned)(ay[j] + e.tdy) < (unsigned)cm.H && (unsigned)(bx[j] + e.tdx) < (unsigned)cm.W;
+          for (int jj = 0; jj < 4; ++jj) {
+            const ConvRowInfo ri = info[rs + 16 * (half * 4 + jj)];
+            const bool ok = (unsigned)(ri.ay + e.tdy) < (unsigned)cm.H && (unsigned)(ri.bx + e.tdx) < (unsigned)cm.W;
+            vh[jj] = make_uint4(0, 0, 0, 0);
+            vl[jj] = make_uint4(0, 0, 0, 0);
             if (ok) {
-              vh[j] = __ldg(reinterpret_cast<const uint4*>(base[j] + ob));
-              vl[j] = __ldg(reinterpret_cast<const uint4*>(base[j] + ob + lo_delta));
+              vh[jj] = __ldg(reinterpret_cast<const uint4*>(ri.base + ob));
+              vl[jj] = __ldg(reinterpret_cast<const uint4*>(ri.base + ob + lo_delta));
+            }
+          }
+          if (!waited) { const long long W0 = clock64(); mbar_wait(bar_empty + 8 * slot, phase ^ 1); g_wait += clock64() - W0; waited = true; }
+          if (mine) {
+            uint8_t* dst = stage + (uint32_t)q * a_lbo + (uint32_t)(rs + 64 * half) * 16u;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              *reinterpret_cast<uint4*>(dst + jj * 256) = vh[jj];
+              *reinterpret_cast<uint4*>(dst + a_half + jj * 256) = vl[jj];
             }
           }
         }
-        c0_l += P.kc16;
-        if (c0_l >= P.k16) {
-          c0_l = 0;
-          w_l += gridDim.x;
-          if (w_l < n_items) rows_of(w_l);
-        }
-        return kchunk;
-      };
-      bool have = w_l < n_items;
-      uint4 ch[2], cl[2];
-      int ck = 0;
-      if (have) {
-        rows_of(w_l);
-        ck = load(ch, cl);
-      }
-      while (have) {
-        const bool have_next = w_l < n_items;
-        uint4 nh[2], nl[2];
-        int nk = 0;
-        if (have_next) nk = load(nh, nl);
-        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-        if (q * 8 < ck) {
-          uint8_t* a_hi = ring + (size_t)slot * P.stage_bytes + st_hl;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            *reinterpret_cast<uint4*>(a_hi + j * 1024) = ch[j];
-            *reinterpret_cast<uint4*>(a_hi + a_half + j * 1024) = cl[j];
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * slot);   // (512 per-thread arrivals on one barrier word serialise)
-        if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) { ch[j] = nh[j]; cl[j] = nl[j]; }
-        ck = nk;
-        have = have_next;
-      }
-    } else {
-    const uint32_t st_off = (uint32_t)(q >> 1) * kCvALbo + (uint32_t)(q & 1) * 8u + (uint32_t)rs * 16u;
-    const float xs = SCALED ? __ldg(P.scales) : 1.f;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      uint64_t base[2];
-      int ay[2], bx[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int row = (w / P.n_tiles) * 128 + rs + 64 * j;
-        const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
-        ay[j] = row < P.n_rows ? a * cm.sy + cm.y0 : -30000;   // rows past the end fail every bounds test
-        bx[j] = b * cm.sx + cm.x0;
-        const long long e = cm.in_nchw ? ((long long)fr * cm.C * cm.H + ay[j]) * cm.W + bx[j]
-                                       : (((long long)fr * cm.H + ay[j]) * cm.W + bx[j]) * cm.pix;
-        base[j] = opaque(reinterpret_cast<uint64_t>(P.x + (row < P.n_rows ? e : 0)));
-      }
-      for (int c0 = 0; c0 < P.k16; c0 += P.kc16) {
-        const int kchunk = 16 * min(P.kc16, P.k16 - c0);  // k covered by this stage
-        float4 v[2][2];
-        // issue every load of this stage first (the only latency hiding a gather thread has), then convert
-#pragma unroll
+      } else {
+        const float xs = SCALED ? __ldg(P.scales) : 1.f;
+#pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           const int kl = hh * 32 + q * 4;
-          if (kl < kchunk) {
-            if (quads) {
-              const ConvTap e = table[(c0 * 16 + kl) >> 2];
-              const long long ob = e.off;
+          if (kl >= kchunk) break;   // uniform per q; the barrier wait below happens in pass 0
+          ConvTap e4[4];
+          if (quads) e4[0] = table[(c0 * 16 + kl) >> 2];
+          else {
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const bool ok = (unsigned)(ay[j] + e.tdy) < (unsigned)cm.H && (unsigned)(bx[j] + e.tdx) < (unsigned)cm.W;
-                v[hh][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok) v[hh][j] = __ldg(reinterpret_cast<const float4*>(base[j] + ob));
-              }
-            } else {
+            for (int i = 0; i < 4; ++i) e4[i] = table[c0 * 16 + kl + i];
+          }
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
+          for (int half = 0; half < 2; ++half) {
+            float4 v[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const ConvRowInfo ri = info[rs + 16 * (half * 4 + jj)];
+              if (quads) {
+                const bool ok = (unsigned)(ri.ay + e4[0].tdy) < (unsigned)cm.H && (unsigned)(ri.bx + e4[0].tdx) < (unsigned)cm.W;
+                v[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) v[jj] = __ldg(reinterpret_cast<const float4*>(ri.base + (long long)e4[0].off));
+              } else {
                 float el[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const ConvTap e = table[c0 * 16 + kl + i];
-                  const bool ok = (unsigned)(ay[j] + e.tdy) < (unsigned)cm.H && (unsigned)(bx[j] + e.tdx) < (unsigned)cm.W;
+                  const bool ok = (unsigned)(ri.ay + e4[i].tdy) < (unsigned)cm.H && (unsigned)(ri.bx + e4[i].tdx) < (unsigned)cm.W;
                   el[i] = 0.f;
-                  if (ok) el[i] = __ldg(reinterpret_cast<const float*>(base[j] + (long long)e.off));
+                  if (ok) el[i] = __ldg(reinterpret_cast<const float*>(ri.base + (long long)e4[i].off));
                 }
-                v[hh][j] = make_float4(el[0], el[1], el[2], el[3]);
+                v[jj] = make_float4(el[0], el[1], el[2], el[3]);
               }
             }
-          }
-        }
-        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-        uint8_t* a_hi = ring + (size_t)slot * P.stage_bytes + st_off;
-        uint8_t* a_lo = a_hi + a_half;
+            if (!waited) { const long long W0 = clock64(); mbar_wait(bar_empty + 8 * slot, phase ^ 1); g_wait += clock64() - W0; waited = true; }
+            uint8_t* dst = stage + (uint32_t)(hh * 4 + (q >> 1)) * a_lbo + (uint32_t)(q & 1) * 8u + (uint32_t)(rs + 64 * half) * 16u;
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (hh * 32 + q * 4 < kchunk) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              float4 x4 = v[hh][j];
+            for (int jj = 0; jj < 4; ++jj) {
+              float4 x4 = v[jj];
               if (SCALED) { x4.x *= xs; x4.y *= xs; x4.z *= xs; x4.w *= xs; }
               uint2 h, l;
               split2_f16(x4.x, x4.y, h.x, l.x);
               split2_f16(x4.z, x4.w, h.y, l.y);
-              const uint32_t o = (uint32_t)hh * 4u * kCvALbo + (uint32_t)j * 1024u;
-              *reinterpret_cast<uint2*>(a_hi + o) = h;
-              *reinterpret_cast<uint2*>(a_lo + o) = l;
+              *reinterpret_cast<uint2*>(dst + jj * 256) = h;
+              *reinterpret_cast<uint2*>(dst + a_half + jj * 256) = l;
             }
           }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_full + 8 * slot);   // (512 per-thread arrivals on one barrier word serialise)
-        if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
       }
+      if (!waited) mbar_wait(bar_empty + 8 * slot, phase ^ 1);   // a thread without work in this chunk still hands it over
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * slot);
+      phase ^= 1;   // G chunks ahead = the same slot, next phase
+      ch += G;
+      while (ch >= chunks_per_item) { ch -= chunks_per_item; ++it; }
     }
-    }  // fp32 input
+    g_loop = clock64() - G0;
+    if (P.dbg && blockIdx.x == 0 && p == 0) { P.dbg[3] = g_loop; P.dbg[4] = g_wait; }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // ================================ epilogue ================================
@@ -372,6 +387,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
     const int cout = P.cout;
     const float unscale = SCALED ? __ldg(P.scales + 2) : 1.f;
     uint32_t item = 0;
+    long long e_wait = 0, e_work = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++item) {
       const uint32_t buf = item & 1u, use = item >> 1;
       const int n_tile = w % P.n_tiles;
@@ -380,7 +396,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
       const int fr = row / per_frame, rem = row - fr * per_frame, a = rem / cm.RB, b = rem - a * cm.RB;
       const int oy = a * cm.osy + cm.oy0, ox = b * cm.osx + cm.ox0;
       const int n0 = n_tile * P.NP, ncols = min(P.NP, P.n_total - n0);
+      const long long E0 = clock64();
       mbar_wait(bar_accf + 8 * buf, use & 1u);
+      const long long E1 = clock64();
+      e_wait += E1 - E0;
       tc_fence_after();
       for (int c = 0; c < ncols; c += 16) {
         float v[16];
@@ -462,6 +481,28 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 if (j < nq) op[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+            }
+          }
+        } else if (have_cols) {
+          // scalar stores with the per-feature table: one shared-memory read replaces the class / offset arithmetic
+          const long long rb_d = cm.out_nchw ? ((long long)fr * cout * cm.Ho + oy) * cm.Wo + ox
+                                             : (((long long)fr * cm.Ho + oy) * cm.Wo + ox) * cout;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i < cnt) {
+              const ConvCol cc = cols[nb + i];
+              if (oy + cc.py < cm.Ho && ox + cc.px < cm.Wo) {
+                const size_t od = (size_t)(rb_d + cc.off);
+                const size_t o = P.out_ld ? (size_t)fr * P.out_ld + cc.pad : od;
+                float y = fmaf(v[i], unscale, cc.bias);
+                if (P.act_elu) y = act_t<ACT_ELU>(y);
+                else if (cm.relu) y = fmaxf(y, 0.f);
+                if (P.relu_mask) {
+                  const float m = __ldg(P.relu_mask + (P.mask_ld ? (size_t)fr * P.mask_ld + cc.pad : od));
+                  y *= m > 0.f ? 1.f : (P.mask_elu ? m + 1.f : 0.f);
+                }
+                P.out[o] = y;
+              }
             }
           }
         } else {
