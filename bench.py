@@ -42,6 +42,11 @@ def parse():
     ap.add_argument("--rows-per-gpu", type=int, default=75776, help="start states per GPU; default = 4 waves of 148 SMs x 128-row tiles")
     ap.add_argument("--cpu-rows", type=int, default=4096, help="rows per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="imagine", choices=["imagine", "update"],
+                    help="imagine = the headline sweep (default, what the driver runs); update = one full training iteration "
+                         "(Agent.train_dynamics + train_actor_critic) with the replay batch sharded over the ranks (SURVEY 8d Config 2-4)")
+    ap.add_argument("--algo", default="repo", choices=["repo", "dreamer", "tia"], help="--workload update: trainer wiring")
+    ap.add_argument("--global-batch", type=int, default=50, help="--workload update: sequences per iteration over all ranks")
     return ap.parse_args()
 
 
@@ -417,10 +422,80 @@ def run_gpu(a):
         dist.destroy_process_group()
 
 
+def run_update(a):
+    """One training iteration at the reference's default sizes, data parallel over the replay batch: every rank takes
+    its columns of the (50, B, 3, 64, 64) batch (uneven shards allowed: 50 over 8 = 7,7,6,6,6,6,6,6), weights its losses
+    by B_local / B, and the flat gradient buckets are all-reduced inside FlatAdam.step (one NCCL collective per
+    parameter group).  Strong scaling: the global batch is fixed."""
+    import torch
+    import torch.distributed as dist
+    from oracle import rssm_oracle as O
+    from repo_b200 import parallel
+    from repo_b200.trainer import Agent, Config
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T, B, A = 50, a.global_batch, DIMS["action"]
+    agent = Agent(Config(batch_size=B, chunk_size=T), A, algo=a.algo, device=dev)
+    agent.optimizers()
+    c0, cn = parallel.shard_rows(B, rank, world)
+    full = O.make_train_batch(7, T, B, A)
+    batch = {k: v[:, c0:c0 + cn].contiguous().to(dev) for k, v in full.items()}
+    st = {}
+
+    def wm():
+        st["b"], st["s"] = agent.train_dynamics(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"])
+
+    def ac():
+        agent.train_actor_critic(st["b"].flatten(0, 1), st["s"].flatten(0, 1))
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return parallel.max_over_ranks(e0.elapsed_time(e1) / n, dev)
+
+    for _ in range(max(a.warmup, 3)):
+        wm(); ac()
+    sampler = ClockSampler(local)
+    sampler.start()
+    it_ms = timed(lambda: (wm(), ac()), a.steps)
+    clocks = sampler.stop()
+    wm_ms = timed(wm, max(3, a.steps // 2))
+    ac_ms = timed(ac, max(3, a.steps // 2))
+    if rank == 0:
+        rows = (T - 1) * B
+        print(json.dumps({
+            "metric": "training iteration ms (world-model update + actor-critic update)", "value": it_ms, "unit": "ms",
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": it_ms, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16x3 split (fp32-grade products, fp32 accumulate) on tcgen05",
+            "data": "synthetic",
+            "config": {"workload": f"{a.algo} training iteration at the reference defaults: batch {B} x chunk {T} of 64x64x3 frames, horizon {HORIZON}",
+                       "algo": a.algo, "global_batch": B, "chunk": T, "horizon": HORIZON,
+                       "parallelism": f"batch columns sharded x{world} (shards {[parallel.shard_rows(B, r, world)[1] for r in range(world)]}), "
+                                      "flat-bucket gradient all-reduce over NCCL"},
+            "world_model_update_ms": wm_ms, "actor_critic_update_ms": ac_ms,
+            "imagined_steps_per_s": rows * (HORIZON - 1) / ac_ms * 1e3, "clocks": clocks}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "update":
+        run_update(a)
     else:
         run_gpu(a)
 
