@@ -79,6 +79,8 @@ def grad_scales(g):
     if dev not in _SCRATCH:
         _SCRATCH[dev] = torch.zeros(2, dtype=torch.int32, device=dev)
     scales = torch.ones(6, dtype=torch.float32, device=dev)
+    if g.numel() == 0:
+        return scales
     g = g.contiguous()
     rc = _lib.lib().repo_b200_pow2_scale(_p(g), g.numel(), 16384.0, 1, _p(scales), _p(_SCRATCH[dev]), _stream())
     _lib.check(rc, "repo_b200_pow2_scale")
@@ -110,6 +112,8 @@ def conv_gemm(x, w_mat, bias, out, frames, n_total, cmap: ConvMap, relu_mask=Non
     `grad_scales`; the gradient is the gathered operand here, so callers pass the triple with the slots swapped)
     applied before the hi/lo split and undone on the accumulator."""
     L = _lib.lib()
+    if frames == 0:
+        return out   # empty batch: nothing to launch (zero-sized tensors have no device pointer)
     flags = int(_is_hl(x)) | (int(_is_hl(out)) << 1) | (int(_is_hl(relu_mask)) << 2)
     if w_mat.shape != (n_total, cmap.K):
         raise RuntimeError(f"conv_gemm: weight matrix {tuple(w_mat.shape)} != ({n_total}, {cmap.K})")
@@ -127,6 +131,8 @@ def conv_wgrad(x, grad_rows, frames, n_total, cmap: ConvMap, scales=None):
     grad_rows is (frames*RA*RB, ld >= n_total) fp32; `scales` = [s_x, s_g, 1/(s_x*s_g)] from `grad_scales`."""
     if grad_rows.dim() != 2 or not grad_rows.is_contiguous():
         raise RuntimeError("conv_wgrad: grad_rows must be a contiguous 2-D tensor")
+    if frames == 0 or grad_rows.shape[0] == 0:
+        return torch.zeros(n_total, cmap.K, device=x.device, dtype=torch.float32)
     if scales is None:
         scales = grad_scales(grad_rows)
     dw = torch.empty(n_total, cmap.K, device=x.device, dtype=torch.float32)
@@ -238,7 +244,7 @@ class _EncoderFn(torch.autograd.Function):
             acts.append(out)
         ctx.maps = maps
         ctx.save_for_backward(*acts, *params)
-        return acts[-1].reshape(F_, -1)  # NCHW flatten == hidden.view(-1, 1024) (encoder.py:39)
+        return acts[-1].reshape(F_, acts[-1].shape[1] * acts[-1].shape[2] * acts[-1].shape[3])  # NCHW flatten (encoder.py:39)
 
     @staticmethod
     def backward(ctx, g):
@@ -342,6 +348,8 @@ def _unshuffle(g, ra, rb, cpad, nchw=False):
         F_, ho, wo, c = g.shape
     G = torch.empty(F_, ra, rb, cpad, device=g.device, dtype=torch.float32)
     db = torch.empty(c, device=g.device, dtype=torch.float32)
+    if F_ == 0:
+        return G, db.zero_()
     rc = _lib.lib().repo_b200_grad_unshuffle(_p(g), int(nchw), _p(G), _p(db), F_, ra, rb, ho, wo, c, cpad, _stream())
     _lib.check(rc, "repo_b200_grad_unshuffle")
     return G, db

@@ -99,7 +99,8 @@ def act_kind(name: str) -> int:
 
 # ----------------------------------------------------------------------------------------------
 def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], row_tile: int = 0) -> torch.Tensor:
-    """y = x W^T + b through the layer machine (bring-up / building block)."""
+    """y = x W^T + b: the tcgen05 conv kernel run as a plain GEMM from 256 rows, the layer machine's one-step program
+    below that (building block of the hoisted embedding projection and the decoder's fc1)."""
     L = _lib.lib()
     x = _chk(x, "x")
     w = _chk(w, "w")
@@ -108,6 +109,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], row_tile
     assert w.shape[1] == in_f
     b = _chk(b, "b", (out_f,)) if b is not None else None
     y = torch.empty(rows, out_f, device=x.device, dtype=torch.float32)
+    if rows == 0:
+        return y
     ws = torch.empty(L.repo_b200_linear_workspace_bytes(in_f, out_f), dtype=torch.uint8, device=x.device)
     rc = L.repo_b200_linear_fwd(_ptr(x), in_f, rows, in_f, _ptr(w), _ptr(b), out_f, _ptr(y), out_f, _ptr(ws), ws.numel(),
                                 row_tile, _stream())

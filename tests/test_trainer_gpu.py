@@ -162,3 +162,24 @@ def test_graphed_updates_match_eager():
     for k, v in graphed.logs.items():
         assert np.isfinite(float(v)), k
         assert abs(float(v) - e_logs[k]) <= 0.25 * abs(e_logs[k]) + 0.5, (k, float(v), e_logs[k])
+
+
+def test_degenerate_batches():
+    """Edge shapes the reference's code also accepts: a single sequence of two frames (one posterior step), zero frames
+    through the conv stacks, and an actor-critic update from a single start row."""
+    from repo_b200.conv import VisualEncoder, VisualObservationModel
+    from repo_b200.trainer import Agent, Config
+    dev = torch.device("cuda:0")
+    enc, dec = VisualEncoder(1024).to(dev), VisualObservationModel(200, 30, 1024).to(dev)
+    with torch.no_grad():
+        assert enc(torch.zeros(0, 3, 64, 64, device=dev)).shape == (0, 1024)
+        assert dec(torch.zeros(0, 200, device=dev), torch.zeros(0, 30, device=dev)).shape == (0, 3, 64, 64)
+    agent = Agent(Config(batch_size=1, chunk_size=2), 6, algo="dreamer", device=dev)
+    batch = {k: v.to(dev) for k, v in O.make_train_batch(5, 2, 1, 6).items()}
+    b, s = agent.train_dynamics(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"])
+    assert b.shape == (1, 1, 200) and s.shape == (1, 1, 30)
+    agent.train_actor_critic(b.flatten(0, 1), s.flatten(0, 1))
+    for k, v in agent.logs.items():
+        assert np.isfinite(float(v)), k
+    for p in agent.model_params + list(agent.actor_model.parameters()) + list(agent.value_model.parameters()):
+        assert torch.isfinite(p).all()
