@@ -84,6 +84,28 @@ int repo_b200_imagine_fwd(const repo_b200_dims* dims, const repo_b200_rssm_weigh
  * [actor h1..h4 4H][action mean A][action std A].  g_*: incoming gradients of the four outputs (nullable).
  * Outputs: pre-activation gradients of the transition layers (d_p (.,2S), d_hp (.,H), d_gi/d_gh (.,3D), d_e (.,D))
  * and of the actor's fc5..fc1 (d_a5 (.,2A), d_a4..d_a1 (.,H)), plus gradients of the start rows (nullable). */
+/* ---- conditional (multitask) variants: ConditionalTransitionModel.imagine (rssm.py:225-248) with a
+ * ConditionalActorModel (actor_critic.py:105-148).  dims.action is the pseudo-action width (action + condition, what the
+ * reference passes to the base class, rssm.py:198-206); `condition` is (n_rows, cond_size), constant over the horizon;
+ * actor fc1 has belief + state + cond_size input columns ([belief | state | condition], actor_critic.py:131-133);
+ * eps_action / actions / d_a5 use the sampled width dims.action - cond_size.  cond_size = 0 is the plain call. */
+int repo_b200_imagine_cond_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const repo_b200_mlp_weights* actor,
+                               const repo_b200_mlp_weights* reward, const repo_b200_mlp_weights* value,
+                               const float* start_belief, const float* start_state, const float* condition, int cond_size,
+                               const float* eps_action, const float* eps_prior, float* beliefs, float* prior_states,
+                               float* prior_means, float* prior_std_devs, float* actions, float* rewards, float* values,
+                               float* returns, int horizon, int n_rows, int act_kind, float min_std, float a_mean_scale,
+                               float a_init_std, float a_min_std, float gamma, float lambda_, float* stash, void* workspace,
+                               size_t workspace_bytes, int flags, int row_tile, void* stream);
+int repo_b200_imagine_cond_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const repo_b200_mlp_weights* actor,
+                               int cond_size, const float* start_belief, const float* beliefs, const float* actions,
+                               const float* prior_std_devs, const float* eps_prior, const float* eps_action,
+                               const float* stash, const float* g_beliefs, const float* g_prior_states,
+                               const float* g_prior_means, const float* g_prior_std_devs, float* d_p, float* d_hp, float* d_gi,
+                               float* d_gh, float* d_e, float* d_a5, float* d_a4, float* d_a3, float* d_a2, float* d_a1,
+                               float* d_start_belief, float* d_start_state, int horizon, int n_rows, int act_kind,
+                               float min_std, float a_mean_scale, float a_min_std, void* stream);
+
 int repo_b200_imagine_stash_floats(const repo_b200_dims* dims);
 int repo_b200_imagine_bwd(const repo_b200_dims* dims, const repo_b200_rssm_weights* rssm,
                           const repo_b200_mlp_weights* actor, const float* start_belief, const float* beliefs,

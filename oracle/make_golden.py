@@ -147,6 +147,38 @@ def golden_imagine(R, name, dims, N, H, seed, scale):
     print(name, {k: tuple(v.shape) for k, v in save.items()})
 
 
+def golden_conditional(R, name, N, H, T, B, C, seed):
+    """ConditionalTransitionModel (rssm.py:187-248) + ConditionalActorModel (actor_critic.py:105-148): observe on
+    (actions, conditions) and imagine with a per-row condition, default sizes, injected noise."""
+    dims = dict(O.DEFAULT_DIMS)
+    D, S, A, Hd, E = dims["belief"], dims["state"], dims["action"], dims["hidden"], dims["embed"]
+    pdims = dict(dims, action=A + C)
+    tm = R.rssm.ConditionalTransitionModel(D, S, A, Hd, E, C, "elu")
+    tm.load_state_dict(O.make_transition_params(seed, pdims))
+    actor = R.actor_critic.ConditionalActorModel(D, S, Hd, A, C, "elu")
+    actor.load_state_dict(O.make_mlp_params(seed + 1, D + S + C, Hd, 2 * A, 4))
+    rs = np.random.RandomState(seed + 2)
+    cond = torch.from_numpy(rs.standard_normal((N, C)).astype(np.float32))
+    x = O.make_imagine_inputs(seed + 20, N, H, dims)
+    queue = []
+    for t in range(H - 1):
+        queue += [x["eps_action"][t], x["eps_prior"][t]]
+    with torch.no_grad(), NoiseInjector(queue):
+        im = tm.imagine(x["belief"], x["state"], cond, actor, H)
+    xo = O.make_observe_inputs(seed + 10, T, B, dims)
+    conds = torch.from_numpy(rs.standard_normal((T - 1, B, C)).astype(np.float32))
+    queue = []
+    for t in range(T - 1):
+        queue += [xo["eps_prior"][t], xo["eps_post"][t]]
+    with torch.no_grad(), NoiseInjector(queue):
+        ob = tm.observe(xo["prev_belief"], xo["prev_state"], xo["actions"], conds, xo["embeds"], xo["nonterms"])
+    save = dict(im_beliefs=im[0], im_prior_states=im[1], im_prior_means=im[2], im_prior_std_devs=im[3],
+                ob_beliefs=ob[0], ob_posterior_states=ob[4], ob_posterior_means=ob[5], ob_prior_std_devs=ob[3])
+    meta = dict(N=N, H=H, T=T, B=B, C=C, seed=seed)
+    np.savez(os.path.join(OUT, name + ".npz"), **np_(save), **{("meta_" + k): np.asarray(v) for k, v in meta.items()})
+    print(name, {k: tuple(v.shape) for k, v in save.items()})
+
+
 def golden_entropy(R, name, seed, M, A, K):
     rs = np.random.RandomState(seed)
     mean = torch.from_numpy((rs.standard_normal((M, A)) * 2.0).astype(np.float32))
@@ -214,6 +246,7 @@ def main():
     golden_imagine(R, "imagine_N8_H15", dims, N=8, H=15, seed=210, scale=1.0)
     golden_imagine(R, "imagine_N16_H15_hot", dims, N=16, H=15, seed=220, scale=2.0)
     golden_imagine(R, "imagine_tiny_dims", small, N=5, H=4, seed=230, scale=1.5)
+    golden_conditional(R, "conditional_N12_H7", N=12, H=7, T=5, B=6, C=4, seed=260)
     golden_entropy(R, "entropy_M50_A6_K100", seed=300, M=50, A=6, K=100)
     golden_lambda_return(R, "lambda_return")
     golden_replay(R, "replay_indices")

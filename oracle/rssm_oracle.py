@@ -211,6 +211,22 @@ def lambda_return(rewards, values, discounts, bootstrap, lambda_=0.95):
     return torch.stack(out, 0)
 
 
+def imagine_conditional(p: Params, ap: Params, prev_belief, prev_state, condition, eps_action, eps_prior, horizon: int,
+                        act="elu", min_std=0.1, prec: Precision = EXACT):
+    """ConditionalTransitionModel.imagine (rssm.py:225-248) with a ConditionalActorModel (actor_critic.py:131-148): the
+    actor sees [belief | state | condition] (detached), the dynamics see the pseudo-action [action | condition]."""
+    belief, state = prev_belief, prev_state
+    outs = [[] for _ in range(5)]
+    for t in range(horizon - 1):
+        mean, std = actor_forward(ap, belief.detach(), torch.cat([state.detach(), condition], 1), prec=prec)
+        action = torch.tanh(mean + std * eps_action[t])
+        belief = compute_belief(p, belief, state, torch.cat([action, condition], 1), act, prec)
+        state, pm, pd = compute_prior_state(p, belief, eps_prior[t], act, min_std, prec)
+        for lst, v in zip(outs, (belief, state, pm, pd, action)):
+            lst.append(v)
+    return [torch.stack(o, 0) for o in outs]
+
+
 def imagine_returns(reward_preds, value_preds, gamma=0.99, lambda_=0.95):
     """dreamer.py:341-349 — H-2 rows, bootstrap = value_preds[-1]."""
     disc = gamma * torch.ones_like(reward_preds)

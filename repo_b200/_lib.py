@@ -35,7 +35,7 @@ class MlpWeights(C.Structure):
 
 EXPORTS = [
     "repo_b200_version", "repo_b200_last_error", "repo_b200_device_info", "repo_b200_debug_flags", "repo_b200_debug_clock",
-    "repo_b200_imagine_workspace_bytes", "repo_b200_imagine_fwd", "repo_b200_imagine_stash_floats", "repo_b200_imagine_bwd",
+    "repo_b200_imagine_workspace_bytes", "repo_b200_imagine_fwd", "repo_b200_imagine_stash_floats", "repo_b200_imagine_bwd", "repo_b200_imagine_cond_fwd", "repo_b200_imagine_cond_bwd",
     "repo_b200_observe_workspace_bytes", "repo_b200_observe_fwd", "repo_b200_observe_stash_floats", "repo_b200_observe_bwd",
     "repo_b200_linear_workspace_bytes", "repo_b200_linear_fwd",
     "repo_b200_head_workspace_bytes", "repo_b200_head_fwd",
@@ -72,6 +72,13 @@ def lib():
         [C.POINTER(Dims), C.POINTER(RssmWeights), C.POINTER(MlpWeights), C.POINTER(MlpWeights), C.POINTER(MlpWeights)]
         + [vp] * 12 + [ci, ci, ci] + [cf] * 6 + [vp, vp, sz, ci, ci, vp])
     L.repo_b200_imagine_fwd.restype = ci
+    L.repo_b200_imagine_cond_fwd.argtypes = (
+        [C.POINTER(Dims), C.POINTER(RssmWeights), C.POINTER(MlpWeights), C.POINTER(MlpWeights), C.POINTER(MlpWeights)]
+        + [vp, vp, vp, ci] + [vp] * 10 + [ci, ci, ci] + [cf] * 6 + [vp, vp, sz, ci, ci, vp])
+    L.repo_b200_imagine_cond_fwd.restype = ci
+    L.repo_b200_imagine_cond_bwd.argtypes = ([C.POINTER(Dims), C.POINTER(RssmWeights), C.POINTER(MlpWeights), ci] + [vp] * 23
+                                             + [ci, ci, ci, cf, cf, cf, vp])
+    L.repo_b200_imagine_cond_bwd.restype = ci
     L.repo_b200_imagine_stash_floats.argtypes = [C.POINTER(Dims)]
     L.repo_b200_imagine_stash_floats.restype = ci
     L.repo_b200_imagine_bwd.argtypes = ([C.POINTER(Dims), C.POINTER(RssmWeights), C.POINTER(MlpWeights)] + [vp] * 23

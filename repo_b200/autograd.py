@@ -147,7 +147,7 @@ class ImagineFn(torch.autograd.Function):
     are detached exactly like `policy.get_action(belief.detach(), state.detach())` (rssm.py:170)."""
 
     @staticmethod
-    def forward(ctx, act, min_std, horizon, a_scalars, prev_belief, prev_state, eps_action, eps_prior, *params):
+    def forward(ctx, act, min_std, horizon, a_scalars, prev_belief, prev_state, eps_action, eps_prior, cond, *params):
         tp, ap = params[:len(PARAM_KEYS)], params[len(PARAM_KEYS):]
         named, anamed = dict(zip(PARAM_KEYS, tp)), dict(zip(ACTOR_KEYS, ap))
         d = ops.dims_of(named)
@@ -157,8 +157,10 @@ class ImagineFn(torch.autograd.Function):
         mean_scale, init_std, a_min_std = a_scalars
         out = ops.imagine_fwd({k: v.detach() for k, v in named.items()}, {k: v.detach() for k, v in anamed.items()}, None, None,
                               prev_belief.detach(), prev_state.detach(), eps_action, eps_prior, horizon, act=act,
-                              min_std=min_std, mean_scale=mean_scale, init_std=init_std, actor_min_std=a_min_std, stash=stash)
+                              min_std=min_std, mean_scale=mean_scale, init_std=init_std, actor_min_std=a_min_std, stash=stash,
+                              cond=None if cond is None else cond.detach())
         ctx.meta = (act, min_std, horizon, a_scalars, d)
+        ctx.cond = None if cond is None else cond.detach()
         outs = (out["beliefs"], out["prior_states"], out["prior_means"], out["prior_std_devs"])
         ctx.save_for_backward(prev_belief, prev_state, eps_action, eps_prior, stash, out["actions"], *outs, *params)
         ctx.mark_non_differentiable(out["actions"])
@@ -174,6 +176,9 @@ class ImagineFn(torch.autograd.Function):
         tp, ap = params[:len(PARAM_KEYS)], params[len(PARAM_KEYS):]
         named, anamed = dict(zip(PARAM_KEYS, tp)), dict(zip(ACTOR_KEYS, ap))
         D, S, A, Hd = d.belief, d.state, d.action, d.hidden
+        cond = ctx.cond
+        csz = 0 if cond is None else cond.shape[1]
+        A = A - csz                                      # sampled action width
         N, T = prev_belief.shape[0], horizon - 1
         dev = prev_belief.device
         c = lambda g: None if g is None else g.contiguous().float()
@@ -187,15 +192,15 @@ class ImagineFn(torch.autograd.Function):
         W = ops.rssm_struct(named, keep)
         Am = ops.mlp_struct(anamed, 5, keep, "actor")
         p = ops._ptr
-        rc = _lib.lib().repo_b200_imagine_bwd(
-            C.byref(d), C.byref(W), C.byref(Am), p(prev_belief.contiguous()), p(beliefs), p(actions), p(prior_sd), p(eps_prior),
+        rc = _lib.lib().repo_b200_imagine_cond_bwd(
+            C.byref(d), C.byref(W), C.byref(Am), csz, p(prev_belief.contiguous()), p(beliefs), p(actions), p(prior_sd), p(eps_prior),
             p(eps_action), p(stash), p(c(g_b)), p(c(g_s)), p(c(g_m)), p(c(g_sd)), p(d_p), p(d_hp), p(d_gi), p(d_gh), p(d_e),
             p(d_a5), p(d_a4), p(d_a3), p(d_a2), p(d_a1), p(d_b0), p(d_s0), horizon, N, ops.act_kind(act), float(min_std),
             float(mean_scale), float(a_min_std), ops._stream())
-        _lib.check(rc, "repo_b200_imagine_bwd")
+        _lib.check(rc, "repo_b200_imagine_cond_bwd")
 
         flat = lambda x: x.reshape(T * N, -1)
-        need = dict(zip(PARAM_KEYS + ["actor." + k for k in ACTOR_KEYS], ctx.needs_input_grad[8:]))
+        need = dict(zip(PARAM_KEYS + ["actor." + k for k in ACTOR_KEYS], ctx.needs_input_grad[9:]))
         gp = {k: None for k in need}
 
         def lin(wkey, bkey, dpre, inp):
@@ -209,26 +214,27 @@ class ImagineFn(torch.autograd.Function):
         off = 5 * D + Hd
         e, hp = stash[..., :D], stash[..., 5 * D:5 * D + Hd]
         h = [stash[..., off + i * Hd: off + (i + 1) * Hd] for i in range(4)]
-        lin("fc_embed_state_action.weight", "fc_embed_state_action.bias", d_e, torch.cat([s_in, actions], -1))
+        crep = [] if cond is None else [cond.unsqueeze(0).expand(T, N, csz)]   # the condition is constant over the horizon
+        lin("fc_embed_state_action.weight", "fc_embed_state_action.bias", d_e, torch.cat([s_in, actions] + crep, -1))
         lin("rnn.weight_ih", "rnn.bias_ih", d_gi, e)
         lin("rnn.weight_hh", "rnn.bias_hh", d_gh, b_in)
         lin("fc_embed_belief_prior.weight", "fc_embed_belief_prior.bias", d_hp, beliefs)
         lin("fc_state_prior.weight", "fc_state_prior.bias", d_p, hp)
-        lin("actor.fc1.weight", "actor.fc1.bias", d_a1, torch.cat([b_in, s_in], -1))
+        lin("actor.fc1.weight", "actor.fc1.bias", d_a1, torch.cat([b_in, s_in] + crep, -1))
         lin("actor.fc2.weight", "actor.fc2.bias", d_a2, h[0])
         lin("actor.fc3.weight", "actor.fc3.bias", d_a3, h[1])
         lin("actor.fc4.weight", "actor.fc4.bias", d_a4, h[2])
         lin("actor.fc5.weight", "actor.fc5.bias", d_a5, h[3])
-        return (None, None, None, None, d_b0 if need_b0 else None, d_s0 if need_s0 else None, None, None,
+        return (None, None, None, None, d_b0 if need_b0 else None, d_s0 if need_s0 else None, None, None, None,
                 *[gp[k] for k in PARAM_KEYS], *[gp["actor." + k] for k in ACTOR_KEYS])
 
 
-def imagine(model, prev_belief, prev_state, policy, horizon, eps_action, eps_prior):
+def imagine(model, prev_belief, prev_state, policy, horizon, eps_action, eps_prior, cond=None):
     tparams = [dict(model.named_parameters())[k] for k in PARAM_KEYS]
     aparams = [dict(policy.named_parameters())[k] for k in ACTOR_KEYS]
     scal = (float(policy._mean_scale), float(policy._init_std), float(policy._min_std))
     *outs, actions = ImagineFn.apply(model.activation_function, model.min_std_dev, horizon, scal, prev_belief, prev_state,
-                                     eps_action, eps_prior, *tparams, *aparams)
+                                     eps_action, eps_prior, cond, *tparams, *aparams)
     return list(outs), actions
 
 

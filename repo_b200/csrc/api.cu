@@ -263,6 +263,7 @@ int check_act(int act) {
 
 void set_dims(VmParams& P, const repo_b200_dims* d) {
   P.D = d->belief; P.S = d->state; P.A = d->action; P.Hd = d->hidden;
+  P.A_act = d->action;
   P.kx16 = cdiv(d->belief + d->state + d->action, 16);
   P.kh16 = cdiv(std::max(d->belief, d->hidden), 16);
 }
@@ -270,16 +271,30 @@ void set_dims(VmParams& P, const repo_b200_dims* d) {
 // imagine stash record per (t,row): [e D][r D][z D][n D][h_n D][prior hidden H][actor h1..h4 4H][action mean A][action std A]
 void build_imagine(Builder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W,
                    const repo_b200_mlp_weights* actor, const repo_b200_mlp_weights* reward,
-                   const repo_b200_mlp_weights* value, int act, bool stash = false) {
-  const int D = d->belief, S = d->state, A = d->action, Hd = d->hidden;
+                   const repo_b200_mlp_weights* value, int act, bool stash = false, int cond = 0) {
+  // cond > 0: ConditionalTransitionModel / ConditionalActorModel (rssm.py:187-248, actor_critic.py:105-148).  X's action slot is
+  // [sampled action (A - cond) | condition (cond)]: the embedding layer reads all of it ([state | action | condition], the
+  // reference's concat order), the actor reads [belief | state] and, as a second accumulating window, the condition columns.
+  const int D = d->belief, S = d->state, A = d->action, Hd = d->hidden, Aa = A - cond;
   const int kD16 = cdiv(D, 16), kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);
   const int so = 5 * D + Hd;  // actor block of the stash
   set_dims(b.P, d);
+  b.P.A_act = Aa;
   // actor (always ELU: actor_critic.py:58 + the positional-arg quirk at dreamer.py:99-105)
-  b.dense_to_h(actor->w[0], actor->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, ACT_ELU, 0, stash ? so : 0xFFFF);
+  if (cond > 0) {
+    const int kc0 = (D + S + Aa) / 16, kx16 = cdiv(D + S + A, 16);
+    VmStage& s = b.begin_stage();
+    b.gemm_rows(actor->w[0], D + S + cond, 0, Hd, 0, D + S, 0, kBS16, 0, 0, 0, 0);
+    b.gemm_rows(actor->w[0], D + S + cond, 0, Hd, D + S, cond, (D + S + Aa) - 16 * kc0, kx16 - kc0, 0, kc0, 0, 1);
+    b.bias_rows(actor->b[0], 0, nullptr, 0, Hd);
+    s.stash_off = (uint16_t)(stash ? so : 0xFFFF);
+    b.end_stage(s, EPI_ACT_H, 0, cdiv(Hd, 128), 0, Hd, ACT_ELU);
+  } else {
+    b.dense_to_h(actor->w[0], actor->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, ACT_ELU, 0, stash ? so : 0xFFFF);
+  }
   for (int i = 1; i < 4; ++i)
     b.dense_to_h(actor->w[i], actor->b[i], Hd, Hd, 0, Hd, 0, kH16, 1, 0, ACT_ELU, 0, stash ? so + i * Hd : 0xFFFF);
-  b.gaussian_head(actor->w[4], actor->b[4], Hd, A, kH16, EPI_ACTION, 0, stash ? so + 4 * Hd : 0xFFFF);
+  b.gaussian_head(actor->w[4], actor->b[4], Hd, Aa, kH16, EPI_ACTION, 0, stash ? so + 4 * Hd : 0xFFFF);
   b.belief_update(W, D, S, A, act, stash);
   b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act, 0,
                stash ? 5 * D : 0xFFFF);
@@ -602,7 +617,23 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
                           int horizon, int n_rows, int act_kind, float min_std, float a_mean_scale, float a_init_std,
                           float a_min_std, float gamma, float lambda_, float* stash, void* ws, size_t ws_bytes,
                           int flags, int row_tile, void* stream) {
+  return repo_b200_imagine_cond_fwd(d, W, actor, reward, value, start_belief, start_state, nullptr, 0, eps_action, eps_prior,
+                                    beliefs, prior_states, prior_means, prior_std_devs, actions, rewards, values, returns,
+                                    horizon, n_rows, act_kind, min_std, a_mean_scale, a_init_std, a_min_std, gamma, lambda_,
+                                    stash, ws, ws_bytes, flags, row_tile, stream);
+}
+
+int repo_b200_imagine_cond_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const repo_b200_mlp_weights* actor,
+                               const repo_b200_mlp_weights* reward, const repo_b200_mlp_weights* value,
+                               const float* start_belief, const float* start_state, const float* condition, int cond_size,
+                               const float* eps_action, const float* eps_prior, float* beliefs, float* prior_states,
+                               float* prior_means, float* prior_std_devs, float* actions, float* rewards, float* values,
+                               float* returns, int horizon, int n_rows, int act_kind, float min_std, float a_mean_scale,
+                               float a_init_std, float a_min_std, float gamma, float lambda_, float* stash, void* ws,
+                               size_t ws_bytes, int flags, int row_tile, void* stream) {
   int rc = check_dims(d);
+  if (cond_size < 0 || cond_size >= (d ? d->action : 1) || (cond_size > 0 && !condition))
+    return fail(-1, "imagine: condition size %d must be in [0, action slot) and come with a tensor", cond_size);
   if (rc) return rc;
   if ((rc = check_act(act_kind))) return rc;
   if (!W || !actor) return fail(-1, "imagine: rssm / actor weights are required");
@@ -614,14 +645,15 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
     return fail(-1, "imagine: NULL input/output pointer");
   if ((reward && !rewards) || (value && !values)) return fail(-1, "imagine: rewards/values output missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool rows = !stash && use_rows_kernel(d, n_rows, row_tile);  // the activation stash is written by the vm kernel
+  // (the activation stash and the conditional variant are served by the vm kernel)
+  const bool rows = !stash && cond_size == 0 && use_rows_kernel(d, n_rows, row_tile);
   Builder b;
   RBuilder rbld;
   if (rows) {
     build_imagine_rows(rbld, d, W, actor, reward, value, act_kind);
     if ((rc = rbld.bind_and_pack(ws, ws_bytes, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
   } else {
-    build_imagine(b, d, W, actor, reward, value, act_kind, stash != nullptr);
+    build_imagine(b, d, W, actor, reward, value, act_kind, stash != nullptr, cond_size);
     if ((rc = b.bind_and_pack(ws, ws_bytes, !(flags & REPO_B200_WEIGHTS_PACKED), st))) return rc;
     b.P.stash = stash;
     b.P.stash_ld = 5 * d->belief + 5 * d->hidden + 2 * d->action;
@@ -634,6 +666,7 @@ int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   P.gamma = gamma; P.lambda = lambda_;
   P.one_minus_lambda = (float)(1.0 - (double)lambda_);
   P.init_belief = start_belief; P.init_state = start_state;
+  P.cond = cond_size > 0 ? condition : nullptr;
   P.eps_action = eps_action; P.eps_prior = eps_prior;
   P.beliefs = beliefs; P.prior_s = prior_states; P.prior_m = prior_means; P.prior_sd = prior_std_devs;
   P.actions_out = actions;
@@ -718,7 +751,22 @@ int repo_b200_imagine_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
                           float* d_a5, float* d_a4, float* d_a3, float* d_a2, float* d_a1, float* d_start_belief,
                           float* d_start_state, int horizon, int n_rows, int act_kind, float min_std,
                           float a_mean_scale, float a_min_std, void* stream) {
+  return repo_b200_imagine_cond_bwd(d, W, actor, 0, start_belief, beliefs, actions, prior_std_devs, eps_prior, eps_action, stash,
+                                    g_beliefs, g_prior_states, g_prior_means, g_prior_std_devs, d_p, d_hp, d_gi, d_gh, d_e, d_a5,
+                                    d_a4, d_a3, d_a2, d_a1, d_start_belief, d_start_state, horizon, n_rows, act_kind, min_std,
+                                    a_mean_scale, a_min_std, stream);
+}
+
+int repo_b200_imagine_cond_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const repo_b200_mlp_weights* actor,
+                               int cond_size, const float* start_belief, const float* beliefs, const float* actions,
+                               const float* prior_std_devs, const float* eps_prior, const float* eps_action,
+                               const float* stash, const float* g_beliefs, const float* g_prior_states,
+                               const float* g_prior_means, const float* g_prior_std_devs, float* d_p, float* d_hp, float* d_gi,
+                               float* d_gh, float* d_e, float* d_a5, float* d_a4, float* d_a3, float* d_a2, float* d_a1,
+                               float* d_start_belief, float* d_start_state, int horizon, int n_rows, int act_kind,
+                               float min_std, float a_mean_scale, float a_min_std, void* stream) {
   int rc = check_dims(d);
+  if (cond_size < 0 || cond_size >= (d ? d->action : 1)) return fail(-1, "imagine_bwd: bad condition size %d", cond_size);
   if (rc) return rc;
   if ((rc = check_act(act_kind))) return rc;
   if (horizon < 1 || n_rows < 0) return fail(-1, "imagine_bwd: bad sizes");
@@ -729,6 +777,7 @@ int repo_b200_imagine_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
     return fail(-1, "imagine_bwd: NULL pointer");
   ImgBwdParams P{};
   P.T = horizon - 1; P.N = n_rows; P.D = d->belief; P.S = d->state; P.A = d->action; P.Hd = d->hidden;
+  P.A_act = d->action - cond_size;
   P.act = act_kind; P.min_std = min_std; P.a_mean_scale = a_mean_scale; P.a_min_std = a_min_std;
   P.w_e = W->fc_embed_state_action_w; P.w_ih = W->rnn_w_ih; P.w_hh = W->rnn_w_hh;
   P.w_p1 = W->fc_embed_belief_prior_w; P.w_p2 = W->fc_state_prior_w;

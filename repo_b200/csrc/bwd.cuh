@@ -198,6 +198,7 @@ namespace rb {
 // outputs -> dynamics -> earlier (belief, state), never through the actor's inputs.
 // =====================================================================================================
 struct ImgBwdParams {
+  int A_act;   // sampled action width (A = slot width incl. a trailing condition)
   int T, N, D, S, A, Hd;
   int act;
   float min_std, a_mean_scale, a_min_std;
@@ -239,7 +240,9 @@ __device__ __forceinline__ void col_dot_rows(const float* __restrict__ W, int ld
 template <int RB>
 __global__ void __launch_bounds__(256) imagine_bwd_kernel(const __grid_constant__ ImgBwdParams P) {
   extern __shared__ float sm[];
-  const int D = P.D, S = P.S, A = P.A, Hd = P.Hd, T = P.T, N = P.N;
+  // A = width of the [action | condition] slot that enters the embedding layer, Aa = sampled action width (Aa == A
+  // unless the model is conditional: rssm.py:225-236; the condition columns carry no gradient)
+  const int D = P.D, S = P.S, A = P.A, Aa = P.A_act, Hd = P.Hd, T = P.T, N = P.N;
   // all vectors are [feature][RB] so one weight element meets RB rows with a vector LDS
   float* db = sm;                  // D
   float* ds = db + D * RB;         // S
@@ -351,23 +354,23 @@ __global__ void __launch_bounds__(256) imagine_bwd_kernel(const __grid_constant_
       for (int r = 0; r < RB; ++r) {
         const int row = row0 + r;
         if (j < S) ds[j * RB + r] = acc[r];
-        else {
+        else if (j - S < Aa) {
           const int a = j - S;
           float dm = 0.f, dsr = 0.f;
           if (row < N) {
             const size_t tr = (size_t)t * N + row;
-            const float av = P.actions[tr * A + a];
+            const float av = P.actions[tr * Aa + a];
             const float du = acc[r] * (1.f - av * av);           // a = tanh(u)
             const float* st = P.stash + tr * P.stash_ld + 5 * D + 5 * Hd;
             const float mean = st[a], sd = st[A + a];
             const float mm = mean / P.a_mean_scale;
             dm = du * (1.f - mm * mm);                            // mean = ms * tanh(m / ms)
-            dsr = du * P.eps_action[tr * A + a] * (1.f - __expf(-(sd - P.a_min_std)));
-            P.d_a5[tr * 2 * A + a] = dm;
-            P.d_a5[tr * 2 * A + A + a] = dsr;
+            dsr = du * P.eps_action[tr * Aa + a] * (1.f - __expf(-(sd - P.a_min_std)));
+            P.d_a5[tr * 2 * Aa + a] = dm;
+            P.d_a5[tr * 2 * Aa + Aa + a] = dsr;
           }
           d5[a * RB + r] = dm;
-          d5[(A + a) * RB + r] = dsr;
+          d5[(Aa + a) * RB + r] = dsr;
         }
       }
     }
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(256) imagine_bwd_kernel(const __grid_constant_
     const float* Wk[4] = {P.w_a5, P.w_a4, P.w_a3, P.w_a2};
     float* outk[4] = {P.d_a4, P.d_a3, P.d_a2, P.d_a1};
     const float* src = d5;
-    int nsrc = 2 * A;
+    int nsrc = 2 * Aa;
     float* dst = dh;
     for (int l = 0; l < 4; ++l) {
       const int hoff = 5 * D + Hd + (3 - l) * Hd;  // h4, h3, h2, h1

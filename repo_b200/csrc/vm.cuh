@@ -89,7 +89,9 @@ struct ConvMap {
 struct VmParams {
   int n_steps, n_stages;
   int N;                 // rows
-  int D, S, A, Hd;       // belief, state, action, hidden sizes
+  int D, S, A, Hd;       // belief, state, action, hidden sizes (A = width of X's action slot)
+  int A_act;             // sampled action width; A - A_act trailing columns of the slot hold a constant per-row condition
+  const float* cond;     // (N, A - A_act) or null: ConditionalTransitionModel.imagine (rssm.py:225-236)
   int kx16, kh16;        // k16 slabs held by X / H
   float min_std;         // RSSM min std
   float a_mean_scale, a_init_std, a_min_std;
@@ -374,6 +376,13 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
             const int n = idx / A, k = idx - n * A, row = row0 + n;
             if (row < N) TL::put(x_hi, x_lo, n, D + S + k, P.actions_in[(size_t)row * A + k]);
           }
+        if (P.cond) {   // constant tail of the action slot: written once, the action epilogue only touches the first A_act columns
+          const int Cn = A - P.A_act;
+          for (int idx = et; idx < NT * Cn; idx += kEpiThreads) {
+            const int n = idx / Cn, k = idx - n * Cn, row = row0 + n;
+            if (row < N) TL::put(x_hi, x_lo, n, D + S + P.A_act + k, P.cond[(size_t)row * Cn + k]);
+          }
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(bar_act);
@@ -554,17 +563,18 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
 
           case EPI_ACTION: {
             const int j = lf;
-            const bool vj = j < A;
+            const int Aa = P.A_act;   // sampled action width (== A unless a condition rides in the slot)
+            const bool vj = j < Aa;
             const float bm = P.bias[(st.bias_tile) * 128 + lf];
             const float bs = P.bias[(st.bias_tile + 1) * 128 + lf];
-            const bool any_valid_in_warp = (q * 32) < A;
+            const bool any_valid_in_warp = (q * 32) < Aa;
             const float inv_ms = 1.f / P.a_mean_scale;
 #pragma unroll 1
             for (int c = 0; c < NT / 16; ++c) {
               float vm[16], vs[16], e[16];
               const int r0 = row0 + c * 16;
-              const size_t o0 = (trow + r0) * A + j;
-              if (any_valid_in_warp) ldg16(e, P.eps_action + o0, A, r0, N, vj);
+              const size_t o0 = (trow + r0) * Aa + j;
+              if (any_valid_in_warp) ldg16(e, P.eps_action + o0, Aa, r0, N, vj);
               tmem_ld16(tacc + c * 16, vm);
               tmem_ld16(tacc + NT + c * 16, vs);
               tmem_ld_wait();
@@ -574,7 +584,7 @@ __global__ void __launch_bounds__(kThreads, 1) rssm_vm_kernel(const __grid_const
                   const float mean = P.a_mean_scale * tanh_f((vm[i] + bm) * inv_ms);
                   const float sd = softplus_f(vs[i] + bs + P.a_init_std) + P.a_min_std;
                   const float a = tanh_f(mean + sd * e[i]);
-                  if (r0 + i < N && P.actions_out) P.actions_out[o0 + (size_t)i * A] = a;
+                  if (r0 + i < N && P.actions_out) P.actions_out[o0 + (size_t)i * Aa] = a;
                   if (P.stash && st.stash_off != 0xFFFF && r0 + i < N) {
                     float* sp = P.stash + (trow + r0 + i) * P.stash_ld + st.stash_off + j;
                     sp[0] = mean; sp[A] = sd;

@@ -85,6 +85,26 @@ class ActorModel(nn.Module):
         return dist.mode() if det else dist.rsample()
 
 
+class ConditionalActorModel(ActorModel):
+    """actor_critic.py:105-148: ActorModel over [belief | state | condition]."""
+
+    def __init__(self, belief_size, state_size, hidden_size, action_size, condition_size, dist="tanh_normal",
+                 activation_function="elu", min_std=0.1, init_std=0.0, mean_scale=5):
+        super().__init__(belief_size, state_size + condition_size, hidden_size, action_size, dist, activation_function, min_std,
+                         init_std, mean_scale)
+        self.condition_size = condition_size
+
+    def forward(self, belief, state, condition):
+        return super().forward(belief, torch.cat((state, condition), dim=1))
+
+    def get_action_dist(self, belief, state, condition):
+        return TanhNormalDist(*self.forward(belief, state, condition))
+
+    def get_action(self, belief, state, condition, det=False):
+        dist = self.get_action_dist(belief, state, condition)
+        return dist.mode() if det else dist.rsample()
+
+
 class TanhNormalDist:
     """SampleDist(Independent(TransformedDistribution(Normal(mean,std), TanhBijector), 1)) with the reference's
     100-sample Monte-Carlo statistics (models/utils.py:112-163, actor_critic.py:89-95)."""

@@ -164,9 +164,11 @@ def imagine_fwd(params: Dict[str, torch.Tensor], actor: Dict[str, torch.Tensor],
                 mean_scale: float = 5.0, init_std: float = 0.0, actor_min_std: float = 0.1,
                 gamma: float = 0.99, lambda_: float = 0.95, row_tile: int = 0,
                 workspace: Optional[torch.Tensor] = None, packed: bool = False, want_actions: bool = True,
-                stash: Optional[torch.Tensor] = None):
+                stash: Optional[torch.Tensor] = None, cond: Optional[torch.Tensor] = None):
     """TransitionModel.imagine (rssm.py:148-184) + reward/value heads + lambda-return in one launch.
-    Returns dict(beliefs, prior_states, prior_means, prior_std_devs, actions, rewards, values, returns)."""
+    Returns dict(beliefs, prior_states, prior_means, prior_std_devs, actions, rewards, values, returns).
+    `cond` (N, C): ConditionalTransitionModel.imagine (rssm.py:225-248) — `params` then belong to a model built with
+    action_size + C pseudo-actions and `actor` to a ConditionalActorModel (fc1 over [belief | state | condition])."""
     L = _lib.lib()
     keep = _Keep()
     d = dims_of(params)
@@ -179,12 +181,18 @@ def imagine_fwd(params: Dict[str, torch.Tensor], actor: Dict[str, torch.Tensor],
     dev = belief.device
     belief = _chk(belief, "prev_belief", (N, d.belief))
     state = _chk(state, "prev_state", (N, d.state))
-    eps_action = _chk(eps_action, "eps_action", (T, N, d.action))
+    csz = 0 if cond is None else cond.shape[1]
+    a_act = d.action - csz
+    if cond is not None:
+        cond = _chk(cond, "condition", (N, csz))
+        if a_act < 1 or actor["fc1.weight"].shape[1] != d.belief + d.state + csz or actor["fc5.weight"].shape[0] != 2 * a_act:
+            raise RuntimeError("conditional imagine: model / actor / condition sizes do not fit together")
+    eps_action = _chk(eps_action, "eps_action", (T, N, a_act))
     eps_prior = _chk(eps_prior, "eps_prior", (T, N, d.state))
     mk = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
     out = dict(beliefs=mk(T, N, d.belief), prior_states=mk(T, N, d.state), prior_means=mk(T, N, d.state),
                prior_std_devs=mk(T, N, d.state))
-    out["actions"] = mk(T, N, d.action) if want_actions else None
+    out["actions"] = mk(T, N, a_act) if want_actions else None
     out["rewards"] = mk(T, N) if Rm is not None else None
     out["values"] = mk(T, N) if Vm is not None else None
     out["returns"] = mk(max(T - 1, 0), N) if (Rm is not None and Vm is not None) else None
@@ -195,15 +203,15 @@ def imagine_fwd(params: Dict[str, torch.Tensor], actor: Dict[str, torch.Tensor],
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=dev)
         packed = False
-    rc = L.repo_b200_imagine_fwd(
+    rc = L.repo_b200_imagine_cond_fwd(
         C.byref(d), C.byref(W), C.byref(Am), C.byref(Rm) if Rm is not None else None,
-        C.byref(Vm) if Vm is not None else None, _ptr(belief), _ptr(state), _ptr(eps_action), _ptr(eps_prior),
+        C.byref(Vm) if Vm is not None else None, _ptr(belief), _ptr(state), _ptr(cond), csz, _ptr(eps_action), _ptr(eps_prior),
         _ptr(out["beliefs"]), _ptr(out["prior_states"]), _ptr(out["prior_means"]), _ptr(out["prior_std_devs"]),
         _ptr(out["actions"]), _ptr(out["rewards"]), _ptr(out["values"]), _ptr(out["returns"]),
         horizon, N, act_kind(act), float(min_std), float(mean_scale), float(init_std), float(actor_min_std),
         float(gamma), float(lambda_), _ptr(stash), _ptr(workspace), workspace.numel(), _lib.WEIGHTS_PACKED if packed else 0,
         row_tile, _stream())
-    _lib.check(rc, "repo_b200_imagine_fwd")
+    _lib.check(rc, "repo_b200_imagine_cond_fwd")
     out["workspace"] = workspace
     return out
 

@@ -62,8 +62,8 @@ class TransitionModel(nn.Module):
                 post.append(torch.randn(B, S, device=like.device))
         return torch.stack(pri), (torch.stack(post) if with_obs else None)
 
-    def _imagine_noise(self, T, N, like):
-        S, A = self.state_size, self.action_size
+    def _imagine_noise(self, T, N, like, action_width=None):
+        S, A = self.state_size, (self.action_size if action_width is None else action_width)
         if not self.rng_compat:
             return self._randn(T, N, A, like), self._randn(T, N, S, like)
         ea, ep = [], []
@@ -99,7 +99,7 @@ class TransitionModel(nn.Module):
         return outs
 
     def imagine(self, prev_belief, prev_state, policy, horizon, *, eps_action=None, eps_prior=None,
-                reward_model=None, value_model=None, gamma=0.99, lambda_=0.95, return_extras=False):
+                reward_model=None, value_model=None, gamma=0.99, lambda_=0.95, return_extras=False, _cond=None):
         """rssm.py:148-184.  `policy` must be an ActorModel-like module (fc1..fc5, `_mean_scale`, `_init_std`,
         `_min_std`: actor_critic.py:50-74); anything else raises (no fallback).  With `reward_model` /
         `value_model` (fc1..fc4) the same launch also produces rewards, values and lambda-returns
@@ -113,15 +113,16 @@ class TransitionModel(nn.Module):
             # up as a tanh-Normal policy in the reference, so only reject things we cannot interpret
             raise TypeError(f"imagine: unsupported policy dist {policy._dist!r}")
         N, T = prev_belief.shape[0], horizon - 1
+        csz = 0 if _cond is None else _cond.shape[1]
         if eps_action is None or eps_prior is None:
-            ea, ep = self._imagine_noise(T, N, prev_belief)
+            ea, ep = self._imagine_noise(T, N, prev_belief, self.action_size - csz)
             eps_action = ea if eps_action is None else eps_action
             eps_prior = ep if eps_prior is None else eps_prior
         if self._wants_grad([prev_belief, prev_state]) or (torch.is_grad_enabled() and any(p.requires_grad for p in policy.parameters())):
             if reward_model is not None or value_model is not None:
                 raise NotImplementedError("imagine under autograd returns the reference's four lists; evaluate the heads on them")
             from . import autograd as _ag
-            traj, actions = _ag.imagine(self, prev_belief, prev_state, policy, horizon, eps_action, eps_prior)
+            traj, actions = _ag.imagine(self, prev_belief, prev_state, policy, horizon, eps_action, eps_prior, _cond)
             return (traj, {"actions": actions}) if return_extras else traj
         out = ops.imagine_fwd(_named(self), _named(policy),
                               _named(reward_model) if reward_model is not None else None,
@@ -130,7 +131,7 @@ class TransitionModel(nn.Module):
                               act=self.activation_function, min_std=self.min_std_dev,
                               mean_scale=float(policy._mean_scale), init_std=float(policy._init_std),
                               actor_min_std=float(policy._min_std), gamma=gamma, lambda_=lambda_,
-                              workspace=self._ws.get("imagine"))
+                              workspace=self._ws.get("imagine"), cond=_cond)
         self._ws["imagine"] = out.pop("workspace")
         traj = [out["beliefs"], out["prior_states"], out["prior_means"], out["prior_std_devs"]]
         if return_extras:
@@ -188,3 +189,24 @@ class TransitionModel(nn.Module):
             raise NotImplementedError(
                 f"TransitionModel.{what}: the backward kernels are not built yet — call under torch.no_grad() "
                 "(refusing to return silently non-differentiable outputs)")
+
+
+class ConditionalTransitionModel(TransitionModel):
+    """rssm.py:187-248 (multitask variants): the task condition rides next to the action.  `observe` concatenates
+    (actions, conditions) into pseudo-actions; `imagine` keeps the (constant) condition in the tail of the kernel's action
+    slot, where the embedding layer reads [state | action | condition] and the ConditionalActorModel's first layer reads
+    [belief | state | condition].  Same fused launches, same hand-written backward."""
+
+    def __init__(self, belief_size, state_size, action_size, hidden_size, embedding_size, condition_size,
+                 activation_function="relu", min_std_dev=0.1):
+        super().__init__(belief_size, state_size, action_size + condition_size, hidden_size, embedding_size,
+                         activation_function, min_std_dev)
+        self.condition_size = condition_size
+
+    def observe(self, prev_belief, prev_state, actions, conditions, observations=None, nonterminals=None, **eps):
+        return super().observe(prev_belief, prev_state, torch.cat((actions, conditions), dim=2), observations, nonterminals, **eps)
+
+    def imagine(self, prev_belief, prev_state, condition, policy, horizon, **kw):
+        if condition.shape != (prev_belief.shape[0], self.condition_size):
+            raise ValueError(f"condition must be ({prev_belief.shape[0]}, {self.condition_size}), got {tuple(condition.shape)}")
+        return super().imagine(prev_belief, prev_state, policy, horizon, _cond=condition.float().contiguous(), **kw)

@@ -603,3 +603,77 @@ def test_flat_adam_matches_clip_grad_norm_plus_torch_adam(dev):
     sd = opt.state_dict()
     assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"} and sd["param_groups"][0]["lr"] == 3e-4
     np.testing.assert_allclose(sd["state"][2]["exp_avg"].cpu().numpy(), opt_ref.state_dict()["state"][2]["exp_avg"].cpu().numpy(), rtol=1e-4, atol=1e-6)
+
+
+def _conditional_case():
+    g, meta = C.load("conditional_N12_H7")
+    seed, N, H, T, B, Cn = (int(meta[k]) for k in ("seed", "N", "H", "T", "B", "C"))
+    dims = dict(O.DEFAULT_DIMS)
+    pdims = dict(dims, action=dims["action"] + Cn)
+    p = O.make_transition_params(seed, pdims)
+    ap = O.make_mlp_params(seed + 1, dims["belief"] + dims["state"] + Cn, dims["hidden"], 2 * dims["action"], 4)
+    rs = np.random.RandomState(seed + 2)
+    cond = torch.from_numpy(rs.standard_normal((N, Cn)).astype(np.float32))
+    x = O.make_imagine_inputs(seed + 20, N, H, dims)
+    xo = O.make_observe_inputs(seed + 10, T, B, dims)
+    conds = torch.from_numpy(rs.standard_normal((T - 1, B, Cn)).astype(np.float32))
+    return g, dims, Cn, p, ap, cond, x, xo, conds, H
+
+
+def test_conditional_model_matches_reference_fixture(dev):
+    """ConditionalTransitionModel.observe / .imagine with a ConditionalActorModel (rssm.py:187-248,
+    actor_critic.py:105-148) through the fused kernels, vs the reference classes' fixture and the oracle."""
+    from repo_b200.models import ConditionalActorModel
+    from repo_b200.rssm import ConditionalTransitionModel
+    g, dims, Cn, p, ap, cond, x, xo, conds, H = _conditional_case()
+    D, S, A, Hd, E = (dims[k] for k in ("belief", "state", "action", "hidden", "embed"))
+    tm = ConditionalTransitionModel(D, S, A, Hd, E, Cn, "elu").to(dev)
+    tm.load_state_dict(p)
+    actor = ConditionalActorModel(D, S, Hd, A, Cn, "elu").to(dev)
+    actor.load_state_dict(ap)
+    with torch.no_grad():
+        im = tm.imagine(x["belief"].to(dev), x["state"].to(dev), cond.to(dev), actor, H,
+                        eps_action=x["eps_action"].to(dev), eps_prior=x["eps_prior"].to(dev))
+        ob = tm.observe(xo["prev_belief"].to(dev), xo["prev_state"].to(dev), xo["actions"].to(dev), conds.to(dev),
+                        xo["embeds"].to(dev), xo["nonterms"].to(dev), eps_prior=xo["eps_prior"].to(dev), eps_post=xo["eps_post"].to(dev))
+    for nm, o in zip(("im_beliefs", "im_prior_states", "im_prior_means", "im_prior_std_devs"), im):
+        close(o, g[nm], nm)
+    for nm, idx in (("ob_beliefs", 0), ("ob_posterior_states", 4), ("ob_posterior_means", 5), ("ob_prior_std_devs", 3)):
+        close(ob[idx], g[nm], nm)
+
+
+def test_conditional_imagine_backward_matches_autograd(dev):
+    """Gradients of the conditional rollout (actor parameters through the dynamics, start rows) vs fp64 autograd of the
+    oracle; the condition columns of the pseudo-action carry no gradient."""
+    from repo_b200.models import ConditionalActorModel
+    from repo_b200.rssm import ConditionalTransitionModel
+    g, dims, Cn, p, ap, cond, x, xo, conds, H = _conditional_case()
+    D, S, A, Hd, E = (dims[k] for k in ("belief", "state", "action", "hidden", "embed"))
+    rs = np.random.RandomState(9)
+    R = [torch.from_numpy(rs.standard_normal(s).astype(np.float32)) for s in ((H - 1, 12, D), (H - 1, 12, S), (H - 1, 12, S), (H - 1, 12, S))]
+    p64 = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    a64 = {k: v.double().requires_grad_(True) for k, v in ap.items()}
+    b64, s64 = x["belief"].double().requires_grad_(True), x["state"].double().requires_grad_(True)
+    outs = O.imagine_conditional(p64, a64, b64, s64, cond.double(), x["eps_action"].double(), x["eps_prior"].double(), H)
+    sum((r.double() * o).sum() for r, o in zip(R, outs)).backward()
+
+    tm = ConditionalTransitionModel(D, S, A, Hd, E, Cn, "elu").to(dev)
+    tm.load_state_dict(p)
+    actor = ConditionalActorModel(D, S, Hd, A, Cn, "elu").to(dev)
+    actor.load_state_dict(ap)
+    gb, gs = x["belief"].to(dev).requires_grad_(True), x["state"].to(dev).requires_grad_(True)
+    im = tm.imagine(gb, gs, cond.to(dev), actor, H, eps_action=x["eps_action"].to(dev), eps_prior=x["eps_prior"].to(dev))
+    sum((r.to(dev) * o).sum() for r, o in zip(R, im)).backward()
+
+    def cmp(got, want, nm):
+        scale = float(want.abs().max()) + 1e-12
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-4, err_msg=nm)
+
+    for k, w in p64.items():
+        if "posterior" in k:
+            continue
+        cmp(dict(tm.named_parameters())[k].grad, w.grad, "rssm." + k)
+    for k, w in a64.items():
+        cmp(dict(actor.named_parameters())[k].grad, w.grad, "actor." + k)
+    cmp(gb.grad, b64.grad, "d start belief")
+    cmp(gs.grad, s64.grad, "d start state")

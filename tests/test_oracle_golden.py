@@ -104,3 +104,26 @@ def test_f16x3_emulation_is_within_tolerance():
                     x["eps_prior"], x["eps_post"], prec=O.Precision("f16x3"))
     for a, b in zip(exact, emu):
         np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_conditional_oracle_matches_reference_fixture():
+    """ConditionalTransitionModel observe / imagine (rssm.py:187-248) with a ConditionalActorModel: oracle restatement vs
+    the fixture produced by the reference's own classes."""
+    g, meta = C.load("conditional_N12_H7")
+    seed, N, H, T, B, Cn = (int(meta[k]) for k in ("seed", "N", "H", "T", "B", "C"))
+    dims = dict(O.DEFAULT_DIMS)
+    pdims = dict(dims, action=dims["action"] + Cn)
+    p = O.make_transition_params(seed, pdims)
+    ap = O.make_mlp_params(seed + 1, dims["belief"] + dims["state"] + Cn, dims["hidden"], 2 * dims["action"], 4)
+    rs = np.random.RandomState(seed + 2)
+    cond = torch.from_numpy(rs.standard_normal((N, Cn)).astype(np.float32))
+    x = O.make_imagine_inputs(seed + 20, N, H, dims)
+    im = O.imagine_conditional(p, ap, x["belief"], x["state"], cond, x["eps_action"], x["eps_prior"], H)
+    for nm, o in zip(("im_beliefs", "im_prior_states", "im_prior_means", "im_prior_std_devs"), im):
+        np.testing.assert_allclose(o.numpy(), g[nm], rtol=2e-5, atol=2e-6, err_msg=nm)
+    xo = O.make_observe_inputs(seed + 10, T, B, dims)
+    conds = torch.from_numpy(rs.standard_normal((T - 1, B, Cn)).astype(np.float32))
+    ob = O.observe(p, xo["prev_belief"], xo["prev_state"], torch.cat([xo["actions"], conds], 2), xo["embeds"], xo["nonterms"],
+                   xo["eps_prior"], xo["eps_post"])
+    for nm, idx in (("ob_beliefs", 0), ("ob_posterior_states", 4), ("ob_posterior_means", 5), ("ob_prior_std_devs", 3)):
+        np.testing.assert_allclose(ob[idx].numpy(), g[nm], rtol=2e-5, atol=2e-6, err_msg=nm)
