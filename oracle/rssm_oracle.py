@@ -301,11 +301,14 @@ def shift_for_observe(actions, embeds, nonterms):
 # ----------------------------------------------------------------------------
 
 def visual_encoder(p: Params, obs):
-    """encoder.py:34-41 with the default embedding_size == 1024 (fc = Identity)."""
+    """encoder.py:34-41; fc = Identity at the default embedding_size == 1024, else Linear(1024, embedding_size)."""
     h = obs
     for i in range(1, 5):
         h = F.relu(F.conv2d(h, p[f"conv{i}.weight"], p[f"conv{i}.bias"], stride=2))
-    return h.reshape(-1, 1024)
+    h = h.reshape(-1, 1024)
+    if "fc.weight" in p:
+        h = F.linear(h, p["fc.weight"], p["fc.bias"])
+    return h
 
 
 def visual_decoder(p: Params, belief, state):

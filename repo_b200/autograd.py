@@ -339,6 +339,31 @@ def mlp(module, n_layers, out_f, belief, state, act):
     return MlpFn.apply(act, out_f, belief, state, *params)
 
 
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b as a differentiable op on the package's GEMM kernels (encoder `fc` when embedding_size != 1024)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return ops.linear(x.detach().contiguous(), weight.detach().contiguous(), bias.detach().contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous().float()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            from .conv import _as_input_side, dense_layer, grad_scales
+            gx = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+            # gradients sit below fp16's normal range: rescale the gathered operand by a power of two (conv.grad_scales)
+            dense_layer(g, weight.detach().t().contiguous(), None, gx, scales=_as_input_side(grad_scales(g)))
+        if ctx.needs_input_grad[1]:
+            gw = _wgrad(g, x.detach()) if x.shape[0] else torch.zeros_like(weight)
+        if ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gw, gb
+
+
 class EntropyFn(torch.autograd.Function):
     """SampleDist.entropy (models/utils.py:160-163) of the tanh-Normal policy with explicit noise."""
 

@@ -302,7 +302,8 @@ class VisualEncoder(nn.Module):
         hidden = _EncoderFn.apply(observation, *params)
         if isinstance(self.fc, nn.Identity):
             return hidden
-        raise NotImplementedError("embedding_size != 1024 needs the extra Linear; not wired to the machine yet")
+        from .autograd import LinearFn
+        return LinearFn.apply(hidden, self.fc.weight, self.fc.bias)   # encoder.py:30,40: Linear(1024, embedding_size)
 
 
 # ------------------------------------------------------------------------------------------------- decoder
@@ -500,8 +501,8 @@ class VisualObservationModel(nn.Module):
         super().__init__()
         if activation_function != "relu":
             raise RuntimeError("the fused conv epilogue implements ReLU (cnn_activation_function default, train_repo.py:32)")
-        if embedding_size != 1024:
-            raise RuntimeError("VisualObservationModel kernels are sized for embedding_size == 1024")
+        if embedding_size % 16:
+            raise RuntimeError("VisualObservationModel: embedding_size must be a multiple of 16")
         self.embedding_size = embedding_size
         self.belief_size = belief_size
         self.fc1 = nn.Linear(belief_size + state_size, embedding_size)

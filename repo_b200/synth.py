@@ -94,7 +94,7 @@ def make_mask_head_params(seed: int) -> Params:
     return {"0.weight": _uniform(rs, (1, 6, 1, 1), b), "0.bias": _uniform(rs, (1,), b)}
 
 
-def make_conv_params(which: str, seed: int, out_channels: int = 3) -> Params:
+def make_conv_params(which: str, seed: int, out_channels: int = 3, embedding_size: int = 1024) -> Params:
     """VisualEncoder (encoder.py:26-29) / VisualObservationModel (decoder.py:35-39) parameters with torch's default
     init distribution (U(+-1/sqrt(fan_in))), from numpy."""
     rs = np.random.RandomState(seed)
@@ -104,10 +104,13 @@ def make_conv_params(which: str, seed: int, out_channels: int = 3) -> Params:
             b = 1.0 / math.sqrt(ci * 16)
             p[f"conv{i}.weight"] = _uniform(rs, (co, ci, 4, 4), b)
             p[f"conv{i}.bias"] = _uniform(rs, (co,), b)
+        if embedding_size != 1024:   # encoder.py:30
+            b = 1.0 / math.sqrt(1024)
+            p["fc.weight"], p["fc.bias"] = _uniform(rs, (embedding_size, 1024), b), _uniform(rs, (embedding_size,), b)
     else:
         b = 1.0 / math.sqrt(230)
-        p["fc1.weight"], p["fc1.bias"] = _uniform(rs, (1024, 230), b), _uniform(rs, (1024,), b)
-        for i, (ci, co, k) in enumerate([(1024, 128, 5), (128, 64, 5), (64, 32, 6), (32, out_channels, 6)], 1):
+        p["fc1.weight"], p["fc1.bias"] = _uniform(rs, (embedding_size, 230), b), _uniform(rs, (embedding_size,), b)
+        for i, (ci, co, k) in enumerate([(embedding_size, 128, 5), (128, 64, 5), (64, 32, 6), (32, out_channels, 6)], 1):
             b = 1.0 / math.sqrt(co * k * k)  # ConvTranspose2d fan_in is computed on dim 1 of its (cin, cout, k, k) weight
             p[f"conv{i}.weight"] = _uniform(rs, (ci, co, k, k), b)
             p[f"conv{i}.bias"] = _uniform(rs, (co,), b)

@@ -180,3 +180,25 @@ def test_decoder_backward_large_batch_branch_matches_small_batch_branch(dev):
         rel_close(big[k], sum(pt[0][k] for pt in parts).cpu().numpy(), "decoder grad " + k, rtol=1e-3, floor=2e-4)
     rel_close(gb, torch.cat([pt[1] for pt in parts]).cpu().numpy(), "d belief", rtol=1e-3, floor=2e-4)
     rel_close(gs, torch.cat([pt[2] for pt in parts]).cpu().numpy(), "d state", rtol=1e-3, floor=2e-4)
+
+
+def test_non_default_embedding_size(dev):
+    """embedding_size != 1024: the encoder gains Linear(1024, E) (encoder.py:30,40) and the decoder's first two layers take E
+    channels (decoder.py:34-35); forward vs the oracle, encoder gradients vs fp64 autograd."""
+    from repo_b200.conv import VisualEncoder, VisualObservationModel
+    E = 512
+    pe, pd = synth.make_conv_params("encoder", 740, embedding_size=E), synth.make_conv_params("decoder", 741, embedding_size=E)
+    enc, dec = VisualEncoder(E).to(dev), VisualObservationModel(200, 30, E).to(dev)
+    enc.load_state_dict(pe)
+    dec.load_state_dict(pd)
+    x = synth.make_frames(742, 5)
+    xi = synth.make_imagine_inputs(743, 5, 2)
+    with torch.no_grad():
+        rel_close(enc(x.to(dev)), O.visual_encoder(pe, x), "embedding (E=512)")
+        rel_close(dec(xi["belief"].to(dev), xi["state"].to(dev)), O.visual_decoder(pd, xi["belief"], xi["state"]), "recon (E=512)")
+    R = torch.from_numpy(np.random.RandomState(5).standard_normal((5, E)).astype(np.float32)) * 1e-4
+    p64 = {k: v.double().requires_grad_(True) for k, v in pe.items()}
+    (O.visual_encoder(p64, x.double()) * R.double()).sum().backward()
+    (enc(x.to(dev)) * R.to(dev)).sum().backward()
+    for k, w in p64.items():
+        rel_close(dict(enc.named_parameters())[k].grad, w.grad, "encoder grad " + k, rtol=2e-3, floor=3e-4)
