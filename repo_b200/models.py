@@ -143,3 +143,58 @@ class TanhNormalDist:
         samples = torch.tanh(self.mean_ + self.std_ * eps)
         idx = torch.argmax(self.log_prob(samples), 0)
         return samples[idx, torch.arange(samples.shape[1], device=samples.device)]
+
+
+# ------------------------------------------------------------------------------------------------ symbolic observations
+class _Mlp3(nn.Module):
+    """fc1 -> act -> fc2 -> act -> fc3 on the package's GEMM kernels (differentiable: autograd.LinearFn)."""
+
+    def __init__(self, in_f, hidden, out_f, activation_function):
+        super().__init__()
+        ops.act_kind(activation_function)
+        self.act_fn = getattr(torch.nn.functional, activation_function)
+        self.fc1 = nn.Linear(in_f, hidden)
+        self.fc2 = nn.Linear(hidden, hidden)
+        self.fc3 = nn.Linear(hidden, out_f)
+
+    def _run(self, x):
+        from .autograd import LinearFn
+        h = self.act_fn(LinearFn.apply(x, self.fc1.weight, self.fc1.bias))
+        h = self.act_fn(LinearFn.apply(h, self.fc2.weight, self.fc2.bias))
+        return LinearFn.apply(h, self.fc3.weight, self.fc3.bias)
+
+
+class SymbolicEncoder(_Mlp3):
+    """encoder.py:6-18 (pixel_obs=False)."""
+
+    def __init__(self, observation_size, embedding_size, activation_function="relu"):
+        super().__init__(observation_size, embedding_size, embedding_size, activation_function)
+
+    def forward(self, observation):
+        return self._run(observation)
+
+
+class SymbolicObservationModel(_Mlp3):
+    """decoder.py:6-25 (pixel_obs=False)."""
+
+    def __init__(self, observation_size, belief_size, state_size, embedding_size, activation_function="relu"):
+        super().__init__(belief_size + state_size, embedding_size, observation_size, activation_function)
+
+    def forward(self, belief, state):
+        return self._run(torch.cat([belief, state], dim=1))
+
+
+def Encoder(symbolic, observation_size, embedding_size, activation_function="relu"):
+    """encoder.py:44-48."""
+    if symbolic:
+        return SymbolicEncoder(observation_size, embedding_size, activation_function)
+    from .conv import VisualEncoder
+    return VisualEncoder(embedding_size, activation_function)
+
+
+def ObservationModel(symbolic, observation_size, belief_size, state_size, embedding_size, activation_function="relu"):
+    """decoder.py:51-66."""
+    if symbolic:
+        return SymbolicObservationModel(observation_size, belief_size, state_size, embedding_size, activation_function)
+    from .conv import VisualObservationModel
+    return VisualObservationModel(belief_size, state_size, embedding_size, activation_function)

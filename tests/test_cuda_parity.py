@@ -677,3 +677,46 @@ def test_conditional_imagine_backward_matches_autograd(dev):
         cmp(dict(actor.named_parameters())[k].grad, w.grad, "actor." + k)
     cmp(gb.grad, b64.grad, "d start belief")
     cmp(gs.grad, s64.grad, "d start state")
+
+
+@pytest.mark.parametrize("rows", [7, 300])
+def test_symbolic_encoder_and_observation_model(dev, rows):
+    """SymbolicEncoder / SymbolicObservationModel (encoder.py:6-18, decoder.py:6-25; pixel_obs=False): forward and all
+    gradients vs the same MLPs in fp64 torch.  24-d observations (walker), both GEMM paths (7 and 300 rows)."""
+    from repo_b200.models import Encoder, ObservationModel
+    torch.manual_seed(3)
+    enc, dec = Encoder(True, 24, 1024, "relu").to(dev), ObservationModel(True, 24, 200, 30, 1024, "relu").to(dev)
+    rs = np.random.RandomState(rows)
+    obs = torch.from_numpy(rs.standard_normal((rows, 24)).astype(np.float32))
+    b, s = torch.from_numpy(rs.standard_normal((rows, 200)).astype(np.float32)) * 0.3, torch.from_numpy(rs.standard_normal((rows, 30)).astype(np.float32))
+    Re, Rd = torch.from_numpy(rs.standard_normal((rows, 1024)).astype(np.float32)) * 1e-3, torch.from_numpy(rs.standard_normal((rows, 24)).astype(np.float32)) * 1e-3
+
+    def ref(mod, x):
+        P = {k: v.detach().cpu().double().requires_grad_(True) for k, v in mod.named_parameters()}
+        x = x.double().requires_grad_(True)
+        h = torch.relu(torch.nn.functional.linear(x, P["fc1.weight"], P["fc1.bias"]))
+        h = torch.relu(torch.nn.functional.linear(h, P["fc2.weight"], P["fc2.bias"]))
+        return torch.nn.functional.linear(h, P["fc3.weight"], P["fc3.bias"]), P, x
+
+    ye, Pe, xe = ref(enc, obs)
+    (ye * Re.double()).sum().backward()
+    yd, Pd, xd = ref(dec, torch.cat([b, s], 1))
+    (yd * Rd.double()).sum().backward()
+    og = obs.to(dev).requires_grad_(True)
+    e = enc(og)
+    (e * Re.to(dev)).sum().backward()
+    bg, sg = b.to(dev).requires_grad_(True), s.to(dev).requires_grad_(True)
+    o = dec(bg, sg)
+    (o * Rd.to(dev)).sum().backward()
+    close(e, ye.detach().float(), "symbolic embedding", atol=2e-4)
+    close(o, yd.detach().float(), "symbolic reconstruction", atol=2e-4)
+
+    def cmp(got, want, nm):
+        scale = float(want.abs().max()) + 1e-12
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-4, err_msg=nm)
+
+    for mod, P, tag in ((enc, Pe, "enc."), (dec, Pd, "dec.")):
+        for k, w in P.items():
+            cmp(dict(mod.named_parameters())[k].grad, w.grad, tag + k)
+    cmp(og.grad, xe.grad, "d obs")
+    cmp(torch.cat([bg.grad, sg.grad], 1), xd.grad, "d [belief|state]")
