@@ -198,3 +198,70 @@ def ObservationModel(symbolic, observation_size, belief_size, state_size, embedd
         return SymbolicObservationModel(observation_size, belief_size, state_size, embedding_size, activation_function)
     from .conv import VisualObservationModel
     return VisualObservationModel(belief_size, state_size, embedding_size, activation_function)
+
+
+# ------------------------------------------------------------------------------------------------ optional heads
+class EnsembleLinearLayer(nn.Module):
+    """models/utils.py:19-49: `ensemble_size` independent linear layers, weight (E, in, out), bias (E, 1, out), applied to a
+    shared (rows, in) input or to per-member (E, rows, in) inputs.  Each member is one GEMM launch (autograd.LinearFn)."""
+
+    def __init__(self, in_dim, out_dim, ensemble_size, bias=True):
+        super().__init__()
+        self.in_dim, self.out_dim, self.ensemble_size = in_dim, out_dim, ensemble_size
+        self.weight = nn.Parameter(torch.rand(ensemble_size, in_dim, out_dim))
+        if bias:
+            self.bias = nn.Parameter(torch.rand(ensemble_size, 1, out_dim))
+        else:
+            self.register_parameter("bias", None)
+
+    def forward(self, x):
+        from .autograd import LinearFn
+        outs = []
+        for e in range(self.ensemble_size):
+            xe = x if x.dim() == 2 else x[e]
+            b = self.bias[e, 0] if self.bias is not None else torch.zeros(self.out_dim, device=x.device)
+            outs.append(LinearFn.apply(xe, self.weight[e].t(), b))
+        return torch.stack(outs, 0)
+
+
+class EnsembleDynamicsModel(nn.Module):
+    """models/utils.py:52-80 (disagreement ensemble, `disag_model` flag): (E, rows, belief) next-belief predictions."""
+
+    def __init__(self, belief_size, state_size, action_size, hidden_size, ensemble_size, activation_function="relu", min_std_dev=0.1):
+        super().__init__()
+        ops.act_kind(activation_function)
+        self.act_fn = getattr(torch.nn.functional, activation_function)
+        self.min_std_dev = min_std_dev
+        self.fc1 = EnsembleLinearLayer(belief_size + state_size + action_size, hidden_size, ensemble_size)
+        self.fc2 = EnsembleLinearLayer(hidden_size, hidden_size, ensemble_size)
+        self.fc3 = EnsembleLinearLayer(hidden_size, hidden_size, ensemble_size)
+        self.fc4 = EnsembleLinearLayer(hidden_size, belief_size, ensemble_size)
+
+    def forward(self, belief, state, action):
+        x = torch.cat((belief, state, action), dim=1)
+        h = self.act_fn(self.fc1(x))
+        h = self.act_fn(self.fc2(h))
+        h = self.act_fn(self.fc3(h))
+        return self.fc4(h)
+
+
+class InverseDynamicsModel(nn.Module):
+    """models/utils.py:83-109 (`inv_dynamics` flag): action distribution from (belief, state, next belief)."""
+
+    def __init__(self, belief_size, state_size, action_size, hidden_size, activation_function="relu", min_std_dev=0.1):
+        super().__init__()
+        ops.act_kind(activation_function)
+        self.act_fn = getattr(torch.nn.functional, activation_function)
+        self.min_std_dev = min_std_dev
+        self.fc1 = nn.Linear(belief_size + state_size + belief_size, hidden_size)
+        self.fc2 = nn.Linear(hidden_size, hidden_size)
+        self.fc3 = nn.Linear(hidden_size, hidden_size)
+        self.fc4 = nn.Linear(hidden_size, 2 * action_size)
+
+    def forward(self, belief, state, next_belief):
+        from .autograd import LinearFn
+        h = torch.cat((belief, state, next_belief), dim=1)
+        for fc in (self.fc1, self.fc2, self.fc3):
+            h = self.act_fn(LinearFn.apply(h, fc.weight, fc.bias))
+        mean, std_dev = torch.chunk(LinearFn.apply(h, self.fc4.weight, self.fc4.bias), chunks=2, dim=1)
+        return mean, torch.nn.functional.softplus(std_dev) + self.min_std_dev

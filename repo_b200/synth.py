@@ -58,6 +58,27 @@ def make_mlp_params(seed: int, in_f: int, hidden: int, out_f: int, n_hidden: int
         p[f"fc{i + 1}.bias"] = _uniform(rs, (sizes[i + 1],), b)
     return p
 
+def make_ensemble_params(seed: int, in_f: int, hidden: int, out_f: int, ensemble: int) -> Params:
+    """EnsembleDynamicsModel fc1..fc4 (models/utils.py:52-80): weight (E, in, out), bias (E, 1, out).  Drawn in
+    +-1/sqrt(fan_in) instead of the reference's U(0,1) default so that four layers keep O(1) activations."""
+    rs = np.random.RandomState(seed)
+    p: Params = {}
+    sizes = [in_f, hidden, hidden, hidden, out_f]
+    for i in range(4):
+        b = 1.0 / math.sqrt(sizes[i])
+        p[f"fc{i + 1}.weight"] = _uniform(rs, (ensemble, sizes[i], sizes[i + 1]), b)
+        p[f"fc{i + 1}.bias"] = _uniform(rs, (ensemble, 1, sizes[i + 1]), b)
+    return p
+
+
+def make_head_rollout(seed: int, T: int, B: int, dims=DEFAULT_DIMS, p_done=0.1):
+    """Inputs of Dreamer.train_disag / train_inv_dynamics (dreamer.py:198-239): beliefs/states (T-1,B,.) as observe
+    returns them, actions / nonterms (T,B,.) as the replay buffer does."""
+    rs = np.random.RandomState(seed)
+    f = lambda a: torch.from_numpy(a.astype(np.float32))
+    D, S, A = dims["belief"], dims["state"], dims["action"]
+    return dict(beliefs=f(np.clip(rs.standard_normal((T - 1, B, D)) * 0.3, -1, 1)), states=f(rs.standard_normal((T - 1, B, S))),
+                actions=f(rs.uniform(-1, 1, (T, B, A))), nonterms=f(rs.uniform(0, 1, (T, B, 1)) >= p_done))
 
 
 def make_observe_inputs(seed: int, T: int, B: int, dims=DEFAULT_DIMS, p_done=1 / 500.0, embed_scale=1.0):

@@ -34,7 +34,7 @@ import torch.nn as nn
 
 from . import losses
 from .conv import TIAObservationModel, VisualEncoder, VisualObservationModel, tia_mix
-from .models import ActorModel, RewardModel, ValueModel, bottle
+from .models import ActorModel, EnsembleDynamicsModel, InverseDynamicsModel, RewardModel, ValueModel, bottle
 from .optim import FlatAdam
 from .rssm import TransitionModel
 
@@ -68,6 +68,13 @@ class Config:
     tia_obs_coef: float = 1.0
     tia_adv_coef: float = 1.0
     tia_reward_train_steps: int = 1
+    disag_model: bool = False          # dreamer.py:116-128 (optional disagreement ensemble)
+    ensemble_size: int = 6
+    disag_lr: float = 3e-4
+    disag_coef: float = 0.0
+    inv_dynamics: bool = False         # dreamer.py:130-141 (optional inverse-dynamics head)
+    inv_dynamics_hidden_size: int = 512
+    inv_dynamics_lr: float = 3e-4
 
 
 class _Frozen:
@@ -112,6 +119,12 @@ class Agent:
                                                                     c.cnn_activation_function).to(dev)
             self.distractor_reward_model = RewardModel(c.belief_size, c.state_size, c.hidden_size, c.dense_activation_function).to(dev)
             self.mask_head = nn.Sequential(nn.Conv2d(6, 1, 1), nn.Sigmoid()).to(dev)  # parameter holder; runs in tia_mix
+        if c.disag_model:
+            self.disag_model = EnsembleDynamicsModel(c.belief_size, c.state_size, action_size, c.hidden_size, c.ensemble_size,
+                                                     c.dense_activation_function).to(dev)
+        if c.inv_dynamics:
+            self.inv_dynamics = InverseDynamicsModel(c.belief_size, c.state_size, action_size, c.inv_dynamics_hidden_size,
+                                                     c.dense_activation_function).to(dev)
         self.logs: Dict[str, torch.Tensor] = {}
         self._opt = None
 
@@ -160,6 +173,11 @@ class Agent:
                 "value": FlatAdam(self.value_model.parameters(), c.value_lr, max_grad_norm=c.grad_clip_norm),
                 "beta": torch.optim.Adam([self.log_beta], lr=c.beta_lr, capturable=True),  # device-side step: graph safe
             }
+            if c.disag_model:
+                self._opt["disag"] = FlatAdam(self.disag_model.parameters(), c.disag_lr, max_grad_norm=c.grad_clip_norm)
+            if c.inv_dynamics:
+                self._opt["inv_dynamics"] = FlatAdam(self.inv_dynamics.parameters(), c.inv_dynamics_lr,
+                                                     max_grad_norm=c.grad_clip_norm)
         return self._opt
 
     # ------------------------------------------------------------------ CUDA graphs
@@ -255,7 +273,57 @@ class Agent:
         if w != 1.0:  # kl_loss / beta_loss / beta carry constants: weight them too so that the SUM over ranks is global
             logs = {k: v * w for k, v in logs.items()}
         self.logs.update(logs)
+        if self.algo == "dreamer":  # dreamer.py:297-301 (RePo's train_dynamics override drops both heads)
+            if c.disag_model:
+                self.train_disag(beliefs, posterior_states, actions, nonterms, step=step)
+            if c.inv_dynamics:
+                self.train_inv_dynamics(beliefs, posterior_states, actions, nonterms, step=step)
         return beliefs.detach(), posterior_states.detach()
+
+    # ------------------------------------------------------------------ optional heads (dreamer.py:198-239)
+    @staticmethod
+    def _transition_rows(beliefs, states, actions, nonterms):
+        """Rows (t, b) with nonterms[1 + t, b] == 1 of (actions[1:-1], beliefs[:-1], states[:-1], beliefs[1:]),
+        detached and flattened time-major (dreamer.py:199-209 / :221-231)."""
+        keep = nonterms[1:-1].flatten() == 1
+        return [x.detach().flatten(0, 1)[keep] for x in (actions[1:-1], beliefs[:-1], states[:-1], beliefs[1:])]
+
+    def _head_step(self, key, loss, local_rows, step):
+        """backward + clip + Adam of one optional head; the loss is a mean over this rank's kept rows, so under data
+        parallelism it is weighted kept_local / kept_global before FlatAdam's SUM all-reduce.  Returns the weight."""
+        w = 1.0
+        if self._world() > 1:
+            import torch.distributed as dist
+            total = torch.tensor([float(local_rows)], device=self.device)
+            dist.all_reduce(total, op=dist.ReduceOp.SUM)
+            w = local_rows / total.clamp(min=1.0)[0]
+        opt = self.optimizers()[key] if step else None
+        if step:
+            opt.zero_grad()
+        (loss * w).backward()
+        if step:
+            opt.step()
+        return w
+
+    def train_disag(self, beliefs, states, actions, nonterms, *, step=True):
+        """dreamer.py:198-217: every ensemble member regresses the next belief, unit-variance Normal NLL summed over
+        members and features, mean over the kept rows."""
+        actions_in, beliefs_in, states_in, beliefs_out = self._transition_rows(beliefs, states, actions, nonterms)
+        ens_preds = self.disag_model(beliefs_in, states_in, actions_in)
+        disag_loss = losses.normal_unit_nll(ens_preds, beliefs_out.unsqueeze(0)).sum(2).sum(0).mean()
+        w = self._head_step("disag", disag_loss, beliefs_in.shape[0], step)
+        self.logs["train/disag_loss"] = disag_loss.detach() * w
+        return disag_loss.detach()
+
+    def train_inv_dynamics(self, beliefs, states, actions, nonterms, *, step=True):
+        """dreamer.py:219-239: Normal(mean, std) NLL of the taken action given (belief, state, next belief)."""
+        actions_in, beliefs_in, states_in, beliefs_out = self._transition_rows(beliefs, states, actions, nonterms)
+        act_mean, act_std = self.inv_dynamics(beliefs_in, states_in, beliefs_out)
+        nll = 0.5 * ((actions_in - act_mean) / act_std) ** 2 + act_std.log() + 0.5 * math.log(2 * math.pi)
+        inv_dyn_loss = nll.sum(1).mean()
+        w = self._head_step("inv_dynamics", inv_dyn_loss, beliefs_in.shape[0], step)
+        self.logs["train/inv_dyn_loss"] = inv_dyn_loss.detach() * w
+        return inv_dyn_loss.detach()
 
     def _train_dynamics_tia(self, obs, actions, rewards, nonterms, eps_prior, eps_post, step, eps_prior_d=None, eps_post_d=None):
         """tia.py:93-201."""
@@ -319,7 +387,8 @@ class Agent:
         return t_beliefs.detach(), t_post_states.detach()
 
     # ------------------------------------------------------------------ actor-critic
-    def train_actor_critic(self, beliefs, states, *, eps_action=None, eps_prior=None, eps_entropy=None, step=True):
+    def train_actor_critic(self, beliefs, states, *, eps_action=None, eps_prior=None, eps_entropy=None, eps_disag=None,
+                           step=True):
         """dreamer.py:304-381 on flattened start rows (N, D), (N, S)."""
         c = self.c
         opt = self.optimizers() if step else None
@@ -333,6 +402,13 @@ class Agent:
         # Independent(Normal(mean, std), 1).entropy().mean() (dreamer.py:325-327), closed form: torch.distributions'
         # argument validation synchronises with the host, which a CUDA-graph capture forbids
         latent_entropy = (0.5 + 0.5 * math.log(2 * math.pi) + imag_sd.log()).sum(-1).mean()
+        disag = None
+        if c.disag_model and c.disag_coef > 0:  # dreamer.py:330-339: ensemble spread as an intrinsic reward
+            dist_ = self.actor_model.get_action_dist(imag_b.flatten(0, 1), imag_s.flatten(0, 1))
+            with _Frozen([self.disag_model]):
+                ens_preds = self.disag_model(imag_b.flatten(0, 1), imag_s.flatten(0, 1), dist_.rsample(eps_disag))
+            disag = ens_preds.std(0).mean(-1).reshape(reward_preds.shape)
+            reward_preds = reward_preds + c.disag_coef * disag
         discounts = c.gamma * torch.ones_like(reward_preds)
         returns = losses.lambda_return(reward_preds[:-1], value_preds[:-1], discounts[:-1], value_preds[-1], c.gae_lambda)
         actor_loss = losses.actor_loss(returns, action_entropy, latent_entropy, c.action_ent_coef, c.latent_ent_coef)
@@ -351,4 +427,6 @@ class Agent:
             opt["value"].step()
         self.logs.update({"train/actor_loss": actor_loss.detach() * w, "train/value_loss": value_loss.detach() * w,
                           "train/action_entropy": action_entropy.detach() * w, "train/latent_entropy": latent_entropy.detach() * w})
+        if disag is not None:
+            self.logs["train/disagreement"] = disag.detach().mean() * w
         return returns.detach()

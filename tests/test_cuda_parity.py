@@ -720,3 +720,58 @@ def test_symbolic_encoder_and_observation_model(dev, rows):
             cmp(dict(mod.named_parameters())[k].grad, w.grad, tag + k)
     cmp(og.grad, xe.grad, "d obs")
     cmp(torch.cat([bg.grad, sg.grad], 1), xd.grad, "d [belief|state]")
+
+
+def test_disagreement_ensemble_and_inverse_dynamics_heads(dev):
+    """EnsembleDynamicsModel / InverseDynamicsModel (models/utils.py:52-109; optional `disag_model` / `inv_dynamics` heads)
+    and their losses (dreamer.py:198-239): forward and gradients vs the same arithmetic in fp64 torch."""
+    from repo_b200.models import EnsembleDynamicsModel, InverseDynamicsModel
+    torch.manual_seed(5)
+    rows, D, S, A, Hd, E = 260, 200, 30, 6, 200, 6
+    ens = EnsembleDynamicsModel(D, S, A, Hd, E, "elu").to(dev)
+    with torch.no_grad():
+        for p in ens.parameters():      # the reference initialises with U(0,1); shrink so activations stay O(1)
+            p.mul_(0.02)
+    inv = InverseDynamicsModel(D, S, A, 512, "elu").to(dev)
+    rs = np.random.RandomState(1)
+    f = lambda *sh: torch.from_numpy(rs.standard_normal(sh).astype(np.float32))
+    b, s, a, nb = f(rows, D) * 0.3, f(rows, S), f(rows, A).clamp(-1, 1), f(rows, D) * 0.3
+
+    def ref_ens(P, x):
+        h = x
+        for i in (1, 2, 3, 4):
+            h = torch.matmul(h, P[f"fc{i}.weight"]) + P[f"fc{i}.bias"]
+            if i < 4:
+                h = torch.nn.functional.elu(h)
+        return h
+
+    P = {k: v.detach().cpu().double().requires_grad_(True) for k, v in ens.named_parameters()}
+    pred64 = ref_ens(P, torch.cat([b, s, a], 1).double())
+    loss64 = (0.5 * (pred64 - nb.double()) ** 2).sum(2).sum(0).mean()      # -Independent(Normal(pred,1),1).log_prob up to a constant
+    loss64.backward()
+    pred = ens(b.to(dev), s.to(dev), a.to(dev))
+    assert pred.shape == (E, rows, D)
+    loss = (0.5 * (pred - nb.to(dev)) ** 2).sum(2).sum(0).mean()
+    loss.backward()
+    close(pred, pred64.detach().float(), "ensemble prediction", atol=3e-4)
+
+    def cmp(got, want, nm):
+        scale = float(want.abs().max()) + 1e-12
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-4, err_msg=nm)
+
+    for k, w in P.items():
+        cmp(dict(ens.named_parameters())[k].grad, w.grad, "ensemble " + k)
+
+    Q = {k: v.detach().cpu().double().requires_grad_(True) for k, v in inv.named_parameters()}
+    h = torch.cat([b, s, nb], 1).double()
+    for i in (1, 2, 3):
+        h = torch.nn.functional.elu(torch.nn.functional.linear(h, Q[f"fc{i}.weight"], Q[f"fc{i}.bias"]))
+    m64, sd64 = torch.chunk(torch.nn.functional.linear(h, Q["fc4.weight"], Q["fc4.bias"]), 2, 1)
+    sd64 = torch.nn.functional.softplus(sd64) + 0.1
+    (-torch.distributions.Independent(torch.distributions.Normal(m64, sd64), 1).log_prob(a.double()).mean()).backward()
+    m, sd = inv(b.to(dev), s.to(dev), nb.to(dev))
+    (-torch.distributions.Independent(torch.distributions.Normal(m, sd), 1).log_prob(a.to(dev)).mean()).backward()
+    close(m, m64.detach().float(), "inverse-dynamics mean", atol=3e-4)
+    close(sd, sd64.detach().float(), "inverse-dynamics std", atol=3e-4)
+    for k, w in Q.items():
+        cmp(dict(inv.named_parameters())[k].grad, w.grad, "inverse dynamics " + k)

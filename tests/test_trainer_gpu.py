@@ -183,3 +183,58 @@ def test_degenerate_batches():
         assert np.isfinite(float(v)), k
     for p in agent.model_params + list(agent.actor_model.parameters()) + list(agent.value_model.parameters()):
         assert torch.isfinite(p).all()
+
+
+def _cmp_grads(g, prefix, module, rtol=1e-3, atol=1e-3):
+    n = 0
+    for name, p in module.named_parameters():
+        want = g[f"{prefix}_grad_{name}"]
+        assert p.grad is not None, name
+        got = p.grad.detach().cpu().numpy()
+        norm = float(np.sqrt((got.astype(np.float64) ** 2).sum()))
+        np.testing.assert_allclose(norm, g[f"{prefix}_gradnorm_{name}"], rtol=2e-3, err_msg=f"norm {prefix} {name}")
+        if want.shape != got.shape:
+            got = got.reshape(-1)[::97]
+        scale = np.abs(want).max() + 1e-30
+        np.testing.assert_allclose(got / scale, want / scale, rtol=rtol, atol=atol, err_msg=f"{prefix} {name}")
+        n += 1
+    return n
+
+
+def test_optional_heads_match_reference_trainer():
+    """Dreamer.train_disag / train_inv_dynamics (dreamer.py:198-239) and the disagreement bonus inside train_actor_critic
+    (dreamer.py:330-339): losses and gradients against the reference's unmodified methods (oracle/make_golden_heads.py)."""
+    from repo_b200 import synth
+    from repo_b200.trainer import Agent, Config
+    dev = torch.device("cuda:0")
+    g, meta = C.load("train_heads")
+    seed, T, B, N, H = (int(meta[k]) for k in ("seed", "T", "B", "N", "H"))
+    D, S, A, Hd = 200, 30, 6, 200
+    cfg = Config(disag_model=True, inv_dynamics=True, disag_coef=float(meta["disag_coef"]))
+    agent = Agent(cfg, A, algo="dreamer", device=dev)
+    agent.disag_model.load_state_dict(synth.make_ensemble_params(seed, D + S + A, Hd, D, cfg.ensemble_size))
+    agent.inv_dynamics.load_state_dict(O.make_mlp_params(seed + 1, 2 * D + S, cfg.inv_dynamics_hidden_size, 2 * A, 3))
+    x = {k: v.to(dev) for k, v in synth.make_head_rollout(seed + 2, T, B).items()}
+    agent.train_disag(x["beliefs"], x["states"], x["actions"], x["nonterms"], step=False)
+    agent.train_inv_dynamics(x["beliefs"], x["states"], x["actions"], x["nonterms"], step=False)
+    np.testing.assert_allclose(agent.logs["train/disag_loss"].item(), g["log_disag_loss"], rtol=1e-3)
+    np.testing.assert_allclose(agent.logs["train/inv_dyn_loss"].item(), g["log_inv_dyn_loss"], rtol=1e-3)
+    assert _cmp_grads(g, "disag", agent.disag_model) == 8
+    assert _cmp_grads(g, "inv", agent.inv_dynamics) == 8
+
+    agent.transition_model.load_state_dict(O.make_transition_params(seed + 3))
+    agent.actor_model.load_state_dict(O.make_mlp_params(seed + 4, D + S, Hd, 2 * A, 4))
+    agent.reward_model.load_state_dict(O.make_mlp_params(seed + 5, D + S, Hd, 1, 3))
+    agent.value_model.load_state_dict(O.make_mlp_params(seed + 6, D + S, Hd, 1, 3))
+    y = O.make_imagine_inputs(seed + 7, N, H)
+    rs = np.random.RandomState(seed + 8)
+    eps_ent = torch.from_numpy(rs.standard_normal((100, (H - 1) * N, A)).astype(np.float32))
+    eps_disag = torch.from_numpy(rs.standard_normal(((H - 1) * N, A)).astype(np.float32))
+    for p in agent.disag_model.parameters():
+        p.grad = None
+    agent.train_actor_critic(y["belief"].to(dev), y["state"].to(dev), eps_action=y["eps_action"].to(dev),
+                             eps_prior=y["eps_prior"].to(dev), eps_entropy=eps_ent.to(dev), eps_disag=eps_disag.to(dev), step=False)
+    for k in ("actor_loss", "value_loss", "action_entropy", "latent_entropy", "disagreement"):
+        np.testing.assert_allclose(agent.logs["train/" + k].item(), g["log_" + k], rtol=1e-3, atol=1e-5, err_msg=k)
+    assert _cmp_grads(g, "actor", agent.actor_model, rtol=2e-3, atol=2e-3) == 10
+    assert all(p.grad is None for p in agent.disag_model.parameters())      # frozen inside the bonus (dreamer.py:332)
