@@ -87,7 +87,7 @@ struct BiasRowsJob {   // dst[dst_off + i] = (i < n) ? a[a_off+i] (+ b[b_off+i])
   const float* b;
   int a_off, b_off, n, n_pad, dst_off;
 };
-constexpr int kMaxRowsJobs = 40;
+constexpr int kMaxRowsJobs = 64;
 struct PackRowsArgs {
   PackRowsJob jobs[kMaxRowsJobs];
   int n_jobs;

@@ -144,6 +144,46 @@ __device__ __forceinline__ void ld_row16(float* dst, const float* base, int n_va
     for (int i = 0; i < 16; ++i) dst[i] = (row_ok && i < n_valid) ? base[i] : 0.f;
   }
 }
+// same for rows whose stride only guarantees 8-byte alignment (state rows: S = 30 floats)
+__device__ __forceinline__ void ld_row16_v2(float* dst, const float* base, int n_valid, bool row_ok) {
+  if (row_ok && n_valid >= 16 && (reinterpret_cast<uintptr_t>(base) & 7) == 0) {
+    const float2* p = reinterpret_cast<const float2*>(base);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 v = __ldg(p + i);
+      dst[2 * i] = v.x; dst[2 * i + 1] = v.y;
+    }
+  } else if (row_ok && (reinterpret_cast<uintptr_t>(base) & 7) == 0) {
+    const float2* p = reinterpret_cast<const float2*>(base);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (2 * i + 1 < n_valid) {
+        const float2 v = __ldg(p + i);
+        dst[2 * i] = v.x; dst[2 * i + 1] = v.y;
+      } else {
+        dst[2 * i] = (2 * i < n_valid) ? __ldg(base + 2 * i) : 0.f;
+        dst[2 * i + 1] = 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dst[i] = (row_ok && i < n_valid) ? __ldg(base + i) : 0.f;
+  }
+}
+__device__ __forceinline__ void st_row16_v2(float* dst, const float* v, int n_valid) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    float2* p = reinterpret_cast<float2*>(dst);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (2 * i + 1 < n_valid) p[i] = make_float2(v[2 * i], v[2 * i + 1]);
+      else if (2 * i < n_valid) dst[2 * i] = v[2 * i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < n_valid) dst[i] = v[i];
+  }
+}
 // 16 floats every lane reads alike, from the smem bias staging buffer (broadcast LDS.128)
 __device__ __forceinline__ void ld_uni16(float* dst, const float* base) {
   const float4* p = reinterpret_cast<const float4*>(base);
@@ -422,10 +462,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         } break;
         case R_PRIOR:
         case R_POST: {
-          if (half == 0) {
-            const float* eps = (st.epi == R_POST ? V.eps_post : V.eps_prior) + (trow + row) * S;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) pre[i] = (row_ok && i < S) ? __ldg(eps + i) : 0.f;
+          {  // the two warps of a quadrant take one 16-state chunk each
+            const int c = half * 16;
+            const float* eps = (st.epi == R_POST ? V.eps_post : V.eps_prior) + (trow + row) * S + c;
+            ld_row16_v2(pre, eps, S - c, row_ok && c < S);
             pre_nt = 1.f;
             if ((st.flags & SF_WRITES_STATE) && V.nonterm && (t + 1) < V.n_steps && row_ok) pre_nt = __ldg(V.nonterm + trow + N + row);
           }
@@ -463,7 +503,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         // output rows are `feature`-strided (32 sectors per store instruction).  Stages with outputs therefore
         // write their smem/TMEM operands first, hand the stage back, and only then store the outputs, which
         // drain while the next stage's MMAs run.
-        bool handed = false;
+        bool handed = false, prefetched = false;
         auto handoff = [&] {
           fence_proxy_async_smem();
           tc_fence_before();
@@ -562,76 +602,70 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
 
           case R_PRIOR:
           case R_POST: {
-            if (half == 0) {
-              const bool post = st.epi == R_POST;
-              const int W = st.width;  // mean at [0,W), raw std at [W,2W)
-              float* o_s = post ? V.post_s : V.prior_s;
-              float* o_m = post ? V.post_m : V.prior_m;
-              float* o_sd = post ? V.post_sd : V.prior_sd;
-              const bool want_kl = post && V.kl != nullptr;
-              float kl = 0.f;
-              float keep_s[32], keep_m[32], keep_sd[32];  // outputs, stored after the hand-off
-              auto chunk = [&](const int c, const float* e) {
-                const int nv = min(16, S - c);
-                float vm[16], vs[16], pm[16], psd[16];
-                const size_t o = (trow + row) * S + c;
-                if (want_kl) {
-                  ld_row16(pm, V.prior_m + o, nv, row_ok);
-                  ld_row16(psd, V.prior_sd + o, nv, row_ok);
-                }
-                tmem_ld16(tacc + c, vm);
-                tmem_ld16(tacc + W + c, vs);
-                tmem_ld_wait();
-                float smp[16];
+            // S <= 32 here (wider states run on the vm.cuh kernel): warp `half` of the quadrant owns states
+            // [16 half, 16 half + 16) of its row — mean at acc [0,W), raw std at [W,2W)
+            const bool post = st.epi == R_POST;
+            const int W = st.width;
+            const int c = half * 16;
+            const int nv = min(16, S - c);
+            const bool want_kl = post && V.kl != nullptr;
+            float kl = 0.f;
+            float vm[16], vs[16], smp[16];
+            if (nv > 0) {
+              float pm[16], psd[16];
+              const size_t o = (trow + row) * S + c;
+              if (want_kl) {
+                ld_row16_v2(pm, V.prior_m + o, nv, row_ok);
+                ld_row16_v2(psd, V.prior_sd + o, nv, row_ok);
+              }
+              tmem_ld16(tacc + c, vm);
+              tmem_ld16(tacc + W + c, vs);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                vm[i] += bias[c + i];
+                vs[i] = softplus_f(vs[i] + bias[W + c + i]) + V.min_std;
+                smp[i] = vm[i] + vs[i] * pre[i];
+              }
+              if (want_kl) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  vm[i] += bias[c + i];
-                  vs[i] = softplus_f(vs[i] + bias[W + c + i]) + V.min_std;
-                  smp[i] = vm[i] + vs[i] * e[i];
-                }
-                if (want_kl) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) {
-                    if (i < nv && row_ok) {
-                      const float ratio = vs[i] / psd[i], vr = ratio * ratio;
-                      const float dm = (vm[i] - pm[i]) / psd[i];
-                      kl += 0.5f * (vr + dm * dm - 1.f - logf(vr));
-                    }
+                  if (i < nv && row_ok) {
+                    const float ratio = vs[i] / psd[i], vr = ratio * ratio;
+                    const float dm = (vm[i] - pm[i]) / psd[i];
+                    kl += 0.5f * (vr + dm * dm - 1.f - logf(vr));
                   }
                 }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { keep_s[c + i] = smp[i]; keep_m[c + i] = vm[i]; keep_sd[c + i] = vs[i]; }
-                if (st.flags & SF_WRITES_STATE) {
-                  if (((D + c) & 1) == 0) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                      if (i + 1 < nv) x_put2(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt, smp[i + 1] * pre_nt);
-                      else if (i < nv) x_put(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt);
-                    }
-                  } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                      if (i < nv) x_put(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt);
-                  }
-                }
-              };
-              chunk(0, pre);                      // S <= 32 here (wider states run on the vm.cuh kernel)
-              if (S > 16) chunk(16, pre + 16);
-              handoff();
-              if (row_ok) {
-                const size_t o = (trow + row) * S;
-                st_row16(o_s + o, keep_s, min(16, S));
-                st_row16(o_m + o, keep_m, min(16, S));
-                st_row16(o_sd + o, keep_sd, min(16, S));
-                if (S > 16) {
-                  st_row16(o_s + o + 16, keep_s + 16, S - 16);
-                  st_row16(o_m + o + 16, keep_m + 16, S - 16);
-                  st_row16(o_sd + o + 16, keep_sd + 16, S - 16);
-                }
-                if (want_kl) V.kl[trow + row] = kl;
               }
-            } else if ((st.flags & SF_LOADS_ACTION) && has_next && row_ok) {
-              for (int j = 0; j < A; ++j) x_put(x_hi, x_lo, r, D + S + j, __ldg(V.actions_in + (trow + N + row) * A + j));
+              if (st.flags & SF_WRITES_STATE) {
+                if (((D + c) & 1) == 0) {
+#pragma unroll
+                  for (int i = 0; i < 16; i += 2) {
+                    if (i + 1 < nv) x_put2(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt, smp[i + 1] * pre_nt);
+                    else if (i < nv) x_put(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (i < nv) x_put(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt);
+                }
+              }
+            }
+            if (half == 1) {
+              if ((st.flags & SF_LOADS_ACTION) && has_next && row_ok)
+                for (int j = 0; j < A; ++j) x_put(x_hi, x_lo, r, D + S + j, __ldg(V.actions_in + (trow + N + row) * A + j));
+              if (want_kl) scratch[r] = kl;
+            }
+            handoff();
+            if (nv > 0 && row_ok) {
+              const size_t o = (trow + row) * S + c;
+              st_row16_v2((post ? V.post_s : V.prior_s) + o, smp, nv);
+              st_row16_v2((post ? V.post_m : V.prior_m) + o, vm, nv);
+              st_row16_v2((post ? V.post_sd : V.prior_sd) + o, vs, nv);
+            }
+            if (want_kl) {   // uniform across the CTA: V.kl and the stage kind are kernel-wide
+              epi_sync();
+              if (half == 0 && row_ok) V.kl[trow + row] = kl + scratch[r];
             }
           } break;
 
@@ -671,12 +705,14 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         }
 
         if (!handed) handoff();
+        if (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5) V.dbg_clock[600 + s * 2] = clock64();
         // fetch for the next stage while its MMAs run
         buf ^= 1;
         {
           const bool wrap = (s + 1 == P.n_rstages);
-          if (!wrap || has_next) prefetch(wrap ? t + 1 : t, wrap ? 0 : s + 1, buf);
+          if (!prefetched && (!wrap || has_next)) prefetch(wrap ? t + 1 : t, wrap ? 0 : s + 1, buf);
         }
+        if (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5) V.dbg_clock[600 + s * 2 + 1] = clock64();
       }
     }
 

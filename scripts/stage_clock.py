@@ -19,6 +19,7 @@ reward = cu(O.make_mlp_params(2, 230, 200, 1, 3))
 value = cu(O.make_mlp_params(3, 230, 200, 1, 3))
 x = O.make_imagine_inputs(1, N, 15)
 a = [params, actor, reward, value, x["belief"].to(dev), x["state"].to(dev), x["eps_action"].to(dev), x["eps_prior"].to(dev), 15]
+_lib.lib().repo_b200_debug_flags(int(os.environ.get('RB_DBG', '0')))
 ops.imagine_fwd(*a, row_tile=128)
 torch.cuda.synchronize()
 NS = 32
@@ -28,6 +29,8 @@ ops.imagine_fwd(*a, row_tile=128)
 torch.cuda.synchronize()
 _lib.lib().repo_b200_debug_clock(None)
 b = buf.cpu().numpy()
+extra = b[600:600 + 64].copy()
+b[600:] = 0
 nz = (b != 0).sum() // (14 * 2)
 b = b[: 14 * nz * 2].reshape(14, nz, 2)
 print("stages per step:", nz)
@@ -40,5 +43,5 @@ for s in range(nz):
     mma = b[t, s, 0] - prev_end
     tot_epi += epi
     tot_mma += mma
-    print(f"{names[s] if s < len(names) else s:>4}: mma_phase {mma:6d} cyc   epilogue {epi:6d} cyc")
+    print(f"{names[s] if s < len(names) else s:>4}: mma_phase {mma:6d} cyc   epilogue {epi:6d} cyc   handoff->stage end {extra[2 * s] - b[t, s, 1]:6d}   prefetch {extra[2 * s + 1] - extra[2 * s]:6d}")
 print("step total:", b[t + 1, 0, 0] - b[t, 0, 0], "cycles; mma", tot_mma, "epi", tot_epi)
