@@ -228,26 +228,24 @@ __device__ __forceinline__ float act_bf(float x) {
 // Pad columns need no guard: their weight rows and bias are zero, so they come out as act(0) = 0.
 // The TMEM load of the next chunk is issued before the current one is processed (latency hidden).
 // DOT: instead of storing H, reduce it against a weight vector (the scalar head's last layer).
-template <int ACT, bool DOT>
+template <int ACT, bool DOT, bool ADDEND>
 __device__ __forceinline__ float rows_act_h(const RowsParams& P, const RStage& st, const float* bias, uint32_t tacc,
                                             uint32_t th_hi, uint32_t th_lo, int half, int row, bool row_ok,
                                             size_t trow) {
   const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
-  const bool addend = (st.flags & SF_ADDEND) != 0;
   const float* wdot = bias + nch * 16;  // DOT: the 1-output layer's weight row follows the bias
-  const float* adrow = addend ? P.v.addend + (trow + row) * P.v.Hd : nullptr;
+  const float* adrow = ADDEND ? P.v.addend + (trow + row) * P.v.Hd : nullptr;
   float dot = 0.f;
-  float ad[16];
-  if (addend && half < nch) ld_row16(ad, adrow + half * 16, nfeat - half * 16, row_ok);
   for (int ch = half; ch < nch; ch += 2) {
     float v[16], bz[16];
     const int f0 = ch * 16;
     tmem_ld16(tacc + f0, v);
     ld_uni16(bz, bias + f0);
-    if (addend) {
+    if (ADDEND) {
+      float ad[16];
+      ld_row16(ad, adrow + f0, nfeat - f0, row_ok);
 #pragma unroll
       for (int i = 0; i < 16; ++i) bz[i] += ad[i];
-      if (ch + 2 < nch) ld_row16(ad, adrow + f0 + 32, nfeat - f0 - 32, row_ok);  // next chunk's rows: in flight
     }
     tmem_ld_wait();
     if (DOT) {
@@ -440,7 +438,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
     // round trip.  So while the MMAs of a stage run, the epilogue warps already fetch what that
     // stage's epilogue will need: its biases into a smem staging buffer, its per-row inputs
     // (noise, previous belief) into registers.
-    float pre[32];  // per-row inputs of the upcoming stage
+    float pre[16];  // per-row inputs (noise) of the upcoming stage; the GRU reads b_prev back from X
     float pre_nt = 1.f;
     auto prefetch = [&](int t, int s, int buf) {
       const RStage& st = P.stages[s];
@@ -448,18 +446,6 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       float* dstb = bias_s + buf * kBiasStage;
       for (int i = et; i < st.bias_n; i += kRowsEpiThreads) dstb[i] = __ldg(V.bias + st.bias_off + i);
       switch (st.epi) {
-        case R_GRU: {
-          const float* bprev = (t == 0) ? V.init_belief : (V.beliefs + (trow - N) * D);
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int c = (half + 2 * k) * 16;
-            if (bprev && c < st.nfeat) ld_row16(pre + 16 * k, bprev + (size_t)row * D + st.unit0 + c, st.nfeat - c, row_ok);
-            else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) pre[16 * k + i] = 0.f;
-            }
-          }
-        } break;
         case R_PRIOR:
         case R_POST: {
           {  // the two warps of a quadrant take one 16-state chunk each
@@ -514,14 +500,20 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
 
         switch (st.epi) {
           case R_ACT_H: {
-            if (st.act == ACT_ELU) rows_act_h<ACT_ELU, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
-            else rows_act_h<ACT_RELU, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            const bool elu = st.act == ACT_ELU;
+            if (st.flags & SF_ADDEND) {
+              if (elu) rows_act_h<ACT_ELU, false, true>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+              else rows_act_h<ACT_RELU, false, true>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            } else {
+              if (elu) rows_act_h<ACT_ELU, false, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+              else rows_act_h<ACT_RELU, false, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            }
           } break;
 
           case R_ACT_DOT: {
             float dot;
-            if (st.act == ACT_ELU) dot = rows_act_h<ACT_ELU, true>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
-            else dot = rows_act_h<ACT_RELU, true>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            if (st.act == ACT_ELU) dot = rows_act_h<ACT_ELU, true, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            else dot = rows_act_h<ACT_RELU, true, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
             if (half == 1) scratch[r] = dot;
             epi_sync();
             if (half == 0 && row_ok) {
@@ -556,10 +548,32 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
 #pragma unroll
                 for (int i = 0; i < 16; ++i) vh[i] = vr[i] * (vh[i] + bb[i]);
                 ld_uni16(bb, bias + 2 * W + c);
+                // b_prev = hi + lo from the belief slot of X (exact to 2^-22 relative; this thread's units, which the
+                // refresh below overwrites only after every warp has passed the epi_sync that follows the last chunk)
+                float bp[16];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const int kg = (u0 + c) / 8 + j;
+                  if (kg * 8 < D) {
+                    const uint4 h4 = *reinterpret_cast<const uint4*>(x_hi + (uint32_t)kg * kXLBO + (uint32_t)r * 16u);
+                    const uint4 l4 = *reinterpret_cast<const uint4*>(x_lo + (uint32_t)kg * kXLBO + (uint32_t)r * 16u);
+                    const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+                      const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+                      bp[8 * j + 2 * e] = hf.x + lf.x;
+                      bp[8 * j + 2 * e + 1] = hf.y + lf.y;
+                    }
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) bp[8 * j + e] = 0.f;
+                  }
+                }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   const float nn = tanh_f(vi[i] + bb[i] + vh[i]);
-                  bnew[k][i] = nn + vz[i] * (pre[16 * k + i] - nn);   // (1-z)*n + z*b_prev
+                  bnew[k][i] = nn + vz[i] * (bp[i] - nn);   // (1-z)*n + z*b_prev
                 }
               }
             }
@@ -631,9 +645,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   if (i < nv && row_ok) {
-                    const float ratio = vs[i] / psd[i], vr = ratio * ratio;
-                    const float dm = (vm[i] - pm[i]) / psd[i];
-                    kl += 0.5f * (vr + dm * dm - 1.f - logf(vr));
+                    const float inv = rcp_f(psd[i]);   // MUFU forms: ~1e-7 relative, far inside the KL tolerance
+                    const float ratio = vs[i] * inv, vr = ratio * ratio;
+                    const float dm = (vm[i] - pm[i]) * inv;
+                    kl += 0.5f * (vr + dm * dm - 1.f - __logf(vr));
                   }
                 }
               }
