@@ -44,7 +44,9 @@ enum RowsEpi : uint8_t {
   R_SCALAR = 5,
   R_ACT_DOT = 6,  // last hidden layer of a scalar head fused with its 1-output layer: out = w . act(acc + b) + b0
 };
-enum RowsFlags : uint8_t { RF_LAST_CHUNK = 16 };  // plus SF_* from vm.cuh
+enum RowsFlags : uint8_t { RF_LAST_CHUNK = 16, RF_SPLIT = 32 };  // plus SF_* from vm.cuh
+// RF_SPLIT (R_ACT_H / R_ACT_DOT): the layer runs as two GEMMs over output features [0, 16*width) and the rest; the
+// first half's accumulators are committed on their own barrier, so its epilogue runs under the second half's MMAs.
 
 struct RGemm {            // acc[:, acc_col ..+n) (+)= A(128 x 16*ksl) * W(n x 16*ksl)^T
   uint32_t w_off16;       // weight blob offset / 16
@@ -60,11 +62,13 @@ struct RGemm {            // acc[:, acc_col ..+n) (+)= A(128 x 16*ksl) * W(n x 1
 struct RStage {
   uint8_t gemm_begin, gemm_end;
   uint8_t epi, flags;
-  uint8_t act, pad0;
+  uint8_t act;
+  uint8_t regs;        // TMEM regions: bit0 = accumulator region, bit1 = region holding this stage's H operand
   uint16_t nfeat;      // valid output features (R_ACT_H) / units in this chunk (R_GRU)
   uint16_t bias_off;   // float offset into the bias blob
   uint16_t unit0;      // R_GRU: first unit of the chunk
-  uint16_t width;      // R_GRU: padded units per chunk (gate stride in the accumulator); heads: padded half width
+  uint16_t width;      // R_GRU: padded units per chunk (gate stride in the accumulator); heads: padded half width;
+                       // RF_SPLIT: 16-column chunks in the first half
   uint16_t bias_n;     // floats this stage reads from the bias blob (staged in smem by the epilogue warps)
 };
 
@@ -230,13 +234,15 @@ __device__ __forceinline__ float act_bf(float x) {
 // DOT: instead of storing H, reduce it against a weight vector (the scalar head's last layer).
 template <int ACT, bool DOT, bool ADDEND>
 __device__ __forceinline__ float rows_act_h(const RowsParams& P, const RStage& st, const float* bias, uint32_t tacc,
-                                            uint32_t th_hi, uint32_t th_lo, int half, int row, bool row_ok,
-                                            size_t trow) {
+                                            int ch_begin, int ch_end, int half, int row, bool row_ok, size_t trow) {
+  // H is written IN PLACE: accumulator columns [16 ch, 16 ch + 16) of this thread's lane become the packed fp16 hi
+  // pairs (8 columns) followed by the lo pairs (8 columns) of the same 16 features, so the region that held the
+  // accumulators is the next layer's A operand and the region that held this layer's operand is free for its accumulators.
   const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
   const float* wdot = bias + nch * 16;  // DOT: the 1-output layer's weight row follows the bias
   const float* adrow = ADDEND ? P.v.addend + (trow + row) * P.v.Hd : nullptr;
   float dot = 0.f;
-  for (int ch = half; ch < nch; ch += 2) {
+  for (int ch = ch_begin + ((half ^ ch_begin) & 1); ch < ch_end; ch += 2) {   // this warp's chunks: ch = half (mod 2)
     float v[16], bz[16];
     const int f0 = ch * 16;
     tmem_ld16(tacc + f0, v);
@@ -258,11 +264,10 @@ __device__ __forceinline__ float rows_act_h(const RowsParams& P, const RStage& s
 #pragma unroll
       for (int i = 0; i < 16; i += 2)
         split2_f16(act_bf<ACT>(v[i] + bz[i]), act_bf<ACT>(v[i + 1] + bz[i + 1]), hi[i >> 1], lo[i >> 1]);
-      tmem_st8(th_hi + ch * 8, hi);
-      tmem_st8(th_lo + ch * 8, lo);
+      tmem_st8(tacc + f0, hi);
+      tmem_st8(tacc + f0 + 8, lo);
     }
   }
-  if (!DOT) tmem_st_wait();
   return dot;
 }
 
@@ -282,6 +287,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
   const int row0 = blockIdx.x * kRowsM;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kRSlots);
   const uint32_t bar_acc = smem_u32(bars + 2 * kRSlots), bar_act = smem_u32(bars + 2 * kRSlots + 1);
+  const uint32_t bar_acc_a = smem_u32(bars + 2 * kRSlots + 3);   // first part of an RF_SPLIT stage
+  const uint32_t bar_acc_b = smem_u32(scratch + 128);            // second part of a three-way split
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRSlots; ++i) {
@@ -289,6 +296,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       mbar_init(bar_empty + 8 * i, 1);
     }
     mbar_init(bar_acc, 1);
+    mbar_init(bar_acc_a, 1);
+    mbar_init(bar_acc_b, 1);
     mbar_init(bar_act, kRowsEpiThreads);
     mbar_fence_init();
   }
@@ -336,12 +345,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
     const uint64_t x_desc = make_smem_desc(smem_u32(x_hi), kXLBO, 128);
     const uint64_t x_lo_delta = x_bytes >> 4;
     constexpr uint64_t kX_slab = (2u * kXLBO) >> 4;
-    const uint32_t th_hi = tmem_base, th_lo = tmem_base + (uint32_t)P.kh_cols;
-    const uint32_t tacc = tmem_base + kAccCol;
     const uint32_t ring_a = smem_u32(ring);
     for (int t = 0; t < V.n_steps; ++t) {
       for (int s = 0; s < P.n_rstages; ++s) {
         const int g0 = P.stages[s].gemm_begin, g1 = P.stages[s].gemm_end;
+        const uint32_t tacc = tmem_base + ((P.stages[s].regs & 1) ? kAccCol : 0u);
+        const uint32_t th = tmem_base + ((P.stages[s].regs & 2) ? kAccCol : 0u);
+        const bool split = (P.stages[s].flags & RF_SPLIT) != 0;
         mbar_wait(bar_act, act_phase);
         act_phase ^= 1;
         tc_fence_after();
@@ -370,7 +380,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
                   umma_f16(d, a_hi + x_lo_delta, b_hi, idesc, 1u);
                   umma_f16(d, a_hi, b_lo, idesc, 1u);
                 } else {
-                  const uint32_t a_hi = th_hi + (kk + j) * 8u, a_lo = th_lo + (kk + j) * 8u;
+                  const uint32_t a_hi = th + (kk + j) * 16u, a_lo = a_hi + 8u;   // per k-slab: 8 hi columns, 8 lo columns
                   umma_f16_ts(d, a_hi, b_hi, idesc, (j == 0) ? acc : 1u);
                   umma_f16_ts(d, a_lo, b_hi, idesc, 1u);
                   umma_f16_ts(d, a_hi, b_lo, idesc, 1u);
@@ -383,6 +393,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             acc = 1u;
             kk += nsl;
             if (++slot == kRSlots) { slot = 0; phase ^= 1; }
+          }
+          if (split && g + 1 < g1) {   // this part's accumulators are complete: its epilogue may start
+            if (elect_one()) umma_commit(g == g0 ? bar_acc_a : bar_acc_b);
+            __syncwarp();
           }
         }
         if (elect_one()) umma_commit(bar_acc);
@@ -402,7 +416,6 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
     const int N = V.N, D = V.D, S = V.S, A = V.A;
     const bool row_ok = row < N;
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t th_hi = tl, th_lo = tl + (uint32_t)P.kh_cols, tacc = tl + kAccCol;
     auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
 
     // ---- init: zero X, then stage [belief | state*nonterm[0] | action[0]] ----
@@ -467,7 +480,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       }
     };
 
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, acc_a_phase = 0, acc_b_phase = 0;
     int buf = 0;
     {  // stage 0 of step 0 never needs per-row inputs ahead of time in either program; stage its biases
       const RStage& st0 = P.stages[0];
@@ -480,8 +493,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       for (int s = 0; s < P.n_rstages; ++s) {
         const RStage& st = P.stages[s];
         const float* bias = bias_s + buf * kBiasStage;
-        mbar_wait(bar_acc, acc_phase);
-        acc_phase ^= 1;
+        const uint32_t tacc = tl + ((st.regs & 1) ? kAccCol : 0u);
+        const bool split = (st.flags & RF_SPLIT) != 0;
+        if (split) {
+          mbar_wait(bar_acc_a, acc_a_phase);
+          acc_a_phase ^= 1;
+        } else {
+          mbar_wait(bar_acc, acc_phase);
+          acc_phase ^= 1;
+        }
         tc_fence_after();
         epi_sync();  // staged biases visible to every epilogue warp
         if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2] = clock64();
@@ -500,20 +520,58 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
 
         switch (st.epi) {
           case R_ACT_H: {
-            const bool elu = st.act == ACT_ELU;
-            if (st.flags & SF_ADDEND) {
-              if (elu) rows_act_h<ACT_ELU, false, true>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
-              else rows_act_h<ACT_RELU, false, true>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            const bool elu = st.act == ACT_ELU, addend = (st.flags & SF_ADDEND) != 0;
+            const int nch = (st.nfeat + 15) >> 4;
+            auto part = [&](int c0, int c1) {
+              if (addend) {
+                if (elu) rows_act_h<ACT_ELU, false, true>(P, st, bias, tacc, c0, c1, half, row, row_ok, trow);
+                else rows_act_h<ACT_RELU, false, true>(P, st, bias, tacc, c0, c1, half, row, row_ok, trow);
+              } else {
+                if (elu) rows_act_h<ACT_ELU, false, false>(P, st, bias, tacc, c0, c1, half, row, row_ok, trow);
+                else rows_act_h<ACT_RELU, false, false>(P, st, bias, tacc, c0, c1, half, row, row_ok, trow);
+              }
+            };
+            if (split) {
+              part(0, st.width);               // under the next part's MMAs
+              int c = st.width;
+              if (st.unit0) {
+                mbar_wait(bar_acc_b, acc_b_phase);
+                acc_b_phase ^= 1;
+                tc_fence_after();
+                part(c, st.unit0);
+                c = st.unit0;
+              }
+              mbar_wait(bar_acc, acc_phase);
+              acc_phase ^= 1;
+              tc_fence_after();
+              part(c, nch);
             } else {
-              if (elu) rows_act_h<ACT_ELU, false, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
-              else rows_act_h<ACT_RELU, false, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+              part(0, nch);
             }
+            tmem_st_wait();
           } break;
 
           case R_ACT_DOT: {
-            float dot;
-            if (st.act == ACT_ELU) dot = rows_act_h<ACT_ELU, true, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
-            else dot = rows_act_h<ACT_RELU, true, false>(P, st, bias, tacc, th_hi, th_lo, half, row, row_ok, trow);
+            const int nch = (st.nfeat + 15) >> 4;
+            const bool elu = st.act == ACT_ELU;
+            float dot = elu ? rows_act_h<ACT_ELU, true, false>(P, st, bias, tacc, 0, split ? (int)st.width : nch, half, row, row_ok, trow)
+                            : rows_act_h<ACT_RELU, true, false>(P, st, bias, tacc, 0, split ? (int)st.width : nch, half, row, row_ok, trow);
+            if (split) {
+              int c = st.width;
+              if (st.unit0) {
+                mbar_wait(bar_acc_b, acc_b_phase);
+                acc_b_phase ^= 1;
+                tc_fence_after();
+                dot += elu ? rows_act_h<ACT_ELU, true, false>(P, st, bias, tacc, c, st.unit0, half, row, row_ok, trow)
+                           : rows_act_h<ACT_RELU, true, false>(P, st, bias, tacc, c, st.unit0, half, row, row_ok, trow);
+                c = st.unit0;
+              }
+              mbar_wait(bar_acc, acc_phase);
+              acc_phase ^= 1;
+              tc_fence_after();
+              dot += elu ? rows_act_h<ACT_ELU, true, false>(P, st, bias, tacc, c, nch, half, row, row_ok, trow)
+                         : rows_act_h<ACT_RELU, true, false>(P, st, bias, tacc, c, nch, half, row, row_ok, trow);
+            }
             if (half == 1) scratch[r] = dot;
             epi_sync();
             if (half == 0 && row_ok) {
