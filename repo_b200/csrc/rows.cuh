@@ -95,6 +95,24 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// 16 lanes x 16 columns in the mma-accumulator fragment layout: thread t gets, for rows t/4 and t/4 + 8 of the 16-lane
+// window, columns {2(t%4), 2(t%4)+1} (v[0..1] / v[2..3]) and {8 + 2(t%4), 9 + 2(t%4)} (v[4..5] / v[6..7]) — i.e. four
+// neighbouring threads hold 8 consecutive columns of one row, which turns per-row stores into 32-byte segments.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // two floats -> packed fp16 hi pair and lo pair (element 0 in the low half).  Both halves must be fp16:
@@ -730,7 +748,44 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               if (want_kl) scratch[r] = kl;
             }
             handoff();
-            if (nv > 0 && row_ok) {
+            // Output rows are S floats apart, so a store with lane = row touches 32 cache lines per instruction and the
+            // 24 of them kept the LSU busy for ~9k cycles.  Transpose through tensor memory instead: park the three
+            // 32 x 16 blocks (lane = row) in columns nobody uses right now and read them back in the 16x256b fragment
+            // layout, where four neighbouring threads hold 8 consecutive floats of a row — 8 rows x 32 bytes per store.
+            // Free columns: the region the NEXT stage does not accumulate into (this stage's dead H operand or its own
+            // consumed accumulators, hence the offset past the 2W accumulator columns), provided the next stage reads X.
+            const RStage& ns = P.stages[(s + 1 == P.n_rstages) ? 0 : s + 1];
+            bool ns_reads_h = false;
+            for (int g = ns.gemm_begin; g < ns.gemm_end; ++g) ns_reads_h |= P.gemms[g].a_src == 1;
+            if (nv > 0 && (S & 1) == 0 && !ns_reads_h && 2 * W <= 128) {
+              const uint32_t tsc = tl + ((ns.regs & 1) ? 0u : kAccCol) + 128u + (uint32_t)(half * 64);
+              tmem_st16f(tsc, smp);
+              tmem_st16f(tsc + 16, vm);
+              tmem_st16f(tsc + 32, vs);
+              tmem_st_wait();
+              float* const outs[3] = {post ? V.post_s : V.prior_s, post ? V.post_m : V.prior_m, post ? V.post_sd : V.prior_sd};
+              const int cq = 2 * (lane & 3);
+#pragma unroll
+              for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                  float tq[8];
+                  tmem_ld_16x256b_x2(tsc + ((uint32_t)(16 * hb) << 16) + 16 * a, tq);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int rb = 0; rb < 2; ++rb) {
+                    const int rr = row0 + q * 32 + 16 * hb + 8 * rb + (lane >> 2);
+                    if (rr < N) {
+                      float* dst = outs[a] + (trow + rr) * S + c + cq;
+#pragma unroll
+                      for (int g = 0; g < 2; ++g)
+                        if (cq + 8 * g + 1 < nv)
+                          *reinterpret_cast<float2*>(dst + 8 * g) = make_float2(tq[4 * g + 2 * rb], tq[4 * g + 2 * rb + 1]);
+                    }
+                  }
+                }
+              }
+            } else if (nv > 0 && row_ok) {   // odd state sizes (rows not 8-byte aligned) and unusual programs
               const size_t o = (trow + row) * S + c;
               st_row16_v2((post ? V.post_s : V.prior_s) + o, smp, nv);
               st_row16_v2((post ? V.post_m : V.prior_m) + o, vm, nv);
