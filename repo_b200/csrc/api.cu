@@ -441,8 +441,10 @@ struct RBuilder {
     const int kD16 = cdiv(D, 16), kx16 = cdiv(D + S + A, 16), kSA0 = D / 16;
     dense_to_h(W->fc_embed_state_action_w, W->fc_embed_state_action_b, S + A, D, 0, S + A, D - 16 * kSA0, kx16 - kSA0,
                0, kSA0, act);
-    const int Wd = std::min(64, r16(D));
-    for (int u0 = 0; u0 < D; u0 += Wd) {
+    // chunks of 64 units; the last one is only as wide as the units that are left (200 units: 64 + 64 + 64 + 16
+    // padded columns instead of 4 x 64 — the tail chunk's MMAs and weight stream shrink to a quarter)
+    for (int u0 = 0, Wd = 0; u0 < D; u0 += Wd) {
+      Wd = std::min(64, r16(D - u0));
       const int nu = std::min(Wd, D - u0);
       RStage& s = begin_stage();
       gemm(W->rnn_w_ih, D, {{u0, nu, 0}, {D + u0, nu, Wd}, {2 * D + u0, nu, 2 * Wd}}, 3 * Wd, 0, D, 0, kD16, 1, 0, 0, 0);
