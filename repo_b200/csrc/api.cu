@@ -548,6 +548,11 @@ int launch_rows(const RowsParams& P, cudaStream_t st) {
 // 128-row tiles pay off once they fill the machine; below that the flexible row tiles of vm.cuh win
 bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
   if (d->state > 32 || d->action > 16) return false;  // the 128-row kernel keeps one row's Gaussian heads in registers
+  // its other budgets: the bias staging buffer holds a scalar head's fc3 bias + fc4 row (2 * r16(hidden) + 16 floats), H and
+  // the GRU's embedding operand fill one 256-column TMEM region, X for 128 rows must fit shared memory next to the ring
+  if (2 * r16(d->hidden) + 16 > kBiasStage || r16(d->belief) > 256 ||
+      rows_smem_bytes(cdiv(d->belief + d->state + d->action, 16)) > 227 * 1024)
+    return false;
   if (row_tile == 128) return true;
   if (row_tile == 16 || row_tile == 32 || row_tile == 64) return false;
   if (g_dbg_flags & 2) return false;

@@ -775,3 +775,39 @@ def test_disagreement_ensemble_and_inverse_dynamics_heads(dev):
     close(sd, sd64.detach().float(), "inverse-dynamics std", atol=3e-4)
     for k, w in Q.items():
         cmp(dict(inv.named_parameters())[k].grad, w.grad, "inverse dynamics " + k)
+
+
+@pytest.mark.parametrize("dims", [
+    dict(belief=200, state=30, action=6, hidden=200, embed=64),    # default widths: two-way split layers, 64+64+64+16 GRU chunks
+    dict(belief=72, state=11, action=3, hidden=136, embed=32),     # odd state size: per-row stores; 64 + 16 GRU chunks
+    dict(belief=144, state=20, action=5, hidden=120, embed=32),    # second state chunk has 4 columns; layers too narrow to split
+    dict(belief=96, state=16, action=16, hidden=240, embed=48),    # one state chunk only; 240-wide (8 + 7 chunk) layers
+    dict(belief=64, state=8, action=4, hidden=256, embed=16),      # hidden > 240 exceeds the bias staging: vm kernel
+    dict(belief=40, state=32, action=2, hidden=64, embed=16),      # two full state chunks; single narrow GRU chunk
+], ids=lambda d: f"D{d['belief']}S{d['state']}A{d['action']}H{d['hidden']}")
+def test_rows_kernel_shape_sweep(ops, dev, dims):
+    """The 128-row kernel's shape-dependent paths (RF_SPLIT layers and their TMEM region ping-pong, the TMEM-transposed
+    Gaussian-head stores and their odd-width fallback, GRU chunk widths, partial row tiles) against the oracle."""
+    D, S, A, Hd = dims["belief"], dims["state"], dims["action"], dims["hidden"]
+    params = O.make_transition_params(71, dims, 1.2)
+    x = O.make_observe_inputs(72, 5, 300, dims, p_done=0.15)           # 300 rows = 2 full tiles + 44 rows
+    g = lambda k: x[k].to(dev)
+    outs, kl, _ = ops.observe_fwd(cu(params, dev), g("prev_belief"), g("prev_state"), g("actions"), g("embeds"),
+                                  g("nonterms"), g("eps_prior"), g("eps_post"), row_tile=128)
+    want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"],
+                     x["eps_prior"], x["eps_post"])
+    for nm, o, w in zip(C.OBS_NAMES, outs, want):
+        close(o, w, f"observe {nm}")
+    close(kl, O.kl_sum(want[5], want[6], want[2], want[3]), "kl", atol=1e-3)
+    actor = O.make_mlp_params(73, D + S, Hd, 2 * A, 4, 1.2)
+    reward = O.make_mlp_params(74, D + S, Hd, 1, 3, 1.2)
+    value = O.make_mlp_params(75, D + S, Hd, 1, 3, 1.2)
+    xi = O.make_imagine_inputs(76, 200, 5, dims)
+    out = run_imagine(ops, dev, params, actor, reward, value, xi, 5, row_tile=128)
+    wi = O.imagine(params, actor, xi["belief"], xi["state"], xi["eps_action"], xi["eps_prior"], 5)
+    for nm, w in zip(C.IMG_NAMES + ["actions"], wi):
+        close(out[nm], w, f"imagine {nm}")
+    rew = O.head_forward(reward, wi[0].flatten(0, 1), wi[1].flatten(0, 1)).reshape(4, 200)
+    val = O.head_forward(value, wi[0].flatten(0, 1), wi[1].flatten(0, 1)).reshape(4, 200)
+    close(out["rewards"], rew, "rewards")
+    close(out["values"], val, "values")
