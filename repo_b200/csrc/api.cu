@@ -456,6 +456,14 @@ struct RBuilder {
       bias_job(W->rnn_b_hh, 2 * D + u0, nullptr, 0, nu, Wd);
       end_stage(s, R_GRU, (u0 + Wd >= D) ? RF_LAST_CHUNK : 0, nu, 0, u0, Wd);
     }
+    // X refresh from tensor memory (RF_PARK / RF_UNPARK): possible when every chunk before the last is a full 64 units
+    // and their packed hi/lo copies (16 columns per 16 units) fit behind the last chunk's 4 W accumulator columns
+    const int n_chunks = cdiv(D, 64);
+    const RStage& last = P.stages[n_stages - 1];
+    if (n_chunks >= 2 && !overflow && n_stages >= 2 && 4 * last.width + 64 * (n_chunks - 1) <= 256 && (D & 7) == 0) {
+      P.stages[n_stages - 2].flags |= RF_PARK;
+      P.stages[n_stages - 1].flags |= RF_UNPARK;
+    }
   }
   void scalar_head(const repo_b200_mlp_weights* M, int D, int S, int Hd, int act, int flags) {
     const int kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);

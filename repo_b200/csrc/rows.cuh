@@ -44,7 +44,10 @@ enum RowsEpi : uint8_t {
   R_SCALAR = 5,
   R_ACT_DOT = 6,  // last hidden layer of a scalar head fused with its 1-output layer: out = w . act(acc + b) + b0
 };
-enum RowsFlags : uint8_t { RF_LAST_CHUNK = 16, RF_SPLIT = 32 };  // plus SF_* from vm.cuh
+enum RowsFlags : uint8_t { RF_LAST_CHUNK = 16, RF_SPLIT = 32, RF_PARK = 64, RF_UNPARK = 128 };  // plus SF_* from vm.cuh
+// RF_PARK (the GRU chunk before the last) / RF_UNPARK (the last): the new belief units of all earlier chunks are parked,
+// already split into fp16 hi/lo, in the accumulator columns the narrow last chunk leaves free, and the belief slot of X
+// is refreshed from there (thread-local TMEM loads) instead of from a global read-back.
 // RF_SPLIT (R_ACT_H / R_ACT_DOT): the layer runs as two GEMMs over output features [0, 16*width) and the rest; the
 // first half's accumulators are committed on their own barrier, so its epilogue runs under the second half's MMAs.
 
@@ -659,7 +662,68 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               const int c = (half + 2 * k) * 16;
               if (c < nu && row_ok) st_row16(V.beliefs + (trow + row) * D + u0 + c, bnew[k], min(16, nu - c));
             }
-            if (st.flags & RF_LAST_CHUNK) {
+            if (st.flags & RF_PARK) {
+              // The last chunk is narrow: its MMAs only touch accumulator columns [0, 4 W_last).  Park this row's new
+              // belief units of this and the earlier chunks (re-read: this thread's own stores) behind them as packed
+              // fp16 hi/lo — 16 columns per 16-unit group, groups g = half (mod 2) are this thread's — while the last
+              // chunk's MMAs run.  The sibling warp shares these TMEM lanes: wait until it has drained its accumulators.
+              // (Re-reading both earlier chunks in one batch, or ahead of this chunk's stores, was tried: the 64 extra
+              // live registers spill into the hidden-layer epilogues, 160.7k -> 184k cycles per step.)
+              epi_sync();
+              const uint32_t tpark = tacc + 4u * P.stages[s + 1].width;
+              const int nprev = u0 >> 6;
+              const float* brow = V.beliefs + (trow + row) * D;
+              for (int pc = 0; pc <= nprev; ++pc) {
+                float pv[2][16];
+                if (pc < nprev) {
+#pragma unroll
+                  for (int k = 0; k < 2; ++k) ld_row16(pv[k], brow + 64 * pc + (half + 2 * k) * 16, 16, row_ok);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 2; ++k)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) pv[k][i] = bnew[k][i];
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  uint32_t hl[16];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) split2_f16(pv[k][2 * i], pv[k][2 * i + 1], hl[i], hl[8 + i]);
+                  tmem_st16f(tpark + 16u * (uint32_t)(4 * pc + half + 2 * k), reinterpret_cast<const float*>(hl));
+                }
+              }
+              tmem_st_wait();
+            }
+            if ((st.flags & RF_LAST_CHUNK) && (st.flags & RF_UNPARK)) {
+              // every chunk's MMAs are done: the belief slot of X may be overwritten.  Earlier chunks: from the parked
+              // columns (this thread's own groups — the same ones whose old values it read for the blend, so no
+              // cross-thread hazard and no barrier); this chunk: from registers.
+              const uint32_t tpark = tacc + 4u * W;
+              const int ngroups = u0 >> 4;
+              for (int g = half; g < ngroups; g += 2) {
+                uint32_t hl[16];
+                tmem_ld16(tpark + 16u * g, reinterpret_cast<float*>(hl));
+                tmem_ld_wait();
+                const uint32_t o = (uint32_t)(2 * g) * kXLBO + (uint32_t)r * 16u;
+                *reinterpret_cast<uint4*>(x_hi + o) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
+                *reinterpret_cast<uint4*>(x_hi + o + kXLBO) = make_uint4(hl[4], hl[5], hl[6], hl[7]);
+                *reinterpret_cast<uint4*>(x_lo + o) = make_uint4(hl[8], hl[9], hl[10], hl[11]);
+                *reinterpret_cast<uint4*>(x_lo + o + kXLBO) = make_uint4(hl[12], hl[13], hl[14], hl[15]);
+              }
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int c = (half + 2 * k) * 16;
+                if (c < nu) {
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    const int u = u0 + c + 8 * j;
+                    if (u + 8 <= D) x_put8(x_hi, x_lo, r, u >> 3, bnew[k] + 8 * j);
+                    else
+                      for (int i = 0; u + i < D && i < 8; ++i) x_put(x_hi, x_lo, r, u + i, bnew[k][8 * j + i]);
+                  }
+                }
+              }
+            } else if (st.flags & RF_LAST_CHUNK) {
               // every chunk's MMAs are done: now the belief slot of X may be overwritten.  Rows were
               // written by both warps of the quadrant, so sync the epilogue warps first; the loads
               // are issued in batches so the L2 latency is paid once per batch, not once per k-group.
