@@ -29,7 +29,7 @@ FLOP_PER_STEP = 1_440_000      # algorithmic forward FLOPs per
 BYTES_PER_STEP = 1_312         # algorithmic HBM bytes per imagined latent step
 HORIZON = 15
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture (profiles/), by rows
-TRAFFIC_BYTES = {75776: 233_884_160 + 1_228_558_000}  # profiles/r01_rssm_rows_kernel_75776x14_ncu_full.txt
+TRAFFIC_BYTES = {75776: 245_965_056 + 1_218_886_000}  # profiles/r01_rssm_rows_kernel_75776x14_ncu_full.txt
 DIMS = dict(belief=200, state=30, action=6, hidden=200, embed=1024)
 
 
