@@ -9,11 +9,15 @@
 // Operand homes:
 //   X = [belief | state | action]  fp16 hi/lo in SHARED memory (K-major core matrices) — A operand
 //       of the layers that read it (SS-mode MMA);
-//   H = hidden activations          fp16 hi/lo packed pairs in TENSOR memory, columns [0,256) — A operand
-//       of the layers that read it (TS-mode MMA), written by the epilogue with tcgen05.st;
+//   H = hidden activations          fp16 hi/lo packed pairs in TENSOR memory — A operand of the layers that read it
+//       (TS-mode MMA).  TMEM is two 256-column regions that swap roles every hidden layer: a layer accumulates into the
+//       region that does not hold its H operand and its epilogue rewrites the accumulators IN PLACE as the next H
+//       (16 fp32 columns of a feature chunk -> 8 columns of hi pairs + 8 of lo pairs, tcgen05.ld / tcgen05.st);
 //   W = weights                     B operand, pre-packed (pack.cuh, PackRowsJob) slabs [hi | lo] of
 //       Npad x 16 K, streamed L2 -> smem ring by the TMA engine (1-D bulk copies);
-//   accumulators                    TMEM columns [256,512).
+//   accumulators                    the other TMEM region (RStage::regs); wide hidden layers run as two GEMMs over
+//       output-feature halves with separate commit barriers (RF_SPLIT), so the first half's epilogue overlaps the
+//       second half's MMAs.
 // x*W = hi*hi + lo*hi + hi*lo (three MMAs, fp32 accumulate) as in vm.cuh.
 //
 // Warps: 0 = weight loader, 1 = MMA issuer + TMEM owner (warpgroup 0 gives its registers away with
@@ -78,7 +82,7 @@ struct RStage {
 struct RowsParams {
   VmParams v;            // dims, scalars, I/O pointers (stage/gemm tables inside are unused here)
   int n_rstages;
-  int kh_cols;           // TMEM columns per H half = 8 * kh16
+  int kh_cols;           // 8 * kh16 (kept for the host-side size checks; H is interleaved hi/lo per 16-feature chunk)
   RStage stages[kRMaxStages];
   RGemm gemms[kRMaxGemms];
 };
