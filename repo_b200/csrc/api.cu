@@ -565,7 +565,10 @@ bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
   if (row_tile == 16 || row_tile == 32 || row_tile == 64) return false;
   if (g_dbg_flags & 2) return false;
   if (g_dbg_flags & 4) return true;
-  return n_rows >= 128 * std::max(1, sm_count()) / 2;
+  // measured crossover (scripts/tile_crossover.py, imagine forward, horizon 15): the 128-row kernel takes ~1.27 ms for
+  // anything up to one wave (18,944 rows); the vm kernel 1.19 ms while 16-row tiles fit one wave of CTAs, 1.5 ms with
+  // 32-row tiles, 2.0 ms with 64 — so the rows kernel takes over as soon as 16-row tiles no longer fit one wave
+  return n_rows > 16 * std::max(1, sm_count());
 }
 
 
