@@ -196,6 +196,53 @@ def imagine(p: Params, ap: Params, prev_belief, prev_state, eps_action, eps_prio
 
 
 # ----------------------------------------------------------------------------
+# optional Dreamer heads
+# ----------------------------------------------------------------------------
+def ensemble_forward(ep: Params, belief, state, action, act="elu"):
+    """EnsembleDynamicsModel.forward (models/utils.py:52-80) on EnsembleLinearLayer weights (E, in, out), biases
+    (E, 1, out) (models/utils.py:19-49): (E, rows, belief) next-belief predictions."""
+    h = torch.cat([belief, state, action], 1)
+    for i in (1, 2, 3):
+        h = _act(act)(torch.matmul(h, ep[f"fc{i}.weight"]) + ep[f"fc{i}.bias"])
+    return torch.matmul(h, ep["fc4.weight"]) + ep["fc4.bias"]
+
+
+def _transition_rows(beliefs, states, actions, nonterms):
+    """dreamer.py:199-209 / :221-231: rows with nonterms[1:-1] == 1 of (actions[1:-1], beliefs[:-1], states[:-1],
+    beliefs[1:]), flattened time-major."""
+    keep = nonterms[1:-1].flatten() == 1
+    return [x.flatten(0, 1)[keep] for x in (actions[1:-1], beliefs[:-1], states[:-1], beliefs[1:])]
+
+
+def disag_loss(ep: Params, beliefs, states, actions, nonterms, act="elu"):
+    """Dreamer.train_disag (dreamer.py:198-217): -Independent(Normal(pred, 1), 1).log_prob(target).sum(0).mean()."""
+    a, b, s, b_next = _transition_rows(beliefs, states, actions, nonterms)
+    pred = ensemble_forward(ep, b, s, a, act)
+    nll = 0.5 * (pred - b_next.unsqueeze(0)) ** 2 + 0.5 * math.log(2 * math.pi)
+    return nll.sum(2).sum(0).mean()
+
+
+def inverse_dynamics_forward(ip: Params, belief, state, next_belief, act="elu", min_std=0.1):
+    """InverseDynamicsModel.forward (models/utils.py:83-109): chunk -> mean first, std = softplus(raw) + min_std."""
+    o = mlp(ip, torch.cat([belief, state, next_belief], 1), 4, act)
+    mean, raw = o.chunk(2, dim=1)
+    return mean, F.softplus(raw) + min_std
+
+
+def inv_dyn_loss(ip: Params, beliefs, states, actions, nonterms, act="elu"):
+    """Dreamer.train_inv_dynamics (dreamer.py:219-239): -Independent(Normal(mean, std), 1).log_prob(action).mean()."""
+    a, b, s, b_next = _transition_rows(beliefs, states, actions, nonterms)
+    mean, std = inverse_dynamics_forward(ip, b, s, b_next, act)
+    nll = 0.5 * ((a - mean) / std) ** 2 + std.log() + 0.5 * math.log(2 * math.pi)
+    return nll.sum(1).mean()
+
+
+def disagreement(ep: Params, beliefs, states, actions, act="elu"):
+    """dreamer.py:333-338: ensemble spread ens_preds.std(0).mean(-1) (torch's unbiased std over the members)."""
+    return ensemble_forward(ep, beliefs, states, actions, act).std(0).mean(-1)
+
+
+# ----------------------------------------------------------------------------
 # reductions hanging off the recurrence
 # ----------------------------------------------------------------------------
 

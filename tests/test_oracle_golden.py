@@ -127,3 +127,28 @@ def test_conditional_oracle_matches_reference_fixture():
                    xo["eps_prior"], xo["eps_post"])
     for nm, idx in (("ob_beliefs", 0), ("ob_posterior_states", 4), ("ob_posterior_means", 5), ("ob_prior_std_devs", 3)):
         np.testing.assert_allclose(ob[idx].numpy(), g[nm], rtol=2e-5, atol=2e-6, err_msg=nm)
+
+
+def test_optional_heads_match_reference_trainer_methods():
+    """Oracle restatement of Dreamer.train_disag / train_inv_dynamics (dreamer.py:198-239) against the losses and
+    gradients the reference's own methods produced (oracle/make_golden_heads.py)."""
+    from repo_b200 import synth
+    g, meta = C.load("train_heads")
+    seed, T, B = int(meta["seed"]), int(meta["T"]), int(meta["B"])
+    ep = {k: v.clone().requires_grad_(True) for k, v in synth.make_ensemble_params(seed, 236, 200, 200, 6).items()}
+    ip = {k: v.clone().requires_grad_(True) for k, v in O.make_mlp_params(seed + 1, 430, 512, 12, 3).items()}
+    x = synth.make_head_rollout(seed + 2, T, B)
+    dl = O.disag_loss(ep, x["beliefs"], x["states"], x["actions"], x["nonterms"])
+    il = O.inv_dyn_loss(ip, x["beliefs"], x["states"], x["actions"], x["nonterms"])
+    np.testing.assert_allclose(dl.item(), g["log_disag_loss"], rtol=1e-5)
+    np.testing.assert_allclose(il.item(), g["log_inv_dyn_loss"], rtol=1e-5)
+    dl.backward()
+    il.backward()
+    for prefix, params in (("disag", ep), ("inv", ip)):
+        for k, p in params.items():
+            want = g[f"{prefix}_grad_{k}"]
+            got = p.grad.numpy()
+            np.testing.assert_allclose(np.sqrt((got.astype(np.float64) ** 2).sum()), g[f"{prefix}_gradnorm_{k}"], rtol=1e-4)
+            if want.shape != got.shape:
+                got = got.reshape(-1)[::97]
+            np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-6 * np.abs(want).max(), err_msg=f"{prefix} {k}")
