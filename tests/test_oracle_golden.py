@@ -152,3 +152,33 @@ def test_optional_heads_match_reference_trainer_methods():
             if want.shape != got.shape:
                 got = got.reshape(-1)[::97]
             np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-6 * np.abs(want).max(), err_msg=f"{prefix} {k}")
+
+
+def test_disagreement_bonus_matches_reference_actor_critic():
+    """dreamer.py:330-339: the ensemble-spread bonus over the imagined rollout, oracle vs the value the reference's
+    train_actor_critic logged (and the other logged scalars of that call)."""
+    from repo_b200 import synth
+    g, meta = C.load("train_heads")
+    seed, N, H = int(meta["seed"]), int(meta["N"]), int(meta["H"])
+    D, S, A, Hd = 200, 30, 6, 200
+    ep = synth.make_ensemble_params(seed, D + S + A, Hd, D, 6)
+    tp, ap = O.make_transition_params(seed + 3), O.make_mlp_params(seed + 4, D + S, Hd, 2 * A, 4)
+    rp, vp = O.make_mlp_params(seed + 5, D + S, Hd, 1, 3), O.make_mlp_params(seed + 6, D + S, Hd, 1, 3)
+    y = O.make_imagine_inputs(seed + 7, N, H)
+    rs = np.random.RandomState(seed + 8)
+    eps_ent = torch.from_numpy(rs.standard_normal((100, (H - 1) * N, A)).astype(np.float32))
+    eps_disag = torch.from_numpy(rs.standard_normal(((H - 1) * N, A)).astype(np.float32))
+    b, s, pm, psd, _ = O.imagine(tp, ap, y["belief"], y["state"], y["eps_action"], y["eps_prior"], H)
+    fb, fs = b.flatten(0, 1), s.flatten(0, 1)
+    mean, std = O.actor_forward(ap, fb, fs)
+    disag = O.disagreement(ep, fb, fs, torch.tanh(mean + std * eps_disag)).reshape(H - 1, N)
+    np.testing.assert_allclose(disag.mean().item(), g["log_disagreement"], rtol=1e-4)
+    ent = O.tanh_normal_entropy(mean, std, eps_ent).mean()
+    np.testing.assert_allclose(ent.item(), g["log_action_entropy"], rtol=1e-4)
+    rew = O.head_forward(rp, fb, fs).reshape(H - 1, N) + float(meta["disag_coef"]) * disag
+    val = O.head_forward(vp, fb, fs).reshape(H - 1, N)
+    ret = O.imagine_returns(rew, val)
+    latent_ent = (0.5 + 0.5 * np.log(2 * np.pi) + psd.log()).sum(-1).mean()
+    actor_loss = -ret.mean() - 3e-4 * ent - 0.0 * latent_ent
+    np.testing.assert_allclose(actor_loss.item(), g["log_actor_loss"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(latent_ent.item(), g["log_latent_entropy"], rtol=1e-5)
