@@ -32,5 +32,9 @@ with torch.no_grad():
     named = lambda m: {k: v.detach() for k, v in m.named_parameters()}
     out = ops.imagine_fwd(named(tm), named(actor), named(reward), named(reward), big["belief"].to(dev), big["state"].to(dev),
                           big["eps_action"].to(dev), big["eps_prior"].to(dev), 4, row_tile=128)
+    xo = O.make_observe_inputs(7, 4, 200)      # 128-row kernel, posterior + KL path, partial second tile
+    go = lambda k: xo[k].to(dev)
+    oo, kl, _ = ops.observe_fwd(named(tm), go("prev_belief"), go("prev_state"), go("actions"), go("embeds"), go("nonterms"),
+                                go("eps_prior"), go("eps_post"), row_tile=128)
 torch.cuda.synchronize()
-print("sanitize workload done", float(out["returns"].sum()))
+print("sanitize workload done", float(out["returns"].sum()), float(kl.sum()))
