@@ -149,26 +149,51 @@ class TransitionModel(nn.Module):
         post = self.compute_posterior_state(belief, observation, eps=eps_post)
         return (belief,) + tuple(prior) + tuple(post)
 
-    # cell-level methods (rssm.py:34-64) run as one-step programs of the same machine
+    # cell-level methods (rssm.py:34-64).  Without gradients they run as one-step programs of the fused machine; when a
+    # gradient is required they are composed from the differentiable GEMM op (autograd.LinearFn: tcgen05 forward, data and
+    # weight gradients) plus elementwise torch ops, so standalone calls stay autograd-connected like the reference's.
+    def _act(self, x):
+        return getattr(torch.nn.functional, self.activation_function)(x)
+
     def compute_belief(self, prev_belief, state, action):
-        self._require_no_grad("compute_belief", [prev_belief, state, action])
+        if self._wants_grad([prev_belief, state, action]):
+            from .autograd import LinearFn
+            fc, rnn = self.fc_embed_state_action, self.rnn
+            h = self._act(LinearFn.apply(torch.cat([state, action], dim=1), fc.weight, fc.bias))
+            gi = LinearFn.apply(h, rnn.weight_ih, rnn.bias_ih)          # torch GRUCell: gates ordered r, z, n
+            gh = LinearFn.apply(prev_belief, rnn.weight_hh, rnn.bias_hh)
+            i_r, i_z, i_n = gi.chunk(3, dim=1)
+            h_r, h_z, h_n = gh.chunk(3, dim=1)
+            r, z = torch.sigmoid(i_r + h_r), torch.sigmoid(i_z + h_z)
+            n = torch.tanh(i_n + r * h_n)
+            return n + z * (prev_belief - n)
         with torch.no_grad():
             outs = self.observe(prev_belief, state, action.unsqueeze(0),
                                 eps_prior=torch.zeros(1, state.shape[0], self.state_size, device=state.device))
         return outs[0][0]
 
+    def _gaussian_head(self, x, fc1, fc2, eps):
+        from .autograd import LinearFn
+        hidden = self._act(LinearFn.apply(x, fc1.weight, fc1.bias))
+        mean, raw = LinearFn.apply(hidden, fc2.weight, fc2.bias).chunk(2, dim=1)      # mean first (rssm.py:45-48)
+        std = torch.nn.functional.softplus(raw) + self.min_std_dev
+        return mean + std * eps, mean, std
+
     def compute_prior_state(self, belief, *, eps=None):
         """rssm.py:42-50 -> (prior_state, prior_mean, prior_std_dev)."""
-        self._require_no_grad("compute_prior_state", [belief])
         if eps is None:
             eps = torch.randn(belief.shape[0], self.state_size, device=belief.device)
+        if self._wants_grad([belief]):
+            return self._gaussian_head(belief, self.fc_embed_belief_prior, self.fc_state_prior, eps)
         return ops.cell_fwd(_named(self), belief, None, eps, act=self.activation_function, min_std=self.min_std_dev)
 
     def compute_posterior_state(self, belief, observation, *, eps=None):
         """rssm.py:52-64 -> (posterior_state, posterior_mean, posterior_std_dev)."""
-        self._require_no_grad("compute_posterior_state", [belief, observation])
         if eps is None:
             eps = torch.randn(belief.shape[0], self.state_size, device=belief.device)
+        if self._wants_grad([belief, observation]):
+            return self._gaussian_head(torch.cat([belief, observation], dim=1), self.fc_embed_belief_posterior,
+                                       self.fc_state_posterior, eps)
         return ops.cell_fwd(_named(self), belief, observation, eps, act=self.activation_function, min_std=self.min_std_dev)
 
     # ------------------------------------------------------------------ helpers
@@ -176,19 +201,6 @@ class TransitionModel(nn.Module):
         if not torch.is_grad_enabled():
             return False
         return any(p.requires_grad for p in self.parameters()) or any(t is not None and t.requires_grad for t in tensors)
-
-    def _require_no_grad(self, what, tensors, extra=()):
-        if not torch.is_grad_enabled():
-            return
-        needs = any(p.requires_grad for p in self.parameters())
-        needs = needs or any(t is not None and t.requires_grad for t in tensors)
-        for m in extra:
-            if m is not None:
-                needs = needs or any(p.requires_grad for p in m.parameters())
-        if needs:
-            raise NotImplementedError(
-                f"TransitionModel.{what}: the backward kernels are not built yet — call under torch.no_grad() "
-                "(refusing to return silently non-differentiable outputs)")
 
 
 class ConditionalTransitionModel(TransitionModel):

@@ -811,3 +811,53 @@ def test_rows_kernel_shape_sweep(ops, dev, dims):
     val = O.head_forward(value, wi[0].flatten(0, 1), wi[1].flatten(0, 1)).reshape(4, 200)
     close(out["rewards"], rew, "rewards")
     close(out["values"], val, "values")
+
+
+@pytest.mark.parametrize("rows", [9, 260])
+def test_standalone_cells_are_differentiable(dev, rows):
+    """compute_belief / compute_prior_state / compute_posterior_state (rssm.py:34-64) called on their own with gradients
+    enabled: outputs and every gradient vs fp64 autograd of the oracle's cells; without gradients the fused one-step
+    programs must give the same values."""
+    from repo_b200.rssm import TransitionModel
+    d = O.DEFAULT_DIMS
+    D, S, A, E = d["belief"], d["state"], d["action"], d["embed"]
+    params = O.make_transition_params(81)
+    tm = TransitionModel(D, S, A, d["hidden"], E, "elu").to(dev)
+    tm.load_state_dict(params)
+    rs = np.random.RandomState(82)
+    f = lambda *sh: torch.from_numpy(rs.standard_normal(sh).astype(np.float32))
+    b0, s0, a0, emb, e1, e2 = f(rows, D).clamp(-1, 1) * 0.5, f(rows, S), f(rows, A).clamp(-1, 1), f(rows, E), f(rows, S), f(rows, S)
+    P64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    b64, s64, a64, m64 = (t.double().requires_grad_(True) for t in (b0, s0, a0, emb))
+    nb64 = O.compute_belief(P64, b64, s64, a64)
+    pr64 = O.compute_prior_state(P64, nb64, e1.double())
+    po64 = O.compute_posterior_state(P64, nb64, m64, e2.double())
+    loss64 = (nb64 ** 2).sum() + sum((t * (i + 1)).sum() for i, t in enumerate(pr64)) + sum((t ** 2).sum() for t in po64)
+    loss64.backward()
+    bg, sg, ag, mg = (t.to(dev).requires_grad_(True) for t in (b0, s0, a0, emb))
+    nb = tm.compute_belief(bg, sg, ag)
+    pr = tm.compute_prior_state(nb, eps=e1.to(dev))
+    po = tm.compute_posterior_state(nb, mg, eps=e2.to(dev))
+    loss = (nb ** 2).sum() + sum((t * (i + 1)).sum() for i, t in enumerate(pr)) + sum((t ** 2).sum() for t in po)
+    loss.backward()
+    close(nb, nb64.detach().float(), "belief")
+    for nm, got, want in zip(("state", "mean", "std"), pr, pr64):
+        close(got, want.detach().float(), "prior " + nm)
+    for nm, got, want in zip(("state", "mean", "std"), po, po64):
+        close(got, want.detach().float(), "posterior " + nm)
+
+    def cmp(got, want, nm):
+        scale = float(want.abs().max()) + 1e-12
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=1e-3, err_msg=nm)
+
+    for k, p in tm.named_parameters():
+        cmp(p.grad, P64[k].grad, k)
+    for nm, got, want in (("belief", bg, b64), ("state", sg, s64), ("action", ag, a64), ("embed", mg, m64)):
+        cmp(got.grad, want.grad, "d " + nm)
+    with torch.no_grad():      # fused one-step programs
+        nb2 = tm.compute_belief(b0.to(dev), s0.to(dev), a0.to(dev))
+        pr2 = tm.compute_prior_state(nb2, eps=e1.to(dev))
+        po2 = tm.compute_posterior_state(nb2, emb.to(dev), eps=e2.to(dev))
+    close(nb2, nb.detach().cpu(), "belief (fused)")
+    for got, want in zip(tuple(pr2) + tuple(po2), tuple(pr) + tuple(po)):
+        close(got, want.detach().cpu(), "fused vs composed")
