@@ -78,3 +78,57 @@ def test_two_rank_row_sharding_matches_single_process():
     assert out["mean_err"] < 1e-6
     assert out["bucket"] == ([3.0] * 6, [30.0] * 5)
     assert out["tmax"] == 2.0
+
+
+def _heads_worker(rank, world, port, out):
+    """Data-parallel wiring of the optional heads: each rank takes a block of batch columns, weights its loss by
+    kept_local / kept_global (Agent._head_step, one all-reduce of the row counts) and the SUM of the per-rank gradients
+    must equal the single-process gradient.  The CUDA GEMM op is replaced by torch on CPU — host logic only."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import repo_b200.autograd as ag
+    from repo_b200 import synth
+    from repo_b200.trainer import Agent, Config
+
+    class TorchLinear:
+        @staticmethod
+        def apply(x, w, b):
+            return torch.nn.functional.linear(x, w, b)
+
+    ag.LinearFn = TorchLinear
+    T, B = 9, 37
+    x = synth.make_head_rollout(702, T, B)
+    cols = slice(0, 20) if rank == 0 else slice(20, B)          # uneven shards, different numbers of kept rows
+    torch.manual_seed(0)
+    agent = Agent(Config(disag_model=True, inv_dynamics=True), 6, algo="dreamer", device="cpu")
+    agent.disag_model.load_state_dict(synth.make_ensemble_params(700, 236, 200, 200, 6))
+    agent.train_disag(x["beliefs"][:, cols], x["states"][:, cols], x["actions"][:, cols], x["nonterms"][:, cols], step=False)
+    grads = [p.grad.clone() for p in agent.disag_model.parameters()]
+    parallel.allreduce_flat(grads)
+    loss = agent.reduced_logs()["train/disag_loss"]
+    if rank == 0:
+        dist.barrier()
+        # single-process run of the same call on the whole batch (no process-group weighting: compare by hand)
+        keep = x["nonterms"][1:-1].flatten() == 1
+        a, b, s, bn = [t.flatten(0, 1)[keep] for t in (x["actions"][1:-1], x["beliefs"][:-1], x["states"][:-1], x["beliefs"][1:])]
+        ref = Agent(Config(disag_model=True), 6, algo="dreamer", device="cpu")
+        ref.disag_model.load_state_dict(synth.make_ensemble_params(700, 236, 200, 200, 6))
+        pred = ref.disag_model(b, s, a)
+        full = (0.5 * (pred - bn.unsqueeze(0)) ** 2 + 0.5 * np.log(2 * np.pi)).sum(2).sum(0).mean()
+        full.backward()
+        out["loss_err"] = abs(loss.item() - full.item()) / abs(full.item())
+        out["grad_err"] = max(float((g - p.grad).abs().max() / (p.grad.abs().max() + 1e-12))
+                              for g, p in zip(grads, ref.disag_model.parameters()))
+    else:
+        dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_optional_heads_weighting():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_heads_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out["loss_err"] < 1e-5
+    assert out["grad_err"] < 1e-4
