@@ -32,6 +32,8 @@ Reference citations (relative to /root/reference):
   lambda_return             common/utils.py:61-71
   KL terms                  algorithms/repo/repo.py:63-83, dreamer.py:278-282
   replay index math         common/buffers.py:156-166
+  ensemble / inverse dyn.   algorithms/repo/models/utils.py:19-109, dreamer.py:198-239, 330-339
+  conv encoder / decoder    algorithms/repo/models/encoder.py:21-41, decoder.py:28-48
 """
 from __future__ import annotations
 
