@@ -182,3 +182,15 @@ def test_disagreement_bonus_matches_reference_actor_critic():
     actor_loss = -ret.mean() - 3e-4 * ent - 0.0 * latent_ent
     np.testing.assert_allclose(actor_loss.item(), g["log_actor_loss"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(latent_ent.item(), g["log_latent_entropy"], rtol=1e-5)
+
+
+def test_conv_oracle_matches_reference_fixture():
+    """Oracle restatement of VisualEncoder / VisualObservationModel (encoder.py:21-41, decoder.py:28-48) against outputs of
+    the reference's own modules on the same seeded weights and frames (oracle/make_golden_conv.py)."""
+    from repo_b200 import synth
+    g, _ = C.load("conv_stacks")
+    pe, pd = synth.make_conv_params("encoder", 700), synth.make_conv_params("decoder", 701)
+    x = synth.make_frames(702, 3)
+    y = synth.make_imagine_inputs(703, 3, 2)
+    np.testing.assert_allclose(O.visual_encoder(pe, x).numpy(), g["embed"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(O.visual_decoder(pd, y["belief"], y["state"]).numpy(), g["recon"], rtol=1e-4, atol=1e-5)
