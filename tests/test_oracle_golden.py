@@ -194,3 +194,40 @@ def test_conv_oracle_matches_reference_fixture():
     y = synth.make_imagine_inputs(703, 3, 2)
     np.testing.assert_allclose(O.visual_encoder(pe, x).numpy(), g["embed"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(O.visual_decoder(pd, y["belief"], y["state"]).numpy(), g["recon"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("algo", ["dreamer", "repo"])
+def test_world_model_losses_match_reference_trainer(algo):
+    """The oracle composed into the world-model loss of Dreamer.train_dynamics (dreamer.py:241-289) / RePo.train_dynamics
+    (repo.py:25-96): conv encoder -> observe -> conv decoder / reward head -> reconstruction, reward and KL terms, against
+    the scalars the reference's own unmodified trainers logged (oracle/make_golden_trainer.py) and their returned latents."""
+    g, meta = C.load(f"train_dynamics_{algo}")
+    seed, T, B = int(meta["seed"]), int(meta["T"]), int(meta["B"])
+    D, S, A, Hd = 200, 30, 6, 200
+    tp, rp = O.make_transition_params(seed), O.make_mlp_params(seed + 2, D + S, Hd, 1, 3)
+    pe, pd = O.make_conv_params("encoder", seed + 4), O.make_conv_params("decoder", seed + 5)
+    batch = O.make_train_batch(seed + 10, T, B, A)
+    eps = O.make_observe_inputs(seed + 11, T, B)
+    obs, actions, rewards, nonterms = batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"]
+    embeds = O.visual_encoder(pe, obs.flatten(0, 1)).reshape(T, B, -1)
+    outs = O.observe(tp, torch.zeros(B, D), torch.zeros(B, S), actions[:-1], embeds[1:], nonterms[:-1],
+                     eps["eps_prior"], eps["eps_post"])                      # the caller's shifts: dreamer.py:256-258
+    beliefs, post_s = outs[0], outs[4]
+    np.testing.assert_allclose(beliefs.numpy(), g["beliefs"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(post_s.numpy(), g["posterior_states"], rtol=1e-4, atol=1e-5)
+    recon = O.visual_decoder(pd, beliefs.flatten(0, 1), post_s.flatten(0, 1)).reshape(T - 1, B, 3, 64, 64)
+    const = 0.5 * np.log(2 * np.pi)
+    obs_loss = (0.5 * (recon - obs[1:]) ** 2 + const).sum((2, 3, 4)).mean((0, 1))            # dreamer.py:262-267
+    rew = O.head_forward(rp, beliefs.flatten(0, 1), post_s.flatten(0, 1)).reshape(T - 1, B)
+    reward_loss = ((0.5 * (rew - rewards[:-1].squeeze(-1)) ** 2 + const) * nonterms[:-1].squeeze(-1)).mean((0, 1))
+    kl = O.kl_sum(outs[5], outs[6], outs[2], outs[3])
+    np.testing.assert_allclose(obs_loss.item(), g["log_obs_loss"], rtol=1e-5)
+    np.testing.assert_allclose(reward_loss.item(), g["log_reward_loss"], rtol=1e-5)
+    if algo == "dreamer":
+        kl_loss = O.dreamer_kl_loss(kl, float(meta["free_nats"]))
+    else:
+        kl_div, kl_viol, kl_loss, beta_loss = O.repo_kl_terms(kl, np.log(float(meta["init_beta"])))
+        np.testing.assert_allclose(kl_div.item(), g["log_kl_div"], rtol=1e-4)
+        np.testing.assert_allclose(float(beta_loss), g["log_beta_loss"], rtol=1e-4)
+    np.testing.assert_allclose(float(kl_loss), g["log_kl_loss"], rtol=1e-4)
+    np.testing.assert_allclose(obs_loss.item() + reward_loss.item() + float(kl_loss), g["log_model_loss"], rtol=1e-5)
