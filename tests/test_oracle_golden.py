@@ -231,3 +231,29 @@ def test_world_model_losses_match_reference_trainer(algo):
         np.testing.assert_allclose(float(beta_loss), g["log_beta_loss"], rtol=1e-4)
     np.testing.assert_allclose(float(kl_loss), g["log_kl_loss"], rtol=1e-4)
     np.testing.assert_allclose(obs_loss.item() + reward_loss.item() + float(kl_loss), g["log_model_loss"], rtol=1e-5)
+
+
+def test_actor_critic_losses_match_reference_trainer():
+    """The oracle composed into Dreamer.train_actor_critic (dreamer.py:304-381): imagine -> heads -> 100-sample entropy ->
+    lambda-return -> actor / value losses, against the scalars the reference's unmodified method logged."""
+    g, meta = C.load("train_actor_critic")
+    seed, N, H = int(meta["seed"]), int(meta["N"]), int(meta["H"])
+    D, S, A, Hd = 200, 30, 6, 200
+    tp, ap = O.make_transition_params(seed), O.make_mlp_params(seed + 1, D + S, Hd, 2 * A, 4)
+    rp, vp = O.make_mlp_params(seed + 2, D + S, Hd, 1, 3), O.make_mlp_params(seed + 3, D + S, Hd, 1, 3)
+    x = O.make_imagine_inputs(seed + 20, N, H)
+    eps_ent = torch.from_numpy(np.random.RandomState(seed + 30).standard_normal((100, (H - 1) * N, A)).astype(np.float32))
+    b, s, pm, psd, _ = O.imagine(tp, ap, x["belief"], x["state"], x["eps_action"], x["eps_prior"], H)
+    fb, fs = b.flatten(0, 1), s.flatten(0, 1)
+    mean, std = O.actor_forward(ap, fb, fs)
+    ent = O.tanh_normal_entropy(mean, std, eps_ent).mean()
+    rew = O.head_forward(rp, fb, fs).reshape(H - 1, N)
+    val = O.head_forward(vp, fb, fs).reshape(H - 1, N)
+    ret = O.imagine_returns(rew, val)                                   # (H-2, N): dreamer.py:342-349
+    latent_ent = (0.5 + 0.5 * np.log(2 * np.pi) + psd.log()).sum(-1).mean()
+    np.testing.assert_allclose(ent.item(), g["log_action_entropy"], rtol=1e-4)
+    np.testing.assert_allclose(latent_ent.item(), g["log_latent_entropy"], rtol=1e-5)
+    np.testing.assert_allclose((-ret.mean() - 3e-4 * ent).item(), g["log_actor_loss"], rtol=1e-4, atol=1e-6)
+    vpred = O.head_forward(vp, b[:-1].flatten(0, 1), s[:-1].flatten(0, 1)).reshape(H - 2, N)     # dreamer.py:362-368
+    value_loss = (0.5 * (vpred - ret) ** 2 + 0.5 * np.log(2 * np.pi)).mean()
+    np.testing.assert_allclose(value_loss.item(), g["log_value_loss"], rtol=1e-4)
