@@ -257,3 +257,46 @@ def test_actor_critic_losses_match_reference_trainer():
     vpred = O.head_forward(vp, b[:-1].flatten(0, 1), s[:-1].flatten(0, 1)).reshape(H - 2, N)     # dreamer.py:362-368
     value_loss = (0.5 * (vpred - ret) ** 2 + 0.5 * np.log(2 * np.pi)).mean()
     np.testing.assert_allclose(value_loss.item(), g["log_value_loss"], rtol=1e-4)
+
+
+def test_tia_world_model_losses_match_reference_trainer():
+    """The oracle composed into TIA.train_dynamics (tia.py:87-201): task + distractor RSSMs observed on shared embeddings,
+    the two 6-channel decoders mixed by the mask head, the distractor-only decoder, the adversarial distractor reward term and
+    both free-nats KL terms, against the scalars the reference's unmodified TIA trainer logged."""
+    import torch.nn.functional as F
+    g, meta = C.load("train_dynamics_tia")
+    seed, T, B = int(meta["seed"]), int(meta["T"]), int(meta["B"])
+    D, S, A, Hd = 200, 30, 6, 200
+    tp, dp = O.make_transition_params(seed), O.make_transition_params(seed + 6)
+    rp, drp = O.make_mlp_params(seed + 2, D + S, Hd, 1, 3), O.make_mlp_params(seed + 9, D + S, Hd, 1, 3)
+    pe = O.make_conv_params("encoder", seed + 4)
+    pt, pdm = O.make_conv_params("decoder", seed + 5, out_channels=6), O.make_conv_params("decoder", seed + 7, out_channels=6)
+    pdo, mh = O.make_conv_params("decoder", seed + 8), O.make_mask_head_params(seed + 12)
+    batch = O.make_train_batch(seed + 10, T, B, A)
+    eps_t, eps_d = O.make_observe_inputs(seed + 11, T, B), O.make_observe_inputs(seed + 13, T, B)
+    obs, actions, rewards, nonterms = batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"]
+    embeds = O.visual_encoder(pe, obs.flatten(0, 1)).reshape(T, B, -1)
+    z = lambda n: torch.zeros(B, n)
+    t = O.observe(tp, z(D), z(S), actions[:-1], embeds[1:], nonterms[:-1], eps_t["eps_prior"], eps_t["eps_post"])
+    d = O.observe(dp, z(D), z(S), actions[:-1], embeds[1:], nonterms[:-1], eps_d["eps_prior"], eps_d["eps_post"])
+    flat = lambda o: (o[0].flatten(0, 1), o[4].flatten(0, 1))
+    t_recon, t_mask = O.visual_decoder(pt, *flat(t)).chunk(2, 1)                      # decoder.py:154-175
+    d_recon, d_mask = O.visual_decoder(pdm, *flat(d)).chunk(2, 1)
+    mask = torch.sigmoid(F.conv2d(torch.cat([t_mask, d_mask], 1), mh["0.weight"], mh["0.bias"]))   # tia.py:72, 126
+    recon = (t_recon * mask + d_recon * (1 - mask)).reshape(T - 1, B, 3, 64, 64)
+    const = 0.5 * np.log(2 * np.pi)
+    nll = lambda x: (0.5 * (x - obs[1:]) ** 2 + const).sum((2, 3, 4)).mean((0, 1))
+    obs_loss = nll(recon)
+    d_obs_loss = nll(O.visual_decoder(pdo, *flat(d)).reshape(T - 1, B, 3, 64, 64))
+    tgt, m = rewards[:-1].squeeze(-1), nonterms[:-1].squeeze(-1)
+    rnll = lambda p_, o: ((0.5 * (O.head_forward(p_, *flat(o)).reshape(T - 1, B) - tgt) ** 2 + const) * m).mean((0, 1))
+    t_reward_loss, d_reward_nll = rnll(rp, t), rnll(drp, d)
+    reward_loss = t_reward_loss - 1.0 * d_reward_nll                                   # adversarial term, tia.py:152-156
+    fn = float(meta["free_nats"])
+    t_kl, d_kl = O.kl_sum(t[5], t[6], t[2], t[3]), O.kl_sum(d[5], d[6], d[2], d[3])
+    kl_loss = torch.clamp(t_kl, min=fn).mean() + torch.clamp(d_kl, min=fn).mean()
+    for name, val in (("obs_loss", obs_loss), ("d_obs_loss", d_obs_loss), ("t_reward_loss", t_reward_loss),
+                      ("d_reward_loss", d_reward_nll), ("kl_loss", kl_loss), ("t_kl_div", t_kl.mean()), ("d_kl_div", d_kl.mean())):
+        np.testing.assert_allclose(float(val), g["log_" + name], rtol=1e-4, err_msg=name)
+    np.testing.assert_allclose(float(reward_loss), g["log_reward_loss"], rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(float(obs_loss + d_obs_loss + reward_loss + kl_loss), g["log_model_loss"], rtol=1e-5)
