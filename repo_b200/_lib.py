@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librepo_b200.so")
+# REPO_B200_PROFILING=1 (scripts/stage_clock.py only) loads the -DRB_STAGE_CLOCK build with in-kernel clock stamps
+LIB_PATH = os.path.join(HERE, "librepo_b200_prof.so" if os.environ.get("REPO_B200_PROFILING") == "1" else "librepo_b200.so")
 
 ACT_KINDS = {"relu": 0, "elu": 1}
 WEIGHTS_PACKED = 1

@@ -388,46 +388,40 @@ struct RBuilder {
     s.bias_off = (uint16_t)n_bias;
     return s;
   }
-  void end_stage(RStage& s, int epi, int flags, int nfeat, int act, int unit0 = 0, int width = 0) {
+  int xdeps[kRMaxStages] = {};
+  void end_stage(RStage& s, int epi, int flags, int nfeat, int act, int unit0 = 0, int width = 0, int xdep = 1) {
     s.gemm_end = (uint8_t)n_gemms;
     s.bias_n = (uint16_t)(n_bias - s.bias_off);
     if (s.bias_n > kBiasStage) overflow = true;
     s.epi = (uint8_t)epi; s.flags = (uint8_t)flags; s.act = (uint8_t)act;
     s.nfeat = (uint16_t)nfeat; s.unit0 = (uint16_t)unit0; s.width = (uint16_t)width;
+    s.rounds = (uint8_t)(epi == R_ACT_H ? cdiv(cdiv(nfeat, 16), kEpiParts) : 1);
+    xdeps[std::min(n_stages, kRMaxStages - 1)] = xdep;
     // accumulators go to the region that does NOT hold the current H; an R_ACT_H epilogue converts them in place,
-    // so that region then holds H and the other one is free for the next layer's accumulators
-    s.regs = (uint8_t)((1 - cur_h) | (cur_h << 1));
-    if (epi == R_ACT_H) cur_h = 1 - cur_h;
+    // so that region then holds H and the other one is free for the next layer's accumulators.  An early stage
+    // (xdep > 1) runs under the previous stage's epilogue, which is still reading the OTHER region: it takes the region
+    // of the dead H operand, and its own H then lives there (no flip).
+    if (xdep > 1 && epi == R_ACT_H) {
+      s.regs = (uint8_t)(cur_h | (cur_h << 1));
+    } else {
+      s.regs = (uint8_t)((1 - cur_h) | (cur_h << 1));
+      if (epi == R_ACT_H) cur_h = 1 - cur_h;
+    }
     ++n_stages;
   }
-  // one hidden layer (or the fc3 half of a scalar head) as GEMMs over consecutive output-feature parts: a part's
-  // epilogue overlaps the next part's MMAs (RF_SPLIT).  Returns c1 | c2 << 8 (part boundaries in 16-column chunks;
-  // c2 = 0 for a two-way split), 0 when the layer is too narrow to split.  The kernel supports three parts, but
-  // measured on B200 (208-wide layers) two win: 7.2k cycles per layer against 8.35k unsplit and 7.6k three-way —
-  // an epilogue running under MMAs is ~30% slower (TMEM port contention) and narrow N costs tensor efficiency.
-  static constexpr bool kThreeWay = false;
-  int split_gemms(const float* w, int ld, int out_f, int col0, int ncols, int kofs, int ksl, int a_src, int a_k16) {
-    const int np = r16(out_f), n = np / 16;
-    int c1 = 0, c2 = 0;
-    if (kThreeWay && n >= 12 && a_src == 1) { c1 = n / 3; c2 = c1 + (n - c1 + 1) / 2; }
-    else if (n >= 8) { c1 = (n + 1) / 2; }
-    const int last0 = (c2 ? c2 : c1) * 16;
-    if (c1 == 0 || out_f <= last0) {
-      gemm(w, ld, {{0, out_f, 0}}, np, col0, ncols, kofs, ksl, a_src, a_k16, 0, 0);
-      return 0;
-    }
-    const int b1 = c1 * 16, b2 = c2 ? c2 * 16 : np;
-    gemm(w, ld, {{0, b1, 0}}, b1, col0, ncols, kofs, ksl, a_src, a_k16, 0, 0);
-    gemm(w, ld, {{b1, std::min(out_f, b2) - b1, 0}}, b2 - b1, col0, ncols, kofs, ksl, a_src, a_k16, b1, 0);
-    if (c2) gemm(w, ld, {{b2, out_f - b2, 0}}, np - b2, col0, ncols, kofs, ksl, a_src, a_k16, b2, 0);
-    return c1 | (c2 << 8);
-  }
+  // One hidden layer = ONE full-width GEMM (N = r16(out_f)): tcgen05.mma is bound by fetching the 128 x 16 A tile (~64
+  // cycles) whenever N < 128, so splitting a 208-wide layer over output features (round 1: 112 + 96 with separate commit
+  // barriers; 64 + 48 + 48 + 48 measured this round: 9.4k cycles per layer against 7.8k two-way) wastes tensor time.
+  // Overlap comes from K-chaining instead (rows.cuh): the consumer's k-slabs trail the producer's epilogue rounds.
+  // `xdep` > 1: the X columns this layer reads were final `xdep` stages ago (e.g. the value head's first layer reads
+  // [belief | state], last written by the prior head 4 stages earlier), so its MMAs may run under the previous stage's
+  // epilogue — they accumulate into the region of the dead H operand instead of the previous stage's accumulator region.
   void dense_to_h(const float* w, const float* b, int ld, int out_f, int col0, int ncols, int kofs, int ksl, int a_src,
-                  int a_k16, int act, int flags = 0) {
+                  int a_k16, int act, int flags = 0, int xdep = 1) {
     RStage& s = begin_stage();
-    const int split = split_gemms(w, ld, out_f, col0, ncols, kofs, ksl, a_src, a_k16);
+    gemm(w, ld, {{0, out_f, 0}}, r16(out_f), col0, ncols, kofs, ksl, a_src, a_k16, 0, 0);
     bias_job(b, 0, nullptr, 0, out_f, r16(out_f));
-    end_stage(s, R_ACT_H, flags | (split ? RF_SPLIT : 0), out_f, act, split >> 8, split & 255);
+    end_stage(s, R_ACT_H, flags, out_f, act, 0, 0, (a_src == 0 && xdep > 1) ? xdep : 1);
   }
   void gaussian_head(const float* w, const float* b, int ld, int n, int ksl, int epi, int flags) {
     const int np = r16(n);
@@ -456,28 +450,35 @@ struct RBuilder {
       bias_job(W->rnn_b_hh, 2 * D + u0, nullptr, 0, nu, Wd);
       end_stage(s, R_GRU, (u0 + Wd >= D) ? RF_LAST_CHUNK : 0, nu, 0, u0, Wd);
     }
-    // X refresh from tensor memory (RF_PARK / RF_UNPARK): possible when every chunk before the last is a full 64 units
-    // and their packed hi/lo copies (16 columns per 16 units) fit behind the last chunk's 4 W accumulator columns
-    const int n_chunks = cdiv(D, 64);
-    const RStage& last = P.stages[n_stages - 1];
-    if (n_chunks >= 2 && !overflow && n_stages >= 2 && 4 * last.width + 64 * (n_chunks - 1) <= 256 && (D & 7) == 0) {
-      P.stages[n_stages - 2].flags |= RF_PARK;
-      P.stages[n_stages - 1].flags |= RF_UNPARK;
-    }
   }
-  void scalar_head(const repo_b200_mlp_weights* M, int D, int S, int Hd, int act, int flags) {
+  void scalar_head(const repo_b200_mlp_weights* M, int D, int S, int Hd, int act, int flags, int xdep = 1) {
     const int kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);
-    dense_to_h(M->w[0], M->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, act);
+    dense_to_h(M->w[0], M->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, act, 0, xdep);
     dense_to_h(M->w[1], M->b[1], Hd, Hd, 0, Hd, 0, kH16, 1, 0, act);
     // fc3 + fc4 in one stage: the epilogue reduces act(fc3) against fc4's single weight row in fp32
     RStage& s = begin_stage();
-    const int split = split_gemms(M->w[2], Hd, Hd, 0, Hd, 0, kH16, 1, 0);
+    gemm(M->w[2], Hd, {{0, Hd, 0}}, r16(Hd), 0, Hd, 0, kH16, 1, 0, 0, 0);
     bias_job(M->b[2], 0, nullptr, 0, Hd, r16(Hd));
     bias_job(M->w[3], 0, nullptr, 0, Hd, r16(Hd));
     bias_job(M->b[3], 0, nullptr, 0, 1, 16);
-    end_stage(s, R_ACT_DOT, flags | (split ? RF_SPLIT : 0), Hd, act, split >> 8, split & 255);
+    end_stage(s, R_ACT_DOT, flags, Hd, act, 0, 0);
   }
-  size_t packed_bytes() const { return align_up_(w_bytes, 256) + (size_t)n_bias * sizeof(float); }
+  // xback of every stage from the xdeps recorded while building (rounds of the stages in between, wrapping into the
+  // previous time step); the first stage of the program may depend on a stage of the previous step.
+  void finish_deps() {
+    // stage 0 follows the LAST stage of the previous step: starting early is only safe when the two accumulate into
+    // different TMEM regions (the region bookkeeping is periodic only if the program flips it an even number of times)
+    if (n_stages && xdeps[0] > 1 && (P.stages[0].regs & 1) == (P.stages[n_stages - 1].regs & 1)) xdeps[0] = 1;
+    for (int i = 0; i < n_stages; ++i) {
+      int back = 0;
+      for (int j = 1; j < xdeps[i]; ++j) back += P.stages[((i - j) % n_stages + n_stages) % n_stages].rounds;
+      P.stages[i].xback = (uint8_t)std::min(back, 255);
+    }
+  }
+  // belief refresh scratch (rows.cuh, R_GRU): one [hi | lo] plane pair per SM
+  size_t scr_plane() const { return (size_t)cdiv(std::max(P.v.D, 1), 8) * kXLBO; }
+  size_t scratch_bytes() const { return (size_t)std::max(1, sm_count()) * 2 * scr_plane(); }
+  size_t packed_bytes() const { return align_up_(w_bytes, 256) + align_up_((size_t)n_bias * sizeof(float), 256) + scratch_bytes(); }
   static size_t align_up_(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
   int bind_and_pack(void* ws, size_t ws_bytes, bool do_pack, cudaStream_t st) {
@@ -488,6 +489,10 @@ struct RBuilder {
     P.v.wblob = wb;
     P.v.bias = bb;
     P.n_rstages = n_stages;
+    P.scr = wb + align_up_(w_bytes, 256) + align_up_((size_t)n_bias * sizeof(float), 256);
+    P.scr_plane = (uint32_t)scr_plane();
+    P.scr_slots = std::max(1, sm_count());
+    finish_deps();
     if (do_pack) {
       pack.wblob = wb;
       bias.bias = bb;
@@ -510,14 +515,18 @@ void build_imagine_rows(RBuilder& b, const repo_b200_dims* d, const repo_b200_rs
   const int D = d->belief, S = d->state, A = d->action, Hd = d->hidden;
   const int kD16 = cdiv(D, 16), kBS16 = cdiv(D + S, 16), kH16 = cdiv(Hd, 16);
   rows_set_dims(b.P, d);
-  b.dense_to_h(actor->w[0], actor->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, ACT_ELU);
+  // [belief | state] is final once the prior head of the previous step has run: with the scalar heads in the program, the
+  // actor's first layer (next step) and the value head's first layer start under the epilogue of the stage before them
+  const int n_head_stages = (reward ? 3 : 0) + (value ? 3 : 0);
+  const bool dbg_no_early = (g_dbg_flags & 32) != 0;
+  b.dense_to_h(actor->w[0], actor->b[0], D + S, Hd, 0, D + S, 0, kBS16, 0, 0, ACT_ELU, 0, dbg_no_early ? 1 : 1 + n_head_stages);
   for (int i = 1; i < 4; ++i) b.dense_to_h(actor->w[i], actor->b[i], Hd, Hd, 0, Hd, 0, kH16, 1, 0, ACT_ELU);
   b.gaussian_head(actor->w[4], actor->b[4], Hd, A, kH16, R_ACTION, 0);
   b.belief_update(W, D, S, A, act);
   b.dense_to_h(W->fc_embed_belief_prior_w, W->fc_embed_belief_prior_b, D, Hd, 0, D, 0, kD16, 0, 0, act);
   b.gaussian_head(W->fc_state_prior_w, W->fc_state_prior_b, Hd, S, kH16, R_PRIOR, SF_WRITES_STATE);
   if (reward) b.scalar_head(reward, D, S, Hd, act, 0);
-  if (value) b.scalar_head(value, D, S, Hd, act, SF_SCALAR_VALUE);
+  if (value) b.scalar_head(value, D, S, Hd, act, SF_SCALAR_VALUE, (reward && !dbg_no_early) ? 4 : 1);
 }
 
 void build_observe_rows(RBuilder& b, const repo_b200_dims* d, const repo_b200_rssm_weights* W, bool with_obs, int act) {

@@ -15,22 +15,33 @@
 //       (16 fp32 columns of a feature chunk -> 8 columns of hi pairs + 8 of lo pairs, tcgen05.ld / tcgen05.st);
 //   W = weights                     B operand, pre-packed (pack.cuh, PackRowsJob) slabs [hi | lo] of
 //       Npad x 16 K, streamed L2 -> smem ring by the TMA engine (1-D bulk copies);
-//   accumulators                    the other TMEM region (RStage::regs); wide hidden layers run as two GEMMs over
-//       output-feature halves with separate commit barriers (RF_SPLIT), so the first half's epilogue overlaps the
-//       second half's MMAs.
+//   accumulators                    the other TMEM region (RStage::regs).
+// Overlap of tensor pipe and epilogue (round 2): K-CHAINING.  A hidden layer's epilogue rewrites its accumulators as H in
+// ROUNDS of four 16-column chunks (one per epilogue warp of a lane quadrant) and signals each round on a ring of
+// mbarriers; the MMA issuer runs the NEXT layer's full-width GEMM (N = 208: tensor-bound — tcgen05.mma is bound by
+// fetching the 128 x 16 A tile, ~64 cycles, whenever N < 128, which is what made N-split layers slow) k-slab by k-slab
+// right behind those rounds.  Stages that only read X and whose inputs were final earlier (RStage::xback) start while the
+// previous stage's epilogue is still running, accumulating into the dead H region.
 // x*W = hi*hi + lo*hi + hi*lo (three MMAs, fp32 accumulate) as in vm.cuh.
 //
 // Warps: 0 = weight loader, 1 = MMA issuer + TMEM owner (warpgroup 0 gives its registers away with
-// setmaxnreg), 4..11 = epilogue (two warps per TMEM lane quadrant; they split the columns of wide
-// layers) running with 208 registers (128*80 + 256*208 <= the 168*384 registers the CTA was launched with).
+// setmaxnreg), 4..19 = epilogue: FOUR warps per TMEM lane quadrant (`part` 0..3 — all four sit on the SM
+// sub-partition that owns the quadrant, so each scheduler has four epilogue warps to hide TMEM / MUFU latency
+// with); they split the 16-column chunks of wide layers, the 16-unit groups of a GRU chunk and the 8-state
+// groups of the Gaussian heads.  Round 1 ran two warps per quadrant at 208 registers: the epilogue warps were
+// busy ~113k of the 160k cycles of a step, each stalled ~65 % of the time.
 #pragma once
 #include "vm.cuh"
 
 namespace rb {
 
 constexpr int kRowsM = 128;
-constexpr int kRowsThreads = 384;   // warpgroup 0: loader, MMA issuer, 2 spare; warpgroups 1-2: epilogue
-constexpr int kRowsEpiThreads = 256;
+constexpr int kRowsThreads = 640;   // warpgroup 0: loader, MMA issuer, 2 spare; warpgroups 1-4: epilogue
+constexpr int kRowsEpiWarp0 = 4;
+constexpr int kRowsEpiThreads = 512;
+constexpr int kEpiParts = 4;        // epilogue warps per TMEM lane quadrant
+constexpr int kRowsEpiWarps = kRowsEpiThreads / 32;
+constexpr int kRoundBars = 8;       // ring of round barriers; the epilogue is never more than 5 rounds ahead of the issuer
 constexpr int kRSlotBytes = 32768;
 constexpr int kRSlots = 3;
 constexpr int kRMaxStages = 32;
@@ -38,6 +49,7 @@ constexpr int kRMaxGemms = 56;
 constexpr int kBiasStage = 512;        // floats per smem bias staging buffer (double-buffered)
 constexpr uint32_t kAccCol = 256;     // accumulators live at TMEM columns [256, 512)
 constexpr uint32_t kXLBO = kRowsM * 16;  // bytes between k-groups of X (128 rows x 16 B)
+constexpr int kRowsMiscBytes = 192 + kEpiParts * 128 * 4;   // 18 mbarrier slots + GruCtx (48 bytes), cross-warp partial sums (floats[parts][128])
 
 enum RowsEpi : uint8_t {
   R_ACT_H = 0,   // H[:, f] = act(acc + bias (+ addend))            -> TMEM H
@@ -48,13 +60,12 @@ enum RowsEpi : uint8_t {
   R_SCALAR = 5,
   R_ACT_DOT = 6,  // last hidden layer of a scalar head fused with its 1-output layer: out = w . act(acc + b) + b0
 };
-enum RowsFlags : uint8_t { RF_LAST_CHUNK = 16, RF_SPLIT = 32, RF_PARK = 64, RF_UNPARK = 128 };  // plus SF_* from vm.cuh
-// RF_PARK (the GRU chunk before the last) / RF_UNPARK (the last): the new belief units of all earlier chunks are parked,
-// already split into fp16 hi/lo, in the accumulator columns the narrow last chunk leaves free, and the belief slot of X
-// is refreshed from there (thread-local TMEM loads) instead of from a global read-back.
-// RF_SPLIT (R_ACT_H / R_ACT_DOT): the layer runs as two GEMMs over output features [0, 16*width) and the rest; the
-// first half's accumulators are committed on their own barrier, so its epilogue runs under the second half's MMAs.
-
+enum RowsFlags : uint8_t { RF_LAST_CHUNK = 16 };  // plus SF_* from vm.cuh
+// Belief refresh (R_GRU): every chunk's hh MMAs read the OLD belief from X, so the new units cannot go into X before the last
+// chunk's MMAs have completed.  Each earlier chunk therefore writes its new units, already split into fp16 hi/lo and in X's
+// shared-memory layout, to a per-SM scratch in global memory (coalesced 16-byte stores, L2-resident), and the last chunk's
+// epilogue pulls them into X with two 1-D bulk copies (TMA engine) that run under its own gate math.  Round 1 parked them in
+// free TMEM columns instead (re-reading beliefs[t] from global, ~9k exposed cycles per step).
 struct RGemm {            // acc[:, acc_col ..+n) (+)= A(128 x 16*ksl) * W(n x 16*ksl)^T
   uint32_t w_off16;       // weight blob offset / 16
   uint16_t slab_bytes16;  // slab bytes / 16  (= n * 4)
@@ -74,15 +85,20 @@ struct RStage {
   uint16_t nfeat;      // valid output features (R_ACT_H) / units in this chunk (R_GRU)
   uint16_t bias_off;   // float offset into the bias blob
   uint16_t unit0;      // R_GRU: first unit of the chunk
-  uint16_t width;      // R_GRU: padded units per chunk (gate stride in the accumulator); heads: padded half width;
-                       // RF_SPLIT: 16-column chunks in the first half
+  uint16_t width;      // R_GRU: padded units per chunk (gate stride in the accumulator); heads: padded half width
   uint16_t bias_n;     // floats this stage reads from the bias blob (staged in smem by the epilogue warps)
+  uint8_t rounds;      // hand-off rounds this stage's epilogue signals: R_ACT_H = ceil(chunks / 4), every other kind 1
+  uint8_t xback;       // rounds (of the stages in between) back from the end of the previous stage to the end of the stage that
+                       // last wrote the X columns this stage reads: 0 = the previous stage (the default)
 };
 
 struct RowsParams {
   VmParams v;            // dims, scalars, I/O pointers (stage/gemm tables inside are unused here)
   int n_rstages;
   int kh_cols;           // 8 * kh16 (kept for the host-side size checks; H is interleaved hi/lo per 16-feature chunk)
+  uint8_t* scr;          // belief refresh scratch: per SM (slot = %smid) an fp16 [hi plane | lo plane] image of X's belief k-groups
+  uint32_t scr_plane;    // bytes per plane (= ceil(D / 8) * kXLBO)
+  int scr_slots;         // slots allocated (SMs whose %smid is not below this use the global re-read path)
   RStage stages[kRMaxStages];
   RGemm gemms[kRMaxGemms];
 };
@@ -120,6 +136,29 @@ __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float* v) {
                : "r"(taddr)
                : "memory");
 }
+// 16 lanes x 8 columns, same fragment layout: v[0..1] = row t/4, columns {2(t%4), 2(t%4)+1}; v[2..3] = row t/4 + 8
+__device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float* v) { tmem_st8(taddr, reinterpret_cast<const uint32_t*>(v)); }
+// 4-byte asynchronous global -> shared copy (LDGSTS): the bias staging needs no register round trip, so the issuing
+// warp does not stall on the L2 latency
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // two floats -> packed fp16 hi pair and lo pair (element 0 in the low half).  Both halves must be fp16:
@@ -156,7 +195,7 @@ __device__ __forceinline__ void x_put8(uint8_t* hi, uint8_t* lo, int row, int kg
 }
 
 __host__ __device__ inline size_t rows_smem_bytes(int kx16) {
-  return (size_t)kRSlots * kRSlotBytes + 2 * (size_t)kx16 * 2 * kXLBO + 1024 + 2 * kBiasStage * sizeof(float);
+  return (size_t)kRSlots * kRSlotBytes + 2 * (size_t)kx16 * 2 * kXLBO + kRowsMiscBytes + 2 * kBiasStage * sizeof(float);
 }
 
 // 16 contiguous floats of one row (guarded tail / alignment handled outside the fast path)
@@ -197,6 +236,27 @@ __device__ __forceinline__ void ld_row16_v2(float* dst, const float* base, int n
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) dst[i] = (row_ok && i < n_valid) ? __ldg(base + i) : 0.f;
+  }
+}
+// 8 floats of one row whose start is 8-byte aligned (state rows, S even); PLAIN loads (not the read-only path): the KL
+// term reads prior_m / prior_sd that this kernel wrote a few stages earlier
+template <bool NC>
+__device__ __forceinline__ void ld_row8_v2(float* dst, const float* base, int n_valid, bool row_ok) {
+  if (row_ok && (reinterpret_cast<uintptr_t>(base) & 7) == 0) {
+    const float2* p = reinterpret_cast<const float2*>(base);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (2 * i + 1 < n_valid) {
+        const float2 v = NC ? __ldg(p + i) : p[i];
+        dst[2 * i] = v.x; dst[2 * i + 1] = v.y;
+      } else {
+        dst[2 * i] = (2 * i < n_valid) ? (NC ? __ldg(base + 2 * i) : base[2 * i]) : 0.f;
+        dst[2 * i + 1] = 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = (row_ok && i < n_valid) ? (NC ? __ldg(base + i) : base[i]) : 0.f;
   }
 }
 __device__ __forceinline__ void st_row16_v2(float* dst, const float* v, int n_valid) {
@@ -253,47 +313,210 @@ __device__ __forceinline__ float act_bf(float x) {
   return fmaxf(x, 0.f);
 }
 
-// H = act(acc + bias (+ addend)): this warp handles 16-column chunks ch = half, half+2, ...
+// H = act(acc + bias (+ addend)) for ONE 16-column chunk of this thread's row.
 // Pad columns need no guard: their weight rows and bias are zero, so they come out as act(0) = 0.
-// The TMEM load of the next chunk is issued before the current one is processed (latency hidden).
 // DOT: instead of storing H, reduce it against a weight vector (the scalar head's last layer).
+// H is written IN PLACE: accumulator columns [16 ch, 16 ch + 16) of this thread's lane become the packed fp16 hi
+// pairs (8 columns) followed by the lo pairs (8 columns) of the same 16 features, so the region that held the
+// accumulators is the next layer's A operand and the region that held this layer's operand is free for its accumulators.
 template <int ACT, bool DOT, bool ADDEND>
-__device__ __forceinline__ float rows_act_h(const RowsParams& P, const RStage& st, const float* bias, uint32_t tacc,
-                                            int ch_begin, int ch_end, int half, int row, bool row_ok, size_t trow) {
-  // H is written IN PLACE: accumulator columns [16 ch, 16 ch + 16) of this thread's lane become the packed fp16 hi
-  // pairs (8 columns) followed by the lo pairs (8 columns) of the same 16 features, so the region that held the
-  // accumulators is the next layer's A operand and the region that held this layer's operand is free for its accumulators.
-  const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
-  const float* wdot = bias + nch * 16;  // DOT: the 1-output layer's weight row follows the bias
-  const float* adrow = ADDEND ? P.v.addend + (trow + row) * P.v.Hd : nullptr;
+__device__ __forceinline__ float rows_act_chunk(const float* bias, const float* wdot, const float* adrow, uint32_t tacc,
+                                                int ch, int nfeat, bool row_ok) {
+  float v[16], bz[16];
+  const int f0 = ch * 16;
   float dot = 0.f;
-  for (int ch = ch_begin + ((half ^ ch_begin) & 1); ch < ch_end; ch += 2) {   // this warp's chunks: ch = half (mod 2)
-    float v[16], bz[16];
-    const int f0 = ch * 16;
-    tmem_ld16(tacc + f0, v);
-    ld_uni16(bz, bias + f0);
-    if (ADDEND) {
-      float ad[16];
-      ld_row16(ad, adrow + f0, nfeat - f0, row_ok);
+  tmem_ld16(tacc + f0, v);
+  ld_uni16(bz, bias + f0);
+  if (ADDEND) {
+    float ad[16];
+    ld_row16(ad, adrow + f0, nfeat - f0, row_ok);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) bz[i] += ad[i];
-    }
-    tmem_ld_wait();
-    if (DOT) {
-      float w[16];
-      ld_uni16(w, wdot + f0);
+    for (int i = 0; i < 16; ++i) bz[i] += ad[i];
+  }
+  tmem_ld_wait();
+  if (DOT) {
+    float w[16];
+    ld_uni16(w, wdot + f0);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) dot = fmaf(w[i], act_bf<ACT>(v[i] + bz[i]), dot);
-    } else {
-      uint32_t hi[8], lo[8];
+    for (int i = 0; i < 16; ++i) dot = fmaf(w[i], act_bf<ACT>(v[i] + bz[i]), dot);
+  } else {
+    uint32_t hi[8], lo[8];
 #pragma unroll
-      for (int i = 0; i < 16; i += 2)
-        split2_f16(act_bf<ACT>(v[i] + bz[i]), act_bf<ACT>(v[i + 1] + bz[i + 1]), hi[i >> 1], lo[i >> 1]);
-      tmem_st8(tacc + f0, hi);
-      tmem_st8(tacc + f0 + 8, lo);
-    }
+    for (int i = 0; i < 16; i += 2)
+      split2_f16(act_bf<ACT>(v[i] + bz[i]), act_bf<ACT>(v[i + 1] + bz[i + 1]), hi[i >> 1], lo[i >> 1]);
+    tmem_st8(tacc + f0, hi);
+    tmem_st8(tacc + f0 + 8, lo);
   }
   return dot;
+}
+
+// In-kernel clock64 stamps (scripts/stage_clock.py) exist only in the profiling build (-DRB_STAGE_CLOCK): in the product
+// build they would cost registers in the epilogue warps, which run at the spill threshold.
+#ifdef RB_STAGE_CLOCK
+#define RB_STAMP(k) do { if (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5) V.dbg_clock[700 + s * 8 + (k)] = clock64(); } while (0)
+#define RB_STAMP_X(k) do { if (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5) V.dbg_clock[600 + s * 2 + (k)] = clock64(); } while (0)
+#define RB_STAGE_BEGIN() do { if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2] = clock64(); } while (0)
+#define RB_STAGE_END() do { if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2 + 1] = clock64(); } while (0)
+#else
+#define RB_STAMP(k) do { } while (0)
+#define RB_STAMP_X(k) do { } while (0)
+#define RB_STAGE_BEGIN() do { } while (0)
+#define RB_STAGE_END() do { } while (0)
+#endif
+
+// One chunk of GRU units (R_GRU).  accumulator: r at [0,W), z at [W,2W), i_n at [2W,3W), h_n at [3W,4W).
+// The stage is handed back as soon as the accumulators have left tensor memory, so the next chunk's MMAs run under the
+// gate math.  Holding all four gate accumulators (64 registers per thread) across that point spilled into every stage
+// of the kernel (hidden-layer epilogues 4.9k -> 10k cycles), so r * (W_hn b + b_hn) is folded before the hand-off:
+// 48 registers (t, z_pre, i_n) cross it.
+__device__ __forceinline__ void rows_gru_stage(uint8_t* x_hi, uint8_t* x_lo, uint8_t* scr, uint32_t scr_plane, uint32_t bar_xb,
+                                               int D, uint32_t tacc, const float* bias, float* bel_row,
+                                               uint32_t bar_handoff, uint32_t xb_parity, int r, int part, bool row_ok, int flags,
+                                               int W, int u0, int nu, long long* dbg = nullptr) {
+#ifdef RB_STAGE_CLOCK
+#define RB_GRU_STAMP(k) do { if (dbg) dbg[k] = clock64(); } while (0)
+#else
+#define RB_GRU_STAMP(k) do { } while (0)
+#endif
+  RB_GRU_STAMP(0);
+  const bool last_chunk = (flags & RF_LAST_CHUNK) != 0;
+  const int c = part * 16;         // this warp's 16-unit group of the chunk
+  const bool mine = c < nu;        // warp-uniform
+  const bool refresh = last_chunk && u0 > 0 && scr != nullptr;
+  if (refresh && threadIdx.x == 32 * kRowsEpiWarp0) {
+    // Every hh MMA has completed (this stage's accumulator barrier) and every earlier chunk's new units are in the scratch
+    // (their writers fenced towards the async proxy and have passed the epilogue barrier at this stage's start): pull belief
+    // k-groups [0, u0/8) into X while this chunk's gate math runs.
+    const uint32_t bytes = (uint32_t)(u0 >> 3) * kXLBO;
+    mbar_arrive_expect_tx(bar_xb, 2u * bytes);
+    bulk_g2s(smem_u32(x_hi), scr, bytes, bar_xb);
+    bulk_g2s(smem_u32(x_lo), scr + scr_plane, bytes, bar_xb);
+  }
+  float vt[16], vz[16], vi[16];   // r * (W_hn b + b_hn), z pre-activation, i_n pre-activation
+  if (mine) {
+    float vh[16];
+    tmem_ld16(tacc + c, vt);            // r
+    tmem_ld16(tacc + 3 * W + c, vh);    // h_n
+    tmem_ld_wait();
+    tmem_ld16(tacc + W + c, vz);        // in flight under the r-gate math
+    tmem_ld16(tacc + 2 * W + c, vi);
+    {
+      float bb[16];
+      ld_uni16(bb, bias + c);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) vt[i] = sigmoid_f(vt[i] + bb[i]);
+      ld_uni16(bb, bias + 3 * W + c);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) vt[i] = vt[i] * (vh[i] + bb[i]);
+    }
+    tmem_ld_wait();
+  }
+  // The accumulators have left tensor memory and X is untouched by this chunk: hand the stage back now, so that the
+  // next chunk's MMAs run under the rest of the gate math and the stores.
+  if (!last_chunk) {
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar_handoff);
+  }
+  RB_GRU_STAMP(1);
+  // Rest of the gate math in two halves of 8 units: new units go to beliefs[t] (fp32) and, split into fp16 hi/lo, either
+  // to the scratch image of X (earlier chunks) or straight into X (last chunk: every chunk's MMAs are done, the belief
+  // slot may be overwritten).
+  const bool to_x = last_chunk && (refresh || u0 == 0);
+  if (mine) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float bn[8];
+      const int kg = (u0 + c) / 8 + j;
+      {
+        float g[8];
+        const float4* pb = reinterpret_cast<const float4*>(bias + c + 8 * j);
+        const int Wq = W >> 2;   // W floats = Wq float4
+        float4 b0 = pb[2 * Wq], b1 = pb[2 * Wq + 1];
+        const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bn[i] = tanh_f(vi[8 * j + i] + bi[i] + vt[8 * j + i]);   // candidate n
+        b0 = pb[Wq]; b1 = pb[Wq + 1];
+        const float bzz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = sigmoid_f(vz[8 * j + i] + bzz[i]);                 // z
+        // b_prev = hi + lo from the belief slot of X (exact to 2^-22 relative).  The refresh overwrites k-groups below
+        // u0/8 only in the last chunk, whose own units lie above them.
+        if (kg * 8 < D) {
+          const uint4 h4 = *reinterpret_cast<const uint4*>(x_hi + (uint32_t)kg * kXLBO + (uint32_t)r * 16u);
+          const uint4 l4 = *reinterpret_cast<const uint4*>(x_lo + (uint32_t)kg * kXLBO + (uint32_t)r * 16u);
+          const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+            const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+            bn[2 * e] = bn[2 * e] + g[2 * e] * ((hf.x + lf.x) - bn[2 * e]);               // (1-z)*n + z*b_prev
+            bn[2 * e + 1] = bn[2 * e + 1] + g[2 * e + 1] * ((hf.y + lf.y) - bn[2 * e + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) bn[e] = bn[e] - g[e] * bn[e];
+        }
+      }
+      RB_GRU_STAMP(2 + 3 * j);
+      const int u = u0 + c + 8 * j;       // first unit of this half
+      const int nval = min(8, u0 + nu - u);
+      if (row_ok && nval > 0) {
+        float* dst = bel_row + u;
+        if (nval == 8 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          reinterpret_cast<float4*>(dst)[0] = make_float4(bn[0], bn[1], bn[2], bn[3]);
+          reinterpret_cast<float4*>(dst)[1] = make_float4(bn[4], bn[5], bn[6], bn[7]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < nval) dst[i] = bn[i];
+        }
+      }
+      RB_GRU_STAMP(3 + 3 * j);
+      if (to_x) {
+        if (u + 8 <= D) x_put8(x_hi, x_lo, r, u >> 3, bn);
+        else
+          for (int i = 0; u + i < D && i < 8; ++i) x_put(x_hi, x_lo, r, u + i, bn[i]);
+      } else if (!last_chunk && scr != nullptr) {
+        // scratch image of X: a warp writes 512 contiguous bytes per store
+        uint4 h, l;
+        split2_f16(bn[0], bn[1], h.x, l.x);
+        split2_f16(bn[2], bn[3], h.y, l.y);
+        split2_f16(bn[4], bn[5], h.z, l.z);
+        split2_f16(bn[6], bn[7], h.w, l.w);
+        const uint32_t o = (uint32_t)kg * kXLBO + (uint32_t)r * 16u;
+        *reinterpret_cast<uint4*>(scr + o) = h;
+        *reinterpret_cast<uint4*>(scr + scr_plane + o) = l;
+      }
+      RB_GRU_STAMP(4 + 3 * j);
+    }
+    if (!last_chunk && scr != nullptr)
+      asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy global writes -> visible to the bulk copy
+  }
+  RB_GRU_STAMP(8);
+  if (!last_chunk) return;
+  // ---- last chunk ----
+  if (to_x) {
+    if (refresh) mbar_wait(bar_xb, xb_parity);   // the earlier chunks' units have landed (async proxy, like the MMAs' reads)
+  } else {
+    // no scratch slot for this SM: a row's units were written by all four warps of the quadrant, so sync the epilogue
+    // warps, then re-read beliefs[t]
+    __threadfence_block();
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    const int nkg = D >> 3;  // full k-groups
+    for (int kg = part; kg < nkg; kg += kEpiParts) {
+      if (row_ok) {
+        float v[8];
+        const float4 lo4 = *reinterpret_cast<const float4*>(bel_row + kg * 8);
+        const float4 hi4 = *reinterpret_cast<const float4*>(bel_row + kg * 8 + 4);
+        v[0] = lo4.x; v[1] = lo4.y; v[2] = lo4.z; v[3] = lo4.w;
+        v[4] = hi4.x; v[5] = hi4.y; v[6] = hi4.z; v[7] = hi4.w;
+        x_put8(x_hi, x_lo, r, kg, v);
+      }
+    }
+    if (part == 0 && row_ok)
+      for (int k = nkg * 8; k < D; ++k) x_put(x_hi, x_lo, r, k, bel_row[k]);
+  }
 }
 
 __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid_constant__ RowsParams P) {
@@ -303,17 +526,17 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
   uint8_t* x_hi = ring + kRSlots * kRSlotBytes;
   const uint32_t x_bytes = (uint32_t)V.kx16 * 2u * kXLBO;
   uint8_t* x_lo = x_hi + x_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(x_lo + x_bytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kRSlots + 2);
-  float* scratch = reinterpret_cast<float*>(bars + 2 * kRSlots + 4);  // 128 floats: cross-warp partial sums
-  float* bias_s = scratch + 128 + 4;                                  // 2 x kBiasStage floats, 16-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_lo + x_bytes);        // 16 slots (128 bytes)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  float* scratch = reinterpret_cast<float*>(bars + 24);                // [kEpiParts][128] cross-warp partial sums (bars + 18: GruCtx)
+  float* bias_s = scratch + kEpiParts * 128;                           // 2 x kBiasStage floats, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * kRowsM;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kRSlots);
-  const uint32_t bar_acc = smem_u32(bars + 2 * kRSlots), bar_act = smem_u32(bars + 2 * kRSlots + 1);
-  const uint32_t bar_acc_a = smem_u32(bars + 2 * kRSlots + 3);   // first part of an RF_SPLIT stage
-  const uint32_t bar_acc_b = smem_u32(scratch + 128);            // second part of a three-way split
+  const uint32_t bar_acc = smem_u32(bars + 2 * kRSlots);         // a stage's accumulators are complete
+  const uint32_t bar_round = smem_u32(bars + 2 * kRSlots + 1);   // kRoundBars hand-off barriers: global round g -> slot g % 8
+  const uint32_t bar_xb = smem_u32(bars + 16);                   // belief refresh bulk copies have landed
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRSlots; ++i) {
@@ -321,9 +544,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       mbar_init(bar_empty + 8 * i, 1);
     }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_acc_a, 1);
-    mbar_init(bar_acc_b, 1);
-    mbar_init(bar_act, kRowsEpiThreads);
+    for (int i = 0; i < kRoundBars; ++i) mbar_init(bar_round + 8 * i, kRowsEpiWarps);   // one arrival per epilogue warp
+    mbar_init(bar_xb, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -335,10 +557,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Each role changes its register budget INSIDE its own branch (ptxas sizes a region by the
-  // setmaxnreg that dominates it; a shared if/else before the role split would cap everything at 80).
+  // Each role changes its register budget INSIDE its own branch (ptxas sizes a region by the setmaxnreg that dominates
+  // it).  640 threads launch with 96 registers each; warpgroup 0 keeps 32, the four epilogue warpgroups get 112.
+  // (576 threads x 112 registers without a hand-over does not launch: registers are granted per 4-warp group.  Stage
+  // bodies as non-inlined functions are sized for the 96-register launch bound, not for 112 — so everything is inlined
+  // and each stage is written to stay inside 112: see the R_GRU case.)
   if (warp == 0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     // ================================ weight loader ================================
     uint32_t slot = 0, phase = 0;
     for (int t = 0; t < V.n_steps; ++t) {
@@ -354,8 +579,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             mbar_wait(bar_empty + 8 * slot, phase ^ 1);
             if (elect_one()) {
               const uint32_t bytes = (uint32_t)nsl * slab_bytes;
-              mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
-              bulk_g2s(smem_u32(ring + slot * kRSlotBytes), src + (size_t)c0 * slab_bytes, bytes, bar_full + 8 * slot);
+#ifdef RB_STAGE_CLOCK
+              if (V.dbg_flags & 8) {   // profiling only: no weight traffic (results are garbage)
+                mbar_arrive(bar_full + 8 * slot);
+              } else
+#endif
+              {
+                mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
+                bulk_g2s(smem_u32(ring + slot * kRSlotBytes), src + (size_t)c0 * slab_bytes, bytes, bar_full + 8 * slot);
+              }
             }
             __syncwarp();
             if (++slot == kRSlots) { slot = 0; phase ^= 1; }
@@ -364,9 +596,18 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       }
     }
   } else if (warp == 1) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     // ================================ MMA issuer ================================
-    uint32_t slot = 0, phase = 0, act_phase = 0;
+    // Hand-off rounds are numbered globally (round 0 = the initial staging of X; then every stage's rounds in program
+    // order) and complete in order; `consumed` = how many this warp has observed.  Waits are lazy but never skip a round.
+    uint32_t slot = 0, phase = 0, consumed = 0, next_round = 1;
+    auto wait_round = [&](uint32_t idx) {
+      while (consumed <= idx) {
+        mbar_wait(bar_round + 8 * (consumed & (kRoundBars - 1)), (consumed / kRoundBars) & 1);
+        ++consumed;
+      }
+      tc_fence_after();
+    };
     const uint64_t x_desc = make_smem_desc(smem_u32(x_hi), kXLBO, 128);
     const uint64_t x_lo_delta = x_bytes >> 4;
     constexpr uint64_t kX_slab = (2u * kXLBO) >> 4;
@@ -376,10 +617,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         const int g0 = P.stages[s].gemm_begin, g1 = P.stages[s].gemm_end;
         const uint32_t tacc = tmem_base + ((P.stages[s].regs & 1) ? kAccCol : 0u);
         const uint32_t th = tmem_base + ((P.stages[s].regs & 2) ? kAccCol : 0u);
-        const bool split = (P.stages[s].flags & RF_SPLIT) != 0;
-        mbar_wait(bar_act, act_phase);
-        act_phase ^= 1;
-        tc_fence_after();
+        const uint32_t my_first = next_round;
+        next_round += P.stages[s].rounds;
+        const uint32_t prev_rounds = (t == 0 && s == 0) ? 1u : (uint32_t)P.stages[s ? s - 1 : P.n_rstages - 1].rounds;
+        const uint32_t prev_first = my_first - prev_rounds;
+        // X-reading GEMMs: the stage that last wrote their columns must have finished (default: the previous stage)
+        const uint32_t xb = P.stages[s].xback;
+        const uint32_t need_x = (my_first >= 1u + xb) ? my_first - 1u - xb : 0u;
         for (int g = g0; g < g1; ++g) {
           const RGemm gm = P.gemms[g];
           const uint32_t slab_bytes = (uint32_t)gm.slab_bytes16 * 16u;
@@ -390,13 +634,20 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
           const uint32_t w_lo = w_lbo * 2u;             // lo half follows the hi half
           uint32_t acc = gm.accumulate;
           uint32_t kk = gm.a_k16;
+          if (gm.a_src == 0) wait_round(need_x);
           for (int c0 = 0; c0 < gm.ksl; c0 += per_slot) {
             const int nsl = min(per_slot, (int)gm.ksl - c0);
+            // H-reading GEMMs trail the producing epilogue: k-slab k = features [16k, 16k+16) = chunk k = round k / 4
+            if (gm.a_src == 1) wait_round(prev_first + min((kk + (uint32_t)nsl - 1u) >> 2, prev_rounds - 1u));
             mbar_wait(bar_full + 8 * slot, phase);
             tc_fence_after();
             if (elect_one()) {
               uint32_t wa = ring_a + slot * kRSlotBytes;
-              for (int j = 0; j < nsl; ++j) {
+              int nsl_issue = nsl;
+#ifdef RB_STAGE_CLOCK
+              if (V.dbg_flags & 16) nsl_issue = 0;   // profiling only: no MMAs
+#endif
+              for (int j = 0; j < nsl_issue; ++j) {
                 const uint64_t b_hi = make_smem_desc(wa, w_lbo, 128);
                 const uint64_t b_lo = make_smem_desc(wa + w_lo, w_lbo, 128);
                 if (gm.a_src == 0) {
@@ -419,29 +670,28 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             kk += nsl;
             if (++slot == kRSlots) { slot = 0; phase ^= 1; }
           }
-          if (split && g + 1 < g1) {   // this part's accumulators are complete: its epilogue may start
-            if (elect_one()) umma_commit(g == g0 ? bar_acc_a : bar_acc_b);
-            __syncwarp();
-          }
         }
         if (elect_one()) umma_commit(bar_acc);
         __syncwarp();
       }
     }
-  } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");  // spare warps of warpgroup 0: the dec is warpgroup-wide
+  } else if (warp < kRowsEpiWarp0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");  // spare warps of warpgroup 0: the dec is warpgroup-wide
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // ================================ epilogue warps ================================
-    const int et = threadIdx.x - 128;      // 0..255
-    const int q = warp & 3;                // TMEM lane quadrant
-    const int half = (warp - 4) >> 2;      // which of the two warps of this quadrant
+    const int et = threadIdx.x - 32 * kRowsEpiWarp0;      // 0..511
+    const int q = warp & 3;                // TMEM lane quadrant (= the SM sub-partition this warp runs on)
+    const int part = (warp - kRowsEpiWarp0) >> 2;      // which of the four warps of this quadrant
     const int r = q * 32 + lane;           // row within the tile = TMEM lane
     const int row = row0 + r;
     const int N = V.N, D = V.D, S = V.S, A = V.A;
     const bool row_ok = row < N;
     const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16);
-    auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+    auto epi_sync = [] { asm volatile("bar.sync 1, 512;" ::: "memory"); };
+    uint32_t smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    uint8_t* const scr = (P.scr && (int)smid < P.scr_slots) ? P.scr + (size_t)smid * 2u * P.scr_plane : nullptr;
 
     // ---- init: zero X, then stage [belief | state*nonterm[0] | action[0]] ----
     {
@@ -452,7 +702,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       if (row_ok) {
         if (V.init_belief) {
           const float* b = V.init_belief + (size_t)row * D;
-          for (int kg = half; kg * 8 < D; kg += 2) {
+          for (int kg = part; kg * 8 < D; kg += kEpiParts) {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = (kg * 8 + i < D) ? b[kg * 8 + i] : 0.f;
@@ -461,51 +711,52 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               for (int i = 0; kg * 8 + i < D; ++i) x_put(x_hi, x_lo, r, kg * 8 + i, v[i]);
           }
         }
-        if (half == 0 && V.init_state) {
+        if (part == 0 && V.init_state) {
           const float m = V.nonterm ? V.nonterm[row] : 1.f;
           for (int j = 0; j < S; ++j) x_put(x_hi, x_lo, r, D + j, V.init_state[(size_t)row * S + j] * m);
         }
-        if (half == 1 && V.actions_in)
+        if (part == 1 && V.actions_in)
           for (int j = 0; j < A; ++j) x_put(x_hi, x_lo, r, D + S + j, V.actions_in[(size_t)row * A + j]);
       }
       fence_proxy_async_smem();
-      mbar_arrive(bar_act);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_round);   // global round 0
     }
+    uint32_t ground = 1;   // next global hand-off round this warp signals
 
     // With ~220 KB of shared memory in use there is next to no L1: every global load is an L2
     // round trip.  So while the MMAs of a stage run, the epilogue warps already fetch what that
-    // stage's epilogue will need: its biases into a smem staging buffer, its per-row inputs
-    // (noise, previous belief) into registers.
-    float pre[16];  // per-row inputs (noise) of the upcoming stage; the GRU reads b_prev back from X
+    // stage's epilogue will need: its biases into a smem staging buffer, its per-row noise (this warp's 8 columns)
+    // into registers.
+    float pre[8];
     float pre_nt = 1.f;
     auto prefetch = [&](int t, int s, int buf) {
       const RStage& st = P.stages[s];
       const size_t trow = (size_t)t * N;
       float* dstb = bias_s + buf * kBiasStage;
-      for (int i = et; i < st.bias_n; i += kRowsEpiThreads) dstb[i] = __ldg(V.bias + st.bias_off + i);
+      for (int i = et; i < st.bias_n; i += kRowsEpiThreads) cp_async4(smem_u32(dstb + i), V.bias + st.bias_off + i);
       switch (st.epi) {
         case R_PRIOR:
         case R_POST: {
-          {  // the two warps of a quadrant take one 16-state chunk each
-            const int c = half * 16;
-            const float* eps = (st.epi == R_POST ? V.eps_post : V.eps_prior) + (trow + row) * S + c;
-            ld_row16_v2(pre, eps, S - c, row_ok && c < S);
-            pre_nt = 1.f;
-            if ((st.flags & SF_WRITES_STATE) && V.nonterm && (t + 1) < V.n_steps && row_ok) pre_nt = __ldg(V.nonterm + trow + N + row);
-          }
+          const int c = part * 8;   // the four warps of a quadrant take one 8-state group each
+          const float* eps = (st.epi == R_POST ? V.eps_post : V.eps_prior) + (trow + row) * S + c;
+          ld_row8_v2<true>(pre, eps, S - c, row_ok && c < S);
+          pre_nt = 1.f;
+          if ((st.flags & SF_WRITES_STATE) && V.nonterm && (t + 1) < V.n_steps && row_ok) pre_nt = __ldg(V.nonterm + trow + N + row);
         } break;
         case R_ACTION: {
-          if (half == 0) {
-            const float* eps = V.eps_action + (trow + row) * A;
+          const int c = part * 8;
+          if (c < A) {
+            const float* eps = V.eps_action + (trow + row) * A + c;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) pre[i] = (row_ok && i < A) ? __ldg(eps + i) : 0.f;
+            for (int i = 0; i < 8; ++i) pre[i] = (row_ok && c + i < A) ? __ldg(eps + i) : 0.f;
           }
         } break;
         default: break;
       }
     };
 
-    uint32_t acc_phase = 0, acc_a_phase = 0, acc_b_phase = 0;
+    uint32_t acc_phase = 0;
     int buf = 0;
     {  // stage 0 of step 0 never needs per-row inputs ahead of time in either program; stage its biases
       const RStage& st0 = P.stages[0];
@@ -519,275 +770,127 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         const RStage& st = P.stages[s];
         const float* bias = bias_s + buf * kBiasStage;
         const uint32_t tacc = tl + ((st.regs & 1) ? kAccCol : 0u);
-        const bool split = (st.flags & RF_SPLIT) != 0;
-        if (split) {
-          mbar_wait(bar_acc_a, acc_a_phase);
-          acc_a_phase ^= 1;
-        } else {
-          mbar_wait(bar_acc, acc_phase);
-          acc_phase ^= 1;
-        }
+        RB_STAMP(0);
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1;
         tc_fence_after();
-        epi_sync();  // staged biases visible to every epilogue warp
-        if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2] = clock64();
-        // The proxy fence before the hand-off also waits for this thread's outstanding GLOBAL stores, and the
-        // output rows are `feature`-strided (32 sectors per store instruction).  Stages with outputs therefore
-        // write their smem/TMEM operands first, hand the stage back, and only then store the outputs, which
-        // drain while the next stage's MMAs run.
-        bool handed = false, prefetched = false;
-        auto handoff = [&] {
-          fence_proxy_async_smem();
+        RB_STAMP(1);
+        cp_async_wait_all();   // this thread's share of the staged biases has landed ...
+        epi_sync();            // ... and everybody else's
+        RB_STAMP(2);
+        RB_STAGE_BEGIN();
+        // One hand-off round: this warp's TMEM / shared-memory writes of the round are done.  The proxy fence also waits
+        // for the thread's outstanding GLOBAL stores, and the output rows are `feature`-strided (32 sectors per store
+        // instruction) — stages with outputs therefore write their smem/TMEM operands first, hand the stage back, and only
+        // then store the outputs, which drain while the next stage's MMAs run.
+        bool handed = false;
+        auto signal_round = [&](bool wrote_smem) {
+          if (wrote_smem) fence_proxy_async_smem();
           tc_fence_before();
-          if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2 + 1] = clock64();
-          mbar_arrive(bar_act);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_round + 8 * (ground & (kRoundBars - 1)));
+          ++ground;
+        };
+        auto handoff = [&] {
+          RB_STAMP(3);
+          RB_STAGE_END();
+          signal_round(true);
           handed = true;
         };
 
         switch (st.epi) {
           case R_ACT_H: {
+            // rounds of four chunks (one per warp of the quadrant); the next layer's MMAs start behind each round
             const bool elu = st.act == ACT_ELU, addend = (st.flags & SF_ADDEND) != 0;
-            const int nch = (st.nfeat + 15) >> 4;
-            auto part = [&](int c0, int c1) {
-              if (addend) {
-                if (elu) rows_act_h<ACT_ELU, false, true>(P, st, bias, tacc, c0, c1, half, row, row_ok, trow);
-                else rows_act_h<ACT_RELU, false, true>(P, st, bias, tacc, c0, c1, half, row, row_ok, trow);
-              } else {
-                if (elu) rows_act_h<ACT_ELU, false, false>(P, st, bias, tacc, c0, c1, half, row, row_ok, trow);
-                else rows_act_h<ACT_RELU, false, false>(P, st, bias, tacc, c0, c1, half, row, row_ok, trow);
+            const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
+            const float* adrow = addend ? V.addend + (trow + row) * V.Hd : nullptr;
+            for (int ch0 = 0; ch0 < nch; ch0 += kEpiParts) {
+              const int ch = ch0 + part;
+              if (ch < nch) {
+                if (addend) {
+                  if (elu) rows_act_chunk<ACT_ELU, false, true>(bias, nullptr, adrow, tacc, ch, nfeat, row_ok);
+                  else rows_act_chunk<ACT_RELU, false, true>(bias, nullptr, adrow, tacc, ch, nfeat, row_ok);
+                } else {
+                  if (elu) rows_act_chunk<ACT_ELU, false, false>(bias, nullptr, nullptr, tacc, ch, nfeat, row_ok);
+                  else rows_act_chunk<ACT_RELU, false, false>(bias, nullptr, nullptr, tacc, ch, nfeat, row_ok);
+                }
+                tmem_st_wait();
               }
-            };
-            if (split) {
-              part(0, st.width);               // under the next part's MMAs
-              int c = st.width;
-              if (st.unit0) {
-                mbar_wait(bar_acc_b, acc_b_phase);
-                acc_b_phase ^= 1;
-                tc_fence_after();
-                part(c, st.unit0);
-                c = st.unit0;
+              if (ch0 + kEpiParts >= nch) {
+                RB_STAMP(3);
+          RB_STAGE_END();
               }
-              mbar_wait(bar_acc, acc_phase);
-              acc_phase ^= 1;
-              tc_fence_after();
-              part(c, nch);
-            } else {
-              part(0, nch);
+              signal_round(false);
             }
-            tmem_st_wait();
+            handed = true;
           } break;
 
           case R_ACT_DOT: {
-            const int nch = (st.nfeat + 15) >> 4;
+            const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
             const bool elu = st.act == ACT_ELU;
-            float dot = elu ? rows_act_h<ACT_ELU, true, false>(P, st, bias, tacc, 0, split ? (int)st.width : nch, half, row, row_ok, trow)
-                            : rows_act_h<ACT_RELU, true, false>(P, st, bias, tacc, 0, split ? (int)st.width : nch, half, row, row_ok, trow);
-            if (split) {
-              int c = st.width;
-              if (st.unit0) {
-                mbar_wait(bar_acc_b, acc_b_phase);
-                acc_b_phase ^= 1;
-                tc_fence_after();
-                dot += elu ? rows_act_h<ACT_ELU, true, false>(P, st, bias, tacc, c, st.unit0, half, row, row_ok, trow)
-                           : rows_act_h<ACT_RELU, true, false>(P, st, bias, tacc, c, st.unit0, half, row, row_ok, trow);
-                c = st.unit0;
-              }
-              mbar_wait(bar_acc, acc_phase);
-              acc_phase ^= 1;
-              tc_fence_after();
-              dot += elu ? rows_act_h<ACT_ELU, true, false>(P, st, bias, tacc, c, nch, half, row, row_ok, trow)
-                         : rows_act_h<ACT_RELU, true, false>(P, st, bias, tacc, c, nch, half, row, row_ok, trow);
-            }
-            if (half == 1) scratch[r] = dot;
+            const float* wdot = bias + nch * 16;   // the 1-output layer's weight row follows the bias
+            float dot = 0.f;
+            for (int ch = part; ch < nch; ch += kEpiParts)
+              dot += elu ? rows_act_chunk<ACT_ELU, true, false>(bias, wdot, nullptr, tacc, ch, nfeat, row_ok)
+                         : rows_act_chunk<ACT_RELU, true, false>(bias, wdot, nullptr, tacc, ch, nfeat, row_ok);
+            handoff();   // the accumulators are consumed; nothing in X / H changes
+            if (part) scratch[part * 128 + r] = dot;
             epi_sync();
-            if (half == 0 && row_ok) {
-              const int nch = (st.nfeat + 15) >> 4;
+            if (part == 0 && row_ok) {
               float* dst = (st.flags & SF_SCALAR_VALUE) ? V.values : V.rewards;
-              dst[trow + row] = dot + scratch[r] + bias[2 * nch * 16];
+              dst[trow + row] = ((dot + scratch[128 + r]) + (scratch[256 + r] + scratch[384 + r])) + bias[2 * nch * 16];
             }
           } break;
 
           case R_GRU: {
-            // accumulator: r at [0,W), z at [W,2W), i_n at [2W,3W), h_n at [3W,4W), W = st.width
-            const int W = st.width, u0 = st.unit0, nu = st.nfeat;  // nu valid units in this chunk
             const bool last_chunk = (st.flags & RF_LAST_CHUNK) != 0;
-            float bnew[2][16];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const int c = (half + 2 * k) * 16;
-              if (c < nu) {
-                float vr[16], vz[16], vi[16], vh[16], bb[16];
-                tmem_ld16(tacc + c, vr);
-                tmem_ld16(tacc + W + c, vz);
-                tmem_ld16(tacc + 2 * W + c, vi);
-                tmem_ld16(tacc + 3 * W + c, vh);
-                tmem_ld_wait();
-                ld_uni16(bb, bias + c);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) vr[i] = sigmoid_f(vr[i] + bb[i]);
-                ld_uni16(bb, bias + W + c);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) vz[i] = sigmoid_f(vz[i] + bb[i]);
-                ld_uni16(bb, bias + 3 * W + c);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) vh[i] = vr[i] * (vh[i] + bb[i]);
-                ld_uni16(bb, bias + 2 * W + c);
-                // b_prev = hi + lo from the belief slot of X (exact to 2^-22 relative; this thread's units, which the
-                // refresh below overwrites only after every warp has passed the epi_sync that follows the last chunk)
-                float bp[16];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  const int kg = (u0 + c) / 8 + j;
-                  if (kg * 8 < D) {
-                    const uint4 h4 = *reinterpret_cast<const uint4*>(x_hi + (uint32_t)kg * kXLBO + (uint32_t)r * 16u);
-                    const uint4 l4 = *reinterpret_cast<const uint4*>(x_lo + (uint32_t)kg * kXLBO + (uint32_t)r * 16u);
-                    const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
-                      const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
-                      bp[8 * j + 2 * e] = hf.x + lf.x;
-                      bp[8 * j + 2 * e + 1] = hf.y + lf.y;
-                    }
-                  } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) bp[8 * j + e] = 0.f;
-                  }
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float nn = tanh_f(vi[i] + bb[i] + vh[i]);
-                  bnew[k][i] = nn + vz[i] * (bp[i] - nn);   // (1-z)*n + z*b_prev
-                }
-              }
+            if (!last_chunk) {
+              RB_STAMP(3);
+          RB_STAGE_END();
             }
-            if (!last_chunk) handoff();  // X is untouched by this chunk: the accumulators are all the issuer waits for
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const int c = (half + 2 * k) * 16;
-              if (c < nu && row_ok) st_row16(V.beliefs + (trow + row) * D + u0 + c, bnew[k], min(16, nu - c));
-            }
-            if (st.flags & RF_PARK) {
-              // The last chunk is narrow: its MMAs only touch accumulator columns [0, 4 W_last).  Park this row's new
-              // belief units of this and the earlier chunks (re-read: this thread's own stores) behind them as packed
-              // fp16 hi/lo — 16 columns per 16-unit group, groups g = half (mod 2) are this thread's — while the last
-              // chunk's MMAs run.  The sibling warp shares these TMEM lanes: wait until it has drained its accumulators.
-              // (Re-reading both earlier chunks in one batch, or ahead of this chunk's stores, was tried: the 64 extra
-              // live registers spill into the hidden-layer epilogues, 160.7k -> 184k cycles per step.)
-              epi_sync();
-              const uint32_t tpark = tacc + 4u * P.stages[s + 1].width;
-              const int nprev = u0 >> 6;
-              const float* brow = V.beliefs + (trow + row) * D;
-              for (int pc = 0; pc <= nprev; ++pc) {
-                float pv[2][16];
-                if (pc < nprev) {
-#pragma unroll
-                  for (int k = 0; k < 2; ++k) ld_row16(pv[k], brow + 64 * pc + (half + 2 * k) * 16, 16, row_ok);
-                } else {
-#pragma unroll
-                  for (int k = 0; k < 2; ++k)
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pv[k][i] = bnew[k][i];
-                }
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                  uint32_t hl[16];
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) split2_f16(pv[k][2 * i], pv[k][2 * i + 1], hl[i], hl[8 + i]);
-                  tmem_st16f(tpark + 16u * (uint32_t)(4 * pc + half + 2 * k), reinterpret_cast<const float*>(hl));
-                }
-              }
-              tmem_st_wait();
-            }
-            if ((st.flags & RF_LAST_CHUNK) && (st.flags & RF_UNPARK)) {
-              // every chunk's MMAs are done: the belief slot of X may be overwritten.  Earlier chunks: from the parked
-              // columns (this thread's own groups — the same ones whose old values it read for the blend, so no
-              // cross-thread hazard and no barrier); this chunk: from registers.
-              const uint32_t tpark = tacc + 4u * W;
-              const int ngroups = u0 >> 4;
-              for (int g = half; g < ngroups; g += 2) {
-                uint32_t hl[16];
-                tmem_ld16(tpark + 16u * g, reinterpret_cast<float*>(hl));
-                tmem_ld_wait();
-                const uint32_t o = (uint32_t)(2 * g) * kXLBO + (uint32_t)r * 16u;
-                *reinterpret_cast<uint4*>(x_hi + o) = make_uint4(hl[0], hl[1], hl[2], hl[3]);
-                *reinterpret_cast<uint4*>(x_hi + o + kXLBO) = make_uint4(hl[4], hl[5], hl[6], hl[7]);
-                *reinterpret_cast<uint4*>(x_lo + o) = make_uint4(hl[8], hl[9], hl[10], hl[11]);
-                *reinterpret_cast<uint4*>(x_lo + o + kXLBO) = make_uint4(hl[12], hl[13], hl[14], hl[15]);
-              }
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const int c = (half + 2 * k) * 16;
-                if (c < nu) {
-#pragma unroll
-                  for (int j = 0; j < 2; ++j) {
-                    const int u = u0 + c + 8 * j;
-                    if (u + 8 <= D) x_put8(x_hi, x_lo, r, u >> 3, bnew[k] + 8 * j);
-                    else
-                      for (int i = 0; u + i < D && i < 8; ++i) x_put(x_hi, x_lo, r, u + i, bnew[k][8 * j + i]);
-                  }
-                }
-              }
-            } else if (st.flags & RF_LAST_CHUNK) {
-              // every chunk's MMAs are done: now the belief slot of X may be overwritten.  Rows were
-              // written by both warps of the quadrant, so sync the epilogue warps first; the loads
-              // are issued in batches so the L2 latency is paid once per batch, not once per k-group.
-              __threadfence_block();
-              epi_sync();
-              const float* b = V.beliefs + (trow + row) * D;
-              const int nkg = D >> 3;  // full k-groups
-              for (int kg0 = half; kg0 < nkg; kg0 += 8) {
-                float v[4][8];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int kg = kg0 + 2 * j;
-                  if (kg < nkg && row_ok) {
-                    const float4 lo4 = *reinterpret_cast<const float4*>(b + kg * 8);
-                    const float4 hi4 = *reinterpret_cast<const float4*>(b + kg * 8 + 4);
-                    v[j][0] = lo4.x; v[j][1] = lo4.y; v[j][2] = lo4.z; v[j][3] = lo4.w;
-                    v[j][4] = hi4.x; v[j][5] = hi4.y; v[j][6] = hi4.z; v[j][7] = hi4.w;
-                  }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int kg = kg0 + 2 * j;
-                  if (kg < nkg && row_ok) x_put8(x_hi, x_lo, r, kg, v[j]);
-                }
-              }
-              if (half == 0 && row_ok)
-                for (int k = nkg * 8; k < D; ++k) x_put(x_hi, x_lo, r, k, b[k]);
+            rows_gru_stage(x_hi, x_lo, scr, P.scr_plane, bar_xb, D, tacc, bias, V.beliefs + (trow + row) * D,
+                           bar_round + 8 * (ground & (kRoundBars - 1)), (uint32_t)(t & 1), r, part, row_ok, st.flags, st.width,
+                           st.unit0, st.nfeat
+#ifdef RB_STAGE_CLOCK
+                           , (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5 && st.unit0 == 64) ? V.dbg_clock + 860 : nullptr
+#endif
+                           );
+            if (!last_chunk) {   // handed back right after the accumulators were read
+              ++ground;
+              handed = true;
             }
           } break;
 
           case R_PRIOR:
           case R_POST: {
-            // S <= 32 here (wider states run on the vm.cuh kernel): warp `half` of the quadrant owns states
-            // [16 half, 16 half + 16) of its row — mean at acc [0,W), raw std at [W,2W)
+            // S <= 32 here (wider states run on the vm.cuh kernel): warp `part` of the quadrant owns states
+            // [8 part, 8 part + 8) of its row — mean at acc [0,W), raw std at [W,2W)
             const bool post = st.epi == R_POST;
             const int W = st.width;
-            const int c = half * 16;
-            const int nv = min(16, S - c);
+            const int c = part * 8;
+            const int nv = max(0, min(8, S - c));   // warp-uniform
             const bool want_kl = post && V.kl != nullptr;
             float kl = 0.f;
-            float vm[16], vs[16], smp[16];
+            float vm[8], vs[8], smp[8];
             if (nv > 0) {
-              float pm[16], psd[16];
+              float pm[8], psd[8];
               const size_t o = (trow + row) * S + c;
               if (want_kl) {
-                ld_row16_v2(pm, V.prior_m + o, nv, row_ok);
-                ld_row16_v2(psd, V.prior_sd + o, nv, row_ok);
+                ld_row8_v2<false>(pm, V.prior_m + o, nv, row_ok);
+                ld_row8_v2<false>(psd, V.prior_sd + o, nv, row_ok);
               }
-              tmem_ld16(tacc + c, vm);
-              tmem_ld16(tacc + W + c, vs);
+              tmem_ld8(tacc + c, vm);
+              tmem_ld8(tacc + W + c, vs);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
+              for (int i = 0; i < 8; ++i) {
                 vm[i] += bias[c + i];
                 vs[i] = softplus_f(vs[i] + bias[W + c + i]) + V.min_std;
                 smp[i] = vm[i] + vs[i] * pre[i];
               }
               if (want_kl) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 8; ++i) {
                   if (i < nv && row_ok) {
                     const float inv = rcp_f(psd[i]);   // MUFU forms: ~1e-7 relative, far inside the KL tolerance
                     const float ratio = vs[i] * inv, vr = ratio * ratio;
@@ -799,37 +902,35 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               if (st.flags & SF_WRITES_STATE) {
                 if (((D + c) & 1) == 0) {
 #pragma unroll
-                  for (int i = 0; i < 16; i += 2) {
+                  for (int i = 0; i < 8; i += 2) {
                     if (i + 1 < nv) x_put2(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt, smp[i + 1] * pre_nt);
                     else if (i < nv) x_put(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt);
                   }
                 } else {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i)
+                  for (int i = 0; i < 8; ++i)
                     if (i < nv) x_put(x_hi, x_lo, r, D + c + i, smp[i] * pre_nt);
                 }
               }
             }
-            if (half == 1) {
-              if ((st.flags & SF_LOADS_ACTION) && has_next && row_ok)
-                for (int j = 0; j < A; ++j) x_put(x_hi, x_lo, r, D + S + j, __ldg(V.actions_in + (trow + N + row) * A + j));
-              if (want_kl) scratch[r] = kl;
-            }
+            if (part == kEpiParts - 1 && (st.flags & SF_LOADS_ACTION) && has_next && row_ok)
+              for (int j = 0; j < A; ++j) x_put(x_hi, x_lo, r, D + S + j, __ldg(V.actions_in + (trow + N + row) * A + j));
+            if (want_kl && part) scratch[part * 128 + r] = kl;
             handoff();
-            // Output rows are S floats apart, so a store with lane = row touches 32 cache lines per instruction and the
-            // 24 of them kept the LSU busy for ~9k cycles.  Transpose through tensor memory instead: park the three
-            // 32 x 16 blocks (lane = row) in columns nobody uses right now and read them back in the 16x256b fragment
-            // layout, where four neighbouring threads hold 8 consecutive floats of a row — 8 rows x 32 bytes per store.
+            // Output rows are S floats apart, so a store with lane = row touches 32 cache lines per instruction and
+            // kept the LSU busy for ~9k cycles.  Transpose through tensor memory instead: park the three 32 x 8 blocks
+            // (lane = row) in columns nobody uses right now and read them back in the 16x256b fragment layout, where
+            // four neighbouring threads hold 8 consecutive floats of a row — 8 rows x 32 bytes per store instruction.
             // Free columns: the region the NEXT stage does not accumulate into (this stage's dead H operand or its own
             // consumed accumulators, hence the offset past the 2W accumulator columns), provided the next stage reads X.
             const RStage& ns = P.stages[(s + 1 == P.n_rstages) ? 0 : s + 1];
             bool ns_reads_h = false;
             for (int g = ns.gemm_begin; g < ns.gemm_end; ++g) ns_reads_h |= P.gemms[g].a_src == 1;
             if (nv > 0 && (S & 1) == 0 && !ns_reads_h && 2 * W <= 128) {
-              const uint32_t tsc = tl + ((ns.regs & 1) ? 0u : kAccCol) + 128u + (uint32_t)(half * 64);
-              tmem_st16f(tsc, smp);
-              tmem_st16f(tsc + 16, vm);
-              tmem_st16f(tsc + 32, vs);
+              const uint32_t tsc = tl + ((ns.regs & 1) ? 0u : kAccCol) + 128u + (uint32_t)(part * 32);
+              tmem_st8f(tsc, smp);
+              tmem_st8f(tsc + 8, vm);
+              tmem_st8f(tsc + 16, vs);
               tmem_st_wait();
               float* const outs[3] = {post ? V.post_s : V.prior_s, post ? V.post_m : V.prior_m, post ? V.post_sd : V.prior_sd};
               const int cq = 2 * (lane & 3);
@@ -837,59 +938,63 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               for (int a = 0; a < 3; ++a) {
 #pragma unroll
                 for (int hb = 0; hb < 2; ++hb) {
-                  float tq[8];
-                  tmem_ld_16x256b_x2(tsc + ((uint32_t)(16 * hb) << 16) + 16 * a, tq);
+                  float tq[4];
+                  tmem_ld_16x256b_x1(tsc + ((uint32_t)(16 * hb) << 16) + 8 * a, tq);
                   tmem_ld_wait();
 #pragma unroll
                   for (int rb = 0; rb < 2; ++rb) {
                     const int rr = row0 + q * 32 + 16 * hb + 8 * rb + (lane >> 2);
-                    if (rr < N) {
-                      float* dst = outs[a] + (trow + rr) * S + c + cq;
-#pragma unroll
-                      for (int g = 0; g < 2; ++g)
-                        if (cq + 8 * g + 1 < nv)
-                          *reinterpret_cast<float2*>(dst + 8 * g) = make_float2(tq[4 * g + 2 * rb], tq[4 * g + 2 * rb + 1]);
-                    }
+                    if (rr < N && cq + 1 < nv)
+                      *reinterpret_cast<float2*>(outs[a] + (trow + rr) * S + c + cq) = make_float2(tq[2 * rb], tq[2 * rb + 1]);
                   }
                 }
               }
             } else if (nv > 0 && row_ok) {   // odd state sizes (rows not 8-byte aligned) and unusual programs
               const size_t o = (trow + row) * S + c;
-              st_row16_v2((post ? V.post_s : V.prior_s) + o, smp, nv);
-              st_row16_v2((post ? V.post_m : V.prior_m) + o, vm, nv);
-              st_row16_v2((post ? V.post_sd : V.prior_sd) + o, vs, nv);
+              float* const outs[3] = {post ? V.post_s : V.prior_s, post ? V.post_m : V.prior_m, post ? V.post_sd : V.prior_sd};
+              const float* const vals[3] = {smp, vm, vs};
+#pragma unroll
+              for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (i < nv) outs[a][o + i] = vals[a][i];
             }
             if (want_kl) {   // uniform across the CTA: V.kl and the stage kind are kernel-wide
               epi_sync();
-              if (half == 0 && row_ok) V.kl[trow + row] = kl + scratch[r];
+              if (part == 0 && row_ok) V.kl[trow + row] = (kl + scratch[128 + r]) + (scratch[256 + r] + scratch[384 + r]);
             }
           } break;
 
           case R_ACTION: {
-            if (half == 0) {   // A <= 16 here
+            const int c = part * 8;   // A <= 16 here: warps 0 and 1 of the quadrant take 8 action dims each
+            if (c < A) {
               const int W = st.width;
               const float inv_ms = 1.f / V.a_mean_scale;
-              float vm[16], vs[16];
-              const size_t o = (trow + row) * A;
-              tmem_ld16(tacc, vm);
-              tmem_ld16(tacc + W, vs);
+              float vm[8], vs[8];
+              const size_t o = (trow + row) * A + c;
+              tmem_ld8(tacc + c, vm);
+              tmem_ld8(tacc + W + c, vs);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float mean = V.a_mean_scale * tanh_f((vm[i] + bias[i]) * inv_ms);
-                const float sd = softplus_f(vs[i] + bias[W + i] + V.a_init_std) + V.a_min_std;
+              for (int i = 0; i < 8; ++i) {
+                const float mean = V.a_mean_scale * tanh_f((vm[i] + bias[c + i]) * inv_ms);
+                const float sd = softplus_f(vs[i] + bias[W + c + i] + V.a_init_std) + V.a_min_std;
                 vm[i] = tanh_f(mean + sd * pre[i]);
               }
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < A) x_put(x_hi, x_lo, r, D + S + i, vm[i]);
+              for (int i = 0; i < 8; ++i)
+                if (c + i < A) x_put(x_hi, x_lo, r, D + S + c + i, vm[i]);
               handoff();
-              if (row_ok && V.actions_out) st_row16(V.actions_out + o, vm, A);
+              if (row_ok && V.actions_out) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (c + i < A) V.actions_out[o + i] = vm[i];
+              }
             }
           } break;
 
           case R_SCALAR: {
-            if (half == 0) {
+            if (part == 0) {
               float v[16];
               tmem_ld16(tacc, v);
               tmem_ld_wait();
@@ -901,19 +1006,19 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         }
 
         if (!handed) handoff();
-        if (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5) V.dbg_clock[600 + s * 2] = clock64();
+        RB_STAMP_X(0);
         // fetch for the next stage while its MMAs run
         buf ^= 1;
         {
           const bool wrap = (s + 1 == P.n_rstages);
-          if (!prefetched && (!wrap || has_next)) prefetch(wrap ? t + 1 : t, wrap ? 0 : s + 1, buf);
+          if (!wrap || has_next) prefetch(wrap ? t + 1 : t, wrap ? 0 : s + 1, buf);
         }
-        if (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5) V.dbg_clock[600 + s * 2 + 1] = clock64();
+        RB_STAMP_X(1);
       }
     }
 
-    // ---- lambda-return: each row's rewards/values were written by this thread (half 0) ----
-    if (half == 0 && row_ok && V.returns && V.rewards && V.values && V.n_steps >= 2) {
+    // ---- lambda-return: each row's rewards/values were written by this thread (part 0) ----
+    if (part == 0 && row_ok && V.returns && V.rewards && V.values && V.n_steps >= 2) {
       const int T = V.n_steps;
       const float g = V.gamma, lam = V.lambda;
       float last = V.values[(size_t)(T - 1) * N + row];

@@ -39,7 +39,8 @@ class SequenceReplayBuffer:
         self.actions[self.pos] = np.array(act).copy()
         self.rewards[self.pos] = np.array(rew).copy()
         self.dones[self.pos] = np.array(done).copy()
-        self._dirty.append(self.pos)
+        if self._dev is not None:   # without a device mirror the first sync uploads everything anyway
+            self._dirty.append(self.pos)
         self.pos += 1
         if self.pos == self.capacity:
             self.pos = 0

@@ -273,7 +273,7 @@ class Agent:
         if w != 1.0:  # kl_loss / beta_loss / beta carry constants: weight them too so that the SUM over ranks is global
             logs = {k: v * w for k, v in logs.items()}
         self.logs.update(logs)
-        if self.algo == "dreamer":  # dreamer.py:297-301 (RePo's train_dynamics override drops both heads)
+        if self.algo in ("dreamer", "repo"):  # dreamer.py:297-301 and repo.py:106-110 (TIA's train_dynamics has neither head)
             if c.disag_model:
                 self.train_disag(beliefs, posterior_states, actions, nonterms, step=step)
             if c.inv_dynamics:

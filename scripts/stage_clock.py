@@ -3,6 +3,8 @@ import ctypes as C
 import os
 import sys
 
+os.environ["REPO_B200_PROFILING"] = "1"   # the library variant built with -DRB_STAGE_CLOCK (python -m repo_b200.build --profiling)
+
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,13 +25,15 @@ _lib.lib().repo_b200_debug_flags(int(os.environ.get('RB_DBG', '0')))
 ops.imagine_fwd(*a, row_tile=128)
 torch.cuda.synchronize()
 NS = 32
-buf = torch.zeros(14 * NS * 2, dtype=torch.int64, device=dev)
+buf = torch.zeros(14 * NS * 2 + 256, dtype=torch.int64, device=dev)
 _lib.lib().repo_b200_debug_clock(C.c_void_p(buf.data_ptr()))
 ops.imagine_fwd(*a, row_tile=128)
 torch.cuda.synchronize()
 _lib.lib().repo_b200_debug_clock(None)
 b = buf.cpu().numpy()
+chunk = b[860:880].copy()
 extra = b[600:600 + 64].copy()
+fine = b[700:700 + 8 * NS // 2 + 64].copy() if len(b) > 700 else None
 b[600:] = 0
 nz = (b != 0).sum() // (14 * 2)
 b = b[: 14 * nz * 2].reshape(14, nz, 2)
@@ -45,3 +49,15 @@ for s in range(nz):
     tot_mma += mma
     print(f"{names[s] if s < len(names) else s:>4}: mma_phase {mma:6d} cyc   epilogue {epi:6d} cyc   handoff->stage end {extra[2 * s] - b[t, s, 1]:6d}   prefetch {extra[2 * s + 1] - extra[2 * s]:6d}")
 print("step total:", b[t + 1, 0, 0] - b[t, 0, 0], "cycles; mma", tot_mma, "epi", tot_epi)
+
+if fine is not None and fine.any():
+    print("# fine stamps of warp 4 (step 5): wait_acc = stage entry -> accumulators ready; sync = bias-staging barrier; body = epilogue math;")
+    print("# st_wait = tcgen05.wait::st; proxy_fence = fence.proxy.async")
+    for s in range(nz):
+        f = fine[8 * s: 8 * s + 8]
+        d = lambda a, c: int(f[c] - f[a]) if f[a] and f[c] else -1
+        print(f"{names[s] if s < len(names) else s:>4}: wait_acc {d(0, 1):6d}  sync {d(1, 2):5d}  body {d(2, 3):6d}  (act_h loop {d(2, 5):6d} st_wait {d(5, 6):5d})  proxy_fence {d(3, 4):5d}")
+
+if chunk.any():
+    c = chunk[chunk != 0]
+    print("# G1, warp 4: entry, handed off, [half j: math done, beliefs stored, scratch stored] x2, fenced:", [int(v - chunk[0]) if v else 0 for v in chunk[:9]])

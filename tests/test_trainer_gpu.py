@@ -238,3 +238,22 @@ def test_optional_heads_match_reference_trainer():
         np.testing.assert_allclose(agent.logs["train/" + k].item(), g["log_" + k], rtol=1e-3, atol=1e-5, err_msg=k)
     assert _cmp_grads(g, "actor", agent.actor_model, rtol=2e-3, atol=2e-3) == 10
     assert all(p.grad is None for p in agent.disag_model.parameters())      # frozen inside the bonus (dreamer.py:332)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo,expect", [("dreamer", True), ("repo", True), ("tia", False)])
+def test_optional_heads_are_trained_by_train_dynamics(algo, expect):
+    """dreamer.py:297-301 and repo.py:106-110 call train_disag / train_inv_dynamics at the end of train_dynamics (RePo's
+    override keeps them — round-1 advisor finding); tia.py:18-201 has neither head."""
+    from repo_b200.trainer import Agent, Config
+    dev = torch.device("cuda:0")
+    T, B, A = 6, 4, 6
+    cfg = Config(batch_size=B, chunk_size=T, disag_model=True, inv_dynamics=True, disag_coef=1.0)
+    agent = Agent(cfg, A, algo=algo, device=dev)
+    batch = {k: v.to(dev) for k, v in O.make_train_batch(3, T, B, A).items()}
+    before = [p.detach().clone() for p in agent.disag_model.parameters()] if expect else None
+    agent.train_dynamics(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"])
+    assert ("train/disag_loss" in agent.logs) == expect
+    assert ("train/inv_dyn_loss" in agent.logs) == expect
+    if expect:   # the ensemble really moved (it is no longer left at its random initialisation)
+        assert any((a - b.detach()).abs().max().item() > 0 for a, b in zip(before, agent.disag_model.parameters()))
