@@ -28,9 +28,14 @@ sys.path.insert(0, ROOT)
 FLOP_PER_STEP = 1_440_000      # algorithmic forward FLOPs per imagined latent step
 BYTES_PER_STEP = 1_312         # algorithmic HBM bytes per imagined latent step
 HORIZON = 15
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture (profiles/), by rows
-TRAFFIC_BYTES = {75776: 245_965_056 + 1_218_886_000}  # profiles/r01_rssm_rows_kernel_75776x14_ncu_full.txt
+# From the committed `ncu --set full` capture of this kernel at the bench shape (profiles/NCU_CAPTURE below): DRAM traffic of one
+# launch (dram__bytes_read.sum + dram__bytes_write.sum) and the tensor-pipe activity.  ncu cannot run inside a timed bench, so
+# these are constants tied to that file; everything else in `roofline` is measured live.
+NCU_CAPTURE = {"file": "profiles/r01_rssm_rows_kernel_75776x14_ncu_full.txt", "rows": 75776,
+               "traffic_bytes": 245_965_056 + 1_218_886_000, "tensor_pipe_active_pct": 36.9}
+MMA_ISSUE_FACTOR = 3.3   # tensor-pipe MACs issued per algorithmic MAC: 3 fp16 products per fp32-grade product x ~1.1 K/N padding
 DIMS = dict(belief=200, state=30, action=6, hidden=200, embed=1024)
+SWEEP_ROWS = (16384, 65536, 262144, 1048576)   # SURVEY 8(d) Config 5: total start states, split evenly over the GPUs
 
 
 def parse():
@@ -42,6 +47,7 @@ def parse():
     ap.add_argument("--rows-per-gpu", type=int, default=75776, help="start states per GPU; default = 4 waves of 148 SMs x 128-row tiles")
     ap.add_argument("--cpu-rows", type=int, default=4096, help="rows per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sweep / default-shape / data-parallel update blocks")
     ap.add_argument("--workload", default="imagine", choices=["imagine", "update"],
                     help="imagine = the headline sweep (default, what the driver runs); update = one full training iteration "
                          "(Agent.train_dynamics + train_actor_critic) with the replay batch sharded over the ranks (SURVEY 8d Config 2-4)")
@@ -51,11 +57,12 @@ def parse():
 
 
 def peaks():
+    """(burst bf16 TF/s, sustained bf16 TF/s, HBM GB/s, source)"""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("bf16_tflops_sustained", 1384.0), d.get("hbm_gbs", 6553.0), "measured (MEASURED_PEAKS.json, sustained bf16)"
-    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        return d.get("bf16_tflops", 1621.6), d.get("bf16_tflops_sustained", 1384.0), d.get("hbm_gbs", 6553.0), "measured (MEASURED_PEAKS.json)"
+    return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -112,24 +119,65 @@ def cpu_imagine_step(O, params, actor, reward, value, x):
     return O.imagine_returns(rew, val, 0.99, 0.95)
 
 
+REF_DIR = "/root/reference"
+
+
+def _reference_step_fn(rows):
+    """The UNMODIFIED reference (TransitionModel.imagine + RewardModel / ValueModel + lambda_return, loaded by file path as
+    oracle/make_golden.py does) when /root/reference exists on this machine; None on the GPU box, where it does not travel."""
+    if not os.path.isdir(REF_DIR):
+        return None
+    try:
+        from oracle import make_golden as MG
+        from oracle import rssm_oracle as O
+        R = MG.load_reference()
+    except Exception:
+        return None
+    D, S, A, Hd = DIMS["belief"], DIMS["state"], DIMS["action"], DIMS["hidden"]
+    tm = R.rssm.TransitionModel(D, S, A, Hd, DIMS["embed"], "elu")
+    tm.load_state_dict(O.make_transition_params(0))
+    actor = R.actor_critic.ActorModel(D, S, Hd, A, "elu")
+    actor.load_state_dict(O.make_mlp_params(1, D + S, Hd, 2 * A, 4))
+    reward = R.decoder.RewardModel(D, S, Hd, "elu")
+    reward.load_state_dict(O.make_mlp_params(2, D + S, Hd, 1, 3))
+    value = R.actor_critic.ValueModel(D, S, Hd, "elu")
+    value.load_state_dict(O.make_mlp_params(3, D + S, Hd, 1, 3))
+    x = O.make_imagine_inputs(4, rows, HORIZON)
+    bottle = R.common_utils.bottle if hasattr(R.common_utils, "bottle") else None
+
+    def step():   # dreamer.py:312-349 without the gradient bookkeeping
+        beliefs, states, _, _ = tm.imagine(x["belief"], x["state"], actor, HORIZON)
+        flat = lambda m: m(beliefs.flatten(0, 1), states.flatten(0, 1)).reshape(beliefs.shape[0], -1)
+        rew, val = flat(reward), flat(value)
+        disc = 0.99 * torch.ones_like(rew[:-1])
+        return R.common_utils.lambda_return(rew[:-1], val[:-1], disc, val[-1], 0.95)
+
+    return step
+
+
 def cpu_baseline(rows, steps, warmup):
-    """The oracle (a torch-CPU restatement of the reference: nn.Linear/GRUCell arithmetic via ATen/MKL on
-    all host threads) timed on a bounded sample of the same workload."""
+    """The reference's own CPU implementation of the path, on all host threads, on a bounded sample of the workload: the
+    unmodified reference modules when /root/reference is present ("reference"), else the oracle, a torch-CPU restatement
+    of it (nn.Linear / GRUCell arithmetic via ATen/MKL; "port")."""
     from oracle import rssm_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    params = O.make_transition_params(0)
-    actor = O.make_mlp_params(1, 230, 200, 12, 4)
-    reward = O.make_mlp_params(2, 230, 200, 1, 3)
-    value = O.make_mlp_params(3, 230, 200, 1, 3)
-    x = O.make_imagine_inputs(4, rows, HORIZON)
+    step = _reference_step_fn(rows)
+    kind = "reference" if step is not None else "port"
+    if step is None:
+        params = O.make_transition_params(0)
+        actor = O.make_mlp_params(1, 230, 200, 12, 4)
+        reward = O.make_mlp_params(2, 230, 200, 1, 3)
+        value = O.make_mlp_params(3, 230, 200, 1, 3)
+        x = O.make_imagine_inputs(4, rows, HORIZON)
+        step = lambda: cpu_imagine_step(O, params, actor, reward, value, x)
     with torch.no_grad():
         for _ in range(warmup):
-            cpu_imagine_step(O, params, actor, reward, value, x)
+            step()
         t0 = time.perf_counter()
         for _ in range(steps):
-            cpu_imagine_step(O, params, actor, reward, value, x)
+            step()
         dt = time.perf_counter() - t0
-    return rows * (HORIZON - 1) * steps / dt, dt / steps, torch.get_num_threads()
+    return rows * (HORIZON - 1) * steps / dt, dt / steps, torch.get_num_threads(), kind
 
 
 def run_reference(a):
@@ -137,14 +185,14 @@ def run_reference(a):
     if rank != 0:
         return
     steps = max(1, min(a.steps, 10))
-    v, sec, cores = cpu_baseline(a.cpu_rows, steps, max(1, min(a.warmup, 2)))
+    v, sec, cores, kind = cpu_baseline(a.cpu_rows, steps, max(1, min(a.warmup, 2)))
     sample = f"{a.cpu_rows} start rows x {HORIZON - 1} steps per step (bounded sample of the {a.rows_per_gpu}-row/GPU workload)"
     line = {
         "impl": "reference", "metric": "imagined latent steps/sec", "value": v, "unit": "steps/s", "n_gpus": a.gpus,
         "steps": steps, "warmup": max(1, min(a.warmup, 2)), "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a),
-        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -224,16 +272,18 @@ def run_gpu(a):
     barrier()
     ms = e0.elapsed_time(e1)
 
-    # kernel-only duration of the layer machine (roofline numerator): events around each launch
-    kms = []
-    for _ in range(5):
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0.record()
+    # kernel-only duration of the layer machine (the roofline numerator): the SAME back-to-back loop with the weights
+    # already packed, i.e. a.steps launches of rssm_rows_kernel alone between two events on the launching stream
+    for _ in range(2):
         ops.imagine_fwd(P, PA, PR, PV, belief, state, eps_a, eps_p, HORIZON, workspace=ws, packed=True)
-        k1.record()
-        torch.cuda.synchronize()
-        kms.append(k0.elapsed_time(k1))
-    kernel_ms = statistics.median(kms)
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(a.steps):
+        last_out = ops.imagine_fwd(P, PA, PR, PV, belief, state, eps_a, eps_p, HORIZON, workspace=ws, packed=True)
+    k1.record()
+    barrier()
+    kernel_ms = k0.elapsed_time(k1) / a.steps
 
     # ---- end to end through the module API with HOST start states ----
     # Each step: H2D of that step's start states from pinned host memory, TransitionModel.imagine (device noise
@@ -284,11 +334,71 @@ def run_gpu(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms, kernel_ms = [float(v) for v in t.tolist()]
 
+    # ---- sampled parity of the timed launch itself: 256 random rows of this rank's 75,776 vs the oracle (checker only;
+    # rows are independent, so the oracle runs on just those rows with the same weights and noise; outside every timed region)
+    parity = None
+    if rank == 0 and not a.no_extras:
+        from oracle import rssm_oracle as ORC
+        gi = torch.Generator().manual_seed(7)
+        idx = torch.randperm(N, generator=gi)[:256].sort().values
+        di = idx.to(dev)
+        cpu = lambda t_: t_.detach().float().cpu()
+        Pc, PAc, PRc, PVc = ({k: cpu(v) for k, v in d_.items()} for d_ in (P, PA, PR, PV))
+        want = ORC.imagine(Pc, PAc, cpu(belief[di]), cpu(state[di]), cpu(eps_a[:, di]), cpu(eps_p[:, di]), HORIZON)
+        rew = ORC.head_forward(PRc, want[0].flatten(0, 1), want[1].flatten(0, 1)).reshape(T, -1)
+        val = ORC.head_forward(PVc, want[0].flatten(0, 1), want[1].flatten(0, 1)).reshape(T, -1)
+        wret = ORC.imagine_returns(rew, val, 0.99, 0.95)
+        got = {"beliefs": last_out["beliefs"][:, di], "prior_states": last_out["prior_states"][:, di],
+               "prior_means": last_out["prior_means"][:, di], "prior_std_devs": last_out["prior_std_devs"][:, di],
+               "returns": last_out["returns"][:, di]}
+        ref = {"beliefs": want[0], "prior_states": want[1], "prior_means": want[2], "prior_std_devs": want[3], "returns": wret}
+        worst = {}
+        for k_, w_ in ref.items():
+            err = (cpu(got[k_]) - w_).abs()
+            worst[k_] = float((err / (1e-5 + 1e-3 * w_.abs())).max())   # > 1 = outside rtol 1e-3 (+ atol 1e-5)
+        parity = {"rows_checked": 256, "of_rows": N, "steps": T, "tolerance": "rtol 1e-3 + atol 1e-5 (north_star: rtol 1e-3)",
+                  "worst_error_over_tolerance": worst, "ok": all(v < 1.0 for v in worst.values())}
+        del want, got, ref
+
+    # ---- SURVEY 8(d) Config 5: total start states split evenly over the GPUs (device-timed, max over ranks) ----
+    sweep = None
+    if not a.no_extras:
+        sweep = {}
+        for total in SWEEP_ROWS:
+            n_loc = total // world
+            gs_ = torch.Generator(device=dev).manual_seed(99 + rank)
+            sb = (torch.randn(n_loc, D, device=dev, generator=gs_) * 0.3).clamp_(-1, 1)
+            ss = torch.randn(n_loc, S, device=dev, generator=gs_)
+            sea = torch.randn(T, n_loc, A, device=dev, generator=gs_)
+            sep = torch.randn(T, n_loc, S, device=dev, generator=gs_)
+            sw = None
+            for _ in range(2):
+                sw = ops.imagine_fwd(P, PA, PR, PV, sb, ss, sea, sep, HORIZON, workspace=sw)["workspace"]
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5 if total <= 262144 else 3
+            s0.record()
+            for _ in range(reps):
+                ops.imagine_fwd(P, PA, PR, PV, sb, ss, sea, sep, HORIZON, workspace=sw)
+            s1.record()
+            barrier()
+            tt = torch.tensor([s0.elapsed_time(s1) / reps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sweep[str(total)] = {"rows_per_gpu": n_loc, "ms": float(tt.item()), "steps_per_s": n_loc * world * T / float(tt.item()) * 1e3}
+            del sb, ss, sea, sep, sw
+        torch.cuda.empty_cache()
+
+    # ---- the communicating path (N > 1): one data-parallel training iteration on ALL ranks ----
+    dp_update = None
+    if world > 1 and not a.no_extras:
+        dp_update = dp_update_block(dev, rank, world, dist)
+
     # ---- RePo default shapes (configs[1]) : forward latency of the two kernels ----
     # (single-process runs only: the trainer-level updates all-reduce their gradient buckets, which would dead-lock
     # against the idle ranks of a multi-GPU imagine sweep)
     default_shape = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not a.no_extras:
         x = O.make_imagine_inputs(5, 2450, HORIZON)
         xa = [x["belief"].to(dev), x["state"].to(dev), x["eps_action"].to(dev), x["eps_prior"].to(dev)]
         xo = O.make_observe_inputs(6, 50, 50)
@@ -393,8 +503,12 @@ def run_gpu(a):
     total_steps = N * T * world
     value_sps = total_steps * a.steps / (ms / 1e3)
     e2e_sps = total_steps * a.steps / (e2e_ms / 1e3)
-    peak_tf, peak_gbs, peak_src = peaks()
+    peak_burst, peak_sust, peak_gbs, peak_src = peaks()
     achieved_tf = N * T * FLOP_PER_STEP / (kernel_ms / 1e3) / 1e12
+    # burst peak when the sampled SM clock sat at its maximum during the timed loops (a short region, not power-capped
+    # down), sustained otherwise
+    at_max = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.97 * clocks["sm_max_mhz"])
+    peak_tf = peak_burst if at_max else peak_sust
     line = {
         "metric": "imagined latent steps/sec", "value": value_sps, "unit": "steps/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
@@ -403,23 +517,100 @@ def run_gpu(a):
         "clocks": clocks,
         "e2e": {"value": e2e_sps, "unit": "steps/s", "h2d_bytes_per_step": N * (D + S) * 4, "d2h_bytes_per_step": (T - 1) * N * 4,
                 "ms_per_step": e2e_ms / a.steps,
-                "what": "per step: pinned-host start states -> H2D (double-buffered on a copy stream), TransitionModel.imagine (device noise draw, fused kernel), D2H of lambda-returns"},
-        "gpu_launches": 3 * a.steps,  # per rank per timed loop: pack_weights + pack_bias + rssm_vm_kernel
+                "what": "per step: pinned-host start states -> H2D (double-buffered on a copy stream), TransitionModel.imagine (device "
+                        "noise draw, fused kernel), D2H of the lambda-returns.  The imagined trajectories (1.2 GB per step) stay on "
+                        "the device, as in the reference, where imagine() feeds the actor / value losses and only scalars leave the GPU "
+                        "(dreamer.py:304-381)"},
+        # per rank per timed step: pack_rows_weights_kernel + pack_rows_bias_kernel + rssm_rows_kernel (the weights are
+        # re-packed every step because an optimiser step would have changed them; ~0.3 % of the step)
+        "gpu_launches": 3 * a.steps,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": TRAFFIC_BYTES.get(N), "kernel": "rssm_rows_kernel", "kernel_ms": kernel_ms,
+                     "peak_kind": "burst" if at_max else "sustained", "frac_of_burst": achieved_tf / peak_burst,
+                     "frac_of_sustained": achieved_tf / peak_sust,
+                     "traffic": NCU_CAPTURE["traffic_bytes"] if N == NCU_CAPTURE["rows"] else None, "traffic_source": NCU_CAPTURE["file"],
+                     "kernel": "rssm_rows_kernel", "kernel_ms": kernel_ms,
+                     "kernel_ms_how": "CUDA events around a.steps back-to-back launches with pre-packed weights, on the launching stream",
                      "algorithmic_flop_per_step": FLOP_PER_STEP, "algorithmic_bytes_per_step": BYTES_PER_STEP,
+                     "mma_issue_factor": MMA_ISSUE_FACTOR, "tensor_pipe_active_pct_ncu": NCU_CAPTURE["tensor_pipe_active_pct"],
+                     "tensor_pipe_busy_estimate": achieved_tf * MMA_ISSUE_FACTOR / 2250.0,
                      "hbm_gbs_achieved": N * T * BYTES_PER_STEP / (kernel_ms / 1e3) / 1e9, "hbm_peak_gbs": peak_gbs,
                      "peak_source": peak_src,
-                     "note": "algorithmic fp32 FLOPs; the kernel issues 3 fp16 MMAs per product (hi*hi+lo*hi+hi*lo), so tensor-pipe work is ~3.3x the algorithmic count"},
+                     "note": "algorithmic fp32 FLOPs (SURVEY 8d: 1.44 MFLOP per imagined step); the kernel issues 3 fp16 MMAs per product "
+                             "(hi*hi + lo*hi + hi*lo) plus K/N padding = mma_issue_factor x the algorithmic MACs on the tensor pipe; "
+                             "tensor_pipe_busy_estimate = achieved x factor / 2250 nominal dense fp16 TFLOP/s"},
+        "parity_sample": parity,
+        "sweep": sweep,
+        "dp_update": dp_update,
         "default_shape": default_shape,
     }
     if not a.no_cpu_baseline and world == 1:
-        v, sec, cores = cpu_baseline(2450, 3, 1)
-        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                                "sample": "RePo default shape: 2450 start rows x 14 steps, 3 timed passes of the oracle (torch CPU fp32)"}
+        v, sec, cores, kind = cpu_baseline(2450, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": kind,
+                                "sample": "RePo default shape: 2450 start rows x 14 steps, 3 timed passes (torch CPU fp32, all host threads)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dp_update_block(dev, rank, world, dist):
+    """One RePo training iteration (Agent.train_dynamics + train_actor_critic) with the replay batch sharded over ALL ranks:
+    strong scaling (global batch 50, shards 7,7,6,6,... with losses weighted B_local / B) and weak scaling (50 sequences per
+    GPU).  The one exchange is FlatAdam's flat-bucket gradient all-reduce (NCCL, one collective per parameter group); it is
+    also timed alone on buffers of the same sizes."""
+    from repo_b200 import parallel, synth
+    from repo_b200.trainer import Agent, Config
+    T, A = 50, DIMS["action"]
+    out = {}
+
+    def timed(fn, n):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return parallel.max_over_ranks(e0.elapsed_time(e1) / n, dev)
+
+    for mode, B in (("strong", 50), ("weak", 50 * world)):
+        agent = Agent(Config(batch_size=B, chunk_size=T), A, algo="repo", device=dev)
+        agent.optimizers()
+        c0, cn = parallel.shard_rows(B, rank, world)
+        full = synth.make_train_batch(7, T, 50, A)                 # every rank draws the same 50 sequences ...
+        cols = [(c0 + j) % 50 for j in range(cn)]                  # ... and takes its columns (weak: the batch tiled x world)
+        batch = {k: v[:, cols].contiguous().to(dev) for k, v in full.items()}
+        st = {}
+
+        def wm():
+            st["b"], st["s"] = agent.train_dynamics(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"])
+
+        def ac():
+            agent.train_actor_critic(st["b"].flatten(0, 1), st["s"].flatten(0, 1))
+
+        for _ in range(3):
+            wm(); ac()
+        out[mode] = {"global_batch": B, "shards": [parallel.shard_rows(B, r, world)[1] for r in range(world)],
+                     "iteration_ms": timed(lambda: (wm(), ac()), 5), "world_model_update_ms": timed(wm, 5),
+                     "actor_critic_update_ms": timed(ac, 5)}
+        buckets = {k: int(o.numel) * 4 for k, o in agent.optimizers().items() if hasattr(o, "numel")}
+        del agent
+    # the collective alone: SUM all-reduce of fp32 buffers of the bucket sizes (world model, actor, value)
+    sizes = buckets if buckets else {"model": 5_170_420 * 4, "actor": 169_212 * 4, "value": 126_801 * 4}
+    bufs = [torch.zeros(max(1, b // 4), device=dev) for b in sizes.values()]
+
+    def ar():
+        for t_ in bufs:
+            dist.all_reduce(t_)
+
+    for _ in range(3):
+        ar()
+    out["allreduce_bytes"] = int(sum(sizes.values()))
+    out["allreduce_buckets"] = sizes
+    out["allreduce_ms"] = timed(ar, 10)
+    out["note"] = ("RePo defaults (batch x chunk 50 of 64x64x3 frames, horizon 15); iteration = train_dynamics + train_actor_critic "
+                   "incl. all optimiser steps; max over ranks; allreduce_ms = the same buckets all-reduced alone")
+    return out
 
 
 def run_update(a):
@@ -429,8 +620,8 @@ def run_update(a):
     parameter group).  Strong scaling: the global batch is fixed."""
     import torch
     import torch.distributed as dist
-    from oracle import rssm_oracle as O
     from repo_b200 import parallel
+    from repo_b200 import synth as O
     from repo_b200.trainer import Agent, Config
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
