@@ -392,7 +392,7 @@ struct RBuilder {
   void end_stage(RStage& s, int epi, int flags, int nfeat, int act, int unit0 = 0, int width = 0, int xdep = 1) {
     s.gemm_end = (uint8_t)n_gemms;
     s.bias_n = (uint16_t)(n_bias - s.bias_off);
-    if (s.bias_n > kBiasStage) overflow = true;
+    if (n_bias > kBiasCap) overflow = true;
     s.epi = (uint8_t)epi; s.flags = (uint8_t)flags; s.act = (uint8_t)act;
     s.nfeat = (uint16_t)nfeat; s.unit0 = (uint16_t)unit0; s.width = (uint16_t)width;
     s.rounds = (uint8_t)(epi == R_ACT_H ? cdiv(cdiv(nfeat, 16), kEpiParts) : 1);
@@ -474,6 +474,12 @@ struct RBuilder {
       for (int j = 1; j < xdeps[i]; ++j) back += P.stages[((i - j) % n_stages + n_stages) % n_stages].rounds;
       P.stages[i].xback = (uint8_t)std::min(back, 255);
     }
+    int r0 = 0;
+    for (int i = 0; i < n_stages; ++i) {
+      P.stages[i].round0 = (uint16_t)r0;
+      r0 += P.stages[i].rounds;
+    }
+    P.rounds_per_step = r0;
   }
   // belief refresh scratch (rows.cuh, R_GRU): one [hi | lo] plane pair per SM
   size_t scr_plane() const { return (size_t)cdiv(std::max(P.v.D, 1), 8) * kXLBO; }
@@ -489,6 +495,7 @@ struct RBuilder {
     P.v.wblob = wb;
     P.v.bias = bb;
     P.n_rstages = n_stages;
+    P.n_bias = n_bias;
     P.scr = wb + align_up_(w_bytes, 256) + align_up_((size_t)n_bias * sizeof(float), 256);
     P.scr_plane = (uint32_t)scr_plane();
     P.scr_slots = std::max(1, sm_count());
@@ -567,7 +574,10 @@ bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
   if (d->state > 32 || d->action > 16) return false;  // the 128-row kernel keeps one row's Gaussian heads in registers
   // its other budgets: the bias staging buffer holds a scalar head's fc3 bias + fc4 row (2 * r16(hidden) + 16 floats), H and
   // the GRU's embedding operand fill one 256-column TMEM region, X for 128 rows must fit shared memory next to the ring
-  if (2 * r16(d->hidden) + 16 > kBiasStage || r16(d->belief) > 256 ||
+  // (upper bound of the bias floats of the largest program, imagine with both scalar heads: ten hidden layers, the GRU's four
+  // gate vectors padded per chunk, two fused fc3+fc4 stages, the Gaussian / action heads)
+  const int bias_floats = 10 * r16(d->hidden) + 4 * (r16(d->belief) + 48) + 2 * (2 * r16(d->hidden) + 16) + 4 * r16(d->state) + 64;
+  if (bias_floats > kBiasCap || r16(d->belief) > 256 ||
       rows_smem_bytes(cdiv(d->belief + d->state + d->action, 16)) > 227 * 1024)
     return false;
   if (row_tile == 128) return true;

@@ -31,6 +31,7 @@
 // groups of the Gaussian heads.  Round 1 ran two warps per quadrant at 208 registers: the epilogue warps were
 // busy ~113k of the 160k cycles of a step, each stalled ~65 % of the time.
 #pragma once
+#include <type_traits>
 #include "vm.cuh"
 
 namespace rb {
@@ -42,14 +43,20 @@ constexpr int kRowsEpiThreads = 512;
 constexpr int kEpiParts = 4;        // epilogue warps per TMEM lane quadrant
 constexpr int kRowsEpiWarps = kRowsEpiThreads / 32;
 constexpr int kRoundBars = 8;       // ring of round barriers; the epilogue is never more than 5 rounds ahead of the issuer
-constexpr int kRSlotBytes = 32768;
+constexpr int kRSlotBytes = 28672;     // two 208-wide slabs; the weight stream is not what bounds the kernel (profiling flag 8)
 constexpr int kRSlots = 3;
 constexpr int kRMaxStages = 32;
 constexpr int kRMaxGemms = 56;
-constexpr int kBiasStage = 512;        // floats per smem bias staging buffer (double-buffered)
+constexpr int kBiasCap = 5248;         // floats of shared memory for the biases of the WHOLE program, resident for the launch
 constexpr uint32_t kAccCol = 256;     // accumulators live at TMEM columns [256, 512)
 constexpr uint32_t kXLBO = kRowsM * 16;  // bytes between k-groups of X (128 rows x 16 B)
 constexpr int kRowsMiscBytes = 192 + kEpiParts * 128 * 4;   // 18 mbarrier slots + GruCtx (48 bytes), cross-warp partial sums (floats[parts][128])
+// Shared-memory map: everything of fixed size first, so that its addresses are the laundered base plus a constant.
+constexpr uint32_t kOffBias = 0;                                     // kBiasCap floats: every stage's bias vector (RStage::bias_off)
+constexpr uint32_t kOffBars = kOffBias + kBiasCap * 4;                // 24 x 8 bytes: mbarriers, TMEM base slot
+constexpr uint32_t kOffScratch = kOffBars + 192;                      // [kEpiParts][128] floats
+constexpr uint32_t kOffRing = (kOffScratch + kEpiParts * 128 * 4 + 127) / 128 * 128;
+constexpr uint32_t kOffX = kOffRing + kRSlots * kRSlotBytes;          // X hi plane, then the lo plane (kx16 k-slabs each)
 
 enum RowsEpi : uint8_t {
   R_ACT_H = 0,   // H[:, f] = act(acc + bias (+ addend))            -> TMEM H
@@ -90,6 +97,7 @@ struct RStage {
   uint8_t rounds;      // hand-off rounds this stage's epilogue signals: R_ACT_H = ceil(chunks / 4), every other kind 1
   uint8_t xback;       // rounds (of the stages in between) back from the end of the previous stage to the end of the stage that
                        // last wrote the X columns this stage reads: 0 = the previous stage (the default)
+  uint16_t round0;     // rounds signalled by the stages before this one within a step (global round = 1 + t * rounds_per_step + round0 + i)
 };
 
 struct RowsParams {
@@ -99,6 +107,8 @@ struct RowsParams {
   uint8_t* scr;          // belief refresh scratch: per SM (slot = %smid) an fp16 [hi plane | lo plane] image of X's belief k-groups
   uint32_t scr_plane;    // bytes per plane (= ceil(D / 8) * kXLBO)
   int scr_slots;         // slots allocated (SMs whose %smid is not below this use the global re-read path)
+  int rounds_per_step;   // sum of RStage::rounds over the program
+  int n_bias;            // floats in the bias blob (<= kBiasCap: resident in shared memory)
   RStage stages[kRMaxStages];
   RGemm gemms[kRMaxGemms];
 };
@@ -161,10 +171,42 @@ __device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Shared memory is addressed through 32-bit shared-window addresses derived from ONE base register (the kernel launders it
+// through an asm so that it is not rematerialised): generic pointers into dynamic shared memory made the compiler rebuild
+// the window base (S2UR SR_CgaCtaId + two ULEAs, a scoreboard stall each time) in front of nearly every access.
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+
 // two floats -> packed fp16 hi pair and lo pair (element 0 in the low half).  Both halves must be fp16:
 // tcgen05 kind::f16 rejects mixed fp16 x bf16 operands (tried: illegal instruction), so a cheap
 // bf16-by-truncation lo half is not an option.
 __device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  // (fma.rn.f32.f16 — SASS FHFMA, x - hi in one instruction — was measured: it issues at half rate, no gain over
+  // HADD2.F32 + FADD; scripts/ubench/pipes.cu)
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
   const __half2 h = *reinterpret_cast<const __half2*>(&hi);
   const float2 hf = __half22float2(h);
@@ -175,27 +217,27 @@ __device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uin
 __device__ __forceinline__ uint32_t x_off(int row, int k) {
   return (uint32_t)(k >> 3) * kXLBO + (uint32_t)row * 16u + (uint32_t)(k & 7) * 2u;
 }
-__device__ __forceinline__ void x_put(uint8_t* hi, uint8_t* lo, int row, int k, float v) {
+__device__ __forceinline__ void x_put(uint32_t hi, uint32_t lo, int row, int k, float v) {
   __half h, l;
   split_f16(v, h, l);
   const uint32_t o = x_off(row, k);
-  *reinterpret_cast<__half*>(hi + o) = h;
-  *reinterpret_cast<__half*>(lo + o) = l;
+  sts_u16(hi + o, __half_as_ushort(h));
+  sts_u16(lo + o, __half_as_ushort(l));
 }
 // 8 consecutive k (one k-group) of one row: a single 16-byte store per half
-__device__ __forceinline__ void x_put8(uint8_t* hi, uint8_t* lo, int row, int kgroup, const float* v) {
+__device__ __forceinline__ void x_put8(uint32_t hi, uint32_t lo, int row, int kgroup, const float* v) {
   uint4 h, l;
   split2_f16(v[0], v[1], h.x, l.x);
   split2_f16(v[2], v[3], h.y, l.y);
   split2_f16(v[4], v[5], h.z, l.z);
   split2_f16(v[6], v[7], h.w, l.w);
   const uint32_t o = (uint32_t)kgroup * kXLBO + (uint32_t)row * 16u;
-  *reinterpret_cast<uint4*>(hi + o) = h;
-  *reinterpret_cast<uint4*>(lo + o) = l;
+  sts_u4(hi + o, h);
+  sts_u4(lo + o, l);
 }
 
 __host__ __device__ inline size_t rows_smem_bytes(int kx16) {
-  return (size_t)kRSlots * kRSlotBytes + 2 * (size_t)kx16 * 2 * kXLBO + kRowsMiscBytes + 2 * kBiasStage * sizeof(float);
+  return (size_t)kOffX + 2 * (size_t)kx16 * 2 * kXLBO;
 }
 
 // 16 contiguous floats of one row (guarded tail / alignment handled outside the fast path)
@@ -274,21 +316,20 @@ __device__ __forceinline__ void st_row16_v2(float* dst, const float* v, int n_va
   }
 }
 // 16 floats every lane reads alike, from the smem bias staging buffer (broadcast LDS.128)
-__device__ __forceinline__ void ld_uni16(float* dst, const float* base) {
-  const float4* p = reinterpret_cast<const float4*>(base);
+__device__ __forceinline__ void ld_uni16(float* dst, uint32_t base) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 v = p[i];
+    const float4 v = lds_f4(base + 16u * i);
     dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
   }
 }
 // state pair (k even) of one row: one 4-byte store per half
-__device__ __forceinline__ void x_put2(uint8_t* hi, uint8_t* lo, int row, int k, float v0, float v1) {
+__device__ __forceinline__ void x_put2(uint32_t hi, uint32_t lo, int row, int k, float v0, float v1) {
   uint32_t h, l;
   split2_f16(v0, v1, h, l);
   const uint32_t o = x_off(row, k);
-  *reinterpret_cast<uint32_t*>(hi + o) = h;
-  *reinterpret_cast<uint32_t*>(lo + o) = l;
+  sts_u32(hi + o, h);
+  sts_u32(lo + o, l);
 }
 __device__ __forceinline__ void st_row16(float* dst, const float* v, int n_valid) {
   if (n_valid >= 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
@@ -320,13 +361,13 @@ __device__ __forceinline__ float act_bf(float x) {
 // pairs (8 columns) followed by the lo pairs (8 columns) of the same 16 features, so the region that held the
 // accumulators is the next layer's A operand and the region that held this layer's operand is free for its accumulators.
 template <int ACT, bool DOT, bool ADDEND>
-__device__ __forceinline__ float rows_act_chunk(const float* bias, const float* wdot, const float* adrow, uint32_t tacc,
+__device__ __forceinline__ float rows_act_chunk(uint32_t bias, uint32_t wdot, const float* adrow, uint32_t tacc,
                                                 int ch, int nfeat, bool row_ok) {
   float v[16], bz[16];
   const int f0 = ch * 16;
   float dot = 0.f;
   tmem_ld16(tacc + f0, v);
-  ld_uni16(bz, bias + f0);
+  ld_uni16(bz, bias + 4u * f0);
   if (ADDEND) {
     float ad[16];
     ld_row16(ad, adrow + f0, nfeat - f0, row_ok);
@@ -336,7 +377,7 @@ __device__ __forceinline__ float rows_act_chunk(const float* bias, const float* 
   tmem_ld_wait();
   if (DOT) {
     float w[16];
-    ld_uni16(w, wdot + f0);
+    ld_uni16(w, wdot + 4u * f0);
 #pragma unroll
     for (int i = 0; i < 16; ++i) dot = fmaf(w[i], act_bf<ACT>(v[i] + bz[i]), dot);
   } else {
@@ -349,6 +390,10 @@ __device__ __forceinline__ float rows_act_chunk(const float* bias, const float* 
   }
   return dot;
 }
+
+// (Splitting the 13th chunk of a 208-wide layer four ways, so that no warp of a quadrant takes 4 chunks against 3, was
+// measured: slower, 6.5k against 5.5k cycles per layer — the four warps share one scheduler, which is what limits them, and
+// the quarter pieces add instructions plus a quadrant barrier for the in-place rewrite.)
 
 // In-kernel clock64 stamps (scripts/stage_clock.py) exist only in the profiling build (-DRB_STAGE_CLOCK): in the product
 // build they would cost registers in the epilogue warps, which run at the spill threshold.
@@ -369,8 +414,8 @@ __device__ __forceinline__ float rows_act_chunk(const float* bias, const float* 
 // gate math.  Holding all four gate accumulators (64 registers per thread) across that point spilled into every stage
 // of the kernel (hidden-layer epilogues 4.9k -> 10k cycles), so r * (W_hn b + b_hn) is folded before the hand-off:
 // 48 registers (t, z_pre, i_n) cross it.
-__device__ __forceinline__ void rows_gru_stage(uint8_t* x_hi, uint8_t* x_lo, uint8_t* scr, uint32_t scr_plane, uint32_t bar_xb,
-                                               int D, uint32_t tacc, const float* bias, float* bel_row,
+__device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uint8_t* scr, uint32_t scr_plane, uint32_t bar_xb,
+                                               int D, uint32_t tacc, uint32_t bias, float* bel_row,
                                                uint32_t bar_handoff, uint32_t xb_parity, int r, int part, bool row_ok, int flags,
                                                int W, int u0, int nu, long long* dbg = nullptr) {
 #ifdef RB_STAGE_CLOCK
@@ -389,8 +434,8 @@ __device__ __forceinline__ void rows_gru_stage(uint8_t* x_hi, uint8_t* x_lo, uin
     // k-groups [0, u0/8) into X while this chunk's gate math runs.
     const uint32_t bytes = (uint32_t)(u0 >> 3) * kXLBO;
     mbar_arrive_expect_tx(bar_xb, 2u * bytes);
-    bulk_g2s(smem_u32(x_hi), scr, bytes, bar_xb);
-    bulk_g2s(smem_u32(x_lo), scr + scr_plane, bytes, bar_xb);
+    bulk_g2s(x_hi, scr, bytes, bar_xb);
+    bulk_g2s(x_lo, scr + scr_plane, bytes, bar_xb);
   }
   float vt[16], vz[16], vi[16];   // r * (W_hn b + b_hn), z pre-activation, i_n pre-activation
   if (mine) {
@@ -402,10 +447,10 @@ __device__ __forceinline__ void rows_gru_stage(uint8_t* x_hi, uint8_t* x_lo, uin
     tmem_ld16(tacc + 2 * W + c, vi);
     {
       float bb[16];
-      ld_uni16(bb, bias + c);
+      ld_uni16(bb, bias + 4u * c);
 #pragma unroll
       for (int i = 0; i < 16; ++i) vt[i] = sigmoid_f(vt[i] + bb[i]);
-      ld_uni16(bb, bias + 3 * W + c);
+      ld_uni16(bb, bias + 4u * (3 * W + c));
 #pragma unroll
       for (int i = 0; i < 16; ++i) vt[i] = vt[i] * (vh[i] + bb[i]);
     }
@@ -430,21 +475,20 @@ __device__ __forceinline__ void rows_gru_stage(uint8_t* x_hi, uint8_t* x_lo, uin
       const int kg = (u0 + c) / 8 + j;
       {
         float g[8];
-        const float4* pb = reinterpret_cast<const float4*>(bias + c + 8 * j);
-        const int Wq = W >> 2;   // W floats = Wq float4
-        float4 b0 = pb[2 * Wq], b1 = pb[2 * Wq + 1];
+        const uint32_t pb = bias + 4u * (c + 8 * j);
+        float4 b0 = lds_f4(pb + 8u * W), b1 = lds_f4(pb + 8u * W + 16u);
         const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) bn[i] = tanh_f(vi[8 * j + i] + bi[i] + vt[8 * j + i]);   // candidate n
-        b0 = pb[Wq]; b1 = pb[Wq + 1];
+        b0 = lds_f4(pb + 4u * W); b1 = lds_f4(pb + 4u * W + 16u);
         const float bzz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = sigmoid_f(vz[8 * j + i] + bzz[i]);                 // z
         // b_prev = hi + lo from the belief slot of X (exact to 2^-22 relative).  The refresh overwrites k-groups below
         // u0/8 only in the last chunk, whose own units lie above them.
         if (kg * 8 < D) {
-          const uint4 h4 = *reinterpret_cast<const uint4*>(x_hi + (uint32_t)kg * kXLBO + (uint32_t)r * 16u);
-          const uint4 l4 = *reinterpret_cast<const uint4*>(x_lo + (uint32_t)kg * kXLBO + (uint32_t)r * 16u);
+          const uint4 h4 = lds_u4(x_hi + (uint32_t)kg * kXLBO + (uint32_t)r * 16u);
+          const uint4 l4 = lds_u4(x_lo + (uint32_t)kg * kXLBO + (uint32_t)r * 16u);
           const uint32_t hw[4] = {h4.x, h4.y, h4.z, h4.w}, lw[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -522,21 +566,23 @@ __device__ __forceinline__ void rows_gru_stage(uint8_t* x_hi, uint8_t* x_lo, uin
 __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid_constant__ RowsParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const VmParams& V = P.v;
-  uint8_t* ring = smem;
-  uint8_t* x_hi = ring + kRSlots * kRSlotBytes;
+  uint32_t sb;   // shared-window address of the dynamic shared memory; volatile asm = never rematerialised from the symbol
+  asm volatile("mov.u32 %0, %1;" : "=r"(sb) : "r"(smem_u32(smem)));
+  const uint32_t ring_a = sb + kOffRing;
+  const uint32_t x_hi = sb + kOffX;
   const uint32_t x_bytes = (uint32_t)V.kx16 * 2u * kXLBO;
-  uint8_t* x_lo = x_hi + x_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(x_lo + x_bytes);        // 16 slots (128 bytes)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
-  float* scratch = reinterpret_cast<float*>(bars + 24);                // [kEpiParts][128] cross-warp partial sums (bars + 18: GruCtx)
-  float* bias_s = scratch + kEpiParts * 128;                           // 2 x kBiasStage floats, 16-byte aligned
+  const uint32_t x_lo = x_hi + x_bytes;
+  const uint32_t bars = sb + kOffBars;                           // 8-byte slots
+  const uint32_t tmem_slot = bars + 8 * 15;
+  const uint32_t scratch = sb + kOffScratch;                     // [kEpiParts][128] cross-warp partial sums
+  const uint32_t bias_s = sb + kOffBias;                         // 2 x kBiasStage floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * kRowsM;
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + kRSlots);
-  const uint32_t bar_acc = smem_u32(bars + 2 * kRSlots);         // a stage's accumulators are complete
-  const uint32_t bar_round = smem_u32(bars + 2 * kRSlots + 1);   // kRoundBars hand-off barriers: global round g -> slot g % 8
-  const uint32_t bar_xb = smem_u32(bars + 16);                   // belief refresh bulk copies have landed
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * kRSlots;
+  const uint32_t bar_acc = bars + 8 * (2 * kRSlots);         // a stage's accumulators are complete
+  const uint32_t bar_round = bars + 8 * (2 * kRSlots + 1);   // kRoundBars hand-off barriers: global round g -> slot g % 8
+  const uint32_t bar_xb = bars + 8 * 16;                     // belief refresh bulk copies have landed
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRSlots; ++i) {
@@ -549,13 +595,13 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = lds_u32(tmem_slot);
 
   // Each role changes its register budget INSIDE its own branch (ptxas sizes a region by the setmaxnreg that dominates
   // it).  640 threads launch with 96 registers each; warpgroup 0 keeps 32, the four epilogue warpgroups get 112.
@@ -586,7 +632,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
 #endif
               {
                 mbar_arrive_expect_tx(bar_full + 8 * slot, bytes);
-                bulk_g2s(smem_u32(ring + slot * kRSlotBytes), src + (size_t)c0 * slab_bytes, bytes, bar_full + 8 * slot);
+                bulk_g2s(ring_a + slot * kRSlotBytes, src + (size_t)c0 * slab_bytes, bytes, bar_full + 8 * slot);
               }
             }
             __syncwarp();
@@ -608,10 +654,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       }
       tc_fence_after();
     };
-    const uint64_t x_desc = make_smem_desc(smem_u32(x_hi), kXLBO, 128);
+    const uint64_t x_desc = make_smem_desc(x_hi, kXLBO, 128);
     const uint64_t x_lo_delta = x_bytes >> 4;
     constexpr uint64_t kX_slab = (2u * kXLBO) >> 4;
-    const uint32_t ring_a = smem_u32(ring);
     for (int t = 0; t < V.n_steps; ++t) {
       for (int s = 0; s < P.n_rstages; ++s) {
         const int g0 = P.stages[s].gemm_begin, g1 = P.stages[s].gemm_end;
@@ -696,8 +741,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
     // ---- init: zero X, then stage [belief | state*nonterm[0] | action[0]] ----
     {
       const uint32_t words = (2 * x_bytes) / 16;
-      uint4* z = reinterpret_cast<uint4*>(x_hi);
-      for (uint32_t i = et; i < words; i += kRowsEpiThreads) z[i] = make_uint4(0, 0, 0, 0);
+      for (uint32_t i = et; i < words; i += kRowsEpiThreads) sts_u4(x_hi + 16u * i, make_uint4(0, 0, 0, 0));
       epi_sync();
       if (row_ok) {
         if (V.init_belief) {
@@ -722,79 +766,60 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_round);   // global round 0
     }
-    uint32_t ground = 1;   // next global hand-off round this warp signals
 
-    // With ~220 KB of shared memory in use there is next to no L1: every global load is an L2
-    // round trip.  So while the MMAs of a stage run, the epilogue warps already fetch what that
-    // stage's epilogue will need: its biases into a smem staging buffer, its per-row noise (this warp's 8 columns)
-    // into registers.
-    float pre[8];
-    float pre_nt = 1.f;
-    auto prefetch = [&](int t, int s, int buf) {
-      const RStage& st = P.stages[s];
-      const size_t trow = (size_t)t * N;
-      float* dstb = bias_s + buf * kBiasStage;
-      for (int i = et; i < st.bias_n; i += kRowsEpiThreads) cp_async4(smem_u32(dstb + i), V.bias + st.bias_off + i);
-      switch (st.epi) {
-        case R_PRIOR:
-        case R_POST: {
-          const int c = part * 8;   // the four warps of a quadrant take one 8-state group each
-          const float* eps = (st.epi == R_POST ? V.eps_post : V.eps_prior) + (trow + row) * S + c;
-          ld_row8_v2<true>(pre, eps, S - c, row_ok && c < S);
-          pre_nt = 1.f;
-          if ((st.flags & SF_WRITES_STATE) && V.nonterm && (t + 1) < V.n_steps && row_ok) pre_nt = __ldg(V.nonterm + trow + N + row);
-        } break;
-        case R_ACTION: {
-          const int c = part * 8;
-          if (c < A) {
-            const float* eps = V.eps_action + (trow + row) * A + c;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pre[i] = (row_ok && c + i < A) ? __ldg(eps + i) : 0.f;
-          }
-        } break;
-        default: break;
-      }
-    };
-
-    uint32_t acc_phase = 0;
-    int buf = 0;
-    {  // stage 0 of step 0 never needs per-row inputs ahead of time in either program; stage its biases
-      const RStage& st0 = P.stages[0];
-      for (int i = et; i < st0.bias_n; i += kRowsEpiThreads) bias_s[i] = __ldg(V.bias + st0.bias_off + i);
-      if (st0.epi == R_GRU || st0.epi == R_PRIOR || st0.epi == R_POST || st0.epi == R_ACTION) __trap();
-    }
+    // The biases of every stage stay in shared memory for the whole launch (RStage::bias_off indexes them).  Round 1 staged
+    // each stage's vector through a double buffer while the previous stage ran: an LDGSTS per thread, a wait for the L2 round
+    // trip and a 512-thread barrier in front of EVERY stage — ~700 cycles of the ~1.6k that separate two dependent layers.
+    for (int i = et; i < P.n_bias; i += kRowsEpiThreads) sts_f(bias_s + 4u * i, __ldg(V.bias + i));
+    epi_sync();
+    uint32_t par = 0;   // parity of the stage counter = phase of the accumulator barrier
     for (int t = 0; t < V.n_steps; ++t) {
       const size_t trow = (size_t)t * N;
       const bool has_next = (t + 1) < V.n_steps;
       for (int s = 0; s < P.n_rstages; ++s) {
         const RStage& st = P.stages[s];
-        const float* bias = bias_s + buf * kBiasStage;
+        const uint32_t bias = bias_s + 4u * st.bias_off;
         const uint32_t tacc = tl + ((st.regs & 1) ? kAccCol : 0u);
         RB_STAMP(0);
-        mbar_wait(bar_acc, acc_phase);
-        acc_phase ^= 1;
+        // Per-row noise of this stage (this warp's 8 columns), requested before the wait for the accumulators so that the L2
+        // round trip runs under the stage's MMAs.  Declared per stage: a value carried around the stage loop would hold 9
+        // registers in every other stage's epilogue too.
+        float pre[8];
+        float pre_nt = 1.f;
+        if (st.epi == R_PRIOR || st.epi == R_POST) {
+          const int c = part * 8;   // the four warps of a quadrant take one 8-state group each
+          const float* eps = (st.epi == R_POST ? V.eps_post : V.eps_prior) + (trow + row) * S + c;
+          ld_row8_v2<true>(pre, eps, S - c, row_ok && c < S);
+          if ((st.flags & SF_WRITES_STATE) && V.nonterm && has_next && row_ok) pre_nt = __ldg(V.nonterm + trow + N + row);
+        } else if (st.epi == R_ACTION) {
+          const int c = part * 8;
+          const float* eps = V.eps_action + (trow + row) * A + c;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pre[i] = (row_ok && c + i < A) ? __ldg(eps + i) : 0.f;
+        }
+        mbar_wait(bar_acc, par);
         tc_fence_after();
         RB_STAMP(1);
-        cp_async_wait_all();   // this thread's share of the staged biases has landed ...
-        epi_sync();            // ... and everybody else's
         RB_STAMP(2);
         RB_STAGE_BEGIN();
         // One hand-off round: this warp's TMEM / shared-memory writes of the round are done.  The proxy fence also waits
         // for the thread's outstanding GLOBAL stores, and the output rows are `feature`-strided (32 sectors per store
         // instruction) — stages with outputs therefore write their smem/TMEM operands first, hand the stage back, and only
         // then store the outputs, which drain while the next stage's MMAs run.
+        // Rounds are numbered globally; the number is recomputed from (t, stage) rather than carried: a running counter
+        // lived in local memory, i.e. an L2 round trip in front of every signal.
+        const uint32_t ground0 = 1u + (uint32_t)t * (uint32_t)P.rounds_per_step + st.round0;
         bool handed = false;
-        auto signal_round = [&](bool wrote_smem) {
+        auto signal_round = [&](bool wrote_smem, uint32_t i) {
           if (wrote_smem) fence_proxy_async_smem();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_round + 8 * (ground & (kRoundBars - 1)));
-          ++ground;
+          if (lane == 0) mbar_arrive(bar_round + 8 * ((ground0 + i) & (kRoundBars - 1)));
         };
-        auto handoff = [&] {
+        auto handoff = [&](bool wrote_smem) {
           RB_STAMP(3);
           RB_STAGE_END();
-          signal_round(true);
+          signal_round(wrote_smem, 0);
           handed = true;
         };
 
@@ -804,23 +829,31 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             const bool elu = st.act == ACT_ELU, addend = (st.flags & SF_ADDEND) != 0;
             const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
             const float* adrow = addend ? V.addend + (trow + row) * V.Hd : nullptr;
-            for (int ch0 = 0; ch0 < nch; ch0 += kEpiParts) {
-              const int ch = ch0 + part;
-              if (ch < nch) {
-                if (addend) {
-                  if (elu) rows_act_chunk<ACT_ELU, false, true>(bias, nullptr, adrow, tacc, ch, nfeat, row_ok);
-                  else rows_act_chunk<ACT_RELU, false, true>(bias, nullptr, adrow, tacc, ch, nfeat, row_ok);
-                } else {
-                  if (elu) rows_act_chunk<ACT_ELU, false, false>(bias, nullptr, nullptr, tacc, ch, nfeat, row_ok);
-                  else rows_act_chunk<ACT_RELU, false, false>(bias, nullptr, nullptr, tacc, ch, nfeat, row_ok);
+            // the activation / addend variant is chosen once per layer, not per chunk
+            auto layer = [&](auto act_tag, auto addend_tag) {
+              constexpr int ACT = decltype(act_tag)::value;
+              constexpr bool AD = decltype(addend_tag)::value;
+              for (int ch0 = 0; ch0 < nch; ch0 += kEpiParts) {
+                const int ch = ch0 + part;
+                if (ch < nch) {
+                  rows_act_chunk<ACT, false, AD>(bias, 0u, adrow, tacc, ch, nfeat, row_ok);
+                  tmem_st_wait();
                 }
-                tmem_st_wait();
+                if (ch0 + kEpiParts >= nch) {
+                  RB_STAMP(3);
+                  RB_STAGE_END();
+                }
+                signal_round(false, (uint32_t)ch0 / kEpiParts);
               }
-              if (ch0 + kEpiParts >= nch) {
-                RB_STAMP(3);
-          RB_STAGE_END();
-              }
-              signal_round(false);
+            };
+            using IC_ELU = std::integral_constant<int, ACT_ELU>;
+            using IC_RELU = std::integral_constant<int, ACT_RELU>;
+            if (addend) {
+              if (elu) layer(IC_ELU{}, std::true_type{});
+              else layer(IC_RELU{}, std::true_type{});
+            } else {
+              if (elu) layer(IC_ELU{}, std::false_type{});
+              else layer(IC_RELU{}, std::false_type{});
             }
             handed = true;
           } break;
@@ -828,37 +861,39 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
           case R_ACT_DOT: {
             const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
             const bool elu = st.act == ACT_ELU;
-            const float* wdot = bias + nch * 16;   // the 1-output layer's weight row follows the bias
+            const uint32_t wdot = bias + 4u * (nch * 16);   // the 1-output layer's weight row follows the bias
             float dot = 0.f;
-            for (int ch = part; ch < nch; ch += kEpiParts)
-              dot += elu ? rows_act_chunk<ACT_ELU, true, false>(bias, wdot, nullptr, tacc, ch, nfeat, row_ok)
-                         : rows_act_chunk<ACT_RELU, true, false>(bias, wdot, nullptr, tacc, ch, nfeat, row_ok);
-            handoff();   // the accumulators are consumed; nothing in X / H changes
-            if (part) scratch[part * 128 + r] = dot;
+            if (elu) {
+              for (int ch = part; ch < nch; ch += kEpiParts) dot += rows_act_chunk<ACT_ELU, true, false>(bias, wdot, nullptr, tacc, ch, nfeat, row_ok);
+            } else {
+              for (int ch = part; ch < nch; ch += kEpiParts) dot += rows_act_chunk<ACT_RELU, true, false>(bias, wdot, nullptr, tacc, ch, nfeat, row_ok);
+            }
+            handoff(false);   // the accumulators are consumed; nothing in X / H changes
+            if (part) sts_f(scratch + 4u * (part * 128 + r), dot);
             epi_sync();
             if (part == 0 && row_ok) {
               float* dst = (st.flags & SF_SCALAR_VALUE) ? V.values : V.rewards;
-              dst[trow + row] = ((dot + scratch[128 + r]) + (scratch[256 + r] + scratch[384 + r])) + bias[2 * nch * 16];
+              dst[trow + row] = ((dot + lds_f(scratch + 4u * (128 + r))) + (lds_f(scratch + 4u * (256 + r)) + lds_f(scratch + 4u * (384 + r)))) + lds_f(bias + 4u * (2 * nch * 16));
             }
           } break;
 
           case R_GRU: {
             const bool last_chunk = (st.flags & RF_LAST_CHUNK) != 0;
+            // the belief refresh (bulk copy scratch -> X, issued by one thread) needs every warp's scratch writes of the
+            // earlier chunks: each warp fences them at the end of its chunk, this barrier orders all warps behind that
+            if (last_chunk && st.unit0 > 0) epi_sync();
             if (!last_chunk) {
               RB_STAMP(3);
           RB_STAGE_END();
             }
             rows_gru_stage(x_hi, x_lo, scr, P.scr_plane, bar_xb, D, tacc, bias, V.beliefs + (trow + row) * D,
-                           bar_round + 8 * (ground & (kRoundBars - 1)), (uint32_t)(t & 1), r, part, row_ok, st.flags, st.width,
+                           bar_round + 8 * (ground0 & (kRoundBars - 1)), (uint32_t)(t & 1), r, part, row_ok, st.flags, st.width,
                            st.unit0, st.nfeat
 #ifdef RB_STAGE_CLOCK
                            , (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5 && st.unit0 == 64) ? V.dbg_clock + 860 : nullptr
 #endif
                            );
-            if (!last_chunk) {   // handed back right after the accumulators were read
-              ++ground;
-              handed = true;
-            }
+            if (!last_chunk) handed = true;   // handed back right after the accumulators were read
           } break;
 
           case R_PRIOR:
@@ -881,11 +916,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               }
               tmem_ld8(tacc + c, vm);
               tmem_ld8(tacc + W + c, vs);
+              const float4 bm0 = lds_f4(bias + 4u * c), bm1 = lds_f4(bias + 4u * c + 16u);
+              const float4 bs0 = lds_f4(bias + 4u * (W + c)), bs1 = lds_f4(bias + 4u * (W + c) + 16u);
+              const float bm[8] = {bm0.x, bm0.y, bm0.z, bm0.w, bm1.x, bm1.y, bm1.z, bm1.w};
+              const float bsd[8] = {bs0.x, bs0.y, bs0.z, bs0.w, bs1.x, bs1.y, bs1.z, bs1.w};
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                vm[i] += bias[c + i];
-                vs[i] = softplus_f(vs[i] + bias[W + c + i]) + V.min_std;
+                vm[i] += bm[i];
+                vs[i] = softplus_f(vs[i] + bsd[i]) + V.min_std;
                 smp[i] = vm[i] + vs[i] * pre[i];
               }
               if (want_kl) {
@@ -915,8 +954,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             }
             if (part == kEpiParts - 1 && (st.flags & SF_LOADS_ACTION) && has_next && row_ok)
               for (int j = 0; j < A; ++j) x_put(x_hi, x_lo, r, D + S + j, __ldg(V.actions_in + (trow + N + row) * A + j));
-            if (want_kl && part) scratch[part * 128 + r] = kl;
-            handoff();
+            if (want_kl && part) sts_f(scratch + 4u * (part * 128 + r), kl);
+            handoff(true);
             // Output rows are S floats apart, so a store with lane = row touches 32 cache lines per instruction and
             // kept the LSU busy for ~9k cycles.  Transpose through tensor memory instead: park the three 32 x 8 blocks
             // (lane = row) in columns nobody uses right now and read them back in the 16x256b fragment layout, where
@@ -961,7 +1000,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             }
             if (want_kl) {   // uniform across the CTA: V.kl and the stage kind are kernel-wide
               epi_sync();
-              if (part == 0 && row_ok) V.kl[trow + row] = (kl + scratch[128 + r]) + (scratch[256 + r] + scratch[384 + r]);
+              if (part == 0 && row_ok) V.kl[trow + row] = (kl + lds_f(scratch + 4u * (128 + r))) + (lds_f(scratch + 4u * (256 + r)) + lds_f(scratch + 4u * (384 + r)));
             }
           } break;
 
@@ -974,17 +1013,21 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               const size_t o = (trow + row) * A + c;
               tmem_ld8(tacc + c, vm);
               tmem_ld8(tacc + W + c, vs);
+              const float4 bm0 = lds_f4(bias + 4u * c), bm1 = lds_f4(bias + 4u * c + 16u);
+              const float4 bs0 = lds_f4(bias + 4u * (W + c)), bs1 = lds_f4(bias + 4u * (W + c) + 16u);
+              const float bm[8] = {bm0.x, bm0.y, bm0.z, bm0.w, bm1.x, bm1.y, bm1.z, bm1.w};
+              const float bsd[8] = {bs0.x, bs0.y, bs0.z, bs0.w, bs1.x, bs1.y, bs1.z, bs1.w};
               tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float mean = V.a_mean_scale * tanh_f((vm[i] + bias[c + i]) * inv_ms);
-                const float sd = softplus_f(vs[i] + bias[W + c + i] + V.a_init_std) + V.a_min_std;
+                const float mean = V.a_mean_scale * tanh_f((vm[i] + bm[i]) * inv_ms);
+                const float sd = softplus_f(vs[i] + bsd[i] + V.a_init_std) + V.a_min_std;
                 vm[i] = tanh_f(mean + sd * pre[i]);
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (c + i < A) x_put(x_hi, x_lo, r, D + S + c + i, vm[i]);
-              handoff();
+              handoff(true);
               if (row_ok && V.actions_out) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -999,20 +1042,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               tmem_ld16(tacc, v);
               tmem_ld_wait();
               float* dst = (st.flags & SF_SCALAR_VALUE) ? V.values : V.rewards;
-              if (row_ok) dst[trow + row] = v[0] + bias[0];
+              if (row_ok) dst[trow + row] = v[0] + lds_f(bias);
             }
           } break;
           default: break;
         }
 
-        if (!handed) handoff();
+        if (!handed) handoff(st.epi != R_SCALAR);
         RB_STAMP_X(0);
-        // fetch for the next stage while its MMAs run
-        buf ^= 1;
-        {
-          const bool wrap = (s + 1 == P.n_rstages);
-          if (!wrap || has_next) prefetch(wrap ? t + 1 : t, wrap ? 0 : s + 1, buf);
-        }
+        par ^= 1;
         RB_STAMP_X(1);
       }
     }
