@@ -274,8 +274,9 @@ def run_gpu(a):
 
     # kernel-only duration of the layer machine (the roofline numerator): the SAME back-to-back loop with the weights
     # already packed, i.e. a.steps launches of rssm_rows_kernel alone between two events on the launching stream
-    for _ in range(2):
-        ops.imagine_fwd(P, PA, PR, PV, belief, state, eps_a, eps_p, HORIZON, workspace=ws, packed=True)
+    last_out = None
+    for _ in range(3):   # same retention pattern as the timed loop (two output sets alive), so that it allocates nothing
+        last_out = ops.imagine_fwd(P, PA, PR, PV, belief, state, eps_a, eps_p, HORIZON, workspace=ws, packed=True)
     barrier()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()

@@ -556,15 +556,25 @@ int launch_rows(const RowsParams& P, cudaStream_t st) {
   if (P.v.N <= 0 || P.v.n_steps <= 0) return 0;
   const size_t smem = rows_smem_bytes(P.v.kx16);
   if (smem > 227 * 1024) return fail(-5, "rows kernel: shared memory budget exceeded (%zu bytes)", smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    CUDA_OK(cudaFuncSetAttribute(rssm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  // program family -> kernel specialisation (rows.cuh, PROG): imagine-like programs have no addend / posterior stages,
+  // observe-like ones no actor / scalar-head stages
+  bool has_addend_post = false, has_actor = false;
+  for (int i = 0; i < P.n_rstages; ++i) {
+    const RStage& s = P.stages[i];
+    has_addend_post |= s.epi == R_POST || (s.epi == R_ACT_H && (s.flags & SF_ADDEND));
+    has_actor |= s.epi == R_ACT_DOT || s.epi == R_ACTION || s.epi == R_SCALAR;
+  }
+  const int prog = !has_addend_post ? 1 : (!has_actor ? 2 : 0);
+  auto kern = prog == 1 ? rssm_rows_kernel<1> : (prog == 2 ? rssm_rows_kernel<2> : rssm_rows_kernel<0>);
+  static size_t configured[3] = {0, 0, 0};
+  if (smem > configured[prog]) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[prog] = smem;
   }
   RowsParams Q = P;
   Q.v.dbg_flags = g_dbg_flags;
   Q.v.dbg_clock = g_dbg_clock;
-  rssm_rows_kernel<<<cdiv(P.v.N, kRowsM), kRowsThreads, smem, st>>>(Q);
+  kern<<<cdiv(P.v.N, kRowsM), kRowsThreads, smem, st>>>(Q);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -437,12 +437,15 @@ __device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uin
     bulk_g2s(x_hi, scr, bytes, bar_xb);
     bulk_g2s(x_lo, scr + scr_plane, bytes, bar_xb);
   }
-  float vt[16], vz[16], vi[16];   // r * (W_hn b + b_hn), z pre-activation, i_n pre-activation
+  // Two 16-register arrays cross the hand-off: the candidate's pre-activation i_n + b_in + r * (W_hn b + b_hn), folded as soon
+  // as its terms are out of tensor memory, and the z pre-activation (three arrays spilled: 16 L2 round trips per chunk).
+  float vt[16], vz[16];
   if (mine) {
     float vh[16];
     tmem_ld16(tacc + c, vt);            // r
     tmem_ld16(tacc + 3 * W + c, vh);    // h_n
     tmem_ld_wait();
+    float vi[16];
     tmem_ld16(tacc + W + c, vz);        // in flight under the r-gate math
     tmem_ld16(tacc + 2 * W + c, vi);
     {
@@ -453,8 +456,11 @@ __device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uin
       ld_uni16(bb, bias + 4u * (3 * W + c));
 #pragma unroll
       for (int i = 0; i < 16; ++i) vt[i] = vt[i] * (vh[i] + bb[i]);
+      ld_uni16(bb, bias + 4u * (2 * W + c));
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) vt[i] += vi[i] + bb[i];
     }
-    tmem_ld_wait();
   }
   // The accumulators have left tensor memory and X is untouched by this chunk: hand the stage back now, so that the
   // next chunk's MMAs run under the rest of the gate math and the stores.
@@ -476,11 +482,9 @@ __device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uin
       {
         float g[8];
         const uint32_t pb = bias + 4u * (c + 8 * j);
-        float4 b0 = lds_f4(pb + 8u * W), b1 = lds_f4(pb + 8u * W + 16u);
-        const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) bn[i] = tanh_f(vi[8 * j + i] + bi[i] + vt[8 * j + i]);   // candidate n
-        b0 = lds_f4(pb + 4u * W); b1 = lds_f4(pb + 4u * W + 16u);
+        for (int i = 0; i < 8; ++i) bn[i] = tanh_f(vt[8 * j + i]);   // candidate n
+        const float4 b0 = lds_f4(pb + 4u * W), b1 = lds_f4(pb + 4u * W + 16u);
         const float bzz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = sigmoid_f(vz[8 * j + i] + bzz[i]);                 // z
@@ -563,7 +567,13 @@ __device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uin
   }
 }
 
+// PROG specialises the epilogue for the program family, so that the register allocation of one family does not carry the
+// other's stage kinds (ptxas spills a value everywhere once ANY path is short of registers; the posterior layer's per-row
+// addend alone is 16 registers): 1 = imagine (no addend, no posterior head), 2 = observe (no actor / scalar-head stages),
+// 0 = everything (one-step cell programs, conditional variants).
+template <int PROG>
 __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid_constant__ RowsParams P) {
+  constexpr bool kHasAddend = PROG != 1, kHasPost = PROG != 1, kHasActor = PROG != 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const VmParams& V = P.v;
   uint32_t sb;   // shared-window address of the dynamic shared memory; volatile asm = never rematerialised from the symbol
@@ -788,10 +798,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         float pre_nt = 1.f;
         if (st.epi == R_PRIOR || st.epi == R_POST) {
           const int c = part * 8;   // the four warps of a quadrant take one 8-state group each
-          const float* eps = (st.epi == R_POST ? V.eps_post : V.eps_prior) + (trow + row) * S + c;
+          const float* eps = ((kHasPost && st.epi == R_POST) ? V.eps_post : V.eps_prior) + (trow + row) * S + c;
           ld_row8_v2<true>(pre, eps, S - c, row_ok && c < S);
           if ((st.flags & SF_WRITES_STATE) && V.nonterm && has_next && row_ok) pre_nt = __ldg(V.nonterm + trow + N + row);
-        } else if (st.epi == R_ACTION) {
+        } else if (kHasActor && st.epi == R_ACTION) {
           const int c = part * 8;
           const float* eps = V.eps_action + (trow + row) * A + c;
 #pragma unroll
@@ -826,7 +836,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         switch (st.epi) {
           case R_ACT_H: {
             // rounds of four chunks (one per warp of the quadrant); the next layer's MMAs start behind each round
-            const bool elu = st.act == ACT_ELU, addend = (st.flags & SF_ADDEND) != 0;
+            const bool elu = st.act == ACT_ELU, addend = kHasAddend && (st.flags & SF_ADDEND) != 0;
             const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
             const float* adrow = addend ? V.addend + (trow + row) * V.Hd : nullptr;
             // the activation / addend variant is chosen once per layer, not per chunk
@@ -848,17 +858,20 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             };
             using IC_ELU = std::integral_constant<int, ACT_ELU>;
             using IC_RELU = std::integral_constant<int, ACT_RELU>;
-            if (addend) {
-              if (elu) layer(IC_ELU{}, std::true_type{});
-              else layer(IC_RELU{}, std::true_type{});
-            } else {
+            if constexpr (kHasAddend) {
+              if (addend) {
+                if (elu) layer(IC_ELU{}, std::true_type{});
+                else layer(IC_RELU{}, std::true_type{});
+              }
+            }
+            if (!addend) {
               if (elu) layer(IC_ELU{}, std::false_type{});
               else layer(IC_RELU{}, std::false_type{});
             }
             handed = true;
           } break;
 
-          case R_ACT_DOT: {
+          case R_ACT_DOT: if constexpr (kHasActor) {
             const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
             const bool elu = st.act == ACT_ELU;
             const uint32_t wdot = bias + 4u * (nch * 16);   // the 1-output layer's weight row follows the bias
@@ -900,7 +913,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
           case R_POST: {
             // S <= 32 here (wider states run on the vm.cuh kernel): warp `part` of the quadrant owns states
             // [8 part, 8 part + 8) of its row — mean at acc [0,W), raw std at [W,2W)
-            const bool post = st.epi == R_POST;
+            const bool post = kHasPost && st.epi == R_POST;
             const int W = st.width;
             const int c = part * 8;
             const int nv = max(0, min(8, S - c));   // warp-uniform
@@ -1004,7 +1017,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             }
           } break;
 
-          case R_ACTION: {
+          case R_ACTION: if constexpr (kHasActor) {
             const int c = part * 8;   // A <= 16 here: warps 0 and 1 of the quadrant take 8 action dims each
             if (c < A) {
               const int W = st.width;
@@ -1036,7 +1049,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             }
           } break;
 
-          case R_SCALAR: {
+          case R_SCALAR: if constexpr (kHasActor) {
             if (part == 0) {
               float v[16];
               tmem_ld16(tacc, v);

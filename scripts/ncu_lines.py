@@ -14,7 +14,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep = sys.argv[1]
-fn = sys.argv[2] if len(sys.argv) > 2 else "_ZN2rb16rssm_rows_kernelENS_10RowsParamsE"
+fn = sys.argv[2] if len(sys.argv) > 2 else "_ZN2rb16rssm_rows_kernelILi1EEEvNS_10RowsParamsE"
 lib = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "repo_b200", "librepo_b200.so")
 
 with tempfile.TemporaryDirectory() as tmp:

@@ -13,7 +13,7 @@ from collections import Counter
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "repo_b200", "librepo_b200.so")
-fn = sys.argv[1] if len(sys.argv) > 1 else "_ZN2rb16rssm_rows_kernelENS_10RowsParamsE"
+fn = sys.argv[1] if len(sys.argv) > 1 else "_ZN2rb16rssm_rows_kernelILi1EEEvNS_10RowsParamsE"
 
 with tempfile.TemporaryDirectory() as tmp:
     subprocess.run(["cuobjdump", "-xelf", "all", LIB], cwd=tmp, check=True, capture_output=True)
