@@ -355,7 +355,7 @@ struct RBuilder {
   struct Seg { int src, n, dst; };
 
   void gemm(const float* w, int ld, std::initializer_list<Seg> segs, int n_pad, int col0, int ncols, int kofs, int ksl,
-            int a_src, int a_k16, int acc_col, int accumulate) {
+            int a_src, int a_k16, int acc_col, int accumulate, int init_cols = 0) {
     if (n_gemms >= kRMaxGemms || pack.n_jobs >= kMaxRowsJobs || n_pad > 256 || n_pad * 64 > kRSlotBytes) { overflow = true; return; }
     RGemm& g = P.gemms[n_gemms++];
     g.w_off16 = (uint32_t)(w_bytes / 16);
@@ -366,6 +366,7 @@ struct RBuilder {
     g.a_k16 = (uint8_t)a_k16;
     g.accumulate = (uint8_t)accumulate;
     g.acc_col = (uint16_t)acc_col;
+    g.init_cols = (uint16_t)init_cols;
     PackRowsJob& j = pack.jobs[pack.n_jobs++];
     j.w = w; j.ld = ld; j.col0 = col0; j.ncols = ncols; j.kofs = kofs; j.ksl = ksl; j.n_pad = n_pad;
     j.nseg = 0;
@@ -441,9 +442,10 @@ struct RBuilder {
       Wd = std::min(64, r16(D - u0));
       const int nu = std::min(Wd, D - u0);
       RStage& s = begin_stage();
-      gemm(W->rnn_w_ih, D, {{u0, nu, 0}, {D + u0, nu, Wd}, {2 * D + u0, nu, 2 * Wd}}, 3 * Wd, 0, D, 0, kD16, 1, 0, 0, 0);
-      gemm(W->rnn_w_hh, D, {{u0, nu, 0}, {D + u0, nu, Wd}}, 2 * Wd, 0, D, 0, kD16, 0, 0, 0, 1);
-      gemm(W->rnn_w_hh, D, {{2 * D + u0, nu, 0}}, Wd, 0, D, 0, kD16, 0, 0, 3 * Wd, 0);
+      // accumulator columns [i_n | r | z | h_n]: W_hh . b -> [r z h_n] first (X only: it can run before the embedding layer
+      // has finished), then W_ih . h -> [i_n r z] on top (its first MMA initialises the i_n columns)
+      gemm(W->rnn_w_hh, D, {{u0, nu, 0}, {D + u0, nu, Wd}, {2 * D + u0, nu, 2 * Wd}}, 3 * Wd, 0, D, 0, kD16, 0, 0, Wd, 0);
+      gemm(W->rnn_w_ih, D, {{2 * D + u0, nu, 0}, {u0, nu, Wd}, {D + u0, nu, 2 * Wd}}, 3 * Wd, 0, D, 0, kD16, 1, 0, 0, 1, Wd);
       bias_job(W->rnn_b_ih, u0, W->rnn_b_hh, u0, nu, Wd);
       bias_job(W->rnn_b_ih, D + u0, W->rnn_b_hh, D + u0, nu, Wd);
       bias_job(W->rnn_b_ih, 2 * D + u0, nullptr, 0, nu, Wd);
@@ -473,6 +475,15 @@ struct RBuilder {
       int back = 0;
       for (int j = 1; j < xdeps[i]; ++j) back += P.stages[((i - j) % n_stages + n_stages) % n_stages].rounds;
       P.stages[i].xback = (uint8_t)std::min(back, 255);
+    }
+    // The first GRU chunk's W_hh GEMM reads the belief slot of X, final since the previous step: it may start as soon as the
+    // previous stage's FIRST round has been signalled (by then every warp has left the stage before that one, including
+    // its post-hand-off use of free TMEM columns as a transpose buffer — the region those MMAs accumulate into).
+    for (int i = 0; i < n_stages; ++i) {
+      const RStage& s = P.stages[i];
+      const RStage& prev = P.stages[(i + n_stages - 1) % n_stages];
+      if (s.epi == R_GRU && s.unit0 == 0 && prev.epi == R_ACT_H && prev.rounds > 1 && n_stages > 2)
+        P.stages[i].xback = (uint8_t)(prev.rounds - 1);
     }
     int r0 = 0;
     for (int i = 0; i < n_stages; ++i) {

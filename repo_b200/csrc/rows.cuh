@@ -82,7 +82,8 @@ struct RGemm {            // acc[:, acc_col ..+n) (+)= A(128 x 16*ksl) * W(n x 1
   uint8_t a_k16;          // first k16 slab inside the source
   uint8_t accumulate;
   uint16_t acc_col;       // column offset inside the accumulator region
-  uint16_t pad;
+  uint16_t init_cols;     // != 0: the GEMM accumulates (accumulate = 1) except into its first init_cols columns, which its very
+                          // first MMA overwrites — that MMA is issued as two (N = init_cols fresh, N = n - init_cols accumulating)
 };
 struct RStage {
   uint8_t gemm_begin, gemm_end;
@@ -409,7 +410,9 @@ __device__ __forceinline__ float rows_act_chunk(uint32_t bias, uint32_t wdot, co
 #define RB_STAGE_END() do { } while (0)
 #endif
 
-// One chunk of GRU units (R_GRU).  accumulator: r at [0,W), z at [W,2W), i_n at [2W,3W), h_n at [3W,4W).
+// One chunk of GRU units (R_GRU).  accumulator: i_n at [0,W), r at [W,2W), z at [2W,3W), h_n at [3W,4W): W_hh . b goes into
+// [W,4W) as ONE N = 3W GEMM over X (it only reads the old belief, so the issuer runs it ahead of the layer that produces the
+// other operand), W_ih . h accumulates into [0,3W).  Bias vectors stay in the order r, z, i_n, h_n.
 // The stage is handed back as soon as the accumulators have left tensor memory, so the next chunk's MMAs run under the
 // gate math.  Holding all four gate accumulators (64 registers per thread) across that point spilled into every stage
 // of the kernel (hidden-layer epilogues 4.9k -> 10k cycles), so r * (W_hn b + b_hn) is folded before the hand-off:
@@ -417,7 +420,7 @@ __device__ __forceinline__ float rows_act_chunk(uint32_t bias, uint32_t wdot, co
 __device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uint8_t* scr, uint32_t scr_plane, uint32_t bar_xb,
                                                int D, uint32_t tacc, uint32_t bias, float* bel_row,
                                                uint32_t bar_handoff, uint32_t xb_parity, int r, int part, bool row_ok, int flags,
-                                               int W, int u0, int nu, long long* dbg = nullptr) {
+                                               int W, int u0, int nu, long long* dbg = nullptr, bool dbg_skip = false) {
 #ifdef RB_STAGE_CLOCK
 #define RB_GRU_STAMP(k) do { if (dbg) dbg[k] = clock64(); } while (0)
 #else
@@ -442,12 +445,12 @@ __device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uin
   float vt[16], vz[16];
   if (mine) {
     float vh[16];
-    tmem_ld16(tacc + c, vt);            // r
+    tmem_ld16(tacc + W + c, vt);        // r
     tmem_ld16(tacc + 3 * W + c, vh);    // h_n
     tmem_ld_wait();
     float vi[16];
-    tmem_ld16(tacc + W + c, vz);        // in flight under the r-gate math
-    tmem_ld16(tacc + 2 * W + c, vi);
+    tmem_ld16(tacc + 2 * W + c, vz);    // in flight under the r-gate math
+    tmem_ld16(tacc + c, vi);
     {
       float bb[16];
       ld_uni16(bb, bias + 4u * c);
@@ -470,6 +473,9 @@ __device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uin
     if ((threadIdx.x & 31) == 0) mbar_arrive(bar_handoff);
   }
   RB_GRU_STAMP(1);
+#ifdef RB_STAGE_CLOCK
+  if (dbg_skip && !last_chunk) return;   // profiling only (flag 32): no gate math under the next chunk's MMAs (results are garbage)
+#endif
   // Rest of the gate math in two halves of 8 units: new units go to beliefs[t] (fp32) and, split into fp16 hi/lo, either
   // to the scratch image of X (earlier chunks) or straight into X (last chunk: every chunk's MMAs are done, the belief
   // slot may be overwritten).
@@ -694,8 +700,14 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             const int nsl = min(per_slot, (int)gm.ksl - c0);
             // H-reading GEMMs trail the producing epilogue: k-slab k = features [16k, 16k+16) = chunk k = round k / 4
             if (gm.a_src == 1) wait_round(prev_first + min((kk + (uint32_t)nsl - 1u) >> 2, prev_rounds - 1u));
+#ifdef RB_STAGE_CLOCK
+            if ((V.dbg_flags & 64) && V.dbg_clock && blockIdx.x == 0 && t == 5 && lane == 0) V.dbg_clock[900 + s * 4 + 1] = clock64();   // inputs of this group ready (last one stays)
+#endif
             mbar_wait(bar_full + 8 * slot, phase);
             tc_fence_after();
+#ifdef RB_STAGE_CLOCK
+            if ((V.dbg_flags & 64) && V.dbg_clock && blockIdx.x == 0 && t == 5 && lane == 0) V.dbg_clock[900 + s * 4 + 2] = clock64();   // its weights have landed
+#endif
             if (elect_one()) {
               uint32_t wa = ring_a + slot * kRSlotBytes;
               int nsl_issue = nsl;
@@ -712,7 +724,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
                   umma_f16(d, a_hi, b_lo, idesc, 1u);
                 } else {
                   const uint32_t a_hi = th + (kk + j) * 16u, a_lo = a_hi + 8u;   // per k-slab: 8 hi columns, 8 lo columns
-                  umma_f16_ts(d, a_hi, b_hi, idesc, (j == 0) ? acc : 1u);
+                  if (j == 0 && c0 == 0 && gm.init_cols) {
+                    const uint32_t ic = gm.init_cols;
+                    umma_f16_ts(d, a_hi, b_hi, make_idesc_f16(128, ic), 0u);
+                    umma_f16_ts(d + ic, a_hi, b_hi + ic, make_idesc_f16(128, gm.n - ic), 1u);   // B rows are 16 bytes apart: + ic in the descriptor's address field
+                  } else
+                    umma_f16_ts(d, a_hi, b_hi, idesc, (j == 0) ? acc : 1u);
                   umma_f16_ts(d, a_lo, b_hi, idesc, 1u);
                   umma_f16_ts(d, a_hi, b_lo, idesc, 1u);
                 }
@@ -728,6 +745,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
         }
         if (elect_one()) umma_commit(bar_acc);
         __syncwarp();
+#ifdef RB_STAGE_CLOCK
+        if ((V.dbg_flags & 64) && V.dbg_clock && blockIdx.x == 0 && t == 5 && lane == 0) V.dbg_clock[900 + s * 4 + 3] = clock64();       // stage committed
+#endif
       }
     }
   } else if (warp < kRowsEpiWarp0) {
@@ -903,7 +923,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
                            bar_round + 8 * (ground0 & (kRoundBars - 1)), (uint32_t)(t & 1), r, part, row_ok, st.flags, st.width,
                            st.unit0, st.nfeat
 #ifdef RB_STAGE_CLOCK
-                           , (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5 && st.unit0 == 64) ? V.dbg_clock + 860 : nullptr
+                           , (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5 && st.unit0 == 64) ? V.dbg_clock + 860 : nullptr,
+                           (V.dbg_flags & 32) != 0
 #endif
                            );
             if (!last_chunk) handed = true;   // handed back right after the accumulators were read

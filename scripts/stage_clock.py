@@ -32,6 +32,7 @@ torch.cuda.synchronize()
 _lib.lib().repo_b200_debug_clock(None)
 b = buf.cpu().numpy()
 chunk = b[860:880].copy()
+issuer = b[900:900 + 4 * NS].copy()
 extra = b[600:600 + 64].copy()
 fine = b[700:700 + 8 * NS // 2 + 64].copy() if len(b) > 700 else None
 b[600:] = 0
@@ -57,6 +58,14 @@ if fine is not None and fine.any():
         f = fine[8 * s: 8 * s + 8]
         d = lambda a, c: int(f[c] - f[a]) if f[a] and f[c] else -1
         print(f"{names[s] if s < len(names) else s:>4}: wait_acc {d(0, 1):6d}  sync {d(1, 2):5d}  body {d(2, 3):6d}  (act_h loop {d(2, 5):6d} st_wait {d(5, 6):5d})  proxy_fence {d(3, 4):5d}")
+
+if issuer.any():
+    print("# MMA issuer (step 5), relative to the END of the previous stage's epilogue (warp 4): last k-slab group's inputs ready, its")
+    print("# weights landed, stage committed; then the epilogue's view: accumulators ready")
+    for s in range(nz):
+        prev_end = b[t, s - 1, 1] if s > 0 else b[t - 1, nz - 1, 1]
+        f = issuer[4 * s: 4 * s + 4]
+        print(f"{names[s] if s < len(names) else s:>4}: inputs_ready {int(f[1] - prev_end):7d}  weights_landed {int(f[2] - prev_end):7d}  committed {int(f[3] - prev_end):7d}  epilogue_begins {int(b[t, s, 0] - prev_end):7d}")
 
 if chunk.any():
     c = chunk[chunk != 0]
