@@ -507,6 +507,8 @@ struct RBuilder {
     P.v.bias = bb;
     P.n_rstages = n_stages;
     P.n_bias = n_bias;
+    // transposed beliefs[t] stores: 32 free TMEM columns behind the GRU's H operand (the embedding layer's output)
+    P.gru_tsc_col = (r16(P.v.D) + 8 * kEpiParts <= 256) ? r16(P.v.D) : -1;
     P.scr = wb + align_up_(w_bytes, 256) + align_up_((size_t)n_bias * sizeof(float), 256);
     P.scr_plane = (uint32_t)scr_plane();
     P.scr_slots = std::max(1, sm_count());

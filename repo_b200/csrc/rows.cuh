@@ -109,6 +109,7 @@ struct RowsParams {
   uint32_t scr_plane;    // bytes per plane (= ceil(D / 8) * kXLBO)
   int scr_slots;         // slots allocated (SMs whose %smid is not below this use the global re-read path)
   int rounds_per_step;   // sum of RStage::rounds over the program
+  int gru_tsc_col;       // R_GRU: first of 32 free TMEM columns behind the H operand (transposed beliefs[t] stores), or -1
   int n_bias;            // floats in the bias blob (<= kBiasCap: resident in shared memory)
   RStage stages[kRMaxStages];
   RGemm gemms[kRMaxGemms];
@@ -361,24 +362,25 @@ __device__ __forceinline__ float act_bf(float x) {
 // H is written IN PLACE: accumulator columns [16 ch, 16 ch + 16) of this thread's lane become the packed fp16 hi
 // pairs (8 columns) followed by the lo pairs (8 columns) of the same 16 features, so the region that held the
 // accumulators is the next layer's A operand and the region that held this layer's operand is free for its accumulators.
+// `tcol`, `bias`, `wdot`, `adrow` address THIS chunk (the callers step them from chunk to chunk in registers: recomputing
+// them from the chunk index cost ~50 instructions per chunk, a quarter of the issue-bound epilogue).
 template <int ACT, bool DOT, bool ADDEND>
-__device__ __forceinline__ float rows_act_chunk(uint32_t bias, uint32_t wdot, const float* adrow, uint32_t tacc,
-                                                int ch, int nfeat, bool row_ok) {
+__device__ __forceinline__ float rows_act_chunk(uint32_t bias, uint32_t wdot, const float* adrow, uint32_t tcol,
+                                                int n_valid, bool row_ok) {
   float v[16], bz[16];
-  const int f0 = ch * 16;
   float dot = 0.f;
-  tmem_ld16(tacc + f0, v);
-  ld_uni16(bz, bias + 4u * f0);
+  tmem_ld16(tcol, v);
+  ld_uni16(bz, bias);
   if (ADDEND) {
     float ad[16];
-    ld_row16(ad, adrow + f0, nfeat - f0, row_ok);
+    ld_row16(ad, adrow, n_valid, row_ok);
 #pragma unroll
     for (int i = 0; i < 16; ++i) bz[i] += ad[i];
   }
   tmem_ld_wait();
   if (DOT) {
     float w[16];
-    ld_uni16(w, wdot + 4u * f0);
+    ld_uni16(w, wdot);
 #pragma unroll
     for (int i = 0; i < 16; ++i) dot = fmaf(w[i], act_bf<ACT>(v[i] + bz[i]), dot);
   } else {
@@ -386,8 +388,8 @@ __device__ __forceinline__ float rows_act_chunk(uint32_t bias, uint32_t wdot, co
 #pragma unroll
     for (int i = 0; i < 16; i += 2)
       split2_f16(act_bf<ACT>(v[i] + bz[i]), act_bf<ACT>(v[i + 1] + bz[i + 1]), hi[i >> 1], lo[i >> 1]);
-    tmem_st8(tacc + f0, hi);
-    tmem_st8(tacc + f0 + 8, lo);
+    tmem_st8(tcol, hi);
+    tmem_st8(tcol + 8, lo);
   }
   return dot;
 }
@@ -401,8 +403,11 @@ __device__ __forceinline__ float rows_act_chunk(uint32_t bias, uint32_t wdot, co
 #ifdef RB_STAGE_CLOCK
 #define RB_STAMP(k) do { if (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5) V.dbg_clock[700 + s * 8 + (k)] = clock64(); } while (0)
 #define RB_STAMP_X(k) do { if (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5) V.dbg_clock[600 + s * 2 + (k)] = clock64(); } while (0)
-#define RB_STAGE_BEGIN() do { if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2] = clock64(); } while (0)
-#define RB_STAGE_END() do { if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2 + 1] = clock64(); } while (0)
+// (flag 64: also the first lane of EVERY epilogue warp at step 5 -> [1200 + warp * 64 + stage * 2 + {0, 1}]: which warp is last?)
+#define RB_STAGE_BEGIN() do { if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2] = clock64(); \
+    if ((V.dbg_flags & 64) && V.dbg_clock && blockIdx.x == 0 && lane == 0 && t == 5) V.dbg_clock[1200 + (et >> 5) * 64 + s * 2] = clock64(); } while (0)
+#define RB_STAGE_END() do { if (V.dbg_clock && blockIdx.x == 0 && et == 0) V.dbg_clock[(t * P.n_rstages + s) * 2 + 1] = clock64(); \
+    if ((V.dbg_flags & 64) && V.dbg_clock && blockIdx.x == 0 && lane == 0 && t == 5) V.dbg_clock[1200 + (et >> 5) * 64 + s * 2 + 1] = clock64(); } while (0)
 #else
 #define RB_STAMP(k) do { } while (0)
 #define RB_STAMP_X(k) do { } while (0)
@@ -420,7 +425,7 @@ __device__ __forceinline__ float rows_act_chunk(uint32_t bias, uint32_t wdot, co
 __device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uint8_t* scr, uint32_t scr_plane, uint32_t bar_xb,
                                                int D, uint32_t tacc, uint32_t bias, float* bel_row,
                                                uint32_t bar_handoff, uint32_t xb_parity, int r, int part, bool row_ok, int flags,
-                                               int W, int u0, int nu, long long* dbg = nullptr, bool dbg_skip = false) {
+                                               int W, int u0, int nu, uint32_t tsc, int rows_left, long long* dbg = nullptr, int dbg_skip = 0) {
 #ifdef RB_STAGE_CLOCK
 #define RB_GRU_STAMP(k) do { if (dbg) dbg[k] = clock64(); } while (0)
 #else
@@ -474,7 +479,7 @@ __device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uin
   }
   RB_GRU_STAMP(1);
 #ifdef RB_STAGE_CLOCK
-  if (dbg_skip && !last_chunk) return;   // profiling only (flag 32): no gate math under the next chunk's MMAs (results are garbage)
+  if ((dbg_skip & 1) && !last_chunk) return;   // profiling only (flag 32): no gate math under the next chunk's MMAs (results are garbage)
 #endif
   // Rest of the gate math in two halves of 8 units: new units go to beliefs[t] (fp32) and, split into fp16 hi/lo, either
   // to the scratch image of X (earlier chunks) or straight into X (last chunk: every chunk's MMAs are done, the belief
@@ -515,7 +520,32 @@ __device__ __forceinline__ void rows_gru_stage(uint32_t x_hi, uint32_t x_lo, uin
       RB_GRU_STAMP(2 + 3 * j);
       const int u = u0 + c + 8 * j;       // first unit of this half
       const int nval = min(8, u0 + nu - u);
-      if (row_ok && nval > 0) {
+#ifdef RB_STAGE_CLOCK
+      if ((dbg_skip & 2) && !last_chunk) continue;   // profiling only (flag 512): gate math but no global stores
+#endif
+      if (tsc != 0u && nval == 8) {
+        // beliefs[t] rows are D floats apart: a store with lane = row touches 32 cache lines per instruction, and the L1
+        // pipeline those stores occupy is the one the tensor core fetches its shared-memory operands through (profiling
+        // flag 512: without the stores a chunk's MMAs take 10.9k instead of 13k cycles, its gate math 4.5k instead of 7.7k).
+        // So the 32 x 8 block goes through 8 free TMEM columns (lane = row in, 16x256b fragments out): four neighbouring
+        // threads then hold 8 consecutive floats of one row — 8 rows x 32 bytes per store instruction.
+        tmem_st8f(tsc, bn);
+        tmem_st_wait();
+        const int ln = threadIdx.x & 31, cq = 2 * (ln & 3);
+        float tq[2][4];
+        tmem_ld_16x256b_x1(tsc, tq[0]);
+        tmem_ld_16x256b_x1(tsc + (16u << 16), tq[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+#pragma unroll
+          for (int rb = 0; rb < 2; ++rb) {
+            const int rr = 16 * hb + 8 * rb + (ln >> 2);   // row within this warp's 32
+            if (rr < rows_left)
+              *reinterpret_cast<float2*>(bel_row + (ptrdiff_t)(rr - ln) * D + u + cq) = make_float2(tq[hb][2 * rb], tq[hb][2 * rb + 1]);
+          }
+        }
+      } else if (row_ok && nval > 0) {
         float* dst = bel_row + u;
         if (nval == 8 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
           reinterpret_cast<float4*>(dst)[0] = make_float4(bn[0], bn[1], bn[2], bn[3]);
@@ -714,26 +744,35 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
 #ifdef RB_STAGE_CLOCK
               if (V.dbg_flags & 16) nsl_issue = 0;   // profiling only: no MMAs
 #endif
-              for (int j = 0; j < nsl_issue; ++j) {
-                const uint64_t b_hi = make_smem_desc(wa, w_lbo, 128);
-                const uint64_t b_lo = make_smem_desc(wa + w_lo, w_lbo, 128);
-                if (gm.a_src == 0) {
-                  const uint64_t a_hi = x_desc + (uint64_t)(kk + j) * kX_slab;
+              // Descriptors are built once per slot and stepped by adding to their address fields (14 bits of address / 16;
+              // shared memory ends below 2^18, so nothing carries into the stride fields): the MMA issue rate is set by this
+              // one thread's instruction chain — it shares its scheduler with four epilogue warps — so the per-MMA work is
+              // kept to the instruction itself plus two additions per k-slab.
+              uint64_t b_hi = make_smem_desc(wa, w_lbo, 128);
+              const uint64_t b_lo_delta = w_lo >> 4, b_step = slab_bytes >> 4;
+              if (gm.a_src == 0) {
+                uint64_t a_hi = x_desc + (uint64_t)kk * kX_slab;
+                for (int j = 0; j < nsl_issue; ++j) {
                   umma_f16(d, a_hi, b_hi, idesc, (j == 0) ? acc : 1u);
                   umma_f16(d, a_hi + x_lo_delta, b_hi, idesc, 1u);
-                  umma_f16(d, a_hi, b_lo, idesc, 1u);
-                } else {
-                  const uint32_t a_hi = th + (kk + j) * 16u, a_lo = a_hi + 8u;   // per k-slab: 8 hi columns, 8 lo columns
+                  umma_f16(d, a_hi, b_hi + b_lo_delta, idesc, 1u);
+                  a_hi += kX_slab;
+                  b_hi += b_step;
+                }
+              } else {
+                uint32_t a_hi = th + kk * 16u;   // per k-slab: 8 hi columns, 8 lo columns
+                for (int j = 0; j < nsl_issue; ++j) {
                   if (j == 0 && c0 == 0 && gm.init_cols) {
                     const uint32_t ic = gm.init_cols;
                     umma_f16_ts(d, a_hi, b_hi, make_idesc_f16(128, ic), 0u);
                     umma_f16_ts(d + ic, a_hi, b_hi + ic, make_idesc_f16(128, gm.n - ic), 1u);   // B rows are 16 bytes apart: + ic in the descriptor's address field
                   } else
                     umma_f16_ts(d, a_hi, b_hi, idesc, (j == 0) ? acc : 1u);
-                  umma_f16_ts(d, a_lo, b_hi, idesc, 1u);
-                  umma_f16_ts(d, a_hi, b_lo, idesc, 1u);
+                  umma_f16_ts(d, a_hi + 8u, b_hi, idesc, 1u);
+                  umma_f16_ts(d, a_hi, b_hi + b_lo_delta, idesc, 1u);
+                  a_hi += 16u;
+                  b_hi += b_step;
                 }
-                wa += slab_bytes;
               }
               umma_commit(bar_empty + 8 * slot);
             }
@@ -863,17 +902,26 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             auto layer = [&](auto act_tag, auto addend_tag) {
               constexpr int ACT = decltype(act_tag)::value;
               constexpr bool AD = decltype(addend_tag)::value;
-              for (int ch0 = 0; ch0 < nch; ch0 += kEpiParts) {
-                const int ch = ch0 + part;
-                if (ch < nch) {
-                  rows_act_chunk<ACT, false, AD>(bias, 0u, adrow, tacc, ch, nfeat, row_ok);
+              // per-chunk state stepped in registers; the empty asm keeps the compiler from re-deriving it from the chunk index
+              uint32_t tcol = tacc + 16u * part, baddr = bias + 64u * part, bar = ground0;
+              int left = nch - part;                       // this warp has a chunk in the round while left > 0
+              const float* ad = AD ? adrow + 16 * part : nullptr;
+              int nval = nfeat - 16 * part;
+              for (int rd = st.rounds; rd > 0; --rd) {
+                asm volatile("" : "+r"(tcol), "+r"(baddr), "+r"(bar), "+r"(left));
+                if (left > 0) {
+                  rows_act_chunk<ACT, false, AD>(baddr, 0u, ad, tcol, nval, row_ok);
                   tmem_st_wait();
                 }
-                if (ch0 + kEpiParts >= nch) {
+                if (rd == 1) {
                   RB_STAMP(3);
                   RB_STAGE_END();
                 }
-                signal_round(false, (uint32_t)ch0 / kEpiParts);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_round + 8 * (bar & (kRoundBars - 1)));
+                tcol += 16u * kEpiParts; baddr += 64u * kEpiParts; ++bar; left -= kEpiParts;
+                if (AD) { ad += 16 * kEpiParts; nval -= 16 * kEpiParts; }
               }
             };
             using IC_ELU = std::integral_constant<int, ACT_ELU>;
@@ -897,9 +945,11 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             const uint32_t wdot = bias + 4u * (nch * 16);   // the 1-output layer's weight row follows the bias
             float dot = 0.f;
             if (elu) {
-              for (int ch = part; ch < nch; ch += kEpiParts) dot += rows_act_chunk<ACT_ELU, true, false>(bias, wdot, nullptr, tacc, ch, nfeat, row_ok);
+              for (int ch = part; ch < nch; ch += kEpiParts)
+                dot += rows_act_chunk<ACT_ELU, true, false>(bias + 64u * ch, wdot + 64u * ch, nullptr, tacc + 16u * ch, 16, row_ok);
             } else {
-              for (int ch = part; ch < nch; ch += kEpiParts) dot += rows_act_chunk<ACT_RELU, true, false>(bias, wdot, nullptr, tacc, ch, nfeat, row_ok);
+              for (int ch = part; ch < nch; ch += kEpiParts)
+                dot += rows_act_chunk<ACT_RELU, true, false>(bias + 64u * ch, wdot + 64u * ch, nullptr, tacc + 16u * ch, 16, row_ok);
             }
             handoff(false);   // the accumulators are consumed; nothing in X / H changes
             if (part) sts_f(scratch + 4u * (part * 128 + r), dot);
@@ -921,10 +971,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             }
             rows_gru_stage(x_hi, x_lo, scr, P.scr_plane, bar_xb, D, tacc, bias, V.beliefs + (trow + row) * D,
                            bar_round + 8 * (ground0 & (kRoundBars - 1)), (uint32_t)(t & 1), r, part, row_ok, st.flags, st.width,
-                           st.unit0, st.nfeat
+                           st.unit0, st.nfeat,
+                           (P.gru_tsc_col >= 0 && (D & 1) == 0) ? tl + ((st.regs & 2) ? kAccCol : 0u) + (uint32_t)P.gru_tsc_col + 8u * part : 0u,
+                           N - (row0 + q * 32)
 #ifdef RB_STAGE_CLOCK
                            , (V.dbg_clock && blockIdx.x == 0 && et == 0 && t == 5 && st.unit0 == 64) ? V.dbg_clock + 860 : nullptr,
-                           (V.dbg_flags & 32) != 0
+                           ((V.dbg_flags & 32) ? 1 : 0) | ((V.dbg_flags & 512) ? 2 : 0)
 #endif
                            );
             if (!last_chunk) handed = true;   // handed back right after the accumulators were read

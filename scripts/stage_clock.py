@@ -25,7 +25,7 @@ _lib.lib().repo_b200_debug_flags(int(os.environ.get('RB_DBG', '0')))
 ops.imagine_fwd(*a, row_tile=128)
 torch.cuda.synchronize()
 NS = 32
-buf = torch.zeros(14 * NS * 2 + 256, dtype=torch.int64, device=dev)
+buf = torch.zeros(14 * NS * 2 + 256 + 1200, dtype=torch.int64, device=dev)
 _lib.lib().repo_b200_debug_clock(C.c_void_p(buf.data_ptr()))
 ops.imagine_fwd(*a, row_tile=128)
 torch.cuda.synchronize()
@@ -33,6 +33,7 @@ _lib.lib().repo_b200_debug_clock(None)
 b = buf.cpu().numpy()
 chunk = b[860:880].copy()
 issuer = b[900:900 + 4 * NS].copy()
+perwarp = b[1200:1200 + 16 * 64].copy().reshape(16, 32, 2)
 extra = b[600:600 + 64].copy()
 fine = b[700:700 + 8 * NS // 2 + 64].copy() if len(b) > 700 else None
 b[600:] = 0
@@ -66,6 +67,13 @@ if issuer.any():
         prev_end = b[t, s - 1, 1] if s > 0 else b[t - 1, nz - 1, 1]
         f = issuer[4 * s: 4 * s + 4]
         print(f"{names[s] if s < len(names) else s:>4}: inputs_ready {int(f[1] - prev_end):7d}  weights_landed {int(f[2] - prev_end):7d}  committed {int(f[3] - prev_end):7d}  epilogue_begins {int(b[t, s, 0] - prev_end):7d}")
+
+if perwarp.any():
+    print("# per epilogue warp (step 5): epilogue END of each stage relative to warp 4's (quadrant = warp % 4, part = warp // 4);")
+    print("# rows = stages, columns = warps 0..15 of the epilogue (quadrant-major within a part)")
+    for s in range(nz):
+        ref = b[t, s, 1]
+        print(f"{names[s] if s < len(names) else s:>4}: " + " ".join(f"{int(perwarp[w, s, 1] - ref):6d}" for w in range(16)))
 
 if chunk.any():
     c = chunk[chunk != 0]
