@@ -394,6 +394,9 @@ __device__ __forceinline__ float rows_act_chunk(uint32_t bias, uint32_t wdot, co
   return dot;
 }
 
+// (A leading quarter-chunk round — chunk 0 split over the four warps of a quadrant, so that the next layer's first k-slab is
+// ready ~300 instead of ~850 cycles into the epilogue — was measured as well: the layer period went from 6.45k to 6.95k
+// cycles; the MMAs of the last, now four-chunk, round trail the epilogue instead.)
 // (Splitting the 13th chunk of a 208-wide layer four ways, so that no warp of a quadrant takes 4 chunks against 3, was
 // measured: slower, 6.5k against 5.5k cycles per layer — the four warps share one scheduler, which is what limits them, and
 // the quarter pieces add instructions plus a quadrant barrier for the in-place rewrite.)
@@ -692,6 +695,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
     // ================================ MMA issuer ================================
     // Hand-off rounds are numbered globally (round 0 = the initial staging of X; then every stage's rounds in program
     // order) and complete in order; `consumed` = how many this warp has observed.  Waits are lazy but never skip a round.
+    // (An mbarrier wait answers ~160 cycles after it is issued even when the phase completed long ago — scripts/ubench/
+    // sync_lat.cu — and a k-slab group needs up to two: ~1.7k cycles per 13-slab layer.  Firing non-blocking test_waits for
+    // the NEXT round / ring slot ahead of a group's MMAs was measured: slower, 4.37 against 4.24 ms — the barrier unit
+    // serialises them, so they delay the MMAs instead of hiding behind them.)
     uint32_t slot = 0, phase = 0, consumed = 0, next_round = 1;
     auto wait_round = [&](uint32_t idx) {
       while (consumed <= idx) {
