@@ -6,7 +6,14 @@ dreamer.py:286-289, 356-359, 370-373 and repo.py:87-96; torch defaults: betas (0
 * the data-parallel exchange is ONE `all_reduce` on the gradient bucket, no packing pass,
 * clip + Adam are two kernels over contiguous memory instead of per-tensor launches and a `.item()`.
 `state_dict()` / `load_state_dict()` keep torch.optim.Adam's layout (per-parameter `exp_avg`, `exp_avg_sq`,
-`step`) so the reference's checkpoints (dreamer.py:501-542) round-trip."""
+`step`) so the reference's checkpoints (dreamer.py:501-542) round-trip.
+
+One deviation: the step counter (bias correction) is ONE per bucket, advanced by every `step()`, whereas
+torch.optim.Adam keeps it per parameter and skips parameters whose `.grad` is None.  They differ only for a parameter
+that sat out some steps — in the reference that is TIA's distractor reward head, which has no gradient in phase 1 of
+the very first iteration (tia.py:150-201), so its count lags the others by one for the whole run (bias correction
+1 - 0.9^(n-1) instead of 1 - 0.9^n: 26 % on its first update, < 1e-4 after 90 steps).  `load_state_dict` takes the
+largest per-parameter count of a checkpoint and warns when they are not all equal."""
 from __future__ import annotations
 
 import ctypes as C
@@ -105,6 +112,7 @@ class FlatAdam:
         return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
+        steps = []
         for i, (p, off) in enumerate(zip(self.params, self.offsets)):
             st = sd["state"].get(i)
             if st is None:
@@ -112,6 +120,12 @@ class FlatAdam:
             n = p.numel()
             self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
             self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
-            self.step_count = int(float(st["step"]))
+            steps.append(int(float(st["step"])))
+        if steps:
+            if min(steps) != max(steps):
+                import warnings
+                warnings.warn(f"FlatAdam keeps one step count per bucket; the checkpoint has per-parameter counts "
+                              f"{min(steps)}..{max(steps)} — using {max(steps)} for all of them")
+            self.step_count = max(steps)
         g = sd["param_groups"][0]
         self.lr, self.betas, self.eps = g["lr"], tuple(g["betas"]), g["eps"]

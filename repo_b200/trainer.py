@@ -185,7 +185,16 @@ class Agent:
         """Capture `train_dynamics` and `train_actor_critic` (optimiser steps included) for batches shaped like the
         example; returns (wm_step, ac_step): `beliefs, states = wm_step(obs, actions, rewards, nonterms)` and
         `ac_step(beliefs.flatten(0, 1), states.flatten(0, 1))`, each ONE graph launch.  Outputs and `self.logs`
-        entries are static tensors overwritten by every replay."""
+        entries are static tensors overwritten by every replay.
+
+        Side effect: capture needs warm-up runs on a side stream, so building the graphs APPLIES four real updates on the
+        example batch (three warm-up calls + the captured one: parameters, Adam moments, step counters and `log_beta`
+        all move; twice that for TIA's two optimiser phases).  Pass a real batch, or snapshot `state_dict()`s around the
+        call if the example must not train.  The optional Dreamer heads select rows with a boolean mask (a host
+        synchronisation) and cannot be captured: `disag_model` / `inv_dynamics` raise here."""
+        if self.c.disag_model or self.c.inv_dynamics:
+            raise RuntimeError("Agent.graphed: the disag_model / inv_dynamics heads index by a boolean mask and cannot be "
+                               "captured in a CUDA graph; run those configurations eagerly")
         from .graphs import GraphedStep
         self.optimizers()
         wm = GraphedStep(lambda o, a, r, n: self.train_dynamics(o, a, r, n), [obs, actions, rewards, nonterms])
