@@ -31,8 +31,9 @@ HORIZON = 15
 # From the committed `ncu --set full` capture of this kernel at the bench shape (profiles/NCU_CAPTURE below): DRAM traffic of one
 # launch (dram__bytes_read.sum + dram__bytes_write.sum) and the tensor-pipe activity.  ncu cannot run inside a timed bench, so
 # these are constants tied to that file; everything else in `roofline` is measured live.
-NCU_CAPTURE = {"file": "profiles/r01_rssm_rows_kernel_75776x14_ncu_full.txt", "rows": 75776,
-               "traffic_bytes": 245_965_056 + 1_218_886_000, "tensor_pipe_active_pct": 36.9}
+NCU_CAPTURE = {"file": "profiles/r02_rssm_rows_kernel_75776x14_ncu_full.txt", "rows": 75776,
+               "traffic_bytes": 235_469_312 + 1_442_514_000, "tensor_pipe_active_pct": 54.5,
+               "l2_to_sm_bytes": 27_600_537_000, "kernel_ms_under_ncu": 4.177}
 MMA_ISSUE_FACTOR = 3.3   # tensor-pipe MACs issued per algorithmic MAC: 3 fp16 products per fp32-grade product x ~1.1 K/N padding
 DIMS = dict(belief=200, state=30, action=6, hidden=200, embed=1024)
 SWEEP_ROWS = (16384, 65536, 262144, 1048576)   # SURVEY 8(d) Config 5: total start states, split evenly over the GPUs
@@ -533,6 +534,7 @@ def run_gpu(a):
                      "kernel_ms_how": "CUDA events around a.steps back-to-back launches with pre-packed weights, on the launching stream",
                      "algorithmic_flop_per_step": FLOP_PER_STEP, "algorithmic_bytes_per_step": BYTES_PER_STEP,
                      "mma_issue_factor": MMA_ISSUE_FACTOR, "tensor_pipe_active_pct_ncu": NCU_CAPTURE["tensor_pipe_active_pct"],
+                     "l2_to_sm_bytes_ncu": NCU_CAPTURE["l2_to_sm_bytes"],
                      "tensor_pipe_busy_estimate": achieved_tf * MMA_ISSUE_FACTOR / 2250.0,
                      "hbm_gbs_achieved": N * T * BYTES_PER_STEP / (kernel_ms / 1e3) / 1e9, "hbm_peak_gbs": peak_gbs,
                      "peak_source": peak_src,

@@ -24,6 +24,10 @@ KEYS = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
     "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
     "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    # L2 -> SM traffic and local-memory (spill) instructions: what the round-1 review asked to see next to lts__throughput
+    "lts__t_bytes.sum", "lts__t_bytes.sum.per_second", "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+    "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
