@@ -15,6 +15,8 @@ from tests import _cases as C
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL = 1e-3, 1e-5
+# Gradient checks below: element-wise rtol 1e-3 (2e-3 where a 100-sample Monte-Carlo entropy or the lambda-return scan is
+# in the chain) with an absolute floor of 2e-5 .. 1e-4 x the tensor's largest entry — ten times tighter than round 1.
 
 
 @pytest.fixture(scope="module")
@@ -209,7 +211,7 @@ def test_linear_building_block(ops, dev):
         w = torch.randn(out_f, in_f, generator=g) / in_f ** 0.5
         b = torch.randn(out_f, generator=g)
         want = (x.double() @ w.double().t() + b.double()).float()
-        close(ops.linear(x.to(dev), w.to(dev), b.to(dev)), want, f"linear {rows}x{in_f}x{out_f}", atol=2e-4)
+        close(ops.linear(x.to(dev), w.to(dev), b.to(dev)), want, f"linear {rows}x{in_f}x{out_f}", atol=2e-5)
 
 
 def test_empty_and_degenerate_sizes(ops, dev):
@@ -356,10 +358,10 @@ def test_observe_backward_matches_autograd_of_the_oracle(dev, name):
             assert got[k] is None or float(got[k].abs().max()) == 0.0
             continue
         scale = float(w.abs().max()) + 1e-12
-        np.testing.assert_allclose(got[k].cpu().double().numpy() / scale, w.numpy() / scale, rtol=1e-3, atol=2e-4, err_msg=k)
+        np.testing.assert_allclose(got[k].cpu().double().numpy() / scale, w.numpy() / scale, rtol=1e-3, atol=2e-5, err_msg=k)
     if with_obs:
         scale = float(want_emb.abs().max())
-        np.testing.assert_allclose(emb.grad.cpu().double().numpy() / scale, want_emb.numpy() / scale, rtol=1e-3, atol=2e-4)
+        np.testing.assert_allclose(emb.grad.cpu().double().numpy() / scale, want_emb.numpy() / scale, rtol=1e-3, atol=2e-5)
 
 
 def test_observe_backward_large_batch_embedding_gradient(dev):
@@ -386,7 +388,7 @@ def test_observe_backward_large_batch_embedding_gradient(dev):
     for k in big:
         want = (halves[0][0][k] + halves[1][0][k]).cpu()
         scale = float(want.abs().max()) + 1e-12
-        np.testing.assert_allclose(big[k].cpu().numpy() / scale, want.numpy() / scale, rtol=1e-3, atol=2e-4, err_msg=k)
+        np.testing.assert_allclose(big[k].cpu().numpy() / scale, want.numpy() / scale, rtol=1e-3, atol=2e-5, err_msg=k)
 
 
 def test_frozen_parameters_get_no_gradient(dev):
@@ -446,7 +448,7 @@ def test_imagine_backward_matches_autograd_of_the_oracle(dev, name):
 
     def cmp(got, want, nm):
         scale = float(want.abs().max()) + 1e-12
-        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=1e-3, atol=3e-4, err_msg=nm)
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=1e-3, atol=3e-5, err_msg=nm)
 
     for k, w in a64.items():
         cmp(dict(pol.named_parameters())[k].grad, w.grad, "actor." + k)
@@ -496,7 +498,7 @@ def test_heads_actor_entropy_under_autograd(dev, N):
 
     def cmp(got, want, nm):
         scale = float(want.abs().max()) + 1e-12
-        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-4, err_msg=nm)
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-5, err_msg=nm)
 
     for k, w in pr64.items():
         cmp(dict(rm.named_parameters())[k].grad, w.grad, "reward." + k)
@@ -561,11 +563,11 @@ def test_train_actor_critic_matches_reference_trainer(dev):
     for k, p in actor.named_parameters():
         w = g["actor_grad_" + k]
         scale = np.abs(w).max() + 1e-12
-        np.testing.assert_allclose(p.grad.cpu().numpy() / scale, w / scale, rtol=2e-3, atol=1e-3, err_msg="actor " + k)
+        np.testing.assert_allclose(p.grad.cpu().numpy() / scale, w / scale, rtol=2e-3, atol=1e-4, err_msg="actor " + k)
     for k, p in value.named_parameters():
         w = g["value_grad_" + k]
         scale = np.abs(w).max() + 1e-12
-        np.testing.assert_allclose(p.grad.cpu().numpy() / scale, w / scale, rtol=2e-3, atol=1e-3, err_msg="value " + k)
+        np.testing.assert_allclose(p.grad.cpu().numpy() / scale, w / scale, rtol=2e-3, atol=1e-4, err_msg="value " + k)
     for p in list(tm.parameters()) + list(reward.parameters()):
         assert p.grad is None  # frozen at call time (dreamer.py:306,315)
 
@@ -687,7 +689,7 @@ def test_conditional_imagine_backward_matches_autograd(dev):
 
     def cmp(got, want, nm):
         scale = float(want.abs().max()) + 1e-12
-        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-4, err_msg=nm)
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-5, err_msg=nm)
 
     for k, w in p64.items():
         if "posterior" in k:
@@ -728,12 +730,12 @@ def test_symbolic_encoder_and_observation_model(dev, rows):
     bg, sg = b.to(dev).requires_grad_(True), s.to(dev).requires_grad_(True)
     o = dec(bg, sg)
     (o * Rd.to(dev)).sum().backward()
-    close(e, ye.detach().float(), "symbolic embedding", atol=2e-4)
-    close(o, yd.detach().float(), "symbolic reconstruction", atol=2e-4)
+    close(e, ye.detach().float(), "symbolic embedding", atol=2e-5)
+    close(o, yd.detach().float(), "symbolic reconstruction", atol=2e-5)
 
     def cmp(got, want, nm):
         scale = float(want.abs().max()) + 1e-12
-        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-4, err_msg=nm)
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-5, err_msg=nm)
 
     for mod, P, tag in ((enc, Pe, "enc."), (dec, Pd, "dec.")):
         for k, w in P.items():
@@ -773,11 +775,11 @@ def test_disagreement_ensemble_and_inverse_dynamics_heads(dev):
     assert pred.shape == (E, rows, D)
     loss = (0.5 * (pred - nb.to(dev)) ** 2).sum(2).sum(0).mean()
     loss.backward()
-    close(pred, pred64.detach().float(), "ensemble prediction", atol=3e-4)
+    close(pred, pred64.detach().float(), "ensemble prediction", atol=3e-5)
 
     def cmp(got, want, nm):
         scale = float(want.abs().max()) + 1e-12
-        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-4, err_msg=nm)
+        np.testing.assert_allclose(got.cpu().double().numpy() / scale, want.numpy() / scale, rtol=2e-3, atol=5e-5, err_msg=nm)
 
     for k, w in P.items():
         cmp(dict(ens.named_parameters())[k].grad, w.grad, "ensemble " + k)
@@ -791,8 +793,8 @@ def test_disagreement_ensemble_and_inverse_dynamics_heads(dev):
     (-torch.distributions.Independent(torch.distributions.Normal(m64, sd64), 1).log_prob(a.double()).mean()).backward()
     m, sd = inv(b.to(dev), s.to(dev), nb.to(dev))
     (-torch.distributions.Independent(torch.distributions.Normal(m, sd), 1).log_prob(a.to(dev)).mean()).backward()
-    close(m, m64.detach().float(), "inverse-dynamics mean", atol=3e-4)
-    close(sd, sd64.detach().float(), "inverse-dynamics std", atol=3e-4)
+    close(m, m64.detach().float(), "inverse-dynamics mean", atol=3e-5)
+    close(sd, sd64.detach().float(), "inverse-dynamics std", atol=3e-5)
     for k, w in Q.items():
         cmp(dict(inv.named_parameters())[k].grad, w.grad, "inverse dynamics " + k)
 

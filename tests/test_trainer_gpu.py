@@ -13,6 +13,11 @@ from tests import _cases as C
 
 pytestmark = pytest.mark.gpu
 
+# Gradients: element-wise rtol 1e-3 with an absolute floor of GRAD_ATOL x the tensor's largest entry (the reference's own
+# fp32 CPU reductions over 2,450 rows carry ~1e-6 of that scale per element).  Exemption: the actor gradients through the
+# 100-sample entropy estimate and the lambda-return scan (floor 10 x GRAD_ATOL).
+GRAD_ATOL = float(__import__("os").environ.get("GRAD_ATOL", "3e-5"))
+
 
 @pytest.mark.parametrize("algo", ["dreamer", "repo", "tia"])
 def test_train_dynamics_matches_reference_trainer(algo):
@@ -61,7 +66,7 @@ def test_train_dynamics_matches_reference_trainer(algo):
             if want.shape != got.shape:
                 got = got.reshape(-1)[::97]
             scale = np.abs(want).max() + 1e-30
-            np.testing.assert_allclose(got / scale, want / scale, rtol=1e-3, atol=1e-3, err_msg=key)
+            np.testing.assert_allclose(got / scale, want / scale, rtol=1e-3, atol=GRAD_ATOL, err_msg=key)
             checked += 1
     # encoder, transition model, decoder, reward head (+ TIA: distractor RSSM, two more decoders, mask head)
     assert checked == 8 + 14 + 10 + 8 + ((14 + 10 + 10 + 2) if algo == "tia" else 0)
@@ -185,7 +190,7 @@ def test_degenerate_batches():
         assert torch.isfinite(p).all()
 
 
-def _cmp_grads(g, prefix, module, rtol=1e-3, atol=1e-3):
+def _cmp_grads(g, prefix, module, rtol=1e-3, atol=GRAD_ATOL):
     n = 0
     for name, p in module.named_parameters():
         want = g[f"{prefix}_grad_{name}"]
@@ -236,7 +241,7 @@ def test_optional_heads_match_reference_trainer():
                              eps_prior=y["eps_prior"].to(dev), eps_entropy=eps_ent.to(dev), eps_disag=eps_disag.to(dev), step=False)
     for k in ("actor_loss", "value_loss", "action_entropy", "latent_entropy", "disagreement"):
         np.testing.assert_allclose(agent.logs["train/" + k].item(), g["log_" + k], rtol=1e-3, atol=1e-5, err_msg=k)
-    assert _cmp_grads(g, "actor", agent.actor_model, rtol=2e-3, atol=2e-3) == 10
+    assert _cmp_grads(g, "actor", agent.actor_model, rtol=1e-3, atol=10 * GRAD_ATOL) == 10
     assert all(p.grad is None for p in agent.disag_model.parameters())      # frozen inside the bonus (dreamer.py:332)
 
 
