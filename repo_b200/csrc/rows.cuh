@@ -698,7 +698,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
     // (An mbarrier wait answers ~160 cycles after it is issued even when the phase completed long ago — scripts/ubench/
     // sync_lat.cu — and a k-slab group needs up to two: ~1.7k cycles per 13-slab layer.  Firing non-blocking test_waits for
     // the NEXT round / ring slot ahead of a group's MMAs was measured: slower, 4.37 against 4.24 ms — the barrier unit
-    // serialises them, so they delay the MMAs instead of hiding behind them.)
+    // serialises them, so they delay the MMAs instead of hiding behind them.  A scout warp doing all the waiting and
+    // publishing "k-slab groups ready" as a shared-memory word the issuer polls with ld.acquire (~30 cycles) was built and
+    // measured too: correct, 138.6k against 133.8k cycles per step — its and the issuer's spinning cost the epilogue warps
+    // on their schedulers more than the shorter waits gave back.)
     uint32_t slot = 0, phase = 0, consumed = 0, next_round = 1;
     auto wait_round = [&](uint32_t idx) {
       while (consumed <= idx) {
