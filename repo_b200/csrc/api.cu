@@ -617,15 +617,21 @@ bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
 }  // namespace
 int conv_gemm_impl(const void* input_, const float* w_mat, int w_ld, int w_col0, const float* bias, const void* relu_mask_,
                    const float* scales, void* out_, int frames, int n_total, ConvMap cm, int hl_flags, const int* dense_opts,
-                   void* ws, size_t ws_bytes, cudaStream_t st);
+                   void* ws, size_t ws_bytes, cudaStream_t st, int out_tile_rows = 0);
 extern "C" size_t repo_b200_conv_workspace_bytes(int K, int n_total);
 namespace {
 
 // y = x @ W[:, w_col0 : w_col0 + in_f]^T + b for row-major operands.  From 256 rows (and 16-byte aligned, 4-float
 // strided operands) this is one launch of the tcgen05 conv kernel run as a plain GEMM (K streams through its ring, so
 // the 1024-wide embedding projection keeps 128-row tiles); below that the vm machine's one-step program.
+// out_tile_rows > 0: the output goes out in the tiled layout of ConvParams::out_tile_rows (conv path only: the caller checks
+// linear_tiled_ok first).
+bool linear_tiled_ok(const float* x, int x_ld, int rows, int in_f, int out_f, size_t ws_bytes) {
+  return rows >= 256 && !(reinterpret_cast<uintptr_t>(x) & 15) && !(x_ld & 3) && !(in_f & 3) && !(out_f & 3) &&
+         ws_bytes >= repo_b200_conv_workspace_bytes(in_f, out_f) && !(g_dbg_flags & 256);
+}
 int run_linear(const float* x, int x_ld, int rows, int in_f, const float* w, int w_ld, int w_col0, const float* b,
-               int out_f, float* y, int y_ld, void* ws, size_t ws_bytes, int row_tile, cudaStream_t st) {
+               int out_f, float* y, int y_ld, void* ws, size_t ws_bytes, int row_tile, cudaStream_t st, int out_tile_rows = 0) {
   const bool aligned = !(reinterpret_cast<uintptr_t>(x) & 15) && !(reinterpret_cast<uintptr_t>(y) & 15) && !(x_ld & 3) &&
                        !(y_ld & 3) && !(in_f & 3);
   if (rows >= 256 && row_tile == 0 && aligned && ws_bytes >= repo_b200_conv_workspace_bytes(in_f, out_f) && !(g_dbg_flags & 256)) {
@@ -633,8 +639,9 @@ int run_linear(const float* x, int x_ld, int rows, int in_f, const float* w, int
     cm.RA = cm.RB = 1; cm.C = in_f; cm.pix = x_ld; cm.H = cm.W = 1; cm.TH = cm.TW = 1; cm.ntaps = 1;
     cm.sy = cm.sx = cm.dy = cm.dx = 1; cm.Ho = cm.Wo = 1; cm.osy = cm.osx = 1;
     const int opts[4] = {0, 0, y_ld != out_f ? y_ld : 0, 0};
-    return conv_gemm_impl(x, w, w_ld, w_col0, b, nullptr, nullptr, y, rows, out_f, cm, 0, opts, ws, ws_bytes, st);
+    return conv_gemm_impl(x, w, w_ld, w_col0, b, nullptr, nullptr, y, rows, out_f, cm, 0, opts, ws, ws_bytes, st, out_tile_rows);
   }
+  if (out_tile_rows) return fail(-1, "linear: tiled output needs the GEMM path");
   if (in_f < 1 || in_f > 1900) return fail(-1, "linear: in_features %d unsupported (1..1900)", in_f);
   if (out_f < 1 || out_f > 128 * 8) return fail(-1, "linear: out_features %d unsupported (1..1024)", out_f);
   Builder bl;
@@ -957,7 +964,7 @@ size_t repo_b200_conv_workspace_bytes(int K, int n_total) {
 // w_mat: (n_total, K) window of a row-major matrix with row stride w_ld (0 = K) starting at column w_col0
 int conv_gemm_impl(const void* input_, const float* w_mat, int w_ld, int w_col0, const float* bias, const void* relu_mask_,
                    const float* scales, void* out_, int frames, int n_total, ConvMap cm, int hl_flags, const int* dense_opts,
-                   void* ws, size_t ws_bytes, cudaStream_t st) {
+                   void* ws, size_t ws_bytes, cudaStream_t st, int out_tile_rows) {
   const float* input = static_cast<const float*>(input_);
   const float* relu_mask = static_cast<const float*>(relu_mask_);
   float* out = static_cast<float*>(out_);
@@ -1021,6 +1028,9 @@ int conv_gemm_impl(const void* input_, const float* w_mat, int w_ld, int w_col0,
     if ((P.out_ld && (P.out_ld < n_total || (P.out_ld & 3))) || (P.mask_ld && (P.mask_ld < n_total || (P.mask_ld & 3))))
       return fail(-1, "conv: row strides must be multiples of 4 and >= n_total");
   }
+  P.out_tile_rows = out_tile_rows;
+  if (out_tile_rows && (cm.RA != 1 || cm.RB != 1 || cm.Ho != 1 || cm.Wo != 1 || cm.shuffle || cm.out_nchw || hl_flags || P.out_ld || (n_total & 3)))
+    return fail(-1, "conv: tiled output is for plain fp32 GEMM maps with n_total % 4 == 0 only");
   P.kc16 = P.NP <= 128 ? 4 : 2;
   P.stage_bytes = conv_stage_bytes(P.kc16, P.NP);
   const int n_ent = conv_table_entries(cm, P.k16, P.in_hl);
@@ -1373,7 +1383,8 @@ size_t repo_b200_observe_workspace_bytes(const repo_b200_dims* d, int t1, int ba
   if (check_dims(d)) return 0;
   const size_t main = observe_main_bytes(d);
   const size_t lin = align_up(repo_b200_linear_workspace_bytes(d->embed, d->hidden), 256);
-  const size_t addend = align_up((size_t)std::max(t1, 0) * std::max(batch, 0) * d->hidden * sizeof(float), 256);
+  // row-major (t1 * batch, hidden), or the rows kernel's tiled layout: batch padded to 128-row tiles, hidden to 16
+  const size_t addend = align_up((size_t)std::max(t1, 0) * cdiv(std::max(batch, 0), 128) * 128 * r16(d->hidden) * sizeof(float), 256);
   return main + lin + addend;
 }
 
@@ -1410,13 +1421,16 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
     b.P.stash_ld = 5 * d->belief + 2 * d->hidden;
   }
   float* addend = reinterpret_cast<float*>(base + main + lin);
+  bool addend_tiled = false;
   if (with_obs) {
     // hoisted, non-recurrent half of the posterior layer: all (t, b) rows in one pass
+    addend_tiled = rows && linear_tiled_ok(embeds, d->embed, t1 * batch, d->embed, d->hidden, lin);
     rc = run_linear(embeds, d->embed, t1 * batch, d->embed, W->fc_embed_belief_posterior_w, d->belief + d->embed,
-                    d->belief, nullptr, d->hidden, addend, d->hidden, base + main, lin, 0, st);
+                    d->belief, nullptr, d->hidden, addend, d->hidden, base + main, lin, 0, st, addend_tiled ? batch : 0);
     if (rc) return rc;
   }
   VmParams& P = rows ? rbld.P.v : b.P;
+  P.addend_tiled = addend_tiled ? 1 : 0;
   P.n_steps = t1;
   P.N = batch;
   P.min_std = min_std;

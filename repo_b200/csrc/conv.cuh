@@ -47,6 +47,10 @@ struct ConvParams {
   // mask can be column windows of wider row-major matrices (the activation stash)
   int act_elu, mask_elu;
   int out_ld, mask_ld;
+  // plain fp32 GEMM maps only: rows are (step, row-in-step) with out_tile_rows rows per step, and the output is stored per
+  // 128-row tile of a step as [chunk of 16 features][quarter][128 rows][4 floats] — the layout rssm_rows_kernel reads its
+  // posterior addend in (32 lanes x 16 contiguous bytes per load; here 32 rows x 16 contiguous bytes per store)
+  int out_tile_rows;
   long long* dbg;   // profiling only: CTA 0 writes cycle sums [mma wait_acc, wait_full, issue | gather g0 loop, wait_empty | epi wait, work | chunks, items]
   ConvMap cm;
   int n_rows, K, k16;      // GEMM rows, real K, k16 slabs
@@ -478,9 +482,16 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
               lp[0] = make_uint4(l[0], l[1], l[2], l[3]); lp[1] = make_uint4(l[4], l[5], l[6], l[7]);
             } else {
               float4* op = reinterpret_cast<float4*>(P.out + o);
+              int qstride = 1;   // float4s between the quarters of a 16-feature group
+              if (P.out_tile_rows) {
+                const int stp = fr / P.out_tile_rows, rr = fr - stp * P.out_tile_rows;
+                const size_t tile = (size_t)stp * ((P.out_tile_rows + 127) >> 7) + (rr >> 7);
+                op = reinterpret_cast<float4*>(P.out + (tile * ((P.n_total + 15) >> 4) + (nb >> 4)) * 2048u) + (rr & 127);
+                qstride = 128;
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                if (j < nq) op[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                if (j < nq) op[j * qstride] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
             }
           }
         } else if (have_cols) {

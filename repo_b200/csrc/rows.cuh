@@ -362,20 +362,36 @@ __device__ __forceinline__ float act_bf(float x) {
 // H is written IN PLACE: accumulator columns [16 ch, 16 ch + 16) of this thread's lane become the packed fp16 hi
 // pairs (8 columns) followed by the lo pairs (8 columns) of the same 16 features, so the region that held the
 // accumulators is the next layer's A operand and the region that held this layer's operand is free for its accumulators.
+// the tiled addend of one chunk (four planes of 128 rows x 4 floats, 512 floats apart) into registers; zeros where the row or
+// the feature quad does not exist (n_valid is a multiple of 4: Hd % 4 == 0 is what selects the tiled layout)
+__device__ __forceinline__ void rows_addend_prefetch(float4* pf, const float* ad, int n_valid, bool row_ok) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    pf[j] = (row_ok && 4 * j < n_valid) ? __ldg(reinterpret_cast<const float4*>(ad + 512 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
 // `tcol`, `bias`, `wdot`, `adrow` address THIS chunk (the callers step them from chunk to chunk in registers: recomputing
 // them from the chunk index cost ~50 instructions per chunk, a quarter of the issue-bound epilogue).
-template <int ACT, bool DOT, bool ADDEND>
+// ADDEND == 2: the addend comes in the TILED layout — per (time step, 128-row tile, 16-feature chunk) four planes of
+// 128 rows x 4 floats — so each of the four loads is 32 lanes x 16 contiguous bytes.  Row-major (ADDEND == 1) puts the 32
+// lanes of a load on 32 different cache lines (rows are Hd floats apart), and at 13 chunks x 16 warps that made the posterior
+// layer's epilogue 15.3k cycles against 3.5k for a layer without an addend.
+template <int ACT, bool DOT, int ADDEND>
 __device__ __forceinline__ float rows_act_chunk(uint32_t bias, uint32_t wdot, const float* adrow, uint32_t tcol,
-                                                int n_valid, bool row_ok) {
+                                                int n_valid, bool row_ok, const float4* pf = nullptr) {
   float v[16], bz[16];
   float dot = 0.f;
   tmem_ld16(tcol, v);
   ld_uni16(bz, bias);
-  if (ADDEND) {
+  if (ADDEND == 1) {
     float ad[16];
     ld_row16(ad, adrow, n_valid, row_ok);
 #pragma unroll
     for (int i = 0; i < 16; ++i) bz[i] += ad[i];
+  } else if (ADDEND == 2) {   // requested one round ahead by the caller (rows_addend_prefetch): already in registers
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bz[4 * j] += pf[j].x; bz[4 * j + 1] += pf[j].y; bz[4 * j + 2] += pf[j].z; bz[4 * j + 3] += pf[j].w;
+    }
   }
   tmem_ld_wait();
   if (DOT) {
@@ -876,6 +892,18 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
 #pragma unroll
           for (int i = 0; i < 8; ++i) pre[i] = (row_ok && c + i < A) ? __ldg(eps + i) : 0.f;
         }
+        // The posterior layer's per-row addend (tiled layout) comes from HBM — ~1.5k cycles away: the first chunk's is
+        // requested here, under the layer's MMAs, each later chunk's one round ahead.
+        // (Holding a chunk's addend in registers one round ahead — 16 registers across the layer — was measured: the layer's
+        // epilogue 11.8k -> 8.6k cycles, but the spills it caused in this specialisation cost every other stage more.)  So the
+        // tile's addend block (contiguous: chunks x 8 KB) is only pulled into L2 here, one 128-byte line per thread and pass.
+        if constexpr (kHasAddend) {
+          if (st.epi == R_ACT_H && (st.flags & SF_ADDEND) && V.addend_tiled) {
+            const char* blk = reinterpret_cast<const char*>(V.addend + ((size_t)t * gridDim.x + blockIdx.x) * (size_t)((st.nfeat + 15) >> 4) * 2048u);
+            const int lines = ((st.nfeat + 15) >> 4) * 64;   // 8 KB per chunk
+            for (int i = et; i < lines; i += kRowsEpiThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + (size_t)i * 128));
+          }
+        }
         mbar_wait(bar_acc, par);
         tc_fence_after();
         RB_STAMP(1);
@@ -907,20 +935,29 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             // rounds of four chunks (one per warp of the quadrant); the next layer's MMAs start behind each round
             const bool elu = st.act == ACT_ELU, addend = kHasAddend && (st.flags & SF_ADDEND) != 0;
             const int nfeat = st.nfeat, nch = (nfeat + 15) >> 4;
-            const float* adrow = addend ? V.addend + (trow + row) * V.Hd : nullptr;
+            // row-major: this row's Hd floats; tiled: (t, tile = this CTA, chunk 0, quarter 0, row r) — 2048 floats per chunk
+            const float* adrow = !addend ? nullptr
+                               : V.addend_tiled ? V.addend + ((size_t)t * gridDim.x + blockIdx.x) * (size_t)nch * 2048u + 4 * r
+                                                : V.addend + (trow + row) * V.Hd;
             // the activation / addend variant is chosen once per layer, not per chunk
             auto layer = [&](auto act_tag, auto addend_tag) {
               constexpr int ACT = decltype(act_tag)::value;
-              constexpr bool AD = decltype(addend_tag)::value;
+              constexpr int AD = decltype(addend_tag)::value;   // 0 none, 1 row-major, 2 tiled
               // per-chunk state stepped in registers; the empty asm keeps the compiler from re-deriving it from the chunk index
               uint32_t tcol = tacc + 16u * part, baddr = bias + 64u * part, bar = ground0;
               int left = nch - part;                       // this warp has a chunk in the round while left > 0
-              const float* ad = AD ? adrow + 16 * part : nullptr;
+              const float* ad = AD == 2 ? adrow + 2048 * part : (AD ? adrow + 16 * part : nullptr);
               int nval = nfeat - 16 * part;
               for (int rd = st.rounds; rd > 0; --rd) {
                 asm volatile("" : "+r"(tcol), "+r"(baddr), "+r"(bar), "+r"(left));
                 if (left > 0) {
-                  rows_act_chunk<ACT, false, AD>(baddr, 0u, ad, tcol, nval, row_ok);
+                  if constexpr (AD == 2) {
+                    float4 cur[4];
+                    rows_addend_prefetch(cur, ad, nval, row_ok);
+                    rows_act_chunk<ACT, false, AD>(baddr, 0u, ad, tcol, nval, row_ok, cur);
+                  } else {
+                    rows_act_chunk<ACT, false, AD>(baddr, 0u, ad, tcol, nval, row_ok);
+                  }
                   tmem_st_wait();
                 }
                 if (rd == 1) {
@@ -931,20 +968,23 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_round + 8 * (bar & (kRoundBars - 1)));
                 tcol += 16u * kEpiParts; baddr += 64u * kEpiParts; ++bar; left -= kEpiParts;
-                if (AD) { ad += 16 * kEpiParts; nval -= 16 * kEpiParts; }
+                if (AD) { ad += (AD == 2 ? 2048 : 16) * kEpiParts; nval -= 16 * kEpiParts; }
               }
             };
             using IC_ELU = std::integral_constant<int, ACT_ELU>;
             using IC_RELU = std::integral_constant<int, ACT_RELU>;
             if constexpr (kHasAddend) {
-              if (addend) {
-                if (elu) layer(IC_ELU{}, std::true_type{});
-                else layer(IC_RELU{}, std::true_type{});
+              if (addend && V.addend_tiled) {
+                if (elu) layer(IC_ELU{}, std::integral_constant<int, 2>{});
+                else layer(IC_RELU{}, std::integral_constant<int, 2>{});
+              } else if (addend) {
+                if (elu) layer(IC_ELU{}, std::integral_constant<int, 1>{});
+                else layer(IC_RELU{}, std::integral_constant<int, 1>{});
               }
             }
             if (!addend) {
-              if (elu) layer(IC_ELU{}, std::false_type{});
-              else layer(IC_RELU{}, std::false_type{});
+              if (elu) layer(IC_ELU{}, std::integral_constant<int, 0>{});
+              else layer(IC_RELU{}, std::integral_constant<int, 0>{});
             }
             handed = true;
           } break;
@@ -956,10 +996,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             float dot = 0.f;
             if (elu) {
               for (int ch = part; ch < nch; ch += kEpiParts)
-                dot += rows_act_chunk<ACT_ELU, true, false>(bias + 64u * ch, wdot + 64u * ch, nullptr, tacc + 16u * ch, 16, row_ok);
+                dot += rows_act_chunk<ACT_ELU, true, 0>(bias + 64u * ch, wdot + 64u * ch, nullptr, tacc + 16u * ch, 16, row_ok);
             } else {
               for (int ch = part; ch < nch; ch += kEpiParts)
-                dot += rows_act_chunk<ACT_RELU, true, false>(bias + 64u * ch, wdot + 64u * ch, nullptr, tacc + 16u * ch, 16, row_ok);
+                dot += rows_act_chunk<ACT_RELU, true, 0>(bias + 64u * ch, wdot + 64u * ch, nullptr, tacc + 16u * ch, 16, row_ok);
             }
             handoff(false);   // the accumulators are consumed; nothing in X / H changes
             if (part) sts_f(scratch + 4u * (part * 128 + r), dot);

@@ -106,7 +106,8 @@ struct VmParams {
   // per-step inputs, time-major
   const float* actions_in;   // (T, N, A) or null
   const float* nonterm;      // (T, N) or null
-  const float* addend;       // (T, N, Hd) or null
+  const float* addend;       // (T, N, Hd) or null; rows kernel only, when addend_tiled: (T, tiles, chunks of 16, 4, 128 rows, 4)
+  int addend_tiled;          // see rssm_rows_kernel: the hoisted projection is stored per 128-row tile, quarter-chunk major
   const float* eps_action;   // (T, N, A)
   const float* eps_prior;    // (T, N, S)
   const float* eps_post;     // (T, N, S)

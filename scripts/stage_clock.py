@@ -14,6 +14,9 @@ from repo_b200 import ops, _lib  # noqa: E402
 
 dev = torch.device("cuda:0")
 cu = lambda p: {k: v.to(dev) for k, v in p.items()}
+OBSERVE = len(sys.argv) > 1 and sys.argv[1] == "observe"   # python scripts/stage_clock.py observe [sequences]: the observe program
+if OBSERVE:
+    sys.argv.pop(1)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 18944
 params = cu(O.make_transition_params(0))
 actor = cu(O.make_mlp_params(1, 230, 200, 12, 4))
@@ -22,12 +25,18 @@ value = cu(O.make_mlp_params(3, 230, 200, 1, 3))
 x = O.make_imagine_inputs(1, N, 15)
 a = [params, actor, reward, value, x["belief"].to(dev), x["state"].to(dev), x["eps_action"].to(dev), x["eps_prior"].to(dev), 15]
 _lib.lib().repo_b200_debug_flags(int(os.environ.get('RB_DBG', '0')))
-ops.imagine_fwd(*a, row_tile=128)
+if OBSERVE:
+    xo = O.make_observe_inputs(1, 16, N)
+    ao = [params] + [xo[k].to(dev) for k in ("prev_belief", "prev_state", "actions", "embeds", "nonterms", "eps_prior", "eps_post")]
+    run = lambda: ops.observe_fwd(*ao, row_tile=128)
+else:
+    run = lambda: ops.imagine_fwd(*a, row_tile=128)
+run()
 torch.cuda.synchronize()
 NS = 32
 buf = torch.zeros(14 * NS * 2 + 256 + 1200, dtype=torch.int64, device=dev)
 _lib.lib().repo_b200_debug_clock(C.c_void_p(buf.data_ptr()))
-ops.imagine_fwd(*a, row_tile=128)
+run()
 torch.cuda.synchronize()
 _lib.lib().repo_b200_debug_clock(None)
 b = buf.cpu().numpy()
@@ -41,7 +50,7 @@ b[600:] = 0
 nz = (b != 0).sum() // (14 * 2)
 b = b[: 14 * nz * 2].reshape(14, nz, 2)
 print("stages per step:", nz)
-names = ["A1", "A2", "A3", "A4", "ACT", "E", "G0", "G1", "G2", "G3", "P1", "P2", "R1", "R2", "R3", "V1", "V2", "V3"]
+names = ["E", "G0", "G1", "G2", "G3", "P1", "P2", "Q1", "Q2"] if OBSERVE else ["A1", "A2", "A3", "A4", "ACT", "E", "G0", "G1", "G2", "G3", "P1", "P2", "R1", "R2", "R3", "V1", "V2", "V3"]
 t = 5
 tot_epi = tot_mma = 0
 for s in range(nz):
