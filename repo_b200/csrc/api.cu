@@ -592,7 +592,8 @@ int launch_rows(const RowsParams& P, cudaStream_t st) {
   return 0;
 }
 
-// 128-row tiles pay off once they fill the machine; below that the flexible row tiles of vm.cuh win
+// the 128-row kernel runs every no-stash program it supports; vm.cuh keeps the stash-writing training forwards, wide states /
+// actions, the conditional model and single rows
 bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
   if (d->state > 32 || d->action > 16) return false;  // the 128-row kernel keeps one row's Gaussian heads in registers
   // its other budgets: the bias staging buffer holds a scalar head's fc3 bias + fc4 row (2 * r16(hidden) + 16 floats), H and
@@ -607,10 +608,11 @@ bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
   if (row_tile == 16 || row_tile == 32 || row_tile == 64) return false;
   if (g_dbg_flags & 2) return false;
   if (g_dbg_flags & 4) return true;
-  // measured crossover (scripts/tile_crossover.py, imagine forward, horizon 15): the 128-row kernel takes ~1.27 ms for
-  // anything up to one wave (18,944 rows); the vm kernel 1.19 ms while 16-row tiles fit one wave of CTAs, 1.5 ms with
-  // 32-row tiles, 2.0 ms with 64 — so the rows kernel takes over as soon as 16-row tiles no longer fit one wave
-  return n_rows > 16 * std::max(1, sm_count());
+  // measured (scripts/tile_crossover.py / observe_crossover.py, round 2): a launch of the 128-row kernel takes 0.97-0.99 ms for
+  // any imagine (horizon 15) up to one wave of CTAs — 16 rows or 18,944 — against 1.19 ms for 16-row tiles of the vm kernel,
+  // and 2.24-2.39 ms against 2.38-2.39 ms for a 49-step observe of 16..128 sequences: the per-step latency of ONE 128-row CTA
+  // is no longer above that of a 16-row vm CTA, so the rows kernel runs everything but single rows (the acting step).
+  return n_rows >= 8;
 }
 
 

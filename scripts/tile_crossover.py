@@ -13,11 +13,11 @@ dev = torch.device("cuda:0")
 cu = lambda p: {k: v.to(dev) for k, v in p.items()}
 params, actor = cu(O.make_transition_params(0)), cu(O.make_mlp_params(1, 230, 200, 12, 4))
 reward, value = cu(O.make_mlp_params(2, 230, 200, 1, 3)), cu(O.make_mlp_params(3, 230, 200, 1, 3))
-for N in (1024, 2450, 4096, 6144, 9472, 18944):
+for N in (16, 128, 512, 1024, 2048, 2450, 4096, 18944):
     x = O.make_imagine_inputs(1, N, 15)
     a = [params, actor, reward, value, x["belief"].to(dev), x["state"].to(dev), x["eps_action"].to(dev), x["eps_prior"].to(dev), 15]
     line = f"N={N:6d}:"
-    for rt in (0, 32, 64, 128):
+    for rt in (0, 16, 32, 128):
         for _ in range(3):
             ops.imagine_fwd(*a, row_tile=rt)
         torch.cuda.synchronize()
