@@ -1008,6 +1008,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               float* dst = (st.flags & SF_SCALAR_VALUE) ? V.values : V.rewards;
               dst[trow + row] = ((dot + lds_f(scratch + 4u * (128 + r))) + (lds_f(scratch + 4u * (256 + r)) + lds_f(scratch + 4u * (384 + r)))) + lds_f(bias + 4u * (2 * nch * 16));
             }
+            // The next writer of `scratch` (the other scalar head, three stages on) is ordered behind these reads by the round
+            // barriers — its accumulators need every warp's rounds of the stages in between — but only through mbarriers,
+            // which compute-sanitizer's racecheck cannot follow: this barrier (~60 cycles, twice per step) keeps it clean.
+            epi_sync();
           } break;
 
           case R_GRU: {
@@ -1137,6 +1141,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
             if (want_kl) {   // uniform across the CTA: V.kl and the stage kind are kernel-wide
               epi_sync();
               if (part == 0 && row_ok) V.kl[trow + row] = (kl + lds_f(scratch + 4u * (128 + r))) + (lds_f(scratch + 4u * (256 + r)) + lds_f(scratch + 4u * (384 + r)));
+              epi_sync();   // as for the scalar heads: orders the next step's partial sums behind these reads for racecheck
             }
           } break;
 
