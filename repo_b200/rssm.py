@@ -62,8 +62,27 @@ class TransitionModel(nn.Module):
                 post.append(torch.randn(B, S, device=like.device))
         return torch.stack(pri), (torch.stack(post) if with_obs else None)
 
+    # `prefetch_noise = True` (off by default): when imagine() draws its own noise, the draw for the NEXT call of the same shape
+    # is enqueued on a side stream right after this call's kernel launch, so it runs under that kernel instead of in front of
+    # the next one (38 M normals per 75,776 x 14 launch: ~0.25 ms of a 4.3 ms call).  The random stream is consumed in the same
+    # order; the only difference is one unused draw left behind by the last call.
+    prefetch_noise = False
+
     def _imagine_noise(self, T, N, like, action_width=None):
         S, A = self.state_size, (self.action_size if action_width is None else action_width)
+        if self.prefetch_noise and not self.rng_compat and like.is_cuda:
+            key = (T, N, A, S, like.device)
+            cur = torch.cuda.current_stream(like.device)
+            nxt = getattr(self, "_noise_next", None)
+            if nxt is not None and nxt[0] == key:
+                _, ea, ep, ev = nxt
+                cur.wait_event(ev)
+                ea.record_stream(cur)
+                ep.record_stream(cur)
+            else:
+                ea, ep = self._randn(T, N, A, like), self._randn(T, N, S, like)
+            self._noise_key = key
+            return ea, ep
         if not self.rng_compat:
             return self._randn(T, N, A, like), self._randn(T, N, S, like)
         ea, ep = [], []
@@ -133,6 +152,17 @@ class TransitionModel(nn.Module):
                               actor_min_std=float(policy._min_std), gamma=gamma, lambda_=lambda_,
                               workspace=self._ws.get("imagine"), cond=_cond)
         self._ws["imagine"] = out.pop("workspace")
+        if self.prefetch_noise and getattr(self, "_noise_key", None) is not None:   # next call's noise, under this call's kernel
+            key, self._noise_key = self._noise_key, None
+            side = getattr(self, "_noise_stream", None)
+            if side is None:
+                side = self._noise_stream = torch.cuda.Stream(device=key[4])
+            with torch.cuda.stream(side):
+                ea2 = torch.randn(key[0], key[1], key[2], device=key[4])
+                ep2 = torch.randn(key[0], key[1], key[3], device=key[4])
+                ev2 = torch.cuda.Event()
+                ev2.record(side)
+            self._noise_next = (key, ea2, ep2, ev2)
         traj = [out["beliefs"], out["prior_states"], out["prior_means"], out["prior_std_devs"]]
         if return_extras:
             return traj, out

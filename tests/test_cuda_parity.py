@@ -107,6 +107,31 @@ def test_small_actions_keep_relative_accuracy(ops, dev, row_tile):
     close(out["actions"], want[4], "small actions", rtol=1e-3, atol=5e-8)
 
 
+def test_noise_prefetch_consumes_the_same_random_stream(dev):
+    """TransitionModel.prefetch_noise draws the next call's noise on a side stream under the current kernel: same values, in
+    the same order, as the in-line draw."""
+    from repo_b200.models import ActorModel
+    from repo_b200.rssm import TransitionModel
+    tm = TransitionModel(200, 30, 6, 200, 1024, "elu").to(dev)
+    tm.load_state_dict(O.make_transition_params(77))
+    actor = ActorModel(200, 30, 200, 6, "elu").to(dev)
+    actor.load_state_dict(O.make_mlp_params(78, 230, 200, 12, 4))
+    x = O.make_imagine_inputs(79, 300, 5)
+    b, s_ = x["belief"].to(dev), x["state"].to(dev)
+    runs = []
+    for prefetch in (False, True):
+        tm.prefetch_noise = prefetch
+        torch.manual_seed(1234)
+        with torch.no_grad():
+            outs = [tm.imagine(b, s_, actor, 5)[0].clone() for _ in range(3)]
+        torch.cuda.synchronize()
+        runs.append(outs)
+    tm.prefetch_noise = False
+    for a_, b_ in zip(*runs):
+        assert torch.equal(a_, b_)
+    assert not torch.equal(runs[0][0], runs[0][1])   # the three calls really used different noise
+
+
 def test_error_is_fp32_grade(ops, dev):
     """hi*hi + lo*hi + hi*lo on fp16 operands keeps ~22 mantissa bits: errors stay ~1e-5, not 1e-3."""
     params, x, gold, meta = C.observe_case("observe_default_tail")
