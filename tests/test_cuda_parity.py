@@ -107,6 +107,21 @@ def test_small_actions_keep_relative_accuracy(ops, dev, row_tile):
     close(out["actions"], want[4], "small actions", rtol=1e-3, atol=5e-8)
 
 
+def test_observe_multi_tile_tiled_addend_vs_oracle(ops, dev):
+    """observe on the 128-row kernel across three row tiles, the last one partial (300 = 128 + 128 + 44 sequences): the hoisted
+    embedding projection travels in the per-tile quarter-chunk layout here (>= 256 rows), row-major in the small golden cases."""
+    params = O.make_transition_params(555)
+    x = O.make_observe_inputs(556, 5, 300, p_done=0.2)
+    outs, kl = run_observe(ops, dev, params, x, row_tile=128)
+    want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"], x["eps_prior"], x["eps_post"])
+    for nm, o, w in zip(C.OBS_NAMES, outs, want):
+        close(o, w, f"multi-tile observe/{nm}")
+    close(kl, O.kl_sum(want[5], want[6], want[2], want[3]), "multi-tile observe/kl", atol=1e-4)
+    auto, _ = run_observe(ops, dev, params, x, row_tile=0)   # the library's own pick must agree bit for bit (same kernel)
+    for o, a_ in zip(outs, auto):
+        assert torch.equal(o, a_)
+
+
 def test_noise_prefetch_consumes_the_same_random_stream(dev):
     """TransitionModel.prefetch_noise draws the next call's noise on a side stream under the current kernel: same values, in
     the same order, as the in-line draw."""
