@@ -42,16 +42,31 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
   return y > 0.f ? 1.f : 0.f;
 }
 
-// out[k] = sum_j W[j*ld + k] * dy[j], j in [j0, j1)  (dy in shared memory, W column walk is coalesced over k)
+// out[k] = sum_j W[j*ld + k] * dy[j], j in [j0, j1)  (dy in shared memory, W column walk is coalesced over k).
+// The kernel is bound by the LATENCY of these L2 reads, not by their bandwidth (one CTA per sequence: 1.4 MB of weights per
+// time step at 18 B/clk/SM with 8 loads in flight per thread), so 16 independent loads are issued before the first FMA.
 __device__ __forceinline__ float col_dot(const float* __restrict__ W, int ld, int k, const float* dy, int j0, int j1) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   int j = j0;
-#pragma unroll 2
+  for (; j + 16 <= j1; j += 16) {
+    float w[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) w[u] = __ldg(W + (size_t)(j + u) * ld + k);
+#pragma unroll
+    for (int u = 0; u < 16; u += 4) {
+      a0 = fmaf(w[u], dy[j + u], a0);
+      a1 = fmaf(w[u + 1], dy[j + u + 1], a1);
+      a2 = fmaf(w[u + 2], dy[j + u + 2], a2);
+      a3 = fmaf(w[u + 3], dy[j + u + 3], a3);
+    }
+  }
   for (; j + 4 <= j1; j += 4) {
-    a0 = fmaf(__ldg(W + (size_t)j * ld + k), dy[j], a0);
-    a1 = fmaf(__ldg(W + (size_t)(j + 1) * ld + k), dy[j + 1], a1);
-    a2 = fmaf(__ldg(W + (size_t)(j + 2) * ld + k), dy[j + 2], a2);
-    a3 = fmaf(__ldg(W + (size_t)(j + 3) * ld + k), dy[j + 3], a3);
+    const float w0 = __ldg(W + (size_t)j * ld + k), w1 = __ldg(W + (size_t)(j + 1) * ld + k);
+    const float w2 = __ldg(W + (size_t)(j + 2) * ld + k), w3 = __ldg(W + (size_t)(j + 3) * ld + k);
+    a0 = fmaf(w0, dy[j], a0);
+    a1 = fmaf(w1, dy[j + 1], a1);
+    a2 = fmaf(w2, dy[j + 2], a2);
+    a3 = fmaf(w3, dy[j + 3], a3);
   }
   for (; j < j1; ++j) a0 = fmaf(__ldg(W + (size_t)j * ld + k), dy[j], a0);
   return (a0 + a1) + (a2 + a3);
