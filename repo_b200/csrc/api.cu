@@ -889,7 +889,8 @@ int repo_b200_imagine_cond_bwd(const repo_b200_dims* d, const repo_b200_rssm_wei
   // into ONE wave of CTAs (2450 rows on 148 SMs -> 20 rows, 123 CTAs: 3.2 ms instead of 3.8 ms with 8 rows).
   // Tried and dropped: streaming the weights through a shared-memory ring with bulk copies from a producer warp —
   // same time for 8, 12 and 20 rows per CTA, i.e. the kernel is bound by its FMA / shared-load issue rate and the
-  // per-stage stash traffic, not by the weight fetch latency.
+  // per-stage stash traffic, not by the weight fetch latency.  Round 2 confirmed it from the other side: splitting every
+  // reduction over two thread groups (512 threads, 16 warps instead of 8 to hide the L2 latency with) — 3.31 vs 3.34 ms.
   const int sms = std::max(1, sm_count());
   const int rb = n_rows <= 8 * sms ? 8 : (n_rows <= 12 * sms ? 12 : 20);
   const size_t smem = (size_t)(9 * P.D + 3 * P.S + 2 * P.Hd + 2 * P.A) * rb * sizeof(float);
