@@ -249,6 +249,10 @@ int repo_b200_im2col(const float* input, float* col, int frames, const int* map,
  * repo_b200_adam_clip_step scales grad by min(1, max_norm / (sqrt(*sqnorm) + 1e-6)) (sqnorm NULL or max_norm <= 0:
  * no clipping) and applies the bias-corrected Adam update of 1-based `step`.  No host synchronisation. */
 int repo_b200_sqnorm_accumulate(const float* grad, long long n, float* sqnorm, void* stream);
+/* bias gradient of a linear / conv layer, i.e. autograd's grad_output.sum(0) behind nn.Linear / nn.Conv2d in the reference
+ * (dreamer.py:286, 356, 370: loss.backward()): out[c] = sum_r x[r * ld + c] for a (rows, cols) row-major window with row
+ * stride ld.  Partial sums of row slices meet through fp32 atomics (summation order varies from run to run). */
+int repo_b200_colsum(const float* x, long long rows, int cols, long long ld, float* out, void* stream);
 int repo_b200_adam_clip_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                              const float* sqnorm, float max_norm, float lr, float beta1, float beta2, float eps,
                              int step, void* stream);

@@ -42,7 +42,7 @@ EXPORTS = [
     "repo_b200_head_workspace_bytes", "repo_b200_head_fwd",
     "repo_b200_tanh_normal_entropy_fwd", "repo_b200_replay_gather",
     "repo_b200_cell_workspace_bytes", "repo_b200_cell_fwd",
-    "repo_b200_sqnorm_accumulate", "repo_b200_adam_clip_step", "repo_b200_adam_clip_step_dev", "repo_b200_conv_workspace_bytes", "repo_b200_conv_gemm", "repo_b200_conv_wgrad", "repo_b200_pow2_scale", "repo_b200_grad_unshuffle", "repo_b200_tia_mix_fwd", "repo_b200_tia_mix_bwd", "repo_b200_im2col",
+    "repo_b200_sqnorm_accumulate", "repo_b200_colsum", "repo_b200_adam_clip_step", "repo_b200_adam_clip_step_dev", "repo_b200_conv_workspace_bytes", "repo_b200_conv_gemm", "repo_b200_conv_wgrad", "repo_b200_pow2_scale", "repo_b200_grad_unshuffle", "repo_b200_tia_mix_fwd", "repo_b200_tia_mix_bwd", "repo_b200_im2col",
     "repo_b200_mlp_workspace_bytes", "repo_b200_mlp_fwd", "repo_b200_mlp_bwd", "repo_b200_tanh_normal_entropy_bwd",
 ]
 
@@ -117,6 +117,8 @@ def lib():
     L.repo_b200_tanh_normal_entropy_bwd.restype = ci
     L.repo_b200_sqnorm_accumulate.argtypes = [vp, C.c_longlong, vp, vp]
     L.repo_b200_sqnorm_accumulate.restype = ci
+    L.repo_b200_colsum.argtypes = [vp, C.c_longlong, ci, C.c_longlong, vp, vp]
+    L.repo_b200_colsum.restype = ci
     L.repo_b200_adam_clip_step.argtypes = [vp, vp, vp, vp, C.c_longlong, vp, cf, cf, cf, cf, cf, ci, vp]
     L.repo_b200_adam_clip_step.restype = ci
     L.repo_b200_adam_clip_step_dev.argtypes = [vp, vp, vp, vp, C.c_longlong, vp, cf, cf, cf, cf, cf, vp, vp]

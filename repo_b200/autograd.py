@@ -101,7 +101,7 @@ class ObserveFn(torch.autograd.Function):
             if need[wkey]:
                 gp[wkey] = _wgrad(flat(dpre), flat(inp))
             if need[bkey]:
-                gp[bkey] = flat(dpre).sum(0)
+                gp[bkey] = ops.colsum(flat(dpre))
 
         lin("fc_embed_state_action.weight", "fc_embed_state_action.bias", d_e, x_sa)
         lin("rnn.weight_ih", "rnn.bias_ih", d_gi, e)
@@ -207,7 +207,7 @@ class ImagineFn(torch.autograd.Function):
             if need[wkey]:
                 gp[wkey] = _wgrad(flat(dpre), flat(inp))
             if need[bkey]:
-                gp[bkey] = flat(dpre).sum(0)
+                gp[bkey] = ops.colsum(flat(dpre))
 
         b_in = torch.cat([prev_belief.unsqueeze(0), beliefs[:-1]], 0)
         s_in = torch.cat([prev_state.unsqueeze(0), prior_s[:-1]], 0)
@@ -325,7 +325,7 @@ class MlpFn(torch.autograd.Function):
         for i in range(L_layers):
             need_w, need_b = ctx.needs_input_grad[4 + 2 * i], ctx.needs_input_grad[5 + 2 * i]
             grads.append(_wgrad(dpre[i], inputs[i]) if need_w else None)
-            grads.append(dpre[i].sum(0) if need_b else None)
+            grads.append(ops.colsum(dpre[i]) if need_b else None)
         gb = dx[:, :d.belief].contiguous() if (need_x and ctx.needs_input_grad[2]) else None
         gs = dx[:, d.belief:d.belief + d.state].contiguous() if (need_x and ctx.needs_input_grad[3]) else None
         return (None, None, gb, gs, *grads)
@@ -360,7 +360,7 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = _wgrad(g, x.detach()) if x.shape[0] else torch.zeros_like(weight)
         if ctx.needs_input_grad[2]:
-            gb = g.sum(0)
+            gb = ops.colsum(g)
         return gx, gw, gb
 
 

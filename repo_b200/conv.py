@@ -30,6 +30,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
+from . import ops as _ops
 
 _MAP_FIELDS = ("enabled RA RB in_nchw C H W TH TW tap0 ntaps sy sx dy dx y0 x0 "
                "out_nchw Ho Wo osy osx oy0 ox0 relu accumulate shuffle pix").split()
@@ -264,7 +265,7 @@ class _EncoderFn(torch.autograd.Function):
             if ctx.needs_input_grad[1 + 2 * i]:
                 grads[2 * i] = conv_wgrad(acts[i], gl, F_, cout, cm, sc).reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
             if ctx.needs_input_grad[2 + 2 * i]:
-                grads[2 * i + 1] = gl.sum(0)
+                grads[2 * i + 1] = _ops.colsum(gl)
             if i == 0:
                 break
             # data gradient = sub-pixel conv of gp with 2x2 taps; features (py, px, ci); masked by the ReLU below
@@ -443,7 +444,7 @@ class _DecoderFn(torch.autograd.Function):
         if need[2]:
             grads[0] = wgrad_gemm(d_h, xin) if big else d_h.t() @ xin
         if need[3]:
-            grads[1] = d_h.sum(0)
+            grads[1] = _ops.colsum(d_h)
         gb = gs = None
         if need[0] or need[1]:
             nin = fc_w.shape[1]

@@ -911,6 +911,21 @@ int repo_b200_imagine_cond_bwd(const repo_b200_dims* d, const repo_b200_rssm_wei
   return go(imagine_bwd_kernel<20>, c20);
 }
 
+int repo_b200_colsum(const float* x, long long rows, int cols, long long ld, float* out, void* stream) {
+  if (rows < 0 || cols < 0 || ld < cols) return fail(-1, "colsum: bad sizes");
+  if (cols == 0) return 0;
+  if (!out || (rows > 0 && !x)) return fail(-1, "colsum: NULL pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_OK(cudaMemsetAsync(out, 0, (size_t)cols * sizeof(float), st));
+  if (rows == 0) return 0;
+  // enough row slices to fill the machine (the column tiles alone are 1..19 blocks), at least 64 rows each
+  const int ct = cdiv(cols, 32);
+  const int slices = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, std::max(1, 4 * sm_count() / ct)));
+  colsum_kernel<<<dim3(ct, slices), 256, 0, st>>>(x, rows, cols, ld, out);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int repo_b200_sqnorm_accumulate(const float* grad, long long n, float* sqnorm, void* stream) {
   if (n < 0) return fail(-1, "sqnorm: bad size");
   if (n == 0) return 0;

@@ -27,6 +27,32 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g
   }
 }
 
+// Bias gradients: out[c] += sum over this block's row slice of x[r * ld + c] (out zeroed by the caller).  The trainers need ~35
+// of these per iteration over tall, narrow matrices ((T*B or (H-1)*N) x 12..600); ATen's generic reduce takes ~33 us for each.
+// One warp reads 32 consecutive columns of a row; the 8 warps of a block stride over the rows of the slice.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long rows, int cols, long long ld,
+                                                     float* __restrict__ out) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y, r0 = (long long)blockIdx.y * per, r1 = min(rows, r0 + per);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < cols) {
+    long long r = r0 + w;
+    for (; r + 24 < r1; r += 32) {   // four independent loads in flight
+      a0 += x[r * ld + c]; a1 += x[(r + 8) * ld + c]; a2 += x[(r + 16) * ld + c]; a3 += x[(r + 24) * ld + c];
+    }
+    for (; r < r1; r += 8) a0 += x[r * ld + c];
+  }
+  __shared__ float part[8][32];
+  part[w][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (w == 0 && c < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += part[i][threadIdx.x];
+    atomicAdd(out + c, v);
+  }
+}
+
 // torch semantics: clip_coef = min(1, max_norm / (||g|| + 1e-6)); Adam with bias correction
 //   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,

@@ -216,6 +216,21 @@ def imagine_fwd(params: Dict[str, torch.Tensor], actor: Dict[str, torch.Tensor],
     return out
 
 
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """x.sum(0) of a 2-D fp32 CUDA tensor whose rows are contiguous (a column window of a wider row-major matrix is fine):
+    the bias gradients of the hand-written backward passes (autograd's grad_output.sum(0) in the reference)."""
+    if x.dim() != 2 or x.dtype != torch.float32 or not x.is_cuda or (x.shape[1] > 1 and x.stride(1) != 1):
+        raise RuntimeError("colsum: expected a 2-D fp32 CUDA tensor with contiguous rows")
+    rows, cols = x.shape
+    ld = x.stride(0) if rows > 1 else max(cols, 1)
+    if ld < cols:
+        raise RuntimeError("colsum: overlapping rows")
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    rc = _lib.lib().repo_b200_colsum(_ptr(x), rows, cols, ld, _ptr(out), _stream())
+    _lib.check(rc, "repo_b200_colsum")
+    return out
+
+
 def head_fwd(head: Dict[str, torch.Tensor], belief: torch.Tensor, state: torch.Tensor, act: str = "elu",
              row_tile: int = 0) -> torch.Tensor:
     """RewardModel / ValueModel forward on (N, D), (N, S) -> (N,)  (decoder.py:189-195, actor_critic.py:20-26)."""

@@ -122,6 +122,18 @@ def test_observe_multi_tile_tiled_addend_vs_oracle(ops, dev):
         assert torch.equal(o, a_)
 
 
+@pytest.mark.parametrize("rows,cols,ld", [(0, 7, 7), (1, 1, 1), (63, 12, 12), (2450, 200, 200), (34300, 600, 600), (2401, 60, 1400), (100000, 32, 32)])
+def test_colsum_matches_sum_over_rows(ops, dev, rows, cols, ld):
+    """the bias-gradient reduction (grad_output.sum(0)), incl. column windows of wider matrices and empty inputs"""
+    g = torch.Generator().manual_seed(rows + cols)
+    base = torch.randn(max(rows, 1), ld, generator=g).to(dev)
+    x = base[:rows, 5:5 + cols] if ld > cols + 5 else base[:rows, :cols]
+    got = ops.colsum(x)
+    want = x.double().sum(0)
+    scale = float(x.double().abs().sum(0).max()) if rows else 1.0
+    np.testing.assert_allclose(got.cpu().double().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-6 * max(scale, 1.0))
+
+
 def test_noise_prefetch_consumes_the_same_random_stream(dev):
     """TransitionModel.prefetch_noise draws the next call's noise on a side stream under the current kernel: same values, in
     the same order, as the in-line draw."""
