@@ -796,6 +796,9 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
                     umma_f16_ts(d, a_hi, b_hi, idesc, (j == 0) ? acc : 1u);
                   umma_f16_ts(d, a_hi + 8u, b_hi, idesc, 1u);
                   umma_f16_ts(d, a_hi, b_hi + b_lo_delta, idesc, 1u);
+#ifdef RB_STAGE_CLOCK
+                  if ((V.dbg_flags & 64) && V.dbg_clock && blockIdx.x == 0 && t == 5 && s == 1) V.dbg_clock[1100 + kk + j] = clock64();   // A2: slab issued
+#endif
                   a_hi += 16u;
                   b_hi += b_step;
                 }

@@ -42,7 +42,7 @@ _lib.lib().repo_b200_debug_clock(None)
 b = buf.cpu().numpy()
 chunk = b[860:880].copy()
 issuer = b[900:900 + 4 * NS].copy()
-groups = b[1100:1100 + 3 * 12].copy().reshape(12, 3)
+slabs = b[1100:1100 + 16].copy()
 perwarp = b[1200:1200 + 16 * 64].copy().reshape(16, 32, 2)
 extra = b[600:600 + 64].copy()
 fine = b[700:700 + 8 * NS // 2 + 64].copy() if len(b) > 700 else None
@@ -78,13 +78,10 @@ if issuer.any():
         f = issuer[4 * s: 4 * s + 4]
         print(f"{names[s] if s < len(names) else s:>4}: inputs_ready {int(f[1] - prev_end):7d}  weights_landed {int(f[2] - prev_end):7d}  committed {int(f[3] - prev_end):7d}  epilogue_begins {int(b[t, s, 0] - prev_end):7d}")
 
-if groups.any():
+if slabs.any():
     e0 = b[t, 0, 0]   # A1's epilogue begins (A2's MMAs are K-chained behind it)
-    print("# stage A2's k-slab groups, issuer times relative to the BEGIN of A1's epilogue (ends at %d; A2's epilogue begins at %d):" % (b[t, 0, 1] - e0, b[t, 1, 0] - e0))
-    print("#   group: round observed / weights landed / MMAs issued")
-    for gi in range(12):
-        if groups[gi].any():
-            print(f"   {gi:2d}: {int(groups[gi, 0] - e0):6d} {int(groups[gi, 1] - e0):6d} {int(groups[gi, 2] - e0):6d}")
+    print("# stage A2: issue time of each k-slab's three MMAs relative to the BEGIN of A1's epilogue (which ends at %d; A2's epilogue begins at %d):" % (b[t, 0, 1] - e0, b[t, 1, 0] - e0))
+    print("#  ", " ".join(f"{int(v - e0):6d}" for v in slabs if v))
 
 if perwarp.any():
     print("# per epilogue warp (step 5): epilogue END of each stage relative to warp 4's (quadrant = warp % 4, part = warp // 4);")
