@@ -592,10 +592,17 @@ int launch_rows(const RowsParams& P, cudaStream_t st) {
   return 0;
 }
 
+// (T, rows, state) tensors the 128-row kernel touches with float2 accesses: 8-byte aligned bases (state sizes are even there)
+bool rows_state_rows_aligned(std::initializer_list<const void*> ptrs) {
+  for (const void* p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) & 7) return false;
+  return true;
+}
 // the 128-row kernel runs every no-stash program it supports; vm.cuh keeps the stash-writing training forwards, wide states /
 // actions, the conditional model and single rows
 bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
   if (d->state > 32 || d->action > 16) return false;  // the 128-row kernel keeps one row's Gaussian heads in registers
+  if (d->state & 1) return false;                      // ... and reads / writes a row's states as float2 pairs
   // its other budgets: the bias staging buffer holds a scalar head's fc3 bias + fc4 row (2 * r16(hidden) + 16 floats), H and
   // the GRU's embedding operand fill one 256-column TMEM region, X for 128 rows must fit shared memory next to the ring
   // (upper bound of the bias floats of the largest program, imagine with both scalar heads: ten hidden layers, the GRU's four
@@ -742,7 +749,8 @@ int repo_b200_imagine_cond_fwd(const repo_b200_dims* d, const repo_b200_rssm_wei
   if ((reward && !rewards) || (value && !values)) return fail(-1, "imagine: rewards/values output missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // (the activation stash and the conditional variant are served by the vm kernel)
-  const bool rows = !stash && cond_size == 0 && use_rows_kernel(d, n_rows, row_tile);
+  const bool rows = !stash && cond_size == 0 && use_rows_kernel(d, n_rows, row_tile) &&
+                    rows_state_rows_aligned({eps_prior, prior_states, prior_means, prior_std_devs});
   Builder b;
   RBuilder rbld;
   if (rows) {
@@ -1423,7 +1431,8 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   if (with_obs && (!eps_post || !post_states || !post_means || !post_std_devs)) return fail(-1, "observe: posterior buffers missing");
   if (ws_bytes < repo_b200_observe_workspace_bytes(d, t1, batch)) return fail(-4, "observe: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool rows = !stash && use_rows_kernel(d, batch, row_tile);  // the activation stash is written by the vm kernel
+  const bool rows = !stash && use_rows_kernel(d, batch, row_tile) &&   // the activation stash is written by the vm kernel
+                    rows_state_rows_aligned({eps_prior, eps_post, prior_states, prior_means, prior_std_devs, post_states, post_means, post_std_devs});
   Builder b;
   RBuilder rbld;
   const size_t main = observe_main_bytes(d);

@@ -286,21 +286,14 @@ __device__ __forceinline__ void ld_row16_v2(float* dst, const float* base, int n
 // term reads prior_m / prior_sd that this kernel wrote a few stages earlier
 template <bool NC>
 __device__ __forceinline__ void ld_row8_v2(float* dst, const float* base, int n_valid, bool row_ok) {
-  if (row_ok && (reinterpret_cast<uintptr_t>(base) & 7) == 0) {
-    const float2* p = reinterpret_cast<const float2*>(base);
+  // ONE code path (predicated float2 loads): with an aligned and an unaligned variant the eight values met in local memory.
+  // The host routes odd state sizes / unaligned tensors to the vm kernel (api.cu: rows_state_rows_aligned).
+  const float2* p = reinterpret_cast<const float2*>(base);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (2 * i + 1 < n_valid) {
-        const float2 v = NC ? __ldg(p + i) : p[i];
-        dst[2 * i] = v.x; dst[2 * i + 1] = v.y;
-      } else {
-        dst[2 * i] = (2 * i < n_valid) ? (NC ? __ldg(base + 2 * i) : base[2 * i]) : 0.f;
-        dst[2 * i + 1] = 0.f;
-      }
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) dst[i] = (row_ok && i < n_valid) ? (NC ? __ldg(base + i) : base[i]) : 0.f;
+  for (int i = 0; i < 4; ++i) {
+    float2 v = make_float2(0.f, 0.f);
+    if (row_ok && 2 * i + 1 < n_valid) v = NC ? __ldg(p + i) : p[i];
+    dst[2 * i] = v.x; dst[2 * i + 1] = v.y;
   }
 }
 __device__ __forceinline__ void st_row16_v2(float* dst, const float* v, int n_valid) {
