@@ -14,6 +14,7 @@
 #include "pack.cuh"
 #include "vm.cuh"
 #include "rows.cuh"
+#include "cluster.cuh"
 #include "conv.cuh"
 #include "elementwise.cuh"
 #include "bwd.cuh"
@@ -623,6 +624,84 @@ bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
 }
 
 
+// ------------------------------------------------------------------------------------------ cluster observe (cluster.cuh)
+// Largest batch the cluster kernel takes on its own initiative: 16 sequences per 16-CTA cluster; 148 SMs hold eight or nine
+// clusters at a time, and a second wave of clusters is still far below the other kernels' ~47 us per time step.
+constexpr int kClusterAutoBatch = 256;
+
+int cluster_max_active() {   // co-resident 16-CTA clusters of the kernel on this device (0: cannot launch)
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  ClGeom g;
+  if (!cl_geometry(200, 30, 6, 200, g)) return cached = 0;
+  if (cudaFuncSetAttribute(rssm_cluster_observe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+      cudaFuncSetAttribute(rssm_cluster_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    cudaGetLastError();
+    return cached = 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kClSize * 8);
+  cfg.blockDim = dim3(kClThreads);
+  cfg.dynamicSmemBytes = g.smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kClSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, rssm_cluster_observe_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  return cached = n;
+}
+
+bool cluster_observe_fits(const repo_b200_dims* d) {
+  ClGeom g;
+  return cl_geometry(d->belief, d->state, d->action, d->hidden, g);
+}
+// row_tile 1 asks for the cluster kernel; auto (0) takes it for small batches
+bool use_cluster_observe(const repo_b200_dims* d, int batch, int row_tile) {
+  if (row_tile != 0 && row_tile != 1) return false;
+  if (!cluster_observe_fits(d)) return false;
+  if (row_tile == 0 && ((g_dbg_flags & 8) || batch > kClusterAutoBatch)) return false;
+  return cluster_max_active() > 0;
+}
+size_t cluster_blob_bytes(const repo_b200_dims* d) {
+  ClGeom g;
+  if (!cl_geometry(d->belief, d->state, d->action, d->hidden, g)) return 0;
+  return (size_t)kClSize * g.cta_bytes;
+}
+
+int launch_cluster_observe(const repo_b200_dims* d, const repo_b200_rssm_weights* W, ClParams& P, void* ws, bool do_pack,
+                           cudaStream_t st) {
+  ClGeom g;
+  if (!cl_geometry(d->belief, d->state, d->action, d->hidden, g)) return fail(-5, "cluster observe: sizes unsupported");
+  if (do_pack) {
+    ClPackArgs a{};
+    a.D = d->belief; a.S = d->state; a.A = d->action; a.Hd = d->hidden; a.E = d->embed; a.with_obs = P.with_obs;
+    a.w_e = W->fc_embed_state_action_w; a.w_ih = W->rnn_w_ih; a.w_hh = W->rnn_w_hh;
+    a.w_pp = W->fc_embed_belief_prior_w; a.w_prior = W->fc_state_prior_w;
+    a.w_pq = W->fc_embed_belief_posterior_w; a.w_post = W->fc_state_posterior_w;
+    a.wblob = static_cast<uint8_t*>(ws);
+    pack_cluster_weights_kernel<<<dim3(6, kClSize), 256, 0, st>>>(a);
+    CUDA_OK(cudaGetLastError());
+  }
+  P.wblob = static_cast<const uint8_t*>(ws);
+  P.b_e = W->fc_embed_state_action_b; P.b_ih = W->rnn_b_ih; P.b_hh = W->rnn_b_hh;
+  P.b_pp = W->fc_embed_belief_prior_b; P.b_prior = W->fc_state_prior_b;
+  P.b_pq = W->fc_embed_belief_posterior_b; P.b_post = W->fc_state_posterior_b;
+  P.dbg_clock = g_dbg_clock;
+  if (cluster_max_active() <= 0) return fail(-5, "cluster observe: a 16-CTA cluster cannot be scheduled on this device");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kClSize * cdiv(P.N, kClRows));
+  cfg.blockDim = dim3(kClThreads);
+  cfg.dynamicSmemBytes = g.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kClSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, rssm_cluster_observe_kernel, P));
+  return 0;
+}
+
 }  // namespace
 int conv_gemm_impl(const void* input_, const float* w_mat, int w_ld, int w_col0, const float* bias, const void* relu_mask_,
                    const float* scales, void* out_, int frames, int n_total, ConvMap cm, int hl_flags, const int* dense_opts,
@@ -709,7 +788,7 @@ size_t repo_b200_imagine_workspace_bytes(const repo_b200_dims* d) {
   build_imagine(b, d, &W, &m, &m, &m, ACT_ELU);
   RBuilder rb_;
   build_imagine_rows(rb_, d, &W, &m, &m, &m, ACT_ELU);
-  return align_up(std::max(b.packed_bytes(), rb_.packed_bytes()), 256);
+  return align_up(std::max(std::max(b.packed_bytes(), rb_.packed_bytes()), cluster_blob_bytes(d)), 256);
 }
 
 int repo_b200_imagine_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const repo_b200_mlp_weights* actor,
@@ -1431,6 +1510,33 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   if (with_obs && (!eps_post || !post_states || !post_means || !post_std_devs)) return fail(-1, "observe: posterior buffers missing");
   if (ws_bytes < repo_b200_observe_workspace_bytes(d, t1, batch)) return fail(-4, "observe: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (row_tile == 1 && !use_cluster_observe(d, batch, row_tile))
+    return fail(-5, "observe: the cluster kernel (row_tile 1) does not take these sizes / this device");
+  if (use_cluster_observe(d, batch, row_tile)) {
+    // small batches: weights resident in the shared memory of a 16-CTA cluster (cluster.cuh), stash or not
+    const size_t main_c = observe_main_bytes(d);
+    const size_t lin_c = align_up(repo_b200_linear_workspace_bytes(d->embed, d->hidden), 256);
+    uint8_t* base_c = static_cast<uint8_t*>(ws);
+    float* addend_c = reinterpret_cast<float*>(base_c + main_c + lin_c);
+    if (with_obs) {
+      rc = run_linear(embeds, d->embed, t1 * batch, d->embed, W->fc_embed_belief_posterior_w, d->belief + d->embed,
+                      d->belief, nullptr, d->hidden, addend_c, d->hidden, base_c + main_c, lin_c, 0, st, 0);
+      if (rc) return rc;
+    }
+    ClParams C{};
+    C.T = t1; C.N = batch; C.D = d->belief; C.S = d->state; C.A = d->action; C.Hd = d->hidden;
+    C.act = act_kind == REPO_B200_ACT_ELU ? ACT_ELU : ACT_RELU;
+    C.with_obs = with_obs ? 1 : 0;
+    C.min_std = min_std;
+    C.init_belief = prev_belief; C.init_state = prev_state; C.actions = actions; C.nonterm = nonterm;
+    C.addend = with_obs ? addend_c : nullptr;
+    C.eps_prior = eps_prior; C.eps_post = eps_post;
+    C.beliefs = beliefs; C.prior_s = prior_states; C.prior_m = prior_means; C.prior_sd = prior_std_devs;
+    C.post_s = post_states; C.post_m = post_means; C.post_sd = post_std_devs;
+    C.kl = with_obs ? kl : nullptr;
+    C.stash = stash; C.stash_ld = 5 * d->belief + 2 * d->hidden;
+    return launch_cluster_observe(d, W, C, base_c, !(flags & REPO_B200_WEIGHTS_PACKED), st);
+  }
   const bool rows = !stash && use_rows_kernel(d, batch, row_tile) &&   // the activation stash is written by the vm kernel
                     rows_state_rows_aligned({eps_prior, eps_post, prior_states, prior_means, prior_std_devs, post_states, post_means, post_std_devs});
   Builder b;

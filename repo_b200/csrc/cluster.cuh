@@ -1,0 +1,606 @@
+// Small-batch observe: one thread-block cluster of 16 CTAs per 16 sequences, weights resident in shared memory.
+//
+// The layer machines (vm.cuh, rows.cuh) give every CTA a tile of rows and stream the whole model (1.4 MB) through it every
+// time step; at the reference's own operating point (batch 50 x 49 steps, experiments/train_repo.py:33-35) that is four CTAs
+// paying ~48 us of L2 latency per step.  Here the model is cut the other way: CTA c of a cluster owns output features
+// [16c, 16c+16) of every belief/hidden-wide layer (and state dimensions [8c, 8c+8) of the two Gaussian heads), its slice of
+// every weight matrix stays in its shared memory for the whole sequence as fp16 hi/lo core-matrix blocks (136 KB at the
+// default sizes), and the 16-row activations of a layer are exchanged between the CTAs with shared::cta -> shared::cluster
+// bulk copies (TMA engine, 1 KB per peer), each landing with complete_tx on the receiver's mbarrier — the arrival of the
+// data is the synchronisation, there is no cluster barrier inside the time loop.
+//
+// A time step of TransitionModel.observe (rssm.py:116-133) is four exchanges:
+//   E    h_e  = act(W_e [state | action] + b)                          -> all CTAs
+//   G    belief' = GRUCell(h_e, belief)                                 -> all CTAs   (W_hh . belief is issued before h_e arrives)
+//   PQ1  h_p = act(W_pp belief' + b),  h_q = act(W_pq belief' + addend[t] + b)   -> the CTAs that own state dimensions
+//   PQ2  prior / posterior mean, std, sample (owners of state dimensions only); next state -> all CTAs
+//
+// Activations are the A operand (M = 128 of which 16 rows exist: the descriptor's other row groups alias the neighbouring
+// bytes and produce accumulator lanes nobody reads), weights the B operand (N = 16..48), accumulators in TMEM with
+// lane = row.  Every product is the same hi*hi + lo*hi + hi*lo fp16 triple as in the other kernels.
+//
+// Buffer hazards: a CTA sends layer L's output only after its own layer-L MMAs, which needed every peer's layer L-1 output,
+// which each peer sent after finishing layer L-1 — so when the data lands, every peer is at most reading layer L's input.
+// The only layer whose output overlaps its own input is the GRU (belief -> belief'): the belief is double-buffered.
+#pragma once
+#include "ptx.cuh"
+#include "vm.cuh"
+
+namespace rb {
+
+constexpr int kClSize = 16;        // CTAs per cluster (non-portable size)
+constexpr int kClRows = 16;        // sequences per cluster
+constexpr int kClThreads = 512;    // warps 0,4,8,12: epilogue (TMEM lanes 0..31); warp 1: MMA issuer
+constexpr uint32_t kClTmemCols = 256;
+constexpr uint32_t kClSlab = 1024; // one k16 slab of a 16-row activation buffer: 2 k-groups x [hi 256 B | lo 256 B]
+
+struct ClGeom {
+  int nK;      // k16 slabs of a belief / hidden wide activation (= CTAs that own features)
+  int nS8;     // CTAs that own state dimensions (8 each)
+  int S8;      // state columns in the SA buffer
+  int kSA16;   // k16 slabs of [state | action]
+  int K, KSA;  // padded widths
+  uint32_t off_sa, off_h1, off_h2, off_b0, off_b1, off_w;  // byte offsets in dynamic shared memory
+  uint32_t w_e, w_hh, w_ih, w_pq1, w_pr, w_po;             // byte offsets inside a CTA's weight image
+  uint32_t cta_bytes;                                      // weight image per CTA
+  uint32_t off_bias, off_bar, smem_bytes;
+};
+
+__host__ __device__ inline bool cl_geometry(int D, int S, int A, int Hd, ClGeom& g) {
+  const int nD = (D + 15) / 16, nH = (Hd + 15) / 16;
+  if (nD != nH || nD > kClSize) return false;
+  g.nK = nD;
+  g.K = nD * 16;
+  g.nS8 = (S + 7) / 8;
+  if (g.nS8 > g.nK) return false;
+  g.S8 = g.nS8 * 8;
+  g.kSA16 = (g.S8 + A + 15) / 16;
+  g.KSA = g.kSA16 * 16;
+  uint32_t o = 0;
+  g.off_sa = o; o += (uint32_t)g.kSA16 * kClSlab;
+  g.off_h1 = o; o += (uint32_t)g.nK * kClSlab;
+  g.off_h2 = o; o += (uint32_t)g.nK * kClSlab;
+  g.off_b0 = o; o += (uint32_t)g.nK * kClSlab;
+  g.off_b1 = o; o += (uint32_t)g.nK * kClSlab;
+  g.off_w = o;
+  uint32_t w = 0;
+  g.w_e = w;   w += 4u * 16u * (uint32_t)g.KSA;
+  g.w_hh = w;  w += 4u * 48u * (uint32_t)g.K;
+  g.w_ih = w;  w += 4u * 48u * (uint32_t)g.K;
+  g.w_pq1 = w; w += 4u * 32u * (uint32_t)g.K;
+  g.w_pr = w;  w += 4u * 16u * (uint32_t)g.K;
+  g.w_po = w;  w += 4u * 16u * (uint32_t)g.K;
+  g.cta_bytes = w;
+  o += w;
+  if (w < 2048) return false;  // the aliased row groups of the last activation slab read up to 2 KB past it
+  g.off_bias = o; o += 144 * 4;
+  g.off_bar = o; o += 16 * 8 + 16;
+  g.smem_bytes = o;
+  return o <= 227u * 1024u;
+}
+
+struct ClParams {
+  int T, N;
+  int D, S, A, Hd;
+  int act, with_obs;
+  float min_std;
+  const uint8_t* wblob;  // kClSize weight images of cta_bytes each
+  const float *b_e, *b_ih, *b_hh, *b_pp, *b_prior, *b_pq, *b_post;
+  const float *init_belief, *init_state, *actions, *nonterm, *addend, *eps_prior, *eps_post;
+  float *beliefs, *prior_s, *prior_m, *prior_sd, *post_s, *post_m, *post_sd, *kl;
+  float* stash;
+  int stash_ld;
+  long long* dbg_clock;
+};
+
+struct ClPackArgs {
+  int D, S, A, Hd, E, with_obs;
+  const float *w_e, *w_ih, *w_hh, *w_pp, *w_prior, *w_pq, *w_post;
+  uint8_t* wblob;
+};
+
+// One block per (weight block kind, cluster rank): fp32 rows of the caller's matrices -> that CTA's fp16 hi/lo B-operand
+// block, element (n, k) at (k/8)*(N*16) + (n/8)*128 + (n%8)*16 + (k%8)*2, hi block then lo block.
+__global__ void __launch_bounds__(256) pack_cluster_weights_kernel(const __grid_constant__ ClPackArgs a) {
+  ClGeom g;
+  if (!cl_geometry(a.D, a.S, a.A, a.Hd, g)) return;
+  const int kind = blockIdx.x, c = blockIdx.y;
+  const int D = a.D, S = a.S, A = a.A, Hd = a.Hd;
+  int N, K;
+  uint32_t off;
+  switch (kind) {
+    case 0: N = 16; K = g.KSA; off = g.w_e; break;
+    case 1: N = 48; K = g.K; off = g.w_hh; break;
+    case 2: N = 48; K = g.K; off = g.w_ih; break;
+    case 3: N = 32; K = g.K; off = g.w_pq1; break;
+    case 4: N = 16; K = g.K; off = g.w_pr; break;
+    default: N = 16; K = g.K; off = g.w_po; break;
+  }
+  uint8_t* dst = a.wblob + (size_t)c * g.cta_bytes + off;
+  const uint32_t lo_delta = (uint32_t)N * (uint32_t)K * 2u;
+  for (int idx = threadIdx.x; idx < N * K; idx += blockDim.x) {
+    const int n = idx / K, k = idx - n * K;
+    float v = 0.f;
+    switch (kind) {
+      case 0: {  // fc_embed_state_action (D, S+A): columns [state padded to S8 | action]
+        const int f = 16 * c + n;
+        int col = -1;
+        if (k < S) col = k;
+        else if (k >= g.S8 && k < g.S8 + A) col = S + (k - g.S8);
+        if (f < D && col >= 0) v = a.w_e[(size_t)f * (S + A) + col];
+      } break;
+      case 1:    // rnn.weight_hh (3D, D): rows r | z | n of this CTA's 16 units
+      case 2: {  // rnn.weight_ih
+        const int gate = n >> 4, u = 16 * c + (n & 15);
+        const float* w = kind == 1 ? a.w_hh : a.w_ih;
+        if (u < D && k < D) v = w[(size_t)(gate * D + u) * D + k];
+      } break;
+      case 3: {  // fc_embed_belief_prior (H, D) | belief half of fc_embed_belief_posterior (H, D+E)
+        const int f = 16 * c + (n & 15);
+        if (f < Hd && k < D) {
+          if (n < 16) v = a.w_pp[(size_t)f * D + k];
+          else if (a.with_obs) v = a.w_pq[(size_t)f * (D + a.E) + k];
+        }
+      } break;
+      default: {  // fc_state_prior / fc_state_posterior (2S, H): rows mean | std of this CTA's 8 state dimensions
+        const int j = 8 * c + (n & 7);
+        const float* w = kind == 4 ? a.w_prior : a.w_post;
+        if (w && j < S && k < Hd) v = w[(size_t)((n >> 3) * S + j) * Hd + k];
+      } break;
+    }
+    __half h, l;
+    split_f16(v, h, l);
+    const uint32_t o = (uint32_t)(k >> 3) * (uint32_t)(N * 16) + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u +
+                       (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<__half*>(dst + o) = h;
+    *reinterpret_cast<__half*>(dst + lo_delta + o) = l;
+  }
+}
+
+// ----------------------------------------------------------------------------- cluster PTX
+__device__ __forceinline__ uint32_t cl_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cl_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cl_mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+// own shared memory -> a peer's shared memory, completion counted in bytes on the PEER's mbarrier
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+
+// byte offset of (row, column k) inside a 16-row activation buffer; the lo half sits 256 B behind the hi half
+__device__ __forceinline__ uint32_t cl_off(int row, int k) {
+  return (uint32_t)(k >> 3) * 512u + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u + (uint32_t)(k & 7) * 2u;
+}
+__device__ __forceinline__ void cl_put(uint8_t* buf, int row, int k, float v) {
+  __half h, l;
+  split_f16(v, h, l);
+  const uint32_t o = cl_off(row, k);
+  *reinterpret_cast<__half*>(buf + o) = h;
+  *reinterpret_cast<__half*>(buf + o + 256) = l;
+}
+// four consecutive columns (k % 4 == 0) of one row
+__device__ __forceinline__ void cl_put4(uint8_t* buf, int row, int k, const float* v) {
+  __align__(8) __half h[4];
+  __align__(8) __half l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_f16(v[i], h[i], l[i]);
+  const uint32_t o = cl_off(row, k);
+  *reinterpret_cast<uint2*>(buf + o) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(buf + o + 256) = *reinterpret_cast<const uint2*>(l);
+}
+__device__ __forceinline__ void cl_put2(uint8_t* buf, int row, int k, float v0, float v1) {
+  __align__(4) __half h[2];
+  __align__(4) __half l[2];
+  split_f16(v0, h[0], l[0]);
+  split_f16(v1, h[1], l[1]);
+  const uint32_t o = cl_off(row, k);
+  *reinterpret_cast<uint32_t*>(buf + o) = *reinterpret_cast<const uint32_t*>(h);
+  *reinterpret_cast<uint32_t*>(buf + o + 256) = *reinterpret_cast<const uint32_t*>(l);
+}
+
+__device__ __forceinline__ float cl_act(float x, int act) { return act == ACT_ELU ? act_t<ACT_ELU>(x) : act_t<ACT_RELU>(x); }
+
+enum ClBar { CB_W = 0, CB_IN_E, CB_IN_G, CB_IN_PQ1, CB_IN_PQ2, CB_ACC_E, CB_ACC_G, CB_ACC_PQ1, CB_ACC_PQ2, CB_COUNT };
+
+__global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(const __grid_constant__ ClParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  ClGeom g;
+  cl_geometry(P.D, P.S, P.A, P.Hd, g);
+  uint8_t* sa = smem + g.off_sa;
+  uint8_t* h1 = smem + g.off_h1;
+  uint8_t* h2 = smem + g.off_h2;
+  uint8_t* bb[2] = {smem + g.off_b0, smem + g.off_b1};
+  uint8_t* wsm = smem + g.off_w;
+  float* bias_s = reinterpret_cast<float*>(smem + g.off_bias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + CB_COUNT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = (int)cl_ctarank();
+  const int row0 = (int)(blockIdx.x / kClSize) * kClRows;
+  const int T = P.T, N = P.N, D = P.D, S = P.S, A = P.A, Hd = P.Hd;
+  const int nK = g.nK, nS8 = g.nS8;
+  const bool active = c < nK, owner = c < nS8, with_obs = P.with_obs != 0;
+  auto bar = [&](int i) { return smem_u32(bars + i); };
+
+  if (tid == 0) {
+    mbar_init(bar(CB_W), 1);
+    for (int i = CB_IN_E; i <= CB_IN_PQ2; ++i) mbar_init(bar(i), 2);  // the issuer's expect_tx + the local epilogue
+    for (int i = CB_ACC_E; i <= CB_ACC_PQ2; ++i) mbar_init(bar(i), 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), kClTmemCols);
+    tmem_relinquish();
+  }
+  // ---- init: zero the activation buffers, stage belief / state / action of step 0, biases of this CTA's features ----
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (uint32_t i = tid; i < g.off_w / 16; i += kClThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  if (active && tid == 0) {  // this CTA's weight image: resident for the whole sequence
+    mbar_arrive_expect_tx(bar(CB_W), g.cta_bytes);
+    const uint8_t* src = P.wblob + (size_t)c * g.cta_bytes;
+    for (uint32_t o = 0; o < g.cta_bytes; o += 32768u)
+      bulk_g2s(smem_u32(wsm + o), src + o, min(32768u, g.cta_bytes - o), bar(CB_W));
+  }
+  if (active) {
+    for (int idx = tid; idx < kClRows * D; idx += kClThreads) {
+      const int n = idx / D, k = idx - n * D, row = row0 + n;
+      if (row < N && P.init_belief) cl_put(bb[0], n, k, P.init_belief[(size_t)row * D + k]);
+    }
+    for (int idx = tid; idx < kClRows * S; idx += kClThreads) {
+      const int n = idx / S, k = idx - n * S, row = row0 + n;
+      if (row < N && P.init_state) {
+        float v = P.init_state[(size_t)row * S + k];
+        if (P.nonterm) v *= P.nonterm[row];
+        cl_put(sa, n, k, v);
+      }
+    }
+    for (int idx = tid; idx < kClRows * A; idx += kClThreads) {
+      const int n = idx / A, k = idx - n * A, row = row0 + n;
+      if (row < N) cl_put(sa, n, g.S8 + k, P.actions[(size_t)row * A + k]);
+    }
+    for (int i = tid; i < 144; i += kClThreads) {
+      float v = 0.f;
+      const int q = i >> 4, u = 16 * c + (i & 15);
+      if (i < 112) {
+        if (q == 0) v = u < D ? P.b_e[u] : 0.f;
+        else if (q == 1) v = u < D ? P.b_ih[u] + P.b_hh[u] : 0.f;
+        else if (q == 2) v = u < D ? P.b_ih[D + u] + P.b_hh[D + u] : 0.f;
+        else if (q == 3) v = u < D ? P.b_ih[2 * D + u] : 0.f;
+        else if (q == 4) v = u < D ? P.b_hh[2 * D + u] : 0.f;
+        else if (q == 5) v = u < Hd ? P.b_pp[u] : 0.f;
+        else v = (u < Hd && with_obs) ? P.b_pq[u] : 0.f;
+      } else {
+        const int h = (i - 112) >> 3, j = 8 * c + (i & 7);  // h: prior mean, prior std, post mean, post std
+        const float* b = h < 2 ? P.b_prior : P.b_post;
+        if (b && j < S && (h < 2 || with_obs)) v = b[(h & 1) * S + j];
+      }
+      bias_s[i] = v;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cl_sync_all();  // every CTA's barriers are initialised and its buffers staged before anybody sends
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+
+  if (active && warp == 1) {
+    // ================================ MMA issuer ================================
+    const uint64_t a_sa = make_smem_desc(smem_u32(sa), 512, 128), a_h1 = make_smem_desc(smem_u32(h1), 512, 128);
+    const uint64_t a_h2 = make_smem_desc(smem_u32(h2), 512, 128);
+    const uint64_t a_b[2] = {make_smem_desc(smem_u32(bb[0]), 512, 128), make_smem_desc(smem_u32(bb[1]), 512, 128)};
+    const uint64_t w_e = make_smem_desc(smem_u32(wsm + g.w_e), 16 * 16, 128);
+    const uint64_t w_hh = make_smem_desc(smem_u32(wsm + g.w_hh), 48 * 16, 128);
+    const uint64_t w_ih = make_smem_desc(smem_u32(wsm + g.w_ih), 48 * 16, 128);
+    const uint64_t w_pq1 = make_smem_desc(smem_u32(wsm + g.w_pq1), 32 * 16, 128);
+    const uint64_t w_pr = make_smem_desc(smem_u32(wsm + g.w_pr), 16 * 16, 128);
+    const uint64_t w_po = make_smem_desc(smem_u32(wsm + g.w_po), 16 * 16, 128);
+    constexpr uint32_t id16 = make_idesc_f16(128, 16), id32 = make_idesc_f16(128, 32), id48 = make_idesc_f16(128, 48);
+    // one product chain: D[128 x n] (+)= A[:, 16*ksl] * W^T; nrows = rows of the packed weight block (its k-group stride)
+    auto chain = [&](uint32_t d, uint64_t a, uint64_t w, int nrows, int wk, int ksl, uint32_t idesc, uint32_t acc0) {
+      const uint64_t w_step = (uint64_t)(nrows * 32) >> 4, w_lo = (uint64_t)(nrows * wk * 2) >> 4;
+      for (int k = 0; k < ksl; ++k) {
+        umma_f16(d, a, w, idesc, k == 0 ? acc0 : 1u);
+        umma_f16(d, a + (256 >> 4), w, idesc, 1u);
+        umma_f16(d, a, w + w_lo, idesc, 1u);
+        a += kClSlab >> 4;
+        w += w_step;
+      }
+    };
+    auto arm_wait = [&](int b, uint32_t tx, uint32_t parity) {
+      if (elect_one()) mbar_arrive_expect_tx(bar(b), tx);
+      __syncwarp();
+      mbar_wait(bar(b), parity);
+      tc_fence_after();
+    };
+    const uint32_t tx_e = (uint32_t)(nS8 - (owner ? 1 : 0)) * 512u;
+    const uint32_t tx_k = (uint32_t)(nK - 1) * kClSlab;
+    mbar_wait(bar(CB_W), 0);
+    for (int t = 0; t < T; ++t) {
+      const uint32_t ph = (uint32_t)t & 1u;
+      if (t > 0) arm_wait(CB_IN_E, tx_e, ph ^ 1u);
+      if (elect_one()) {
+        chain(tb + 64, a_sa, w_e, 16, g.KSA, g.kSA16, id16, 0u);
+        umma_commit(bar(CB_ACC_E));
+        if (t == 0) chain(tb + 0, a_b[0], w_hh, 48, g.K, nK, id48, 0u);  // W_hh . belief: r | z | h_n
+      }
+      __syncwarp();
+      arm_wait(CB_IN_G, tx_k, ph);
+      if (elect_one()) {
+        chain(tb + 0, a_h1, w_ih, 48, g.K, nK, id32, 1u);                                  // r, z += W_ih . h_e
+        chain(tb + 48, a_h1, w_ih + ((4u * 128u) >> 4), 48, g.K, nK, id16, 0u);            // i_n
+        umma_commit(bar(CB_ACC_G));
+      }
+      __syncwarp();
+      arm_wait(CB_IN_PQ1, tx_k, ph);
+      if (elect_one()) {
+        chain(tb + 80, a_b[(t + 1) & 1], w_pq1, 32, g.K, nK, id32, 0u);
+        umma_commit(bar(CB_ACC_PQ1));
+        if (t + 1 < T) chain(tb + 0, a_b[(t + 1) & 1], w_hh, 48, g.K, nK, id48, 0u);  // next step's W_hh . belief
+      }
+      __syncwarp();
+      if (owner) {
+        arm_wait(CB_IN_PQ2, tx_k * (with_obs ? 2u : 1u), ph);
+        if (elect_one()) {
+          chain(tb + 112, a_h1, w_pr, 16, g.K, nK, id16, 0u);
+          if (with_obs) chain(tb + 128, a_h2, w_po, 16, g.K, nK, id16, 0u);
+          umma_commit(bar(CB_ACC_PQ2));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (active && (warp & 3) == 0) {
+    // ================================ epilogue warps ================================
+    const int e = warp >> 2;          // 0..3: which 4 of this CTA's 16 features (2 of its 8 state dimensions)
+    const int r = lane & 15;          // row of the cluster's 16 (lanes 16..31 mirror 0..15 and stay silent)
+    const int row = row0 + r;
+    const bool row_ok = lane < 16 && row < N;
+    const int f0 = 16 * c + 4 * e;    // first of this thread's 4 features
+    const int j0 = 8 * c + 2 * e;     // first of this thread's 2 state dimensions
+    const int act = P.act;
+    auto epi_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    // send [off, off+bytes) of this CTA's shared memory to the same place in peers [0, npeers), then arrive locally
+    auto send = [&](uint32_t local_addr, uint32_t bytes, int npeers, int b) {
+      if (lane < npeers && lane != c) bulk_s2c(cl_mapa(local_addr, (uint32_t)lane), local_addr, bytes, cl_mapa(bar(b), (uint32_t)lane));
+    };
+    float be[4], br[4], bz[4], bin[4], bhn[4], bpp[4], bpq[4], bprev[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      be[i] = bias_s[4 * e + i];
+      br[i] = bias_s[16 + 4 * e + i];
+      bz[i] = bias_s[32 + 4 * e + i];
+      bin[i] = bias_s[48 + 4 * e + i];
+      bhn[i] = bias_s[64 + 4 * e + i];
+      bpp[i] = bias_s[80 + 4 * e + i];
+      bpq[i] = bias_s[96 + 4 * e + i];
+      bprev[i] = (row_ok && P.init_belief && f0 + i < D) ? P.init_belief[(size_t)row * D + f0 + i] : 0.f;
+    }
+    float bpm[2], bps[2], bqm[2], bqs[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      bpm[i] = bias_s[112 + 2 * e + i];
+      bps[i] = bias_s[120 + 2 * e + i];
+      bqm[i] = bias_s[128 + 2 * e + i];
+      bqs[i] = bias_s[136 + 2 * e + i];
+    }
+    for (int t = 0; t < T; ++t) {
+      const uint32_t ph = (uint32_t)t & 1u;
+      const size_t trow = (size_t)t * N;
+      const bool has_next = t + 1 < T;
+      float* stash = (P.stash && row_ok) ? P.stash + (trow + row) * P.stash_ld : nullptr;
+      // per-step inputs, requested before the first wait
+      float ad[4] = {0.f, 0.f, 0.f, 0.f}, ep[2] = {0.f, 0.f}, eq[2] = {0.f, 0.f}, nt = 1.f;
+      if (row_ok) {
+        if (with_obs) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (f0 + i < Hd) ad[i] = __ldg(P.addend + (trow + row) * Hd + f0 + i);
+        }
+        if (owner) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (j0 + i < S) {
+              ep[i] = __ldg(P.eps_prior + (trow + row) * S + j0 + i);
+              if (with_obs) eq[i] = __ldg(P.eps_post + (trow + row) * S + j0 + i);
+            }
+          if (has_next && P.nonterm) nt = __ldg(P.nonterm + trow + N + row);
+        }
+      }
+      // ---- E: h_e = act(W_e [state | action] + b) -> H1 slab c of every CTA
+      {
+        mbar_wait(bar(CB_ACC_E), ph);
+        tc_fence_after();
+        float v[4];
+        tmem_ld4(tb + 64 + 4 * e, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (f0 + i < D) ? cl_act(v[i] + be[i], act) : 0.f;
+        if (lane < 16) cl_put4(h1, r, f0, v);
+        if (stash) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (f0 + i < D) stash[f0 + i] = v[i];
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        epi_sync();
+        if (e == 0) {
+          send(smem_u32(h1) + (uint32_t)c * kClSlab, kClSlab, nK, CB_IN_G);
+          if (lane == 0) mbar_arrive(bar(CB_IN_G));
+        }
+      }
+      // ---- G: GRUCell gates -> belief' -> B[(t+1)&1] slab c of every CTA, beliefs[t]
+      {
+        mbar_wait(bar(CB_ACC_G), ph);
+        tc_fence_after();
+        float vr[4], vz[4], vh[4], vi[4], bn[4];
+        tmem_ld4(tb + 0 + 4 * e, vr);
+        tmem_ld4(tb + 16 + 4 * e, vz);
+        tmem_ld4(tb + 32 + 4 * e, vh);
+        tmem_ld4(tb + 48 + 4 * e, vi);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float rr = sigmoid_f(vr[i] + br[i]);
+          const float zz = sigmoid_f(vz[i] + bz[i]);
+          const float hn = vh[i] + bhn[i];
+          const float nn = tanh_f(vi[i] + bin[i] + rr * hn);
+          bn[i] = (f0 + i < D) ? (1.f - zz) * nn + zz * bprev[i] : 0.f;
+          bprev[i] = bn[i];
+          if (stash && f0 + i < D) {
+            float* sp = stash + D + f0 + i;
+            sp[0] = rr; sp[D] = zz; sp[2 * D] = nn; sp[3 * D] = hn;
+          }
+        }
+        uint8_t* bnew = bb[(t + 1) & 1];
+        if (lane < 16) cl_put4(bnew, r, f0, bn);
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (f0 + i < D) P.beliefs[(trow + row) * D + f0 + i] = bn[i];
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        epi_sync();
+        if (e == 0) {
+          send(smem_u32(bnew) + (uint32_t)c * kClSlab, kClSlab, nK, CB_IN_PQ1);
+          if (lane == 0) mbar_arrive(bar(CB_IN_PQ1));
+        }
+      }
+      // ---- PQ1: prior / posterior hidden layers -> H1 / H2 slab c of the CTAs that own state dimensions
+      {
+        mbar_wait(bar(CB_ACC_PQ1), ph);
+        tc_fence_after();
+        float vp[4], vq[4];
+        tmem_ld4(tb + 80 + 4 * e, vp);
+        tmem_ld4(tb + 96 + 4 * e, vq);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vp[i] = (f0 + i < Hd) ? cl_act(vp[i] + bpp[i], act) : 0.f;
+          vq[i] = (f0 + i < Hd && with_obs) ? cl_act(vq[i] + bpq[i] + ad[i], act) : 0.f;
+        }
+        if (lane < 16) {
+          cl_put4(h1, r, f0, vp);
+          if (with_obs) cl_put4(h2, r, f0, vq);
+        }
+        if (stash) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (f0 + i < Hd) {
+              stash[5 * D + f0 + i] = vp[i];
+              if (with_obs) stash[5 * D + Hd + f0 + i] = vq[i];
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        epi_sync();
+        if (e == 0) {
+          send(smem_u32(h1) + (uint32_t)c * kClSlab, kClSlab, nS8, CB_IN_PQ2);
+          if (with_obs) send(smem_u32(h2) + (uint32_t)c * kClSlab, kClSlab, nS8, CB_IN_PQ2);
+          if (owner && lane == 0) mbar_arrive(bar(CB_IN_PQ2));
+        }
+      }
+      // ---- PQ2: Gaussian heads (owners of state dimensions), next step's state and action -> SA of every CTA
+      {
+        if (owner) {
+          mbar_wait(bar(CB_ACC_PQ2), ph);
+          tc_fence_after();
+          float pm[2], ps[2], qm[2] = {0.f, 0.f}, qs[2] = {0.f, 0.f};
+          tmem_ld2(tb + 112 + 2 * e, pm);
+          tmem_ld2(tb + 120 + 2 * e, ps);
+          if (with_obs) {
+            tmem_ld2(tb + 128 + 2 * e, qm);
+            tmem_ld2(tb + 136 + 2 * e, qs);
+          }
+          tmem_ld_wait();
+          float nxt[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const bool vj = j0 + i < S;
+            const float m = pm[i] + bpm[i];
+            const float sd = softplus_f(ps[i] + bps[i]) + P.min_std;
+            const float smp = m + sd * ep[i];
+            nxt[i] = smp;
+            if (row_ok && vj) {
+              const size_t o = (trow + row) * S + j0 + i;
+              P.prior_s[o] = smp; P.prior_m[o] = m; P.prior_sd[o] = sd;
+            }
+            if (with_obs) {
+              const float m2 = qm[i] + bqm[i];
+              const float sd2 = softplus_f(qs[i] + bqs[i]) + P.min_std;
+              const float smp2 = m2 + sd2 * eq[i];
+              nxt[i] = smp2;
+              if (row_ok && vj) {
+                const size_t o = (trow + row) * S + j0 + i;
+                P.post_s[o] = smp2; P.post_m[o] = m2; P.post_sd[o] = sd2;
+              }
+            }
+            if (!vj || !row_ok) nxt[i] = 0.f;
+          }
+          if (has_next && lane < 16) cl_put2(sa, r, j0, nxt[0] * nt, nxt[1] * nt);
+        }
+        if (has_next) {
+          if (row_ok)
+            for (int a = e; a < A; a += 4) cl_put(sa, r, g.S8 + a, __ldg(P.actions + (trow + N + row) * A + a));
+          fence_proxy_async_smem();
+          tc_fence_before();
+          epi_sync();
+          if (e == 0) {
+            if (owner) send(smem_u32(sa) + (uint32_t)c * 512u, 512u, nK, CB_IN_E);
+            if (lane == 0) mbar_arrive(bar(CB_IN_E));
+          }
+        }
+      }
+    }
+  }
+
+  // ---- KL[t, row] = sum_j KL(posterior || prior): after the loop, from the stored moments (deterministic order) ----
+  tc_fence_before();
+  cl_sync_all();   // also: nobody exits while a peer may still write into its shared memory
+  if (P.kl && with_obs) {
+    for (int item = c * kClThreads + tid; item < T * kClRows; item += kClSize * kClThreads) {
+      const int t = item / kClRows, row = row0 + (item % kClRows);
+      if (row < N) {
+        const size_t o = ((size_t)t * N + row) * S;
+        float acc = 0.f;
+        for (int j = 0; j < S; ++j) {
+          const float psd = P.prior_sd[o + j], ratio = P.post_sd[o + j] / psd, vr = ratio * ratio;
+          const float dm = (P.post_m[o + j] - P.prior_m[o + j]) / psd;
+          acc += 0.5f * (vr + dm * dm - 1.f - logf(vr));
+        }
+        P.kl[(size_t)t * N + row] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tb, kClTmemCols);
+}
+
+}  // namespace rb

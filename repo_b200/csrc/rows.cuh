@@ -1047,8 +1047,28 @@ __global__ void __launch_bounds__(kRowsThreads, 1) rssm_rows_kernel(const __grid
               float pm[8], psd[8];
               const size_t o = (trow + row) * S + c;
               if (want_kl) {
-                ld_row8_v2<false>(pm, V.prior_m + o, nv, row_ok);
-                ld_row8_v2<false>(psd, V.prior_sd + o, nv, row_ok);
+                // The prior's mean / std of this very (row, state group) were computed by this thread two stages ago.  If the
+                // prior stage parked them in tensor memory for its transposed stores (see below: same condition, same
+                // columns — nothing has written them since: the posterior hidden layer works in the other region, this
+                // stage's accumulators occupy columns [0, 2W) of this one), they are read back from there; the global
+                // re-read (lane = row, 30-float rows: 32 cache lines per load) made this epilogue 9.3k cycles against 1.5k
+                // for the prior's.
+                bool parked = false;
+                if (s >= 2 && P.stages[s - 2].epi == R_PRIOR && 2 * (int)P.stages[s - 2].width <= 128) {
+                  const RStage& pn = P.stages[s - 1];   // the stage that followed the prior head
+                  bool pn_reads_h = false;
+                  for (int g = pn.gemm_begin; g < pn.gemm_end; ++g) pn_reads_h |= P.gemms[g].a_src == 1;
+                  if (!pn_reads_h) {
+                    const uint32_t tpr = tl + ((pn.regs & 1) ? 0u : kAccCol) + 128u + (uint32_t)(part * 32);
+                    tmem_ld8(tpr + 8, pm);
+                    tmem_ld8(tpr + 16, psd);
+                    parked = true;
+                  }
+                }
+                if (!parked) {
+                  ld_row8_v2<false>(pm, V.prior_m + o, nv, row_ok);
+                  ld_row8_v2<false>(psd, V.prior_sd + o, nv, row_ok);
+                }
               }
               tmem_ld8(tacc + c, vm);
               tmem_ld8(tacc + W + c, vs);

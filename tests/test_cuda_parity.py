@@ -107,6 +107,53 @@ def test_small_actions_keep_relative_accuracy(ops, dev, row_tile):
     close(out["actions"], want[4], "small actions", rtol=1e-3, atol=5e-8)
 
 
+@pytest.mark.parametrize("name", C.OBSERVE_CASES)
+def test_cluster_observe_vs_golden_and_oracle(ops, dev, name):
+    """row_tile=1: the 16-CTA cluster kernel (weights resident in shared memory, activations exchanged through distributed
+    shared memory) on every observe fixture it takes; the stash it writes for the backward pass must match the vm kernel's."""
+    params, x, gold, meta = C.observe_case(name)
+    d = C.dims_of(meta)
+    if (d["belief"] + 15) // 16 != (d["hidden"] + 15) // 16:
+        with pytest.raises(RuntimeError):
+            run_observe(ops, dev, params, x, 1)
+        return
+    g = lambda k: None if x[k] is None else x[k].to(dev)
+    T1, B = x["actions"].shape[:2]
+    stash = torch.zeros(T1, B, 5 * d["belief"] + 2 * d["hidden"], device=dev)
+    outs, kl, _ = ops.observe_fwd(cu(params, dev), g("prev_belief"), g("prev_state"), g("actions"), g("embeds"), g("nonterms"),
+                                  g("eps_prior"), g("eps_post"), row_tile=1, stash=stash)
+    want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"],
+                     x["eps_prior"], x["eps_post"])
+    keep = int(meta["keep"])
+    for nm, o, w in zip(C.OBS_NAMES, outs, want):
+        close(o, w, f"{name}/{nm} vs oracle")
+        close(o if keep == 0 else o[-keep:], gold[nm], f"{name}/{nm} vs reference fixture")
+    if meta["use_obs"]:
+        close(kl, gold["kl_tb"], f"{name}/kl", atol=1e-3)
+        close(kl, O.kl_sum(want[5], want[6], want[2], want[3]), f"{name}/kl vs oracle", atol=1e-4)
+    stash_vm = torch.zeros_like(stash)
+    ops.observe_fwd(cu(params, dev), g("prev_belief"), g("prev_state"), g("actions"), g("embeds"), g("nonterms"),
+                    g("eps_prior"), g("eps_post"), row_tile=16, stash=stash_vm)
+    close(stash, stash_vm.cpu(), f"{name}/stash vs the vm kernel")
+
+
+@pytest.mark.parametrize("T,B", [(49, 50), (3, 1), (6, 16), (4, 17), (5, 200)])
+def test_cluster_observe_batch_shapes(ops, dev, T, B):
+    """partial clusters (B not a multiple of 16), one row, more clusters than fit at once; auto routing picks the cluster
+    kernel for these batches and must agree with the explicit request bit for bit"""
+    params = O.make_transition_params(900 + B)
+    x = O.make_observe_inputs(901 + T, T, B, p_done=0.2)
+    outs, kl = run_observe(ops, dev, params, x, row_tile=1)
+    want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"], x["eps_prior"], x["eps_post"])
+    for nm, o, w in zip(C.OBS_NAMES, outs, want):
+        close(o, w, f"cluster observe {T}x{B}/{nm}")
+    close(kl, O.kl_sum(want[5], want[6], want[2], want[3]), "cluster observe/kl", atol=1e-4)
+    auto, kl_auto = run_observe(ops, dev, params, x, row_tile=0)
+    for o, a_ in zip(outs, auto):
+        assert torch.equal(o, a_)
+    assert torch.equal(kl, kl_auto)
+
+
 def test_observe_multi_tile_tiled_addend_vs_oracle(ops, dev):
     """observe on the 128-row kernel across three row tiles, the last one partial (300 = 128 + 128 + 44 sequences): the hoisted
     embedding projection travels in the per-tile quarter-chunk layout here (>= 256 rows), row-major in the small golden cases."""
