@@ -150,6 +150,20 @@ int repo_b200_observe_bwd(const repo_b200_dims* dims, const repo_b200_rssm_weigh
                           float* d_p, float* d_hp, float* d_gi, float* d_gh, float* d_e, float* d_prev_belief,
                           float* d_prev_state, int t1, int batch, int with_obs, int act_kind, float min_std_dev,
                           void* stream);
+/* Same pass with a caller-provided workspace (>= repo_b200_observe_bwd_workspace_bytes, 16-byte aligned), which lets small
+ * batches run on the cluster kernel (csrc/cluster_bwd.cuh: transposed weight slices resident in the shared memory of a
+ * 16-CTA cluster, every dx = dy W on the tensor cores, per-sequence power-of-two units).  mode: 0 = auto (cluster kernel when
+ * it takes the sizes and batch <= 256, else the kernel above), 1 = cluster kernel or an error, 2 = the kernel above. */
+size_t repo_b200_observe_bwd_workspace_bytes(const repo_b200_dims* dims, int batch);
+int repo_b200_observe_bwd_ws(const repo_b200_dims* dims, const repo_b200_rssm_weights* rssm, const float* prev_belief,
+                             const float* beliefs, const float* prior_std_devs, const float* posterior_std_devs,
+                             const float* eps_prior, const float* eps_post, const float* nonterminals, const float* stash,
+                             const float* g_beliefs, const float* g_prior_states, const float* g_prior_means,
+                             const float* g_prior_std_devs, const float* g_posterior_states,
+                             const float* g_posterior_means, const float* g_posterior_std_devs, float* d_q, float* d_hq,
+                             float* d_p, float* d_hp, float* d_gi, float* d_gh, float* d_e, float* d_prev_belief,
+                             float* d_prev_state, int t1, int batch, int with_obs, int act_kind, float min_std_dev,
+                             void* workspace, size_t workspace_bytes, int mode, void* stream);
 
 /* ---- cell: TransitionModel.compute_prior_state (rssm.py:42-50; embed == NULL) or
  * compute_posterior_state (rssm.py:52-64; embed (N,E)).  belief (N,D), eps (N,S) -> state, mean, std_dev (N,S). */

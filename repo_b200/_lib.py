@@ -38,6 +38,7 @@ EXPORTS = [
     "repo_b200_version", "repo_b200_last_error", "repo_b200_device_info", "repo_b200_debug_flags", "repo_b200_debug_clock",
     "repo_b200_imagine_workspace_bytes", "repo_b200_imagine_fwd", "repo_b200_imagine_stash_floats", "repo_b200_imagine_bwd", "repo_b200_imagine_cond_fwd", "repo_b200_imagine_cond_bwd",
     "repo_b200_observe_workspace_bytes", "repo_b200_observe_fwd", "repo_b200_observe_stash_floats", "repo_b200_observe_bwd",
+    "repo_b200_observe_bwd_workspace_bytes", "repo_b200_observe_bwd_ws",
     "repo_b200_linear_workspace_bytes", "repo_b200_linear_fwd",
     "repo_b200_head_workspace_bytes", "repo_b200_head_fwd",
     "repo_b200_tanh_normal_entropy_fwd", "repo_b200_replay_gather",
@@ -94,6 +95,10 @@ def lib():
     L.repo_b200_observe_stash_floats.restype = ci
     L.repo_b200_observe_bwd.argtypes = [C.POINTER(Dims), C.POINTER(RssmWeights)] + [vp] * 24 + [ci, ci, ci, ci, cf, vp]
     L.repo_b200_observe_bwd.restype = ci
+    L.repo_b200_observe_bwd_workspace_bytes.argtypes = [C.POINTER(Dims), ci]
+    L.repo_b200_observe_bwd_workspace_bytes.restype = sz
+    L.repo_b200_observe_bwd_ws.argtypes = ([C.POINTER(Dims), C.POINTER(RssmWeights)] + [vp] * 24 + [ci, ci, ci, ci, cf, vp, sz, ci, vp])
+    L.repo_b200_observe_bwd_ws.restype = ci
     L.repo_b200_head_workspace_bytes.argtypes = [C.POINTER(Dims)]
     L.repo_b200_head_workspace_bytes.restype = sz
     L.repo_b200_head_fwd.argtypes = [C.POINTER(Dims), C.POINTER(MlpWeights), vp, vp, vp, ci, ci, vp, sz, ci, ci, vp]

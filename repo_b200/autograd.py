@@ -33,6 +33,9 @@ def _wgrad(dpre, x):
 PARAM_KEYS = [k for _, k in ops._RSSM_KEYS]
 
 
+# 0 = auto (cluster kernel for small batches), 1 = cluster kernel or an error, 2 = the per-sequence fp32 kernel (tests)
+OBSERVE_BWD_MODE = 0
+
 class ObserveFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, act, min_std, prev_belief, prev_state, actions, observations, nonterminals, eps_prior, eps_post,
@@ -78,12 +81,14 @@ class ObserveFn(torch.autograd.Function):
         nt = None if nonterminals is None else nonterminals.reshape(T1, B).contiguous()
         p = ops._ptr
         L = _lib.lib()
-        rc = L.repo_b200_observe_bwd(
+        # small batches: the cluster kernel (transposed weight slices resident in shared memory) needs a workspace
+        ws = torch.empty(L.repo_b200_observe_bwd_workspace_bytes(C.byref(d), B), dtype=torch.uint8, device=dev)
+        rc = L.repo_b200_observe_bwd_ws(
             C.byref(d), C.byref(W), p(prev_belief.contiguous()), p(beliefs), p(prior_sd), p(post_sd), p(eps_prior), p(eps_post),
             p(nt), p(stash), p(g[0]), p(g[1]), p(g[2]), p(g[3]), p(g[4]), p(g[5]), p(g[6]), p(d_q), p(d_hq), p(d_p), p(d_hp),
             p(d_gi), p(d_gh), p(d_e), p(d_b0), p(d_s0), T1, B, int(ctx.with_obs), ops.act_kind(ctx.act), float(ctx.min_std),
-            ops._stream())
-        _lib.check(rc, "repo_b200_observe_bwd")
+            p(ws), ws.numel(), OBSERVE_BWD_MODE, ops._stream())
+        _lib.check(rc, "repo_b200_observe_bwd_ws")
 
         # ---- weight gradients: dW = dpre^T @ input over all (t,b) rows (plain GEMMs) ----
         flat = lambda x: x.reshape(T1 * B, -1)

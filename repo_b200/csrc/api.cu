@@ -18,6 +18,7 @@
 #include "conv.cuh"
 #include "elementwise.cuh"
 #include "bwd.cuh"
+#include "cluster_bwd.cuh"
 #include "optim.cuh"
 
 using namespace rb;
@@ -921,6 +922,102 @@ int repo_b200_observe_bwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   const size_t smem = (size_t)(10 * P.D + 5 * P.S + P.Hd + kObsGroups * 256) * sizeof(float);
   observe_bwd_kernel<<<batch, 256 * kObsGroups, smem, static_cast<cudaStream_t>(stream)>>>(P);
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+size_t repo_b200_observe_bwd_workspace_bytes(const repo_b200_dims* d, int batch) {
+  if (check_dims(d) || batch < 0) return 0;
+  ClBwdGeom g;
+  if (!clb_geometry(d->belief, d->state, d->action, d->hidden, g)) return 256;
+  return align_up((size_t)kClSize * g.cta_bytes, 256) + align_up((size_t)std::max(batch, 1) * 2 * sizeof(float), 256);
+}
+
+static int cluster_bwd_max_active() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  ClBwdGeom g;
+  if (!clb_geometry(200, 30, 6, 200, g)) return cached = 0;
+  if (cudaFuncSetAttribute(rssm_cluster_observe_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+      cudaFuncSetAttribute(rssm_cluster_observe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    cudaGetLastError();
+    return cached = 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kClSize * 8);
+  cfg.blockDim = dim3(kClThreads);
+  cfg.dynamicSmemBytes = g.smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kClSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, rssm_cluster_observe_bwd_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  return cached = n;
+}
+
+int repo_b200_observe_bwd_ws(const repo_b200_dims* d, const repo_b200_rssm_weights* W, const float* prev_belief,
+                             const float* beliefs, const float* prior_std_devs, const float* post_std_devs,
+                             const float* eps_prior, const float* eps_post, const float* nonterminals, const float* stash,
+                             const float* g_beliefs, const float* g_prior_states, const float* g_prior_means,
+                             const float* g_prior_std_devs, const float* g_post_states, const float* g_post_means,
+                             const float* g_post_std_devs, float* d_q, float* d_hq, float* d_p, float* d_hp, float* d_gi,
+                             float* d_gh, float* d_e, float* d_prev_belief, float* d_prev_state, int t1, int batch,
+                             int with_obs, int act_kind, float min_std, void* ws, size_t ws_bytes, int mode, void* stream) {
+  int rc = check_dims(d);
+  if (rc) return rc;
+  if (mode < 0 || mode > 2) return fail(-1, "observe_bwd: mode %d unknown (0 auto, 1 cluster, 2 per-sequence kernel)", mode);
+  ClBwdGeom g;
+  const bool fits = clb_geometry(d->belief, d->state, d->action, d->hidden, g);
+  bool cluster = mode != 2 && fits && ws && ws_bytes >= repo_b200_observe_bwd_workspace_bytes(d, batch) &&
+                 (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && (mode == 1 || (batch <= kClusterAutoBatch && !(g_dbg_flags & 8)));
+  if (cluster && t1 > 0 && batch > 0 && cluster_bwd_max_active() <= 0) cluster = false;
+  if (mode == 1 && !cluster)
+    return fail(-5, "observe_bwd: the cluster kernel (mode 1) does not take these sizes / this workspace / this device");
+  if (!cluster)
+    return repo_b200_observe_bwd(d, W, prev_belief, beliefs, prior_std_devs, post_std_devs, eps_prior, eps_post, nonterminals,
+                                 stash, g_beliefs, g_prior_states, g_prior_means, g_prior_std_devs, g_post_states,
+                                 g_post_means, g_post_std_devs, d_q, d_hq, d_p, d_hp, d_gi, d_gh, d_e, d_prev_belief,
+                                 d_prev_state, t1, batch, with_obs, act_kind, min_std, stream);
+  if ((rc = check_act(act_kind))) return rc;
+  if (t1 < 0 || batch < 0) return fail(-1, "observe_bwd: bad sizes");
+  if (t1 == 0 || batch == 0) return 0;
+  if (!W || !beliefs || !prior_std_devs || !eps_prior || !stash || !d_p || !d_hp || !d_gi || !d_gh || !d_e)
+    return fail(-1, "observe_bwd: NULL pointer");
+  if (with_obs && (!post_std_devs || !eps_post || !d_q || !d_hq)) return fail(-1, "observe_bwd: posterior buffers missing");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  float* scales = reinterpret_cast<float*>(base + align_up((size_t)kClSize * g.cta_bytes, 256));
+  ClBwdPackArgs a{};
+  a.D = d->belief; a.S = d->state; a.A = d->action; a.Hd = d->hidden; a.E = d->embed; a.with_obs = with_obs;
+  a.w_e = W->fc_embed_state_action_w; a.w_ih = W->rnn_w_ih; a.w_hh = W->rnn_w_hh;
+  a.w_pp = W->fc_embed_belief_prior_w; a.w_prior = W->fc_state_prior_w;
+  a.w_pq = W->fc_embed_belief_posterior_w; a.w_post = W->fc_state_posterior_w;
+  a.wblob = base;
+  pack_cluster_bwd_weights_kernel<<<dim3(7, kClSize), 256, 0, st>>>(a);
+  CUDA_OK(cudaGetLastError());
+  ClBwdParams P{};
+  P.T = t1; P.N = batch; P.D = d->belief; P.S = d->state; P.A = d->action; P.Hd = d->hidden;
+  P.act = act_kind; P.with_obs = with_obs; P.min_std = min_std;
+  P.wblob = base; P.scales = scales;
+  P.init_belief = prev_belief; P.beliefs = beliefs; P.prior_sd = prior_std_devs; P.post_sd = post_std_devs;
+  P.eps_prior = eps_prior; P.eps_post = eps_post; P.nonterm = nonterminals;
+  P.stash = stash; P.stash_ld = 5 * d->belief + 2 * d->hidden;
+  P.g_beliefs = g_beliefs; P.g_prior_s = g_prior_states; P.g_prior_m = g_prior_means; P.g_prior_sd = g_prior_std_devs;
+  P.g_post_s = g_post_states; P.g_post_m = g_post_means; P.g_post_sd = g_post_std_devs;
+  P.d_q = d_q; P.d_hq = d_hq; P.d_p = d_p; P.d_hp = d_hp; P.d_gi = d_gi; P.d_gh = d_gh; P.d_e = d_e;
+  P.d_init_belief = d_prev_belief; P.d_init_state = d_prev_state;
+  observe_bwd_scale_kernel<<<batch, 256, 0, st>>>(P, scales);
+  CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(kClSize * cdiv(batch, kClRows));
+  cfg.blockDim = dim3(kClThreads);
+  cfg.dynamicSmemBytes = g.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kClSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, rssm_cluster_observe_bwd_kernel, P));
   return 0;
 }
 
