@@ -653,6 +653,11 @@ int cluster_max_active() {   // co-resident 16-CTA clusters of the kernel on thi
   return cached = n;
 }
 
+bool ptrs_aligned(std::initializer_list<const void*> ptrs, uintptr_t a) {
+  for (const void* p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) & (a - 1)) return false;
+  return true;
+}
 bool cluster_observe_fits(const repo_b200_dims* d) {
   ClGeom g;
   return cl_geometry(d->belief, d->state, d->action, d->hidden, g);
@@ -681,7 +686,7 @@ int launch_cluster_observe(const repo_b200_dims* d, const repo_b200_rssm_weights
     a.w_pp = W->fc_embed_belief_prior_w; a.w_prior = W->fc_state_prior_w;
     a.w_pq = W->fc_embed_belief_posterior_w; a.w_post = W->fc_state_posterior_w;
     a.wblob = static_cast<uint8_t*>(ws);
-    pack_cluster_weights_kernel<<<dim3(6, kClSize), 256, 0, st>>>(a);
+    pack_cluster_weights_kernel<<<dim3(8, kClSize), 256, 0, st>>>(a);
     CUDA_OK(cudaGetLastError());
   }
   P.wblob = static_cast<const uint8_t*>(ws);
@@ -969,7 +974,10 @@ int repo_b200_observe_bwd_ws(const repo_b200_dims* d, const repo_b200_rssm_weigh
   ClBwdGeom g;
   const bool fits = clb_geometry(d->belief, d->state, d->action, d->hidden, g);
   bool cluster = mode != 2 && fits && ws && ws_bytes >= repo_b200_observe_bwd_workspace_bytes(d, batch) &&
-                 (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && (mode == 1 || (batch <= kClusterAutoBatch && !(g_dbg_flags & 8)));
+                 (mode == 1 || (batch <= kClusterAutoBatch && !(g_dbg_flags & 8))) &&
+                 ptrs_aligned({ws, prev_belief, beliefs, stash, g_beliefs, d_hq, d_hp, d_gi, d_gh, d_e}, 16) &&
+                 ptrs_aligned({prior_std_devs, post_std_devs, eps_prior, eps_post, g_prior_states, g_prior_means, g_prior_std_devs,
+                               g_post_states, g_post_means, g_post_std_devs, d_q, d_p}, 8);
   if (cluster && t1 > 0 && batch > 0 && cluster_bwd_max_active() <= 0) cluster = false;
   if (mode == 1 && !cluster)
     return fail(-5, "observe_bwd: the cluster kernel (mode 1) does not take these sizes / this workspace / this device");
@@ -1006,6 +1014,7 @@ int repo_b200_observe_bwd_ws(const repo_b200_dims* d, const repo_b200_rssm_weigh
   P.g_post_s = g_post_states; P.g_post_m = g_post_means; P.g_post_sd = g_post_std_devs;
   P.d_q = d_q; P.d_hq = d_hq; P.d_p = d_p; P.d_hp = d_hp; P.d_gi = d_gi; P.d_gh = d_gh; P.d_e = d_e;
   P.d_init_belief = d_prev_belief; P.d_init_state = d_prev_state;
+  P.dbg_clock = g_dbg_clock;
   observe_bwd_scale_kernel<<<batch, 256, 0, st>>>(P, scales);
   CUDA_OK(cudaGetLastError());
   cudaLaunchConfig_t cfg{};
@@ -1607,9 +1616,12 @@ int repo_b200_observe_fwd(const repo_b200_dims* d, const repo_b200_rssm_weights*
   if (with_obs && (!eps_post || !post_states || !post_means || !post_std_devs)) return fail(-1, "observe: posterior buffers missing");
   if (ws_bytes < repo_b200_observe_workspace_bytes(d, t1, batch)) return fail(-4, "observe: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (row_tile == 1 && !use_cluster_observe(d, batch, row_tile))
-    return fail(-5, "observe: the cluster kernel (row_tile 1) does not take these sizes / this device");
-  if (use_cluster_observe(d, batch, row_tile)) {
+  // the cluster kernel moves a thread's 4 features / 2 state dimensions with one vector access
+  const bool cl_aligned = ptrs_aligned({prev_belief, beliefs, stash, ws}, 16) &&
+                          ptrs_aligned({eps_prior, eps_post, prior_states, prior_means, prior_std_devs, post_states, post_means, post_std_devs}, 8);
+  if (row_tile == 1 && !(cl_aligned && use_cluster_observe(d, batch, row_tile)))
+    return fail(-5, "observe: the cluster kernel (row_tile 1) does not take these sizes / this alignment / this device");
+  if (cl_aligned && use_cluster_observe(d, batch, row_tile)) {
     // small batches: weights resident in the shared memory of a 16-CTA cluster (cluster.cuh), stash or not
     const size_t main_c = observe_main_bytes(d);
     const size_t lin_c = align_up(repo_b200_linear_workspace_bytes(d->embed, d->hidden), 256);

@@ -17,7 +17,11 @@
 //
 // Activations are the A operand (M = 128 of which 16 rows exist: the descriptor's other row groups alias the neighbouring
 // bytes and produce accumulator lanes nobody reads), weights the B operand (N = 16..48), accumulators in TMEM with
-// lane = row.  Every product is the same hi*hi + lo*hi + hi*lo fp16 triple as in the other kernels.
+// lane = row.  Every product is the same hi*hi + lo*hi + hi*lo fp16 triple as in the other kernels, but ONE tcgen05.mma
+// per k16 slab computes all three: the lo halves of the 16 rows sit 256 B behind the hi halves, i.e. they ARE row groups
+// 2..3 of the M = 128 operand (accumulator lanes 16..31 = lo * W), and a weight block stacks its lo rows under its hi rows
+// (N doubles: columns [0, N) = x * W_hi, [N, 2N) = x * W_lo).  The epilogue adds lane r's two column groups and lane
+// r + 16's first one (one warp shuffle).  Issue cost, not tensor throughput, bounds these tiny MMAs (~40 cycles each).
 //
 // Buffer hazards: a CTA sends layer L's output only after its own layer-L MMAs, which needed every peer's layer L-1 output,
 // which each peer sent after finishing layer L-1 — so when the data lands, every peer is at most reading layer L's input.
@@ -30,8 +34,8 @@ namespace rb {
 
 constexpr int kClSize = 16;        // CTAs per cluster (non-portable size)
 constexpr int kClRows = 16;        // sequences per cluster
-constexpr int kClThreads = 512;    // warps 0,4,8,12: epilogue (TMEM lanes 0..31); warp 1: MMA issuer
-constexpr uint32_t kClTmemCols = 256;
+constexpr int kClThreads = 416;    // 13 warps; warps 0,4,8,12: epilogue (TMEM lanes 0..31); warp 1: MMA issuer
+constexpr uint32_t kClTmemCols = 512;
 constexpr uint32_t kClSlab = 1024; // one k16 slab of a 16-row activation buffer: 2 k-groups x [hi 256 B | lo 256 B]
 
 struct ClGeom {
@@ -41,7 +45,7 @@ struct ClGeom {
   int kSA16;   // k16 slabs of [state | action]
   int K, KSA;  // padded widths
   uint32_t off_sa, off_h1, off_h2, off_b0, off_b1, off_w;  // byte offsets in dynamic shared memory
-  uint32_t w_e, w_hh, w_ih, w_pq1, w_pr, w_po;             // byte offsets inside a CTA's weight image
+  uint32_t w_e, w_hh_rz, w_hh_n, w_ih_rz, w_ih_n, w_pq1, w_pr, w_po;   // byte offsets inside a CTA's weight image
   uint32_t cta_bytes;                                      // weight image per CTA
   uint32_t off_bias, off_bar, smem_bytes;
 };
@@ -49,6 +53,7 @@ struct ClGeom {
 __host__ __device__ inline bool cl_geometry(int D, int S, int A, int Hd, ClGeom& g) {
   const int nD = (D + 15) / 16, nH = (Hd + 15) / 16;
   if (nD != nH || nD > kClSize) return false;
+  if ((D & 3) || (Hd & 3) || (S & 1)) return false;   // a thread's 4 features / 2 state dimensions: one vector access
   g.nK = nD;
   g.K = nD * 16;
   g.nS8 = (S + 7) / 8;
@@ -65,8 +70,10 @@ __host__ __device__ inline bool cl_geometry(int D, int S, int A, int Hd, ClGeom&
   g.off_w = o;
   uint32_t w = 0;
   g.w_e = w;   w += 4u * 16u * (uint32_t)g.KSA;
-  g.w_hh = w;  w += 4u * 48u * (uint32_t)g.K;
-  g.w_ih = w;  w += 4u * 48u * (uint32_t)g.K;
+  g.w_hh_rz = w; w += 4u * 32u * (uint32_t)g.K;
+  g.w_hh_n = w;  w += 4u * 16u * (uint32_t)g.K;
+  g.w_ih_rz = w; w += 4u * 32u * (uint32_t)g.K;
+  g.w_ih_n = w;  w += 4u * 16u * (uint32_t)g.K;
   g.w_pq1 = w; w += 4u * 32u * (uint32_t)g.K;
   g.w_pr = w;  w += 4u * 16u * (uint32_t)g.K;
   g.w_po = w;  w += 4u * 16u * (uint32_t)g.K;
@@ -99,8 +106,16 @@ struct ClPackArgs {
   uint8_t* wblob;
 };
 
-// One block per (weight block kind, cluster rank): fp32 rows of the caller's matrices -> that CTA's fp16 hi/lo B-operand
-// block, element (n, k) at (k/8)*(N*16) + (n/8)*128 + (n%8)*16 + (k%8)*2, hi block then lo block.
+// One block per (weight block kind, cluster rank): fp32 rows of the caller's matrices -> that CTA's fp16 B-operand block of
+// 2N rows (hi rows [0, N), lo rows [N, 2N)), element (n', k) at (k/8)*(2N*16) + (n'/8)*128 + (n'%8)*16 + (k%8)*2.
+__device__ __forceinline__ void cl_pack_store(uint8_t* dst, int N, int n, int k, float v) {
+  __half h, l;
+  split_f16(v, h, l);
+  const uint32_t kg = (uint32_t)(k >> 3) * (uint32_t)(2 * N * 16) + (uint32_t)(k & 7) * 2u;
+  *reinterpret_cast<__half*>(dst + kg + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u) = h;
+  *reinterpret_cast<__half*>(dst + kg + (uint32_t)((N + n) >> 3) * 128u + (uint32_t)((N + n) & 7) * 16u) = l;
+}
+
 __global__ void __launch_bounds__(256) pack_cluster_weights_kernel(const __grid_constant__ ClPackArgs a) {
   ClGeom g;
   if (!cl_geometry(a.D, a.S, a.A, a.Hd, g)) return;
@@ -110,14 +125,15 @@ __global__ void __launch_bounds__(256) pack_cluster_weights_kernel(const __grid_
   uint32_t off;
   switch (kind) {
     case 0: N = 16; K = g.KSA; off = g.w_e; break;
-    case 1: N = 48; K = g.K; off = g.w_hh; break;
-    case 2: N = 48; K = g.K; off = g.w_ih; break;
-    case 3: N = 32; K = g.K; off = g.w_pq1; break;
-    case 4: N = 16; K = g.K; off = g.w_pr; break;
+    case 1: N = 32; K = g.K; off = g.w_hh_rz; break;
+    case 2: N = 16; K = g.K; off = g.w_hh_n; break;
+    case 3: N = 32; K = g.K; off = g.w_ih_rz; break;
+    case 4: N = 16; K = g.K; off = g.w_ih_n; break;
+    case 5: N = 32; K = g.K; off = g.w_pq1; break;
+    case 6: N = 16; K = g.K; off = g.w_pr; break;
     default: N = 16; K = g.K; off = g.w_po; break;
   }
   uint8_t* dst = a.wblob + (size_t)c * g.cta_bytes + off;
-  const uint32_t lo_delta = (uint32_t)N * (uint32_t)K * 2u;
   for (int idx = threadIdx.x; idx < N * K; idx += blockDim.x) {
     const int n = idx / K, k = idx - n * K;
     float v = 0.f;
@@ -129,13 +145,19 @@ __global__ void __launch_bounds__(256) pack_cluster_weights_kernel(const __grid_
         else if (k >= g.S8 && k < g.S8 + A) col = S + (k - g.S8);
         if (f < D && col >= 0) v = a.w_e[(size_t)f * (S + A) + col];
       } break;
-      case 1:    // rnn.weight_hh (3D, D): rows r | z | n of this CTA's 16 units
-      case 2: {  // rnn.weight_ih
+      case 1:    // rnn.weight_hh (3D, D): rows r | z of this CTA's 16 units
+      case 3: {  // rnn.weight_ih
         const int gate = n >> 4, u = 16 * c + (n & 15);
         const float* w = kind == 1 ? a.w_hh : a.w_ih;
         if (u < D && k < D) v = w[(size_t)(gate * D + u) * D + k];
       } break;
-      case 3: {  // fc_embed_belief_prior (H, D) | belief half of fc_embed_belief_posterior (H, D+E)
+      case 2:    // rnn.weight_hh, gate n
+      case 4: {  // rnn.weight_ih, gate n
+        const int u = 16 * c + n;
+        const float* w = kind == 2 ? a.w_hh : a.w_ih;
+        if (u < D && k < D) v = w[(size_t)(2 * D + u) * D + k];
+      } break;
+      case 5: {  // fc_embed_belief_prior (H, D) | belief half of fc_embed_belief_posterior (H, D+E)
         const int f = 16 * c + (n & 15);
         if (f < Hd && k < D) {
           if (n < 16) v = a.w_pp[(size_t)f * D + k];
@@ -144,16 +166,11 @@ __global__ void __launch_bounds__(256) pack_cluster_weights_kernel(const __grid_
       } break;
       default: {  // fc_state_prior / fc_state_posterior (2S, H): rows mean | std of this CTA's 8 state dimensions
         const int j = 8 * c + (n & 7);
-        const float* w = kind == 4 ? a.w_prior : a.w_post;
+        const float* w = kind == 6 ? a.w_prior : a.w_post;
         if (w && j < S && k < Hd) v = w[(size_t)((n >> 3) * S + j) * Hd + k];
       } break;
     }
-    __half h, l;
-    split_f16(v, h, l);
-    const uint32_t o = (uint32_t)(k >> 3) * (uint32_t)(N * 16) + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u +
-                       (uint32_t)(k & 7) * 2u;
-    *reinterpret_cast<__half*>(dst + o) = h;
-    *reinterpret_cast<__half*>(dst + lo_delta + o) = l;
+    cl_pack_store(dst, N, n, k, v);
   }
 }
 
@@ -188,6 +205,23 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
 }
+
+// x * W of one value: lane r holds hi * W_hi (`a`) and hi * W_lo (`b`, N columns further), lane r + 16 holds lo * W_hi
+__device__ __forceinline__ float cl_sum3(float a, float b) { return a + b + __shfl_down_sync(0xffffffffu, a, 16); }
+
+// A thread's 4 features / 2 state dimensions are contiguous in every global tensor: one 16-byte (8-byte) access instead of
+// four (two) scalar ones — lane = row, so a warp's scalar access touches 16 sectors whatever its width.  The geometry
+// check demands sizes that are multiples of 4 (state: 2), the host 16-byte aligned tensors.
+__device__ __forceinline__ void ldg4(float* v, const float* p) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ldg2(float* v, const float* p) {
+  const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+  v[0] = t.x; v[1] = t.y;
+}
+__device__ __forceinline__ void stg4(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void stg2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 
 // byte offset of (row, column k) inside a 16-row activation buffer; the lo half sits 256 B behind the hi half
 __device__ __forceinline__ uint32_t cl_off(int row, int k) {
@@ -315,20 +349,17 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(con
     const uint64_t a_sa = make_smem_desc(smem_u32(sa), 512, 128), a_h1 = make_smem_desc(smem_u32(h1), 512, 128);
     const uint64_t a_h2 = make_smem_desc(smem_u32(h2), 512, 128);
     const uint64_t a_b[2] = {make_smem_desc(smem_u32(bb[0]), 512, 128), make_smem_desc(smem_u32(bb[1]), 512, 128)};
-    const uint64_t w_e = make_smem_desc(smem_u32(wsm + g.w_e), 16 * 16, 128);
-    const uint64_t w_hh = make_smem_desc(smem_u32(wsm + g.w_hh), 48 * 16, 128);
-    const uint64_t w_ih = make_smem_desc(smem_u32(wsm + g.w_ih), 48 * 16, 128);
-    const uint64_t w_pq1 = make_smem_desc(smem_u32(wsm + g.w_pq1), 32 * 16, 128);
-    const uint64_t w_pr = make_smem_desc(smem_u32(wsm + g.w_pr), 16 * 16, 128);
-    const uint64_t w_po = make_smem_desc(smem_u32(wsm + g.w_po), 16 * 16, 128);
-    constexpr uint32_t id16 = make_idesc_f16(128, 16), id32 = make_idesc_f16(128, 32), id48 = make_idesc_f16(128, 48);
-    // one product chain: D[128 x n] (+)= A[:, 16*ksl] * W^T; nrows = rows of the packed weight block (its k-group stride)
-    auto chain = [&](uint32_t d, uint64_t a, uint64_t w, int nrows, int wk, int ksl, uint32_t idesc, uint32_t acc0) {
-      const uint64_t w_step = (uint64_t)(nrows * 32) >> 4, w_lo = (uint64_t)(nrows * wk * 2) >> 4;
+    // weight blocks of N outputs hold 2N rows (hi rows, then lo rows): k-group stride 2N * 16 bytes
+    auto wdesc = [&](uint32_t off, int n) { return make_smem_desc(smem_u32(wsm + off), (uint32_t)(2 * n * 16), 128); };
+    const uint64_t w_e = wdesc(g.w_e, 16), w_hh_rz = wdesc(g.w_hh_rz, 32), w_hh_n = wdesc(g.w_hh_n, 16);
+    const uint64_t w_ih_rz = wdesc(g.w_ih_rz, 32), w_ih_n = wdesc(g.w_ih_n, 16), w_pq1 = wdesc(g.w_pq1, 32);
+    const uint64_t w_pr = wdesc(g.w_pr, 16), w_po = wdesc(g.w_po, 16);
+    constexpr uint32_t id32 = make_idesc_f16(128, 32), id64 = make_idesc_f16(128, 64);
+    // one product chain: D[128 x 2n] (+)= A[:, 16*ksl] * [W_hi; W_lo]^T, one MMA per k16 slab (lanes 16..31 = lo rows of A)
+    auto chain = [&](uint32_t d, uint64_t a, uint64_t w, int n, int ksl, uint32_t idesc, uint32_t acc0) {
+      const uint64_t w_step = (uint64_t)(2 * n * 32) >> 4;
       for (int k = 0; k < ksl; ++k) {
         umma_f16(d, a, w, idesc, k == 0 ? acc0 : 1u);
-        umma_f16(d, a + (256 >> 4), w, idesc, 1u);
-        umma_f16(d, a, w + w_lo, idesc, 1u);
         a += kClSlab >> 4;
         w += w_step;
       }
@@ -346,30 +377,36 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(con
       const uint32_t ph = (uint32_t)t & 1u;
       if (t > 0) arm_wait(CB_IN_E, tx_e, ph ^ 1u);
       if (elect_one()) {
-        chain(tb + 64, a_sa, w_e, 16, g.KSA, g.kSA16, id16, 0u);
+        chain(tb + 128, a_sa, w_e, 16, g.kSA16, id32, 0u);
         umma_commit(bar(CB_ACC_E));
-        if (t == 0) chain(tb + 0, a_b[0], w_hh, 48, g.K, nK, id48, 0u);  // W_hh . belief: r | z | h_n
+        if (t == 0) {   // W_hh . belief: r | z, h_n
+          chain(tb + 0, a_b[0], w_hh_rz, 32, nK, id64, 0u);
+          chain(tb + 64, a_b[0], w_hh_n, 16, nK, id32, 0u);
+        }
       }
       __syncwarp();
       arm_wait(CB_IN_G, tx_k, ph);
       if (elect_one()) {
-        chain(tb + 0, a_h1, w_ih, 48, g.K, nK, id32, 1u);                                  // r, z += W_ih . h_e
-        chain(tb + 48, a_h1, w_ih + ((4u * 128u) >> 4), 48, g.K, nK, id16, 0u);            // i_n
+        chain(tb + 0, a_h1, w_ih_rz, 32, nK, id64, 1u);   // r, z += W_ih . h_e
+        chain(tb + 96, a_h1, w_ih_n, 16, nK, id32, 0u);   // i_n
         umma_commit(bar(CB_ACC_G));
       }
       __syncwarp();
       arm_wait(CB_IN_PQ1, tx_k, ph);
       if (elect_one()) {
-        chain(tb + 80, a_b[(t + 1) & 1], w_pq1, 32, g.K, nK, id32, 0u);
+        chain(tb + 160, a_b[(t + 1) & 1], w_pq1, 32, nK, id64, 0u);
         umma_commit(bar(CB_ACC_PQ1));
-        if (t + 1 < T) chain(tb + 0, a_b[(t + 1) & 1], w_hh, 48, g.K, nK, id48, 0u);  // next step's W_hh . belief
+        if (t + 1 < T) {   // next step's W_hh . belief
+          chain(tb + 0, a_b[(t + 1) & 1], w_hh_rz, 32, nK, id64, 0u);
+          chain(tb + 64, a_b[(t + 1) & 1], w_hh_n, 16, nK, id32, 0u);
+        }
       }
       __syncwarp();
       if (owner) {
         arm_wait(CB_IN_PQ2, tx_k * (with_obs ? 2u : 1u), ph);
         if (elect_one()) {
-          chain(tb + 112, a_h1, w_pr, 16, g.K, nK, id16, 0u);
-          if (with_obs) chain(tb + 128, a_h2, w_po, 16, g.K, nK, id16, 0u);
+          chain(tb + 224, a_h1, w_pr, 16, nK, id32, 0u);
+          if (with_obs) chain(tb + 256, a_h2, w_po, 16, nK, id32, 0u);
           umma_commit(bar(CB_ACC_PQ2));
         }
         __syncwarp();
@@ -386,8 +423,15 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(con
     const int act = P.act;
     auto epi_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
     // send [off, off+bytes) of this CTA's shared memory to the same place in peers [0, npeers), then arrive locally
+    // [local_addr, +bytes) of this CTA's shared memory -> the same place in peers [0, npeers): lane l < nK - 1 talks to peer
+    // (c + 1 + l) % nK, and the four epilogue warps share the lanes (a bulk copy is issued from the warp's uniform datapath)
+    // (every sender starts with a different receiver; a copy occupies the sender's port for bytes / ~20 cycles)
+    const uint32_t smem0 = smem_u32(smem);
+    const int peer = (c + 1 + (lane & 15)) % nK;
+    const uint32_t peer0 = cl_mapa(smem0, (uint32_t)peer);
     auto send = [&](uint32_t local_addr, uint32_t bytes, int npeers, int b) {
-      if (lane < npeers && lane != c) bulk_s2c(cl_mapa(local_addr, (uint32_t)lane), local_addr, bytes, cl_mapa(bar(b), (uint32_t)lane));
+      if (lane < nK - 1 && peer < npeers && (lane & 3) == e)
+        bulk_s2c(peer0 + (local_addr - smem0), local_addr, bytes, peer0 + (bar(b) - smem0));
     };
     float be[4], br[4], bz[4], bin[4], bhn[4], bpp[4], bpq[4], bprev[4];
 #pragma unroll
@@ -414,155 +458,147 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(con
       const size_t trow = (size_t)t * N;
       const bool has_next = t + 1 < T;
       float* stash = (P.stash && row_ok) ? P.stash + (trow + row) * P.stash_ld : nullptr;
-      // per-step inputs, requested before the first wait
       float ad[4] = {0.f, 0.f, 0.f, 0.f}, ep[2] = {0.f, 0.f}, eq[2] = {0.f, 0.f}, nt = 1.f;
-      if (row_ok) {
-        if (with_obs) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (f0 + i < Hd) ad[i] = __ldg(P.addend + (trow + row) * Hd + f0 + i);
-        }
-        if (owner) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-            if (j0 + i < S) {
-              ep[i] = __ldg(P.eps_prior + (trow + row) * S + j0 + i);
-              if (with_obs) eq[i] = __ldg(P.eps_post + (trow + row) * S + j0 + i);
-            }
-          if (has_next && P.nonterm) nt = __ldg(P.nonterm + trow + N + row);
-        }
-      }
       // ---- E: h_e = act(W_e [state | action] + b) -> H1 slab c of every CTA
       {
         mbar_wait(bar(CB_ACC_E), ph);
         tc_fence_after();
-        float v[4];
-        tmem_ld4(tb + 64 + 4 * e, v);
+        float v[4], vl[4];
+        tmem_ld4(tb + 128 + 4 * e, v);
+        tmem_ld4(tb + 144 + 4 * e, vl);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = (f0 + i < D) ? cl_act(v[i] + be[i], act) : 0.f;
+        for (int i = 0; i < 4; ++i) v[i] = (f0 + i < D) ? cl_act(cl_sum3(v[i], vl[i]) + be[i], act) : 0.f;
         if (lane < 16) cl_put4(h1, r, f0, v);
-        if (stash) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (f0 + i < D) stash[f0 + i] = v[i];
-        }
+        if (stash && f0 < D) stg4(stash + f0, v);
         fence_proxy_async_smem();
         tc_fence_before();
         epi_sync();
-        if (e == 0) {
-          send(smem_u32(h1) + (uint32_t)c * kClSlab, kClSlab, nK, CB_IN_G);
-          if (lane == 0) mbar_arrive(bar(CB_IN_G));
+        send(smem_u32(h1) + (uint32_t)c * kClSlab, kClSlab, nK, CB_IN_G);
+        if (e == 0 && lane == 0) mbar_arrive(bar(CB_IN_G));
+      }
+      // per-step inputs: requested after the first exchange is on its way (fence.proxy.async waits for loads in flight)
+      if (row_ok) {
+        if (with_obs && f0 < Hd) ldg4(ad, P.addend + (trow + row) * Hd + f0);
+        if (owner) {
+          if (j0 < S) {
+            ldg2(ep, P.eps_prior + (trow + row) * S + j0);
+            if (with_obs) ldg2(eq, P.eps_post + (trow + row) * S + j0);
+          }
+          if (has_next && P.nonterm) nt = __ldg(P.nonterm + trow + N + row);
         }
       }
       // ---- G: GRUCell gates -> belief' -> B[(t+1)&1] slab c of every CTA, beliefs[t]
       {
         mbar_wait(bar(CB_ACC_G), ph);
         tc_fence_after();
-        float vr[4], vz[4], vh[4], vi[4], bn[4];
+        float vr[4], vz[4], vh[4], vi[4], lr[4], lz[4], lh[4], li[4], bn[4];
         tmem_ld4(tb + 0 + 4 * e, vr);
         tmem_ld4(tb + 16 + 4 * e, vz);
-        tmem_ld4(tb + 32 + 4 * e, vh);
-        tmem_ld4(tb + 48 + 4 * e, vi);
+        tmem_ld4(tb + 32 + 4 * e, lr);
+        tmem_ld4(tb + 48 + 4 * e, lz);
+        tmem_ld4(tb + 64 + 4 * e, vh);
+        tmem_ld4(tb + 80 + 4 * e, lh);
+        tmem_ld4(tb + 96 + 4 * e, vi);
+        tmem_ld4(tb + 112 + 4 * e, li);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float rr = sigmoid_f(vr[i] + br[i]);
-          const float zz = sigmoid_f(vz[i] + bz[i]);
-          const float hn = vh[i] + bhn[i];
-          const float nn = tanh_f(vi[i] + bin[i] + rr * hn);
+          const float rr = sigmoid_f(cl_sum3(vr[i], lr[i]) + br[i]);
+          const float zz = sigmoid_f(cl_sum3(vz[i], lz[i]) + bz[i]);
+          const float hn = cl_sum3(vh[i], lh[i]) + bhn[i];
+          const float nn = tanh_f(cl_sum3(vi[i], li[i]) + bin[i] + rr * hn);
           bn[i] = (f0 + i < D) ? (1.f - zz) * nn + zz * bprev[i] : 0.f;
           bprev[i] = bn[i];
-          if (stash && f0 + i < D) {
-            float* sp = stash + D + f0 + i;
-            sp[0] = rr; sp[D] = zz; sp[2 * D] = nn; sp[3 * D] = hn;
-          }
+          vr[i] = rr; vz[i] = zz; vi[i] = nn; vh[i] = hn;
+        }
+        if (stash && f0 < D) {
+          stg4(stash + D + f0, vr);
+          stg4(stash + 2 * D + f0, vz);
+          stg4(stash + 3 * D + f0, vi);
+          stg4(stash + 4 * D + f0, vh);
         }
         uint8_t* bnew = bb[(t + 1) & 1];
         if (lane < 16) cl_put4(bnew, r, f0, bn);
-        if (row_ok) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (f0 + i < D) P.beliefs[(trow + row) * D + f0 + i] = bn[i];
-        }
+        if (row_ok && f0 < D) stg4(P.beliefs + (trow + row) * D + f0, bn);
         fence_proxy_async_smem();
         tc_fence_before();
         epi_sync();
-        if (e == 0) {
-          send(smem_u32(bnew) + (uint32_t)c * kClSlab, kClSlab, nK, CB_IN_PQ1);
-          if (lane == 0) mbar_arrive(bar(CB_IN_PQ1));
-        }
+        send(smem_u32(bnew) + (uint32_t)c * kClSlab, kClSlab, nK, CB_IN_PQ1);
+        if (e == 0 && lane == 0) mbar_arrive(bar(CB_IN_PQ1));
       }
       // ---- PQ1: prior / posterior hidden layers -> H1 / H2 slab c of the CTAs that own state dimensions
       {
         mbar_wait(bar(CB_ACC_PQ1), ph);
         tc_fence_after();
-        float vp[4], vq[4];
-        tmem_ld4(tb + 80 + 4 * e, vp);
-        tmem_ld4(tb + 96 + 4 * e, vq);
+        float vp[4], vq[4], lp[4], lq[4];
+        tmem_ld4(tb + 160 + 4 * e, vp);
+        tmem_ld4(tb + 176 + 4 * e, vq);
+        tmem_ld4(tb + 192 + 4 * e, lp);
+        tmem_ld4(tb + 208 + 4 * e, lq);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          vp[i] = (f0 + i < Hd) ? cl_act(vp[i] + bpp[i], act) : 0.f;
-          vq[i] = (f0 + i < Hd && with_obs) ? cl_act(vq[i] + bpq[i] + ad[i], act) : 0.f;
+          const float sp = cl_sum3(vp[i], lp[i]), sq = cl_sum3(vq[i], lq[i]);
+          vp[i] = (f0 + i < Hd) ? cl_act(sp + bpp[i], act) : 0.f;
+          vq[i] = (f0 + i < Hd && with_obs) ? cl_act(sq + bpq[i] + ad[i], act) : 0.f;
         }
         if (lane < 16) {
           cl_put4(h1, r, f0, vp);
           if (with_obs) cl_put4(h2, r, f0, vq);
         }
-        if (stash) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (f0 + i < Hd) {
-              stash[5 * D + f0 + i] = vp[i];
-              if (with_obs) stash[5 * D + Hd + f0 + i] = vq[i];
-            }
+        if (stash && f0 < Hd) {
+          stg4(stash + 5 * D + f0, vp);
+          if (with_obs) stg4(stash + 5 * D + Hd + f0, vq);
         }
         fence_proxy_async_smem();
         tc_fence_before();
         epi_sync();
-        if (e == 0) {
-          send(smem_u32(h1) + (uint32_t)c * kClSlab, kClSlab, nS8, CB_IN_PQ2);
-          if (with_obs) send(smem_u32(h2) + (uint32_t)c * kClSlab, kClSlab, nS8, CB_IN_PQ2);
-          if (owner && lane == 0) mbar_arrive(bar(CB_IN_PQ2));
-        }
+        send(smem_u32(h1) + (uint32_t)c * kClSlab, kClSlab, nS8, CB_IN_PQ2);
+        if (with_obs) send(smem_u32(h2) + (uint32_t)c * kClSlab, kClSlab, nS8, CB_IN_PQ2);
+        if (owner && e == 0 && lane == 0) mbar_arrive(bar(CB_IN_PQ2));
       }
       // ---- PQ2: Gaussian heads (owners of state dimensions), next step's state and action -> SA of every CTA
       {
         if (owner) {
           mbar_wait(bar(CB_ACC_PQ2), ph);
           tc_fence_after();
-          float pm[2], ps[2], qm[2] = {0.f, 0.f}, qs[2] = {0.f, 0.f};
-          tmem_ld2(tb + 112 + 2 * e, pm);
-          tmem_ld2(tb + 120 + 2 * e, ps);
+          float pm[2], ps[2], qm[2] = {0.f, 0.f}, qs[2] = {0.f, 0.f}, lpm[2], lps[2], lqm[2] = {0.f, 0.f}, lqs[2] = {0.f, 0.f};
+          tmem_ld2(tb + 224 + 2 * e, pm);
+          tmem_ld2(tb + 232 + 2 * e, ps);
+          tmem_ld2(tb + 240 + 2 * e, lpm);
+          tmem_ld2(tb + 248 + 2 * e, lps);
           if (with_obs) {
-            tmem_ld2(tb + 128 + 2 * e, qm);
-            tmem_ld2(tb + 136 + 2 * e, qs);
+            tmem_ld2(tb + 256 + 2 * e, qm);
+            tmem_ld2(tb + 264 + 2 * e, qs);
+            tmem_ld2(tb + 272 + 2 * e, lqm);
+            tmem_ld2(tb + 280 + 2 * e, lqs);
           }
           tmem_ld_wait();
-          float nxt[2];
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            const bool vj = j0 + i < S;
-            const float m = pm[i] + bpm[i];
-            const float sd = softplus_f(ps[i] + bps[i]) + P.min_std;
-            const float smp = m + sd * ep[i];
-            nxt[i] = smp;
-            if (row_ok && vj) {
-              const size_t o = (trow + row) * S + j0 + i;
-              P.prior_s[o] = smp; P.prior_m[o] = m; P.prior_sd[o] = sd;
-            }
+            pm[i] = cl_sum3(pm[i], lpm[i]);
+            ps[i] = cl_sum3(ps[i], lps[i]);
+            qm[i] = cl_sum3(qm[i], lqm[i]);
+            qs[i] = cl_sum3(qs[i], lqs[i]);
+          }
+          float nxt[2], m1[2], sd1[2], s1[2], m2[2], sd2[2], s2[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            m1[i] = pm[i] + bpm[i];
+            sd1[i] = softplus_f(ps[i] + bps[i]) + P.min_std;
+            s1[i] = m1[i] + sd1[i] * ep[i];
+            m2[i] = qm[i] + bqm[i];
+            sd2[i] = softplus_f(qs[i] + bqs[i]) + P.min_std;
+            s2[i] = m2[i] + sd2[i] * eq[i];
+            nxt[i] = (row_ok && j0 < S) ? (with_obs ? s2[i] : s1[i]) : 0.f;
+          }
+          if (row_ok && j0 < S) {   // S is even: both of this thread's dimensions exist or neither
+            const size_t o = (trow + row) * S + j0;
+            stg2(P.prior_s + o, s1[0], s1[1]); stg2(P.prior_m + o, m1[0], m1[1]); stg2(P.prior_sd + o, sd1[0], sd1[1]);
             if (with_obs) {
-              const float m2 = qm[i] + bqm[i];
-              const float sd2 = softplus_f(qs[i] + bqs[i]) + P.min_std;
-              const float smp2 = m2 + sd2 * eq[i];
-              nxt[i] = smp2;
-              if (row_ok && vj) {
-                const size_t o = (trow + row) * S + j0 + i;
-                P.post_s[o] = smp2; P.post_m[o] = m2; P.post_sd[o] = sd2;
-              }
+              stg2(P.post_s + o, s2[0], s2[1]); stg2(P.post_m + o, m2[0], m2[1]); stg2(P.post_sd + o, sd2[0], sd2[1]);
             }
-            if (!vj || !row_ok) nxt[i] = 0.f;
           }
           if (has_next && lane < 16) cl_put2(sa, r, j0, nxt[0] * nt, nxt[1] * nt);
         }
@@ -572,10 +608,8 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(con
           fence_proxy_async_smem();
           tc_fence_before();
           epi_sync();
-          if (e == 0) {
-            if (owner) send(smem_u32(sa) + (uint32_t)c * 512u, 512u, nK, CB_IN_E);
-            if (lane == 0) mbar_arrive(bar(CB_IN_E));
-          }
+          if (owner) send(smem_u32(sa) + (uint32_t)c * 512u, 512u, nK, CB_IN_E);
+          if (e == 0 && lane == 0) mbar_arrive(bar(CB_IN_E));
         }
       }
     }

@@ -30,6 +30,7 @@ struct ClBwdGeom {
 __host__ __device__ inline bool clb_geometry(int D, int S, int A, int Hd, ClBwdGeom& g) {
   const int nD = (D + 15) / 16, nH = (Hd + 15) / 16;
   if (nD != nH || nD > kClSize) return false;
+  if ((D & 3) || (Hd & 3) || (S & 1)) return false;   // a thread's 4 features / 2 state dimensions: one vector access
   g.nK = nD;
   g.K = nD * 16;
   g.nS8 = (S + 7) / 8;
@@ -65,6 +66,7 @@ struct ClBwdParams {
   int stash_ld;
   const float *g_beliefs, *g_prior_s, *g_prior_m, *g_prior_sd, *g_post_s, *g_post_m, *g_post_sd;
   float *d_q, *d_hq, *d_p, *d_hp, *d_gi, *d_gh, *d_e, *d_init_belief, *d_init_state;
+  long long* dbg_clock;   // profiling build only: CTA 0 writes [step][32] clock64 stamps
 };
 
 struct ClBwdPackArgs {
@@ -73,8 +75,8 @@ struct ClBwdPackArgs {
   uint8_t* wblob;
 };
 
-// One block per (kind, cluster rank): the TRANSPOSED slices as fp16 hi/lo B-operand blocks (rows = outputs of the product,
-// k = the buffer column of the gradient operand; the column orders are those of the DQP / DH / DG / DE buffers below).
+// One block per (kind, cluster rank): the TRANSPOSED slices as fp16 B-operand blocks of 2N rows (hi rows, then lo rows, see
+// cluster.cuh; rows = outputs of the product, k = the buffer column of the gradient operand in the DQP / DH / DG / DE order).
 __global__ void __launch_bounds__(256) pack_cluster_bwd_weights_kernel(const __grid_constant__ ClBwdPackArgs a) {
   ClBwdGeom g;
   if (!clb_geometry(a.D, a.S, a.A, a.Hd, g)) return;
@@ -92,7 +94,6 @@ __global__ void __launch_bounds__(256) pack_cluster_bwd_weights_kernel(const __g
     default: N = 16; K = 16 * g.nK; off = g.w7; break;
   }
   uint8_t* dst = a.wblob + (size_t)c * g.cta_bytes + off;
-  const uint32_t lo_delta = (uint32_t)N * (uint32_t)K * 2u;
   for (int idx = threadIdx.x; idx < N * K; idx += blockDim.x) {
     // k fastest would read the sources with stride (they are walked down a column): n fastest keeps the reads coalesced
     const int k = idx / N, n = idx - k * N;
@@ -127,12 +128,7 @@ __global__ void __launch_bounds__(256) pack_cluster_bwd_weights_kernel(const __g
         if (n < 8 && j < S && f < D) v = a.w_e[(size_t)f * (S + A) + j];
       } break;
     }
-    __half h, l;
-    split_f16(v, h, l);
-    const uint32_t o = (uint32_t)(k >> 3) * (uint32_t)(N * 16) + (uint32_t)(n >> 3) * 128u + (uint32_t)(n & 7) * 16u +
-                       (uint32_t)(k & 7) * 2u;
-    *reinterpret_cast<__half*>(dst + o) = h;
-    *reinterpret_cast<__half*>(dst + lo_delta + o) = l;
+    cl_pack_store(dst, N, n, k, v);
   }
 }
 
@@ -168,6 +164,12 @@ __global__ void __launch_bounds__(256) observe_bwd_scale_kernel(ClBwdParams P, f
   }
 }
 
+#ifdef RB_STAGE_CLOCK
+#define CLB_STAMP(slot) do { if (P.dbg_clock && blockIdx.x == 0 && lane == 0) P.dbg_clock[(size_t)k * 32 + (slot)] = clock64(); } while (0)
+#else
+#define CLB_STAMP(slot) do { } while (0)
+#endif
+
 enum ClBwdBar { BB_W = 0, BB_IN_23, BB_IN_4, BB_IN_6, BB_IN_7, BB_ACC_23, BB_ACC_4, BB_ACC_6, BB_ACC_7, BB_COUNT };
 
 __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_bwd_kernel(const __grid_constant__ ClBwdParams P) {
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_bwd_kernel
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_slot), 128);
+    tmem_alloc(smem_u32(tmem_slot), 256);
     tmem_relinquish();
   }
   {
@@ -225,22 +227,18 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_bwd_kernel
     // ================================ MMA issuer ================================
     const uint64_t a_dqp = make_smem_desc(smem_u32(dqp), 512, 128), a_dh = make_smem_desc(smem_u32(dh), 512, 128);
     const uint64_t a_dg = make_smem_desc(smem_u32(dg), 512, 128);
-    const uint64_t w2 = make_smem_desc(smem_u32(wsm + g.w2), 16 * 16, 128), w3 = make_smem_desc(smem_u32(wsm + g.w3), 16 * 16, 128);
-    const uint64_t w4 = make_smem_desc(smem_u32(wsm + g.w4), 16 * 16, 128);
-    const uint64_t w6rz = make_smem_desc(smem_u32(wsm + g.w6rz), 32 * 16, 128);
-    const uint64_t w6n = make_smem_desc(smem_u32(wsm + g.w6n), 16 * 16, 128), w6h = make_smem_desc(smem_u32(wsm + g.w6h), 16 * 16, 128);
-    const uint64_t w7 = make_smem_desc(smem_u32(wsm + g.w7), 16 * 16, 128);
-    constexpr uint32_t id16 = make_idesc_f16(128, 16), id32 = make_idesc_f16(128, 32);
-    // D[128 x n] (+)= A * W^T over `steps` k16 slabs; the i-th step reads A slab first + (i / inner) * outer + i % inner
-    auto chain = [&](uint32_t d, uint64_t a_base, int first, int inner, int outer, uint64_t w, int nrows, int steps,
-                     uint32_t idesc, uint32_t acc0) {
-      const uint64_t w_step = (uint64_t)(nrows * 32) >> 4, w_lo = (uint64_t)(nrows * steps * 32) >> 4;
+    auto wdesc = [&](uint32_t off, int n) { return make_smem_desc(smem_u32(wsm + off), (uint32_t)(2 * n * 16), 128); };
+    const uint64_t w2 = wdesc(g.w2, 16), w3 = wdesc(g.w3, 16), w4 = wdesc(g.w4, 16), w6rz = wdesc(g.w6rz, 32);
+    const uint64_t w6n = wdesc(g.w6n, 16), w6h = wdesc(g.w6h, 16), w7 = wdesc(g.w7, 16);
+    constexpr uint32_t id32 = make_idesc_f16(128, 32), id64 = make_idesc_f16(128, 64);
+    // D[128 x 2n] (+)= A * [W_hi; W_lo]^T over `steps` k16 slabs, one MMA each (accumulator lanes 16..31 = lo rows of A);
+    // the i-th step reads A slab first + (i / inner) * outer + i % inner
+    auto chain = [&](uint32_t d, uint64_t a_base, int first, int inner, int outer, uint64_t w, int n, int steps,
+                     uint32_t idesc) {
+      const uint64_t w_step = (uint64_t)(2 * n * 32) >> 4;
       for (int i = 0; i < steps; ++i) {
         const int slab = first + (inner == 1 ? i * outer : (i >> 1) * outer + (i & 1));
-        const uint64_t a = a_base + (uint64_t)slab * (kClSlab >> 4);
-        umma_f16(d, a, w, idesc, i == 0 ? acc0 : 1u);
-        umma_f16(d, a + (256 >> 4), w, idesc, 1u);
-        umma_f16(d, a, w + w_lo, idesc, 1u);
+        umma_f16(d, a_base + (uint64_t)slab * (kClSlab >> 4), w, idesc, i == 0 ? 0u : 1u);
         w += w_step;
       }
     };
@@ -255,33 +253,41 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_bwd_kernel
     for (int k = 0; k < T; ++k) {
       const uint32_t ph = (uint32_t)k & 1u;
       arm_wait(BB_IN_23, tx_23, ph);
+      CLB_STAMP(16);
       if (elect_one()) {
-        if (with_obs) chain(tb + 0, a_dqp, 0, 1, 2, w2, 16, nS8, id16, 0u);
-        chain(tb + 16, a_dqp, 1, 1, 2, w3, 16, nS8, id16, 0u);
+        if (with_obs) chain(tb + 0, a_dqp, 0, 1, 2, w2, 16, nS8, id32);
+        chain(tb + 32, a_dqp, 1, 1, 2, w3, 16, nS8, id32);
         umma_commit(bar(BB_ACC_23));
       }
       __syncwarp();
+      CLB_STAMP(17);
       arm_wait(BB_IN_4, (uint32_t)(nK - 1) * 2u * kClSlab, ph);
+      CLB_STAMP(18);
       if (elect_one()) {
-        chain(tb + 32, a_dh, 0, 1, 1, w4, 16, 2 * nK, id16, 0u);
+        chain(tb + 64, a_dh, 0, 1, 1, w4, 16, 2 * nK, id32);
         umma_commit(bar(BB_ACC_4));
       }
       __syncwarp();
+      CLB_STAMP(19);
       arm_wait(BB_IN_6, (uint32_t)(nK - 1) * 4u * kClSlab, ph);
+      CLB_STAMP(20);
       if (elect_one()) {
-        chain(tb + 48, a_dg, 0, 2, 4, w6rz, 32, 2 * nK, id32, 0u);   // de | dbelief  <-  d r, d z
-        chain(tb + 48, a_dg, 2, 1, 4, w6n, 16, nK, id16, 1u);        // de += W_ih[n]^T dn
-        chain(tb + 64, a_dg, 3, 1, 4, w6h, 16, nK, id16, 1u);        // dbelief += W_hh[n]^T (dn r)
+        chain(tb + 96, a_dg, 0, 2, 4, w6rz, 32, 2 * nK, id64);   // de | dbelief  <-  d r, d z
+        chain(tb + 160, a_dg, 2, 1, 4, w6n, 16, nK, id32);       // de's share of W_ih[n]^T dn        (summed in the epilogue)
+        chain(tb + 192, a_dg, 3, 1, 4, w6h, 16, nK, id32);       // dbelief's share of W_hh[n]^T (dn r)
         umma_commit(bar(BB_ACC_6));
       }
       __syncwarp();
+      CLB_STAMP(21);
       if (owner) {
         arm_wait(BB_IN_7, (uint32_t)(nK - 1) * kClSlab, ph);
+        CLB_STAMP(22);
         if (elect_one()) {
-          chain(tb + 80, a_dh, 0, 1, 1, w7, 16, nK, id16, 0u);
+          chain(tb + 224, a_dh, 0, 1, 1, w7, 16, nK, id32);
           umma_commit(bar(BB_ACC_7));
         }
         __syncwarp();
+        CLB_STAMP(23);
       }
     }
   } else if (active && (warp & 3) == 0) {
@@ -292,57 +298,84 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_bwd_kernel
     const int act = P.act;
     const float sc = row_ok ? P.scales[2 * row] : 1.f, inv = row_ok ? P.scales[2 * row + 1] : 1.f;
     auto epi_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    // lane l < nK - 1 talks to peer (c + 1 + l) % nK (every sender starts with a different receiver); the four warps share
+    // the lanes: a bulk copy is issued from the warp's uniform datapath, one at a time, and occupies the sender's port for
+    // bytes / ~20 cycles
+    const uint32_t smem0 = smem_u32(smem);
+    const int peer = (c + 1 + (lane & 15)) % nK;
+    const uint32_t peer0 = cl_mapa(smem0, (uint32_t)peer);
     auto send = [&](uint32_t local_addr, uint32_t bytes, int npeers, int b) {
-      if (lane < npeers && lane != c) bulk_s2c(cl_mapa(local_addr, (uint32_t)lane), local_addr, bytes, cl_mapa(bar(b), (uint32_t)lane));
+      if (lane < nK - 1 && peer < npeers && (lane & 3) == e)
+        bulk_s2c(peer0 + (local_addr - smem0), local_addr, bytes, peer0 + (bar(b) - smem0));
     };
     auto ldq = [&](const float* p, size_t o, float mul) { return p ? __ldg(p + o) * mul : 0.f; };
     float db[4] = {0.f, 0.f, 0.f, 0.f}, ds[2] = {0.f, 0.f};
+    // what stage 1 reads from global memory is the first thing a reverse step needs: it is requested one step ahead
+    struct HeadIn { float gqs[2], gqm[2], gqsd[2], eq[2], sdq[2], gps[2], gpm[2], gpsd[2], ep[2], sdp[2], nt; };
+    auto load_heads = [&](int t) {
+      HeadIn h;
+      h.nt = 1.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) h.gqs[i] = h.gqm[i] = h.gqsd[i] = h.eq[i] = h.gps[i] = h.gpm[i] = h.gpsd[i] = h.ep[i] = 0.f, h.sdq[i] = h.sdp[i] = 1.f;
+      if (owner && row_ok && t >= 0 && j0 < S) {   // S is even: both dimensions exist or neither
+        const size_t tr = (size_t)t * N + row, o = tr * S + j0;
+        if (P.nonterm) h.nt = __ldg(P.nonterm + tr);
+        if (with_obs) {
+          if (P.g_post_s) ldg2(h.gqs, P.g_post_s + o);
+          if (P.g_post_m) ldg2(h.gqm, P.g_post_m + o);
+          if (P.g_post_sd) ldg2(h.gqsd, P.g_post_sd + o);
+          ldg2(h.eq, P.eps_post + o);
+          ldg2(h.sdq, P.post_sd + o);
+        }
+        if (P.g_prior_s) ldg2(h.gps, P.g_prior_s + o);
+        if (P.g_prior_m) ldg2(h.gpm, P.g_prior_m + o);
+        if (P.g_prior_sd) ldg2(h.gpsd, P.g_prior_sd + o);
+        ldg2(h.ep, P.eps_prior + o);
+        ldg2(h.sdp, P.prior_sd + o);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          h.gqs[i] *= sc; h.gqm[i] *= sc; h.gqsd[i] *= sc; h.gps[i] *= sc; h.gpm[i] *= sc; h.gpsd[i] *= sc;
+        }
+      } else if (owner && row_ok && t >= 0 && P.nonterm) {
+        h.nt = __ldg(P.nonterm + (size_t)t * N + row);
+      }
+      return h;
+    };
+    HeadIn hn = load_heads(T - 1);
     for (int k = 0; k < T; ++k) {
       const int t = T - 1 - k;
       const uint32_t ph = (uint32_t)k & 1u;
       const size_t tr = (size_t)t * N + row;
+      if (e == 0) CLB_STAMP(0);
       // ---- everything this step reads from global memory is independent of the recurrence: requested up front ----
+      // the stashed activations a stage needs are requested one stage ahead (short live ranges: 128 registers per thread)
+      const float* st = P.stash + tr * P.stash_ld;
       float she[4], sr[4], sz[4], sn[4], shn[4], shp[4], shq[4], bprev[4], gg[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int f = f0 + i;
-        const bool ok = row_ok && f < D, okh = row_ok && f < Hd;
-        const float* st = P.stash + tr * P.stash_ld;
-        she[i] = ok ? __ldg(st + f) : 0.f;
-        sr[i] = ok ? __ldg(st + D + f) : 0.f;
-        sz[i] = ok ? __ldg(st + 2 * D + f) : 0.f;
-        sn[i] = ok ? __ldg(st + 3 * D + f) : 0.f;
-        shn[i] = ok ? __ldg(st + 4 * D + f) : 0.f;
-        shp[i] = okh ? __ldg(st + 5 * D + f) : 0.f;
-        shq[i] = (okh && with_obs) ? __ldg(st + 5 * D + Hd + f) : 0.f;
-        bprev[i] = !ok ? 0.f : (t > 0 ? __ldg(P.beliefs + (tr - N) * D + f) : (P.init_belief ? __ldg(P.init_belief + (size_t)row * D + f) : 0.f));
-        gg[i] = ok ? ldq(P.g_beliefs, tr * D + f, sc) : 0.f;
-      }
-      float nt = 1.f;
+      const HeadIn hd = hn;
+      const float nt = hd.nt;
       // ---- 1: Gaussian heads (elementwise, owners of state dimensions) -> DQP slice [dq mean | dq raw | dp mean | dp raw]
       if (owner) {
         float dqm[2] = {0.f, 0.f}, dqr[2] = {0.f, 0.f}, dpm[2] = {0.f, 0.f}, dpr[2] = {0.f, 0.f};
-        if (row_ok && P.nonterm) nt = __ldg(P.nonterm + tr);
+        if (row_ok && j0 < S) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int j = j0 + i;
-          if (row_ok && j < S) {
-            const size_t o = tr * S + j;
+          for (int i = 0; i < 2; ++i) {
             if (with_obs) {
-              const float gs = ldq(P.g_post_s, o, sc) + ds[i];   // the posterior sample feeds step t+1
-              dqm[i] = ldq(P.g_post_m, o, sc) + gs;
-              const float dsd = ldq(P.g_post_sd, o, sc) + gs * __ldg(P.eps_post + o);
-              dqr[i] = dsd * (1.f - __expf(-(__ldg(P.post_sd + o) - P.min_std)));   // softplus' = 1 - exp(-softplus)
-              P.d_q[tr * 2 * S + j] = dqm[i] * inv;
-              P.d_q[tr * 2 * S + S + j] = dqr[i] * inv;
+              const float gs = hd.gqs[i] + ds[i];   // the posterior sample feeds step t+1
+              dqm[i] = hd.gqm[i] + gs;
+              const float dsd = hd.gqsd[i] + gs * hd.eq[i];
+              dqr[i] = dsd * (1.f - __expf(-(hd.sdq[i] - P.min_std)));   // softplus' = 1 - exp(-softplus)
             }
-            const float gsp = ldq(P.g_prior_s, o, sc) + (with_obs ? 0.f : ds[i]);
-            dpm[i] = ldq(P.g_prior_m, o, sc) + gsp;
-            const float dsdp = ldq(P.g_prior_sd, o, sc) + gsp * __ldg(P.eps_prior + o);
-            dpr[i] = dsdp * (1.f - __expf(-(__ldg(P.prior_sd + o) - P.min_std)));
-            P.d_p[tr * 2 * S + j] = dpm[i] * inv;
-            P.d_p[tr * 2 * S + S + j] = dpr[i] * inv;
+            const float gsp = hd.gps[i] + (with_obs ? 0.f : ds[i]);
+            dpm[i] = hd.gpm[i] + gsp;
+            const float dsdp = hd.gpsd[i] + gsp * hd.ep[i];
+            dpr[i] = dsdp * (1.f - __expf(-(hd.sdp[i] - P.min_std)));
           }
+          if (with_obs) {
+            stg2(P.d_q + tr * 2 * S + j0, dqm[0] * inv, dqm[1] * inv);
+            stg2(P.d_q + tr * 2 * S + S + j0, dqr[0] * inv, dqr[1] * inv);
+          }
+          stg2(P.d_p + tr * 2 * S + j0, dpm[0] * inv, dpm[1] * inv);
+          stg2(P.d_p + tr * 2 * S + S + j0, dpr[0] * inv, dpr[1] * inv);
         }
         if (lane < 16) {
           cl_put2(dqp, r, 32 * c + 2 * e, dqm[0], dqm[1]);
@@ -352,28 +385,46 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_bwd_kernel
         }
         fence_proxy_async_smem();
         epi_sync();
+        send(smem_u32(dqp) + (uint32_t)c * 2u * kClSlab, 2u * kClSlab, nK, BB_IN_23);
         if (e == 0) {
-          send(smem_u32(dqp) + (uint32_t)c * 2u * kClSlab, 2u * kClSlab, nK, BB_IN_23);
           if (lane == 0) mbar_arrive(bar(BB_IN_23));
+          CLB_STAMP(1);
         }
       }
+      // (requested only now: fence.proxy.async above would wait for every load still in flight)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) shp[i] = shq[i] = 0.f;
+      if (row_ok && f0 < Hd) {
+        ldg4(shp, st + 5 * D + f0);
+        if (with_obs) ldg4(shq, st + 5 * D + Hd + f0);
+      }
+      hn = load_heads(t - 1);
       // ---- 2/3: hidden layers of the two heads -> DH slice [dh_q | dh_p]
       {
         mbar_wait(bar(BB_ACC_23), ph);
         tc_fence_after();
-        float vq[4] = {0.f, 0.f, 0.f, 0.f}, vp[4];
-        if (with_obs) tmem_ld4(tb + 0 + 4 * e, vq);
-        tmem_ld4(tb + 16 + 4 * e, vp);
+        if (e == 0) CLB_STAMP(2);
+        float vq[4] = {0.f, 0.f, 0.f, 0.f}, lq[4] = {0.f, 0.f, 0.f, 0.f}, vp[4], lp[4];
+        if (with_obs) {
+          tmem_ld4(tb + 0 + 4 * e, vq);
+          tmem_ld4(tb + 16 + 4 * e, lq);
+        }
+        tmem_ld4(tb + 32 + 4 * e, vp);
+        tmem_ld4(tb + 48 + 4 * e, lp);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const bool okh = row_ok && f0 + i < Hd;
+          vq[i] = cl_sum3(vq[i], lq[i]);
+          vp[i] = cl_sum3(vp[i], lp[i]);
           vq[i] = (okh && with_obs) ? vq[i] * act_grad_from_output(shq[i], act) : 0.f;
           vp[i] = okh ? vp[i] * act_grad_from_output(shp[i], act) : 0.f;
-          if (okh) {
-            if (with_obs) P.d_hq[tr * Hd + f0 + i] = vq[i] * inv;
-            P.d_hp[tr * Hd + f0 + i] = vp[i] * inv;
-          }
+          lq[i] = vq[i] * inv;
+          lp[i] = vp[i] * inv;
+        }
+        if (row_ok && f0 < Hd) {
+          if (with_obs) stg4(P.d_hq + tr * Hd + f0, lq);
+          stg4(P.d_hp + tr * Hd + f0, lp);
         }
         if (lane < 16) {
           cl_put4(dh, r, 32 * c + 4 * e, vq);
@@ -382,9 +433,23 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_bwd_kernel
         fence_proxy_async_smem();
         tc_fence_before();
         epi_sync();
+        send(smem_u32(dh) + (uint32_t)c * 2u * kClSlab, 2u * kClSlab, nK, BB_IN_4);
         if (e == 0) {
-          send(smem_u32(dh) + (uint32_t)c * 2u * kClSlab, 2u * kClSlab, nK, BB_IN_4);
           if (lane == 0) mbar_arrive(bar(BB_IN_4));
+          CLB_STAMP(3);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sr[i] = sz[i] = sn[i] = shn[i] = bprev[i] = gg[i] = 0.f;
+        if (row_ok && f0 < D) {
+          ldg4(sr, st + D + f0);
+          ldg4(sz, st + 2 * D + f0);
+          ldg4(sn, st + 3 * D + f0);
+          ldg4(shn, st + 4 * D + f0);
+          if (t > 0) ldg4(bprev, P.beliefs + (tr - N) * D + f0);
+          else if (P.init_belief) ldg4(bprev, P.init_belief + (size_t)row * D + f0);
+          if (P.g_beliefs) ldg4(gg, P.g_beliefs + tr * D + f0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gg[i] *= sc;
         }
       }
       // ---- 4: dbelief_t complete -> GRU gate gradients -> DG slice [dr | dz | dn | dn r]
@@ -392,25 +457,31 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_bwd_kernel
       {
         mbar_wait(bar(BB_ACC_4), ph);
         tc_fence_after();
-        float v[4], drp[4], dzp[4], dnp[4], dnr[4];
-        tmem_ld4(tb + 32 + 4 * e, v);
+        if (e == 0) CLB_STAMP(4);
+        float v[4], vl[4], drp[4], dzp[4], dnp[4], dnr[4];
+        tmem_ld4(tb + 64 + 4 * e, v);
+        tmem_ld4(tb + 80 + 4 * e, vl);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const bool ok = row_ok && f0 + i < D;
-          const float g_ = ok ? gg[i] + db[i] + v[i] : 0.f;
+          const float s4 = cl_sum3(v[i], vl[i]);
+          const float g_ = ok ? gg[i] + db[i] + s4 : 0.f;
           const float z = sz[i], n = sn[i], rr = sr[i];
           dnp[i] = g_ * (1.f - z) * (1.f - n * n);
           dzp[i] = g_ * (bprev[i] - n) * z * (1.f - z);
           drp[i] = dnp[i] * shn[i] * rr * (1.f - rr);
           dnr[i] = dnp[i] * rr;
           dbd[i] = g_ * z;   // direct path to belief_{t-1}; W_hh^T dgh joins in stage 6
-          if (ok) {
-            float* o_gi = P.d_gi + tr * 3 * D + f0 + i;
-            float* o_gh = P.d_gh + tr * 3 * D + f0 + i;
-            o_gi[0] = drp[i] * inv; o_gi[D] = dzp[i] * inv; o_gi[2 * D] = dnp[i] * inv;
-            o_gh[0] = drp[i] * inv; o_gh[D] = dzp[i] * inv; o_gh[2 * D] = dnr[i] * inv;
-          }
+        }
+        if (row_ok && f0 < D) {
+          float o1[4], o2[4], o3[4], o4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { o1[i] = drp[i] * inv; o2[i] = dzp[i] * inv; o3[i] = dnp[i] * inv; o4[i] = dnr[i] * inv; }
+          float* o_gi = P.d_gi + tr * 3 * D + f0;
+          float* o_gh = P.d_gh + tr * 3 * D + f0;
+          stg4(o_gi, o1); stg4(o_gi + D, o2); stg4(o_gi + 2 * D, o3);
+          stg4(o_gh, o1); stg4(o_gh + D, o2); stg4(o_gh + 2 * D, o4);
         }
         if (lane < 16) {
           cl_put4(dg, r, 64 * c + 4 * e, drp);
@@ -421,45 +492,65 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_bwd_kernel
         fence_proxy_async_smem();
         tc_fence_before();
         epi_sync();
+        send(smem_u32(dg) + (uint32_t)c * 4u * kClSlab, 4u * kClSlab, nK, BB_IN_6);
         if (e == 0) {
-          send(smem_u32(dg) + (uint32_t)c * 4u * kClSlab, 4u * kClSlab, nK, BB_IN_6);
           if (lane == 0) mbar_arrive(bar(BB_IN_6));
+          CLB_STAMP(5);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) she[i] = 0.f;
+        if (row_ok && f0 < D) ldg4(she, st + f0);
       }
       // ---- 6: de -> DE slab c of the owners; carried dbelief
       {
         mbar_wait(bar(BB_ACC_6), ph);
         tc_fence_after();
-        float vde[4], vdb[4];
-        tmem_ld4(tb + 48 + 4 * e, vde);
-        tmem_ld4(tb + 64 + 4 * e, vdb);
+        if (e == 0) CLB_STAMP(6);
+        float vde[4], vdb[4], lde[4], ldb[4], ne[4], nl[4], hb[4], hl[4];
+        tmem_ld4(tb + 96 + 4 * e, vde);
+        tmem_ld4(tb + 112 + 4 * e, vdb);
+        tmem_ld4(tb + 128 + 4 * e, lde);
+        tmem_ld4(tb + 144 + 4 * e, ldb);
+        tmem_ld4(tb + 160 + 4 * e, ne);
+        tmem_ld4(tb + 176 + 4 * e, nl);
+        tmem_ld4(tb + 192 + 4 * e, hb);
+        tmem_ld4(tb + 208 + 4 * e, hl);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const bool ok = row_ok && f0 + i < D;
+          vde[i] = cl_sum3(vde[i], lde[i]) + cl_sum3(ne[i], nl[i]);
+          vdb[i] = cl_sum3(vdb[i], ldb[i]) + cl_sum3(hb[i], hl[i]);
           vde[i] = ok ? vde[i] * act_grad_from_output(she[i], act) : 0.f;
           db[i] = ok ? dbd[i] + vdb[i] : 0.f;
-          if (ok) P.d_e[tr * D + f0 + i] = vde[i] * inv;
+          lde[i] = vde[i] * inv;
         }
+        if (row_ok && f0 < D) stg4(P.d_e + tr * D + f0, lde);
         if (lane < 16) cl_put4(de_buf, r, 16 * c + 4 * e, vde);
         fence_proxy_async_smem();
         tc_fence_before();
         epi_sync();
+        send(smem_u32(de_buf) + (uint32_t)c * kClSlab, kClSlab, nS8, BB_IN_7);
         if (e == 0) {
-          send(smem_u32(de_buf) + (uint32_t)c * kClSlab, kClSlab, nS8, BB_IN_7);
           if (owner && lane == 0) mbar_arrive(bar(BB_IN_7));
+          CLB_STAMP(7);
         }
       }
       // ---- 7: the state that entered this step: s_{t-1} nonterm[t]
       if (owner) {
         mbar_wait(bar(BB_ACC_7), ph);
         tc_fence_after();
-        float v[2];
-        tmem_ld2(tb + 80 + 2 * e, v);
+        if (e == 0) CLB_STAMP(8);
+        float v[2], vl[2];
+        tmem_ld2(tb + 224 + 2 * e, v);
+        tmem_ld2(tb + 240 + 2 * e, vl);
         tmem_ld_wait();
         tc_fence_before();
 #pragma unroll
-        for (int i = 0; i < 2; ++i) ds[i] = (row_ok && j0 + i < S) ? v[i] * nt : 0.f;
+        for (int i = 0; i < 2; ++i) {
+          const float s7 = cl_sum3(v[i], vl[i]);
+          ds[i] = (row_ok && j0 + i < S) ? s7 * nt : 0.f;
+        }
       }
     }
     if (row_ok) {
@@ -476,7 +567,7 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_bwd_kernel
 
   tc_fence_before();
   cl_sync_all();   // nobody exits while a peer may still write into its shared memory
-  if (warp == 1) tmem_dealloc(tb, 128);
+  if (warp == 1) tmem_dealloc(tb, 256);
 }
 
 }  // namespace rb

@@ -58,30 +58,31 @@ def bwd(params, x, outs, st, G, mode, with_obs, reps=1):
     return res, ms
 
 
-for (T, B, pd, with_obs, gscale) in [(3, 5, 0.0, True, 1.0), (8, 10, 0.3, True, 1e-4), (49, 50, 0.1, True, 4e-4), (7, 33, 0.2, False, 1.0), (5, 130, 0.1, True, 1e-6)]:
-    params = cu(O.make_transition_params(100 + T))
-    x = O.make_observe_inputs(200 + B, T, B, p_done=pd)
-    if not with_obs:
-        x["embeds"] = None; x["eps_post"] = None
-    outs, st = fwd(params, x, with_obs)
-    rs = np.random.RandomState(5)
-    feat = [200] + [30] * 6
-    G = [torch.from_numpy((gscale * rs.standard_normal((T, B, f))).astype(np.float32)).to(dev) for f in feat[:7 if with_obs else 4]]
-    r1, _ = bwd(params, x, outs, st, G, 1, with_obs)
-    r2, _ = bwd(params, x, outs, st, G, 2, with_obs)
-    msg = []
-    for k in r1:
-        if not with_obs and k in ("d_q", "d_hq"):
-            continue
-        sc = r2[k].abs().max().item() + 1e-30
-        msg.append(f"{k} {((r1[k] - r2[k]).abs().max().item() / sc):.2e}")
-    print(f"T={T} B={B} obs={with_obs} g~{gscale:g}: max|cluster - fp32| / max|fp32|: " + "  ".join(msg), flush=True)
+if __name__ == "__main__":
+    for (T, B, pd, with_obs, gscale) in [(3, 5, 0.0, True, 1.0), (8, 10, 0.3, True, 1e-4), (49, 50, 0.1, True, 4e-4), (7, 33, 0.2, False, 1.0), (5, 130, 0.1, True, 1e-6)]:
+        params = cu(O.make_transition_params(100 + T))
+        x = O.make_observe_inputs(200 + B, T, B, p_done=pd)
+        if not with_obs:
+            x["embeds"] = None; x["eps_post"] = None
+        outs, st = fwd(params, x, with_obs)
+        rs = np.random.RandomState(5)
+        feat = [200] + [30] * 6
+        G = [torch.from_numpy((gscale * rs.standard_normal((T, B, f))).astype(np.float32)).to(dev) for f in feat[:7 if with_obs else 4]]
+        r1, _ = bwd(params, x, outs, st, G, 1, with_obs)
+        r2, _ = bwd(params, x, outs, st, G, 2, with_obs)
+        msg = []
+        for k in r1:
+            if not with_obs and k in ("d_q", "d_hq"):
+                continue
+            sc = r2[k].abs().max().item() + 1e-30
+            msg.append(f"{k} {((r1[k] - r2[k]).abs().max().item() / sc):.2e}")
+        print(f"T={T} B={B} obs={with_obs} g~{gscale:g}: max|cluster - fp32| / max|fp32|: " + "  ".join(msg), flush=True)
 
-params = cu(O.make_transition_params(1))
-x = O.make_observe_inputs(2, 49, 50, p_done=0.05)
-outs, st = fwd(params, x, True)
-rs = np.random.RandomState(6)
-G = [torch.from_numpy((4e-4 * rs.standard_normal((49, 50, f))).astype(np.float32)).to(dev) for f in [200] + [30] * 6]
-for mode in (1, 2):
-    _, ms = bwd(params, x, outs, st, G, mode, True, reps=20)
-    print(f"observe backward 50x49 mode={mode}: {ms:.3f} ms = {ms*1e3/49:.1f} us per time step", flush=True)
+    params = cu(O.make_transition_params(1))
+    x = O.make_observe_inputs(2, 49, 50, p_done=0.05)
+    outs, st = fwd(params, x, True)
+    rs = np.random.RandomState(6)
+    G = [torch.from_numpy((4e-4 * rs.standard_normal((49, 50, f))).astype(np.float32)).to(dev) for f in [200] + [30] * 6]
+    for mode in (1, 2):
+        _, ms = bwd(params, x, outs, st, G, mode, True, reps=20)
+        print(f"observe backward 50x49 mode={mode}: {ms:.3f} ms = {ms*1e3/49:.1f} us per time step", flush=True)

@@ -422,11 +422,15 @@ def _autograd_reference(params, x, R, with_obs, use_nt):
     return {k: v.grad for k, v in p64.items()}, (emb.grad if emb is not None else None)
 
 
+@pytest.mark.parametrize("bwd_mode", [1, 2])
 @pytest.mark.parametrize("name", ["observe_T8_B10", "observe_T8_B10_hot", "observe_prior_only", "observe_no_nonterm", "observe_tiny_dims"])
-def test_observe_backward_matches_autograd_of_the_oracle(dev, name):
-    """BPTT through the hand-written reverse-time kernel vs fp64 autograd of the oracle (the reference
-    obtains these gradients from autograd over rssm.py:116-133)."""
+def test_observe_backward_matches_autograd_of_the_oracle(dev, name, bwd_mode, monkeypatch):
+    """BPTT through the hand-written reverse-time kernels vs fp64 autograd of the oracle (the reference
+    obtains these gradients from autograd over rssm.py:116-133).  bwd_mode 1: the cluster kernel (tcgen05, transposed weight
+    slices resident in shared memory; what small batches run by default), 2: the per-sequence fp32 kernel."""
     from repo_b200.rssm import TransitionModel
+    from repo_b200 import autograd as AG
+    monkeypatch.setattr(AG, "OBSERVE_BWD_MODE", bwd_mode)
     params, x, gold, meta = C.observe_case(name)
     dims = C.dims_of(meta)
     with_obs, use_nt = bool(meta["use_obs"]), bool(meta["use_nt"])
