@@ -430,7 +430,23 @@ def run_gpu(a):
             return s0.elapsed_time(s1) / n
 
         img_ms = timeit(lambda: ops.imagine_fwd(P, PA, PR, PV, *xa, HORIZON))
-        obs_ms = timeit(lambda: ops.observe_fwd(P, *oa))
+        obs_ms = timeit(lambda: ops.observe_fwd(P, *oa))   # 50 sequences: the 16-CTA cluster kernel (csrc/cluster.cuh)
+
+        # the same pass under autograd, as Agent.train_dynamics runs it: forward with the activation stash, BPTT through
+        # the cluster backward kernel (csrc/cluster_bwd.cuh), the seven weight-gradient GEMMs and the bias sums
+        from repo_b200.rssm import TransitionModel
+        tm_ = TransitionModel(D, S, A, Hd, 1024, "elu").to(dev)
+        tm_.load_state_dict({k_: v_ for k_, v_ in P.items()})
+        gsum_ = [torch.randn_like(t_) * 4e-4 for t_ in ops.observe_fwd(P, *oa)[0]]
+
+        def obs_train():
+            for p_ in tm_.parameters():
+                p_.grad = None
+            outs_ = tm_.observe(oa[0], oa[1], oa[2], oa[3], oa[4], eps_prior=oa[5], eps_post=oa[6])
+            torch.autograd.backward(list(outs_), gsum_)
+
+        obs_train_ms = timeit(obs_train)
+        del tm_, gsum_
 
         # observe at a batch that fills the GPU (the other half of the hot path; SURVEY §8d "Roofline - observe":
         # 1,112,000 FLOP and 5,884 B per row-step): 18,944 sequences x 49 steps through the 128-row kernel
@@ -516,7 +532,8 @@ def run_gpu(a):
         ac_ms = upd["actor_critic_update_ms"]
         default_shape = {"imagine_2450x14_ms": img_ms, "imagine_steps_per_s": 2450 * 14 / img_ms * 1e3,
                          "observe_49x50_ms": obs_ms, "observe_row_steps_per_s": 2450 / obs_ms * 1e3,
-                         "observe_us_per_time_step": obs_ms * 1e3 / 49, "observe_large_batch": observe_large,
+                         "observe_us_per_time_step": obs_ms * 1e3 / 49, "observe_fwd_bwd_49x50_ms": obs_train_ms,
+                         "observe_large_batch": observe_large,
                          **upd, "actor_critic_update_steps_per_s": 2450 * 14 / ac_ms * 1e3,
                          "note": "world_model_update = Agent.train_dynamics on a (50,50,3,64,64) batch: conv encoder + observe + conv "
                                  "decoder + reward/KL losses, all backward passes, clip + Adam; actor_critic_update = "
