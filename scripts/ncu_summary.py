@@ -51,7 +51,8 @@ def main():
     if len(src) > 2:
         h = src[1]
         ix = {k: i for i, k in enumerate(h)}
-        data = [r for r in src[2:] if len(r) == len(h)]
+        # (a report with several kernels repeats the header rows per kernel: keep the numeric rows, all kernels pooled)
+        data = [r for r in src[2:] if len(r) == len(h) and (r[ix["# Samples"]] or "0").isdigit()]
         tot = sum(int(r[ix["# Samples"]] or 0) for r in data) or 1
         stall = [c for c in h if c.startswith("stall_") and "Not Issued" not in c]
         agg = collections.Counter()
