@@ -36,11 +36,12 @@ def bwd(params, x, outs, st, G, mode, with_obs, reps=1):
     ws = torch.empty(L.repo_b200_observe_bwd_workspace_bytes(C.byref(d), B), dtype=torch.uint8, device=dev)
     nt = g("nonterms")
     nt = None if nt is None else nt.reshape(T1, B).contiguous()
+    pb, e1_, e2_ = g("prev_belief"), g("eps_prior"), g("eps_post")   # kept alive: only raw pointers cross the C-ABI
     GG = list(G) + [None] * (7 - len(G))
     post_sd = outs[6] if with_obs else None
     def call():
         rc = L.repo_b200_observe_bwd_ws(
-            C.byref(d), C.byref(W), p(g("prev_belief")), p(outs[0]), p(outs[3]), p(post_sd), p(g("eps_prior")), p(g("eps_post")),
+            C.byref(d), C.byref(W), p(pb), p(outs[0]), p(outs[3]), p(post_sd), p(e1_), p(e2_),
             p(nt), p(st), *[p(t) for t in GG], p(res["d_q"]) if with_obs else None, p(res["d_hq"]) if with_obs else None,
             p(res["d_p"]), p(res["d_hp"]), p(res["d_gi"]), p(res["d_gh"]), p(res["d_e"]), p(res["d_b0"]), p(res["d_s0"]),
             T1, B, int(with_obs), ops.act_kind("elu"), 0.1, p(ws), ws.numel(), mode, ops._stream())

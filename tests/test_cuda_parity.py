@@ -986,3 +986,87 @@ def test_standalone_cells_are_differentiable(dev, rows):
     close(nb2, nb.detach().cpu(), "belief (fused)")
     for got, want in zip(tuple(pr2) + tuple(po2), tuple(pr) + tuple(po)):
         close(got, want.detach().cpu(), "fused vs composed")
+
+
+@pytest.mark.parametrize("dims", [
+    dict(belief=200, state=30, action=6, hidden=200, embed=64),    # defaults: 13 feature CTAs (the last with 8), 4 state owners (the last with 6)
+    dict(belief=64, state=16, action=4, hidden=64, embed=32),      # 4 feature CTAs, 2 state owners, both full
+    dict(belief=128, state=30, action=16, hidden=116, embed=48),   # hidden narrower than belief inside the same multiple of 16; 4 SA slabs
+    dict(belief=224, state=32, action=2, hidden=224, embed=16),    # 14 feature CTAs, 4 full owners
+    dict(belief=16, state=8, action=1, hidden=16, embed=16),       # ONE feature CTA = the only owner: every exchange is local
+], ids=lambda d: f"D{d['belief']}S{d['state']}A{d['action']}H{d['hidden']}")
+def test_cluster_kernels_shape_sweep(ops, dev, dims):
+    """The cluster kernels' shape-dependent paths (number of feature CTAs / state owners, partial last slices, [state | action]
+    slab count, a partial cluster of rows): forward against the oracle; backward (mode 1) against the per-sequence fp32
+    kernel (mode 2) on the same forward tensors and incoming gradients."""
+    import ctypes as CT
+    from repo_b200 import _lib
+    D, S, Hd = dims["belief"], dims["state"], dims["hidden"]
+    B = 21
+    params = O.make_transition_params(81, dims, 1.2)
+    x = O.make_observe_inputs(82, 7, B, dims, p_done=0.15)
+    T = x["actions"].shape[0]
+    g = lambda k: x[k].to(dev)
+    P = cu(params, dev)
+    stash = torch.zeros(T, B, 5 * D + 2 * Hd, device=dev)
+    outs, kl, _ = ops.observe_fwd(P, g("prev_belief"), g("prev_state"), g("actions"), g("embeds"), g("nonterms"),
+                                  g("eps_prior"), g("eps_post"), row_tile=1, stash=stash)
+    want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"], x["eps_prior"], x["eps_post"])
+    for nm, o, w in zip(C.OBS_NAMES, outs, want):
+        close(o, w, f"cluster observe {nm}")
+    close(kl, O.kl_sum(want[5], want[6], want[2], want[3]), "kl", atol=1e-3)
+
+    rs = np.random.RandomState(83)
+    G = [torch.from_numpy((3e-4 * rs.standard_normal((T, B, f))).astype(np.float32)).to(dev) for f in [D] + [S] * 6]
+    L = _lib.lib()
+    d = ops.dims_of(P)
+    keep = ops._Keep()
+    W = ops.rssm_struct(P, keep)
+    p = ops._ptr
+    nt = g("nonterms").reshape(T, B).contiguous()
+    xd = {k_: g(k_) for k_ in ("prev_belief", "eps_prior", "eps_post")}   # (kept alive: only raw pointers cross the C-ABI)
+
+    def backward(mode):
+        mk = lambda *sh: torch.zeros(*sh, device=dev)
+        r = dict(d_q=mk(T, B, 2 * S), d_hq=mk(T, B, Hd), d_p=mk(T, B, 2 * S), d_hp=mk(T, B, Hd), d_gi=mk(T, B, 3 * D),
+                 d_gh=mk(T, B, 3 * D), d_e=mk(T, B, D), d_b0=mk(B, D), d_s0=mk(B, S))
+        ws = torch.empty(L.repo_b200_observe_bwd_workspace_bytes(CT.byref(d), B), dtype=torch.uint8, device=dev)
+        rc = L.repo_b200_observe_bwd_ws(
+            CT.byref(d), CT.byref(W), p(xd["prev_belief"]), p(outs[0]), p(outs[3]), p(outs[6]), p(xd["eps_prior"]), p(xd["eps_post"]),
+            p(nt), p(stash), *[p(t) for t in G], p(r["d_q"]), p(r["d_hq"]), p(r["d_p"]), p(r["d_hp"]), p(r["d_gi"]), p(r["d_gh"]),
+            p(r["d_e"]), p(r["d_b0"]), p(r["d_s0"]), T, B, 1, ops.act_kind("elu"), 0.1, p(ws), ws.numel(), mode, ops._stream())
+        _lib.check(rc, "repo_b200_observe_bwd_ws")
+        return r
+
+    r1, r2 = backward(1), backward(2)
+    for k_ in r1:
+        scale = float(r2[k_].abs().max()) + 1e-30
+        np.testing.assert_allclose((r1[k_] / scale).cpu().numpy(), (r2[k_] / scale).cpu().numpy(), rtol=1e-3, atol=2e-5, err_msg=k_)
+
+
+def test_cluster_kernels_refuse_what_they_cannot_take(ops, dev):
+    """row_tile = 1 is a demand, not a hint: sizes outside the geometry (belief and hidden in different multiples of 16; sizes
+    that are not multiples of 4) and misaligned tensors raise instead of silently running another kernel; auto routing
+    (row_tile = 0) runs them on the row-tiled kernels with the same results as before."""
+    for dims in (dict(belief=64, state=8, action=4, hidden=256, embed=16), dict(belief=72, state=11, action=3, hidden=72, embed=32)):
+        params = O.make_transition_params(91, dims, 1.0)
+        x = O.make_observe_inputs(92, 3, 5, dims)
+        with pytest.raises(RuntimeError):
+            run_observe(ops, dev, params, x, row_tile=1)
+        outs, kl = run_observe(ops, dev, params, x, row_tile=0)
+        want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"], x["eps_prior"], x["eps_post"])
+        for nm, o, w in zip(C.OBS_NAMES, outs, want):
+            close(o, w, f"fallback observe {nm}")
+    # a misaligned (but contiguous) noise tensor: a view that starts one float into its storage
+    params = O.make_transition_params(93)
+    x = O.make_observe_inputs(94, 3, 5)
+    g = lambda k: x[k].to(dev)
+    flat = torch.zeros(x["eps_prior"].numel() + 1, device=dev)
+    eps = flat[1:].view(x["eps_prior"].shape)
+    eps.copy_(g("eps_prior"))
+    with pytest.raises(RuntimeError):
+        ops.observe_fwd(cu(params, dev), g("prev_belief"), g("prev_state"), g("actions"), g("embeds"), g("nonterms"), eps, g("eps_post"), row_tile=1)
+    outs, _, _ = ops.observe_fwd(cu(params, dev), g("prev_belief"), g("prev_state"), g("actions"), g("embeds"), g("nonterms"), eps, g("eps_post"))
+    want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"], x["eps_prior"], x["eps_post"])
+    for nm, o, w in zip(C.OBS_NAMES, outs, want):
+        close(o, w, f"misaligned observe {nm}")
