@@ -153,7 +153,7 @@ int repo_b200_observe_bwd(const repo_b200_dims* dims, const repo_b200_rssm_weigh
 /* Same pass with a caller-provided workspace (>= repo_b200_observe_bwd_workspace_bytes, 16-byte aligned), which lets small
  * batches run on the cluster kernel (csrc/cluster_bwd.cuh: transposed weight slices resident in the shared memory of a
  * 16-CTA cluster, every dx = dy W on the tensor cores, per-sequence power-of-two units).  mode: 0 = auto (cluster kernel when
- * it takes the sizes and batch <= 256, else the kernel above), 1 = cluster kernel or an error, 2 = the kernel above. */
+ * it takes the sizes and alignments, else the kernel above), 1 = cluster kernel or an error, 2 = the kernel above. */
 size_t repo_b200_observe_bwd_workspace_bytes(const repo_b200_dims* dims, int batch);
 int repo_b200_observe_bwd_ws(const repo_b200_dims* dims, const repo_b200_rssm_weights* rssm, const float* prev_belief,
                              const float* beliefs, const float* prior_std_devs, const float* posterior_std_devs,

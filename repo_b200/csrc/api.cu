@@ -626,9 +626,12 @@ bool use_rows_kernel(const repo_b200_dims* d, int n_rows, int row_tile) {
 
 
 // ------------------------------------------------------------------------------------------ cluster observe (cluster.cuh)
-// Largest batch the cluster kernel takes on its own initiative: 16 sequences per 16-CTA cluster; 148 SMs hold eight or nine
-// clusters at a time, and a second wave of clusters is still far below the other kernels' ~47 us per time step.
-constexpr int kClusterAutoBatch = 256;
+// Largest batch the cluster kernel takes on its own initiative: 16 sequences per 16-CTA cluster, about six clusters resident
+// at a time (a cluster needs 16 free SMs inside one GPC), 0.43 ms per wave of a 49-step observe against 2.2-2.5 ms for ANY
+// batch up to 18,944 sequences on the 128-row kernel.  Measured (scripts/cluster_crossover.py): 16/50 sequences 0.43 ms,
+// 128: 0.78, 256: 1.14, 512: 1.89, 768: 2.60 (128-row kernel: 2.47), 1024: 3.67 (2.50).  The backward has no such limit:
+// the per-sequence fp32 kernel costs 12 us per sequence (1.77 ms per wave of 148), the cluster kernel 6 us.
+constexpr int kClusterAutoBatch = 640;
 
 int cluster_max_active() {   // co-resident 16-CTA clusters of the kernel on this device (0: cannot launch)
   static int cached = -1;
@@ -974,7 +977,7 @@ int repo_b200_observe_bwd_ws(const repo_b200_dims* d, const repo_b200_rssm_weigh
   ClBwdGeom g;
   const bool fits = clb_geometry(d->belief, d->state, d->action, d->hidden, g);
   bool cluster = mode != 2 && fits && ws && ws_bytes >= repo_b200_observe_bwd_workspace_bytes(d, batch) &&
-                 (mode == 1 || (batch <= kClusterAutoBatch && !(g_dbg_flags & 8))) &&
+                 (mode == 1 || !(g_dbg_flags & 8)) &&
                  ptrs_aligned({ws, prev_belief, beliefs, stash, g_beliefs, d_hq, d_hp, d_gi, d_gh, d_e}, 16) &&
                  ptrs_aligned({prior_std_devs, post_std_devs, eps_prior, eps_post, g_prior_states, g_prior_means, g_prior_std_devs,
                                g_post_states, g_post_means, g_post_std_devs, d_q, d_p}, 8);

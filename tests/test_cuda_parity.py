@@ -164,9 +164,13 @@ def test_observe_multi_tile_tiled_addend_vs_oracle(ops, dev):
     for nm, o, w in zip(C.OBS_NAMES, outs, want):
         close(o, w, f"multi-tile observe/{nm}")
     close(kl, O.kl_sum(want[5], want[6], want[2], want[3]), "multi-tile observe/kl", atol=1e-4)
-    auto, _ = run_observe(ops, dev, params, x, row_tile=0)   # the library's own pick must agree bit for bit (same kernel)
-    for o, a_ in zip(outs, auto):
-        assert torch.equal(o, a_)
+    # the library's own pick for 300 sequences is the cluster kernel (up to 640): bit for bit what row_tile = 1 gives, and
+    # within tolerance of the 128-row kernel's result
+    auto, _ = run_observe(ops, dev, params, x, row_tile=0)
+    forced, _ = run_observe(ops, dev, params, x, row_tile=1)
+    for o, a_, f_ in zip(outs, auto, forced):
+        assert torch.equal(a_, f_)
+        close(a_, o.cpu(), "auto vs 128-row kernel")
 
 
 @pytest.mark.parametrize("rows,cols,ld", [(0, 7, 7), (1, 1, 1), (63, 12, 12), (2450, 200, 200), (34300, 600, 600), (2401, 60, 1400), (100000, 32, 32)])
