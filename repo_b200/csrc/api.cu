@@ -1389,6 +1389,14 @@ int repo_b200_grad_unshuffle(const float* g, int g_nchw, float* G, float* db, in
   if (rows <= 0) return 0;
   const long long total = rows * cpad;
   const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)std::max(1, sm_count()) * 16);
+  if (channels <= 64 && (cpad & 15) == 0 && rows < (1ll << 30) && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(G) & 15) == 0) {
+    const int rows_per_pass = 256 / (cpad / 4);
+    const int blocks4 = (int)std::min<long long>((rows + rows_per_pass - 1) / rows_per_pass, (long long)std::max(1, sm_count()) * 16);
+    grad_unshuffle4_kernel<<<blocks4, 256, 0, st>>>(g, g_nchw, G, db, (int)rows, RA, RB, Ho, Wo, channels, cpad);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   grad_unshuffle_kernel<<<blocks, 256, 0, st>>>(g, g_nchw, G, db, rows, RA, RB, Ho, Wo, channels, cpad);
   CUDA_OK(cudaGetLastError());
   return 0;

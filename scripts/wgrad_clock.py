@@ -7,8 +7,10 @@ Fr = 2450
 def to_hl(x):
     hi = x.half(); return torch.stack([hi, (x - hi.float()).half()]).contiguous()
 for name, cm, xs, n, ld in [("dec4", cv._deconv_map(32, 30, 30, 6, True, False), (Fr, 30, 30, 32), 12, 16),
-                            ("dec3", cv._deconv_map(64, 13, 13, 6, False, True), (Fr, 13, 13, 64), 128, 128)]:
-    x = to_hl(torch.randn(xs, device=dev))
+                            ("dec3", cv._deconv_map(64, 13, 13, 6, False, True), (Fr, 13, 13, 64), 128, 128),
+                            ("enc1", cv._enc_maps((64, 64))[0], (Fr, 3, 64, 64), 32, 32),
+                            ("enc2", cv._enc_maps((64, 64))[1], (Fr, 31, 31, 32), 64, 64)]:
+    x = torch.randn(xs, device=dev) if name == "enc1" else to_hl(torch.randn(xs, device=dev))
     rows = Fr * cm.RA * cm.RB
     g = torch.randn(rows, ld, device=dev) * 1e-4
     sc = cv.grad_scales(g)
