@@ -601,6 +601,9 @@ def run_gpu(a):
         dist.destroy_process_group()
 
 
+DP_GRAPHS = os.environ.get("REPO_B200_DP_GRAPHS", "1") != "0"
+
+
 def dp_update_block(dev, rank, world, dist):
     """One RePo training iteration (Agent.train_dynamics + train_actor_critic) with the replay batch sharded over ALL ranks:
     strong scaling (global batch 50, shards 7,7,6,6,... with losses weighted B_local / B) and weak scaling (50 sequences per
@@ -643,6 +646,25 @@ def dp_update_block(dev, rank, world, dist):
                      "iteration_ms": timed(lambda: (wm(), ac()), 5), "world_model_update_ms": timed(wm, 5),
                      "actor_critic_update_ms": timed(ac, 5)}
         buckets = {k: int(o.numel) * 4 for k, o in agent.optimizers().items() if hasattr(o, "numel")}
+        # the same iteration as two CUDA-graph replays (Agent.graphed): the gradient all-reduces are captured inside the
+        # graphs (NCCL collectives are capturable; every rank captures in lock-step).  With 6-7 sequences per GPU the eager
+        # iteration is bound by the host issuing ~750 launches, not by the GPU.
+        if DP_GRAPHS:
+            try:
+                g_wm, g_ac = agent.graphed(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"])
+                gs = {}
+
+                def it_g():
+                    gs["b"], gs["s"] = g_wm(batch["obs"], batch["actions"], batch["rewards"], batch["nonterms"])
+                    g_ac(gs["b"].flatten(0, 1), gs["s"].flatten(0, 1))
+
+                for _ in range(3):
+                    it_g()
+                out[mode]["iteration_graphed_ms"] = timed(it_g, 10)
+                del g_wm, g_ac
+            except Exception as exc:  # noqa: BLE001 - reported in the line, the eager numbers above stand
+                out[mode]["iteration_graphed_ms"] = None
+                out[mode]["graph_capture_error"] = str(exc)[:200]
         del agent
     # the collective alone: SUM all-reduce of fp32 buffers of the bucket sizes (world model, actor, value)
     sizes = buckets if buckets else {"model": 5_170_420 * 4, "actor": 169_212 * 4, "value": 126_801 * 4}

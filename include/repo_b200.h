@@ -83,7 +83,9 @@ int repo_b200_imagine_fwd(const repo_b200_dims* dims, const repo_b200_rssm_weigh
  * repo_b200_imagine_fwd when non-NULL: per (t,row) [embed hidden D][r D][z D][n D][h_n D][prior hidden H]
  * [actor h1..h4 4H][action mean A][action std A].  g_*: incoming gradients of the four outputs (nullable).
  * Outputs: pre-activation gradients of the transition layers (d_p (.,2S), d_hp (.,H), d_gi/d_gh (.,3D), d_e (.,D))
- * and of the actor's fc5..fc1 (d_a5 (.,2A), d_a4..d_a1 (.,H)), plus gradients of the start rows (nullable). */
+ * and of the actor's fc5..fc1 (d_a5 (.,2A), d_a4..d_a1 (.,H)), plus gradients of the start rows (nullable).
+ * d_a4..d_a1 may all be NULL: the actor's inputs are detached (rssm.py:170), so nothing in the recurrence reads its hidden
+ * layers' gradients and the caller may compute them after the time loop from d_a5 (dense GEMMs over all (t,row)). */
 /* ---- conditional (multitask) variants: ConditionalTransitionModel.imagine (rssm.py:225-248) with a
  * ConditionalActorModel (actor_critic.py:105-148).  dims.action is the pseudo-action width (action + condition, what the
  * reference passes to the base class, rssm.py:198-206); `condition` is (n_rows, cond_size), constant over the horizon;

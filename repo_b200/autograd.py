@@ -189,7 +189,13 @@ class ImagineFn(torch.autograd.Function):
         c = lambda g: None if g is None else g.contiguous().float()
         mk = lambda f: torch.empty(T, N, f, device=dev, dtype=torch.float32)
         d_p, d_hp, d_gi, d_gh, d_e = mk(2 * S), mk(Hd), mk(3 * D), mk(3 * D), mk(D)
-        d_a5, d_a4, d_a3, d_a2, d_a1 = mk(2 * A), mk(Hd), mk(Hd), mk(Hd), mk(Hd)
+        # The actor's hidden layers feed nothing back into the recurrence (its inputs are detached, rssm.py:170): from
+        # `_DENSE_MIN_ROWS` (t,row) samples the kernel stops at d_a5 and fc5 -> fc2 run afterwards as four dense tcgen05
+        # GEMMs over all samples (activation derivative from the stashed h4..h1 fused in the epilogue) — 27 % of the fp32
+        # SIMT kernel's per-step work, moved to the tensor cores.
+        hoist = T * N >= _DENSE_MIN_ROWS and Hd % 4 == 0 and (2 * A) % 4 == 0
+        d_a5 = mk(2 * A)
+        d_a4, d_a3, d_a2, d_a1 = (None,) * 4 if hoist else (mk(Hd), mk(Hd), mk(Hd), mk(Hd))
         need_b0, need_s0 = ctx.needs_input_grad[4], ctx.needs_input_grad[5]
         d_b0 = torch.empty(N, D, device=dev) if (need_b0 or need_s0) else None
         d_s0 = torch.empty(N, S, device=dev) if (need_b0 or need_s0) else None
@@ -203,6 +209,19 @@ class ImagineFn(torch.autograd.Function):
             p(d_a5), p(d_a4), p(d_a3), p(d_a2), p(d_a1), p(d_b0), p(d_s0), horizon, N, ops.act_kind(act), float(min_std),
             float(mean_scale), float(a_min_std), ops._stream())
         _lib.check(rc, "repo_b200_imagine_cond_bwd")
+        if hoist:
+            from .conv import _as_input_side, dense_layer, grad_scales
+            off_a = 5 * D + Hd
+            st2 = stash.reshape(T * N, -1)
+            g_prev = d_a5.reshape(T * N, 2 * A)
+            outs_a = []
+            for li, wkey in zip((4, 3, 2, 1), ("fc5.weight", "fc4.weight", "fc3.weight", "fc2.weight")):
+                dst = torch.empty(T * N, Hd, device=dev, dtype=torch.float32)
+                dense_layer(g_prev, anamed[wkey].detach().t().contiguous(), None, dst,
+                            mask=st2[:, off_a + (li - 1) * Hd: off_a + li * Hd], mask_act="elu", scales=_as_input_side(grad_scales(g_prev)))
+                outs_a.append(dst.reshape(T, N, Hd))
+                g_prev = dst
+            d_a4, d_a3, d_a2, d_a1 = outs_a
 
         flat = lambda x: x.reshape(T * N, -1)
         need = dict(zip(PARAM_KEYS + ["actor." + k for k in ACTOR_KEYS], ctx.needs_input_grad[9:]))

@@ -1065,8 +1065,11 @@ int repo_b200_imagine_cond_bwd(const repo_b200_dims* d, const repo_b200_rssm_wei
   if (horizon == 1 || n_rows == 0) return 0;
   if (!W || !actor || actor->n_layers != 5) return fail(-1, "imagine_bwd: weights missing");
   if (!start_belief || !beliefs || !actions || !prior_std_devs || !eps_prior || !eps_action || !stash || !d_p || !d_hp ||
-      !d_gi || !d_gh || !d_e || !d_a5 || !d_a4 || !d_a3 || !d_a2 || !d_a1)
+      !d_gi || !d_gh || !d_e || !d_a5)
     return fail(-1, "imagine_bwd: NULL pointer");
+  // d_a4 .. d_a1 all NULL: the caller hoists the actor's hidden layers out of the time loop (they feed nothing back)
+  if ((!d_a4 || !d_a3 || !d_a2 || !d_a1) && (d_a4 || d_a3 || d_a2 || d_a1))
+    return fail(-1, "imagine_bwd: d_a4 .. d_a1 must be given together or all be NULL");
   ImgBwdParams P{};
   P.T = horizon - 1; P.N = n_rows; P.D = d->belief; P.S = d->state; P.A = d->action; P.Hd = d->hidden;
   P.A_act = d->action - cond_size;

@@ -390,7 +390,9 @@ __global__ void __launch_bounds__(256) imagine_bwd_kernel(const __grid_constant_
       }
     }
     __syncthreads();
-    // ---- actor chain fc5 -> fc2 (ELU everywhere); its inputs are detached, so it stops at d1 ----
+    // ---- actor chain fc5 -> fc2 (ELU everywhere); its inputs are detached, so it stops at d1.  Nothing in the recurrence
+    // reads it (rssm.py:170): with d_a4 == NULL the caller runs it AFTER the time loop as dense GEMMs over all (t, row). ----
+    if (P.d_a4 == nullptr) continue;
     const float* Wk[4] = {P.w_a5, P.w_a4, P.w_a3, P.w_a2};
     float* outk[4] = {P.d_a4, P.d_a3, P.d_a2, P.d_a1};
     const float* src = d5;

@@ -1074,3 +1074,34 @@ def test_cluster_kernels_refuse_what_they_cannot_take(ops, dev):
     want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"], x["eps_prior"], x["eps_post"])
     for nm, o, w in zip(C.OBS_NAMES, outs, want):
         close(o, w, f"misaligned observe {nm}")
+
+
+def test_imagine_backward_hoisted_actor_chain(dev, monkeypatch):
+    """From 1024 (t, row) samples the imagine backward stops at the action head inside the time loop and runs the actor's
+    hidden layers afterwards as dense GEMMs (their inputs are detached, rssm.py:170): actor and transition gradients must
+    match the all-in-kernel chain on the same rollout."""
+    from repo_b200 import autograd as AG
+    from repo_b200.models import ActorModel
+    from repo_b200.rssm import TransitionModel
+    params = O.make_transition_params(311)
+    actor = O.make_mlp_params(312, 230, 200, 12, 4)
+    N, H = 300, 6                                          # 1,500 samples: above the threshold
+    x = O.make_imagine_inputs(313, N, H)
+    rs = np.random.RandomState(314)
+    R = [torch.from_numpy((1e-3 * rs.standard_normal((H - 1, N, f))).astype(np.float32)).to(dev) for f in (200, 30, 30, 30)]
+
+    def run(min_rows):
+        monkeypatch.setattr(AG, "_DENSE_MIN_ROWS", min_rows)
+        m = TransitionModel(200, 30, 6, 200, 1024, "elu").to(dev)
+        m.load_state_dict(params)
+        pol = ActorModel(200, 30, 200, 6, "elu").to(dev)
+        pol.load_state_dict(actor)
+        outs = m.imagine(x["belief"].to(dev), x["state"].to(dev), pol, H, eps_action=x["eps_action"].to(dev), eps_prior=x["eps_prior"].to(dev))
+        sum((r * o).sum() for r, o in zip(R, outs)).backward()
+        return {**{"actor." + k: v.grad for k, v in pol.named_parameters()}, **{k: v.grad for k, v in m.named_parameters() if v.grad is not None}}
+
+    hoisted, fused = run(1024), run(10 ** 9)
+    assert set(hoisted) == set(fused) and any(k.startswith("actor.fc2") for k in hoisted)
+    for k in fused:
+        scale = float(fused[k].abs().max()) + 1e-30
+        np.testing.assert_allclose((hoisted[k] / scale).cpu().numpy(), (fused[k] / scale).cpu().numpy(), rtol=1e-3, atol=2e-5, err_msg=k)
