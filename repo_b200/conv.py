@@ -173,7 +173,7 @@ def wgrad_gemm(dpre, x):
     """dW (n, k) = dpre^T @ x for 2-D fp32 operands — the weight gradient of a Linear layer over all (t, row) samples —
     on the tcgen05 weight-gradient kernel (fp16 hi/lo three-product arithmetic, gradient operand rescaled by a power of
     two).  `x` may be a column window of a wider row-major matrix (e.g. a slice of the activation stash); n > 256 is
-    processed in 256-column slices of dpre."""
+    processed in 256-column slices of dpre inside one launch."""
     rows, n = dpre.shape
     k = x.shape[1]
     if x.shape[0] != rows:
@@ -189,19 +189,12 @@ def wgrad_gemm(dpre, x):
     kk = x.shape[1]
     cmap = ConvMap(RA=1, RB=1, in_nchw=0, C=kk, H=1, W=1, TH=1, TW=1, sy=1, sx=1, dy=1, dx=1, Ho=1, Wo=1, pix=x.stride(0))
     sc = grad_scales(dpre)
-    L = _lib.lib()
-    outs = []
-    for n0 in range(0, n, 256):
-        nn_ = min(256, n - n0)
-        npad = (nn_ + 3) // 4 * 4
-        if npad != nn_ or (n % 4):
-            raise RuntimeError("wgrad_gemm: output features must be a multiple of 4")
-        dw = torch.empty(nn_, kk, device=x.device, dtype=torch.float32)
-        g_view = dpre[:, n0:]
-        rc = L.repo_b200_conv_wgrad(_p(x), C.c_void_p(g_view.data_ptr()), _p(sc), _p(dw), rows, nn_, n, cmap.carray(), 0, _stream())
-        _lib.check(rc, "repo_b200_conv_wgrad")
-        outs.append(dw)
-    dw = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+    if n % 4:
+        raise RuntimeError("wgrad_gemm: output features must be a multiple of 4")
+    dw = torch.empty(n, kk, device=x.device, dtype=torch.float32)
+    # (more than 256 output features run as 256-wide slices inside ONE launch: blockIdx.y = slice)
+    rc = _lib.lib().repo_b200_conv_wgrad(_p(x), _p(dpre), _p(sc), _p(dw), rows, n, n, cmap.carray(), 0, _stream())
+    _lib.check(rc, "repo_b200_conv_wgrad")
     return dw[:, :k] if kk != k else dw
 
 

@@ -1294,20 +1294,26 @@ int repo_b200_conv_wgrad(const void* input_, const float* grad_rows, const float
   if (cm.pix == 0) cm.pix = cm.C;
   if (cm.pix < cm.C) return fail(-1, "conv: pixel stride %d < channels %d", cm.pix, cm.C);
   if (cm.tap0 != 0 || cm.ntaps != cm.TH * cm.TW) return fail(-1, "conv_wgrad: partial tap windows are not supported");
-  if (cm.ntaps < 1 || cm.C < 1 || n_total < 1 || n_total > 256 || (n_total & 3) || g_ld < n_total || (g_ld & 3))
-    return fail(-1, "conv_wgrad: n_total must be a multiple of 4 and <= 256 (got %d, row stride %d)", n_total, g_ld);
+  if (cm.ntaps < 1 || cm.C < 1 || n_total < 1 || (n_total & 3) || g_ld < n_total || (g_ld & 3))
+    return fail(-1, "conv_wgrad: n_total must be a multiple of 4 (got %d, row stride %d)", n_total, g_ld);
+  // more than 256 output features: slices of 256 (the accumulator tile), all in one launch (blockIdx.y = slice)
+  const int n_all = n_total;
+  const int n_slices = cdiv(n_all, 256);
+  if (n_slices > 1) n_total = 256;
+  const int n_last = n_all - (n_slices - 1) * 256;
   if ((reinterpret_cast<uintptr_t>(input) & 15) || (reinterpret_cast<uintptr_t>(grad_rows) & 15))
     return fail(-1, "conv_wgrad: tensors must be 16-byte aligned");
   const int K = cm.ntaps * cm.C;
   const long long rows = (long long)frames * cm.RA * cm.RB;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)n_total * K * sizeof(float), st));
+  CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)n_all * K * sizeof(float), st));
   if (rows <= 0) return 0;
   if (rows > 0x7fffffffLL - 128) return fail(-1, "conv_wgrad: too many rows");
   WgradParams P{};
   P.x = input; P.g = grad_rows; P.dw = dw; P.scales = scales; P.cm = cm;
   P.n_rows = (int)rows; P.K = K; P.k16 = cdiv(K, 16); P.n_total = n_total; P.g_ld = g_ld;
   P.NP = cdiv(n_total, 16) * 16;
+  P.n_last = n_last;
   P.x_hl = input_hl ? 1 : 0;
   P.dbg = g_dbg_clock;
   if (P.x_hl && (cm.in_nchw || (cm.C & 7) || cm.pix != cm.C)) return fail(-1, "conv_wgrad: HL input needs NHWC and C %% 8 == 0");
@@ -1329,7 +1335,8 @@ int repo_b200_conv_wgrad(const void* input_, const float* grad_rows, const float
     m += P.mt[s];
     mt_top = std::max(mt_top, P.mt[s]);
     P.cta0[s] = cta;
-    const int splits = std::max(1, std::min(stages_total, (sms * P.mt[s] + m_tiles / 2) / m_tiles));
+    // row splits: fill the SMs once over all (slice, super tile) pairs — every split adds one atomic pass over its dW tile
+    const int splits = std::max(1, std::min(stages_total, (sms * P.mt[s] + m_tiles * n_slices / 2) / (m_tiles * n_slices)));
     cta += splits;
   }
   P.cta0[P.n_super] = cta;
@@ -1343,7 +1350,7 @@ int repo_b200_conv_wgrad(const void* input_, const float* grad_rows, const float
     CUDA_OK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  conv_wgrad_kernel<<<cta, kCvThreads, smem, st>>>(P);
+  conv_wgrad_kernel<<<dim3(cta, n_slices), kCvThreads, smem, st>>>(P);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -580,6 +580,9 @@ struct WgradParams {
   long long x_lo_bytes;
   ConvMap cm;
   int n_rows, K, k16, n_total, g_ld, NP;
+  // blockIdx.y = slice of the output features: slice s takes columns [s * NP, s * NP + n) of g and rows [s * NP, ..) of dw,
+  // n = NP except n_last in the last slice (dW of a wide Linear layer in ONE launch instead of one per 256 features)
+  int n_last;
   int n_super;                       // super tiles
   int m0[kWgMaxSuper], mt[kWgMaxSuper];   // first 128-k tile and tile count of each super tile
   int cta0[kWgMaxSuper + 1];         // first CTA of each super tile (prefix sums of the row splits)
@@ -600,6 +603,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 4), bar_accf = smem_u32(bars + 8);
   const ConvMap& cm = P.cm;
+  const int n_slice = (blockIdx.y + 1 == gridDim.y) ? P.n_last : P.n_total;   // output features of this CTA's slice
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kCvMaxStages; ++i) {
@@ -713,12 +717,12 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
       // one L2 round trip per stage, overlapped with the wait for the MMAs that still read the slot
       float4 gv[4];
       {
-        const float* grow = P.g + (size_t)(valid ? row : 0) * P.g_ld;
+        const float* grow = P.g + (size_t)blockIdx.y * P.NP + (size_t)(valid ? row : 0) * P.g_ld;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int n = i * 64 + q * 4;
           gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < nblocks && valid && n < P.n_total) gv[i] = __ldg(reinterpret_cast<const float4*>(grow + n));
+          if (i < nblocks && valid && n < n_slice) gv[i] = __ldg(reinterpret_cast<const float4*>(grow + n));
         }
       }
       if (P.x_hl) {
@@ -837,14 +841,15 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
       tc_fence_after();
       for (int t = 0; t < mt; ++t) {
         const int k = (m0 + t) * 128 + qd * 32 + lane;
-        for (int c = 0; c < P.n_total; c += 16) {
+        float* dw = P.dw + (size_t)blockIdx.y * P.NP * P.K;
+        for (int c = 0; c < n_slice; c += 16) {
           float v[16];
           tmem_ld16(tlane + (uint32_t)(t * P.NP + c), v);
           tmem_ld_wait();
           if (k < P.K) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (c + i < P.n_total) atomicAdd(P.dw + (size_t)(c + i) * P.K + k, v[i] * unscale);
+              if (c + i < n_slice) atomicAdd(dw + (size_t)(c + i) * P.K + k, v[i] * unscale);
           }
         }
       }
