@@ -786,7 +786,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
             }
           }
           if (!waited) {
+            const long long T1 = clock64();
             mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+            const long long T2 = clock64();
+            c_issue += T1 - T0; c_wait += T2 - T1; c_store -= T2;
             waited = true;
           }
 #pragma unroll
@@ -821,7 +824,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_wgrad_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * slot);
       const long long T4 = clock64();
-      if (P.x_hl) { c_store += T3; c_arrive += T4 - T3; }
+      c_store += T3; c_arrive += T4 - T3;
       if (++slot == (uint32_t)n_stages) { slot = 0; phase ^= 1; }
       rb += kWgRows;
       while (rb >= cm.RB) { rb -= cm.RB; ++ra; }
