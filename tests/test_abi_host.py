@@ -40,6 +40,22 @@ def test_workspace_sizes(lib):
     assert b"belief_size" in lib.repo_b200_last_error()
 
 
+def test_cluster_kernel_workspaces_and_modes(lib):
+    """Host logic of the small-batch cluster kernels that needs no GPU: the observe workspace holds the 16 per-rank weight
+    images (136,192 bytes each at the default sizes), the backward workspace the 16 transposed images (128,000 bytes each)
+    plus two floats per sequence; sizes outside the cluster geometry get the minimal backward workspace (the entry point
+    then runs the per-sequence kernel); an unknown mode is refused before anything is launched."""
+    from repo_b200._lib import Dims
+    d = Dims(200, 30, 6, 200, 1024)
+    assert lib.repo_b200_observe_workspace_bytes(C.byref(d), 49, 50) >= 16 * 136192
+    need = lib.repo_b200_observe_bwd_workspace_bytes(C.byref(d), 50)
+    assert need >= 16 * 128000 + 50 * 8 and need % 256 == 0
+    odd = Dims(64, 8, 4, 256, 16)      # belief and hidden in different multiples of 16: no cluster geometry
+    assert lib.repo_b200_observe_bwd_workspace_bytes(C.byref(odd), 50) == 256
+    rc = lib.repo_b200_observe_bwd_ws(C.byref(d), None, *([None] * 24), 5, 3, 1, 1, 0.1, None, 0, 7, None)
+    assert rc == -1 and b"mode" in lib.repo_b200_last_error()
+
+
 def test_no_device_fails_loudly(lib):
     if torch.cuda.is_available():
         pytest.skip("has a GPU")
