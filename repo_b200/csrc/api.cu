@@ -1091,7 +1091,11 @@ int repo_b200_imagine_cond_bwd(const repo_b200_dims* d, const repo_b200_rssm_wei
   // per-stage stash traffic, not by the weight fetch latency.  Round 2 confirmed it from the other side: splitting every
   // reduction over two thread groups (512 threads, 16 warps instead of 8 to hide the L2 latency with) — 3.31 vs 3.34 ms.
   const int sms = std::max(1, sm_count());
-  const int rb = n_rows <= 8 * sms ? 8 : (n_rows <= 12 * sms ? 12 : 20);
+  // (few rows, e.g. a data-parallel shard of 343: 4 rows per CTA spread the shard over 86 SMs instead of 43 — the per-step
+  // time of a CTA is what such a launch costs, and it grows with the rows the CTA carries)
+  // Up to 12 rows per CTA two CTAs are resident per SM (bwd.cuh): the block size is the smallest that keeps the launch
+  // inside one wave of 2 x SMs CTAs (2,450 rows -> 12 rows, 205 CTAs).
+  const int rb = n_rows <= 4 * sms ? 4 : (n_rows <= 16 * sms ? 8 : (n_rows <= 24 * sms ? 12 : 20));
   const size_t smem = (size_t)(9 * P.D + 3 * P.S + 2 * P.Hd + 2 * P.A) * rb * sizeof(float);
   if (smem > 220 * 1024) return fail(-1, "imagine_bwd: model too wide for the %d-row backward block", rb);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1104,7 +1108,8 @@ int repo_b200_imagine_cond_bwd(const repo_b200_dims* d, const repo_b200_rssm_wei
     CUDA_OK(cudaGetLastError());
     return 0;
   };
-  static size_t c8 = 0, c12 = 0, c20 = 0;
+  static size_t c4 = 0, c8 = 0, c12 = 0, c20 = 0;
+  if (rb == 4) return go(imagine_bwd_kernel<4>, c4);
   if (rb == 8) return go(imagine_bwd_kernel<8>, c8);
   if (rb == 12) return go(imagine_bwd_kernel<12>, c12);
   return go(imagine_bwd_kernel<20>, c20);

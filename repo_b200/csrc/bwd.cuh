@@ -252,8 +252,11 @@ __device__ __forceinline__ void col_dot_rows(const float* __restrict__ W, int ld
   }
 }
 
+// Up to 12 rows per CTA two CTAs share an SM (<= 128 registers, 2 x 110 KB of shared memory): the kernel's time is set by
+// the instruction stream of a CTA (0.55 ms + 0.077 ms per row it carries, measured at 4 / 8 / 12 / 20 rows), and two
+// warps per scheduler leave issue slots empty that a second CTA fills.
 template <int RB>
-__global__ void __launch_bounds__(256) imagine_bwd_kernel(const __grid_constant__ ImgBwdParams P) {
+__global__ void __launch_bounds__(256, RB <= 12 ? 2 : 1) imagine_bwd_kernel(const __grid_constant__ ImgBwdParams P) {
   extern __shared__ float sm[];
   // A = width of the [action | condition] slot that enters the embedding layer, Aa = sampled action width (Aa == A
   // unless the model is conditional: rssm.py:225-236; the condition columns carry no gradient)
