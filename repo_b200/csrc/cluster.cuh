@@ -16,12 +16,14 @@
 //   PQ2  prior / posterior mean, std, sample (owners of state dimensions only); next state -> all CTAs
 //
 // Activations are the A operand (M = 128 of which 16 rows exist: the descriptor's other row groups alias the neighbouring
-// bytes and produce accumulator lanes nobody reads), weights the B operand (N = 16..48), accumulators in TMEM with
-// lane = row.  Every product is the same hi*hi + lo*hi + hi*lo fp16 triple as in the other kernels, but ONE tcgen05.mma
+// bytes and produce accumulator lanes nobody reads), weights the B operand (16 or 32 outputs per block, twice that many rows,
+// see below), accumulators in TMEM with lane = row.  Every product is the same hi*hi + lo*hi + hi*lo fp16 triple as in the other kernels, but ONE tcgen05.mma
 // per k16 slab computes all three: the lo halves of the 16 rows sit 256 B behind the hi halves, i.e. they ARE row groups
 // 2..3 of the M = 128 operand (accumulator lanes 16..31 = lo * W), and a weight block stacks its lo rows under its hi rows
 // (N doubles: columns [0, N) = x * W_hi, [N, 2N) = x * W_lo).  The epilogue adds lane r's two column groups and lane
-// r + 16's first one (one warp shuffle).  Issue cost, not tensor throughput, bounds these tiny MMAs (~40 cycles each).
+// r + 16's first one (one warp shuffle).  An MMA costs ~47 cycles whatever N is here (the 4 KB A-operand read), so the
+// count is what matters: 81 per step instead of 243.  The four epilogue warps (warp % 4 == 0: TMEM lanes 0..31) each take
+// 4 of the CTA's 16 features for all 16 rows; every global access of a thread is one 16-byte (state: 8-byte) vector.
 //
 // Buffer hazards: a CTA sends layer L's output only after its own layer-L MMAs, which needed every peer's layer L-1 output,
 // which each peer sent after finishing layer L-1 — so when the data lands, every peer is at most reading layer L's input.
