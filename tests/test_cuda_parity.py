@@ -1105,3 +1105,52 @@ def test_imagine_backward_hoisted_actor_chain(dev, monkeypatch):
     for k in fused:
         scale = float(fused[k].abs().max()) + 1e-30
         np.testing.assert_allclose((hoisted[k] / scale).cpu().numpy(), (fused[k] / scale).cpu().numpy(), rtol=1e-3, atol=2e-5, err_msg=k)
+
+
+def test_cluster_observe_long_sequence_and_row_scales(ops, dev):
+    """150 steps through the cluster kernels (barrier phases wrap 75 times; no error build-up beyond tolerance), and a
+    backward whose incoming gradients differ by twelve orders of magnitude between sequences: every sequence runs in its
+    own power-of-two units, so each row must agree with the fp32 per-sequence kernel relative to ITS OWN magnitude."""
+    import ctypes as CT
+    from repo_b200 import _lib
+    params = O.make_transition_params(401)
+    x = O.make_observe_inputs(402, 151, 20, p_done=0.02)
+    T, B = x["actions"].shape[:2]
+    g = lambda k: x[k].to(dev)
+    P = cu(params, dev)
+    stash = torch.zeros(T, B, 5 * 200 + 2 * 200, device=dev)
+    keepx = {k_: g(k_) for k_ in ("prev_belief", "prev_state", "actions", "embeds", "nonterms", "eps_prior", "eps_post")}
+    outs, kl, _ = ops.observe_fwd(P, *[keepx[k_] for k_ in ("prev_belief", "prev_state", "actions", "embeds", "nonterms", "eps_prior", "eps_post")],
+                                  row_tile=1, stash=stash)
+    want = O.observe(params, x["prev_belief"], x["prev_state"], x["actions"], x["embeds"], x["nonterms"], x["eps_prior"], x["eps_post"])
+    for nm, o, w in zip(C.OBS_NAMES, outs, want):
+        close(o, w, f"150-step cluster observe {nm}")
+
+    rs = np.random.RandomState(403)
+    row_scale = torch.from_numpy(10.0 ** rs.uniform(-9, 3, size=(1, B, 1)).astype(np.float32)).to(dev)
+    G = [torch.from_numpy(rs.standard_normal((T, B, f)).astype(np.float32)).to(dev) * row_scale for f in [200] + [30] * 6]
+    L = _lib.lib()
+    d = ops.dims_of(P)
+    keep = ops._Keep()
+    W = ops.rssm_struct(P, keep)
+    p = ops._ptr
+    nt = keepx["nonterms"].reshape(T, B).contiguous()
+
+    def backward(mode):
+        mk = lambda *sh: torch.zeros(*sh, device=dev)
+        r = dict(d_q=mk(T, B, 60), d_hq=mk(T, B, 200), d_p=mk(T, B, 60), d_hp=mk(T, B, 200), d_gi=mk(T, B, 600),
+                 d_gh=mk(T, B, 600), d_e=mk(T, B, 200))
+        b0, s0 = mk(B, 200), mk(B, 30)
+        ws = torch.empty(L.repo_b200_observe_bwd_workspace_bytes(CT.byref(d), B), dtype=torch.uint8, device=dev)
+        rc = L.repo_b200_observe_bwd_ws(
+            CT.byref(d), CT.byref(W), p(keepx["prev_belief"]), p(outs[0]), p(outs[3]), p(outs[6]), p(keepx["eps_prior"]),
+            p(keepx["eps_post"]), p(nt), p(stash), *[p(t) for t in G], p(r["d_q"]), p(r["d_hq"]), p(r["d_p"]), p(r["d_hp"]),
+            p(r["d_gi"]), p(r["d_gh"]), p(r["d_e"]), p(b0), p(s0), T, B, 1, ops.act_kind("elu"), 0.1, p(ws), ws.numel(), mode,
+            ops._stream())
+        _lib.check(rc, "repo_b200_observe_bwd_ws")
+        return r
+
+    r1, r2 = backward(1), backward(2)
+    for k_ in r1:
+        per_row = r2[k_].abs().amax(dim=(0, 2), keepdim=True) + 1e-38      # each sequence against its own magnitude
+        np.testing.assert_allclose((r1[k_] / per_row).cpu().numpy(), (r2[k_] / per_row).cpu().numpy(), rtol=1e-3, atol=3e-5, err_msg=k_)
