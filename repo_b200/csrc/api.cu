@@ -1225,8 +1225,7 @@ int conv_gemm_impl(const void* input_, const float* w_mat, int w_ld, int w_col0,
       b.a = bias; b.b = nullptr; b.a_off = nt * P.NP; b.b_off = 0; b.n = j.seg_n[0]; b.n_pad = P.NP; b.dst_off = nt * P.NP;
     }
     pa.n_jobs = ba.n_jobs = P.n_tiles;
-    pack_rows_weights_kernel<<<P.n_tiles * P.k16, 256, 0, st>>>(pa);
-    pack_rows_bias_kernel<<<P.n_tiles, 256, 0, st>>>(ba);
+    pack_rows_both_kernel<<<P.n_tiles * P.k16 + P.n_tiles, 256, 0, st>>>(pa, ba, P.n_tiles * P.k16);
     CUDA_OK(cudaGetLastError());
   }
   P.x = input; P.wblob = wblob; P.bias = bias_p; P.relu_mask = relu_mask; P.scales = scales; P.out = out;

@@ -100,11 +100,11 @@ struct BiasRowsArgs {
   float* bias;
 };
 
-__global__ void __launch_bounds__(256) pack_rows_weights_kernel(const __grid_constant__ PackRowsArgs a) {
+__device__ __forceinline__ void pack_rows_weights_block(const PackRowsArgs& a, int block) {
   int ji = 0;
-  while (ji + 1 < a.n_jobs && (int)blockIdx.x >= a.jobs[ji + 1].blk0) ++ji;
+  while (ji + 1 < a.n_jobs && block >= a.jobs[ji + 1].blk0) ++ji;
   const PackRowsJob& j = a.jobs[ji];
-  const int slab = blockIdx.x - j.blk0;
+  const int slab = block - j.blk0;
   const int m = threadIdx.x;
   if (m >= j.n_pad) return;
   int src_row = -1;
@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(256) pack_rows_weights_kernel(const __grid_con
   }
 }
 
-__global__ void __launch_bounds__(256) pack_rows_bias_kernel(const __grid_constant__ BiasRowsArgs a) {
-  const BiasRowsJob& j = a.jobs[blockIdx.x];
+__device__ __forceinline__ void pack_rows_bias_block(const BiasRowsArgs& a, int block) {
+  const BiasRowsJob& j = a.jobs[block];
   for (int i = threadIdx.x; i < j.n_pad; i += blockDim.x) {
     float v = 0.f;
     if (i < j.n) {
@@ -138,6 +138,20 @@ __global__ void __launch_bounds__(256) pack_rows_bias_kernel(const __grid_consta
     }
     a.bias[j.dst_off + i] = v;
   }
+}
+
+__global__ void __launch_bounds__(256) pack_rows_weights_kernel(const __grid_constant__ PackRowsArgs a) {
+  pack_rows_weights_block(a, (int)blockIdx.x);
+}
+__global__ void __launch_bounds__(256) pack_rows_bias_kernel(const __grid_constant__ BiasRowsArgs a) {
+  pack_rows_bias_block(a, (int)blockIdx.x);
+}
+// weights and biases of one launch's operands in ONE kernel: blocks [0, n_weight_blocks) pack weight slabs, the rest biases
+// (a dense layer / conv call is then two launches — pack + GEMM — instead of three; ~90 such calls per training iteration)
+__global__ void __launch_bounds__(256) pack_rows_both_kernel(const __grid_constant__ PackRowsArgs a, const __grid_constant__ BiasRowsArgs b,
+                                                             int n_weight_blocks) {
+  if ((int)blockIdx.x < n_weight_blocks) pack_rows_weights_block(a, (int)blockIdx.x);
+  else pack_rows_bias_block(b, (int)blockIdx.x - n_weight_blocks);
 }
 
 }  // namespace rb
