@@ -49,7 +49,7 @@ struct ClGeom {
   uint32_t off_sa, off_h1, off_h2, off_b0, off_b1, off_w;  // byte offsets in dynamic shared memory
   uint32_t w_e, w_hh_rz, w_hh_n, w_ih_rz, w_ih_n, w_pq1, w_pr, w_po;   // byte offsets inside a CTA's weight image
   uint32_t cta_bytes;                                      // weight image per CTA
-  uint32_t off_bias, off_bar, smem_bytes;
+  uint32_t off_bias, off_stage, off_bar, smem_bytes;
 };
 
 __host__ __device__ inline bool cl_geometry(int D, int S, int A, int Hd, ClGeom& g) {
@@ -83,6 +83,7 @@ __host__ __device__ inline bool cl_geometry(int D, int S, int A, int Hd, ClGeom&
   o += w;
   if (w < 2048) return false;  // the aliased row groups of the last activation slab read up to 2 KB past it
   g.off_bias = o; o += 144 * 4;
+  g.off_stage = o; o += 2u * kClRows * 64u;   // two steps of this CTA's slice of the hoisted embedding projection (TMA-staged)
   g.off_bar = o; o += 16 * 8 + 16;
   g.smem_bytes = o;
   return o <= 227u * 1024u;
@@ -258,7 +259,8 @@ __device__ __forceinline__ void cl_put2(uint8_t* buf, int row, int k, float v0, 
 
 __device__ __forceinline__ float cl_act(float x, int act) { return act == ACT_ELU ? act_t<ACT_ELU>(x) : act_t<ACT_RELU>(x); }
 
-enum ClBar { CB_W = 0, CB_IN_E, CB_IN_G, CB_IN_PQ1, CB_IN_PQ2, CB_ACC_E, CB_ACC_G, CB_ACC_PQ1, CB_ACC_PQ2, CB_COUNT };
+enum ClBar { CB_W = 0, CB_IN_E, CB_IN_G, CB_IN_PQ1, CB_IN_PQ2, CB_ACC_E, CB_ACC_G, CB_ACC_PQ1, CB_ACC_PQ2,
+             CB_AD_FULL0, CB_AD_FULL1, CB_AD_FREE0, CB_AD_FREE1, CB_COUNT };
 
 __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(const __grid_constant__ ClParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(con
     mbar_init(bar(CB_W), 1);
     for (int i = CB_IN_E; i <= CB_IN_PQ2; ++i) mbar_init(bar(i), 2);  // the issuer's expect_tx + the local epilogue
     for (int i = CB_ACC_E; i <= CB_ACC_PQ2; ++i) mbar_init(bar(i), 1);
+    for (int i = CB_AD_FULL0; i <= CB_AD_FREE1; ++i) mbar_init(bar(i), 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -414,6 +417,26 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(con
         __syncwarp();
       }
     }
+  } else if (active && warp == 2 && with_obs) {
+    // ================================ per-step input loader ================================
+    // The per-step embeddings — the hoisted embedding projection, i.e. the posterior layer's addend, T x N x hidden in global
+    // memory — are staged by the TMA engine: per step one 64-byte bulk copy per sequence (this CTA's 16 features; lane =
+    // sequence of the cluster) into a two-step ring, completion on an mbarrier; the epilogue reads its four values from
+    // shared memory.  (The noise rows were staged the same way in an experiment — one bulk copy per tensor and step on the
+    // CTAs that own state dimensions — and cost 0.02 ms per 49-step pass against 8-byte loads issued a stage ahead; they
+    // stay plain loads.)
+    uint8_t* stage = smem + g.off_stage;
+    const int nfeat = min(16, Hd - 16 * c);                       // multiple of 4: the copy is a multiple of 16 bytes
+    const int rows_valid = max(0, min(kClRows, N - row0));
+    for (int t = 0; t < T; ++t) {
+      const int slot = t & 1;
+      if (t >= 2) mbar_wait(bar(CB_AD_FREE0 + slot), (uint32_t)(((t >> 1) - 1) & 1));   // step t-2 has been consumed
+      if (lane == 0) mbar_arrive_expect_tx(bar(CB_AD_FULL0 + slot), (uint32_t)(rows_valid * nfeat * 4));
+      __syncwarp();
+      if (lane < rows_valid)
+        bulk_g2s(smem_u32(stage + slot * (kClRows * 64) + lane * 64), P.addend + ((size_t)t * N + row0 + lane) * Hd + 16 * c,
+                 (uint32_t)(nfeat * 4), bar(CB_AD_FULL0 + slot));
+    }
   } else if (active && (warp & 3) == 0) {
     // ================================ epilogue warps ================================
     const int e = warp >> 2;          // 0..3: which 4 of this CTA's 16 features (2 of its 8 state dimensions)
@@ -481,7 +504,6 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(con
       }
       // per-step inputs: requested after the first exchange is on its way (fence.proxy.async waits for loads in flight)
       if (row_ok) {
-        if (with_obs && f0 < Hd) ldg4(ad, P.addend + (trow + row) * Hd + f0);
         if (owner) {
           if (j0 < S) {
             ldg2(ep, P.eps_prior + (trow + row) * S + j0);
@@ -534,6 +556,13 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(con
         mbar_wait(bar(CB_ACC_PQ1), ph);
         tc_fence_after();
         float vp[4], vq[4], lp[4], lq[4];
+        if (with_obs) {   // this step's addend slice has been staged by the loader warp
+          mbar_wait(bar(CB_AD_FULL0 + (t & 1)), (uint32_t)((t >> 1) & 1));
+          if (row_ok && f0 < Hd) {
+            const float4 a4 = *reinterpret_cast<const float4*>(smem + g.off_stage + (t & 1) * (kClRows * 64) + r * 64 + 16 * e);
+            ad[0] = a4.x; ad[1] = a4.y; ad[2] = a4.z; ad[3] = a4.w;
+          }
+        }
         tmem_ld4(tb + 160 + 4 * e, vp);
         tmem_ld4(tb + 176 + 4 * e, vq);
         tmem_ld4(tb + 192 + 4 * e, lp);
@@ -559,6 +588,7 @@ __global__ void __launch_bounds__(kClThreads, 1) rssm_cluster_observe_kernel(con
         send(smem_u32(h1) + (uint32_t)c * kClSlab, kClSlab, nS8, CB_IN_PQ2);
         if (with_obs) send(smem_u32(h2) + (uint32_t)c * kClSlab, kClSlab, nS8, CB_IN_PQ2);
         if (owner && e == 0 && lane == 0) mbar_arrive(bar(CB_IN_PQ2));
+        if (with_obs && e == 0 && lane == 0) mbar_arrive(bar(CB_AD_FREE0 + (t & 1)));   // (after epi_sync: all four warps have read it)
       }
       // ---- PQ2: Gaussian heads (owners of state dimensions), next step's state and action -> SA of every CTA
       {
