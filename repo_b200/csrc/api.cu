@@ -1256,7 +1256,9 @@ int conv_gemm_impl(const void* input_, const float* w_mat, int w_ld, int w_col0,
   P.stage_bytes = conv_stage_bytes(P.kc16, P.NP);
   const int n_ent = conv_table_entries(cm, P.k16, P.in_hl);
   if (n_ent > 2048) return fail(-1, "conv: K = %d needs %d gather-table entries (max 2048)", K, n_ent);
-  const size_t fixed = 128 + 4 * 128 * sizeof(ConvRowInfo) + kCvColEntries * sizeof(ConvCol) + (size_t)n_ent * sizeof(ConvTap);
+  P.bias_smem = (P.n_tiles * P.NP <= 4096) ? 1 : 0;
+  const size_t fixed = 128 + 4 * 128 * sizeof(ConvRowInfo) + kCvColEntries * sizeof(ConvCol) + (size_t)n_ent * sizeof(ConvTap) +
+                       (P.bias_smem ? (size_t)P.n_tiles * P.NP * sizeof(float) + 32 : 0);
   P.n_stages = std::min<int>(kCvMaxStages, (int)((227 * 1024 - fixed) / P.stage_bytes));
   if (P.n_stages < 2) return fail(-1, "conv: ring does not fit shared memory");
   const size_t smem = (size_t)P.n_stages * P.stage_bytes + fixed;

@@ -57,6 +57,9 @@ struct ConvParams {
   int n_total, NP, n_tiles;  // output features, features per tile (multiple of 16, <= 256), tiles
   int cout;                // channels per output pixel (n_total, or n_total/4 when cm.shuffle)
   int kc16, n_stages, stage_bytes;  // ring geometry: k16 slabs per stage, stages, bytes per stage
+  // biases staged in shared memory by the prologue (n_tiles * NP floats behind the tap table): the epilogue's per-group bias
+  // read was a global load on the critical path of every 16-column group — 9 of the 16 us a one-tile launch takes
+  int bias_smem;
 };
 
 // A operand (gathered rows) inside a ring stage: k-group g (8 fp16 of every row) starts at g * kCvALbo; the 32-byte
@@ -124,11 +127,14 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
   ConvRowInfo* row_info = reinterpret_cast<ConvRowInfo*>(bars + 16);   // 4 gather groups x 128 rows
   ConvCol* cols = reinterpret_cast<ConvCol*>(row_info + 4 * 128);      // scalar-store epilogue: one entry per feature
   ConvTap* table = reinterpret_cast<ConvTap*>(cols + kCvColEntries);
+  float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(table + conv_table_entries(P.cm, P.k16, P.in_hl)) + 15) & ~uintptr_t(15));
+  const float* bias_src = P.bias_smem ? bias_s : P.bias;   // what the epilogue reads
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 4);
   const uint32_t bar_accf = smem_u32(bars + 8), bar_acce = smem_u32(bars + 10);
   const ConvMap& cm = P.cm;
+  const uint64_t t_entry = global_timer_ns();   // (profiling: CTA 0 reports entry / prologue / MMA / epilogue / exit times)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kCvMaxStages; ++i) {
@@ -146,6 +152,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
     tmem_relinquish();
   }
   conv_build_table(table, cm, P.k16, P.in_hl, threadIdx.x, kCvThreads);
+  if (P.bias_smem)
+    for (int n = threadIdx.x; n < P.n_tiles * P.NP; n += kCvThreads) bias_s[n] = P.bias[n];
   const bool have_cols = P.n_tiles == 1 && P.n_total <= kCvColEntries;
   if (have_cols) {
     for (int n = threadIdx.x; n < P.n_total; n += kCvThreads) {
@@ -166,6 +174,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) { P.dbg[10] = (long long)t_entry; P.dbg[11] = (long long)global_timer_ns(); }
 
   const int row_tiles = (P.n_rows + 127) / 128;
   const int n_items = row_tiles * P.n_tiles;
@@ -241,7 +250,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
       if (elect_one()) umma_commit(bar_accf + 8 * buf);
       __syncwarp();
     }
-    if (P.dbg && blockIdx.x == 0 && lane == 0) { P.dbg[0] = m_acc; P.dbg[1] = m_full; P.dbg[2] = m_issue; P.dbg[7] = n_chunks; P.dbg[8] = item; }
+    if (P.dbg && blockIdx.x == 0 && lane == 0) { P.dbg[0] = m_acc; P.dbg[1] = m_full; P.dbg[2] = m_issue; P.dbg[7] = n_chunks; P.dbg[8] = item; P.dbg[12] = (long long)global_timer_ns(); }
   } else if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // spare warps of warpgroup 0: the dec is warpgroup-wide
   } else if (warp >= 8) {
@@ -426,11 +435,11 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
             const size_t od = (((size_t)fr * cm.Ho + yy) * cm.Wo + xx) * cout + co;
             const size_t o = P.out_ld ? (size_t)fr * P.out_ld + co : od;          // plain GEMM into a column window
             const size_t om = P.mask_ld ? (size_t)fr * P.mask_ld + co : od;
-            const float4* bp = reinterpret_cast<const float4*>(P.bias + nb);
+            const float4* bp = reinterpret_cast<const float4*>(bias_src + nb);
             float y[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 bb = __ldg(bp + j);
+              const float4 bb = bp[j];
               y[4 * j] = fmaf(v[4 * j], unscale, bb.x); y[4 * j + 1] = fmaf(v[4 * j + 1], unscale, bb.y);
               y[4 * j + 2] = fmaf(v[4 * j + 2], unscale, bb.z); y[4 * j + 3] = fmaf(v[4 * j + 3], unscale, bb.w);
             }
@@ -531,7 +540,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
                 const size_t od = cm.out_nchw ? (((size_t)fr * cout + co) * cm.Ho + yy) * cm.Wo + xx
                                               : (((size_t)fr * cm.Ho + yy) * cm.Wo + xx) * cout + co;
                 const size_t o = P.out_ld ? (size_t)fr * P.out_ld + co : od;
-                float y = fmaf(v[i], unscale, __ldg(P.bias + n));
+                float y = fmaf(v[i], unscale, bias_src[n]);
                 if (P.act_elu) y = act_t<ACT_ELU>(y);
                 else if (cm.relu) y = fmaxf(y, 0.f);
                 if (P.relu_mask) {
@@ -547,11 +556,13 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_rows_kernel(const __grid_c
       tc_fence_before();
       mbar_arrive(bar_acce + 8 * buf);
     }
+    if (P.dbg && blockIdx.x == 0 && r == 0) P.dbg[13] = (long long)global_timer_ns();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) P.dbg[14] = (long long)global_timer_ns();
 }
 
 
